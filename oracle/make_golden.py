@@ -1,0 +1,201 @@
+"""TEST INFRASTRUCTURE ONLY -- generate tests/golden/*.pt by RUNNING THE REFERENCE.
+
+Run in the build container (needs /root/reference):
+
+    python -m oracle.make_golden
+
+Each fixture stores seeded inputs, the weights (reference state-dict key
+names) and the outputs the *unmodified reference modules* produced on CPU in
+fp32.  ``tests/test_golden.py`` checks the oracle against them everywhere
+(including the GPU box, where /root/reference does not exist) and the GPU
+tests check the CUDA path against them.  Fixtures are small on purpose.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import torch
+
+from oracle import refshim
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+TINY_LIBRA = dict(hidden_size=64, intermediate_size=176, num_hidden_layers=2, num_attention_heads=4,
+                  vocab_size=320, contiguous_signal_size=32, max_position_embeddings=2048)
+ATTN_HD128 = dict(hidden_size=256, intermediate_size=352, num_hidden_layers=1, num_attention_heads=2,
+                  vocab_size=320, contiguous_signal_size=32, max_position_embeddings=2048)
+TINY_CLIP = dict(hidden_size=128, intermediate_size=256, num_hidden_layers=3, num_attention_heads=2,
+                 image_size=56, patch_size=14, num_channels=3)
+
+
+def randomize_like_bench(model, seed: int):
+    """randomise weight_B (bridges are zero-init) and norm weights so
+    routing, low-rank and bridge paths are numerically exercised."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n.endswith("weight_B"):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.05)
+            elif "norm" in n and p.ndim == 1:
+                p.copy_(1 + 0.1 * torch.randn(p.shape, generator=g))
+
+
+def make_libra_inputs(V: int, S: int, B: int, n_text: int, pad_last: int, seed: int, images_per_sample=1):
+    g = torch.Generator().manual_seed(seed)
+    T = 1 + 578 * images_per_sample + n_text
+    ids = torch.randint(3, V, (B, T), generator=g)
+    ids[:, 0] = 1
+    input_ids = ids[None].repeat(2, 1, 1)
+    vi = torch.full((B, T), 578)
+    spans = []
+    for b in range(B):
+        sp = []
+        pos = 1 + 2 * b
+        for _ in range(images_per_sample):
+            input_ids[:, b, pos] = V + 512
+            input_ids[:, b, pos + 577] = V + 513
+            input_ids[:, b, pos + 1:pos + 577] = torch.randint(0, 512, (2, 576), generator=g) + V
+            vi[b, pos:pos + 578] = torch.arange(578)
+            if pos + 578 < T:
+                sp.append([pos + 578, pos + 579])
+            pos += 578 + 3
+        spans.append(sp)
+    am = torch.ones(B, T, dtype=torch.long)
+    if pad_last:
+        am[-1, -pad_last:] = 0
+    sig = torch.randn(B, T, S, generator=g)
+    sig[(vi >= 578) | (vi == 0) | (vi == 577)] = 0
+    labels = input_ids.clone()
+    labels[:, am == 0] = -100
+    labels[labels == V + 512] = -100
+    labels[labels == 1] = -100
+    for b, sp in enumerate(spans):
+        for s, e in sp:
+            labels[:, b, s:e] = -100
+    return dict(input_ids=input_ids, attention_mask=am, vision_indices=vi, contiguous_signal=sig, labels=labels)
+
+
+def golden_decoder(m):
+    torch.manual_seed(0)
+    cfg = m.configuration_libra.LibraConfig(**TINY_LIBRA)
+    model = m.modeling_libra.LibraForCausalLM(cfg).eval()
+    randomize_like_bench(model, 11)
+    inp = make_libra_inputs(cfg.vocab_size, cfg.contiguous_signal_size, B=2, n_text=40, pad_last=7, seed=5)
+    out = model(input_ids=inp["input_ids"], attention_mask=inp["attention_mask"],
+                vision_indices=inp["vision_indices"], contiguous_signal=inp["contiguous_signal"],
+                labels=inp["labels"], use_cache=False, output_hidden_states=True)
+    out.loss.backward()
+    logits = out.logits.detach()
+    sel = torch.tensor([0, 1, 2, 3, 300, 577, 578, 579, 580, 581, 600, logits.shape[2] - 8, logits.shape[2] - 1])
+    grads = {n: p.grad.clone() for n, p in model.named_parameters()
+             if p.grad is not None and (("layers.1" in n and ("bridge" in n or "vision_q_proj" in n or n.endswith("q_proj.weight")
+                                                               or "layernorm" in n or "down_proj" in n))
+                                        or n in ("model.vision_signal_norm.weight", "vision_lm_head.heads.1.weight"))}
+    keep = {k: v.clone() for k, v in model.state_dict().items()
+            if "placeholder" not in k and "inv_freq" not in k}
+    return dict(config=TINY_LIBRA, state_dict=keep, inputs=inp, loss=out.loss.detach(),
+                logits_positions=sel, logits_at=logits[:, :, sel].clone(),
+                logits_lse=torch.logsumexp(logits, dim=-1),
+                hidden_after_layer0=out.hidden_states[1].detach().clone(),
+                last_hidden=out.hidden_states[-1].detach().clone(), grads=grads)
+
+
+def golden_attention(m):
+    """One LibraAttention module at the production head_dim (128), 2 heads."""
+    torch.manual_seed(1)
+    cfg = m.configuration_libra.LibraConfig(**ATTN_HD128)
+    attn = m.modeling_libra.LibraAttention(cfg).eval()
+    g = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        for n, p in attn.named_parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * (0.05 if n.endswith("weight_B") or "weight_A" in n else 0.06))
+    B, T = 2, 192
+    x = torch.randn(B, T, cfg.hidden_size, generator=g)
+    flag = torch.zeros(B, T, dtype=torch.bool)
+    flag[0, 1:120] = True
+    flag[1, 30:150] = True
+    am = torch.ones(B, T, dtype=torch.long)
+    am[1, -20:] = 0
+    mask = m.modeling_llama._make_causal_mask((B, T), x.dtype, x.device) + m.modeling_llama._expand_mask(am, x.dtype, T)
+    pos = torch.arange(T)[None].expand(B, T)
+    x.requires_grad_(True)
+    y, _, _ = attn(hidden_states=x, attention_mask=mask, position_ids=pos, vision_flag=flag)
+    gy = torch.randn(y.shape, generator=g)
+    (y * gy).sum().backward()
+    sd = {"self_attn." + k: v.detach().clone() for k, v in attn.state_dict().items() if "inv_freq" not in k}
+    return dict(config=ATTN_HD128, state_dict=sd, x=x.detach(), flag=flag, attention_mask=am, grad_out=gy,
+                out=y.detach(), grad_x=x.grad.clone(),
+                grad_kbridge_B=attn.vision_k_bridge_on_language.weight_B.grad.clone(),
+                grad_vbridge_A=attn.vision_v_bridge_on_vision.weight_A.grad.clone(),
+                grad_vq_A=attn.vision_q_proj.weight_A.grad.clone())
+
+
+def golden_clip(m):
+    torch.manual_seed(2)
+    cfg = m.configuration_clip.CLIPVisionConfig(**TINY_CLIP)
+    model = m.modeling_clip.CLIPVisionModel(cfg).eval()
+    g = torch.Generator().manual_seed(7)
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if "norm" in n or n.endswith("bias"):
+                p.copy_((1.0 if n.endswith("weight") else 0.0) + 0.1 * torch.randn(p.shape, generator=g))
+    px = torch.rand(3, 3, 56, 56, generator=g)
+    mean = torch.tensor([0.48145466, 0.4578275, 0.40821073]).view(1, 3, 1, 1)
+    std = torch.tensor([0.26862954, 0.26130258, 0.27577711]).view(1, 3, 1, 1)
+    px = (px - mean) / std
+    with torch.no_grad():
+        out = model(px, output_hidden_states=True)
+    return dict(config=TINY_CLIP, state_dict={k: v.clone() for k, v in model.state_dict().items() if "position_ids" not in k},
+                pixel_values=px, hidden_states=[h.clone() for h in out.hidden_states])
+
+
+def golden_lfq(m):
+    lfq = m.lfq.LFQ(dim=18, codebook_size=512, num_codebooks=2).eval()
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(2, 18, 24, 24, generator=g)
+    x[0, :, 0, 0] = 0.0                        # exact zeros quantise to bit 0 (x > 0 is strict)
+    x[0, 3, 1, 1] = -0.0
+    with torch.no_grad():
+        quant, _, idx = lfq(x)
+        codes = lfq.indices_to_codes(idx)
+    lfq_p = m.lfq.LFQ(dim=32, codebook_size=512, num_codebooks=2).eval()
+    xp = torch.randn(2, 32, 6, 6, generator=g)
+    with torch.no_grad():
+        _, _, idx_p = lfq_p(xp)
+    return dict(x=x, indices=idx, quantized=quant, codes=codes,
+                xp=xp, proj_w=lfq_p.project_in.weight.detach().clone(), proj_b=lfq_p.project_in.bias.detach().clone(),
+                indices_p=idx_p)
+
+
+def golden_norms_rope(m):
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(37, 256, generator=g) * 3
+    w = 1 + 0.1 * torch.randn(256, generator=g)
+    norm = m.modeling_llama.LlamaRMSNorm(256, eps=1e-6)
+    with torch.no_grad():
+        norm.weight.copy_(w)
+    y32 = norm(x).detach()
+    ybf = norm(x.bfloat16()).detach()
+    rot = m.modeling_llama.LlamaRotaryEmbedding(128, max_position_embeddings=2048)
+    q = torch.randn(1, 2, 40, 128, generator=g)
+    k = torch.randn(1, 2, 40, 128, generator=g)
+    cos, sin = rot(q, seq_len=40)
+    pos = torch.arange(40)[None]
+    qe, ke = m.modeling_libra.apply_rotary_pos_emb(q, [k, k * 2], cos, sin, pos)
+    return dict(x=x, w=w, y32=y32, ybf=ybf, q=q, k=k, q_rot=qe, k_rot=ke[0], k2_rot=ke[1])
+
+
+def main():
+    m = refshim.import_reference()
+    os.makedirs(OUT, exist_ok=True)
+    for name, fn in (("decoder_tiny", golden_decoder), ("attention_hd128", golden_attention),
+                     ("clip_tiny", golden_clip), ("lfq", golden_lfq), ("norms_rope", golden_norms_rope)):
+        obj = fn(m)
+        path = os.path.join(OUT, name + ".pt")
+        torch.save(obj, path)
+        print(f"{name}: {os.path.getsize(path) / 1e6:.2f} MB")
+
+
+if __name__ == "__main__":
+    sys.exit(main())

