@@ -1,0 +1,203 @@
+/* libra_b200 -- C ABI of the sm_100a kernel library (liblibra_b200.so).
+ *
+ * The reference (YifanXu74/Libra) is pure Python/PyTorch: it has no native
+ * interface to mirror.  Each entry point below replaces the PyTorch-eager code
+ * of one reference function on the training hot path (file:line cited per
+ * function, paths relative to the reference root); libra_b200/ops.py binds
+ * them with ctypes and INTEGRATION.md shows the binding a reference maintainer
+ * would add.
+ *
+ * Conventions
+ *  - plain C types and raw device pointers only; the caller (PyTorch) owns all
+ *    memory including workspaces;
+ *  - every function only enqueues work on `stream` (a cudaStream_t passed as
+ *    void*): it never synchronises, allocates device memory or throws;
+ *  - returns LB_OK (0) or a negative LB_E* code; the message for the calling
+ *    thread is available through lb_last_error();
+ *  - tensors are row-major and dense unless a leading dimension is given;
+ *    activations and weights are bf16 (uint16 storage), statistics fp32;
+ *  - "sorted rows": the decoder keeps its [N, C] activations permuted so that
+ *    language tokens come first and vision tokens second (the reference's
+ *    modality routing, modeling_libra.py:111-147, then needs no gather/scatter);
+ *    `flag[r]` (uint8) is 1 for a vision row;
+ *  - device: the current CUDA device of the calling thread, which must be
+ *    compute capability 10.x (no fallback path).
+ */
+#ifndef LIBRA_B200_H
+#define LIBRA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LB_OK 0
+#define LB_EINVAL (-1)   /* bad shape / argument */
+#define LB_EALIGN (-2)   /* pointer or leading dimension not aligned as required */
+#define LB_EDTYPE (-3)   /* unsupported dtype code */
+#define LB_ELAUNCH (-4)  /* CUDA launch / runtime failure (text in lb_last_error) */
+#define LB_EARCH (-5)    /* device is not sm_100 */
+#define LB_EDRIVER (-6)  /* driver entry point (tensor-map encode) unavailable */
+
+#define LB_DT_BF16 0
+#define LB_DT_F32 1
+
+int lb_version(void);
+/* copies the calling thread's last error text (NUL terminated) into buf */
+int lb_last_error(char* buf, int n);
+/* LB_OK when the current device can run this library */
+int lb_device_check(void);
+int lb_sm_count(void);
+
+/* ---- A13 LlamaRMSNorm routed by modality --------------------------------
+ * libra/models/llama/modeling_llama.py:127-132, routed at
+ * libra/models/libra/modeling_libra.py:463,479,817 (and :559,642 un-routed).
+ * y = w[flag] * x * rsqrt(mean(x^2)+eps), fp32 internally, one cast.
+ * flag may be NULL (every row uses w_lang).  rstd [rows] fp32 is saved for bwd. */
+int lb_rmsnorm_fwd(const void* x, const void* w_lang, const void* w_vis, const uint8_t* flag, void* y, float* rstd,
+                   int64_t rows, int cols, float eps, void* stream);
+/* dx; dw_lang/dw_vis [cols] fp32 are ACCUMULATED into (caller zeroes).  partial is a
+ * workspace of lb_rmsnorm_bwd_workspace(rows, cols) bytes.  residual_grad
+ * (optional, may be NULL) is added to dx (fuses the residual branch). */
+int64_t lb_rmsnorm_bwd_workspace(int64_t rows, int cols);
+int lb_rmsnorm_bwd(const void* dy, const void* x, const void* w_lang, const void* w_vis, const uint8_t* flag,
+                   const float* rstd, const void* residual_grad, void* dx, float* dw_lang, float* dw_vis, void* partial,
+                   int64_t rows, int cols, void* stream);
+
+/* ---- A1/A4 nn.LayerNorm (CLIP) ------------------------------------------
+ * libra/models/clip/modeling_clip.py:386-388,866 (eps from config, affine). */
+int lb_layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd, int64_t rows,
+                     int cols, float eps, void* stream);
+int64_t lb_layernorm_bwd_workspace(int64_t rows, int cols);
+int lb_layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, void* dx,
+                     float* dw, float* db, void* partial, int64_t rows, int cols, void* stream);
+
+/* ---- A15 SwiGLU product  silu(gate) * up ---------------------------------
+ * libra/models/libra/modeling_libra.py:232-233.  ld_* are row pitches in elements. */
+int lb_swiglu_fwd(const void* gate, const void* up, void* out, int64_t rows, int cols, int64_t ld_gate, int64_t ld_up,
+                  int64_t ld_out, void* stream);
+int lb_swiglu_bwd(const void* dout, const void* gate, const void* up, void* dgate, void* dup, int64_t rows, int cols,
+                  int64_t ld_dout, int64_t ld_gate, int64_t ld_up, int64_t ld_dgate, int64_t ld_dup, void* stream);
+
+/* ---- A3 quick_gelu with bias:  y = g(x+b), g(z) = z*sigmoid(1.702 z) ------
+ * libra/models/clip/modeling_clip.py:374-378 (fc1 bias + activation). bias may be NULL. */
+int lb_bias_quick_gelu_fwd(const void* x, const void* bias, void* y, int64_t rows, int cols, void* stream);
+/* dx = dy * g'(x+b) */
+int lb_bias_quick_gelu_bwd(const void* dy, const void* x, const void* bias, void* dx, int64_t rows, int cols,
+                           void* stream);
+
+/* ---- row permutation (sorted <-> original token order) --------------------
+ * dst[r] = src[index[r]] for r in [0,rows); rows of `cols` bf16. */
+int lb_gather_rows(const void* src, const int32_t* index, void* dst, int64_t rows, int cols, void* stream);
+
+/* ---- A17 embeddings ------------------------------------------------------
+ * libra/models/libra/modeling_libra.py:625-661.  Writes, for sorted row r:
+ *  language: out[r, :] = embed[ids0[r]]                         (cols = hidden)
+ *  vision  : cat[i, :] = [vemb0[ids0[i]] | vemb1[ids1[i]] | signal[signal_row[i]]]  (2*half + signal cols)
+ * ids are int64 per (sorted) row, vision ids already offset-subtracted by the caller; signal is the
+ * [B*T, signal_cols] tensor in original token order (NULL = zeros, modeling_libra.py:647-653) and
+ * signal_row[i] the original token index of vision row i (NULL = identity). */
+int lb_embed_lang_fwd(const int64_t* ids, const void* table, void* out, int64_t rows, int cols, void* stream);
+int lb_embed_vision_cat_fwd(const int64_t* ids0, const int64_t* ids1, const void* table0, const void* table1,
+                            const void* signal, const int32_t* signal_row, void* out, int64_t rows, int half,
+                            int signal_cols, void* stream);
+/* scatter-add of row gradients into an fp32 table gradient: dtable[ids[r], :] += dy[r, col0:col0+cols] */
+int lb_embed_bwd(const int64_t* ids, const void* dy, int64_t ld_dy, int col0, float* dtable, int64_t rows, int cols,
+                 void* stream);
+
+/* ---- A7 LFQ sign-quantise + index pack (bit exact) ------------------------
+ * libra/models/libra/taming/modules/quantization/lookup_free_quantization.py:185-208,
+ * ImageTokenizer.encode offsets/BOI/EOI libra/models/libra/image_tokenizer.py:75-95.
+ * h: [n_img*tokens, num_codebooks*bits] (bf16 or fp32 by dtype); writes
+ * ids[q, img, 1+t] = offset + sum_d [h>0] 2^(bits-1-d), ids[q,img,0]=boi, ids[q,img,tokens+1]=eoi
+ * into an int64 [num_codebooks, n_img, tokens+2] tensor. */
+int lb_lfq_pack(const void* h, int dtype, int64_t n_img, int tokens, int num_codebooks, int bits, int64_t offset,
+                int64_t boi, int64_t eoi, int64_t* ids, void* stream);
+/* inverse: codes[..., q*bits+d] = +-1 (bf16/fp32) from ids (without BOI/EOI, offset removed): indices_to_codes :129-158 */
+int lb_lfq_unpack(const int64_t* idx, int64_t n, int num_codebooks, int bits, void* codes, int dtype, void* stream);
+
+/* ---- A12 + A10(bridge operands) attention prologue ------------------------
+ * libra/models/libra/modeling_libra.py:318-340 (bridge add, RoPE on q and both key variants),
+ * :282-286 (value variants).  Inputs in sorted rows; outputs in ORIGINAL token order [B*T, H*D]:
+ *   Q    = rope(q)
+ *   Kfv  = rope(k + [lang j] kb)   Vfv = v + [lang j] vb      (what VISION queries see)
+ *   Kfl  = rope(k + [vis  j] kb)   Vfl = v + [vis  j] vb      (what LANGUAGE queries see)
+ * with kb_j = tk_j . Bk[m_j]^T, vb_j = tv_j . Bv[m_j]^T (rank-R bridge, R <= 16).
+ * sorted_of[bt] = sorted row of original token bt; pos[bt] = rotary position;
+ * cos/sin: fp32 tables [n_pos, D/2].  flag_sorted[r] = 1 for vision rows. */
+int lb_attn_prep_fwd(const void* q, const void* k, const void* v, const void* tk, const void* tv, const void* Bk_lang,
+                     const void* Bk_vis, const void* Bv_lang, const void* Bv_vis, const uint8_t* flag_sorted,
+                     const int32_t* sorted_of, const int32_t* pos, const float* cos_t, const float* sin_t, void* Q,
+                     void* Kfv, void* Kfl, void* Vfv, void* Vfl, int64_t n_tokens, int heads, int head_dim, int rank,
+                     void* stream);
+/* adjoint: from dQ,dKfv,dKfl,dVfv,dVfl (original order) to dq,dk,dv,dkb,dvb (sorted rows, [N,H*D]) */
+int lb_attn_prep_bwd(const void* dQ, const void* dKfv, const void* dKfl, const void* dVfv, const void* dVfl,
+                     const uint8_t* flag_sorted, const int32_t* sorted_of, const int32_t* pos, const float* cos_t,
+                     const float* sin_t, void* dq, void* dk, void* dv, void* dkb, void* dvb, int64_t n_tokens, int heads,
+                     int head_dim, void* stream);
+
+/* ---- A10 bridge attention core (tcgen05 flash attention) ------------------
+ * libra/models/libra/modeling_libra.py:363-397 + attn_with_bridge :267-296; replaces the disabled
+ * utils/llama_flash_attn_monkey_patch.py:75-178.  Also A2 (CLIPAttention core, modeling_clip.py:309-349)
+ * with causal=0, one variant, head_dim 64.
+ *
+ * Q,K*,V*: [B*T, H*D] bf16, original token order.  work: int32 [n_work,4] = {batch, q_tile, variant, 0}
+ * (variant 0: rows with qflag==0 attend K0/V0; variant 1: rows with qflag==1 attend K1/V1; a 128-row
+ * q tile that holds both modalities appears twice).  qflag[B*T] (may be NULL when only variant 0 exists).
+ * kv_start/kv_end [B]: valid key range per sample (padding), NULL = [0,T).
+ * out_row[B*T] (may be NULL): destination row of each token in O (sorted-row scatter).
+ * lse [B,H,T] fp32 (natural log, of the scaled scores).  scale multiplies Q.K^T. */
+int lb_attn_fwd(const void* Q, const void* K0, const void* V0, const void* K1, const void* V1, const uint8_t* qflag,
+                const int32_t* work, int n_work, const int32_t* kv_start, const int32_t* kv_end,
+                const int32_t* out_row, void* O, float* lse, int batch, int seqlen, int heads, int head_dim, int causal,
+                float scale, void* stream);
+
+/* delta[b,h,t] = sum_d dO*O per head, plus dO gathered to original order.
+ * O_rows/dO_rows are indexed by row_of[bt] (NULL = identity). */
+int lb_attn_bwd_prepare(const void* O, const void* dO, const int32_t* row_of, void* dO_orig, float* delta, int batch,
+                        int seqlen, int heads, int head_dim, void* stream);
+
+/* dQ (original order).  Same work list semantics as forward. */
+int lb_attn_bwd_dq(const void* Q, const void* K0, const void* V0, const void* K1, const void* V1, const void* dO,
+                   const float* lse, const float* delta, const uint8_t* qflag, const int32_t* work, int n_work,
+                   const int32_t* kv_start, const int32_t* kv_end, void* dQ, int batch, int seqlen, int heads,
+                   int head_dim, int causal, float scale, void* stream);
+/* dK0,dV0 (gradient w.r.t. the variant-0 operands, from qflag==0 query rows) and dK1,dV1.
+ * work_kv: int32 [n_work,4] = {batch, kv_tile, variant, first_q_tile}. */
+int lb_attn_bwd_dkv(const void* Q, const void* K0, const void* V0, const void* K1, const void* V1, const void* dO,
+                    const float* lse, const float* delta, const uint8_t* qflag, const int32_t* work_kv, int n_work,
+                    const int32_t* kv_start, const int32_t* kv_end, void* dK0, void* dV0, void* dK1, void* dV1, int batch,
+                    int seqlen, int heads, int head_dim, int causal, float scale, void* stream);
+
+/* ---- tcgen05 GEMM ---------------------------------------------------------
+ * C[M,N] = op(A) . op(B) (+ C when accumulate), bf16 inputs, fp32 accumulation in TMEM.
+ *  trans_a = 0: A stored [M,K] (K contiguous);  1: A stored [K,M]
+ *  trans_b = 0: B stored [N,K] (K contiguous, the nn.Linear weight layout);  1: B stored [K,N]
+ * out_dtype LB_DT_BF16 / LB_DT_F32.  bias (bf16 [N], may be NULL) is added before `act`
+ * (0 none, 1 quick_gelu).  Leading dimensions in elements, multiples of 8. */
+int lb_gemm_bf16(const void* A, const void* B, void* C, const void* bias, int64_t M, int64_t N, int64_t K, int64_t lda,
+                 int64_t ldb, int64_t ldc, int trans_a, int trans_b, int out_dtype, int accumulate, int act,
+                 void* stream);
+
+/* ---- A1 patch embedding (im2col-free) --------------------------------------
+ * libra/models/clip/modeling_clip.py:193-228.  pixels [B,3,S,S] bf16, weight [C, 3*P*P] bf16 (conv weight
+ * flattened), class_emb [C], pos_emb [(S/P)^2+1, C]; writes emb [B, (S/P)^2+1, C] = cat(cls, conv) + pos. */
+int lb_patch_embed_fwd(const void* pixels, const void* weight, const void* class_emb, const void* pos_emb, void* emb,
+                       int batch, int image_size, int patch, int channels_out, void* stream);
+
+/* ---- A18 routed heads: fused cross-entropy over a logits block -------------
+ * libra/models/libra/modeling_libra.py:1159-1174 restricted to the finite vocabulary range of the row's modality
+ * (the -inf placeholders of :1020-1052 contribute exp(-inf)=0).  logits [rows, vocab] bf16 (ld elements),
+ * labels int64 (already shifted; -100 = ignore; label index relative to this block's vocabulary range).
+ * Writes per-row loss (fp32, 0 where ignored) and overwrites logits with d(loss_sum)/dlogits * grad_scale. */
+int lb_cross_entropy_fwd_bwd(void* logits, int64_t ld, const int64_t* labels, float* row_loss, int64_t rows, int vocab,
+                             float grad_scale, void* stream);
+
+/* ---- diagnostics: single-tile tcgen05 probes (tests/test_umma_probe.py) ---- */
+int lb_probe_umma(int mode, const void* A, const void* B, float* D, int K, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIBRA_B200_H */

@@ -1,0 +1,105 @@
+"""ctypes binding of liblibra_b200.so (the C ABI declared in include/libra_b200.h).
+
+The library is the product's only compute path: if it is missing or the device is not
+sm_100 every op raises -- there is no eager/CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+
+import torch  # noqa: F401  (loads libcudart.so.12 that the library links against)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liblibra_b200.so")
+
+P, I, L, F = c_void_p, c_int, c_int64, c_float
+
+# name -> (restype, argtypes); mirrors include/libra_b200.h one to one
+SIGNATURES = {
+    "lb_version": (I, []),
+    "lb_last_error": (I, [c_char_p, I]),
+    "lb_device_check": (I, []),
+    "lb_sm_count": (I, []),
+    "lb_rmsnorm_fwd": (I, [P, P, P, P, P, P, L, I, F, P]),
+    "lb_rmsnorm_bwd_workspace": (L, [L, I]),
+    "lb_rmsnorm_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, L, I, P]),
+    "lb_layernorm_fwd": (I, [P, P, P, P, P, P, L, I, F, P]),
+    "lb_layernorm_bwd_workspace": (L, [L, I]),
+    "lb_layernorm_bwd": (I, [P, P, P, P, P, P, P, P, P, L, I, P]),
+    "lb_swiglu_fwd": (I, [P, P, P, L, I, L, L, L, P]),
+    "lb_swiglu_bwd": (I, [P, P, P, P, P, L, I, L, L, L, L, L, P]),
+    "lb_bias_quick_gelu_fwd": (I, [P, P, P, L, I, P]),
+    "lb_bias_quick_gelu_bwd": (I, [P, P, P, P, L, I, P]),
+    "lb_gather_rows": (I, [P, P, P, L, I, P]),
+    "lb_embed_lang_fwd": (I, [P, P, P, L, I, P]),
+    "lb_embed_vision_cat_fwd": (I, [P, P, P, P, P, P, P, L, I, I, P]),
+    "lb_embed_bwd": (I, [P, P, L, I, P, L, I, P]),
+    "lb_lfq_pack": (I, [P, I, L, I, I, I, L, L, L, P, P]),
+    "lb_lfq_unpack": (I, [P, L, I, I, P, I, P]),
+    "lb_attn_prep_fwd": (I, [P] * 19 + [L, I, I, I, P]),
+    "lb_attn_prep_bwd": (I, [P] * 15 + [L, I, I, P]),
+    "lb_attn_fwd": (I, [P, P, P, P, P, P, P, I, P, P, P, P, P, I, I, I, I, I, F, P]),
+    "lb_attn_bwd_prepare": (I, [P, P, P, P, P, I, I, I, I, P]),
+    "lb_attn_bwd_dq": (I, [P] * 10 + [I, P, P, P, I, I, I, I, I, F, P]),
+    "lb_attn_bwd_dkv": (I, [P] * 10 + [I, P, P, P, P, P, P, I, I, I, I, I, F, P]),
+    "lb_gemm_bf16": (I, [P, P, P, P, L, L, L, L, L, L, I, I, I, I, I, P]),
+    "lb_patch_embed_fwd": (I, [P, P, P, P, P, I, I, I, I, P]),
+    "lb_cross_entropy_fwd_bwd": (I, [P, L, P, P, L, I, F, P]),
+    "lb_probe_umma": (I, [I, P, P, P, I, P]),
+}
+
+_lib = None
+
+
+class LibraB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (building is the job of libra_b200.build / __graft_entry__.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LibraB200Error(
+            f"{LIB_PATH} not found: build it with `python -m libra_b200.build` "
+            "(libra_b200 has no fallback path without its CUDA library)")
+    lib = ctypes.CDLL(LIB_PATH)
+    missing = []
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            missing.append(name)
+            continue
+        fn.restype = res
+        fn.argtypes = args
+    lib._missing = missing
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    lib = load()
+    buf = ctypes.create_string_buffer(512)
+    lib.lb_last_error(buf, 512)
+    return buf.value.decode("utf-8", "replace")
+
+
+def call(name: str, *args):
+    """Invoke an int-returning entry point; raise with the library's message on failure."""
+    lib = load()
+    fn = getattr(lib, name)
+    rc = fn(*args)
+    if rc != 0:
+        raise LibraB200Error(f"{name} failed ({rc}): {last_error()}")
+    return rc
+
+
+def require_device():
+    """Fail loudly unless a CUDA sm_100 device is current."""
+    if not torch.cuda.is_available():
+        raise LibraB200Error("libra_b200 needs a CUDA sm_100 (B200) device; none is visible and there is no CPU path")
+    call("lb_device_check")

@@ -1,0 +1,429 @@
+// Bridge attention forward (A10) -- causal FlashAttention-style kernel on tcgen05 with TMEM accumulators.
+// Also serves A2 (CLIP ViT attention: non-causal, head_dim 64, single variant).
+//
+// Formulation (SURVEY A10 / modeling_libra.py:320-327,282-286): the keys/values a query row sees depend only on the
+// QUERY's modality, so the prologue (lb_attn_prep_fwd) materialises K0/V0 (seen by qflag==0 rows) and K1/V1 (seen by
+// qflag==1 rows).  A work item = (sample, 128-row q tile, variant); a tile holding both modalities is listed twice
+// and each item only writes the rows of its variant.  Every MMA operand is then a plain TMA tile: per kv tile exactly
+// one S = Q.K^T and one O += P.V, no element-wise bridge select.
+//
+// CTA = 192 threads:  warps 0-3 softmax/correction/epilogue (thread <-> query row <-> TMEM lane),
+//                     warp 4 TMA producer, warp 5 tcgen05.mma issuer (+ TMEM alloc).
+// TMEM columns: [0,128) S (fp32), P (bf16, 64 columns) aliased over it; [128,128+D) O accumulator.
+// Two CTAs per SM (<= 96 KB smem, 256 TMEM columns each): while one CTA runs its softmax the other owns the tensor pipe.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace lb {
+
+constexpr int AT_BM = 128;       // query rows per tile
+constexpr int AT_BN = 128;       // keys per tile
+constexpr int AT_THREADS = 192;
+constexpr float LOG2E = 1.4426950408889634f;
+
+struct AttnFwdParams {
+    const uint8_t* qflag;        // [B*T] or null
+    const int32_t* work;         // [n_work][4] = {b, q_tile, variant, -}
+    const int32_t* kv_start;     // [B] or null
+    const int32_t* kv_end;       // [B] or null
+    const int32_t* out_row;      // [B*T] or null
+    __nv_bfloat16* O;
+    float* lse;                  // [B,H,T]
+    int batch, seqlen, heads;
+    float scale;
+};
+
+template <int D>
+struct AttnFwdSmem {
+    static constexpr int Q_BYTES = AT_BM * D * 2;
+    static constexpr int K_BYTES = AT_BN * D * 2;
+    static constexpr int V_BYTES = AT_BN * D * 2;
+    static constexpr int BAR_OFF = Q_BYTES + K_BYTES + V_BYTES;
+    static constexpr int TOTAL = BAR_OFF + 1024 + 128;
+};
+
+// barrier indices
+enum { B_Q = 0, B_KFULL, B_KEMPTY, B_VFULL, B_VEMPTY, B_SFULL, B_PFULL, B_OREADY, B_COUNT };
+
+template <int D, bool CAUSAL>
+__global__ void __launch_bounds__(AT_THREADS, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
+                const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
+                const __grid_constant__ CUtensorMap tmV1, const AttnFwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    using S = AttnFwdSmem<D>;
+    uint8_t* sQ = smem;
+    uint8_t* sK = smem + S::Q_BYTES;
+    uint8_t* sV = sK + S::K_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
+
+    const int warp = threadIdx.x >> 5;
+    const int b = p.work[blockIdx.x * 4 + 0];
+    const int q_tile = p.work[blockIdx.x * 4 + 1];
+    const int variant = p.work[blockIdx.x * 4 + 2];
+    const int h = blockIdx.y;
+    const int T = p.seqlen;
+    const int q0 = q_tile * AT_BM;
+    const int kvs = p.kv_start ? p.kv_start[b] : 0;
+    const int kve = p.kv_end ? p.kv_end[b] : T;
+    // kv tile range
+    const int first_tile = kvs / AT_BN;
+    int last_tile = (kve + AT_BN - 1) / AT_BN;                      // exclusive
+    if (CAUSAL && last_tile > q_tile + 1) last_tile = q_tile + 1;
+    const int n_tiles = last_tile > first_tile ? last_tile - first_tile : 0;
+
+    constexpr uint32_t TMEM_COLS = 256;
+    constexpr uint32_t COL_S = 0, COL_O = 128;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < B_COUNT; ++i) mbar_init(bars + i, i == B_PFULL ? 128 : 1);
+        fence_barrier_init();
+    }
+    if (warp == 4 && elect_one()) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(variant ? &tmK1 : &tmK0);
+        tma_prefetch_desc(variant ? &tmV1 : &tmV0);
+    }
+    if (warp == 5) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        // ------------------------------------------------------------ TMA producer
+        if (elect_one() && n_tiles > 0) {
+            const CUtensorMap* tK = variant ? &tmK1 : &tmK0;
+            const CUtensorMap* tV = variant ? &tmV1 : &tmV0;
+            const int row_q = b * T + q0;
+            mbar_arrive_expect_tx(bars + B_Q, S::Q_BYTES);
+#pragma unroll
+            for (int c = 0; c < D / 64; ++c) tma_load_2d(sQ + c * (AT_BM * 128), &tmQ, bars + B_Q, h * D + c * 64, row_q);
+            for (int it = 0; it < n_tiles; ++it) {
+                const int row_k = b * T + (first_tile + it) * AT_BN;
+                const uint32_t ph = (uint32_t)it & 1u;
+                mbar_wait(bars + B_KEMPTY, ph ^ 1u);
+                mbar_arrive_expect_tx(bars + B_KFULL, S::K_BYTES);
+#pragma unroll
+                for (int c = 0; c < D / 64; ++c)
+                    tma_load_2d(sK + c * (AT_BN * 128), tK, bars + B_KFULL, h * D + c * 64, row_k);
+                mbar_wait(bars + B_VEMPTY, ph ^ 1u);
+                mbar_arrive_expect_tx(bars + B_VFULL, S::V_BYTES);
+#pragma unroll
+                for (int c = 0; c < D / 64; ++c)
+                    tma_load_2d(sV + c * (AT_BN * 128), tV, bars + B_VFULL, h * D + c * 64, row_k);
+            }
+        }
+    } else if (warp == 5) {
+        // ------------------------------------------------------------ MMA issuer
+        if (elect_one() && n_tiles > 0) {
+            constexpr uint32_t idesc_qk = make_idesc_bf16(AT_BM, AT_BN, 0, 0);
+            constexpr uint32_t idesc_pv = make_idesc_bf16(AT_BM, D, 0, 1);
+            const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV);
+            mbar_wait(bars + B_Q, 0);
+            for (int it = 0; it < n_tiles; ++it) {
+                const uint32_t ph = (uint32_t)it & 1u;
+                mbar_wait(bars + B_KFULL, ph);
+                tc_fence_after_sync();
+#pragma unroll
+                for (int kk = 0; kk < D / 16; ++kk) {
+                    const uint32_t off = (uint32_t)(kk / 4) * (AT_BM * 128) + (uint32_t)(kk % 4) * 32;
+                    umma_ss(tmem_base + COL_S, desc_kmajor(aQ + off), desc_kmajor(aK + off), idesc_qk, kk ? 1u : 0u);
+                }
+                tc_commit(bars + B_KEMPTY);
+                tc_commit(bars + B_SFULL);
+                mbar_wait(bars + B_PFULL, ph);
+                mbar_wait(bars + B_VFULL, ph);
+                tc_fence_after_sync();
+#pragma unroll
+                for (int kk = 0; kk < AT_BN / 16; ++kk) {
+                    // A = P (TMEM, 8 columns per 16 keys); B = V as MN-major: 16 key rows = 2048 B, d-chunks 16 KB apart
+                    umma_ts(tmem_base + COL_O, tmem_base + COL_S + kk * 8,
+                            desc_mnmajor(aV + kk * 2048, AT_BN * 128), idesc_pv, (it | kk) ? 1u : 0u);
+                }
+                tc_commit(bars + B_VEMPTY);
+                tc_commit(bars + B_OREADY);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ softmax / correction / epilogue
+        const int r = threadIdx.x;                      // query row in tile == TMEM lane
+        const int qi = q0 + r;                          // position in the sample
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const float sl2 = p.scale * LOG2E;
+        float m_used = -CUDART_INF_F, l = 0.f;
+        for (int it = 0; it < n_tiles; ++it) {
+            const uint32_t ph = (uint32_t)it & 1u;
+            const int kv0 = (first_tile + it) * AT_BN;
+            const bool need_mask = (CAUSAL && kv0 + AT_BN - 1 > q0) || (kv0 + AT_BN > kve) || (kv0 < kvs);
+            mbar_wait(bars + B_SFULL, ph);
+            tc_fence_after_sync();
+            // ---- pass 1: row max
+            float mx = -CUDART_INF_F;
+#pragma unroll 1
+            for (int c = 0; c < AT_BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(lane_addr + COL_S + c * 32, v);
+                tc_wait_ld();
+                if (need_mask) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int kj = kv0 + c * 32 + j;
+                        const bool ok = (!CAUSAL || kj <= qi) && kj < kve && kj >= kvs;
+                        mx = fmaxf(mx, ok ? __uint_as_float(v[j]) : -CUDART_INF_F);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+                }
+            }
+            const float m_new = fmaxf(m_used, mx);
+            // ---- lazy correction: rescale O only when the running max moved by more than 2^8
+            const bool grow = (m_new - m_used) * sl2 > 8.f;      // also true when m_used == -inf and m_new finite
+            if (it == 0) {
+                m_used = m_new;
+            } else if (__any_sync(0xffffffffu, grow)) {
+                mbar_wait(bars + B_OREADY, ph ^ 1u);              // PV of the previous tile has landed in O
+                tc_fence_after_sync();
+                const float alpha = grow ? ((m_used == -CUDART_INF_F) ? 0.f : exp2f((m_used - m_new) * sl2)) : 1.f;
+                if (grow) {
+                    m_used = m_new;
+                    l *= alpha;
+                }
+#pragma unroll 1
+                for (int c = 0; c < D / 32; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(lane_addr + COL_O + c * 32, v);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * alpha);
+                    tmem_st32(lane_addr + COL_O + c * 32, v);
+                }
+                tc_wait_st();
+            }
+            const float m_off = (m_used == -CUDART_INF_F) ? 0.f : m_used * sl2;
+            // ---- pass 2: P = exp2(S*sl2 - m), row sum, P (bf16) -> TMEM over S
+#pragma unroll 1
+            for (int c = 0; c < AT_BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(lane_addr + COL_S + c * 32, v);
+                tc_wait_ld();
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    float p0 = exp2f(__uint_as_float(v[j]) * sl2 - m_off);
+                    float p1 = exp2f(__uint_as_float(v[j + 1]) * sl2 - m_off);
+                    if (need_mask) {
+                        const int kj = kv0 + c * 32 + j;
+                        const bool ok0 = (!CAUSAL || kj <= qi) && kj < kve && kj >= kvs;
+                        const bool ok1 = (!CAUSAL || kj + 1 <= qi) && kj + 1 < kve && kj + 1 >= kvs;
+                        p0 = ok0 ? p0 : 0.f;
+                        p1 = ok1 ? p1 : 0.f;
+                    }
+                    l += p0 + p1;
+                    pk[j >> 1] = pack_bf16(p0, p1);
+                }
+                tmem_st16(lane_addr + COL_S + c * 16, pk);
+            }
+            tc_wait_st();
+            tc_fence_before_sync();
+            mbar_arrive(bars + B_PFULL);
+        }
+        // ---- epilogue
+        const int64_t bt = (int64_t)b * T + qi;
+        const bool row_ok = (qi < T) && (!p.qflag || (int)p.qflag[qi < T ? bt : 0] == variant);
+        if (n_tiles > 0) {
+            mbar_wait(bars + B_OREADY, (uint32_t)(n_tiles - 1) & 1u);
+            tc_fence_after_sync();
+        }
+        const float inv_l = l > 0.f ? 1.f / l : 0.f;
+        const int64_t dst = row_ok ? (p.out_row ? (int64_t)p.out_row[bt] : bt) : 0;
+        __nv_bfloat16* orow = p.O + dst * ((int64_t)p.heads * D) + (int64_t)h * D;
+#pragma unroll 1
+        for (int c = 0; c < D / 32; ++c) {
+            uint32_t v[32];
+            if (n_tiles > 0) {
+                tmem_ld32(lane_addr + COL_O + c * 32, v);
+                tc_wait_ld();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0u;
+            }
+            if (row_ok) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    uint4 o;
+                    o.x = pack_bf16(__uint_as_float(v[j + 0]) * inv_l, __uint_as_float(v[j + 1]) * inv_l);
+                    o.y = pack_bf16(__uint_as_float(v[j + 2]) * inv_l, __uint_as_float(v[j + 3]) * inv_l);
+                    o.z = pack_bf16(__uint_as_float(v[j + 4]) * inv_l, __uint_as_float(v[j + 5]) * inv_l);
+                    o.w = pack_bf16(__uint_as_float(v[j + 6]) * inv_l, __uint_as_float(v[j + 7]) * inv_l);
+                    *reinterpret_cast<uint4*>(orow + c * 32 + j) = o;
+                }
+            }
+            __syncwarp();
+        }
+        if (row_ok && p.lse) {
+            // natural-log LSE of the scaled scores; +inf marks a row with no visible key (P == 0 in backward)
+            p.lse[((int64_t)b * p.heads + h) * T + qi] = l > 0.f ? (m_used * p.scale + __logf(l)) : CUDART_INF_F;
+        }
+        tc_fence_before_sync();
+    }
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+template <int D, bool CAUSAL>
+static int launch_attn_fwd(const CUtensorMap* tm, const AttnFwdParams& p, int n_work, cudaStream_t st) {
+    using S = AttnFwdSmem<D>;
+    auto kern = attn_fwd_kernel<D, CAUSAL>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        if (e != cudaSuccess) return fail(LB_ELAUNCH, "attn_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    dim3 grid((unsigned)n_work, (unsigned)p.heads);
+    kern<<<grid, AT_THREADS, S::TOTAL, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], p);
+    return check_launch("attn_fwd");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Single-tile probes of the two tcgen05 operand forms the attention kernels rely on (tests/test_umma_probe.py):
+//   mode 0: D = A(TMEM) . B^T, B stored [N=128, K] (K-major)      mode 1: B stored [K, N=128] (MN-major)
+// A [128, K] bf16 row-major is written to TMEM by the threads exactly as the softmax writes P.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) probe_ts_kernel(const __grid_constant__ CUtensorMap tmB,
+                                                       const __nv_bfloat16* __restrict__ A, float* __restrict__ Dout,
+                                                       int K, int mode) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sB = smem;                                   // up to 128 x 128 bf16 = 32 KB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 32768);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        mbar_init(bars + 0, 1);
+        mbar_init(bars + 1, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(tmem_slot, 256);
+        tmem_relinquish();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    if (threadIdx.x == 0) {
+        mbar_arrive_expect_tx(bars + 0, (uint32_t)(128 * K * 2));
+        if (mode == 0) {
+            for (int c = 0; c < K / 64; ++c) tma_load_2d(sB + c * (128 * 128), &tmB, bars + 0, c * 64, 0);     // {64 k, 128 n}
+        } else {
+            for (int c = 0; c < 2; ++c) tma_load_2d(sB + c * (K * 128), &tmB, bars + 0, c * 64, 0);            // {64 n, K k}
+        }
+    }
+    // A row -> TMEM columns [128, 128 + K/2)
+    for (int c = 0; c < K / 32; ++c) {
+        uint32_t pk[16];
+        const uint4* src = reinterpret_cast<const uint4*>(A + (int64_t)threadIdx.x * K + c * 32);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint4 u = src[j];
+            pk[j * 4 + 0] = u.x; pk[j * 4 + 1] = u.y; pk[j * 4 + 2] = u.z; pk[j * 4 + 3] = u.w;
+        }
+        tmem_st16(lane_addr + 128 + c * 16, pk);
+    }
+    tc_wait_st();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    if (threadIdx.x == 0) {
+        mbar_wait(bars + 0, 0);
+        tc_fence_after_sync();
+        const uint32_t aB = smem_u32(sB);
+        const uint32_t idesc = make_idesc_bf16(128, 128, 0, mode ? 1 : 0);
+        for (int kk = 0; kk < K / 16; ++kk) {
+            const uint64_t bd = mode == 0 ? desc_kmajor(aB + (kk / 4) * (128 * 128) + (kk % 4) * 32)
+                                          : desc_mnmajor(aB + kk * 2048, (uint32_t)K * 128);
+            umma_ts(tmem_base, tmem_base + 128 + kk * 8, bd, idesc, kk ? 1u : 0u);
+        }
+        tc_commit(bars + 1);
+    }
+    mbar_wait(bars + 1, 0);
+    tc_fence_after_sync();
+    for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(lane_addr + c * 32, v);
+        tc_wait_ld();
+        for (int j = 0; j < 32; ++j) Dout[(int64_t)threadIdx.x * 128 + c * 32 + j] = __uint_as_float(v[j]);
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
+}  // namespace lb
+
+using namespace lb;
+
+extern "C" {
+
+int lb_attn_fwd(const void* Q, const void* K0, const void* V0, const void* K1, const void* V1, const uint8_t* qflag,
+                const int32_t* work, int n_work, const int32_t* kv_start, const int32_t* kv_end,
+                const int32_t* out_row, void* O, float* lse, int batch, int seqlen, int heads, int head_dim, int causal,
+                float scale, void* stream) {
+    LB_REQUIRE(batch > 0 && seqlen > 0 && heads > 0 && n_work >= 0, LB_EINVAL, "attn_fwd: bad shape");
+    LB_REQUIRE(head_dim == 64 || head_dim == 128, LB_EINVAL, "attn_fwd: head_dim %d (64 or 128 supported)", head_dim);
+    LB_REQUIRE(Q && K0 && V0 && O && work, LB_EINVAL, "attn_fwd: null argument");
+    LB_REQUIRE(((uintptr_t)O & 15) == 0, LB_EALIGN, "attn_fwd: O must be 16-byte aligned");
+    if (n_work == 0) return LB_OK;
+    int rc = require_sm100();
+    if (rc) return rc;
+    const uint64_t rows = (uint64_t)batch * seqlen, cols = (uint64_t)heads * head_dim;
+    CUtensorMap tm[5];
+    const void* ptrs[5] = {Q, K0, V0, K1 ? K1 : K0, V1 ? V1 : V0};
+    for (int i = 0; i < 5; ++i) {
+        rc = make_tmap_bf16_2d(&tm[i], ptrs[i], rows, cols, cols, 128, 64);
+        if (rc) return rc;
+    }
+    AttnFwdParams p;
+    p.qflag = qflag; p.work = work; p.kv_start = kv_start; p.kv_end = kv_end; p.out_row = out_row;
+    p.O = (__nv_bfloat16*)O; p.lse = lse; p.batch = batch; p.seqlen = seqlen; p.heads = heads; p.scale = scale;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (head_dim == 128) return causal ? launch_attn_fwd<128, true>(tm, p, n_work, st) : launch_attn_fwd<128, false>(tm, p, n_work, st);
+    return causal ? launch_attn_fwd<64, true>(tm, p, n_work, st) : launch_attn_fwd<64, false>(tm, p, n_work, st);
+}
+
+int lb_probe_umma(int mode, const void* A, const void* B, float* D, int K, void* stream) {
+    LB_REQUIRE((mode == 0 || mode == 1) && A && B && D && (K == 64 || K == 128), LB_EINVAL, "probe: bad arguments");
+    int rc = require_sm100();
+    if (rc) return rc;
+    CUtensorMap tmB;
+    if (mode == 0) rc = make_tmap_bf16_2d(&tmB, B, 128, (uint64_t)K, (uint64_t)K, 128, 64);
+    else           rc = make_tmap_bf16_2d(&tmB, B, (uint64_t)K, 128, 128, (uint32_t)K, 64);
+    if (rc) return rc;
+    static bool configured = false;
+    const int smem = 32768 + 1024 + 64;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(probe_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return fail(LB_ELAUNCH, "probe: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    probe_ts_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(tmB, (const __nv_bfloat16*)A, D, K, mode);
+    return check_launch("probe_umma");
+}
+
+}

@@ -1,0 +1,125 @@
+// Host-side plumbing of the C ABI: thread-local error text, device checks and
+// TMA tensor-map encoding through the driver entry point.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace lb {
+
+static thread_local char g_err[512] = {0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(LB_ELAUNCH, "%s: %s", what, cudaGetErrorString(e));
+    return LB_OK;
+}
+
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+int require_sm100() {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail(LB_ELAUNCH, "cudaGetDevice: %s", cudaGetErrorString(e));
+    int major = 0;
+    e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e != cudaSuccess) return fail(LB_ELAUNCH, "cudaDeviceGetAttribute: %s", cudaGetErrorString(e));
+    if (major != 10) return fail(LB_EARCH, "libra_b200 needs an sm_100 device (compute capability 10.x), got %d.x", major);
+    return LB_OK;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    });
+    return fn;
+}
+
+int make_tmap_bf16_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, int swizzle128) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return fail(LB_EDRIVER, "cuTensorMapEncodeTiled entry point unavailable");
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(LB_EALIGN, "TMA base pointer must be 16-byte aligned");
+    cuuint64_t gdim[5];
+    cuuint64_t gstr[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bx[i] = box[i];
+        es[i] = 1;
+        if (i > 0) {
+            gstr[i - 1] = strides_bytes[i - 1];
+            if (gstr[i - 1] % 16) return fail(LB_EALIGN, "TMA stride %d (%llu B) must be a multiple of 16", i,
+                                              (unsigned long long)gstr[i - 1]);
+        }
+    }
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(LB_EDRIVER, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return LB_OK;
+}
+
+int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                      uint32_t box_rows, uint32_t box_cols) {
+    uint64_t dims[2] = {cols, rows};
+    uint64_t strides[1] = {ld_elems * 2};
+    uint32_t box[2] = {box_cols, box_rows};
+    return make_tmap_bf16_nd(out, base, 2, dims, strides, box, 1);
+}
+
+}  // namespace lb
+
+extern "C" {
+
+int lb_version(void) { return 100; }
+
+int lb_last_error(char* buf, int n) {
+    if (!buf || n <= 0) return LB_EINVAL;
+    strncpy(buf, lb::g_err, (size_t)n - 1);
+    buf[n - 1] = 0;
+    return LB_OK;
+}
+
+int lb_device_check(void) { return lb::require_sm100(); }
+
+int lb_sm_count(void) { return lb::sm_count(); }
+
+}

@@ -1,0 +1,252 @@
+"""Raw (non-autograd) Python entry points over the C ABI.  Every function enqueues CUDA work on
+torch's current stream and returns torch tensors that own the output memory.
+
+These are the leaves; `libra_b200.functional` wraps them in torch.autograd.Function objects and
+`libra_b200.models` composes those into the reference's module interface.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+BF16 = torch.bfloat16
+DT_BF16, DT_F32 = 0, 1
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _st():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t: torch.Tensor, dtype=None, name="tensor"):
+    if not t.is_cuda:
+        raise _lib.LibraB200Error(f"{name} must be a CUDA tensor (libra_b200 has no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t
+
+
+# ------------------------------------------------------------------ norms
+def rmsnorm_fwd(x, w_lang, w_vis=None, flag=None, eps=1e-6):
+    _chk(x, BF16, "x"); _chk(w_lang, BF16, "w_lang")
+    rows, cols = x.numel() // x.shape[-1], x.shape[-1]
+    y = torch.empty_like(x)
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+    _lib.call("lb_rmsnorm_fwd", _p(x), _p(w_lang), _p(w_vis), _p(flag), _p(y), _p(rstd), rows, cols, float(eps), _st())
+    return y, rstd
+
+
+def rmsnorm_bwd(dy, x, w_lang, w_vis, flag, rstd, residual_grad=None, need_dw=True):
+    _chk(dy, BF16, "dy"); _chk(x, BF16, "x")
+    rows, cols = x.numel() // x.shape[-1], x.shape[-1]
+    dx = torch.empty_like(x)
+    ws = torch.empty(_lib.load().lb_rmsnorm_bwd_workspace(rows, cols), dtype=torch.uint8, device=x.device)
+    dwl = torch.zeros(cols, dtype=torch.float32, device=x.device) if need_dw else None
+    dwv = torch.zeros(cols, dtype=torch.float32, device=x.device) if (need_dw and w_vis is not None) else None
+    _lib.call("lb_rmsnorm_bwd", _p(dy), _p(x), _p(w_lang), _p(w_vis), _p(flag), _p(rstd), _p(residual_grad), _p(dx),
+              _p(dwl), _p(dwv), _p(ws), rows, cols, _st())
+    return dx, dwl, dwv
+
+
+def layernorm_fwd(x, w, b, eps=1e-5):
+    _chk(x, BF16, "x")
+    rows, cols = x.numel() // x.shape[-1], x.shape[-1]
+    y = torch.empty_like(x)
+    mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+    _lib.call("lb_layernorm_fwd", _p(x), _p(w), _p(b), _p(y), _p(mean), _p(rstd), rows, cols, float(eps), _st())
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, w, mean, rstd):
+    rows, cols = x.numel() // x.shape[-1], x.shape[-1]
+    dx = torch.empty_like(x)
+    ws = torch.empty(_lib.load().lb_layernorm_bwd_workspace(rows, cols), dtype=torch.uint8, device=x.device)
+    dw = torch.zeros(cols, dtype=torch.float32, device=x.device)
+    db = torch.zeros(cols, dtype=torch.float32, device=x.device)
+    _lib.call("lb_layernorm_bwd", _p(dy), _p(x), _p(w), _p(mean), _p(rstd), _p(dx), _p(dw), _p(db), _p(ws), rows, cols, _st())
+    return dx, dw, db
+
+
+# ------------------------------------------------------------ elementwise
+def swiglu_fwd(gate, up):
+    """gate/up: [rows, cols] views (last dim contiguous, row pitch arbitrary multiple of 8)."""
+    rows, cols = gate.shape
+    out = torch.empty(rows, cols, dtype=BF16, device=gate.device)
+    _lib.call("lb_swiglu_fwd", _p(gate), _p(up), _p(out), rows, cols, gate.stride(0), up.stride(0), cols, _st())
+    return out
+
+
+def swiglu_bwd(dout, gate, up, dgate=None, dup=None):
+    rows, cols = gate.shape
+    if dgate is None:
+        dgate = torch.empty(rows, cols, dtype=BF16, device=gate.device)
+    if dup is None:
+        dup = torch.empty(rows, cols, dtype=BF16, device=gate.device)
+    _lib.call("lb_swiglu_bwd", _p(dout), _p(gate), _p(up), _p(dgate), _p(dup), rows, cols, dout.stride(0),
+              gate.stride(0), up.stride(0), dgate.stride(0), dup.stride(0), _st())
+    return dgate, dup
+
+
+def bias_quick_gelu_fwd(x, bias=None):
+    _chk(x, BF16, "x")
+    rows, cols = x.numel() // x.shape[-1], x.shape[-1]
+    y = torch.empty_like(x)
+    _lib.call("lb_bias_quick_gelu_fwd", _p(x), _p(bias), _p(y), rows, cols, _st())
+    return y
+
+
+def bias_quick_gelu_bwd(dy, x, bias=None):
+    rows, cols = x.numel() // x.shape[-1], x.shape[-1]
+    dx = torch.empty_like(x)
+    _lib.call("lb_bias_quick_gelu_bwd", _p(dy), _p(x), _p(bias), _p(dx), rows, cols, _st())
+    return dx
+
+
+def gather_rows(src, index):
+    """dst[r] = src[index[r]]; src [*, cols] bf16, index int32."""
+    _chk(src, BF16, "src"); _chk(index, torch.int32, "index")
+    cols = src.shape[-1]
+    dst = torch.empty(index.numel(), cols, dtype=BF16, device=src.device)
+    _lib.call("lb_gather_rows", _p(src), _p(index), _p(dst), index.numel(), cols, _st())
+    return dst
+
+
+def embed_lang(ids, table):
+    _chk(ids, torch.int64, "ids"); _chk(table, BF16, "table")
+    out = torch.empty(ids.numel(), table.shape[1], dtype=BF16, device=table.device)
+    _lib.call("lb_embed_lang_fwd", _p(ids), _p(table), _p(out), ids.numel(), table.shape[1], _st())
+    return out
+
+
+def embed_vision_cat(ids0, ids1, table0, table1, signal, signal_row, signal_cols):
+    half = table0.shape[1]
+    rows = ids0.numel()
+    out = torch.empty(rows, 2 * half + signal_cols, dtype=BF16, device=table0.device)
+    _lib.call("lb_embed_vision_cat_fwd", _p(ids0), _p(ids1), _p(table0), _p(table1), _p(signal), _p(signal_row), _p(out),
+              rows, half, signal_cols, _st())
+    return out
+
+
+def embed_bwd(ids, dy, col0, cols, dtable):
+    """dtable[ids[r]] += dy[r, col0:col0+cols]; dtable fp32."""
+    _lib.call("lb_embed_bwd", _p(ids), _p(dy), dy.stride(0), col0, _p(dtable), ids.numel(), cols, _st())
+    return dtable
+
+
+def lfq_pack(h, n_img, tokens, num_codebooks, bits, offset, boi, eoi):
+    dt = DT_BF16 if h.dtype == BF16 else DT_F32
+    if h.dtype not in (BF16, torch.float32):
+        raise TypeError("lfq_pack: bf16 or fp32")
+    _chk(h, None, "h")
+    ids = torch.empty(num_codebooks, n_img, tokens + 2, dtype=torch.int64, device=h.device)
+    _lib.call("lb_lfq_pack", _p(h), dt, n_img, tokens, num_codebooks, bits, offset, boi, eoi, _p(ids), _st())
+    return ids
+
+
+def lfq_unpack(idx, num_codebooks, bits, dtype=BF16):
+    _chk(idx, torch.int64, "idx")
+    n = idx.numel() // num_codebooks
+    codes = torch.empty(*idx.shape[:-1], num_codebooks * bits, dtype=dtype, device=idx.device)
+    _lib.call("lb_lfq_unpack", _p(idx), n, num_codebooks, bits, _p(codes), DT_BF16 if dtype == BF16 else DT_F32, _st())
+    return codes
+
+
+def cross_entropy_fwd_bwd(logits, labels, vocab, grad_scale):
+    """In place: logits (bf16 [rows, ld]) become grad_scale * d(sum loss)/dlogits.  Returns per-row loss (fp32)."""
+    rows = logits.shape[0]
+    loss = torch.empty(rows, dtype=torch.float32, device=logits.device)
+    _lib.call("lb_cross_entropy_fwd_bwd", _p(logits), logits.stride(0), _p(labels), _p(loss), rows, vocab,
+              float(grad_scale), _st())
+    return loss
+
+
+# ---------------------------------------------------------------- GEMM
+def gemm(a, b, trans_a=False, trans_b=False, out=None, out_dtype=BF16, bias=None, act=0, accumulate=False):
+    """C = op(A) op(B).  a: [M,K] (or [K,M] if trans_a); b: [N,K] (or [K,N] if trans_b) -- nn.Linear layout by default."""
+    M = a.shape[1] if trans_a else a.shape[0]
+    K = a.shape[0] if trans_a else a.shape[1]
+    N = b.shape[1] if trans_b else b.shape[0]
+    if out is None:
+        out = torch.empty(M, N, dtype=out_dtype, device=a.device)
+    _lib.call("lb_gemm_bf16", _p(a), _p(b), _p(out), _p(bias), M, N, K, a.stride(0), b.stride(0), out.stride(0),
+              int(trans_a), int(trans_b), DT_BF16 if out.dtype == BF16 else DT_F32, int(accumulate), int(act), _st())
+    return out
+
+
+def probe_umma(mode, a, b):
+    K = a.shape[1]
+    d = torch.empty(128, 128, dtype=torch.float32, device=a.device)
+    _lib.call("lb_probe_umma", mode, _p(a), _p(b), _p(d), K, _st())
+    return d
+
+
+# ------------------------------------------------------------ attention
+def attn_prep_fwd(q, k, v, tk, tv, Bk_l, Bk_v, Bv_l, Bv_v, flag_sorted, sorted_of, pos, cos_t, sin_t, heads, head_dim):
+    n = q.shape[0]
+    C = heads * head_dim
+    outs = [torch.empty(n, C, dtype=BF16, device=q.device) for _ in range(5)]
+    rank = 0 if tk is None else tk.shape[1]
+    _lib.call("lb_attn_prep_fwd", _p(q), _p(k), _p(v), _p(tk), _p(tv), _p(Bk_l), _p(Bk_v), _p(Bv_l), _p(Bv_v),
+              _p(flag_sorted), _p(sorted_of), _p(pos), _p(cos_t), _p(sin_t), *[_p(o) for o in outs], n, heads, head_dim,
+              rank, _st())
+    return outs   # Q, Kfv, Kfl, Vfv, Vfl
+
+
+def attn_prep_bwd(dQ, dKfv, dKfl, dVfv, dVfl, flag_sorted, sorted_of, pos, cos_t, sin_t, heads, head_dim, bridge=True):
+    n = dQ.shape[0]
+    C = heads * head_dim
+    dq, dk, dv = (torch.empty(n, C, dtype=BF16, device=dQ.device) for _ in range(3))
+    dkb = torch.empty(n, C, dtype=BF16, device=dQ.device) if bridge else None
+    dvb = torch.empty(n, C, dtype=BF16, device=dQ.device) if bridge else None
+    _lib.call("lb_attn_prep_bwd", _p(dQ), _p(dKfv), _p(dKfl), _p(dVfv), _p(dVfl), _p(flag_sorted), _p(sorted_of), _p(pos),
+              _p(cos_t), _p(sin_t), _p(dq), _p(dk), _p(dv), _p(dkb), _p(dvb), n, heads, head_dim, _st())
+    return dq, dk, dv, dkb, dvb
+
+
+def attn_fwd(Q, K0, V0, K1, V1, qflag, work, kv_start, kv_end, out_row, batch, seqlen, heads, head_dim, causal, scale,
+             out=None):
+    C = heads * head_dim
+    if out is None:
+        out = torch.zeros(batch * seqlen, C, dtype=BF16, device=Q.device)
+    lse = torch.full((batch, heads, seqlen), float("inf"), dtype=torch.float32, device=Q.device)
+    _lib.call("lb_attn_fwd", _p(Q), _p(K0), _p(V0), _p(K1), _p(V1), _p(qflag), _p(work), work.shape[0], _p(kv_start),
+              _p(kv_end), _p(out_row), _p(out), _p(lse), batch, seqlen, heads, head_dim, int(causal), float(scale), _st())
+    return out, lse
+
+
+def attn_bwd_prepare(O, dO, row_of, batch, seqlen, heads, head_dim, want_dO_orig=True):
+    C = heads * head_dim
+    dO_orig = torch.empty(batch * seqlen, C, dtype=BF16, device=O.device) if want_dO_orig else None
+    delta = torch.empty(batch, heads, seqlen, dtype=torch.float32, device=O.device)
+    _lib.call("lb_attn_bwd_prepare", _p(O), _p(dO), _p(row_of), _p(dO_orig), _p(delta), batch, seqlen, heads, head_dim, _st())
+    return dO_orig, delta
+
+
+def attn_bwd_dq(Q, K0, V0, K1, V1, dO, lse, delta, qflag, work, kv_start, kv_end, batch, seqlen, heads, head_dim, causal,
+                scale):
+    dQ = torch.zeros_like(Q)
+    _lib.call("lb_attn_bwd_dq", _p(Q), _p(K0), _p(V0), _p(K1), _p(V1), _p(dO), _p(lse), _p(delta), _p(qflag), _p(work),
+              work.shape[0], _p(kv_start), _p(kv_end), _p(dQ), batch, seqlen, heads, head_dim, int(causal), float(scale),
+              _st())
+    return dQ
+
+
+def attn_bwd_dkv(Q, K0, V0, K1, V1, dO, lse, delta, qflag, work_kv, kv_start, kv_end, batch, seqlen, heads, head_dim,
+                 causal, scale, two_variants=True):
+    dK0, dV0 = torch.zeros_like(K0), torch.zeros_like(V0)
+    dK1 = torch.zeros_like(K0) if two_variants else None
+    dV1 = torch.zeros_like(V0) if two_variants else None
+    _lib.call("lb_attn_bwd_dkv", _p(Q), _p(K0), _p(V0), _p(K1), _p(V1), _p(dO), _p(lse), _p(delta), _p(qflag),
+              _p(work_kv), work_kv.shape[0], _p(kv_start), _p(kv_end), _p(dK0), _p(dV0), _p(dK1), _p(dV1), batch, seqlen,
+              heads, head_dim, int(causal), float(scale), _st())
+    return dK0, dV0, dK1, dV1

@@ -1,0 +1,154 @@
+"""Bridge-attention kernels (tcgen05) vs the oracle's bridge_attention_core in fp32 on identical inputs.
+Tolerance: inputs are bf16, P is rounded to bf16 before P.V (as in the reference), accumulation fp32:
+|err| <= 2e-2 abs / 2e-2 rel on O(1) outputs."""
+import math
+
+import pytest
+import torch
+
+from gpu_util import need_gpu, assert_close, rel_err
+from oracle import libra_oracle as O
+
+pytestmark = pytest.mark.gpu
+dev = "cuda"
+
+
+def make_case(B, T, H, D, seed, flag_spans, pad=None, bridge=True):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    mk = lambda: torch.randn(B, T, H * D, device=dev, generator=g).bfloat16()
+    q, k, kc, v, vc = mk(), mk(), mk(), mk(), mk()
+    if bridge:
+        kc = (k.float() + 0.5 * kc.float()).bfloat16()       # cross variants = plain + something
+        vc = (v.float() + 0.5 * vc.float()).bfloat16()
+    else:
+        kc, vc = k, v
+    flag = torch.zeros(B, T, dtype=torch.bool, device=dev)
+    for b, s, e in flag_spans:
+        flag[b, s:e] = True
+    fo = flag[..., None]
+    Kfv, Kfl = torch.where(fo, k, kc), torch.where(fo, kc, k)      # vision token: fv plain / fl cross
+    Vfv, Vfl = torch.where(fo, v, vc), torch.where(fo, vc, v)
+    kv_end = [T] * B
+    if pad:
+        for b, n in pad:
+            kv_end[b] = T - n
+    return dict(q=q, k=k, kc=kc, v=v, vc=vc, flag=flag, Kfv=Kfv.contiguous(), Kfl=Kfl.contiguous(), Vfv=Vfv.contiguous(),
+                Vfl=Vfl.contiguous(), kv_end=kv_end, B=B, T=T, H=H, D=D)
+
+
+def oracle_out(c, causal=True, grads=None):
+    B, T, H, D = c["B"], c["T"], c["H"], c["D"]
+    hd = lambda t: t.float().view(B, T, H, D).transpose(1, 2)
+    valid = torch.ones(B, T, dtype=torch.long, device=dev)
+    for b in range(B):
+        valid[b, c["kv_end"][b]:] = 0
+    ts = [c[n].float().clone().requires_grad_(grads is not None) for n in ("q", "k", "kc", "v", "vc")]
+    q, k, kc, v, vc = (hd(t) for t in ts)
+    if causal:
+        o = O.bridge_attention_core(q, k, kc, v, vc - v, c["flag"], valid)
+    else:
+        p = torch.softmax(torch.matmul(q, k.transpose(2, 3)) / math.sqrt(D), -1)
+        o = torch.matmul(p, v)
+    o = o.transpose(1, 2).reshape(B, T, H * D)
+    if grads is not None:
+        o.backward(grads.float().view(B, T, H * D))
+        return o.detach(), [t.grad for t in ts]
+    return o
+
+
+def run_fwd(c, causal=True, out_row=None):
+    from libra_b200 import ops, schedule
+    B, T, H, D = c["B"], c["T"], c["H"], c["D"]
+    w = schedule.build_attn_work(c["flag"].cpu() if causal else None, B, T, causal, dev,
+                                 kv_end=c["kv_end"] if causal else None)
+    flat = lambda t: t.reshape(B * T, H * D)
+    qflag = c["flag"].reshape(-1).to(torch.uint8) if causal else None
+    o, lse = ops.attn_fwd(flat(c["q"]), flat(c["Kfl"]) if causal else flat(c["k"]), flat(c["Vfl"]) if causal else flat(c["v"]),
+                          flat(c["Kfv"]) if causal else None, flat(c["Vfv"]) if causal else None, qflag, w.work_q,
+                          w.kv_start, w.kv_end, out_row, B, T, H, D, causal, 1.0 / math.sqrt(D))
+    torch.cuda.synchronize()
+    return o.view(B, T, H * D), lse, w
+
+
+CASES = [
+    dict(B=1, T=128, H=1, D=128, spans=[], pad=None),                        # one tile, language only
+    dict(B=1, T=256, H=2, D=128, spans=[(0, 128, 256)], pad=None),          # homogeneous tiles, both variants
+    dict(B=2, T=192, H=2, D=128, spans=[(0, 1, 120), (1, 30, 150)], pad=[(1, 20)]),   # the golden layout
+    dict(B=2, T=700, H=2, D=128, spans=[(0, 1, 579), (1, 50, 628)], pad=[(0, 33)]),   # one image, ragged T
+    dict(B=1, T=1300, H=1, D=128, spans=[(0, 1, 579), (0, 600, 1178)], pad=None),     # two images
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"B{c['B']}T{c['T']}H{c['H']}")
+def test_bridge_attention_forward(case):
+    need_gpu()
+    c = make_case(case["B"], case["T"], case["H"], case["D"], 17, case["spans"], case["pad"])
+    o, lse, _ = run_fwd(c)
+    want = oracle_out(c)
+    for b in range(c["B"]):
+        e = c["kv_end"][b]           # padded query rows are unspecified (garbage in the reference too)
+        assert_close(o[b, :e], want[b, :e], rtol=2e-2, atol=2e-2, msg=f"sample {b}")
+    assert torch.isfinite(o.float()).all()
+
+
+def test_bridge_attention_matches_reference_golden(golden):
+    """The reference LibraAttention output (tests/golden/attention_hd128.pt), core kernel in the loop:
+    projections/bridge/rope by the oracle in fp32, attention core by the CUDA kernel."""
+    need_gpu()
+    g = golden("attention_hd128")
+    d = O.LibraDims.from_config(g["config"])
+    sd = {k: v.to(dev) for k, v in g["state_dict"].items()}
+    x, flag, am = g["x"].to(dev), g["flag"].to(dev), g["attention_mask"].to(dev)
+    B, T, C = x.shape
+    H, D = d.num_attention_heads, d.head_dim
+    pre = "self_attn"
+    proj = lambda n: O.route(x, flag, lambda r: r @ sd[f"{pre}.{n}_proj.weight"].t(),
+                             lambda r: (r @ sd[f"{pre}.vision_{n}_proj.weight_A"].t()) @ sd[f"{pre}.vision_{n}_proj.weight_B"].t())
+    br = lambda n: O.route(x, flag,
+                           lambda r: (r @ sd[f"{pre}.vision_{n}_bridge_on_language.weight_A"].t()) @ sd[f"{pre}.vision_{n}_bridge_on_language.weight_B"].t(),
+                           lambda r: (r @ sd[f"{pre}.vision_{n}_bridge_on_vision.weight_A"].t()) @ sd[f"{pre}.vision_{n}_bridge_on_vision.weight_B"].t())
+    q, k, v, kb, vb = proj("q"), proj("k"), proj("v"), br("k"), br("v")
+    cos, sin = O.rope_tables(D, 2048, 10000.0, torch.float32, dev)
+    pos = torch.arange(T, device=dev)[None].expand(B, T)
+    cs, sn = cos[pos][:, None], sin[pos][:, None]
+    hd = lambda t: t.view(B, T, H, D).transpose(1, 2)
+    unhd = lambda t: t.transpose(1, 2).reshape(B, T, C)
+    qr = unhd(O.rope_apply(hd(q), cs, sn))
+    ks, kc = unhd(O.rope_apply(hd(k), cs, sn)), unhd(O.rope_apply(hd(k + kb), cs, sn))
+    c = dict(q=qr.bfloat16(), B=B, T=T, H=H, D=D, flag=flag, kv_end=[int(am[b].sum()) for b in range(B)])
+    fo = flag[..., None]
+    c["Kfv"], c["Kfl"] = torch.where(fo, ks, kc).bfloat16().contiguous(), torch.where(fo, kc, ks).bfloat16().contiguous()
+    c["Vfv"], c["Vfl"] = torch.where(fo, v, v + vb).bfloat16().contiguous(), torch.where(fo, v + vb, v).bfloat16().contiguous()
+    o, _, _ = run_fwd(c)
+    y = O.route(o.float(), flag, lambda r: r @ sd[f"{pre}.o_proj.weight"].t(),
+                lambda r: (r @ sd[f"{pre}.vision_o_proj.weight_A"].t()) @ sd[f"{pre}.vision_o_proj.weight_B"].t())
+    want = g["out"].to(dev)
+    for b in range(B):
+        e = c["kv_end"][b]
+        assert rel_err(y[b, :e], want[b, :e]) < 2e-2, rel_err(y[b, :e], want[b, :e])
+
+
+def test_out_row_scatter_and_lse():
+    need_gpu()
+    c = make_case(2, 300, 2, 128, 5, [(0, 1, 200), (1, 100, 290)])
+    N = 600
+    perm = torch.randperm(N, device=dev).to(torch.int32)
+    o_s, lse, _ = run_fwd(c, out_row=perm)
+    o, _, _ = run_fwd(c)
+    assert torch.equal(o_s.view(N, -1)[perm.long()], o.view(N, -1))
+    # lse = logsumexp of the scaled, masked scores of the variant each row sees
+    B, T, H, D = 2, 300, 2, 128
+    hd = lambda t: t.float().view(B, T, H, D).transpose(1, 2)
+    X = (c["flag"][:, :, None] != c["flag"][:, None, :])[:, None]
+    s = torch.where(X, hd(c["q"]) @ hd(c["kc"]).transpose(2, 3), hd(c["q"]) @ hd(c["k"]).transpose(2, 3)) / math.sqrt(D)
+    s = s.masked_fill(~torch.ones(T, T, dtype=torch.bool, device=dev).tril(), float("-inf"))
+    assert_close(lse, torch.logsumexp(s, -1), rtol=1e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("B,T,H", [(2, 577, 4), (1, 128, 2), (3, 200, 1)])
+def test_vit_attention_forward(B, T, H):
+    need_gpu()
+    c = make_case(B, T, H, 64, 23, [], bridge=False)
+    o, _, _ = run_fwd(c, causal=False)
+    want = oracle_out(c, causal=False)
+    assert_close(o, want, rtol=2e-2, atol=2e-2)
