@@ -164,11 +164,14 @@ int lb_attn_bwd_dq(const void* Q, const void* K0, const void* V0, const void* K1
                    const int32_t* kv_start, const int32_t* kv_end, void* dQ, int batch, int seqlen, int heads,
                    int head_dim, int causal, float scale, void* stream);
 /* dK0,dV0 (gradient w.r.t. the variant-0 operands, from qflag==0 query rows) and dK1,dV1.
- * work_kv: int32 [n_work,4] = {batch, kv_tile, variant, first_q_tile}. */
+ * work_kv: int32 [n_work,4] = {batch, kv_tile, variant, first_q_tile}; qtile_has: uint8 [B,2,ceil(T/128)]
+ * (1 when the q tile holds rows of that modality; NULL = visit every tile).  Rows of kv tiles without a
+ * work item are not written: the caller zero-fills dK*,dV*. */
 int lb_attn_bwd_dkv(const void* Q, const void* K0, const void* V0, const void* K1, const void* V1, const void* dO,
-                    const float* lse, const float* delta, const uint8_t* qflag, const int32_t* work_kv, int n_work,
-                    const int32_t* kv_start, const int32_t* kv_end, void* dK0, void* dV0, void* dK1, void* dV1, int batch,
-                    int seqlen, int heads, int head_dim, int causal, float scale, void* stream);
+                    const float* lse, const float* delta, const uint8_t* qflag, const uint8_t* qtile_has,
+                    const int32_t* work_kv, int n_work, const int32_t* kv_start, const int32_t* kv_end, void* dK0,
+                    void* dV0, void* dK1, void* dV1, int batch, int seqlen, int heads, int head_dim, int causal,
+                    float scale, void* stream);
 
 /* ---- tcgen05 GEMM ---------------------------------------------------------
  * C[M,N] = op(A) . op(B) (+ C when accumulate), bf16 inputs, fp32 accumulation in TMEM.

@@ -43,7 +43,7 @@ SIGNATURES = {
     "lb_attn_fwd": (I, [P, P, P, P, P, P, P, I, P, P, P, P, P, I, I, I, I, I, F, P]),
     "lb_attn_bwd_prepare": (I, [P, P, P, P, P, I, I, I, I, P]),
     "lb_attn_bwd_dq": (I, [P] * 10 + [I, P, P, P, I, I, I, I, I, F, P]),
-    "lb_attn_bwd_dkv": (I, [P] * 10 + [I, P, P, P, P, P, P, I, I, I, I, I, F, P]),
+    "lb_attn_bwd_dkv": (I, [P] * 11 + [I, P, P, P, P, P, P, I, I, I, I, I, F, P]),
     "lb_gemm_bf16": (I, [P, P, P, P, L, L, L, L, L, L, I, I, I, I, I, P]),
     "lb_patch_embed_fwd": (I, [P, P, P, P, P, I, I, I, I, P]),
     "lb_cross_entropy_fwd_bwd": (I, [P, L, P, P, L, I, F, P]),

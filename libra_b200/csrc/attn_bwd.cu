@@ -1,0 +1,559 @@
+// Bridge attention backward (A10) on tcgen05/TMEM: two kernels, no atomics, deterministic.
+//
+//   lb_attn_bwd_dq : CTA = (sample, 128-row q tile, variant, head); loops over 64-wide kv tiles:
+//                    S = Q.K^T, dP = dO.V^T (SS MMAs) -> dS = P*(dP-delta)*scale (threads) -> dQ += dS.K (TS MMA, K as MN-major B)
+//   lb_attn_bwd_dkv: CTA = (sample, 128-row kv tile, variant, head); loops over 128-row q tiles that contain rows of the
+//                    variant: S^T = K.Q^T, dP^T = V.dO^T -> P^T, dS^T (threads) -> dV += P^T.dO, dK += dS^T.Q (TS MMAs,
+//                    dO / Q as MN-major B).
+// P is recomputed from the saved log-sum-exp; delta = rowsum(dO*O) comes from lb_attn_bwd_prepare.
+// Gradients w.r.t. the two operand variants (K0/V0 seen by qflag==0 rows, K1/V1 by qflag==1 rows) are written to
+// separate buffers; the prologue's adjoint (lb_attn_prep_bwd) folds them into dk, dv and the bridge gradients.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace lb {
+
+constexpr int BW_THREADS = 192;
+constexpr float LOG2E_F = 1.4426950408889634f;
+
+struct AttnBwdParams {
+    const uint8_t* qflag;      // [B*T] or null
+    const uint8_t* qtile_has;  // [B,2,n_qtiles] or null (dK/dV only): q tile holds rows of the variant
+    const int32_t* work;       // [n][4]
+    const int32_t* kv_start;
+    const int32_t* kv_end;
+    const float* lse;          // [B,H,T]
+    const float* delta;        // [B,H,T]
+    __nv_bfloat16* out0;       // dQ            | dK0
+    __nv_bfloat16* out1;       //               | dV0
+    __nv_bfloat16* out2;       //               | dK1
+    __nv_bfloat16* out3;       //               | dV1
+    int batch, seqlen, heads;
+    float scale;
+};
+
+// =====================================================================================================
+// dQ kernel
+// =====================================================================================================
+template <int D>
+struct DqSmem {
+    static constexpr int BN = 64;
+    static constexpr int Q_BYTES = 128 * D * 2;
+    static constexpr int DO_BYTES = 128 * D * 2;
+    static constexpr int K_BYTES = BN * D * 2;
+    static constexpr int V_BYTES = BN * D * 2;
+    static constexpr int BAR_OFF = Q_BYTES + DO_BYTES + K_BYTES + V_BYTES;
+    static constexpr int TOTAL = BAR_OFF + 1024 + 128;
+};
+enum { DQ_QDO = 0, DQ_KFULL, DQ_KEMPTY, DQ_VFULL, DQ_VEMPTY, DQ_SDP, DQ_DS, DQ_READY, DQ_NBAR };
+
+template <int D, bool CAUSAL>
+__global__ void __launch_bounds__(BW_THREADS, 2)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
+                   const __grid_constant__ CUtensorMap tmK0, const __grid_constant__ CUtensorMap tmV0,
+                   const __grid_constant__ CUtensorMap tmK1, const __grid_constant__ CUtensorMap tmV1,
+                   const AttnBwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    using S = DqSmem<D>;
+    constexpr int BN = S::BN;
+    uint8_t* sQ = smem;
+    uint8_t* sdO = sQ + S::Q_BYTES;
+    uint8_t* sK = sdO + S::DO_BYTES;
+    uint8_t* sV = sK + S::K_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + DQ_NBAR);
+
+    const int warp = threadIdx.x >> 5;
+    const int b = p.work[blockIdx.x * 4 + 0];
+    const int q_tile = p.work[blockIdx.x * 4 + 1];
+    const int variant = p.work[blockIdx.x * 4 + 2];
+    const int h = blockIdx.y;
+    const int T = p.seqlen;
+    const int q0 = q_tile * 128;
+    const int kvs = p.kv_start ? p.kv_start[b] : 0;
+    const int kve = p.kv_end ? p.kv_end[b] : T;
+    const int first_tile = kvs / BN;
+    int last_tile = (kve + BN - 1) / BN;
+    if (CAUSAL && last_tile > (q0 + 128) / BN) last_tile = (q0 + 128) / BN;
+    const int n_tiles = last_tile > first_tile ? last_tile - first_tile : 0;
+
+    constexpr uint32_t TMEM_COLS = 256, COL_S = 0, COL_DP = 64, COL_DQ = 128;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < DQ_NBAR; ++i) mbar_init(bars + i, i == DQ_DS ? 128 : 1);
+        fence_barrier_init();
+    }
+    if (warp == 5) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        if (elect_one() && n_tiles > 0) {
+            const CUtensorMap* tK = variant ? &tmK1 : &tmK0;
+            const CUtensorMap* tV = variant ? &tmV1 : &tmV0;
+            const int row_q = b * T + q0;
+            mbar_arrive_expect_tx(bars + DQ_QDO, S::Q_BYTES + S::DO_BYTES);
+#pragma unroll
+            for (int c = 0; c < D / 64; ++c) {
+                tma_load_2d(sQ + c * (128 * 128), &tmQ, bars + DQ_QDO, h * D + c * 64, row_q);
+                tma_load_2d(sdO + c * (128 * 128), &tmdO, bars + DQ_QDO, h * D + c * 64, row_q);
+            }
+            for (int it = 0; it < n_tiles; ++it) {
+                const int row_k = b * T + (first_tile + it) * BN;
+                const uint32_t ph = (uint32_t)it & 1u;
+                mbar_wait(bars + DQ_KEMPTY, ph ^ 1u);
+                mbar_arrive_expect_tx(bars + DQ_KFULL, S::K_BYTES);
+#pragma unroll
+                for (int c = 0; c < D / 64; ++c) tma_load_2d(sK + c * (BN * 128), tK, bars + DQ_KFULL, h * D + c * 64, row_k);
+                mbar_wait(bars + DQ_VEMPTY, ph ^ 1u);
+                mbar_arrive_expect_tx(bars + DQ_VFULL, S::V_BYTES);
+#pragma unroll
+                for (int c = 0; c < D / 64; ++c) tma_load_2d(sV + c * (BN * 128), tV, bars + DQ_VFULL, h * D + c * 64, row_k);
+            }
+        }
+    } else if (warp == 5) {
+        if (elect_one() && n_tiles > 0) {
+            constexpr uint32_t idesc_s = make_idesc_bf16(128, BN, 0, 0);
+            constexpr uint32_t idesc_dq = make_idesc_bf16(128, D, 0, 1);
+            const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aK = smem_u32(sK), aV = smem_u32(sV);
+            mbar_wait(bars + DQ_QDO, 0);
+            for (int it = 0; it < n_tiles; ++it) {
+                const uint32_t ph = (uint32_t)it & 1u;
+                mbar_wait(bars + DQ_KFULL, ph);
+                tc_fence_after_sync();
+#pragma unroll
+                for (int kk = 0; kk < D / 16; ++kk) {
+                    const uint32_t offA = (uint32_t)(kk / 4) * (128 * 128) + (uint32_t)(kk % 4) * 32;
+                    const uint32_t offB = (uint32_t)(kk / 4) * (BN * 128) + (uint32_t)(kk % 4) * 32;
+                    umma_ss(tmem_base + COL_S, desc_kmajor(aQ + offA), desc_kmajor(aK + offB), idesc_s, kk ? 1u : 0u);
+                }
+                mbar_wait(bars + DQ_VFULL, ph);
+                tc_fence_after_sync();
+#pragma unroll
+                for (int kk = 0; kk < D / 16; ++kk) {
+                    const uint32_t offA = (uint32_t)(kk / 4) * (128 * 128) + (uint32_t)(kk % 4) * 32;
+                    const uint32_t offB = (uint32_t)(kk / 4) * (BN * 128) + (uint32_t)(kk % 4) * 32;
+                    umma_ss(tmem_base + COL_DP, desc_kmajor(adO + offA), desc_kmajor(aV + offB), idesc_s, kk ? 1u : 0u);
+                }
+                tc_commit(bars + DQ_VEMPTY);
+                tc_commit(bars + DQ_SDP);
+                mbar_wait(bars + DQ_DS, ph);
+                tc_fence_after_sync();
+#pragma unroll
+                for (int kk = 0; kk < BN / 16; ++kk)
+                    umma_ts(tmem_base + COL_DQ, tmem_base + COL_S + kk * 8, desc_mnmajor(aK + kk * 2048, BN * 128), idesc_dq,
+                            (it | kk) ? 1u : 0u);
+                tc_commit(bars + DQ_KEMPTY);
+                tc_commit(bars + DQ_READY);
+            }
+        }
+    } else {
+        const int r = threadIdx.x;
+        const int qi = q0 + r;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const float sl2 = p.scale * LOG2E_F;
+        const int64_t stat_idx = ((int64_t)b * p.heads + h) * T + (qi < T ? qi : 0);
+        const bool row_ok = (qi < T) && (!p.qflag || (int)p.qflag[(int64_t)b * T + (qi < T ? qi : 0)] == variant);
+        const float lse2 = row_ok ? p.lse[stat_idx] * LOG2E_F : CUDART_INF_F;
+        const float dlt = row_ok ? p.delta[stat_idx] : 0.f;
+        for (int it = 0; it < n_tiles; ++it) {
+            const uint32_t ph = (uint32_t)it & 1u;
+            const int kv0 = (first_tile + it) * BN;
+            const bool need_mask = (CAUSAL && kv0 + BN - 1 > q0) || (kv0 + BN > kve) || (kv0 < kvs);
+            mbar_wait(bars + DQ_SDP, ph);
+            tc_fence_after_sync();
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t s[32], dp[32];
+                tmem_ld32(lane_addr + COL_S + c * 32, s);
+                tmem_ld32(lane_addr + COL_DP + c * 32, dp);
+                tc_wait_ld();
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    float p0 = exp2f(__uint_as_float(s[j]) * sl2 - lse2);
+                    float p1 = exp2f(__uint_as_float(s[j + 1]) * sl2 - lse2);
+                    if (need_mask) {
+                        const int kj = kv0 + c * 32 + j;
+                        p0 = ((!CAUSAL || kj <= qi) && kj < kve && kj >= kvs) ? p0 : 0.f;
+                        p1 = ((!CAUSAL || kj + 1 <= qi) && kj + 1 < kve && kj + 1 >= kvs) ? p1 : 0.f;
+                    }
+                    const float d0 = p0 * (__uint_as_float(dp[j]) - dlt) * p.scale;
+                    const float d1 = p1 * (__uint_as_float(dp[j + 1]) - dlt) * p.scale;
+                    pk[j >> 1] = pack_bf16(d0, d1);
+                }
+                tmem_st16(lane_addr + COL_S + c * 16, pk);     // dS (bf16) over S: chunk c of S is consumed, see fwd
+            }
+            tc_wait_st();
+            tc_fence_before_sync();
+            mbar_arrive(bars + DQ_DS);
+        }
+        if (n_tiles > 0) {
+            mbar_wait(bars + DQ_READY, (uint32_t)(n_tiles - 1) & 1u);
+            tc_fence_after_sync();
+        }
+        __nv_bfloat16* orow = p.out0 + ((int64_t)b * T + (qi < T ? qi : 0)) * ((int64_t)p.heads * D) + (int64_t)h * D;
+#pragma unroll 1
+        for (int c = 0; c < D / 32; ++c) {
+            uint32_t v[32];
+            if (n_tiles > 0) {
+                tmem_ld32(lane_addr + COL_DQ + c * 32, v);
+                tc_wait_ld();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0u;
+            }
+            if (row_ok) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    uint4 o;
+                    o.x = pack_bf16(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
+                    o.y = pack_bf16(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                    o.z = pack_bf16(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+                    o.w = pack_bf16(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+                    *reinterpret_cast<uint4*>(orow + c * 32 + j) = o;
+                }
+            }
+            __syncwarp();
+        }
+        tc_fence_before_sync();
+    }
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// =====================================================================================================
+// dK/dV kernel
+// =====================================================================================================
+template <int D>
+struct DkvSmem {
+    static constexpr int K_BYTES = 128 * D * 2;
+    static constexpr int V_BYTES = 128 * D * 2;
+    static constexpr int Q_BYTES = 128 * D * 2;      // per stage
+    static constexpr int DO_BYTES = 128 * D * 2;     // per stage
+    static constexpr int STAGES = 2;
+    static constexpr int STAT_OFF = K_BYTES + V_BYTES + STAGES * (Q_BYTES + DO_BYTES);
+    static constexpr int STAT_BYTES = 2 * 128 * 12;  // [stage][lse2, delta, ok] x 128
+    static constexpr int BAR_OFF = STAT_OFF + STAT_BYTES;
+    static constexpr int TOTAL = BAR_OFF + 1024 + 256;
+};
+enum { KV_KV = 0, KV_QFULL0, KV_QFULL1, KV_QEMPTY0, KV_QEMPTY1, KV_SDP, KV_PDS, KV_DONE, KV_NBAR };
+
+template <int D, bool CAUSAL>
+__global__ void __launch_bounds__(BW_THREADS, 1)
+attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
+                    const __grid_constant__ CUtensorMap tmK0, const __grid_constant__ CUtensorMap tmV0,
+                    const __grid_constant__ CUtensorMap tmK1, const __grid_constant__ CUtensorMap tmV1,
+                    const AttnBwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    using S = DkvSmem<D>;
+    uint8_t* sK = smem;
+    uint8_t* sV = sK + S::K_BYTES;
+    uint8_t* sQ0 = sV + S::V_BYTES;                       // stage s: sQ0 + s*(Q+dO), dO right after Q
+    float* stats = reinterpret_cast<float*>(smem + S::STAT_OFF);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + KV_NBAR);
+
+    const int warp = threadIdx.x >> 5;
+    const int b = p.work[blockIdx.x * 4 + 0];
+    const int kv_tile = p.work[blockIdx.x * 4 + 1];
+    const int variant = p.work[blockIdx.x * 4 + 2];
+    const int first_q = p.work[blockIdx.x * 4 + 3];
+    const int h = blockIdx.y;
+    const int T = p.seqlen;
+    const int kv0 = kv_tile * 128;
+    const int kvs = p.kv_start ? p.kv_start[b] : 0;
+    const int kve = p.kv_end ? p.kv_end[b] : T;
+    const int nqt = (T + 127) / 128;
+
+    constexpr uint32_t TMEM_COLS = 512, COL_S = 0, COL_DP = 128, COL_DV = 256, COL_DK = 256 + D;
+
+    // q tiles that hold rows of this variant (host-computed bitmap; without it every tile is visited and the
+    // per-row flags alone do the masking)
+    auto tile_has = [&](int qt) -> bool {
+        return p.qtile_has ? p.qtile_has[((int64_t)b * 2 + variant) * nqt + qt] != 0 : true;
+    };
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < KV_NBAR; ++i) mbar_init(bars + i, i == KV_PDS ? 128 : 1);
+        fence_barrier_init();
+    }
+    if (warp == 5) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    // tile list in shared memory (<= 64 q tiles, T <= 8192)
+    __shared__ int s_tiles[64];
+    __shared__ int s_ntiles;
+    if (threadIdx.x == 32) {
+        int n = 0;
+        for (int qt = first_q; qt < nqt && n < 64; ++qt)
+            if (tile_has(qt)) s_tiles[n++] = qt;
+        s_ntiles = n;
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const int n_tiles = s_ntiles;
+
+    if (warp == 4) {
+        if (elect_one() && n_tiles > 0) {
+            const CUtensorMap* tK = variant ? &tmK1 : &tmK0;
+            const CUtensorMap* tV = variant ? &tmV1 : &tmV0;
+            const int row_k = b * T + kv0;
+            mbar_arrive_expect_tx(bars + KV_KV, S::K_BYTES + S::V_BYTES);
+#pragma unroll
+            for (int c = 0; c < D / 64; ++c) {
+                tma_load_2d(sK + c * (128 * 128), tK, bars + KV_KV, h * D + c * 64, row_k);
+                tma_load_2d(sV + c * (128 * 128), tV, bars + KV_KV, h * D + c * 64, row_k);
+            }
+            for (int it = 0; it < n_tiles; ++it) {
+                const int st = it & 1;
+                const uint32_t ph = (uint32_t)(it >> 1) & 1u;
+                const int row_q = b * T + s_tiles[it] * 128;
+                uint8_t* q = sQ0 + st * (S::Q_BYTES + S::DO_BYTES);
+                uint8_t* d = q + S::Q_BYTES;
+                mbar_wait(bars + KV_QEMPTY0 + st, ph ^ 1u);
+                mbar_arrive_expect_tx(bars + KV_QFULL0 + st, S::Q_BYTES + S::DO_BYTES);
+#pragma unroll
+                for (int c = 0; c < D / 64; ++c) {
+                    tma_load_2d(q + c * (128 * 128), &tmQ, bars + KV_QFULL0 + st, h * D + c * 64, row_q);
+                    tma_load_2d(d + c * (128 * 128), &tmdO, bars + KV_QFULL0 + st, h * D + c * 64, row_q);
+                }
+            }
+        }
+    } else if (warp == 5) {
+        if (elect_one() && n_tiles > 0) {
+            constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+            constexpr uint32_t idesc_g = make_idesc_bf16(128, D, 0, 1);
+            const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
+            mbar_wait(bars + KV_KV, 0);
+            for (int it = 0; it < n_tiles; ++it) {
+                const int st = it & 1;
+                const uint32_t phq = (uint32_t)(it >> 1) & 1u;
+                const uint32_t ph = (uint32_t)it & 1u;
+                const uint32_t aQ = smem_u32(sQ0 + st * (S::Q_BYTES + S::DO_BYTES));
+                const uint32_t adO = aQ + S::Q_BYTES;
+                mbar_wait(bars + KV_QFULL0 + st, phq);
+                tc_fence_after_sync();
+#pragma unroll
+                for (int kk = 0; kk < D / 16; ++kk) {
+                    const uint32_t off = (uint32_t)(kk / 4) * (128 * 128) + (uint32_t)(kk % 4) * 32;
+                    umma_ss(tmem_base + COL_S, desc_kmajor(aK + off), desc_kmajor(aQ + off), idesc_s, kk ? 1u : 0u);
+                }
+#pragma unroll
+                for (int kk = 0; kk < D / 16; ++kk) {
+                    const uint32_t off = (uint32_t)(kk / 4) * (128 * 128) + (uint32_t)(kk % 4) * 32;
+                    umma_ss(tmem_base + COL_DP, desc_kmajor(aV + off), desc_kmajor(adO + off), idesc_s, kk ? 1u : 0u);
+                }
+                tc_commit(bars + KV_SDP);
+                mbar_wait(bars + KV_PDS, ph);
+                tc_fence_after_sync();
+#pragma unroll
+                for (int kk = 0; kk < 128 / 16; ++kk)
+                    umma_ts(tmem_base + COL_DV, tmem_base + COL_S + kk * 8, desc_mnmajor(adO + kk * 2048, 128 * 128), idesc_g,
+                            (it | kk) ? 1u : 0u);
+#pragma unroll
+                for (int kk = 0; kk < 128 / 16; ++kk)
+                    umma_ts(tmem_base + COL_DK, tmem_base + COL_DP + kk * 8, desc_mnmajor(aQ + kk * 2048, 128 * 128), idesc_g,
+                            (it | kk) ? 1u : 0u);
+                tc_commit(bars + KV_QEMPTY0 + st);
+            }
+            tc_commit(bars + KV_DONE);
+        }
+    } else {
+        const int r = threadIdx.x;               // kv row in tile == TMEM lane
+        const int kj = kv0 + r;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const float sl2 = p.scale * LOG2E_F;
+        const bool key_ok = kj < kve && kj >= kvs;
+        for (int it = 0; it < n_tiles; ++it) {
+            const int st = it & 1;
+            const uint32_t ph = (uint32_t)it & 1u;
+            const int q0 = s_tiles[it] * 128;
+            float* sl = stats + st * 384;        // [lse2 | delta | ok]
+            {
+                const int qi = q0 + r;
+                const bool ok = qi < T && (!p.qflag || (int)p.qflag[(int64_t)b * T + (qi < T ? qi : 0)] == variant);
+                const int64_t si = ((int64_t)b * p.heads + h) * T + (qi < T ? qi : 0);
+                sl[r] = ok ? p.lse[si] * LOG2E_F : CUDART_INF_F;
+                sl[128 + r] = ok ? p.delta[si] : 0.f;
+                sl[256 + r] = ok ? 1.f : 0.f;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(bars + KV_SDP, ph);
+            tc_fence_after_sync();
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t s[32], dp[32];
+                tmem_ld32(lane_addr + COL_S + c * 32, s);
+                tmem_ld32(lane_addr + COL_DP + c * 32, dp);
+                tc_wait_ld();
+                uint32_t pp[16], pd[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const int col = c * 32 + j;
+                    const int qa = q0 + col;
+                    const bool ok0 = key_ok && sl[256 + col] != 0.f && (!CAUSAL || kj <= qa);
+                    const bool ok1 = key_ok && sl[256 + col + 1] != 0.f && (!CAUSAL || kj <= qa + 1);
+                    const float p0 = ok0 ? exp2f(__uint_as_float(s[j]) * sl2 - sl[col]) : 0.f;
+                    const float p1 = ok1 ? exp2f(__uint_as_float(s[j + 1]) * sl2 - sl[col + 1]) : 0.f;
+                    const float d0 = p0 * (__uint_as_float(dp[j]) - sl[128 + col]) * p.scale;
+                    const float d1 = p1 * (__uint_as_float(dp[j + 1]) - sl[128 + col + 1]) * p.scale;
+                    pp[j >> 1] = pack_bf16(p0, p1);
+                    pd[j >> 1] = pack_bf16(d0, d1);
+                }
+                tmem_st16(lane_addr + COL_S + c * 16, pp);      // P^T over S^T (chunk already consumed)
+                tmem_st16(lane_addr + COL_DP + c * 16, pd);     // dS^T over dP^T
+            }
+            tc_wait_st();
+            tc_fence_before_sync();
+            mbar_arrive(bars + KV_PDS);
+        }
+        if (n_tiles > 0) {
+            mbar_wait(bars + KV_DONE, 0);
+            tc_fence_after_sync();
+            const bool row_ok = kj < T;
+            const int64_t off = ((int64_t)b * T + (row_ok ? kj : 0)) * ((int64_t)p.heads * D) + (int64_t)h * D;
+            __nv_bfloat16* dk_row = (variant ? p.out2 : p.out0) + off;
+            __nv_bfloat16* dv_row = (variant ? p.out3 : p.out1) + off;
+#pragma unroll 1
+            for (int c = 0; c < 2 * D / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(lane_addr + COL_DV + c * 32, v);      // dV columns then dK columns (contiguous)
+                tc_wait_ld();
+                __nv_bfloat16* dst = (c < D / 32) ? (dv_row + c * 32) : (dk_row + (c - D / 32) * 32);
+                if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        uint4 o;
+                        o.x = pack_bf16(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
+                        o.y = pack_bf16(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                        o.z = pack_bf16(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+                        o.w = pack_bf16(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+                        *reinterpret_cast<uint4*>(dst + j) = o;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        tc_fence_before_sync();
+    }
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+template <typename KernT>
+static int configure(KernT kern, int smem, const char* what) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return fail(LB_ELAUNCH, "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+    return LB_OK;
+}
+
+template <int D, bool CAUSAL>
+static int launch_dq(const CUtensorMap* tm, const AttnBwdParams& p, int n_work, cudaStream_t st) {
+    auto kern = attn_bwd_dq_kernel<D, CAUSAL>;
+    static bool configured = false;
+    if (!configured) {
+        int rc = configure(kern, DqSmem<D>::TOTAL, "attn_bwd_dq");
+        if (rc) return rc;
+        configured = true;
+    }
+    kern<<<dim3((unsigned)n_work, (unsigned)p.heads), BW_THREADS, DqSmem<D>::TOTAL, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4],
+                                                                                       tm[5], p);
+    return check_launch("attn_bwd_dq");
+}
+
+template <int D, bool CAUSAL>
+static int launch_dkv(const CUtensorMap* tm, const AttnBwdParams& p, int n_work, cudaStream_t st) {
+    auto kern = attn_bwd_dkv_kernel<D, CAUSAL>;
+    static bool configured = false;
+    if (!configured) {
+        int rc = configure(kern, DkvSmem<D>::TOTAL, "attn_bwd_dkv");
+        if (rc) return rc;
+        configured = true;
+    }
+    kern<<<dim3((unsigned)n_work, (unsigned)p.heads), BW_THREADS, DkvSmem<D>::TOTAL, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4],
+                                                                                        tm[5], p);
+    return check_launch("attn_bwd_dkv");
+}
+
+static int make_maps(CUtensorMap* tm, const void* Q, const void* dO, const void* K0, const void* V0, const void* K1,
+                     const void* V1, int batch, int seqlen, int heads, int head_dim, uint32_t q_box, uint32_t kv_box) {
+    const uint64_t rows = (uint64_t)batch * seqlen, cols = (uint64_t)heads * head_dim;
+    const void* ptrs[6] = {Q, dO, K0, V0, K1 ? K1 : K0, V1 ? V1 : V0};
+    for (int i = 0; i < 6; ++i) {
+        int rc = make_tmap_bf16_2d(&tm[i], ptrs[i], rows, cols, cols, i < 2 ? q_box : kv_box, 64);
+        if (rc) return rc;
+    }
+    return LB_OK;
+}
+
+}  // namespace lb
+
+using namespace lb;
+
+extern "C" {
+
+int lb_attn_bwd_dq(const void* Q, const void* K0, const void* V0, const void* K1, const void* V1, const void* dO,
+                   const float* lse, const float* delta, const uint8_t* qflag, const int32_t* work, int n_work,
+                   const int32_t* kv_start, const int32_t* kv_end, void* dQ, int batch, int seqlen, int heads,
+                   int head_dim, int causal, float scale, void* stream) {
+    LB_REQUIRE(batch > 0 && seqlen > 0 && heads > 0 && n_work >= 0, LB_EINVAL, "attn_bwd_dq: bad shape");
+    LB_REQUIRE(head_dim == 64 || head_dim == 128, LB_EINVAL, "attn_bwd_dq: head_dim %d (64 or 128 supported)", head_dim);
+    LB_REQUIRE(Q && K0 && V0 && dO && lse && delta && work && dQ, LB_EINVAL, "attn_bwd_dq: null argument");
+    if (n_work == 0) return LB_OK;
+    int rc = require_sm100();
+    if (rc) return rc;
+    CUtensorMap tm[6];
+    rc = make_maps(tm, Q, dO, K0, V0, K1, V1, batch, seqlen, heads, head_dim, 128, 64);
+    if (rc) return rc;
+    AttnBwdParams p{};
+    p.qflag = qflag; p.work = work; p.kv_start = kv_start; p.kv_end = kv_end; p.lse = lse; p.delta = delta;
+    p.out0 = (__nv_bfloat16*)dQ; p.batch = batch; p.seqlen = seqlen; p.heads = heads; p.scale = scale;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (head_dim == 128) return causal ? launch_dq<128, true>(tm, p, n_work, st) : launch_dq<128, false>(tm, p, n_work, st);
+    return causal ? launch_dq<64, true>(tm, p, n_work, st) : launch_dq<64, false>(tm, p, n_work, st);
+}
+
+int lb_attn_bwd_dkv(const void* Q, const void* K0, const void* V0, const void* K1, const void* V1, const void* dO,
+                    const float* lse, const float* delta, const uint8_t* qflag, const uint8_t* qtile_has,
+                    const int32_t* work_kv, int n_work, const int32_t* kv_start, const int32_t* kv_end, void* dK0,
+                    void* dV0, void* dK1, void* dV1, int batch, int seqlen, int heads, int head_dim, int causal,
+                    float scale, void* stream) {
+    LB_REQUIRE(batch > 0 && seqlen > 0 && heads > 0 && n_work >= 0, LB_EINVAL, "attn_bwd_dkv: bad shape");
+    LB_REQUIRE(head_dim == 64 || head_dim == 128, LB_EINVAL, "attn_bwd_dkv: head_dim %d (64 or 128 supported)", head_dim);
+    LB_REQUIRE(seqlen <= 8192, LB_EINVAL, "attn_bwd_dkv: seqlen %d > 8192", seqlen);
+    LB_REQUIRE(Q && K0 && V0 && dO && lse && delta && work_kv && dK0 && dV0, LB_EINVAL, "attn_bwd_dkv: null argument");
+    if (n_work == 0) return LB_OK;
+    int rc = require_sm100();
+    if (rc) return rc;
+    CUtensorMap tm[6];
+    rc = make_maps(tm, Q, dO, K0, V0, K1, V1, batch, seqlen, heads, head_dim, 128, 128);
+    if (rc) return rc;
+    AttnBwdParams p{};
+    p.qflag = qflag; p.qtile_has = qtile_has; p.work = work_kv; p.kv_start = kv_start; p.kv_end = kv_end; p.lse = lse; p.delta = delta;
+    p.out0 = (__nv_bfloat16*)dK0; p.out1 = (__nv_bfloat16*)dV0;
+    p.out2 = (__nv_bfloat16*)(dK1 ? dK1 : dK0); p.out3 = (__nv_bfloat16*)(dV1 ? dV1 : dV0);
+    p.batch = batch; p.seqlen = seqlen; p.heads = heads; p.scale = scale;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (head_dim == 128) return causal ? launch_dkv<128, true>(tm, p, n_work, st) : launch_dkv<128, false>(tm, p, n_work, st);
+    return causal ? launch_dkv<64, true>(tm, p, n_work, st) : launch_dkv<64, false>(tm, p, n_work, st);
+}
+
+}

@@ -1,0 +1,349 @@
+"""Differentiable ops (torch.autograd.Function) over the CUDA kernels, in the decoder's *sorted-row* layout:
+rows [0, n_lang) are language tokens, rows [n_lang, N) vision tokens (libra_b200.schedule.build_routing).
+
+Plain dense GEMMs (nn.Linear-shaped products) go through cuBLAS via torch.matmul; everything else on the
+hot path -- norms, SwiGLU, bridge/RoPE prologue, attention forward/backward, cross-entropy, embeddings -- is
+this library's own sm_100a code.  There is no non-CUDA fallback anywhere in this module.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import ops
+from .schedule import AttnWork, Routing
+
+BF16 = torch.bfloat16
+
+
+# ----------------------------------------------------------------------------- norms
+class RoutedRMSNorm(torch.autograd.Function):
+    """LlamaRMSNorm with the weight picked per row by modality (modeling_libra.py:463,479,817)."""
+
+    @staticmethod
+    def forward(ctx, x, w_lang, w_vis, flag, eps):
+        y, rstd = ops.rmsnorm_fwd(x, w_lang, w_vis, flag, eps)
+        ctx.save_for_backward(x, w_lang, w_vis, flag, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w_lang, w_vis, flag, rstd = ctx.saved_tensors
+        need_dw = ctx.needs_input_grad[1] or (w_vis is not None and ctx.needs_input_grad[2])
+        dx, dwl, dwv = ops.rmsnorm_bwd(dy.contiguous(), x, w_lang, w_vis, flag, rstd, need_dw=need_dw)
+        gl = dwl.to(w_lang.dtype) if (need_dw and ctx.needs_input_grad[1]) else None
+        gv = dwv.to(w_vis.dtype) if (need_dw and w_vis is not None and ctx.needs_input_grad[2]) else None
+        return dx, gl, gv, None, None
+
+
+def rmsnorm(x, w_lang, w_vis=None, flag=None, eps=1e-6):
+    return RoutedRMSNorm.apply(x, w_lang, w_vis, flag, eps)
+
+
+class LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        y, mean, rstd = ops.layernorm_fwd(x, w, b, eps)
+        ctx.save_for_backward(x, w, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, mean, rstd = ctx.saved_tensors
+        dx, dw, db = ops.layernorm_bwd(dy.contiguous(), x, w, mean, rstd)
+        return dx, dw.to(w.dtype), db.to(w.dtype), None
+
+
+def layernorm(x, w, b, eps=1e-5):
+    return LayerNorm.apply(x, w, b, eps)
+
+
+# ----------------------------------------------------------------------------- activations
+class SwiGLU(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gate, up):
+        ctx.save_for_backward(gate, up)
+        return ops.swiglu_fwd(gate, up)
+
+    @staticmethod
+    def backward(ctx, dout):
+        gate, up = ctx.saved_tensors
+        dg, du = ops.swiglu_bwd(dout.contiguous(), gate, up)
+        return dg, du
+
+
+def swiglu(gate, up):
+    return SwiGLU.apply(gate, up)
+
+
+class BiasQuickGelu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, bias):
+        ctx.save_for_backward(x, bias)
+        return ops.bias_quick_gelu_fwd(x, bias)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, bias = ctx.saved_tensors
+        dx = ops.bias_quick_gelu_bwd(dy.contiguous(), x, bias)
+        db = dx.reshape(-1, dx.shape[-1]).sum(0).to(bias.dtype) if (bias is not None and ctx.needs_input_grad[1]) else None
+        return dx, db
+
+
+def bias_quick_gelu(x, bias):
+    return BiasQuickGelu.apply(x, bias)
+
+
+# ----------------------------------------------------------------------------- routed linear
+class RoutedLinear(torch.autograd.Function):
+    """y[:n_lang] = x[:n_lang] W^T ;  y[n_lang:] = (x[n_lang:] A^T) B^T
+    (language nn.Linear | vision LibraLinear, modeling_libra.py:192-199, routed by :129-147).
+    The two row ranges are contiguous, so there is no gather/scatter and no boolean indexing."""
+
+    @staticmethod
+    def forward(ctx, x, n_lang, W, A, B):
+        N = x.shape[0]
+        y = torch.empty(N, W.shape[0] if W is not None else B.shape[0], dtype=x.dtype, device=x.device)
+        xl, xv = x[:n_lang], x[n_lang:]
+        if n_lang > 0:
+            torch.matmul(xl, W.t(), out=y[:n_lang])
+        mid = None
+        if N - n_lang > 0:
+            mid = torch.matmul(xv, A.t())
+            torch.matmul(mid, B.t(), out=y[n_lang:])
+        ctx.n_lang = n_lang
+        ctx.save_for_backward(x, W, A, B, mid)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W, A, B, mid = ctx.saved_tensors
+        n_lang = ctx.n_lang
+        N = x.shape[0]
+        dy = dy.contiguous()
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dW = dA = dB = None
+        if n_lang > 0:
+            if dx is not None:
+                torch.matmul(dy[:n_lang], W, out=dx[:n_lang])
+            if ctx.needs_input_grad[2]:
+                dW = torch.matmul(dy[:n_lang].t(), x[:n_lang])
+        elif ctx.needs_input_grad[2]:
+            dW = torch.zeros_like(W)
+        if N - n_lang > 0:
+            dyv = dy[n_lang:]
+            dmid = torch.matmul(dyv, B)
+            if dx is not None:
+                torch.matmul(dmid, A, out=dx[n_lang:])
+            if ctx.needs_input_grad[4]:
+                dB = torch.matmul(dyv.t(), mid)
+            if ctx.needs_input_grad[3]:
+                dA = torch.matmul(dmid.t(), x[n_lang:])
+        else:
+            if ctx.needs_input_grad[3]:
+                dA = torch.zeros_like(A)
+            if ctx.needs_input_grad[4]:
+                dB = torch.zeros_like(B)
+        return dx, None, dW, dA, dB
+
+
+def routed_linear(x, n_lang, W, A, B):
+    return RoutedLinear.apply(x, n_lang, W, A, B)
+
+
+class RoutedDown(torch.autograd.Function):
+    """t[:n_lang] = x[:n_lang] A_lang^T ; t[n_lang:] = x[n_lang:] A_vis^T  -- the rank-r first halves of the
+    bridge LibraLinears (vision_{k,v}_bridge_on_{language,vision}.weight_A, modeling_libra.py:259-263,318-319)."""
+
+    @staticmethod
+    def forward(ctx, x, n_lang, A_lang, A_vis):
+        N = x.shape[0]
+        t = torch.empty(N, A_lang.shape[0], dtype=x.dtype, device=x.device)
+        if n_lang > 0:
+            torch.matmul(x[:n_lang], A_lang.t(), out=t[:n_lang])
+        if N - n_lang > 0:
+            torch.matmul(x[n_lang:], A_vis.t(), out=t[n_lang:])
+        ctx.n_lang = n_lang
+        ctx.save_for_backward(x, A_lang, A_vis)
+        return t
+
+    @staticmethod
+    def backward(ctx, dt):
+        x, A_lang, A_vis = ctx.saved_tensors
+        n = ctx.n_lang
+        dt = dt.contiguous()
+        dx = torch.empty_like(x)
+        torch.matmul(dt[:n], A_lang, out=dx[:n])
+        torch.matmul(dt[n:], A_vis, out=dx[n:])
+        dAl = torch.matmul(dt[:n].t(), x[:n]) if ctx.needs_input_grad[2] else None
+        dAv = torch.matmul(dt[n:].t(), x[n:]) if ctx.needs_input_grad[3] else None
+        return dx, None, dAl, dAv
+
+
+def routed_down(x, n_lang, A_lang, A_vis):
+    return RoutedDown.apply(x, n_lang, A_lang, A_vis)
+
+
+# ----------------------------------------------------------------------------- attention
+@dataclass
+class AttnMeta:
+    routing: Routing
+    work: AttnWork
+    pos: torch.Tensor            # [B*T] int32 rotary position per original token
+    cos: torch.Tensor            # [n_pos, D/2] fp32
+    sin: torch.Tensor
+    batch: int
+    seqlen: int
+    heads: int
+    head_dim: int
+
+
+class BridgeAttention(torch.autograd.Function):
+    """LibraAttention core with use_bridge=True (modeling_libra.py:318-397, 267-296): bridge add + RoPE prologue,
+    tcgen05 flash attention over the two key/value variants, output scattered back to sorted rows."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, tk, tv, Bk_l, Bk_v, Bv_l, Bv_v, meta: AttnMeta):
+        rt, w = meta.routing, meta.work
+        Q, Kfv, Kfl, Vfv, Vfl = ops.attn_prep_fwd(q, k, v, tk, tv, Bk_l, Bk_v, Bv_l, Bv_v, rt.flag_sorted, rt.inv, meta.pos,
+                                                 meta.cos, meta.sin, meta.heads, meta.head_dim)
+        scale = 1.0 / math.sqrt(meta.head_dim)
+        o = torch.empty_like(q)
+        # variant 0 = language queries (see Kfl/Vfl), variant 1 = vision queries (see Kfv/Vfv); rows land in sorted order
+        o, lse = ops.attn_fwd(Q, Kfl, Vfl, Kfv, Vfv, rt.flag_orig, w.work_q, w.kv_start, w.kv_end, rt.inv, meta.batch,
+                              meta.seqlen, meta.heads, meta.head_dim, True, scale, out=o)
+        ctx.meta = meta
+        ctx.scale = scale
+        ctx.save_for_backward(Q, Kfv, Kfl, Vfv, Vfl, o, lse, tk, tv, Bk_l, Bk_v, Bv_l, Bv_v)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        meta: AttnMeta = ctx.meta
+        rt, w = meta.routing, meta.work
+        Q, Kfv, Kfl, Vfv, Vfl, o, lse, tk, tv, Bk_l, Bk_v, Bv_l, Bv_v = ctx.saved_tensors
+        B, T, H, D = meta.batch, meta.seqlen, meta.heads, meta.head_dim
+        dO, delta = ops.attn_bwd_prepare(o, do.contiguous(), rt.inv, B, T, H, D)
+        dQ = ops.attn_bwd_dq(Q, Kfl, Vfl, Kfv, Vfv, dO, lse, delta, rt.flag_orig, w.work_q, w.kv_start, w.kv_end, B, T, H, D,
+                             True, ctx.scale)
+        dKfl, dVfl, dKfv, dVfv = ops.attn_bwd_dkv(Q, Kfl, Vfl, Kfv, Vfv, dO, lse, delta, rt.flag_orig, w.qtile_has, w.work_kv,
+                                                 w.kv_start, w.kv_end, B, T, H, D, True, ctx.scale)
+        dq, dk, dv, dkb, dvb = ops.attn_prep_bwd(dQ, dKfv, dKfl, dVfv, dVfl, rt.flag_sorted, rt.inv, meta.pos, meta.cos,
+                                                 meta.sin, H, D)
+        n = rt.n_lang
+        # kb = tk . B^T  =>  d_tk = dkb . B ; dB = dkb^T . tk   (per modality segment)
+        d_tk = torch.empty_like(tk)
+        d_tv = torch.empty_like(tv)
+        torch.matmul(dkb[:n], Bk_l, out=d_tk[:n])
+        torch.matmul(dkb[n:], Bk_v, out=d_tk[n:])
+        torch.matmul(dvb[:n], Bv_l, out=d_tv[:n])
+        torch.matmul(dvb[n:], Bv_v, out=d_tv[n:])
+        g = ctx.needs_input_grad
+        dBk_l = torch.matmul(dkb[:n].t(), tk[:n]) if g[5] else None
+        dBk_v = torch.matmul(dkb[n:].t(), tk[n:]) if g[6] else None
+        dBv_l = torch.matmul(dvb[:n].t(), tv[:n]) if g[7] else None
+        dBv_v = torch.matmul(dvb[n:].t(), tv[n:]) if g[8] else None
+        return dq, dk, dv, d_tk, d_tv, dBk_l, dBk_v, dBv_l, dBv_v, None
+
+
+def bridge_attention(q, k, v, tk, tv, Bk_l, Bk_v, Bv_l, Bv_v, meta: AttnMeta):
+    return BridgeAttention.apply(q, k, v, tk, tv, Bk_l, Bk_v, Bv_l, Bv_v, meta)
+
+
+class PlainAttention(torch.autograd.Function):
+    """Non-causal self-attention over [B*T, H*D] (CLIPAttention core, modeling_clip.py:309-349).
+    q must already carry the head_dim**-0.5 scale (the reference scales q before the matmul)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, work: AttnWork, batch, seqlen, heads, head_dim):
+        o, lse = ops.attn_fwd(q, k, v, None, None, None, work.work_q, None, None, None, batch, seqlen, heads, head_dim, False,
+                              1.0)
+        ctx.args = (work, batch, seqlen, heads, head_dim)
+        ctx.save_for_backward(q, k, v, o, lse)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        work, B, T, H, D = ctx.args
+        q, k, v, o, lse = ctx.saved_tensors
+        dO, delta = ops.attn_bwd_prepare(o, do.contiguous(), None, B, T, H, D)
+        dq = ops.attn_bwd_dq(q, k, v, None, None, dO, lse, delta, None, work.work_q, None, None, B, T, H, D, False, 1.0)
+        dk, dv, _, _ = ops.attn_bwd_dkv(q, k, v, None, None, dO, lse, delta, None, work.qtile_has, work.work_kv, None, None, B,
+                                        T, H, D, False, 1.0, two_variants=False)
+        return dq, dk, dv, None, None, None, None, None
+
+
+def plain_attention(q, k, v, work, batch, seqlen, heads, head_dim):
+    return PlainAttention.apply(q, k, v, work, batch, seqlen, heads, head_dim)
+
+
+# ----------------------------------------------------------------------------- embeddings
+class EmbedLang(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ids, table):
+        ctx.save_for_backward(ids)
+        ctx.shape = table.shape
+        return ops.embed_lang(ids, table)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (ids,) = ctx.saved_tensors
+        dt = torch.zeros(ctx.shape, dtype=torch.float32, device=dy.device)
+        dy = dy.contiguous()
+        ops.embed_bwd(ids, dy, 0, ctx.shape[1], dt)
+        return None, dt.to(dy.dtype)
+
+
+class EmbedVisionCat(torch.autograd.Function):
+    """[vemb0[id0] | vemb1[id1] | signal] per vision row (modeling_libra.py:629-644)."""
+
+    @staticmethod
+    def forward(ctx, ids0, ids1, table0, table1, signal, signal_row, signal_cols):
+        ctx.save_for_backward(ids0, ids1)
+        ctx.shapes = (table0.shape, table1.shape)
+        return ops.embed_vision_cat(ids0, ids1, table0, table1, signal, signal_row, signal_cols)
+
+    @staticmethod
+    def backward(ctx, dy):
+        ids0, ids1 = ctx.saved_tensors
+        s0, s1 = ctx.shapes
+        dy = dy.contiguous()
+        d0 = torch.zeros(s0, dtype=torch.float32, device=dy.device)
+        d1 = torch.zeros(s1, dtype=torch.float32, device=dy.device)
+        ops.embed_bwd(ids0, dy, 0, s0[1], d0)
+        ops.embed_bwd(ids1, dy, s0[1], s1[1], d1)
+        return None, None, d0.to(dy.dtype), d1.to(dy.dtype), None, None, None
+
+
+# ----------------------------------------------------------------------------- heads + loss
+class HeadCrossEntropy(torch.autograd.Function):
+    """sum over rows of CE(x W^T, labels) * row_scale, fused: logits are produced by one GEMM, reduced and turned
+    into their own gradient in place by lb_cross_entropy_fwd_bwd, and never leave bf16 / HBM more than 3 times
+    (modeling_libra.py:1018-1052 restricted to the finite vocabulary block of the row's modality, :1159-1174).
+    Returns (loss_sum fp32 scalar tensor, n_valid fp32 scalar tensor)."""
+
+    @staticmethod
+    def forward(ctx, x, W, labels, grad_scale):
+        logits = torch.matmul(x, W.t())
+        row_loss = ops.cross_entropy_fwd_bwd(logits, labels, W.shape[0], grad_scale)
+        ctx.save_for_backward(x, W, logits)
+        return row_loss.sum()
+
+    @staticmethod
+    def backward(ctx, g):
+        x, W, dlogits = ctx.saved_tensors
+        dx = torch.matmul(dlogits, W) if ctx.needs_input_grad[0] else None
+        dW = torch.matmul(dlogits.t(), x) if ctx.needs_input_grad[1] else None
+        # upstream gradient of the (already pre-scaled) partial loss is a scalar
+        if dx is not None:
+            dx = dx * g.to(dx.dtype)
+        if dW is not None:
+            dW = dW * g.to(dW.dtype)
+        return dx, dW, None, None
+
+
+def head_cross_entropy(x, W, labels, grad_scale=1.0):
+    return HeadCrossEntropy.apply(x, W, labels, grad_scale)

@@ -241,12 +241,12 @@ def attn_bwd_dq(Q, K0, V0, K1, V1, dO, lse, delta, qflag, work, kv_start, kv_end
     return dQ
 
 
-def attn_bwd_dkv(Q, K0, V0, K1, V1, dO, lse, delta, qflag, work_kv, kv_start, kv_end, batch, seqlen, heads, head_dim,
-                 causal, scale, two_variants=True):
+def attn_bwd_dkv(Q, K0, V0, K1, V1, dO, lse, delta, qflag, qtile_has, work_kv, kv_start, kv_end, batch, seqlen, heads,
+                 head_dim, causal, scale, two_variants=True):
     dK0, dV0 = torch.zeros_like(K0), torch.zeros_like(V0)
     dK1 = torch.zeros_like(K0) if two_variants else None
     dV1 = torch.zeros_like(V0) if two_variants else None
     _lib.call("lb_attn_bwd_dkv", _p(Q), _p(K0), _p(V0), _p(K1), _p(V1), _p(dO), _p(lse), _p(delta), _p(qflag),
-              _p(work_kv), work_kv.shape[0], _p(kv_start), _p(kv_end), _p(dK0), _p(dV0), _p(dK1), _p(dV1), batch, seqlen,
+              _p(qtile_has), _p(work_kv), work_kv.shape[0], _p(kv_start), _p(kv_end), _p(dK0), _p(dV0), _p(dK1), _p(dV1), batch, seqlen,
               heads, head_dim, int(causal), float(scale), _st())
     return dK0, dV0, dK1, dV1

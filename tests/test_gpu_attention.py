@@ -152,3 +152,61 @@ def test_vit_attention_forward(B, T, H):
     o, _, _ = run_fwd(c, causal=False)
     want = oracle_out(c, causal=False)
     assert_close(o, want, rtol=2e-2, atol=2e-2)
+
+
+def run_bwd(c, o, lse, w, dO, causal=True):
+    from libra_b200 import ops
+    B, T, H, D = c["B"], c["T"], c["H"], c["D"]
+    flat = lambda t: t.reshape(B * T, H * D).contiguous()
+    qflag = c["flag"].reshape(-1).to(torch.uint8) if causal else None
+    K0, V0 = (flat(c["Kfl"]), flat(c["Vfl"])) if causal else (flat(c["k"]), flat(c["v"]))
+    K1, V1 = (flat(c["Kfv"]), flat(c["Vfv"])) if causal else (None, None)
+    dO_orig, delta = ops.attn_bwd_prepare(flat(o), flat(dO), None, B, T, H, D)
+    assert torch.equal(dO_orig, flat(dO))
+    scale = 1.0 / math.sqrt(D)
+    dQ = ops.attn_bwd_dq(flat(c["q"]), K0, V0, K1, V1, dO_orig, lse, delta, qflag, w.work_q, w.kv_start, w.kv_end, B, T, H, D,
+                         causal, scale)
+    dK0, dV0, dK1, dV1 = ops.attn_bwd_dkv(flat(c["q"]), K0, V0, K1, V1, dO_orig, lse, delta, qflag, w.qtile_has, w.work_kv,
+                                         w.kv_start, w.kv_end, B, T, H, D, causal, scale, two_variants=causal)
+    torch.cuda.synchronize()
+    return delta, dQ, dK0, dV0, dK1, dV1
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: f"B{c['B']}T{c['T']}H{c['H']}")
+def test_bridge_attention_backward(case):
+    need_gpu()
+    c = make_case(case["B"], case["T"], case["H"], case["D"], 29, case["spans"], case["pad"])
+    B, T, H, D = c["B"], c["T"], c["H"], c["D"]
+    o, lse, w = run_fwd(c)
+    g = torch.Generator(device=dev).manual_seed(3)
+    dO = torch.randn(B, T, H * D, device=dev, generator=g).bfloat16()
+    for b in range(B):
+        dO[b, c["kv_end"][b]:] = 0          # padded rows carry no gradient
+    delta, dQ, dK0, dV0, dK1, dV1 = run_bwd(c, o, lse, w, dO)
+    _, (gq, gk, gkc, gv, gvc) = oracle_out(c, grads=dO)
+    hd = lambda t: t.float().view(B, T, H, D)
+    want_delta = (hd(o) * hd(dO)).sum(-1).permute(0, 2, 1)
+    assert_close(delta, want_delta, rtol=1e-2, atol=2e-2, msg="delta")
+    assert_close(dQ.view(B, T, -1), gq, rtol=3e-2, atol=3e-2, msg="dQ")
+    # oracle leaves are (k plain, k cross, v plain, v cross); the kernel differentiates (Kfl,Vfl)=variant 0 and (Kfv,Vfv)=variant 1
+    fo = c["flag"][..., None]
+    r = lambda t: t.view(B, T, -1).float()
+    # Kfl = flag ? kc : k ; Kfv = flag ? k : kc   =>   dk = where(flag, dKfv, dKfl), dkc = where(flag, dKfl, dKfv)
+    assert_close(torch.where(fo, r(dK1), r(dK0)), gk, rtol=3e-2, atol=3e-2, msg="dK plain")
+    assert_close(torch.where(fo, r(dK0), r(dK1)), gkc, rtol=3e-2, atol=3e-2, msg="dK cross")
+    assert_close(torch.where(fo, r(dV1), r(dV0)), gv, rtol=3e-2, atol=3e-2, msg="dV plain")
+    assert_close(torch.where(fo, r(dV0), r(dV1)), gvc, rtol=3e-2, atol=3e-2, msg="dV cross")
+
+
+@pytest.mark.parametrize("B,T,H", [(2, 577, 4), (1, 128, 2)])
+def test_vit_attention_backward(B, T, H):
+    need_gpu()
+    c = make_case(B, T, H, 64, 31, [], bridge=False)
+    o, lse, w = run_fwd(c, causal=False)
+    g = torch.Generator(device=dev).manual_seed(4)
+    dO = torch.randn(B, T, H * 64, device=dev, generator=g).bfloat16()
+    delta, dQ, dK0, dV0, _, _ = run_bwd(c, o, lse, w, dO, causal=False)
+    _, (gq, gk, _, gv, _) = oracle_out(c, causal=False, grads=dO)
+    assert_close(dQ.view(B, T, -1), gq, rtol=3e-2, atol=3e-2, msg="dQ")
+    assert_close(dK0.view(B, T, -1), gk, rtol=3e-2, atol=3e-2, msg="dK")
+    assert_close(dV0.view(B, T, -1), gv, rtol=3e-2, atol=3e-2, msg="dV")
