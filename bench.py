@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- Libra-11B training throughput on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py --gpus 1 --steps K --warmup W
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --gpus N --steps K --warmup W      (CPU reference arm)
+
+A "step" is one optimizer step of LibraForCausalLM (Libra-11B shapes, random init, bf16) on a synthetic batch of
+B=8 samples x T=2048 tokens per GPU (<s> + one 578-token image + 1469 text tokens: BASELINE.json configs[2]):
+micro-batched forward + backward through the libra_b200 CUDA path, one NCCL all-reduce of the flat bf16 gradient
+buffer when N > 1, fused AdamW.  `value` = tokens of all ranks / max-over-ranks device time with the inputs resident
+in HBM; `e2e` repeats the measurement through the public model API with pinned HOST inputs copied in, and the loss read
+back, inside the timed region.  Weak scaling: per-GPU batch is fixed.
+
+Only this file's `cpu_baseline` leg and `--impl reference` execute anything under oracle/ (the CPU checker), never
+the measured CUDA path.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch
+import torch.distributed as dist
+
+METRIC = "libra11b_train_tokens_per_sec"
+UNIT = "tokens/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="libra_b200", choices=["libra_b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="samples per GPU per optimizer step")
+    ap.add_argument("--micro-batch", type=int, default=4)
+    ap.add_argument("--seq", type=int, default=2048)
+    ap.add_argument("--images", type=int, default=1)
+    ap.add_argument("--layers", type=int, default=32)
+    ap.add_argument("--ckpt", type=int, default=0, help="gradient checkpointing per decoder layer")
+    ap.add_argument("--frozen-language", type=int, default=0)
+    ap.add_argument("--optimizer", default="adamw", choices=["adamw", "none"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--tiny", action="store_true", help="tiny model for plumbing checks (NOT a bench value)")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d.get("hbm_gbs"), tflops_burst=d.get("bf16_tflops"),
+                    tflops_sustained=d.get("bf16_tflops_sustained"), source="measured")
+    return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, source="fallback")
+
+
+# --------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm = [float(r[0]) for r in rows if len(r) >= 8 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.strip().lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+# --------------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_sample(n_layers: int = 2, threads: int = 0, repeats: int = 1):
+    """Times the oracle (CPU restatement of the reference's LibraForCausalLM path, oracle/libra_oracle.py) on the
+    host cores: forward+backward of `n_layers` FULL-WIDTH Libra-11B decoder layers in bf16 on BASELINE.json configs[0]'s
+    sequence (1 image + 32 text tokens, T=611), scaled by 32/n_layers to a whole-model tokens/s figure."""
+    from oracle import libra_oracle as O
+    threads = threads or (os.cpu_count() or 1)
+    torch.set_num_threads(threads)
+    d = O.LibraDims()
+    g = torch.Generator().manual_seed(0)
+    H, I, R = d.hidden_size, d.intermediate_size, d.bridge_rank
+    sd = {}
+
+    def w(*s):
+        return (torch.randn(*s, generator=g) * 0.02).bfloat16().requires_grad_(True)
+    for i in range(n_layers):
+        p = f"model.layers.{i}"
+        for n in "qkvo":
+            sd[f"{p}.self_attn.{n}_proj.weight"] = w(H, H)
+            sd[f"{p}.self_attn.vision_{n}_proj.weight_A"] = w(H // 4, H)
+            sd[f"{p}.self_attn.vision_{n}_proj.weight_B"] = w(H, H // 4)
+        for n in "kv":
+            for m in ("language", "vision"):
+                sd[f"{p}.self_attn.vision_{n}_bridge_on_{m}.weight_A"] = w(R, H)
+                sd[f"{p}.self_attn.vision_{n}_bridge_on_{m}.weight_B"] = w(H, R)
+        for n, (i_, o_) in dict(gate=(H, I), up=(H, I), down=(I, H)).items():
+            sd[f"{p}.mlp.{n}_proj.weight"] = w(o_, i_)
+            sd[f"{p}.mlp.vision_{n}_proj.weight_A"] = w(o_ // 4, i_)
+            sd[f"{p}.mlp.vision_{n}_proj.weight_B"] = w(o_, o_ // 4)
+        for n in ("input_layernorm", "post_attention_layernorm", "vision_input_layernorm", "vision_post_attention_layernorm"):
+            sd[f"{p}.{n}.weight"] = torch.ones(H, dtype=torch.bfloat16).requires_grad_(True)
+    T = 611
+    flag = torch.zeros(1, T, dtype=torch.bool)
+    flag[0, 1:579] = True
+    pos = torch.arange(T)[None]
+    times = []
+    for _ in range(repeats):
+        h = torch.randn(1, T, H, generator=g).bfloat16().requires_grad_(True)
+        t0 = time.perf_counter()
+        x = h
+        for i in range(n_layers):
+            x = O.decoder_layer(sd, i, d, x, flag, pos, None)
+        x.float().pow(2).mean().backward()
+        times.append(time.perf_counter() - t0)
+    t = statistics.median(times)
+    value = T / (t * 32.0 / n_layers)
+    return dict(value=value, unit=UNIT, cores=threads, kind="port",
+                sample=f"oracle fwd+bwd of {n_layers} full-width Libra-11B decoder layers, bf16, B=1 T=611 (1 image + 32 text), "
+                       f"{t:.2f} s, scaled x{32 // n_layers} to 32 layers (embeddings/heads excluded)")
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_reference_sample(n_layers=1 if (args.warmup + args.steps) > 6 else 2)
+        if i >= args.warmup:
+            vals.append(r)
+    v = statistics.median([x["value"] for x in vals]) if vals else float("nan")
+    cb = dict(vals[-1], value=v) if vals else None
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "Libra-11B train step B=8 T=2048 per GPU (BASELINE.json configs[2]); the CPU arm times a bounded "
+                                   "sample (see cpu_baseline.sample)"},
+            "cpu_baseline": cb, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------- CUDA arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and not (world == 1 and args.gpus == 1):
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    from libra_b200 import _lib, ops, synthetic
+    from libra_b200.models import LibraConfig, LibraForCausalLM
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    _lib.require_device()        # no fallback: fail loudly without the CUDA library / an sm_100 device
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = LibraConfig(num_hidden_layers=args.layers)
+    if args.tiny:
+        cfg = LibraConfig(hidden_size=256, intermediate_size=704, num_hidden_layers=2, num_attention_heads=2, vocab_size=1024,
+                          contiguous_signal_size=64)
+    torch.manual_seed(0)
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.bfloat16)
+    with torch.device(dev):
+        model = LibraForCausalLM(cfg)
+    torch.set_default_dtype(prev)
+    model = model.to(torch.bfloat16).train()
+    synthetic.randomize_for_bench(model, seed=0)
+    if args.ckpt:
+        model.gradient_checkpointing_enable()
+    if args.frozen_language:
+        for n, p in model.named_parameters():
+            p.requires_grad = "vision" in n
+    params = [p for p in model.parameters() if p.requires_grad]
+    n_train = sum(p.numel() for p in params)
+    # one flat bf16 gradient buffer; every .grad is a view into it (a single NCCL all-reduce per step)
+    flat = torch.zeros(n_train, dtype=torch.bfloat16, device=dev)
+    off = 0
+    for p in params:
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+    opt = torch.optim.AdamW(params, lr=1e-5, betas=(0.9, 0.95), weight_decay=0.0, fused=True) if args.optimizer == "adamw" else None
+
+    B, T, MB = args.batch, args.seq, args.micro_batch
+    assert B % MB == 0
+    host = synthetic.libra_batch(B, T, args.images, vocab=cfg.vocab_size, signal=cfg.contiguous_signal_size, seed=1234 + rank, pin=True)
+    resident = {k: v.to(dev) for k, v in host.items()}
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
+
+    def micro(inp, i):
+        sl = slice(i * MB, (i + 1) * MB)
+        out = model(input_ids=inp["input_ids"][:, sl], attention_mask=None, vision_indices=inp["vision_indices"][sl],
+                    contiguous_signal=inp["contiguous_signal"][sl], labels=inp["labels"][:, sl])
+        return out.loss
+
+    def step(inp, from_host: bool):
+        if from_host:
+            inp = {k: v.to(dev, non_blocking=True) for k, v in inp.items()}
+        flat.zero_()
+        total = None
+        for i in range(B // MB):
+            loss = micro(inp, i) * (MB / B) / world
+            loss.backward()
+            total = loss.detach() if total is None else total + loss.detach()
+        if world > 1:
+            dist.all_reduce(flat)
+        if opt is not None:
+            opt.step()
+        return float(total.item()) if from_host else total
+
+    def timed(k, from_host):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev[0].record()
+        last = None
+        for _ in range(k):
+            last = step(host if from_host else resident, from_host)
+        ev[1].record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = ev[0].elapsed_time(ev[1])
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, last
+
+    for _ in range(args.warmup):
+        step(resident, False)
+    torch.cuda.synchronize()
+    mem_gb = torch.cuda.max_memory_allocated() / 2 ** 30
+
+    _lib.reset_launch_counts()
+    ops.enable_timing()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, last_loss = timed(args.steps, False)
+    clocks = sampler.stop() if sampler else None
+    kt = ops.disable_timing()
+    launches = _lib.total_launches()
+    tokens_step = B * T * world
+    value = tokens_step * args.steps / (ms / 1e3)
+
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(1):
+            step(host, True)
+        ms_e, _ = timed(args.steps, True)
+        e2e = {"value": tokens_step * args.steps / (ms_e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+               "d2h_bytes_per_step": 4, "ms_per_step": ms_e / args.steps}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the bridge-attention forward kernel (the kernel BASELINE.json's second metric names)
+    peaks = load_peaks()
+    fl = synthetic.decoder_flops(cfg, MB, T, args.images * synthetic.IMG)
+    kern = {}
+    for name, evs in (kt or {}).items():
+        if evs:
+            kern[name] = sum(s.elapsed_time(e) for s, e in evs) / len(evs)
+    roof = None
+    if "lb_attn_fwd" in kern:
+        t_ms = kern["lb_attn_fwd"]
+        ach = fl["attn_per_layer_fwd"] / (t_ms * 1e-3) / 1e12
+        roof = {"kernel": "attn_fwd_kernel<128,causal> (bridge attention forward)", "bound": "tensor", "achieved": ach,
+                "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tflops_sustained"],
+                "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); kernel timed inside a long step",
+                "traffic": None, "avg_launch_ms": t_ms,
+                "algorithmic_flops_per_launch": fl["attn_per_layer_fwd"],
+                "other_kernels_ms": {k: v for k, v in kern.items() if k != "lb_attn_fwd"},
+                "bwd_achieved_tflops": (2.5 * fl["attn_per_layer_fwd"] / ((kern.get("lb_attn_bwd_dq", 0) + kern.get("lb_attn_bwd_dkv", 0)) * 1e-3) / 1e12)
+                if kern.get("lb_attn_bwd_dq") else None}
+    model_flops_step = 3.0 * fl["total"] * (B // MB)
+    cb = None
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            cb = cpu_reference_sample(n_layers=2)
+        except Exception as ex:      # the checker must never take the measured path down
+            cb = {"error": repr(ex)}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": f"Libra-11B train step (fwd+bwd{'+AdamW' if opt else ''}{'+grad all-reduce' if world > 1 else ''}), "
+                               f"B={B} (micro-batch {MB}) x T={T} per GPU, {args.images} image(s)/sample, {cfg.num_hidden_layers} layers, "
+                               f"all params trainable={not args.frozen_language}, ckpt={bool(args.ckpt)} -- BASELINE.json configs[2]",
+                   "global_batch": B * world, "seq_len": T, "parallelism": f"dp{world}", "trainable_params": n_train,
+                   "l2": "working set (>= 22 GB of weights per step) far exceeds the 126 MB L2; no explicit flush",
+                   "tiny": bool(args.tiny)},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cb,
+        "loss": float(last_loss.item()) if last_loss is not None else None,
+        "model_tflops_per_gpu": model_flops_step / (ms / args.steps * 1e-3) / 1e12, "peak_mem_gb": mem_gb,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -88,11 +88,31 @@ def last_error() -> str:
     return buf.value.decode("utf-8", "replace")
 
 
+# CUDA kernels enqueued by one successful call of each entry point (host-side launch accounting for bench.py)
+KERNELS_PER_CALL = {
+    "lb_rmsnorm_fwd": 1, "lb_rmsnorm_bwd": 3, "lb_layernorm_fwd": 1, "lb_layernorm_bwd": 3, "lb_swiglu_fwd": 1,
+    "lb_swiglu_bwd": 1, "lb_bias_quick_gelu_fwd": 1, "lb_bias_quick_gelu_bwd": 1, "lb_gather_rows": 1,
+    "lb_embed_lang_fwd": 1, "lb_embed_vision_cat_fwd": 3, "lb_embed_bwd": 1, "lb_lfq_pack": 1, "lb_lfq_unpack": 1,
+    "lb_attn_prep_fwd": 1, "lb_attn_prep_bwd": 1, "lb_attn_fwd": 1, "lb_attn_bwd_prepare": 1, "lb_attn_bwd_dq": 1,
+    "lb_attn_bwd_dkv": 1, "lb_gemm_bf16": 1, "lb_patch_embed_fwd": 1, "lb_cross_entropy_fwd_bwd": 1, "lb_probe_umma": 1,
+}
+launch_counts: dict = {}
+
+
+def reset_launch_counts():
+    launch_counts.clear()
+
+
+def total_launches() -> int:
+    return sum(KERNELS_PER_CALL.get(k, 1) * v for k, v in launch_counts.items())
+
+
 def call(name: str, *args):
     """Invoke an int-returning entry point; raise with the library's message on failure."""
     lib = load()
     fn = getattr(lib, name)
     rc = fn(*args)
+    launch_counts[name] = launch_counts.get(name, 0) + 1
     if rc != 0:
         raise LibraB200Error(f"{name} failed ({rc}): {last_error()}")
     return rc

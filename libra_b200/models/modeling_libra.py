@@ -1,0 +1,455 @@
+"""Host-side mirror of the reference's decoder interface (libra/models/libra/modeling_libra.py), running on the
+libra_b200 CUDA kernels.
+
+Same class names, constructor arguments, forward signature, output object and **state-dict keys** as the reference
+(LibraLinear.weight_A/weight_B, self_attn.vision_k_bridge_on_language, model.vision_embed_tokens.{0,1}, ...), so
+`from_pretrained` of a reference checkpoint, the reference's train.py and the HF Trainer work against it.
+
+What differs is the execution plan: the [B,T,C] activations are permuted once per batch into
+"sorted rows" (language tokens first, vision tokens second) and stay that way through all layers, which turns
+the reference's ~52 boolean gather/scatter ops per layer (cal_language_vision, :111-147) into two contiguous row
+ranges; attention runs on one fused tcgen05 kernel (libra_b200.functional.bridge_attention).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import List, Optional, Tuple, Union
+
+import torch
+import torch.utils.checkpoint
+from torch import nn
+from transformers.modeling_outputs import CausalLMOutputWithPast
+from transformers.modeling_utils import PreTrainedModel
+
+from .. import _lib
+from .. import functional as LF
+from .. import schedule
+from .configuration_libra import LibraConfig
+
+BF16 = torch.bfloat16
+
+
+@dataclass
+class LibraCausalLMOutputWithPast(CausalLMOutputWithPast):
+    """Same fields as the reference output class (modeling_libra.py:98-109)."""
+    loss: Optional[torch.FloatTensor] = None
+    logits: torch.FloatTensor = None
+    past_key_values: Optional[Tuple[Tuple[torch.FloatTensor]]] = None
+    hidden_states: Optional[Tuple[torch.FloatTensor]] = None
+    attentions: Optional[Tuple[torch.FloatTensor]] = None
+    past_hidden_states: Optional[torch.FloatTensor] = None
+    past_vision_flag: Optional[torch.BoolTensor] = None
+
+
+class LlamaRMSNorm(nn.Module):
+    """Parameter holder (libra/models/llama/modeling_llama.py:118-132); the maths runs in lb_rmsnorm_*."""
+
+    def __init__(self, hidden_size, eps=1e-6):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(hidden_size))
+        self.variance_epsilon = eps
+
+    def forward(self, x):
+        shp = x.shape
+        return LF.rmsnorm(x.reshape(-1, shp[-1]).contiguous(), self.weight, None, None, self.variance_epsilon).view(shp)
+
+
+class LibraLinear(nn.Module):
+    """Low-rank pair y = (x A^T) B^T (modeling_libra.py:150-204): same parameters, shapes and initialisation."""
+
+    def __init__(self, in_features: int, out_features: int, bias: bool = False, down_ratio=4, rank=None):
+        super().__init__()
+        assert in_features % down_ratio == 0
+        assert bias is False, "Not checked yet."
+        self.in_features, self.out_features, self.down_ratio, self.rank = in_features, out_features, down_ratio, rank
+        mid = rank if rank is not None else out_features // down_ratio
+        self.weight_A = nn.Parameter(torch.empty(mid, in_features))
+        self.weight_B = nn.Parameter(torch.empty(out_features, mid))
+        self.register_parameter("bias", None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.init.kaiming_uniform_(self.weight_A, a=math.sqrt(5))
+        if self.rank is not None:
+            nn.init.constant_(self.weight_B, 0.0)
+        else:
+            nn.init.kaiming_uniform_(self.weight_B, a=math.sqrt(5))
+
+    def forward(self, x):
+        return nn.functional.linear(nn.functional.linear(x, self.weight_A), self.weight_B)
+
+
+class _RotaryBuffers(nn.Module):
+    """Keeps the `rotary_emb.inv_freq` state-dict key of the reference (modeling_llama.py:135-139)."""
+
+    def __init__(self, dim, base=10000.0):
+        super().__init__()
+        self.register_buffer("inv_freq", 1.0 / (base ** (torch.arange(0, dim, 2).float() / dim)))
+
+
+class LibraAttention(nn.Module):
+    def __init__(self, config: LibraConfig):
+        super().__init__()
+        H = config.hidden_size
+        self.hidden_size, self.num_heads = H, config.num_attention_heads
+        self.head_dim = H // self.num_heads
+        self.q_proj = nn.Linear(H, H, bias=False)
+        self.k_proj = nn.Linear(H, H, bias=False)
+        self.v_proj = nn.Linear(H, H, bias=False)
+        self.o_proj = nn.Linear(H, H, bias=False)
+        self.rotary_emb = _RotaryBuffers(self.head_dim)
+        r = config.vision_down_ratio
+        self.vision_q_proj = LibraLinear(H, H, down_ratio=r)
+        self.vision_k_proj = LibraLinear(H, H, down_ratio=r)
+        self.vision_v_proj = LibraLinear(H, H, down_ratio=r)
+        self.vision_o_proj = LibraLinear(H, H, down_ratio=r)
+        self.use_bridge = config.use_bridge
+        if self.use_bridge:
+            self.vision_v_bridge_on_language = LibraLinear(H, H, rank=config.bridge_rank)
+            self.vision_v_bridge_on_vision = LibraLinear(H, H, rank=config.bridge_rank)
+            self.vision_k_bridge_on_language = LibraLinear(H, H, rank=config.bridge_rank)
+            self.vision_k_bridge_on_vision = LibraLinear(H, H, rank=config.bridge_rank)
+
+
+class LibraMLP(nn.Module):
+    def __init__(self, config: LibraConfig):
+        super().__init__()
+        H, I, r = config.hidden_size, config.intermediate_size, config.vision_down_ratio
+        self.gate_proj = nn.Linear(H, I, bias=False)
+        self.down_proj = nn.Linear(I, H, bias=False)
+        self.up_proj = nn.Linear(H, I, bias=False)
+        self.vision_gate_proj = LibraLinear(H, I, down_ratio=r)
+        self.vision_down_proj = LibraLinear(I, H, down_ratio=r)
+        self.vision_up_proj = LibraLinear(H, I, down_ratio=r)
+
+
+class LibraDecoderLayer(nn.Module):
+    """LibraDecoderLayer (modeling_libra.py:416-491) on sorted rows."""
+
+    def __init__(self, config: LibraConfig):
+        super().__init__()
+        self.hidden_size = config.hidden_size
+        self.self_attn = LibraAttention(config)
+        self.mlp = LibraMLP(config)
+        self.input_layernorm = LlamaRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
+        self.post_attention_layernorm = LlamaRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
+        self.vision_input_layernorm = LlamaRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
+        self.vision_post_attention_layernorm = LlamaRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
+
+    def forward(self, h: torch.Tensor, meta: LF.AttnMeta) -> torch.Tensor:
+        """h: [N, C] bf16, sorted rows."""
+        rt = meta.routing
+        nl, flag = rt.n_lang, rt.flag_sorted
+        a, m = self.self_attn, self.mlp
+        eps = self.input_layernorm.variance_epsilon
+        n1 = LF.rmsnorm(h, self.input_layernorm.weight, self.vision_input_layernorm.weight, flag, eps)
+        q = LF.routed_linear(n1, nl, a.q_proj.weight, a.vision_q_proj.weight_A, a.vision_q_proj.weight_B)
+        k = LF.routed_linear(n1, nl, a.k_proj.weight, a.vision_k_proj.weight_A, a.vision_k_proj.weight_B)
+        v = LF.routed_linear(n1, nl, a.v_proj.weight, a.vision_v_proj.weight_A, a.vision_v_proj.weight_B)
+        tk = LF.routed_down(n1, nl, a.vision_k_bridge_on_language.weight_A, a.vision_k_bridge_on_vision.weight_A)
+        tv = LF.routed_down(n1, nl, a.vision_v_bridge_on_language.weight_A, a.vision_v_bridge_on_vision.weight_A)
+        o = LF.bridge_attention(q, k, v, tk, tv, a.vision_k_bridge_on_language.weight_B, a.vision_k_bridge_on_vision.weight_B,
+                                a.vision_v_bridge_on_language.weight_B, a.vision_v_bridge_on_vision.weight_B, meta)
+        h = h + LF.routed_linear(o, nl, a.o_proj.weight, a.vision_o_proj.weight_A, a.vision_o_proj.weight_B)
+        n2 = LF.rmsnorm(h, self.post_attention_layernorm.weight, self.vision_post_attention_layernorm.weight, flag, eps)
+        g = LF.routed_linear(n2, nl, m.gate_proj.weight, m.vision_gate_proj.weight_A, m.vision_gate_proj.weight_B)
+        u = LF.routed_linear(n2, nl, m.up_proj.weight, m.vision_up_proj.weight_A, m.vision_up_proj.weight_B)
+        act = LF.swiglu(g, u)
+        return h + LF.routed_linear(act, nl, m.down_proj.weight, m.vision_down_proj.weight_A, m.vision_down_proj.weight_B)
+
+
+class LibraPreTrainedModel(PreTrainedModel):
+    config_class = LibraConfig
+    base_model_prefix = "model"
+    supports_gradient_checkpointing = True
+    _no_split_modules = ["LibraDecoderLayer"]
+    _skip_keys_device_placement = "past_key_values"
+
+    def _init_weights(self, module):
+        """modeling_libra.py:502-519."""
+        std = self.config.initializer_range
+        if isinstance(module, LibraLinear):
+            module.weight_A.data.normal_(mean=0.0, std=std)
+            if module.rank is not None or self.config.addition_mode:
+                module.weight_B.data.zero_()
+            else:
+                module.weight_B.data.normal_(mean=0.0, std=std)
+        elif isinstance(module, nn.Linear):
+            module.weight.data.normal_(mean=0.0, std=std)
+            if module.bias is not None:
+                module.bias.data.zero_()
+        elif isinstance(module, nn.Embedding):
+            module.weight.data.normal_(mean=0.0, std=std)
+            if module.padding_idx is not None:
+                module.weight.data[module.padding_idx].zero_()
+
+    def _set_gradient_checkpointing(self, module=None, value=False, **kw):
+        for m in self.modules():
+            if isinstance(m, LibraModel):
+                m.gradient_checkpointing = value
+
+    def gradient_checkpointing_enable(self, gradient_checkpointing_kwargs=None):
+        self._set_gradient_checkpointing(value=True)
+
+    def gradient_checkpointing_disable(self):
+        self._set_gradient_checkpointing(value=False)
+
+
+class LibraModel(LibraPreTrainedModel):
+    def __init__(self, config: LibraConfig):
+        super().__init__(config)
+        self.padding_idx = config.pad_token_id
+        self.vocab_size = config.vocab_size
+        H = config.hidden_size
+        self.embed_tokens = nn.Embedding(config.vocab_size, H, self.padding_idx)
+        self.layers = nn.ModuleList([LibraDecoderLayer(config) for _ in range(config.num_hidden_layers)])
+        self.norm = LlamaRMSNorm(H, eps=config.rms_norm_eps)
+        self.vision_vocab_size = config.vision_vocab_size
+        self.vision_codebook_num = config.vision_codebook_num
+        assert H % config.vision_codebook_num == 0
+        self.vision_embed_tokens = nn.ModuleList(
+            [nn.Embedding(config.vision_vocab_size, H // config.vision_codebook_num) for _ in range(config.vision_codebook_num)])
+        self.vision_norm = LlamaRMSNorm(H, eps=config.rms_norm_eps)
+        self.contiguous_signal_size = config.contiguous_signal_size
+        self.vision_contiguous_signal_processor = nn.Linear(config.contiguous_signal_size + H, H, bias=False)
+        self.vision_signal_norm = LlamaRMSNorm(config.contiguous_signal_size + H, eps=config.rms_norm_eps)
+        self.max_vision_token_length = config.max_vision_token_length
+        self.image_feature_resolution = config.image_feature_resolution
+        assert self.image_feature_resolution ** 2 + 2 == self.max_vision_token_length
+        self.gradient_checkpointing = False
+        self._meta_cache = {}
+        self._rope_cache = None
+        self.post_init()
+
+    def get_input_embeddings(self):
+        return self.embed_tokens
+
+    def set_input_embeddings(self, value):
+        self.embed_tokens = value
+
+    # -------------------------------------------------------------- per-batch metadata
+    def _rope_tables(self, n_pos: int, device):
+        c = self._rope_cache
+        if c is None or c[0].shape[0] < n_pos or c[0].device != device:
+            D = self.config.hidden_size // self.config.num_attention_heads
+            inv_freq = 1.0 / (10000.0 ** (torch.arange(0, D, 2, device=device).float() / D))
+            t = torch.arange(max(n_pos, self.config.max_position_embeddings), device=device, dtype=torch.float32)
+            fr = torch.outer(t, inv_freq)
+            # the reference rounds cos/sin to the activation dtype (bf16) before the rotation (modeling_llama.py:161-164)
+            self._rope_cache = c = (fr.cos().to(BF16).float().contiguous(), fr.sin().to(BF16).float().contiguous())
+        return c
+
+    def build_meta(self, vision_flag: torch.Tensor, attention_mask: Optional[torch.Tensor],
+                   position_ids: Optional[torch.Tensor]) -> LF.AttnMeta:
+        """One host round trip per distinct batch layout: routing permutation, attention work lists, key ranges."""
+        B, T = vision_flag.shape
+        dev = vision_flag.device
+        flag_cpu = vision_flag.detach().to("cpu")
+        am_cpu = None if attention_mask is None else attention_mask.detach().to("cpu").to(torch.bool)
+        key = (B, T, flag_cpu.numpy().tobytes(), None if am_cpu is None else am_cpu.numpy().tobytes())
+        hit = self._meta_cache.get(key)
+        if hit is None:
+            kv_start = kv_end = None
+            if am_cpu is not None and not bool(am_cpu.all()):
+                kv_start, kv_end = [], []
+                for b in range(B):
+                    nz = torch.nonzero(am_cpu[b]).flatten()
+                    s, e = (int(nz[0]), int(nz[-1]) + 1) if nz.numel() else (0, 0)
+                    if nz.numel() != e - s:
+                        raise NotImplementedError("attention_mask must be one contiguous run of ones per sample "
+                                                  "(left or right padding)")
+                    kv_start.append(s)
+                    kv_end.append(e)
+            rt_cpu = schedule.build_routing(flag_cpu)
+            rt = schedule.Routing(rt_cpu.n_tokens, rt_cpu.n_lang, rt_cpu.n_vis, rt_cpu.perm.to(dev), rt_cpu.inv.to(dev),
+                                  rt_cpu.flag_sorted.to(dev), rt_cpu.flag_orig.to(dev))
+            work = schedule.build_attn_work(flag_cpu, B, T, True, dev, kv_start, kv_end)
+            hit = (rt, work)
+            if len(self._meta_cache) > 16:
+                self._meta_cache.clear()
+            self._meta_cache[key] = hit
+        rt, work = hit
+        if position_ids is None:
+            pos = torch.arange(T, device=dev, dtype=torch.int32).repeat(B)
+            n_pos = T
+        else:
+            pos = position_ids.to(dev).reshape(-1, T).expand(B, T).reshape(-1).to(torch.int32).contiguous()
+            n_pos = int(pos.max().item()) + 1
+        cos, sin = self._rope_tables(n_pos, dev)
+        H = self.config.num_attention_heads
+        return LF.AttnMeta(rt, work, pos, cos, sin, B, T, H, self.config.hidden_size // H)
+
+    # -------------------------------------------------------------- embeddings (sorted rows)
+    def embed_sorted(self, input_ids: torch.Tensor, meta: LF.AttnMeta, contiguous_signal: Optional[torch.Tensor]):
+        """get_inputs_embeds_from_multicodebook (modeling_libra.py:625-661, :746-748) producing sorted rows."""
+        rt = meta.routing
+        nl = rt.n_lang
+        perm = rt.perm.long()
+        flat = input_ids.reshape(input_ids.shape[0], -1)
+        h_lang = LF.EmbedLang.apply(flat[0][perm[:nl]].contiguous(), self.embed_tokens.weight)
+        if rt.n_vis == 0:
+            return h_lang
+        vis_rows = perm[nl:]
+        ids0 = (flat[0][vis_rows] - self.vocab_size).contiguous()
+        ids1 = (flat[1][vis_rows] - self.vocab_size).contiguous()
+        sig = None
+        if contiguous_signal is not None:
+            sig = contiguous_signal.reshape(-1, contiguous_signal.shape[-1]).to(BF16).contiguous()
+        cat = LF.EmbedVisionCat.apply(ids0, ids1, self.vision_embed_tokens[0].weight, self.vision_embed_tokens[1].weight, sig,
+                                      rt.perm[nl:].contiguous(), self.contiguous_signal_size)
+        cat = LF.rmsnorm(cat, self.vision_signal_norm.weight, None, None, self.vision_signal_norm.variance_epsilon)
+        h_vis = nn.functional.linear(cat, self.vision_contiguous_signal_processor.weight)
+        return torch.cat([h_lang, h_vis], dim=0)
+
+    def forward_sorted(self, input_ids, meta: LF.AttnMeta, contiguous_signal=None, collect_hidden=False):
+        """Returns the final-normed hidden states in sorted rows [N, C] (and per-layer inputs if requested)."""
+        h = self.embed_sorted(input_ids, meta, contiguous_signal)
+        hiddens = [h] if collect_hidden else None
+        for layer in self.layers:
+            if self.gradient_checkpointing and self.training and torch.is_grad_enabled():
+                h = torch.utils.checkpoint.checkpoint(layer, h, meta, use_reentrant=False)
+            else:
+                h = layer(h, meta)
+            if collect_hidden:
+                hiddens.append(h)
+        hn = LF.rmsnorm(h, self.norm.weight, self.vision_norm.weight, meta.routing.flag_sorted, self.norm.variance_epsilon)
+        return hn, hiddens
+
+
+class MultiLMHead(nn.Module):
+    def __init__(self, head_num, input_dim, output_dim):
+        super().__init__()
+        self.heads = nn.ModuleList([nn.Linear(input_dim, output_dim, bias=False) for _ in range(head_num)])
+
+
+class LibraForCausalLM(LibraPreTrainedModel):
+    def __init__(self, config: LibraConfig):
+        super().__init__(config)
+        bad = config.unsupported_branches()
+        if bad:
+            raise NotImplementedError(
+                "libra_b200 implements the reference's default (shipped) configuration; unsupported: " + ", ".join(bad))
+        self.model = LibraModel(config)
+        self.lm_head = nn.Linear(config.hidden_size, config.vocab_size, bias=False)
+        self.vision_codebook_num = config.vision_codebook_num
+        self.vision_lm_head = MultiLMHead(config.vision_codebook_num, config.hidden_size, config.vision_vocab_size)
+        self.max_vision_token_length = config.max_vision_token_length
+        self.image_feature_resolution = config.image_feature_resolution
+        # parameters/buffers the reference registers (kept for state-dict compatibility, :867-882)
+        self.vision_hidden_placeholder = nn.Parameter(torch.empty(config.hidden_size))
+        self.vision_hidden_placeholder.data.normal_(mean=0.0, std=config.initializer_range)
+        self.register_buffer("naive_placeholder", torch.zeros(config.hidden_size))
+        self.register_buffer("vision_logits_placeholder", torch.full([1, config.vision_vocab_size], -float("inf")))
+        self.register_buffer("language_logits_placeholder", torch.full([1, config.vocab_size], -float("inf")))
+        eoi = torch.full([1, 1, 1, config.vocab_size + config.vision_vocab_size], -float("inf"))
+        eoi[:, :, :, config.newline_token_id] = float("inf")
+        self.register_buffer("eoi_to_newline_logits_placeholder", eoi)
+        self.post_init()
+
+    def get_input_embeddings(self):
+        return self.model.embed_tokens
+
+    def set_input_embeddings(self, value):
+        self.model.embed_tokens = value
+
+    def get_output_embeddings(self):
+        return self.lm_head
+
+    def get_decoder(self):
+        return self.model
+
+    # -------------------------------------------------------------- heads
+    def _fused_loss(self, hn, meta, labels):
+        """mean over codebooks of the shifted CE (modeling_libra.py:1159-1174) without materialising [Q,B,T,V+Vv]."""
+        rt = meta.routing
+        nl = rt.n_lang
+        V, Vv, Q = self.config.vocab_size, self.config.vision_vocab_size, self.vision_codebook_num
+        shift = torch.full_like(labels, -100)
+        shift[:, :, :-1] = labels[:, :, 1:]
+        ls = shift.reshape(Q, -1)[:, rt.perm.long()]                      # [Q, N] sorted rows
+        counts = (ls != -100).sum(dim=1).clamp(min=1).to(torch.float32)   # per plane
+        lab_l = ls[0, :nl]
+        bad = ((lab_l >= V) & (lab_l != -100)).any()
+        S_l = LF.head_cross_entropy(hn[:nl], self.lm_head.weight, torch.where(lab_l >= V, -100, lab_l).contiguous())
+        total = 0.0
+        for c in range(Q):
+            lab_v = ls[c, nl:]
+            rel = lab_v - V
+            oob = (lab_v != -100) & ((rel < 0) | (rel >= Vv))
+            bad = bad | oob.any()
+            S_v = LF.head_cross_entropy(hn[nl:], self.vision_lm_head.heads[c].weight,
+                                        torch.where((lab_v == -100) | oob, -100, rel).contiguous()) if rt.n_vis else 0.0
+            total = total + (S_l + S_v) / counts[c]
+        loss = total / Q
+        # a label outside its row's finite vocabulary block hits a -inf logit in the reference => loss = inf
+        return loss + torch.where(bad, float("inf"), 0.0).to(loss.dtype)
+
+    def _materialize_logits(self, hn, meta):
+        """cal_vl_logits (modeling_libra.py:1018-1052): [Q,B,T,V+Vv] with -inf outside the row's block."""
+        rt = meta.routing
+        nl = rt.n_lang
+        V, Vv, Q = self.config.vocab_size, self.config.vision_vocab_size, self.vision_codebook_num
+        out = torch.full((Q, rt.n_tokens, V + Vv), float("-inf"), dtype=hn.dtype, device=hn.device)
+        perm = rt.perm.long()
+        ll = nn.functional.linear(hn[:nl], self.lm_head.weight)
+        for c in range(Q):
+            out[c, perm[:nl], :V] = ll
+            if rt.n_vis:
+                out[c, perm[nl:], V:] = nn.functional.linear(hn[nl:], self.vision_lm_head.heads[c].weight)
+        return out.view(Q, meta.batch, meta.seqlen, V + Vv)
+
+    def forward(
+        self,
+        input_ids: torch.LongTensor = None,
+        attention_mask: Optional[torch.Tensor] = None,
+        position_ids: Optional[torch.LongTensor] = None,
+        past_key_values: Optional[List[torch.FloatTensor]] = None,
+        inputs_embeds: Optional[torch.FloatTensor] = None,
+        labels: Optional[torch.LongTensor] = None,
+        use_cache: Optional[bool] = None,
+        output_attentions: Optional[bool] = None,
+        output_hidden_states: Optional[bool] = None,
+        return_dict: Optional[bool] = None,
+        vision_indices: Optional[torch.LongTensor] = None,
+        contiguous_signal: Optional[torch.Tensor] = None,
+        past_hidden_states: Optional[torch.Tensor] = None,
+        past_vision_flag: Optional[torch.BoolTensor] = None,
+        return_logits: Optional[bool] = None,
+    ) -> Union[Tuple, LibraCausalLMOutputWithPast]:
+        """Same arguments as the reference (modeling_libra.py:1069-1085).  `return_logits` (extra, optional):
+        None = materialise the [Q,B,T,V+Vv] logits unless a training loss is being computed (HF Trainer only reads
+        .loss); True/False force it."""
+        _lib.require_device()
+        if past_key_values is not None or use_cache:
+            raise NotImplementedError("KV-cached decoding is outside the training hot path (SURVEY.md section 8f N1)")
+        if inputs_embeds is not None or output_attentions:
+            raise NotImplementedError("inputs_embeds / output_attentions are not supported by the fused path")
+        if input_ids is None or vision_indices is None:
+            raise ValueError("input_ids [Q,B,T] and vision_indices [B,T] are required")
+        if self.lm_head.weight.dtype != BF16:
+            raise TypeError("libra_b200 computes in bf16: call model.to(torch.bfloat16) as train.py:31-32 does")
+        assert len(input_ids) == self.vision_codebook_num
+        vision_flag = vision_indices < self.max_vision_token_length
+        if not torch.equal(vision_flag, input_ids[0] >= self.config.vocab_size):
+            raise AssertionError("Inconsistent input_ids and vision_flag")
+        meta = self.model.build_meta(vision_flag, attention_mask, position_ids)
+        hn, hiddens = self.model.forward_sorted(input_ids, meta, contiguous_signal, collect_hidden=bool(output_hidden_states))
+
+        training_loss = labels is not None and torch.is_grad_enabled() and self.training
+        want_logits = (not training_loss) if return_logits is None else return_logits
+        loss = None
+        if labels is not None:
+            assert len(labels) == self.vision_codebook_num
+            loss = self._fused_loss(hn, meta, labels.to(hn.device))
+        logits = self._materialize_logits(hn, meta) if want_logits else None
+        hs = None
+        if hiddens is not None:
+            inv = meta.routing.inv.long()
+            C = hn.shape[-1]
+            hs = tuple(t[inv].view(meta.batch, meta.seqlen, C) for t in hiddens[:-1]) + (hn[inv].view(meta.batch, meta.seqlen, C),)
+        if return_dict is False:
+            out = (logits,)
+            return ((loss,) + out) if loss is not None else out
+        return LibraCausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=None, hidden_states=hs,
+                                           attentions=None, past_hidden_states=None, past_vision_flag=None)

@@ -25,6 +25,33 @@ def _st():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# Optional device-side timing of selected kernels (bench.py roofline): name -> list of (start_event, stop_event)
+# recorded on torch's current stream, i.e. the stream the kernel is launched on.
+TIMED = None
+
+
+def enable_timing(names=("lb_attn_fwd", "lb_attn_bwd_dq", "lb_attn_bwd_dkv")):
+    global TIMED
+    TIMED = {n: [] for n in names}
+
+
+def disable_timing():
+    global TIMED
+    t, TIMED = TIMED, None
+    return t
+
+
+def _timed_call(name, *args):
+    if TIMED is not None and name in TIMED:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        _lib.call(name, *args)
+        e.record()
+        TIMED[name].append((s, e))
+    else:
+        _lib.call(name, *args)
+
+
 def _chk(t: torch.Tensor, dtype=None, name="tensor"):
     if not t.is_cuda:
         raise _lib.LibraB200Error(f"{name} must be a CUDA tensor (libra_b200 has no CPU path)")
@@ -219,7 +246,7 @@ def attn_fwd(Q, K0, V0, K1, V1, qflag, work, kv_start, kv_end, out_row, batch, s
     if out is None:
         out = torch.zeros(batch * seqlen, C, dtype=BF16, device=Q.device)
     lse = torch.full((batch, heads, seqlen), float("inf"), dtype=torch.float32, device=Q.device)
-    _lib.call("lb_attn_fwd", _p(Q), _p(K0), _p(V0), _p(K1), _p(V1), _p(qflag), _p(work), work.shape[0], _p(kv_start),
+    _timed_call("lb_attn_fwd", _p(Q), _p(K0), _p(V0), _p(K1), _p(V1), _p(qflag), _p(work), work.shape[0], _p(kv_start),
               _p(kv_end), _p(out_row), _p(out), _p(lse), batch, seqlen, heads, head_dim, int(causal), float(scale), _st())
     return out, lse
 
@@ -235,7 +262,7 @@ def attn_bwd_prepare(O, dO, row_of, batch, seqlen, heads, head_dim, want_dO_orig
 def attn_bwd_dq(Q, K0, V0, K1, V1, dO, lse, delta, qflag, work, kv_start, kv_end, batch, seqlen, heads, head_dim, causal,
                 scale):
     dQ = torch.zeros_like(Q)
-    _lib.call("lb_attn_bwd_dq", _p(Q), _p(K0), _p(V0), _p(K1), _p(V1), _p(dO), _p(lse), _p(delta), _p(qflag), _p(work),
+    _timed_call("lb_attn_bwd_dq", _p(Q), _p(K0), _p(V0), _p(K1), _p(V1), _p(dO), _p(lse), _p(delta), _p(qflag), _p(work),
               work.shape[0], _p(kv_start), _p(kv_end), _p(dQ), batch, seqlen, heads, head_dim, int(causal), float(scale),
               _st())
     return dQ
@@ -246,7 +273,7 @@ def attn_bwd_dkv(Q, K0, V0, K1, V1, dO, lse, delta, qflag, qtile_has, work_kv, k
     dK0, dV0 = torch.zeros_like(K0), torch.zeros_like(V0)
     dK1 = torch.zeros_like(K0) if two_variants else None
     dV1 = torch.zeros_like(V0) if two_variants else None
-    _lib.call("lb_attn_bwd_dkv", _p(Q), _p(K0), _p(V0), _p(K1), _p(V1), _p(dO), _p(lse), _p(delta), _p(qflag),
+    _timed_call("lb_attn_bwd_dkv", _p(Q), _p(K0), _p(V0), _p(K1), _p(V1), _p(dO), _p(lse), _p(delta), _p(qflag),
               _p(qtile_has), _p(work_kv), work_kv.shape[0], _p(kv_start), _p(kv_end), _p(dK0), _p(dV0), _p(dK1), _p(dV1), batch, seqlen,
               heads, head_dim, int(causal), float(scale), _st())
     return dK0, dV0, dK1, dV1

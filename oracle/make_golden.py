@@ -21,7 +21,7 @@ from oracle import refshim
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
-TINY_LIBRA = dict(hidden_size=64, intermediate_size=176, num_hidden_layers=2, num_attention_heads=4,
+TINY_LIBRA = dict(hidden_size=128, intermediate_size=352, num_hidden_layers=2, num_attention_heads=1,
                   vocab_size=320, contiguous_signal_size=32, max_position_embeddings=2048)
 ATTN_HD128 = dict(hidden_size=256, intermediate_size=352, num_hidden_layers=1, num_attention_heads=2,
                   vocab_size=320, contiguous_signal_size=32, max_position_embeddings=2048)

@@ -1,0 +1,147 @@
+"""End-to-end LibraForCausalLM (CUDA path, bf16) vs the fixture produced by the REFERENCE in fp32
+(tests/golden/decoder_tiny.pt) and vs the oracle on other layouts.
+
+Tolerances: the model runs in bf16 like the reference's training dtype; BASELINE.md asks logits within 1e-3 rel of the
+reference *measured against fp32 with the bf16 reference's own distance as the noise floor*.  We therefore assert
+  err(ours_bf16, ref_fp32) <= 1.5 * err(oracle_bf16, ref_fp32) + small
+on relative Frobenius errors, plus absolute caps."""
+import pytest
+import torch
+
+from gpu_util import need_gpu, rel_err
+from oracle import libra_oracle as O
+
+pytestmark = pytest.mark.gpu
+dev = "cuda"
+
+
+def build(g):
+    from libra_b200.models import LibraConfig, LibraForCausalLM
+    model = LibraForCausalLM(LibraConfig(**g["config"]))
+    model.load_state_dict(g["state_dict"], strict=False)
+    return model.to(torch.bfloat16).to(dev)
+
+
+def oracle_bf16(g, inp, labels=True):
+    sd = {k: (v.to(dev).bfloat16() if v.is_floating_point() else v.to(dev)) for k, v in g["state_dict"].items()}
+    d = O.LibraDims.from_config(g["config"])
+    return O.libra_forward(sd, d, inp["input_ids"].to(dev), inp["vision_indices"].to(dev),
+                           attention_mask=inp["attention_mask"].to(dev),
+                           contiguous_signal=inp["contiguous_signal"].to(dev).bfloat16(),
+                           labels=inp["labels"].to(dev) if labels else None, return_hidden=True)
+
+
+def test_forward_logits_and_loss_vs_reference_golden(golden):
+    need_gpu()
+    g = golden("decoder_tiny")
+    inp = g["inputs"]
+    model = build(g).eval()
+    with torch.no_grad():
+        out = model(input_ids=inp["input_ids"].to(dev), attention_mask=inp["attention_mask"].to(dev),
+                    vision_indices=inp["vision_indices"].to(dev), contiguous_signal=inp["contiguous_signal"].to(dev),
+                    labels=inp["labels"].to(dev), output_hidden_states=True)
+        orc = oracle_bf16(g, inp)
+    assert out.logits.shape == (2, 2, inp["input_ids"].shape[2], 320 + 514)
+    sel = g["logits_positions"].to(dev)
+    want = g["logits_at"].to(dev)
+    got = out.logits[:, :, sel].float()
+    fin = torch.isfinite(want)
+    assert torch.equal(fin, torch.isfinite(got)), "the -inf placeholder pattern must match the reference"
+    valid = inp["attention_mask"].to(dev)[:, sel].bool()[None, :, :, None].expand_as(fin) & fin
+    e_ours = rel_err(got[valid], want[valid])
+    e_orc = rel_err(orc["logits"][:, :, sel].float()[valid], want[valid])
+    assert e_ours <= 1.5 * e_orc + 5e-3, (e_ours, e_orc)
+    assert abs(float(out.loss) - float(g["loss"])) <= 1.5 * abs(float(orc["loss"]) - float(g["loss"])) + 2e-2
+    # hidden states: [B,T,C] in original order
+    h1 = out.hidden_states[1].float()
+    m = inp["attention_mask"].to(dev).bool()
+    assert rel_err(h1[m], g["hidden_after_layer0"].to(dev)[m]) <= 1.5 * rel_err(orc["hidden_states"][1].float()[m], g["hidden_after_layer0"].to(dev)[m]) + 5e-3
+    lse = torch.logsumexp(out.logits.float(), -1)
+    mm = m[None].expand_as(lse)
+    assert rel_err(lse[mm], g["logits_lse"].to(dev)[mm]) < 2e-2
+
+
+def test_training_step_gradients_vs_reference_golden(golden):
+    need_gpu()
+    g = golden("decoder_tiny")
+    inp = g["inputs"]
+    model = build(g).train()
+    out = model(input_ids=inp["input_ids"].to(dev), attention_mask=inp["attention_mask"].to(dev),
+                vision_indices=inp["vision_indices"].to(dev), contiguous_signal=inp["contiguous_signal"].to(dev),
+                labels=inp["labels"].to(dev))
+    assert out.logits is None            # fused loss: the 4.3 GB logits tensor is not materialised in training
+    assert abs(float(out.loss) - float(g["loss"])) < 5e-2
+    out.loss.backward()
+    params = dict(model.named_parameters())
+    # noise floor: the oracle in bf16 with autograd
+    sd = {k: (v.to(dev).bfloat16().requires_grad_(True) if v.is_floating_point() else v.to(dev)) for k, v in g["state_dict"].items()}
+    d = O.LibraDims.from_config(g["config"])
+    o = O.libra_forward(sd, d, inp["input_ids"].to(dev), inp["vision_indices"].to(dev), attention_mask=inp["attention_mask"].to(dev),
+                        contiguous_signal=inp["contiguous_signal"].to(dev).bfloat16(), labels=inp["labels"].to(dev))
+    o["loss"].backward()
+    worst = 0.0
+    for n, want in g["grads"].items():
+        want = want.to(dev)
+        assert params[n].grad is not None, n
+        e_ours = rel_err(params[n].grad, want)
+        e_orc = rel_err(sd[n].grad, want)
+        worst = max(worst, e_ours)
+        assert e_ours <= 2.0 * e_orc + 3e-2, (n, e_ours, e_orc)
+    assert worst < 0.15
+
+
+def test_gradient_checkpointing_and_frozen_language(golden):
+    need_gpu()
+    g = golden("decoder_tiny")
+    inp = {k: v.to(dev) for k, v in g["inputs"].items()}
+    m1, m2 = build(g).train(), build(g).train()
+    m2.gradient_checkpointing_enable()
+    for m in (m1, m2):       # frozen_language: only parameters whose name contains "vision" train (modeling_libra.py:1342-1346)
+        for n, p in m.named_parameters():
+            p.requires_grad = "vision" in n
+    kw = dict(input_ids=inp["input_ids"], attention_mask=inp["attention_mask"], vision_indices=inp["vision_indices"],
+              contiguous_signal=inp["contiguous_signal"], labels=inp["labels"])
+    l1, l2 = m1(**kw).loss, m2(**kw).loss
+    assert float(l1) == float(l2)
+    l1.backward(); l2.backward()
+    for (n, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        if "vision" in n:
+            assert p1.grad is not None and torch.equal(p1.grad, p2.grad), n      # recompute is bit-identical (deterministic kernels)
+        else:
+            assert p1.grad is None
+
+
+def test_other_layouts_vs_oracle(golden):
+    """two images per sample + left padding + explicit position ids, against the oracle in bf16 on the GPU."""
+    need_gpu()
+    from oracle.make_golden import make_libra_inputs
+    g = golden("decoder_tiny")
+    model = build(g).eval()
+    cfg = g["config"]
+    inp = make_libra_inputs(cfg["vocab_size"], cfg["contiguous_signal_size"], B=2, n_text=30, pad_last=11, seed=77, images_per_sample=2)
+    with torch.no_grad():
+        out = model(input_ids=inp["input_ids"].to(dev), attention_mask=inp["attention_mask"].to(dev),
+                    vision_indices=inp["vision_indices"].to(dev), contiguous_signal=inp["contiguous_signal"].to(dev),
+                    labels=inp["labels"].to(dev))
+        orc = oracle_bf16(g, inp)
+        sd32 = {k: v.to(dev) for k, v in g["state_dict"].items()}
+        o32 = O.libra_forward(sd32, O.LibraDims.from_config(cfg), inp["input_ids"].to(dev), inp["vision_indices"].to(dev),
+                              attention_mask=inp["attention_mask"].to(dev), contiguous_signal=inp["contiguous_signal"].to(dev),
+                              labels=inp["labels"].to(dev))
+    m = inp["attention_mask"].to(dev).bool()[None, :, :, None]
+    fin = torch.isfinite(o32["logits"]) & m
+    e_ours = rel_err(out.logits.float()[fin], o32["logits"][fin])
+    e_orc = rel_err(orc["logits"].float()[fin], o32["logits"][fin])
+    assert e_ours <= 1.5 * e_orc + 5e-3, (e_ours, e_orc)
+    assert abs(float(out.loss) - float(o32["loss"])) < 5e-2
+
+
+def test_mislabelled_targets_give_inf_like_the_reference(golden):
+    need_gpu()
+    g = golden("decoder_tiny")
+    inp = {k: v.to(dev) for k, v in g["inputs"].items()}
+    labels = g["inputs"]["input_ids"].clone().to(dev)      # raw next-token labels: BOI after text is a vision id on a language row
+    model = build(g).train()
+    out = model(input_ids=inp["input_ids"], attention_mask=inp["attention_mask"], vision_indices=inp["vision_indices"],
+                contiguous_signal=inp["contiguous_signal"], labels=labels)
+    assert torch.isinf(out.loss)
