@@ -183,10 +183,12 @@ int lb_gemm_bf16(const void* A, const void* B, void* C, const void* bias, int64_
                  int64_t ldb, int64_t ldc, int trans_a, int trans_b, int out_dtype, int accumulate, int act,
                  void* stream);
 
-/* ---- A1 patch embedding (im2col-free) --------------------------------------
- * libra/models/clip/modeling_clip.py:193-228.  pixels [B,3,S,S] bf16, weight [C, 3*P*P] bf16 (conv weight
- * flattened), class_emb [C], pos_emb [(S/P)^2+1, C]; writes emb [B, (S/P)^2+1, C] = cat(cls, conv) + pos. */
-int lb_patch_embed_fwd(const void* pixels, const void* weight, const void* class_emb, const void* pos_emb, void* emb,
+/* ---- A1 patch embedding (im2col-free, TMA-staged) ----------------------------
+ * libra/models/clip/modeling_clip.py:193-228.  pixels [B,3,S,S] bf16 (NCHW), class_emb [C], pos_emb [(S/14)^2+1, C];
+ * writes emb [B, (S/14)^2+1, C] = cat(cls, conv14x14/s14(pixels)) + pos.  The conv weight [C,3,14,14] is K-packed
+ * once into [C, 768] (3 channels x 4 kernel-row groups x 64, zero padded) by lb_patch_embed_pack_weight. */
+int lb_patch_embed_pack_weight(const void* weight, void* packed, int channels_out, int patch, void* stream);
+int lb_patch_embed_fwd(const void* pixels, const void* weight_packed, const void* class_emb, const void* pos_emb, void* emb,
                        int batch, int image_size, int patch, int channels_out, void* stream);
 
 /* ---- A18 routed heads: fused cross-entropy over a logits block -------------

@@ -446,6 +446,9 @@ __global__ void __launch_bounds__(256) cross_entropy_kernel(__nv_bfloat16* __res
     const bool vec = ((ld & 7) == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
     const int nvec = vec ? (vocab >> 3) : 0;
     float m = -CUDART_INF_F, s = 0.f;
+    // read the target logit BEFORE any thread overwrites the row with its gradient (the block-wide reduction below
+    // orders this read against those writes)
+    const float x_label = (label >= 0) ? __bfloat162float(row[label]) : 0.f;
     if (label >= 0) {     // ignored rows only need a zero gradient
         for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
             float f[8];
@@ -487,7 +490,7 @@ __global__ void __launch_bounds__(256) cross_entropy_kernel(__nv_bfloat16* __res
         s = gs;
     }
     const float lse = m + __logf(s);
-    if (threadIdx.x == 0) row_loss[r] = (label >= 0) ? (lse - __bfloat162float(row[label])) : 0.f;
+    if (threadIdx.x == 0) row_loss[r] = (label >= 0) ? (lse - x_label) : 0.f;
     const float inv = (label >= 0) ? grad_scale / s : 0.f;
     for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
         float f[8];

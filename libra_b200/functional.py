@@ -255,29 +255,30 @@ def bridge_attention(q, k, v, tk, tv, Bk_l, Bk_v, Bv_l, Bv_v, meta: AttnMeta):
 
 class PlainAttention(torch.autograd.Function):
     """Non-causal self-attention over [B*T, H*D] (CLIPAttention core, modeling_clip.py:309-349).
-    q must already carry the head_dim**-0.5 scale (the reference scales q before the matmul)."""
+    `scale` multiplies q.k^T inside the kernel (the reference pre-multiplies q by head_dim**-0.5, :299)."""
 
     @staticmethod
-    def forward(ctx, q, k, v, work: AttnWork, batch, seqlen, heads, head_dim):
+    def forward(ctx, q, k, v, work: AttnWork, batch, seqlen, heads, head_dim, scale):
         o, lse = ops.attn_fwd(q, k, v, None, None, None, work.work_q, None, None, None, batch, seqlen, heads, head_dim, False,
-                              1.0)
-        ctx.args = (work, batch, seqlen, heads, head_dim)
+                              scale)
+        ctx.args = (work, batch, seqlen, heads, head_dim, scale)
         ctx.save_for_backward(q, k, v, o, lse)
         return o
 
     @staticmethod
     def backward(ctx, do):
-        work, B, T, H, D = ctx.args
+        work, B, T, H, D, scale = ctx.args
         q, k, v, o, lse = ctx.saved_tensors
-        dO, delta = ops.attn_bwd_prepare(o, do.contiguous(), None, B, T, H, D)
-        dq = ops.attn_bwd_dq(q, k, v, None, None, dO, lse, delta, None, work.work_q, None, None, B, T, H, D, False, 1.0)
+        dO, delta = ops.attn_bwd_prepare(o, do.contiguous(), None, B, T, H, D, want_dO_orig=False)
+        dO = do.contiguous()
+        dq = ops.attn_bwd_dq(q, k, v, None, None, dO, lse, delta, None, work.work_q, None, None, B, T, H, D, False, scale)
         dk, dv, _, _ = ops.attn_bwd_dkv(q, k, v, None, None, dO, lse, delta, None, work.qtile_has, work.work_kv, None, None, B,
-                                        T, H, D, False, 1.0, two_variants=False)
-        return dq, dk, dv, None, None, None, None, None
+                                        T, H, D, False, scale, two_variants=False)
+        return dq, dk, dv, None, None, None, None, None, None
 
 
-def plain_attention(q, k, v, work, batch, seqlen, heads, head_dim):
-    return PlainAttention.apply(q, k, v, work, batch, seqlen, heads, head_dim)
+def plain_attention(q, k, v, work, batch, seqlen, heads, head_dim, scale=1.0):
+    return PlainAttention.apply(q.contiguous(), k.contiguous(), v.contiguous(), work, batch, seqlen, heads, head_dim, scale)
 
 
 # ----------------------------------------------------------------------------- embeddings

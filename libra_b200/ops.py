@@ -210,6 +210,25 @@ def gemm(a, b, trans_a=False, trans_b=False, out=None, out_dtype=BF16, bias=None
     return out
 
 
+def patch_embed_pack_weight(weight):
+    """conv weight [C,3,14,14] (bf16) -> K-packed [C,768]."""
+    C = weight.shape[0]
+    packed = torch.empty(C, 768, dtype=BF16, device=weight.device)
+    _lib.call("lb_patch_embed_pack_weight", _p(weight.contiguous()), _p(packed), C, weight.shape[-1], _st())
+    return packed
+
+
+def patch_embed_fwd(pixels, weight_packed, class_emb, pos_emb, patch=14):
+    """pixels [B,3,S,S] bf16 -> embeddings [B, (S/patch)^2+1, C] (class token + position embedding added)."""
+    _chk(pixels, BF16, "pixels")
+    B, _, S, _ = pixels.shape
+    C = weight_packed.shape[0]
+    G = S // patch
+    emb = torch.empty(B, G * G + 1, C, dtype=BF16, device=pixels.device)
+    _lib.call("lb_patch_embed_fwd", _p(pixels), _p(weight_packed), _p(class_emb), _p(pos_emb), _p(emb), B, S, patch, C, _st())
+    return emb
+
+
 def probe_umma(mode, a, b):
     K = a.shape[1]
     d = torch.empty(128, 128, dtype=torch.float32, device=a.device)

@@ -33,6 +33,7 @@ for s in $suites; do
       ;;
     attn_bwd) run attn_bwd 600 tests/test_gpu_attention.py -k "backward" ;;
     model) run model 900 tests/test_gpu_model.py ;;
+    vision) run vision 600 tests/test_gpu_vision.py ;;
     all) run all 1800 tests ;;
   esac
 done
