@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--tiny", action="store_true", help="tiny model for plumbing checks (NOT a bench value)")
+    ap.add_argument("--cuda-profiler-range", action="store_true",
+                    help="bracket the timed region with cudaProfilerStart/Stop (use with ncu --profile-from-start off)")
     return ap.parse_args()
 
 
@@ -212,13 +214,23 @@ def main():
             p.requires_grad = "vision" in n
     params = [p for p in model.parameters() if p.requires_grad]
     n_train = sum(p.numel() for p in params)
-    # one flat bf16 gradient buffer; every .grad is a view into it (a single NCCL all-reduce per step)
+    # Flat storage: one bf16 buffer for the trainable weights and one for their gradients; every parameter (and its
+    # .grad) is a view.  => a single NCCL all-reduce per step and a single-tensor fused AdamW launch.
+    flat_w = torch.empty(n_train, dtype=torch.bfloat16, device=dev)
     flat = torch.zeros(n_train, dtype=torch.bfloat16, device=dev)
     off = 0
-    for p in params:
-        p.grad = flat[off:off + p.numel()].view_as(p)
-        off += p.numel()
-    opt = torch.optim.AdamW(params, lr=1e-5, betas=(0.9, 0.95), weight_decay=0.0, fused=True) if args.optimizer == "adamw" else None
+    with torch.no_grad():
+        for p in params:
+            n = p.numel()
+            flat_w[off:off + n].copy_(p.reshape(-1))
+            p.data = flat_w[off:off + n].view_as(p)
+            p.grad = flat[off:off + n].view_as(p)
+            off += n
+    opt = None
+    if args.optimizer == "adamw":
+        master = torch.nn.Parameter(flat_w)
+        master.grad = flat
+        opt = torch.optim.AdamW([master], lr=1e-5, betas=(0.9, 0.95), weight_decay=0.0, fused=True)
 
     B, T, MB = args.batch, args.seq, args.micro_batch
     assert B % MB == 0
@@ -275,9 +287,12 @@ def main():
     _lib.reset_launch_counts()
     ops.enable_timing()
     sampler = ClockSampler(local) if rank == 0 else None
-    torch.cuda.nvtx.range_push("timed")
+    if args.cuda_profiler_range:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
     ms, last_loss = timed(args.steps, False)
-    torch.cuda.nvtx.range_pop()
+    if args.cuda_profiler_range:
+        torch.cuda.profiler.stop()
     clocks = sampler.stop() if sampler else None
     kt = ops.disable_timing()
     launches = _lib.total_launches()

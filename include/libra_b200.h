@@ -118,19 +118,19 @@ int lb_lfq_pack(const void* h, int dtype, int64_t n_img, int tokens, int num_cod
 int lb_lfq_unpack(const int64_t* idx, int64_t n, int num_codebooks, int bits, void* codes, int dtype, void* stream);
 
 /* ---- A12 + A10(bridge operands) attention prologue ------------------------
- * libra/models/libra/modeling_libra.py:318-340 (bridge add, RoPE on q and both key variants),
- * :282-286 (value variants).  Inputs in sorted rows; outputs in ORIGINAL token order [B*T, H*D]:
+ * libra/models/libra/modeling_libra.py:320-340 (RoPE on q and both key variants, variant selection per key modality),
+ * :282-286 (value variants).  Inputs in sorted rows [N, H*D]; kc = k + kb and vc = v + vb are the bridged ("cross")
+ * tensors (the rank-r bridge products are plain GEMMs with beta = 1 done by the caller; NULL = no bridge).
+ * Outputs in ORIGINAL token order [B*T, H*D]:
  *   Q    = rope(q)
- *   Kfv  = rope(k + [lang j] kb)   Vfv = v + [lang j] vb      (what VISION queries see)
- *   Kfl  = rope(k + [vis  j] kb)   Vfl = v + [vis  j] vb      (what LANGUAGE queries see)
- * with kb_j = tk_j . Bk[m_j]^T, vb_j = tv_j . Bv[m_j]^T (rank-R bridge, R <= 16).
- * sorted_of[bt] = sorted row of original token bt; pos[bt] = rotary position;
- * cos/sin: fp32 tables [n_pos, D/2].  flag_sorted[r] = 1 for vision rows. */
-int lb_attn_prep_fwd(const void* q, const void* k, const void* v, const void* tk, const void* tv, const void* Bk_lang,
-                     const void* Bk_vis, const void* Bv_lang, const void* Bv_vis, const uint8_t* flag_sorted,
-                     const int32_t* sorted_of, const int32_t* pos, const float* cos_t, const float* sin_t, void* Q,
-                     void* Kfv, void* Kfl, void* Vfv, void* Vfl, int64_t n_tokens, int heads, int head_dim, int rank,
-                     void* stream);
+ *   Kfv  = rope(lang j ? kc : k)    Vfv = lang j ? vc : v      (what VISION queries see)
+ *   Kfl  = rope(vis  j ? kc : k)    Vfl = vis  j ? vc : v      (what LANGUAGE queries see)
+ * sorted_of[bt] = sorted row of original token bt; pos[bt] = rotary position; cos/sin: fp32 tables [n_pos, D/2];
+ * flag_sorted[r] = 1 for vision rows. */
+int lb_attn_prep_fwd(const void* q, const void* k, const void* kc, const void* v, const void* vc,
+                     const uint8_t* flag_sorted, const int32_t* sorted_of, const int32_t* pos, const float* cos_t,
+                     const float* sin_t, void* Q, void* Kfv, void* Kfl, void* Vfv, void* Vfl, int64_t n_tokens, int heads,
+                     int head_dim, void* stream);
 /* adjoint: from dQ,dKfv,dKfl,dVfv,dVfl (original order) to dq,dk,dv,dkb,dvb (sorted rows, [N,H*D]) */
 int lb_attn_prep_bwd(const void* dQ, const void* dKfv, const void* dKfl, const void* dVfv, const void* dVfl,
                      const uint8_t* flag_sorted, const int32_t* sorted_of, const int32_t* pos, const float* cos_t,

@@ -14,7 +14,10 @@
 
 namespace lb {
 
-constexpr int BW_THREADS = 192;
+constexpr int BW_COMPUTE_WARPS = 8;              // two warpgroups, each owns half of the score columns of a tile
+constexpr int BW_COMPUTE_THREADS = BW_COMPUTE_WARPS * 32;
+constexpr int BW_WARP_TMA = BW_COMPUTE_WARPS, BW_WARP_MMA = BW_COMPUTE_WARPS + 1;
+constexpr int BW_THREADS = (BW_COMPUTE_WARPS + 2) * 32;
 constexpr float LOG2E_F = 1.4426950408889634f;
 
 struct AttnBwdParams {
@@ -82,10 +85,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     constexpr uint32_t TMEM_COLS = 256, COL_S = 0, COL_DP = 64, COL_DQ = 128;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < DQ_NBAR; ++i) mbar_init(bars + i, i == DQ_DS ? 128 : 1);
+        for (int i = 0; i < DQ_NBAR; ++i) mbar_init(bars + i, i == DQ_DS ? BW_COMPUTE_THREADS : 1);
         fence_barrier_init();
     }
-    if (warp == 5) {
+    if (warp == BW_WARP_MMA) {
         tmem_alloc(tmem_slot, TMEM_COLS);
         tmem_relinquish();
     }
@@ -94,7 +97,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 4) {
+    if (warp == BW_WARP_TMA) {
         if (elect_one() && n_tiles > 0) {
             const CUtensorMap* tK = variant ? &tmK1 : &tmK0;
             const CUtensorMap* tV = variant ? &tmV1 : &tmV0;
@@ -118,7 +121,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 for (int c = 0; c < D / 64; ++c) tma_load_2d(sV + c * (BN * 128), tV, bars + DQ_VFULL, h * D + c * 64, row_k);
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == BW_WARP_MMA) {
         if (elect_one() && n_tiles > 0) {
             constexpr uint32_t idesc_s = make_idesc_bf16(128, BN, 0, 0);
             constexpr uint32_t idesc_dq = make_idesc_bf16(128, D, 0, 1);
@@ -147,17 +150,20 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 mbar_wait(bars + DQ_DS, ph);
                 tc_fence_after_sync();
 #pragma unroll
-                for (int kk = 0; kk < BN / 16; ++kk)
-                    umma_ts(tmem_base + COL_DQ, tmem_base + COL_S + kk * 8, desc_mnmajor(aK + kk * 2048, BN * 128), idesc_dq,
-                            (it | kk) ? 1u : 0u);
+                for (int kk = 0; kk < BN / 16; ++kk)     // dS of keys 16kk.. lives at column 32*(kk/2) + 8*(kk%2)
+                    umma_ts(tmem_base + COL_DQ, tmem_base + COL_S + (uint32_t)(kk / 2) * 32 + (uint32_t)(kk % 2) * 8,
+                            desc_mnmajor(aK + kk * 2048, BN * 128), idesc_dq, (it | kk) ? 1u : 0u);
                 tc_commit(bars + DQ_KEMPTY);
                 tc_commit(bars + DQ_READY);
             }
         }
     } else {
-        const int r = threadIdx.x;
+        // ---------------- compute warps: dS = P * (dP - delta) * scale for my 32 of the tile's 64 key columns
+        const int half = warp >> 2;
+        const int r = (warp & 3) * 32 + (threadIdx.x & 31);
         const int qi = q0 + r;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        const uint32_t colS = COL_S + half * 32, colDP = COL_DP + half * 32;      // my dS (bf16) goes to [colS, colS+16)
         const float sl2 = p.scale * LOG2E_F;
         const int64_t stat_idx = ((int64_t)b * p.heads + h) * T + (qi < T ? qi : 0);
         const bool row_ok = (qi < T) && (!p.qflag || (int)p.qflag[(int64_t)b * T + (qi < T ? qi : 0)] == variant);
@@ -165,23 +171,23 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const float dlt = row_ok ? p.delta[stat_idx] : 0.f;
         for (int it = 0; it < n_tiles; ++it) {
             const uint32_t ph = (uint32_t)it & 1u;
-            const int kv0 = (first_tile + it) * BN;
-            const bool need_mask = (CAUSAL && kv0 + BN - 1 > q0) || (kv0 + BN > kve) || (kv0 < kvs);
+            const int kv0 = (first_tile + it) * BN + half * 32;
+            const bool need_mask = (CAUSAL && kv0 + 31 > q0) || (kv0 + 32 > kve) || (kv0 < kvs);
             mbar_wait(bars + DQ_SDP, ph);
             tc_fence_after_sync();
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t s[32], dp[32];
-                tmem_ld32(lane_addr + COL_S + c * 32, s);
-                tmem_ld32(lane_addr + COL_DP + c * 32, dp);
-                tc_wait_ld();
-                uint32_t pk[16];
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    float p0 = exp2f(__uint_as_float(s[j]) * sl2 - lse2);
-                    float p1 = exp2f(__uint_as_float(s[j + 1]) * sl2 - lse2);
+            for (int c = 0; c < 2; ++c) {
+                uint32_t s[16], dp[16];
+                tmem_ld16(lane_addr + colS + c * 16, s);
+                tmem_ld16(lane_addr + colDP + c * 16, dp);
+                tc_wait_ld();
+                uint32_t pk[8];
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                    float p0 = fast_ex2(fmaf(__uint_as_float(s[j]), sl2, -lse2));
+                    float p1 = fast_ex2(fmaf(__uint_as_float(s[j + 1]), sl2, -lse2));
                     if (need_mask) {
-                        const int kj = kv0 + c * 32 + j;
+                        const int kj = kv0 + c * 16 + j;
                         p0 = ((!CAUSAL || kj <= qi) && kj < kve && kj >= kvs) ? p0 : 0.f;
                         p1 = ((!CAUSAL || kj + 1 <= qi) && kj + 1 < kve && kj + 1 >= kvs) ? p1 : 0.f;
                     }
@@ -189,7 +195,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     const float d1 = p1 * (__uint_as_float(dp[j + 1]) - dlt) * p.scale;
                     pk[j >> 1] = pack_bf16(d0, d1);
                 }
-                tmem_st16(lane_addr + COL_S + c * 16, pk);     // dS (bf16) over S: chunk c of S is consumed, see fwd
+                tmem_st8(lane_addr + colS + c * 8, pk);       // dS (bf16) over my own, already consumed S columns
             }
             tc_wait_st();
             tc_fence_before_sync();
@@ -199,12 +205,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             mbar_wait(bars + DQ_READY, (uint32_t)(n_tiles - 1) & 1u);
             tc_fence_after_sync();
         }
-        __nv_bfloat16* orow = p.out0 + ((int64_t)b * T + (qi < T ? qi : 0)) * ((int64_t)p.heads * D) + (int64_t)h * D;
+        constexpr int DH = D / 2;
+        __nv_bfloat16* orow = p.out0 + ((int64_t)b * T + (qi < T ? qi : 0)) * ((int64_t)p.heads * D) + (int64_t)h * D + half * DH;
 #pragma unroll 1
-        for (int c = 0; c < D / 32; ++c) {
+        for (int c = 0; c < DH / 32; ++c) {
             uint32_t v[32];
             if (n_tiles > 0) {
-                tmem_ld32(lane_addr + COL_DQ + c * 32, v);
+                tmem_ld32(lane_addr + COL_DQ + half * DH + c * 32, v);
                 tc_wait_ld();
             } else {
 #pragma unroll
@@ -226,7 +233,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc_fence_before_sync();
     }
     __syncthreads();
-    if (warp == 5) {
+    if (warp == BW_WARP_MMA) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
@@ -286,10 +293,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     };
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < KV_NBAR; ++i) mbar_init(bars + i, i == KV_PDS ? 128 : 1);
+        for (int i = 0; i < KV_NBAR; ++i) mbar_init(bars + i, i == KV_PDS ? BW_COMPUTE_THREADS : 1);
         fence_barrier_init();
     }
-    if (warp == 5) {
+    if (warp == BW_WARP_MMA) {
         tmem_alloc(tmem_slot, TMEM_COLS);
         tmem_relinquish();
     }
@@ -308,7 +315,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t tmem_base = *tmem_slot;
     const int n_tiles = s_ntiles;
 
-    if (warp == 4) {
+    if (warp == BW_WARP_TMA) {
         if (elect_one() && n_tiles > 0) {
             const CUtensorMap* tK = variant ? &tmK1 : &tmK0;
             const CUtensorMap* tV = variant ? &tmV1 : &tmV0;
@@ -334,7 +341,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == BW_WARP_MMA) {
         if (elect_one() && n_tiles > 0) {
             constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
             constexpr uint32_t idesc_g = make_idesc_bf16(128, D, 0, 1);
@@ -362,61 +369,74 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 mbar_wait(bars + KV_PDS, ph);
                 tc_fence_after_sync();
 #pragma unroll
-                for (int kk = 0; kk < 128 / 16; ++kk)
-                    umma_ts(tmem_base + COL_DV, tmem_base + COL_S + kk * 8, desc_mnmajor(adO + kk * 2048, 128 * 128), idesc_g,
-                            (it | kk) ? 1u : 0u);
+                for (int kk = 0; kk < 128 / 16; ++kk)    // P^T of queries 16kk.. lives at column 64*(kk/4) + 8*(kk%4)
+                    umma_ts(tmem_base + COL_DV, tmem_base + COL_S + (uint32_t)(kk / 4) * 64 + (uint32_t)(kk % 4) * 8,
+                            desc_mnmajor(adO + kk * 2048, 128 * 128), idesc_g, (it | kk) ? 1u : 0u);
 #pragma unroll
                 for (int kk = 0; kk < 128 / 16; ++kk)
-                    umma_ts(tmem_base + COL_DK, tmem_base + COL_DP + kk * 8, desc_mnmajor(aQ + kk * 2048, 128 * 128), idesc_g,
-                            (it | kk) ? 1u : 0u);
+                    umma_ts(tmem_base + COL_DK, tmem_base + COL_DP + (uint32_t)(kk / 4) * 64 + (uint32_t)(kk % 4) * 8,
+                            desc_mnmajor(aQ + kk * 2048, 128 * 128), idesc_g, (it | kk) ? 1u : 0u);
                 tc_commit(bars + KV_QEMPTY0 + st);
             }
             tc_commit(bars + KV_DONE);
         }
     } else {
-        const int r = threadIdx.x;               // kv row in tile == TMEM lane
+        // ---------------- compute warps: thread <-> kv row (TMEM lane); warpgroup `half` owns 64 of the 128 query columns
+        const int half = warp >> 2;
+        const int r = (warp & 3) * 32 + (threadIdx.x & 31);
         const int kj = kv0 + r;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        const uint32_t colS = COL_S + half * 64, colDP = COL_DP + half * 64;
         const float sl2 = p.scale * LOG2E_F;
         const bool key_ok = kj < kve && kj >= kvs;
+        const int tid = threadIdx.x;             // 0..255
         for (int it = 0; it < n_tiles; ++it) {
             const int st = it & 1;
             const uint32_t ph = (uint32_t)it & 1u;
             const int q0 = s_tiles[it] * 128;
-            float* sl = stats + st * 384;        // [lse2 | delta | ok]
+            float* sl = stats + st * 384;        // [lse2 | delta | ok] x 128 query columns
             {
-                const int qi = q0 + r;
+                const int col = tid & 127;
+                const int qi = q0 + col;
                 const bool ok = qi < T && (!p.qflag || (int)p.qflag[(int64_t)b * T + (qi < T ? qi : 0)] == variant);
                 const int64_t si = ((int64_t)b * p.heads + h) * T + (qi < T ? qi : 0);
-                sl[r] = ok ? p.lse[si] * LOG2E_F : CUDART_INF_F;
-                sl[128 + r] = ok ? p.delta[si] : 0.f;
-                sl[256 + r] = ok ? 1.f : 0.f;
+                if (tid < 128) {
+                    sl[col] = ok ? p.lse[si] * LOG2E_F : CUDART_INF_F;
+                    sl[256 + col] = ok ? 1.f : 0.f;
+                } else {
+                    sl[128 + col] = ok ? p.delta[si] : 0.f;
+                }
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            named_bar_sync(1, BW_COMPUTE_THREADS);
             mbar_wait(bars + KV_SDP, ph);
             tc_fence_after_sync();
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
+            const int qbase = q0 + half * 64;
+            // warp-uniform: tile straddles the key range or the causal diagonal (excluded query rows carry lse = +inf)
+            const bool need_mask = (kv0 + 128 > kve) || (kv0 < kvs) || (CAUSAL && kv0 + 127 > qbase);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
                 uint32_t s[32], dp[32];
-                tmem_ld32(lane_addr + COL_S + c * 32, s);
-                tmem_ld32(lane_addr + COL_DP + c * 32, dp);
+                tmem_ld32(lane_addr + colS + c * 32, s);
+                tmem_ld32(lane_addr + colDP + c * 32, dp);
                 tc_wait_ld();
                 uint32_t pp[16], pd[16];
+                const float* lse_c = sl + half * 64 + c * 32;
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
-                    const int col = c * 32 + j;
-                    const int qa = q0 + col;
-                    const bool ok0 = key_ok && sl[256 + col] != 0.f && (!CAUSAL || kj <= qa);
-                    const bool ok1 = key_ok && sl[256 + col + 1] != 0.f && (!CAUSAL || kj <= qa + 1);
-                    const float p0 = ok0 ? exp2f(__uint_as_float(s[j]) * sl2 - sl[col]) : 0.f;
-                    const float p1 = ok1 ? exp2f(__uint_as_float(s[j + 1]) * sl2 - sl[col + 1]) : 0.f;
-                    const float d0 = p0 * (__uint_as_float(dp[j]) - sl[128 + col]) * p.scale;
-                    const float d1 = p1 * (__uint_as_float(dp[j + 1]) - sl[128 + col + 1]) * p.scale;
+                    float p0 = fast_ex2(fmaf(__uint_as_float(s[j]), sl2, -lse_c[j]));          // lse = +inf on excluded rows
+                    float p1 = fast_ex2(fmaf(__uint_as_float(s[j + 1]), sl2, -lse_c[j + 1]));
+                    if (need_mask) {
+                        const int qa = qbase + c * 32 + j;
+                        p0 = (key_ok && (!CAUSAL || kj <= qa)) ? p0 : 0.f;
+                        p1 = (key_ok && (!CAUSAL || kj <= qa + 1)) ? p1 : 0.f;
+                    }
+                    const float d0 = p0 * (__uint_as_float(dp[j]) - lse_c[128 + j]) * p.scale;
+                    const float d1 = p1 * (__uint_as_float(dp[j + 1]) - lse_c[128 + j + 1]) * p.scale;
                     pp[j >> 1] = pack_bf16(p0, p1);
                     pd[j >> 1] = pack_bf16(d0, d1);
                 }
-                tmem_st16(lane_addr + COL_S + c * 16, pp);      // P^T over S^T (chunk already consumed)
-                tmem_st16(lane_addr + COL_DP + c * 16, pd);     // dS^T over dP^T
+                tmem_st16(lane_addr + colS + c * 16, pp);      // P^T over my own, already consumed S^T columns
+                tmem_st16(lane_addr + colDP + c * 16, pd);     // dS^T over dP^T
             }
             tc_wait_st();
             tc_fence_before_sync();
@@ -427,14 +447,14 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             tc_fence_after_sync();
             const bool row_ok = kj < T;
             const int64_t off = ((int64_t)b * T + (row_ok ? kj : 0)) * ((int64_t)p.heads * D) + (int64_t)h * D;
-            __nv_bfloat16* dk_row = (variant ? p.out2 : p.out0) + off;
-            __nv_bfloat16* dv_row = (variant ? p.out3 : p.out1) + off;
+            // warpgroup 0 stores dV (columns [COL_DV, +D)), warpgroup 1 stores dK (columns [COL_DK, +D))
+            __nv_bfloat16* dst_row = (half == 0 ? (variant ? p.out3 : p.out1) : (variant ? p.out2 : p.out0)) + off;
+            const uint32_t col0 = half == 0 ? COL_DV : COL_DK;
 #pragma unroll 1
-            for (int c = 0; c < 2 * D / 32; ++c) {
+            for (int c = 0; c < D / 32; ++c) {
                 uint32_t v[32];
-                tmem_ld32(lane_addr + COL_DV + c * 32, v);      // dV columns then dK columns (contiguous)
+                tmem_ld32(lane_addr + col0 + c * 32, v);
                 tc_wait_ld();
-                __nv_bfloat16* dst = (c < D / 32) ? (dv_row + c * 32) : (dk_row + (c - D / 32) * 32);
                 if (row_ok) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
@@ -443,7 +463,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                         o.y = pack_bf16(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
                         o.z = pack_bf16(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
                         o.w = pack_bf16(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
-                        *reinterpret_cast<uint4*>(dst + j) = o;
+                        *reinterpret_cast<uint4*>(dst_row + c * 32 + j) = o;
                     }
                 }
                 __syncwarp();
@@ -452,7 +472,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tc_fence_before_sync();
     }
     __syncthreads();
-    if (warp == 5) {
+    if (warp == BW_WARP_MMA) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }

@@ -19,7 +19,10 @@ namespace lb {
 
 constexpr int AT_BM = 128;       // query rows per tile
 constexpr int AT_BN = 128;       // keys per tile
-constexpr int AT_THREADS = 192;
+constexpr int AT_SOFTMAX_WARPS = 8;                 // two warpgroups: each owns half of the key columns of a tile
+constexpr int AT_SOFTMAX_THREADS = AT_SOFTMAX_WARPS * 32;
+constexpr int AT_WARP_TMA = AT_SOFTMAX_WARPS, AT_WARP_MMA = AT_SOFTMAX_WARPS + 1;
+constexpr int AT_THREADS = (AT_SOFTMAX_WARPS + 2) * 32;
 constexpr float LOG2E = 1.4426950408889634f;
 
 struct AttnFwdParams {
@@ -39,13 +42,16 @@ struct AttnFwdSmem {
     static constexpr int Q_BYTES = AT_BM * D * 2;
     static constexpr int K_BYTES = AT_BN * D * 2;
     static constexpr int V_BYTES = AT_BN * D * 2;
-    static constexpr int BAR_OFF = Q_BYTES + K_BYTES + V_BYTES;
+    static constexpr int RED_OFF = Q_BYTES + K_BYTES + V_BYTES;      // float red[2 parity][2 halves][128 rows]
+    static constexpr int BAR_OFF = RED_OFF + 2 * 2 * 128 * 4;
     static constexpr int TOTAL = BAR_OFF + 1024 + 128;
 };
 
 // barrier indices
 enum { B_Q = 0, B_KFULL, B_KEMPTY, B_VFULL, B_VEMPTY, B_SFULL, B_PFULL, B_OREADY, B_COUNT };
 
+// TMEM columns: S (fp32) at [0,128); each softmax warpgroup h writes its half of P (bf16, 32 columns) over the start of
+// ITS OWN half of S: P(keys 64h .. 64h+63) at [64h, 64h+32).  O accumulator at [128, 128+D).
 template <int D, bool CAUSAL>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
@@ -57,6 +63,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint8_t* sQ = smem;
     uint8_t* sK = smem + S::Q_BYTES;
     uint8_t* sV = sK + S::K_BYTES;
+    float* red = reinterpret_cast<float*>(smem + S::RED_OFF);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
 
@@ -69,7 +76,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int q0 = q_tile * AT_BM;
     const int kvs = p.kv_start ? p.kv_start[b] : 0;
     const int kve = p.kv_end ? p.kv_end[b] : T;
-    // kv tile range
     const int first_tile = kvs / AT_BN;
     int last_tile = (kve + AT_BN - 1) / AT_BN;                      // exclusive
     if (CAUSAL && last_tile > q_tile + 1) last_tile = q_tile + 1;
@@ -79,15 +85,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     constexpr uint32_t COL_S = 0, COL_O = 128;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < B_COUNT; ++i) mbar_init(bars + i, i == B_PFULL ? 128 : 1);
+        for (int i = 0; i < B_COUNT; ++i) mbar_init(bars + i, i == B_PFULL ? AT_SOFTMAX_THREADS : 1);
         fence_barrier_init();
     }
-    if (warp == 4 && elect_one()) {
+    if (warp == AT_WARP_TMA && elect_one()) {
         tma_prefetch_desc(&tmQ);
         tma_prefetch_desc(variant ? &tmK1 : &tmK0);
         tma_prefetch_desc(variant ? &tmV1 : &tmV0);
     }
-    if (warp == 5) {
+    if (warp == AT_WARP_MMA) {
         tmem_alloc(tmem_slot, TMEM_COLS);
         tmem_relinquish();
     }
@@ -96,7 +102,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 4) {
+    if (warp == AT_WARP_TMA) {
         // ------------------------------------------------------------ TMA producer
         if (elect_one() && n_tiles > 0) {
             const CUtensorMap* tK = variant ? &tmK1 : &tmK0;
@@ -120,7 +126,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     tma_load_2d(sV + c * (AT_BN * 128), tV, bars + B_VFULL, h * D + c * 64, row_k);
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == AT_WARP_MMA) {
         // ------------------------------------------------------------ MMA issuer
         if (elect_one() && n_tiles > 0) {
             constexpr uint32_t idesc_qk = make_idesc_bf16(AT_BM, AT_BN, 0, 0);
@@ -143,8 +149,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 tc_fence_after_sync();
 #pragma unroll
                 for (int kk = 0; kk < AT_BN / 16; ++kk) {
-                    // A = P (TMEM, 8 columns per 16 keys); B = V as MN-major: 16 key rows = 2048 B, d-chunks 16 KB apart
-                    umma_ts(tmem_base + COL_O, tmem_base + COL_S + kk * 8,
+                    // A = P in TMEM: keys 16kk.. live at column 64*(kk/4) + 8*(kk%4); B = V as MN-major (16 key rows = 2048 B)
+                    umma_ts(tmem_base + COL_O, tmem_base + COL_S + (uint32_t)(kk / 4) * 64 + (uint32_t)(kk % 4) * 8,
                             desc_mnmajor(aV + kk * 2048, AT_BN * 128), idesc_pv, (it | kk) ? 1u : 0u);
                 }
                 tc_commit(bars + B_VEMPTY);
@@ -153,103 +159,130 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
     } else {
         // ------------------------------------------------------------ softmax / correction / epilogue
-        const int r = threadIdx.x;                      // query row in tile == TMEM lane
-        const int qi = q0 + r;                          // position in the sample
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const int half = warp >> 2;                               // which 64 key columns of the tile / which D/2 columns of O
+        const int r = (warp & 3) * 32 + (threadIdx.x & 31);       // query row in tile == TMEM lane
+        const int qi = q0 + r;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        const uint32_t colS = COL_S + half * 64;                  // my S columns; my P goes to [colS, colS+32)
+        constexpr int DH = D / 2;
+        const uint32_t colO = COL_O + half * DH;
         const float sl2 = p.scale * LOG2E;
         float m_used = -CUDART_INF_F, l = 0.f;
         for (int it = 0; it < n_tiles; ++it) {
             const uint32_t ph = (uint32_t)it & 1u;
-            const int kv0 = (first_tile + it) * AT_BN;
-            const bool need_mask = (CAUSAL && kv0 + AT_BN - 1 > q0) || (kv0 + AT_BN > kve) || (kv0 < kvs);
+            const int kv0 = (first_tile + it) * AT_BN + half * 64;     // first key of my half
+            const bool need_mask = (CAUSAL && kv0 + 63 > q0) || (kv0 + 64 > kve) || (kv0 < kvs);
             mbar_wait(bars + B_SFULL, ph);
             tc_fence_after_sync();
-            // ---- pass 1: row max
-            float mx = -CUDART_INF_F;
-#pragma unroll 1
-            for (int c = 0; c < AT_BN / 32; ++c) {
+            // ---- pass 1: max over my 64 columns
+            float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
                 uint32_t v[32];
-                tmem_ld32(lane_addr + COL_S + c * 32, v);
+                tmem_ld32(lane_addr + colS + c * 32, v);
                 tc_wait_ld();
                 if (need_mask) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
+                    for (int j = 0; j < 32; j += 2) {
                         const int kj = kv0 + c * 32 + j;
-                        const bool ok = (!CAUSAL || kj <= qi) && kj < kve && kj >= kvs;
-                        mx = fmaxf(mx, ok ? __uint_as_float(v[j]) : -CUDART_INF_F);
+                        const bool ok0 = (!CAUSAL || kj <= qi) && kj < kve && kj >= kvs;
+                        const bool ok1 = (!CAUSAL || kj + 1 <= qi) && kj + 1 < kve && kj + 1 >= kvs;
+                        mx0 = fmaxf(mx0, ok0 ? __uint_as_float(v[j]) : -CUDART_INF_F);
+                        mx1 = fmaxf(mx1, ok1 ? __uint_as_float(v[j + 1]) : -CUDART_INF_F);
                     }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+                    for (int j = 0; j < 32; j += 2) {
+                        mx0 = fmaxf(mx0, __uint_as_float(v[j]));
+                        mx1 = fmaxf(mx1, __uint_as_float(v[j + 1]));
+                    }
                 }
             }
-            const float m_new = fmaxf(m_used, mx);
-            // ---- lazy correction: rescale O only when the running max moved by more than 2^8
+            // ---- exchange the partial max with the thread owning the other half of this row
+            float* rbuf = red + (it & 1) * 256;
+            rbuf[half * 128 + r] = fmaxf(mx0, mx1);
+            named_bar_sync(1, AT_SOFTMAX_THREADS);
+            const float m_new = fmaxf(m_used, fmaxf(rbuf[r], rbuf[128 + r]));
+            // ---- lazy correction: rescale O only when the running max moved by more than 2^8 (both halves decide alike)
             const bool grow = (m_new - m_used) * sl2 > 8.f;      // also true when m_used == -inf and m_new finite
             if (it == 0) {
                 m_used = m_new;
             } else if (__any_sync(0xffffffffu, grow)) {
                 mbar_wait(bars + B_OREADY, ph ^ 1u);              // PV of the previous tile has landed in O
                 tc_fence_after_sync();
-                const float alpha = grow ? ((m_used == -CUDART_INF_F) ? 0.f : exp2f((m_used - m_new) * sl2)) : 1.f;
+                const float alpha = grow ? ((m_used == -CUDART_INF_F) ? 0.f : fast_ex2((m_used - m_new) * sl2)) : 1.f;
                 if (grow) {
                     m_used = m_new;
                     l *= alpha;
                 }
 #pragma unroll 1
-                for (int c = 0; c < D / 32; ++c) {
+                for (int c = 0; c < DH / 32; ++c) {
                     uint32_t v[32];
-                    tmem_ld32(lane_addr + COL_O + c * 32, v);
+                    tmem_ld32(lane_addr + colO + c * 32, v);
                     tc_wait_ld();
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * alpha);
-                    tmem_st32(lane_addr + COL_O + c * 32, v);
+                    tmem_st32(lane_addr + colO + c * 32, v);
                 }
                 tc_wait_st();
             }
             const float m_off = (m_used == -CUDART_INF_F) ? 0.f : m_used * sl2;
-            // ---- pass 2: P = exp2(S*sl2 - m), row sum, P (bf16) -> TMEM over S
-#pragma unroll 1
-            for (int c = 0; c < AT_BN / 32; ++c) {
+            // ---- pass 2: P = 2^(S*sl2 - m), partial row sum, P (bf16) over my own S columns
+            float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
                 uint32_t v[32];
-                tmem_ld32(lane_addr + COL_S + c * 32, v);
+                tmem_ld32(lane_addr + colS + c * 32, v);
                 tc_wait_ld();
                 uint32_t pk[16];
+                if (need_mask) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    float p0 = exp2f(__uint_as_float(v[j]) * sl2 - m_off);
-                    float p1 = exp2f(__uint_as_float(v[j + 1]) * sl2 - m_off);
-                    if (need_mask) {
+                    for (int j = 0; j < 32; j += 2) {
                         const int kj = kv0 + c * 32 + j;
                         const bool ok0 = (!CAUSAL || kj <= qi) && kj < kve && kj >= kvs;
                         const bool ok1 = (!CAUSAL || kj + 1 <= qi) && kj + 1 < kve && kj + 1 >= kvs;
-                        p0 = ok0 ? p0 : 0.f;
-                        p1 = ok1 ? p1 : 0.f;
+                        const float p0 = ok0 ? fast_ex2(fmaf(__uint_as_float(v[j]), sl2, -m_off)) : 0.f;
+                        const float p1 = ok1 ? fast_ex2(fmaf(__uint_as_float(v[j + 1]), sl2, -m_off)) : 0.f;
+                        l0 += p0;
+                        l1 += p1;
+                        pk[j >> 1] = pack_bf16(p0, p1);
                     }
-                    l += p0 + p1;
-                    pk[j >> 1] = pack_bf16(p0, p1);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        const float p0 = fast_ex2(fmaf(__uint_as_float(v[j]), sl2, -m_off));
+                        const float p1 = fast_ex2(fmaf(__uint_as_float(v[j + 1]), sl2, -m_off));
+                        l0 += p0;
+                        l1 += p1;
+                        pk[j >> 1] = pack_bf16(p0, p1);
+                    }
                 }
-                tmem_st16(lane_addr + COL_S + c * 16, pk);
+                tmem_st16(lane_addr + colS + c * 16, pk);       // chunk c of P overwrites S columns already consumed
             }
+            l += l0 + l1;
             tc_wait_st();
             tc_fence_before_sync();
             mbar_arrive(bars + B_PFULL);
         }
-        // ---- epilogue
+        // ---- epilogue: combine the two partial row sums, normalise, write my half of the O columns
+        float* rbuf = red + (n_tiles & 1) * 256;
+        rbuf[half * 128 + r] = l;
+        named_bar_sync(1, AT_SOFTMAX_THREADS);
+        const float l_tot = rbuf[r] + rbuf[128 + r];
         const int64_t bt = (int64_t)b * T + qi;
         const bool row_ok = (qi < T) && (!p.qflag || (int)p.qflag[qi < T ? bt : 0] == variant);
         if (n_tiles > 0) {
             mbar_wait(bars + B_OREADY, (uint32_t)(n_tiles - 1) & 1u);
             tc_fence_after_sync();
         }
-        const float inv_l = l > 0.f ? 1.f / l : 0.f;
+        const float inv_l = l_tot > 0.f ? 1.f / l_tot : 0.f;
         const int64_t dst = row_ok ? (p.out_row ? (int64_t)p.out_row[bt] : bt) : 0;
-        __nv_bfloat16* orow = p.O + dst * ((int64_t)p.heads * D) + (int64_t)h * D;
+        __nv_bfloat16* orow = p.O + dst * ((int64_t)p.heads * D) + (int64_t)h * D + half * DH;
 #pragma unroll 1
-        for (int c = 0; c < D / 32; ++c) {
+        for (int c = 0; c < DH / 32; ++c) {
             uint32_t v[32];
             if (n_tiles > 0) {
-                tmem_ld32(lane_addr + COL_O + c * 32, v);
+                tmem_ld32(lane_addr + colO + c * 32, v);
                 tc_wait_ld();
             } else {
 #pragma unroll
@@ -268,14 +301,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
             __syncwarp();
         }
-        if (row_ok && p.lse) {
+        if (row_ok && p.lse && half == 0) {
             // natural-log LSE of the scaled scores; +inf marks a row with no visible key (P == 0 in backward)
-            p.lse[((int64_t)b * p.heads + h) * T + qi] = l > 0.f ? (m_used * p.scale + __logf(l)) : CUDART_INF_F;
+            p.lse[((int64_t)b * p.heads + h) * T + qi] = l_tot > 0.f ? (m_used * p.scale + __logf(l_tot)) : CUDART_INF_F;
         }
         tc_fence_before_sync();
     }
     __syncthreads();
-    if (warp == 5) {
+    if (warp == AT_WARP_MMA) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }

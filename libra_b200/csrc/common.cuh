@@ -61,6 +61,17 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// 2^x on the SFU (MUFU.EX2), flush-to-zero; ex2(-inf) = 0
+__device__ __forceinline__ float fast_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);   // .x = lo (low 16 bits), .y = hi
     return *reinterpret_cast<uint32_t*>(&v);

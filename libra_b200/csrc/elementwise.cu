@@ -184,31 +184,18 @@ __global__ void lfq_unpack_kernel(const int64_t* __restrict__ idx, int64_t n, in
 
 // ------------------------------------------------ attention prologue (fwd)
 // One CTA per original token.  A "unit" is 8 rotary pairs: elements [d0,d0+8) and [d0+D/2, d0+D/2+8) of one head.
-template <int MAXR>
+// kc = k + kb and vc = v + vb (the bridged variants) are produced upstream by rank-r GEMMs (beta = 1).
 __global__ void __launch_bounds__(256) attn_prep_fwd_kernel(
-    const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
-    const __nv_bfloat16* __restrict__ tk, const __nv_bfloat16* __restrict__ tv, const __nv_bfloat16* __restrict__ Bk_l,
-    const __nv_bfloat16* __restrict__ Bk_v, const __nv_bfloat16* __restrict__ Bv_l, const __nv_bfloat16* __restrict__ Bv_v,
-    const uint8_t* __restrict__ flag_sorted, const int32_t* __restrict__ sorted_of, const int32_t* __restrict__ pos,
-    const float* __restrict__ cos_t, const float* __restrict__ sin_t, __nv_bfloat16* __restrict__ Q,
-    __nv_bfloat16* __restrict__ Kfv, __nv_bfloat16* __restrict__ Kfl, __nv_bfloat16* __restrict__ Vfv,
-    __nv_bfloat16* __restrict__ Vfl, int heads, int D, int R) {
+    const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ kc,
+    const __nv_bfloat16* __restrict__ v, const __nv_bfloat16* __restrict__ vc, const uint8_t* __restrict__ flag_sorted,
+    const int32_t* __restrict__ sorted_of, const int32_t* __restrict__ pos, const float* __restrict__ cos_t,
+    const float* __restrict__ sin_t, __nv_bfloat16* __restrict__ Q, __nv_bfloat16* __restrict__ Kfv,
+    __nv_bfloat16* __restrict__ Kfl, __nv_bfloat16* __restrict__ Vfv, __nv_bfloat16* __restrict__ Vfl, int heads, int D) {
     const int64_t bt = blockIdx.x;
     const int64_t s = sorted_of[bt];
     const bool vis = flag_sorted[s] != 0;
     const int C = heads * D, half = D >> 1, upH = D >> 4;      // units per head
     const int p = pos[bt];
-    float tkr[MAXR], tvr[MAXR];
-    const bool bridge = (tk != nullptr);
-    if (bridge) {
-#pragma unroll
-        for (int r = 0; r < MAXR; ++r) {
-            tkr[r] = r < R ? __bfloat162float(tk[s * R + r]) : 0.f;
-            tvr[r] = r < R ? __bfloat162float(tv[s * R + r]) : 0.f;
-        }
-    }
-    const __nv_bfloat16* Bk = vis ? Bk_v : Bk_l;
-    const __nv_bfloat16* Bv = vis ? Bv_v : Bv_l;
     for (int u = threadIdx.x; u < heads * upH; u += blockDim.x) {
         const int h = u / upH, d0 = (u - h * upH) * 8;
         const int c_lo = h * D + d0, c_hi = c_lo + half;
@@ -220,94 +207,34 @@ __global__ void __launch_bounds__(256) attn_prep_fwd_kernel(
             cs[0] = a.x; cs[1] = a.y; cs[2] = a.z; cs[3] = a.w; cs[4] = b.x; cs[5] = b.y; cs[6] = b.z; cs[7] = b.w;
             sn[0] = c.x; sn[1] = c.y; sn[2] = c.z; sn[3] = c.w; sn[4] = d.x; sn[5] = d.y; sn[6] = d.z; sn[7] = d.w;
         }
-        float xl[8], xh[8], o_lo[8], o_hi[8];
-        // ---- Q
-        unpack8(__ldg(reinterpret_cast<const uint4*>(q + s * C + c_lo)), xl);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(q + s * C + c_hi)), xh);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            o_lo[j] = xl[j] * cs[j] - xh[j] * sn[j];
-            o_hi[j] = xh[j] * cs[j] + xl[j] * sn[j];
-        }
-        *reinterpret_cast<uint4*>(Q + bt * C + c_lo) = pack8(o_lo);
-        *reinterpret_cast<uint4*>(Q + bt * C + c_hi) = pack8(o_hi);
-        // ---- K: plain and bridged
-        unpack8(__ldg(reinterpret_cast<const uint4*>(k + s * C + c_lo)), xl);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(k + s * C + c_hi)), xh);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            o_lo[j] = xl[j] * cs[j] - xh[j] * sn[j];
-            o_hi[j] = xh[j] * cs[j] + xl[j] * sn[j];
-        }
-        const uint4 kp_lo = pack8(o_lo), kp_hi = pack8(o_hi);
-        uint4 kc_lo = kp_lo, kc_hi = kp_hi;
-        if (bridge) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float al = 0.f, ah = 0.f;
-                float wl[8], wh[8];
-                if (MAXR == 8) {
-                    unpack8(__ldg(reinterpret_cast<const uint4*>(Bk + (int64_t)(c_lo + j) * R)), wl);
-                    unpack8(__ldg(reinterpret_cast<const uint4*>(Bk + (int64_t)(c_hi + j) * R)), wh);
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        al += tkr[r] * wl[r];
-                        ah += tkr[r] * wh[r];
-                    }
-                } else {
-                    for (int r = 0; r < R; ++r) {
-                        al += tkr[r] * __bfloat162float(Bk[(int64_t)(c_lo + j) * R + r]);
-                        ah += tkr[r] * __bfloat162float(Bk[(int64_t)(c_hi + j) * R + r]);
-                    }
-                }
-                // reference: kb is a bf16 Linear output, k + kb a bf16 add
-                xl[j] = __bfloat162float(__float2bfloat16(xl[j] + __bfloat162float(__float2bfloat16(al))));
-                xh[j] = __bfloat162float(__float2bfloat16(xh[j] + __bfloat162float(__float2bfloat16(ah))));
-            }
+        auto rope = [&](const __nv_bfloat16* src, uint4& lo, uint4& hi) {
+            float xl[8], xh[8], o_lo[8], o_hi[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(src + s * C + c_lo)), xl);
+            unpack8(__ldg(reinterpret_cast<const uint4*>(src + s * C + c_hi)), xh);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 o_lo[j] = xl[j] * cs[j] - xh[j] * sn[j];
                 o_hi[j] = xh[j] * cs[j] + xl[j] * sn[j];
             }
-            kc_lo = pack8(o_lo);
-            kc_hi = pack8(o_hi);
-        }
+            lo = pack8(o_lo);
+            hi = pack8(o_hi);
+        };
+        uint4 lo, hi;
+        rope(q, lo, hi);
+        *reinterpret_cast<uint4*>(Q + bt * C + c_lo) = lo;
+        *reinterpret_cast<uint4*>(Q + bt * C + c_hi) = hi;
+        uint4 kp_lo, kp_hi, kc_lo, kc_hi;
+        rope(k, kp_lo, kp_hi);
+        if (kc) rope(kc, kc_lo, kc_hi); else { kc_lo = kp_lo; kc_hi = kp_hi; }
         // vision token: vision queries (fv) see plain, language queries (fl) see bridged; language token: the reverse
         *reinterpret_cast<uint4*>(Kfv + bt * C + c_lo) = vis ? kp_lo : kc_lo;
         *reinterpret_cast<uint4*>(Kfv + bt * C + c_hi) = vis ? kp_hi : kc_hi;
         *reinterpret_cast<uint4*>(Kfl + bt * C + c_lo) = vis ? kc_lo : kp_lo;
         *reinterpret_cast<uint4*>(Kfl + bt * C + c_hi) = vis ? kc_hi : kp_hi;
-        // ---- V
         const uint4 vp_lo = __ldg(reinterpret_cast<const uint4*>(v + s * C + c_lo));
         const uint4 vp_hi = __ldg(reinterpret_cast<const uint4*>(v + s * C + c_hi));
-        uint4 vc_lo = vp_lo, vc_hi = vp_hi;
-        if (bridge) {
-            unpack8(vp_lo, xl);
-            unpack8(vp_hi, xh);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float al = 0.f, ah = 0.f;
-                float wl[8], wh[8];
-                if (MAXR == 8) {
-                    unpack8(__ldg(reinterpret_cast<const uint4*>(Bv + (int64_t)(c_lo + j) * R)), wl);
-                    unpack8(__ldg(reinterpret_cast<const uint4*>(Bv + (int64_t)(c_hi + j) * R)), wh);
-#pragma unroll
-                    for (int r = 0; r < 8; ++r) {
-                        al += tvr[r] * wl[r];
-                        ah += tvr[r] * wh[r];
-                    }
-                } else {
-                    for (int r = 0; r < R; ++r) {
-                        al += tvr[r] * __bfloat162float(Bv[(int64_t)(c_lo + j) * R + r]);
-                        ah += tvr[r] * __bfloat162float(Bv[(int64_t)(c_hi + j) * R + r]);
-                    }
-                }
-                xl[j] += __bfloat162float(__float2bfloat16(al));
-                xh[j] += __bfloat162float(__float2bfloat16(ah));
-            }
-            vc_lo = pack8(xl);
-            vc_hi = pack8(xh);
-        }
+        const uint4 vc_lo = vc ? __ldg(reinterpret_cast<const uint4*>(vc + s * C + c_lo)) : vp_lo;
+        const uint4 vc_hi = vc ? __ldg(reinterpret_cast<const uint4*>(vc + s * C + c_hi)) : vp_hi;
         *reinterpret_cast<uint4*>(Vfv + bt * C + c_lo) = vis ? vp_lo : vc_lo;
         *reinterpret_cast<uint4*>(Vfv + bt * C + c_hi) = vis ? vp_hi : vc_hi;
         *reinterpret_cast<uint4*>(Vfl + bt * C + c_lo) = vis ? vc_lo : vp_lo;
@@ -662,38 +589,22 @@ int lb_lfq_unpack(const int64_t* idx, int64_t n, int num_codebooks, int bits, vo
     return check_launch("lfq_unpack");
 }
 
-int lb_attn_prep_fwd(const void* q, const void* k, const void* v, const void* tk, const void* tv, const void* Bk_lang,
-                     const void* Bk_vis, const void* Bv_lang, const void* Bv_vis, const uint8_t* flag_sorted,
-                     const int32_t* sorted_of, const int32_t* pos, const float* cos_t, const float* sin_t, void* Q,
-                     void* Kfv, void* Kfl, void* Vfv, void* Vfl, int64_t n_tokens, int heads, int head_dim, int rank,
-                     void* stream) {
+int lb_attn_prep_fwd(const void* q, const void* k, const void* kc, const void* v, const void* vc,
+                     const uint8_t* flag_sorted, const int32_t* sorted_of, const int32_t* pos, const float* cos_t,
+                     const float* sin_t, void* Q, void* Kfv, void* Kfl, void* Vfv, void* Vfl, int64_t n_tokens, int heads,
+                     int head_dim, void* stream) {
     LB_REQUIRE(n_tokens >= 0 && heads > 0 && head_dim >= 16 && head_dim % 16 == 0, LB_EINVAL,
                "attn_prep: head_dim=%d must be a multiple of 16", head_dim);
-    LB_REQUIRE(rank >= 0 && rank <= 16, LB_EINVAL, "attn_prep: bridge rank %d > 16", rank);
     LB_REQUIRE(q && k && v && flag_sorted && sorted_of && pos && cos_t && sin_t && Q && Kfv && Kfl && Vfv && Vfl,
                LB_EINVAL, "attn_prep: null argument");
-    LB_REQUIRE(AL16(q) && AL16(k) && AL16(v) && AL16(Q) && AL16(Kfv) && AL16(Kfl) && AL16(Vfv) && AL16(Vfl) &&
-                   AL16(cos_t) && AL16(sin_t),
+    LB_REQUIRE(AL16(q) && AL16(k) && AL16(v) && (!kc || AL16(kc)) && (!vc || AL16(vc)) && AL16(Q) && AL16(Kfv) && AL16(Kfl) &&
+                   AL16(Vfv) && AL16(Vfl) && AL16(cos_t) && AL16(sin_t),
                LB_EALIGN, "attn_prep: pointers must be 16-byte aligned");
-    const bool bridge = rank > 0 && tk && tv;
-    if (bridge) LB_REQUIRE(Bk_lang && Bk_vis && Bv_lang && Bv_vis, LB_EINVAL, "attn_prep: missing bridge weights");
     if (n_tokens == 0) return LB_OK;
-    const void* tkp = bridge ? tk : nullptr;
-    if (bridge && rank == 8 && AL16(Bk_lang) && AL16(Bk_vis) && AL16(Bv_lang) && AL16(Bv_vis)) {
-        attn_prep_fwd_kernel<8><<<(unsigned)n_tokens, 256, 0, (cudaStream_t)stream>>>(
-            (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (const __nv_bfloat16*)tkp,
-            (const __nv_bfloat16*)tv, (const __nv_bfloat16*)Bk_lang, (const __nv_bfloat16*)Bk_vis,
-            (const __nv_bfloat16*)Bv_lang, (const __nv_bfloat16*)Bv_vis, flag_sorted, sorted_of, pos, cos_t, sin_t,
-            (__nv_bfloat16*)Q, (__nv_bfloat16*)Kfv, (__nv_bfloat16*)Kfl, (__nv_bfloat16*)Vfv, (__nv_bfloat16*)Vfl, heads,
-            head_dim, rank);
-    } else {
-        attn_prep_fwd_kernel<16><<<(unsigned)n_tokens, 256, 0, (cudaStream_t)stream>>>(
-            (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, (const __nv_bfloat16*)tkp,
-            (const __nv_bfloat16*)tv, (const __nv_bfloat16*)Bk_lang, (const __nv_bfloat16*)Bk_vis,
-            (const __nv_bfloat16*)Bv_lang, (const __nv_bfloat16*)Bv_vis, flag_sorted, sorted_of, pos, cos_t, sin_t,
-            (__nv_bfloat16*)Q, (__nv_bfloat16*)Kfv, (__nv_bfloat16*)Kfl, (__nv_bfloat16*)Vfv, (__nv_bfloat16*)Vfl, heads,
-            head_dim, rank);
-    }
+    attn_prep_fwd_kernel<<<(unsigned)n_tokens, 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)kc, (const __nv_bfloat16*)v,
+        (const __nv_bfloat16*)vc, flag_sorted, sorted_of, pos, cos_t, sin_t, (__nv_bfloat16*)Q, (__nv_bfloat16*)Kfv,
+        (__nv_bfloat16*)Kfl, (__nv_bfloat16*)Vfv, (__nv_bfloat16*)Vfl, heads, head_dim);
     return check_launch("attn_prep_fwd");
 }
 

@@ -208,8 +208,18 @@ class BridgeAttention(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, tk, tv, Bk_l, Bk_v, Bv_l, Bv_v, meta: AttnMeta):
         rt, w = meta.routing, meta.work
-        Q, Kfv, Kfl, Vfv, Vfl = ops.attn_prep_fwd(q, k, v, tk, tv, Bk_l, Bk_v, Bv_l, Bv_v, rt.flag_sorted, rt.inv, meta.pos,
-                                                 meta.cos, meta.sin, meta.heads, meta.head_dim)
+        n = rt.n_lang
+        # bridged variants k + tk.Bk^T, v + tv.Bv^T per modality segment: rank-r GEMMs with beta = 1 (cuBLAS)
+        kc, vc = torch.empty_like(k), torch.empty_like(v)
+        if n > 0:
+            torch.addmm(k[:n], tk[:n], Bk_l.t(), out=kc[:n])
+            torch.addmm(v[:n], tv[:n], Bv_l.t(), out=vc[:n])
+        if rt.n_vis > 0:
+            torch.addmm(k[n:], tk[n:], Bk_v.t(), out=kc[n:])
+            torch.addmm(v[n:], tv[n:], Bv_v.t(), out=vc[n:])
+        Q, Kfv, Kfl, Vfv, Vfl = ops.attn_prep_fwd(q, k, kc, v, vc, rt.flag_sorted, rt.inv, meta.pos, meta.cos, meta.sin,
+                                                 meta.heads, meta.head_dim)
+        del kc, vc
         scale = 1.0 / math.sqrt(meta.head_dim)
         o = torch.empty_like(q)
         # variant 0 = language queries (see Kfl/Vfl), variant 1 = vision queries (see Kfv/Vfv); rows land in sorted order

@@ -1,8 +1,8 @@
 """Host-side mirror of the reference's `libra.models` package surface (libra/models/__init__.py,
 libra/models/libra/__init__.py): same class names, running on the libra_b200 CUDA kernels."""
 from .configuration_libra import LibraConfig
-from .modeling_libra import (LibraCausalLMOutputWithPast, LibraDecoderLayer, LibraForCausalLM, LibraLinear, LibraModel,
+from .modeling_libra import (LibraCausalLMOutputWithPast, LibraDecoderLayer, LibraForCausalLM, LibraLinear, LibraModel, LibraTrainWrapper,
                              LibraPreTrainedModel)
 
-__all__ = ["LibraConfig", "LibraForCausalLM", "LibraModel", "LibraDecoderLayer", "LibraLinear", "LibraPreTrainedModel",
+__all__ = ["LibraConfig", "LibraForCausalLM", "LibraTrainWrapper", "LibraModel", "LibraDecoderLayer", "LibraLinear", "LibraPreTrainedModel",
            "LibraCausalLMOutputWithPast"]

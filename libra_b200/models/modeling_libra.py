@@ -453,3 +453,54 @@ class LibraForCausalLM(LibraPreTrainedModel):
             return ((loss,) + out) if loss is not None else out
         return LibraCausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=None, hidden_states=hs,
                                            attentions=None, past_hidden_states=None, past_vision_flag=None)
+
+
+class LibraTrainWrapper(LibraPreTrainedModel):
+    """Host mirror of LibraTrainWrapper (modeling_libra.py:1292-1437): tokenizer -> labels -> LibraForCausalLM.
+
+    The reference builds its LibraTokenizer from checkpoint files (sentencepiece model + vision_tokenizer_config.yaml)
+    that are not part of the repository; text tokenisation is outside the hot path.  This mirror
+    therefore takes the tokenizer as an object: anything callable as `tokenizer(samples, return_tensors="pt",
+    padding="longest", max_length=..., truncation=True)` that returns `input_ids`, `attention_mask`, `vision_indices`,
+    `coninous_signal` -- the reference's own `LibraTokenizer` qualifies -- and exposes `.image_tokenizer.boi_token_id`,
+    `.text_tokenizer.{bos_token_id, pad_token_id, eos_token_id, model_max_length}`."""
+
+    def __init__(self, config: LibraConfig, module: Optional["LibraForCausalLM"] = None, tokenizer=None, model_kwargs=None):
+        super().__init__(config)
+        self.module = module if module is not None else LibraForCausalLM(config)
+        self.tokenizer = tokenizer
+        if tokenizer is not None:
+            self.change_pad_token_to_eos(pad_token_id=tokenizer.text_tokenizer.pad_token_id,
+                                         eos_token_id=tokenizer.text_tokenizer.eos_token_id)
+        model_kwargs = model_kwargs or {}
+        if model_kwargs.get("frozen_language", False):                      # :1342-1346
+            for key, p in self.module.named_parameters():
+                if "vision" not in key:
+                    p.requires_grad = False
+        for flag, pat in (("freeze_vision_value", "vision_v_proj"), ("freeze_text_embedding", ".embed_tokens"),
+                          ("freeze_vision_embedding", ".vision_embed_tokens")):      # :1348-1364
+            if model_kwargs.get(flag, False):
+                for key, p in self.module.named_parameters():
+                    if pat in key:
+                        p.requires_grad = False
+
+    @classmethod
+    def from_config(cls, config, **kw):
+        return cls(config, **kw)
+
+    def change_pad_token_to_eos(self, pad_token_id=0, eos_token_id=2):       # :1390-1395
+        w = self.module.get_input_embeddings().weight
+        w.data[pad_token_id] = w.data[eos_token_id].clone()
+
+    def get_labels(self, inputs, label_mask_position_map):                   # :1397-1411
+        from .tokenization_libra import get_labels
+        return get_labels(inputs["input_ids"], inputs["attention_mask"], self.tokenizer.image_tokenizer.boi_token_id,
+                          self.tokenizer.text_tokenizer.bos_token_id, label_mask_position_map)
+
+    def forward(self, samples, return_loss=None, **kwargs):                  # :1414-1433
+        inputs = self.tokenizer(samples, return_tensors="pt", padding="longest",
+                                max_length=self.tokenizer.text_tokenizer.model_max_length, truncation=True)
+        labels = self.get_labels(inputs, samples["label_mask_position_map"])
+        return self.module(input_ids=inputs["input_ids"], attention_mask=inputs["attention_mask"],
+                           vision_indices=inputs["vision_indices"], contiguous_signal=inputs["coninous_signal"],
+                           labels=labels, use_cache=False, **kwargs)

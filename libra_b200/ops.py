@@ -237,14 +237,13 @@ def probe_umma(mode, a, b):
 
 
 # ------------------------------------------------------------ attention
-def attn_prep_fwd(q, k, v, tk, tv, Bk_l, Bk_v, Bv_l, Bv_v, flag_sorted, sorted_of, pos, cos_t, sin_t, heads, head_dim):
+def attn_prep_fwd(q, k, kc, v, vc, flag_sorted, sorted_of, pos, cos_t, sin_t, heads, head_dim):
+    """kc/vc: bridged variants (k + kb, v + vb) or None."""
     n = q.shape[0]
     C = heads * head_dim
     outs = [torch.empty(n, C, dtype=BF16, device=q.device) for _ in range(5)]
-    rank = 0 if tk is None else tk.shape[1]
-    _lib.call("lb_attn_prep_fwd", _p(q), _p(k), _p(v), _p(tk), _p(tv), _p(Bk_l), _p(Bk_v), _p(Bv_l), _p(Bv_v),
-              _p(flag_sorted), _p(sorted_of), _p(pos), _p(cos_t), _p(sin_t), *[_p(o) for o in outs], n, heads, head_dim,
-              rank, _st())
+    _lib.call("lb_attn_prep_fwd", _p(q), _p(k), _p(kc), _p(v), _p(vc), _p(flag_sorted), _p(sorted_of), _p(pos), _p(cos_t),
+              _p(sin_t), *[_p(o) for o in outs], n, heads, head_dim, _st())
     return outs   # Q, Kfv, Kfl, Vfv, Vfl
 
 

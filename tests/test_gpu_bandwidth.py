@@ -175,8 +175,10 @@ def test_attn_prep_fwd_bwd():
     pos = torch.arange(T, device=dev, dtype=torch.int32).repeat(B)
     cos, sin = O.rope_tables(D, 2048, 10000.0, torch.float32, dev)
     cos_t, sin_t = cos[:, :D // 2].contiguous(), sin[:, :D // 2].contiguous()
-    Q, Kfv, Kfl, Vfv, Vfl = ops.attn_prep_fwd(q, k, v, tk, tv, Bk_l, Bk_v, Bv_l, Bv_v, rt.flag_sorted, rt.inv, pos, cos_t,
-                                             sin_t, H, D)
+    nl = rt.n_lang
+    kc = torch.cat([torch.addmm(k[:nl], tk[:nl], Bk_l.t()), torch.addmm(k[nl:], tk[nl:], Bk_v.t())])
+    vc = torch.cat([torch.addmm(v[:nl], tv[:nl], Bv_l.t()), torch.addmm(v[nl:], tv[nl:], Bv_v.t())])
+    Q, Kfv, Kfl, Vfv, Vfl = ops.attn_prep_fwd(q, k, kc, v, vc, rt.flag_sorted, rt.inv, pos, cos_t, sin_t, H, D)
 
     leaves = [t.float().requires_grad_(True) for t in (q, k, v, tk, tv)]
     qf, kf, vf, tkf, tvf = leaves
