@@ -103,71 +103,89 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------- CPU reference arm
-def cpu_reference_sample(n_layers: int = 1, threads: int = 0, repeats: int = 1, dtype=torch.float32):
-    """Times the oracle (CPU restatement of the reference's LibraForCausalLM path, oracle/libra_oracle.py) on the
-    host cores: forward+backward of `n_layers` FULL-WIDTH Libra-11B decoder layers on BASELINE.json configs[0]'s
-    sequence (1 image + 32 text tokens, T=611), scaled by 32/n_layers to a whole-model tokens/s figure.  fp32 by
-    default: bf16 GEMMs are far slower than fp32 on host CPUs without AMX (measured 89 s for 2 layers in bf16)."""
-    from oracle import libra_oracle as O
-    threads = threads or (os.cpu_count() or 1)
-    torch.set_num_threads(threads)
-    d = O.LibraDims()
-    g = torch.Generator().manual_seed(0)
-    H, I, R = d.hidden_size, d.intermediate_size, d.bridge_rank
-    sd = {}
+class CpuReference:
+    """The oracle (CPU restatement of the reference's LibraForCausalLM path, oracle/libra_oracle.py) on the host cores:
+    forward+backward of `n_layers` FULL-WIDTH Libra-11B decoder layers on BASELINE.json configs[0]'s sequence (1 image +
+    32 text tokens, T=611), scaled by 32/n_layers to a whole-model tokens/s figure.  fp32 by default: bf16 GEMMs are far
+    slower than fp32 on host CPUs without AMX (measured on the GPU box: 89 s for 2 layers in bf16)."""
 
-    def w(*s):
-        return (torch.randn(*s, generator=g) * 0.02).to(dtype).requires_grad_(True)
-    for i in range(n_layers):
-        p = f"model.layers.{i}"
-        for n in "qkvo":
-            sd[f"{p}.self_attn.{n}_proj.weight"] = w(H, H)
-            sd[f"{p}.self_attn.vision_{n}_proj.weight_A"] = w(H // 4, H)
-            sd[f"{p}.self_attn.vision_{n}_proj.weight_B"] = w(H, H // 4)
-        for n in "kv":
-            for m in ("language", "vision"):
-                sd[f"{p}.self_attn.vision_{n}_bridge_on_{m}.weight_A"] = w(R, H)
-                sd[f"{p}.self_attn.vision_{n}_bridge_on_{m}.weight_B"] = w(H, R)
-        for n, (i_, o_) in dict(gate=(H, I), up=(H, I), down=(I, H)).items():
-            sd[f"{p}.mlp.{n}_proj.weight"] = w(o_, i_)
-            sd[f"{p}.mlp.vision_{n}_proj.weight_A"] = w(o_ // 4, i_)
-            sd[f"{p}.mlp.vision_{n}_proj.weight_B"] = w(o_, o_ // 4)
-        for n in ("input_layernorm", "post_attention_layernorm", "vision_input_layernorm", "vision_post_attention_layernorm"):
-            sd[f"{p}.{n}.weight"] = torch.ones(H, dtype=dtype).requires_grad_(True)
-    T = 611
-    flag = torch.zeros(1, T, dtype=torch.bool)
-    flag[0, 1:579] = True
-    pos = torch.arange(T)[None]
-    times = []
-    for _ in range(repeats):
-        h = torch.randn(1, T, H, generator=g).to(dtype).requires_grad_(True)
+    def __init__(self, n_layers: int = 1, threads: int = 0, dtype=torch.float32):
+        from oracle import libra_oracle as O
+        self.O = O
+        self.threads = threads or (os.cpu_count() or 1)
+        torch.set_num_threads(self.threads)
+        self.n_layers, self.dtype = n_layers, dtype
+        self.d = d = O.LibraDims()
+        g = torch.Generator().manual_seed(0)
+        H, I, R = d.hidden_size, d.intermediate_size, d.bridge_rank
+        sd = {}
+
+        def w(*s):
+            return (torch.randn(*s, generator=g) * 0.02).to(dtype).requires_grad_(True)
+        for i in range(n_layers):
+            p = f"model.layers.{i}"
+            for n in "qkvo":
+                sd[f"{p}.self_attn.{n}_proj.weight"] = w(H, H)
+                sd[f"{p}.self_attn.vision_{n}_proj.weight_A"] = w(H // 4, H)
+                sd[f"{p}.self_attn.vision_{n}_proj.weight_B"] = w(H, H // 4)
+            for n in "kv":
+                for m in ("language", "vision"):
+                    sd[f"{p}.self_attn.vision_{n}_bridge_on_{m}.weight_A"] = w(R, H)
+                    sd[f"{p}.self_attn.vision_{n}_bridge_on_{m}.weight_B"] = w(H, R)
+            for n, (i_, o_) in dict(gate=(H, I), up=(H, I), down=(I, H)).items():
+                sd[f"{p}.mlp.{n}_proj.weight"] = w(o_, i_)
+                sd[f"{p}.mlp.vision_{n}_proj.weight_A"] = w(o_ // 4, i_)
+                sd[f"{p}.mlp.vision_{n}_proj.weight_B"] = w(o_, o_ // 4)
+            for n in ("input_layernorm", "post_attention_layernorm", "vision_input_layernorm", "vision_post_attention_layernorm"):
+                sd[f"{p}.{n}.weight"] = torch.ones(H, dtype=dtype).requires_grad_(True)
+        self.sd = sd
+        self.T = 611
+        self.flag = torch.zeros(1, self.T, dtype=torch.bool)
+        self.flag[0, 1:579] = True
+        self.pos = torch.arange(self.T)[None]
+        self.h = torch.randn(1, self.T, H, generator=g).to(dtype)
+
+    def step(self) -> float:
+        """seconds for one forward+backward of the sample"""
+        for t in self.sd.values():
+            t.grad = None
+        h = self.h.clone().requires_grad_(True)
         t0 = time.perf_counter()
         x = h
-        for i in range(n_layers):
-            x = O.decoder_layer(sd, i, d, x, flag, pos, None)
+        for i in range(self.n_layers):
+            x = self.O.decoder_layer(self.sd, i, self.d, x, self.flag, self.pos, None)
         x.float().pow(2).mean().backward()
-        times.append(time.perf_counter() - t0)
-    t = statistics.median(times)
-    value = T / (t * 32.0 / n_layers)
-    return dict(value=value, unit=UNIT, cores=threads, kind="port",
-                sample=f"oracle fwd+bwd of {n_layers} full-width Libra-11B decoder layer(s), {str(dtype).split('.')[-1]}, B=1 T=611 (1 image + 32 text), "
-                       f"{t:.2f} s, scaled x{32 // n_layers} to 32 layers (embeddings/heads excluded)")
+        return time.perf_counter() - t0
+
+    def result(self, seconds: float) -> dict:
+        value = self.T / (seconds * 32.0 / self.n_layers)
+        return dict(value=value, unit=UNIT, cores=self.threads, kind="port",
+                    sample=f"oracle fwd+bwd of {self.n_layers} full-width Libra-11B decoder layer(s), {str(self.dtype).split('.')[-1]}, "
+                           f"B=1 T=611 (1 image + 32 text), {seconds:.2f} s, scaled x{32 // self.n_layers} to 32 layers "
+                           f"(embeddings/heads excluded)")
+
+
+def cpu_reference_sample(n_layers: int = 1) -> dict:
+    ref = CpuReference(n_layers)
+    ref.step()                       # warm-up (thread pool, allocator)
+    return ref.result(ref.step())
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    vals = []
+    ref = CpuReference(n_layers=1)
+    secs = []
     for i in range(args.warmup + args.steps):
-        r = cpu_reference_sample(n_layers=1)
+        t = ref.step()
         if i >= args.warmup:
-            vals.append(r)
-    v = statistics.median([x["value"] for x in vals]) if vals else float("nan")
-    cb = dict(vals[-1], value=v) if vals else None
+            secs.append(t)
+    cb = ref.result(statistics.median(secs)) if secs else None
+    v = cb["value"] if cb else float("nan")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic",
+            "warmup": args.warmup, "ms_per_step": (statistics.median(secs) * 1e3 if secs else None), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
             "config": {"workload": "Libra-11B train step B=8 T=2048 per GPU (BASELINE.json configs[2]); the CPU arm times a bounded "
                                    "sample (see cpu_baseline.sample)"},
             "cpu_baseline": cb, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

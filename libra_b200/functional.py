@@ -98,6 +98,21 @@ def bias_quick_gelu(x, bias):
 
 
 # ----------------------------------------------------------------------------- routed linear
+# Weight-gradient accumulation fusion: when a parameter already owns a .grad buffer (e.g. a view into the flat
+# data-parallel gradient buffer, libra_b200.dist.FlatGradBuffer), dW is accumulated straight into it by the GEMM
+# (beta = 1) instead of being materialised and added by autograd afterwards (saves ~3 passes over the weight size).
+FUSE_WGRAD_ACCUMULATE = True
+
+
+def _wgrad(W: torch.Tensor, a_t: torch.Tensor, b: torch.Tensor):
+    """dW = a_t @ b, either returned (autograd accumulates) or accumulated in place into W.grad (returns None)."""
+    g = W.grad
+    if FUSE_WGRAD_ACCUMULATE and g is not None and g.dtype == a_t.dtype and g.is_contiguous():
+        g.addmm_(a_t, b)
+        return None
+    return torch.matmul(a_t, b)
+
+
 class RoutedLinear(torch.autograd.Function):
     """y[:n_lang] = x[:n_lang] W^T ;  y[n_lang:] = (x[n_lang:] A^T) B^T
     (language nn.Linear | vision LibraLinear, modeling_libra.py:192-199, routed by :129-147).
@@ -130,7 +145,7 @@ class RoutedLinear(torch.autograd.Function):
             if dx is not None:
                 torch.matmul(dy[:n_lang], W, out=dx[:n_lang])
             if ctx.needs_input_grad[2]:
-                dW = torch.matmul(dy[:n_lang].t(), x[:n_lang])
+                dW = _wgrad(W, dy[:n_lang].t(), x[:n_lang])
         elif ctx.needs_input_grad[2]:
             dW = torch.zeros_like(W)
         if N - n_lang > 0:
@@ -139,9 +154,9 @@ class RoutedLinear(torch.autograd.Function):
             if dx is not None:
                 torch.matmul(dmid, A, out=dx[n_lang:])
             if ctx.needs_input_grad[4]:
-                dB = torch.matmul(dyv.t(), mid)
+                dB = _wgrad(B, dyv.t(), mid)
             if ctx.needs_input_grad[3]:
-                dA = torch.matmul(dmid.t(), x[n_lang:])
+                dA = _wgrad(A, dmid.t(), x[n_lang:])
         else:
             if ctx.needs_input_grad[3]:
                 dA = torch.zeros_like(A)
@@ -347,7 +362,7 @@ class HeadCrossEntropy(torch.autograd.Function):
     def backward(ctx, g):
         x, W, dlogits = ctx.saved_tensors
         dx = torch.matmul(dlogits, W) if ctx.needs_input_grad[0] else None
-        dW = torch.matmul(dlogits.t(), x) if ctx.needs_input_grad[1] else None
+        dW = torch.matmul(dlogits.t(), x) if ctx.needs_input_grad[1] else None      # scaled by g below: not fusable
         # upstream gradient of the (already pre-scaled) partial loss is a scalar
         if dx is not None:
             dx = dx * g.to(dx.dtype)
