@@ -55,6 +55,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--tiny", action="store_true", help="tiny model for plumbing checks (NOT a bench value)")
+    ap.add_argument("--overlap-allreduce", type=int, default=1,
+                    help="N>1: reduce the flat gradient buffer in a few large reverse-layer chunks during the last micro-batch's backward")
+    ap.add_argument("--allreduce-chunks", type=int, default=8)
     ap.add_argument("--cuda-profiler-range", action="store_true",
                     help="bracket the timed region with cudaProfilerStart/Stop (use with ncu --profile-from-start off)")
     return ap.parse_args()
@@ -246,9 +249,8 @@ def main():
             off += n
     opt = None
     if args.optimizer == "adamw":
-        master = torch.nn.Parameter(flat_w)
-        master.grad = flat
-        opt = torch.optim.AdamW([master], lr=1e-5, betas=(0.9, 0.95), weight_decay=0.0, fused=True)
+        from libra_b200.optim import FlatAdamW
+        opt = FlatAdamW(flat_w, flat, lr=1e-5, betas=(0.9, 0.95), weight_decay=0.0)     # one fused kernel per step
 
     B, T, MB = args.batch, args.seq, args.micro_batch
     assert B % MB == 0
@@ -262,17 +264,70 @@ def main():
                     contiguous_signal=inp["contiguous_signal"][sl], labels=inp["labels"][:, sl])
         return out.loss
 
+    # ---- gradient all-reduce plan (N > 1): the flat buffer is [embeddings | layer 0 | ... | layer L-1 | norms+heads] in
+    # registration order; chunk c covers a contiguous group of layers and is reduced as soon as the LAST micro-batch's
+    # backward has passed the group's first layer.  Still one logical all-reduce of the buffer, issued as a few large pieces.
+    offsets = {}
+    off = 0
+    for n_, p_ in model.named_parameters():
+        if p_.requires_grad:
+            offsets[n_] = (off, off + p_.numel())
+            off += p_.numel()
+    L = cfg.num_hidden_layers
+    layer_lo = [min(v[0] for k, v in offsets.items() if k.startswith(f"model.layers.{i}.")) for i in range(L)]
+    n_chunks = max(1, min(args.allreduce_chunks, L))
+    group = (L + n_chunks - 1) // n_chunks
+    first_layers = list(range(0, L, group))                     # chunk c starts at layer first_layers[c]
+    pending = []
+    state = {"armed": False}
+
+    def on_layer_grad_ready(li):
+        if not state["armed"] or li not in first_layers:
+            return
+        c = first_layers.index(li)
+        lo = layer_lo[li] if c > 0 else 0                        # chunk 0 also carries the embeddings
+        hi = layer_lo[first_layers[c + 1]] if c + 1 < len(first_layers) else layer_lo[L - 1] + sum(
+            p_.numel() for k, p_ in model.named_parameters() if p_.requires_grad and k.startswith(f"model.layers.{L - 1}."))
+        if c == 0:
+            return                                                # reduced after backward together with the tail (embeddings finish last)
+        pending.append(dist.all_reduce(flat[lo:hi], async_op=True))
+        state.setdefault("done_hi", []).append((lo, hi))
+
+    if world > 1 and args.overlap_allreduce:
+        model.model.layer_grad_ready_hook = on_layer_grad_ready
+
+    def reduce_gradients():
+        if world == 1:
+            return
+        if not args.overlap_allreduce:
+            dist.all_reduce(flat)
+            return
+        done = sorted(state.pop("done_hi", []))
+        # everything not yet issued: [0, first issued lo) and [last issued hi, end)
+        lo_issued = done[0][0] if done else n_train
+        hi_issued = done[-1][1] if done else n_train
+        if lo_issued > 0:
+            pending.append(dist.all_reduce(flat[:lo_issued], async_op=True))
+        if hi_issued < n_train:
+            pending.append(dist.all_reduce(flat[hi_issued:], async_op=True))
+        for w_ in pending:
+            w_.wait()
+        pending.clear()
+
     def step(inp, from_host: bool):
         if from_host:
             inp = {k: v.to(dev, non_blocking=True) for k, v in inp.items()}
         flat.zero_()
         total = None
-        for i in range(B // MB):
+        n_micro = B // MB
+        for i in range(n_micro):
+            state["armed"] = (i == n_micro - 1)
             loss = micro(inp, i) * (MB / B) / world
             loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
+        state["armed"] = False
         if world > 1:
-            dist.all_reduce(flat)
+            reduce_gradients()
         if opt is not None:
             opt.step()
         return float(total.item()) if from_host else total

@@ -199,6 +199,11 @@ int lb_patch_embed_fwd(const void* pixels, const void* weight_packed, const void
 int lb_cross_entropy_fwd_bwd(void* logits, int64_t ld, const int64_t* labels, float* row_loss, int64_t rows, int vocab,
                              float grad_scale, void* stream);
 
+/* ---- fused AdamW over flat bf16 buffers (torch.optim.AdamW semantics, reference recipe trainer.py:38-85 /
+ * libra_pretrain.yaml:81-91 uses AdamW; fp32 maths, bf16 storage).  n elements (multiple of 8); step counts from 1. */
+int lb_adamw_bf16(void* param, const void* grad, void* exp_avg, void* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int step, void* stream);
+
 /* ---- diagnostics: single-tile tcgen05 probes (tests/test_umma_probe.py) ---- */
 int lb_probe_umma(int mode, const void* A, const void* B, float* D, int K, void* stream);
 

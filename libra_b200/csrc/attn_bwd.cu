@@ -36,6 +36,66 @@ struct AttnBwdParams {
     float scale;
 };
 
+// ---- score-tile helpers with the mask as a template parameter (the common unmasked path carries no index arithmetic)
+// dQ kernel: thread = query row; 32 key columns at TMEM `ts` (S) / `tdp` (dP); dS (bf16) is written over S.
+template <bool MASK, bool CAUSAL>
+__device__ __forceinline__ void dq_tile(uint32_t ts, uint32_t tdp, float sl2, float lse2, float dlt, float scale, int kv0, int qi,
+                                        int kvs, int kve) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        uint32_t s[16], dp[16];
+        tmem_ld16(ts + c * 16, s);
+        tmem_ld16(tdp + c * 16, dp);
+        tc_wait_ld();
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+            float p0 = fast_ex2(fmaf(__uint_as_float(s[j]), sl2, -lse2));
+            float p1 = fast_ex2(fmaf(__uint_as_float(s[j + 1]), sl2, -lse2));
+            if (MASK) {
+                const int kj = kv0 + c * 16 + j;
+                p0 = ((!CAUSAL || kj <= qi) && kj < kve && kj >= kvs) ? p0 : 0.f;
+                p1 = ((!CAUSAL || kj + 1 <= qi) && kj + 1 < kve && kj + 1 >= kvs) ? p1 : 0.f;
+            }
+            const float d0 = p0 * (__uint_as_float(dp[j]) - dlt) * scale;
+            const float d1 = p1 * (__uint_as_float(dp[j + 1]) - dlt) * scale;
+            pk[j >> 1] = pack_bf16(d0, d1);
+        }
+        tmem_st8(ts + c * 8, pk);       // dS (bf16) over my own, already consumed S columns
+    }
+}
+
+// dK/dV kernel: thread = key row; 64 query columns at TMEM `ts` (S^T) / `tdp` (dP^T); per-column lse2 / delta in smem.
+template <bool MASK, bool CAUSAL>
+__device__ __forceinline__ void dkv_tile(uint32_t ts, uint32_t tdp, const float* __restrict__ st, float sl2, float scale, int kj,
+                                         int qbase, bool key_ok) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        uint32_t s[32], dp[32];
+        tmem_ld32(ts + c * 32, s);
+        tmem_ld32(tdp + c * 32, dp);
+        tc_wait_ld();
+        uint32_t pp[16], pd[16];
+        const float* lse_c = st + c * 32;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+            float p0 = fast_ex2(fmaf(__uint_as_float(s[j]), sl2, -lse_c[j]));          // lse = +inf on excluded query rows
+            float p1 = fast_ex2(fmaf(__uint_as_float(s[j + 1]), sl2, -lse_c[j + 1]));
+            if (MASK) {
+                const int qa = qbase + c * 32 + j;
+                p0 = (key_ok && (!CAUSAL || kj <= qa)) ? p0 : 0.f;
+                p1 = (key_ok && (!CAUSAL || kj <= qa + 1)) ? p1 : 0.f;
+            }
+            const float d0 = p0 * (__uint_as_float(dp[j]) - lse_c[128 + j]) * scale;
+            const float d1 = p1 * (__uint_as_float(dp[j + 1]) - lse_c[128 + j + 1]) * scale;
+            pp[j >> 1] = pack_bf16(p0, p1);
+            pd[j >> 1] = pack_bf16(d0, d1);
+        }
+        tmem_st16(ts + c * 16, pp);       // P^T over my own, already consumed S^T columns
+        tmem_st16(tdp + c * 16, pd);      // dS^T over dP^T
+    }
+}
+
 // =====================================================================================================
 // dQ kernel
 // =====================================================================================================
@@ -175,28 +235,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const bool need_mask = (CAUSAL && kv0 + 31 > q0) || (kv0 + 32 > kve) || (kv0 < kvs);
             mbar_wait(bars + DQ_SDP, ph);
             tc_fence_after_sync();
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t s[16], dp[16];
-                tmem_ld16(lane_addr + colS + c * 16, s);
-                tmem_ld16(lane_addr + colDP + c * 16, dp);
-                tc_wait_ld();
-                uint32_t pk[8];
-#pragma unroll
-                for (int j = 0; j < 16; j += 2) {
-                    float p0 = fast_ex2(fmaf(__uint_as_float(s[j]), sl2, -lse2));
-                    float p1 = fast_ex2(fmaf(__uint_as_float(s[j + 1]), sl2, -lse2));
-                    if (need_mask) {
-                        const int kj = kv0 + c * 16 + j;
-                        p0 = ((!CAUSAL || kj <= qi) && kj < kve && kj >= kvs) ? p0 : 0.f;
-                        p1 = ((!CAUSAL || kj + 1 <= qi) && kj + 1 < kve && kj + 1 >= kvs) ? p1 : 0.f;
-                    }
-                    const float d0 = p0 * (__uint_as_float(dp[j]) - dlt) * p.scale;
-                    const float d1 = p1 * (__uint_as_float(dp[j + 1]) - dlt) * p.scale;
-                    pk[j >> 1] = pack_bf16(d0, d1);
-                }
-                tmem_st8(lane_addr + colS + c * 8, pk);       // dS (bf16) over my own, already consumed S columns
-            }
+            if (need_mask) dq_tile<true, CAUSAL>(lane_addr + colS, lane_addr + colDP, sl2, lse2, dlt, p.scale, kv0, qi, kvs, kve);
+            else           dq_tile<false, CAUSAL>(lane_addr + colS, lane_addr + colDP, sl2, lse2, dlt, p.scale, kv0, qi, kvs, kve);
             tc_wait_st();
             tc_fence_before_sync();
             mbar_arrive(bars + DQ_DS);
@@ -413,31 +453,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const int qbase = q0 + half * 64;
             // warp-uniform: tile straddles the key range or the causal diagonal (excluded query rows carry lse = +inf)
             const bool need_mask = (kv0 + 128 > kve) || (kv0 < kvs) || (CAUSAL && kv0 + 127 > qbase);
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t s[32], dp[32];
-                tmem_ld32(lane_addr + colS + c * 32, s);
-                tmem_ld32(lane_addr + colDP + c * 32, dp);
-                tc_wait_ld();
-                uint32_t pp[16], pd[16];
-                const float* lse_c = sl + half * 64 + c * 32;
-#pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    float p0 = fast_ex2(fmaf(__uint_as_float(s[j]), sl2, -lse_c[j]));          // lse = +inf on excluded rows
-                    float p1 = fast_ex2(fmaf(__uint_as_float(s[j + 1]), sl2, -lse_c[j + 1]));
-                    if (need_mask) {
-                        const int qa = qbase + c * 32 + j;
-                        p0 = (key_ok && (!CAUSAL || kj <= qa)) ? p0 : 0.f;
-                        p1 = (key_ok && (!CAUSAL || kj <= qa + 1)) ? p1 : 0.f;
-                    }
-                    const float d0 = p0 * (__uint_as_float(dp[j]) - lse_c[128 + j]) * p.scale;
-                    const float d1 = p1 * (__uint_as_float(dp[j + 1]) - lse_c[128 + j + 1]) * p.scale;
-                    pp[j >> 1] = pack_bf16(p0, p1);
-                    pd[j >> 1] = pack_bf16(d0, d1);
-                }
-                tmem_st16(lane_addr + colS + c * 16, pp);      // P^T over my own, already consumed S^T columns
-                tmem_st16(lane_addr + colDP + c * 16, pd);     // dS^T over dP^T
-            }
+            if (need_mask) dkv_tile<true, CAUSAL>(lane_addr + colS, lane_addr + colDP, sl + half * 64, sl2, p.scale, kj, qbase, key_ok);
+            else           dkv_tile<false, CAUSAL>(lane_addr + colS, lane_addr + colDP, sl + half * 64, sl2, p.scale, kj, qbase, key_ok);
             tc_wait_st();
             tc_fence_before_sync();
             mbar_arrive(bars + KV_PDS);

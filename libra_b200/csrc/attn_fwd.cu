@@ -7,10 +7,10 @@
 // and each item only writes the rows of its variant.  Every MMA operand is then a plain TMA tile: per kv tile exactly
 // one S = Q.K^T and one O += P.V, no element-wise bridge select.
 //
-// CTA = 192 threads:  warps 0-3 softmax/correction/epilogue (thread <-> query row <-> TMEM lane),
-//                     warp 4 TMA producer, warp 5 tcgen05.mma issuer (+ TMEM alloc).
-// TMEM columns: [0,128) S (fp32), P (bf16, 64 columns) aliased over it; [128,128+D) O accumulator.
-// Two CTAs per SM (<= 96 KB smem, 256 TMEM columns each): while one CTA runs its softmax the other owns the tensor pipe.
+// CTA = 320 threads:  warps 0-7 softmax/correction/epilogue: two warpgroups, thread <-> (query row = TMEM lane, half of
+//                     the tile's key columns); warp 8 TMA producer, warp 9 tcgen05.mma issuer (+ TMEM alloc).
+// TMEM columns: [0,128) S (fp32), P (bf16) aliased over the start of each half; [128,128+D) O accumulator.
+// Two CTAs per SM (<= 100 KB smem, 256 TMEM columns each): while one CTA runs its softmax the other owns the tensor pipe.
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -49,6 +49,59 @@ struct AttnFwdSmem {
 
 // barrier indices
 enum { B_Q = 0, B_KFULL, B_KEMPTY, B_VFULL, B_VEMPTY, B_SFULL, B_PFULL, B_OREADY, B_COUNT };
+
+// ---- softmax tile helpers: MASK is a template parameter so the (common) unmasked path carries no index arithmetic.
+// Each thread owns one query row (TMEM lane) and 64 key columns starting at TMEM address `ts` / key index `kv0`.
+template <bool MASK, bool CAUSAL>
+__device__ __forceinline__ float softmax_tile_max(uint32_t ts, int kv0, int qi, int kvs, int kve) {
+    float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld32(ts + c * 32, v);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+            float a = __uint_as_float(v[j]), b = __uint_as_float(v[j + 1]);
+            if (MASK) {
+                const int kj = kv0 + c * 32 + j;
+                a = ((!CAUSAL || kj <= qi) && kj < kve && kj >= kvs) ? a : -CUDART_INF_F;
+                b = ((!CAUSAL || kj + 1 <= qi) && kj + 1 < kve && kj + 1 >= kvs) ? b : -CUDART_INF_F;
+            }
+            mx0 = fmaxf(mx0, a);
+            mx1 = fmaxf(mx1, b);
+        }
+    }
+    return fmaxf(mx0, mx1);
+}
+
+// P = 2^(S*sl2 - m_off) for my 64 columns, written as bf16 over the first 32 of my own S columns; returns the row-sum part
+template <bool MASK, bool CAUSAL>
+__device__ __forceinline__ float softmax_tile_exp(uint32_t ts, float sl2, float m_off, int kv0, int qi, int kvs, int kve) {
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld32(ts + c * 32, v);
+        tc_wait_ld();
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+            float p0 = fast_ex2(fmaf(__uint_as_float(v[j]), sl2, -m_off));
+            float p1 = fast_ex2(fmaf(__uint_as_float(v[j + 1]), sl2, -m_off));
+            if (MASK) {
+                const int kj = kv0 + c * 32 + j;
+                p0 = ((!CAUSAL || kj <= qi) && kj < kve && kj >= kvs) ? p0 : 0.f;
+                p1 = ((!CAUSAL || kj + 1 <= qi) && kj + 1 < kve && kj + 1 >= kvs) ? p1 : 0.f;
+            }
+            l0 += p0;
+            l1 += p1;
+            pk[j >> 1] = pack_bf16(p0, p1);
+        }
+        tmem_st16(ts + c * 16, pk);       // chunk c of P overwrites S columns already consumed
+    }
+    return l0 + l1;
+}
 
 // TMEM columns: S (fp32) at [0,128); each softmax warpgroup h writes its half of P (bf16, 32 columns) over the start of
 // ITS OWN half of S: P(keys 64h .. 64h+63) at [64h, 64h+32).  O accumulator at [128, 128+D).
@@ -175,32 +228,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             mbar_wait(bars + B_SFULL, ph);
             tc_fence_after_sync();
             // ---- pass 1: max over my 64 columns
-            float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F;
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t v[32];
-                tmem_ld32(lane_addr + colS + c * 32, v);
-                tc_wait_ld();
-                if (need_mask) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        const int kj = kv0 + c * 32 + j;
-                        const bool ok0 = (!CAUSAL || kj <= qi) && kj < kve && kj >= kvs;
-                        const bool ok1 = (!CAUSAL || kj + 1 <= qi) && kj + 1 < kve && kj + 1 >= kvs;
-                        mx0 = fmaxf(mx0, ok0 ? __uint_as_float(v[j]) : -CUDART_INF_F);
-                        mx1 = fmaxf(mx1, ok1 ? __uint_as_float(v[j + 1]) : -CUDART_INF_F);
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        mx0 = fmaxf(mx0, __uint_as_float(v[j]));
-                        mx1 = fmaxf(mx1, __uint_as_float(v[j + 1]));
-                    }
-                }
-            }
+            const float mx = need_mask ? softmax_tile_max<true, CAUSAL>(lane_addr + colS, kv0, qi, kvs, kve)
+                                       : softmax_tile_max<false, CAUSAL>(lane_addr + colS, kv0, qi, kvs, kve);
             // ---- exchange the partial max with the thread owning the other half of this row
             float* rbuf = red + (it & 1) * 256;
-            rbuf[half * 128 + r] = fmaxf(mx0, mx1);
+            rbuf[half * 128 + r] = mx;
             named_bar_sync(1, AT_SOFTMAX_THREADS);
             const float m_new = fmaxf(m_used, fmaxf(rbuf[r], rbuf[128 + r]));
             // ---- lazy correction: rescale O only when the running max moved by more than 2^8 (both halves decide alike)
@@ -228,38 +260,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
             const float m_off = (m_used == -CUDART_INF_F) ? 0.f : m_used * sl2;
             // ---- pass 2: P = 2^(S*sl2 - m), partial row sum, P (bf16) over my own S columns
-            float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t v[32];
-                tmem_ld32(lane_addr + colS + c * 32, v);
-                tc_wait_ld();
-                uint32_t pk[16];
-                if (need_mask) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        const int kj = kv0 + c * 32 + j;
-                        const bool ok0 = (!CAUSAL || kj <= qi) && kj < kve && kj >= kvs;
-                        const bool ok1 = (!CAUSAL || kj + 1 <= qi) && kj + 1 < kve && kj + 1 >= kvs;
-                        const float p0 = ok0 ? fast_ex2(fmaf(__uint_as_float(v[j]), sl2, -m_off)) : 0.f;
-                        const float p1 = ok1 ? fast_ex2(fmaf(__uint_as_float(v[j + 1]), sl2, -m_off)) : 0.f;
-                        l0 += p0;
-                        l1 += p1;
-                        pk[j >> 1] = pack_bf16(p0, p1);
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 2) {
-                        const float p0 = fast_ex2(fmaf(__uint_as_float(v[j]), sl2, -m_off));
-                        const float p1 = fast_ex2(fmaf(__uint_as_float(v[j + 1]), sl2, -m_off));
-                        l0 += p0;
-                        l1 += p1;
-                        pk[j >> 1] = pack_bf16(p0, p1);
-                    }
-                }
-                tmem_st16(lane_addr + colS + c * 16, pk);       // chunk c of P overwrites S columns already consumed
-            }
-            l += l0 + l1;
+            l += need_mask ? softmax_tile_exp<true, CAUSAL>(lane_addr + colS, sl2, m_off, kv0, qi, kvs, kve)
+                           : softmax_tile_exp<false, CAUSAL>(lane_addr + colS, sl2, m_off, kv0, qi, kvs, kve);
             tc_wait_st();
             tc_fence_before_sync();
             mbar_arrive(bars + B_PFULL);

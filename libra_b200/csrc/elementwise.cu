@@ -436,6 +436,32 @@ __global__ void __launch_bounds__(256) cross_entropy_kernel(__nv_bfloat16* __res
     }
 }
 
+// ------------------------------------------------ fused AdamW over flat bf16 buffers
+// torch.optim.AdamW semantics (decoupled weight decay, bias-corrected moments), fp32 maths, bf16 storage of p, m, v.
+__global__ void __launch_bounds__(256) adamw_bf16_kernel(__nv_bfloat16* __restrict__ p, const __nv_bfloat16* __restrict__ g,
+                                                         __nv_bfloat16* __restrict__ m, __nv_bfloat16* __restrict__ v,
+                                                         int64_t nvec, float lr, float beta1, float beta2, float eps,
+                                                         float weight_decay, float bc1, float bc2_sqrt) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        float fp[8], fg[8], fm[8], fv[8];
+        unpack8(reinterpret_cast<const uint4*>(p)[i], fp);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(g) + i), fg);
+        unpack8(reinterpret_cast<const uint4*>(m)[i], fm);
+        unpack8(reinterpret_cast<const uint4*>(v)[i], fv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            fp[j] *= (1.f - lr * weight_decay);
+            fm[j] = beta1 * fm[j] + (1.f - beta1) * fg[j];
+            fv[j] = beta2 * fv[j] + (1.f - beta2) * fg[j] * fg[j];
+            const float denom = sqrtf(fv[j]) / bc2_sqrt + eps;
+            fp[j] -= (lr / bc1) * (fm[j] / denom);
+        }
+        reinterpret_cast<uint4*>(p)[i] = pack8(fp);
+        reinterpret_cast<uint4*>(m)[i] = pack8(fm);
+        reinterpret_cast<uint4*>(v)[i] = pack8(fv);
+    }
+}
+
 static int ew_grid(int64_t work_items, int threads) {
     int64_t g = (work_items + threads - 1) / threads;
     const int64_t cap = (int64_t)sm_count() * 16;
@@ -638,6 +664,22 @@ int lb_attn_bwd_prepare(const void* O, const void* dO, const int32_t* row_of, vo
     attn_bwd_prepare_kernel<<<(unsigned)((int64_t)batch * seqlen), 256, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)O, (const __nv_bfloat16*)dO, row_of, (__nv_bfloat16*)dO_orig, delta, seqlen, heads, head_dim);
     return check_launch("attn_bwd_prepare");
+}
+
+int lb_adamw_bf16(void* param, const void* grad, void* exp_avg, void* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int step, void* stream) {
+    LB_REQUIRE(n >= 0 && n % 8 == 0 && step >= 1, LB_EINVAL, "adamw: n=%lld must be a multiple of 8 and step >= 1", (long long)n);
+    LB_REQUIRE(param && grad && exp_avg && exp_avg_sq && AL16(param) && AL16(grad) && AL16(exp_avg) && AL16(exp_avg_sq), LB_EALIGN,
+               "adamw: null/unaligned pointer");
+    if (n == 0) return LB_OK;
+    const float bc1 = 1.f - powf(beta1, (float)step);
+    const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+    const int64_t nvec = n / 8;
+    adamw_bf16_kernel<<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)param, (const __nv_bfloat16*)grad,
+                                                                          (__nv_bfloat16*)exp_avg, (__nv_bfloat16*)exp_avg_sq,
+                                                                          nvec, lr, beta1, beta2, eps, weight_decay, bc1,
+                                                                          bc2_sqrt);
+    return check_launch("adamw_bf16");
 }
 
 int lb_cross_entropy_fwd_bwd(void* logits, int64_t ld, const int64_t* labels, float* row_loss, int64_t rows, int vocab,

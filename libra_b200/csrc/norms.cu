@@ -184,14 +184,23 @@ __global__ void __launch_bounds__(NT) rmsnorm_bwd_kernel(const __nv_bfloat16* __
     }
 }
 
-// out[c] += sum_b partial[b][c]   (width = number of fp32 columns per block record)
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, int nblocks, int width, int off, int stride,
-                                       float* __restrict__ out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= width) return;
+// out[c] += sum_b partial[b][off + c]: CTA = 32 columns x 8 row lanes, rows strided by 8, then a shared-memory fold.
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int nblocks, int width, int off,
+                                                              int stride, float* __restrict__ out) {
+    __shared__ float sm[8][33];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cx;
     float s = 0.f;
-    for (int b = 0; b < nblocks; ++b) s += partial[(int64_t)b * stride + off + c];
-    out[c] += s;
+    if (c < width)
+        for (int b = ry; b < nblocks; b += 8) s += partial[(int64_t)b * stride + off + c];
+    sm[ry][cx] = s;
+    __syncthreads();
+    if (ry == 0 && c < width) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += sm[i][cx];
+        out[c] += t;
+    }
 }
 
 // -------------------------------------------------------------- LayerNorm fwd
@@ -381,7 +390,7 @@ int lb_rmsnorm_bwd(const void* dy, const void* x, const void* w_lang, const void
                                             (float*)partial, rows, cols);
     rc = check_launch("rmsnorm_bwd");
     if (rc) return rc;
-    const int tb = 256, gb = ceil_div(cols, tb);
+    const int tb = 256, gb = ceil_div(cols, 32);
     if (dw_lang) reduce_partials_kernel<<<gb, tb, 0, st>>>((const float*)partial, grid, cols, 0, 2 * cols, dw_lang);
     if (dw_vis) reduce_partials_kernel<<<gb, tb, 0, st>>>((const float*)partial, grid, cols, cols, 2 * cols, dw_vis);
     return check_launch("rmsnorm_bwd_reduce");
@@ -413,7 +422,7 @@ int lb_layernorm_bwd(const void* dy, const void* x, const void* w, const float* 
                                               mean, rstd, (__nv_bfloat16*)dx, (float*)partial, rows, cols);
     rc = check_launch("layernorm_bwd");
     if (rc) return rc;
-    const int tb = 256, gb = ceil_div(cols, tb);
+    const int tb = 256, gb = ceil_div(cols, 32);
     if (dw) reduce_partials_kernel<<<gb, tb, 0, st>>>((const float*)partial, grid, cols, 0, 2 * cols, dw);
     if (db) reduce_partials_kernel<<<gb, tb, 0, st>>>((const float*)partial, grid, cols, cols, 2 * cols, db);
     return check_launch("layernorm_bwd_reduce");

@@ -43,6 +43,35 @@ def rmsnorm(x, w_lang, w_vis=None, flag=None, eps=1e-6):
     return RoutedRMSNorm.apply(x, w_lang, w_vis, flag, eps)
 
 
+class ResidualRMSNorm(torch.autograd.Function):
+    """(x, norm(x)): the first output is x itself (the residual branch).  Having both consumers of x behind one node lets
+    backward fold the residual gradient into the norm's backward kernel (lb_rmsnorm_bwd `residual_grad`) instead of
+    autograd materialising dx_norm and adding the two gradients with a separate pass."""
+
+    @staticmethod
+    def forward(ctx, x, w_lang, w_vis, flag, eps):
+        y, rstd = ops.rmsnorm_fwd(x, w_lang, w_vis, flag, eps)
+        ctx.save_for_backward(x, w_lang, w_vis, flag, rstd)
+        return x.view_as(x), y
+
+    @staticmethod
+    def backward(ctx, dres, dy):
+        x, w_lang, w_vis, flag, rstd = ctx.saved_tensors
+        need_dw = ctx.needs_input_grad[1] or (w_vis is not None and ctx.needs_input_grad[2])
+        if dy is None:
+            return dres, None, None, None, None
+        res = None if dres is None else dres.contiguous()
+        dx, dwl, dwv = ops.rmsnorm_bwd(dy.contiguous(), x, w_lang, w_vis, flag, rstd, residual_grad=res, need_dw=need_dw)
+        gl = dwl.to(w_lang.dtype) if (need_dw and ctx.needs_input_grad[1]) else None
+        gv = dwv.to(w_vis.dtype) if (need_dw and w_vis is not None and ctx.needs_input_grad[2]) else None
+        return dx, gl, gv, None, None
+
+
+def residual_rmsnorm(x, w_lang, w_vis=None, flag=None, eps=1e-6):
+    """returns (x_for_residual, normed)"""
+    return ResidualRMSNorm.apply(x, w_lang, w_vis, flag, eps)
+
+
 class LayerNorm(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, eps):
@@ -114,21 +143,26 @@ def _wgrad(W: torch.Tensor, a_t: torch.Tensor, b: torch.Tensor):
 
 
 class RoutedLinear(torch.autograd.Function):
-    """y[:n_lang] = x[:n_lang] W^T ;  y[n_lang:] = (x[n_lang:] A^T) B^T
+    """y[:n_lang] = x[:n_lang] W^T ;  y[n_lang:] = (x[n_lang:] A^T) B^T   (+ residual, fused into the GEMM as beta = 1)
     (language nn.Linear | vision LibraLinear, modeling_libra.py:192-199, routed by :129-147).
     The two row ranges are contiguous, so there is no gather/scatter and no boolean indexing."""
 
     @staticmethod
-    def forward(ctx, x, n_lang, W, A, B):
+    def forward(ctx, x, n_lang, W, A, B, residual):
         N = x.shape[0]
-        y = torch.empty(N, W.shape[0] if W is not None else B.shape[0], dtype=x.dtype, device=x.device)
-        xl, xv = x[:n_lang], x[n_lang:]
+        y = torch.empty(N, W.shape[0], dtype=x.dtype, device=x.device)
         if n_lang > 0:
-            torch.matmul(xl, W.t(), out=y[:n_lang])
+            if residual is None:
+                torch.matmul(x[:n_lang], W.t(), out=y[:n_lang])
+            else:
+                torch.addmm(residual[:n_lang], x[:n_lang], W.t(), out=y[:n_lang])
         mid = None
         if N - n_lang > 0:
-            mid = torch.matmul(xv, A.t())
-            torch.matmul(mid, B.t(), out=y[n_lang:])
+            mid = torch.matmul(x[n_lang:], A.t())
+            if residual is None:
+                torch.matmul(mid, B.t(), out=y[n_lang:])
+            else:
+                torch.addmm(residual[n_lang:], mid, B.t(), out=y[n_lang:])
         ctx.n_lang = n_lang
         ctx.save_for_backward(x, W, A, B, mid)
         return y
@@ -162,11 +196,126 @@ class RoutedLinear(torch.autograd.Function):
                 dA = torch.zeros_like(A)
             if ctx.needs_input_grad[4]:
                 dB = torch.zeros_like(B)
-        return dx, None, dW, dA, dB
+        return dx, None, dW, dA, dB, (dy if ctx.needs_input_grad[5] else None)
 
 
-def routed_linear(x, n_lang, W, A, B):
-    return RoutedLinear.apply(x, n_lang, W, A, B)
+def routed_linear(x, n_lang, W, A, B, residual=None):
+    return RoutedLinear.apply(x, n_lang, W, A, B, residual)
+
+
+class RoutedFanout(torch.autograd.Function):
+    """Several routed projections of the SAME input in one autograd node (q/k/v + the two bridge down-projections, or
+    gate + up).  Forward is the same GEMMs as RoutedLinear / RoutedDown; backward accumulates every branch's input
+    gradient into one buffer through the GEMM (beta = 1), replacing autograd's N-1 full-size gradient additions.
+    kinds[i] == "lin":  weights (W, A, B) -> y = [x_l W^T ; (x_v A^T) B^T];   "down": weights (A_lang, A_vis)."""
+
+    @staticmethod
+    def forward(ctx, x, n_lang, kinds, *weights):
+        N = x.shape[0]
+        xl, xv = x[:n_lang], x[n_lang:]
+        outs, mids, wi = [], [], 0
+        for kind in kinds:
+            if kind == "lin":
+                W, A, B = weights[wi:wi + 3]
+                wi += 3
+                y = torch.empty(N, W.shape[0], dtype=x.dtype, device=x.device)
+                mid = None
+                if n_lang > 0:
+                    torch.matmul(xl, W.t(), out=y[:n_lang])
+                if N - n_lang > 0:
+                    mid = torch.matmul(xv, A.t())
+                    torch.matmul(mid, B.t(), out=y[n_lang:])
+                mids.append(mid)
+            else:
+                Al, Av = weights[wi:wi + 2]
+                wi += 2
+                y = torch.empty(N, Al.shape[0], dtype=x.dtype, device=x.device)
+                if n_lang > 0:
+                    torch.matmul(xl, Al.t(), out=y[:n_lang])
+                if N - n_lang > 0:
+                    torch.matmul(xv, Av.t(), out=y[n_lang:])
+                mids.append(None)
+            outs.append(y)
+        ctx.n_lang, ctx.kinds, ctx.n_mid = n_lang, kinds, len(mids)
+        ctx.mid_present = [m is not None for m in mids]
+        ctx.save_for_backward(x, *weights, *[m for m in mids if m is not None])
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *douts):
+        saved = ctx.saved_tensors
+        x = saved[0]
+        nw = sum(3 if k == "lin" else 2 for k in ctx.kinds)
+        weights = saved[1:1 + nw]
+        mids_saved = list(saved[1 + nw:])
+        n, N = ctx.n_lang, x.shape[0]
+        need_dx = ctx.needs_input_grad[0]
+        dx = torch.empty_like(x) if need_dx else None
+        first_l, first_v = True, True
+        grads = []
+        wi = 0
+        ng = ctx.needs_input_grad
+
+        def acc(dst, a, b, first):
+            if first:
+                torch.matmul(a, b, out=dst)
+            else:
+                dst.addmm_(a, b)
+
+        for oi, kind in enumerate(ctx.kinds):
+            dy = douts[oi]
+            if kind == "lin":
+                W, A, B = weights[wi:wi + 3]
+                gW = gA = gB = None
+                mid = mids_saved.pop(0) if ctx.mid_present[oi] else None
+                if dy is not None:
+                    dy = dy.contiguous()
+                    if n > 0:
+                        if need_dx:
+                            acc(dx[:n], dy[:n], W, first_l)
+                            first_l = False
+                        if ng[3 + wi]:
+                            gW = _wgrad(W, dy[:n].t(), x[:n])
+                    if N - n > 0:
+                        dmid = torch.matmul(dy[n:], B)
+                        if need_dx:
+                            acc(dx[n:], dmid, A, first_v)
+                            first_v = False
+                        if ng[3 + wi + 2]:
+                            gB = _wgrad(B, dy[n:].t(), mid)
+                        if ng[3 + wi + 1]:
+                            gA = _wgrad(A, dmid.t(), x[n:])
+                grads += [gW, gA, gB]
+                wi += 3
+            else:
+                Al, Av = weights[wi:wi + 2]
+                gl = gv = None
+                if dy is not None:
+                    dy = dy.contiguous()
+                    if n > 0:
+                        if need_dx:
+                            acc(dx[:n], dy[:n], Al, first_l)
+                            first_l = False
+                        if ng[3 + wi]:
+                            gl = _wgrad(Al, dy[:n].t(), x[:n])
+                    if N - n > 0:
+                        if need_dx:
+                            acc(dx[n:], dy[n:], Av, first_v)
+                            first_v = False
+                        if ng[3 + wi + 1]:
+                            gv = _wgrad(Av, dy[n:].t(), x[n:])
+                grads += [gl, gv]
+                wi += 2
+        if need_dx:
+            if first_l and n > 0:
+                dx[:n].zero_()
+            if first_v and N - n > 0:
+                dx[n:].zero_()
+        return (dx, None, None, *grads)
+
+
+def routed_fanout(x, n_lang, kinds, *weights):
+    return RoutedFanout.apply(x, n_lang, tuple(kinds), *weights)
 
 
 class RoutedDown(torch.autograd.Function):
@@ -255,7 +404,7 @@ class BridgeAttention(torch.autograd.Function):
         dQ = ops.attn_bwd_dq(Q, Kfl, Vfl, Kfv, Vfv, dO, lse, delta, rt.flag_orig, w.work_q, w.kv_start, w.kv_end, B, T, H, D,
                              True, ctx.scale)
         dKfl, dVfl, dKfv, dVfv = ops.attn_bwd_dkv(Q, Kfl, Vfl, Kfv, Vfv, dO, lse, delta, rt.flag_orig, w.qtile_has, w.work_kv,
-                                                 w.kv_start, w.kv_end, B, T, H, D, True, ctx.scale)
+                                                 w.kv_start, w.kv_end, B, T, H, D, True, ctx.scale, kv_cover=w.kv_cover)
         dq, dk, dv, dkb, dvb = ops.attn_prep_bwd(dQ, dKfv, dKfl, dVfv, dVfl, rt.flag_sorted, rt.inv, meta.pos, meta.cos,
                                                  meta.sin, H, D)
         n = rt.n_lang

@@ -143,20 +143,25 @@ class LibraDecoderLayer(nn.Module):
         nl, flag = rt.n_lang, rt.flag_sorted
         a, m = self.self_attn, self.mlp
         eps = self.input_layernorm.variance_epsilon
-        n1 = LF.rmsnorm(h, self.input_layernorm.weight, self.vision_input_layernorm.weight, flag, eps)
-        q = LF.routed_linear(n1, nl, a.q_proj.weight, a.vision_q_proj.weight_A, a.vision_q_proj.weight_B)
-        k = LF.routed_linear(n1, nl, a.k_proj.weight, a.vision_k_proj.weight_A, a.vision_k_proj.weight_B)
-        v = LF.routed_linear(n1, nl, a.v_proj.weight, a.vision_v_proj.weight_A, a.vision_v_proj.weight_B)
-        tk = LF.routed_down(n1, nl, a.vision_k_bridge_on_language.weight_A, a.vision_k_bridge_on_vision.weight_A)
-        tv = LF.routed_down(n1, nl, a.vision_v_bridge_on_language.weight_A, a.vision_v_bridge_on_vision.weight_A)
+        # (residual branch, normed) behind one autograd node => the residual gradient is folded into the norm backward
+        hr, n1 = LF.residual_rmsnorm(h, self.input_layernorm.weight, self.vision_input_layernorm.weight, flag, eps)
+        q, k, v, tk, tv = LF.routed_fanout(
+            n1, nl, ("lin", "lin", "lin", "down", "down"),
+            a.q_proj.weight, a.vision_q_proj.weight_A, a.vision_q_proj.weight_B,
+            a.k_proj.weight, a.vision_k_proj.weight_A, a.vision_k_proj.weight_B,
+            a.v_proj.weight, a.vision_v_proj.weight_A, a.vision_v_proj.weight_B,
+            a.vision_k_bridge_on_language.weight_A, a.vision_k_bridge_on_vision.weight_A,
+            a.vision_v_bridge_on_language.weight_A, a.vision_v_bridge_on_vision.weight_A)
         o = LF.bridge_attention(q, k, v, tk, tv, a.vision_k_bridge_on_language.weight_B, a.vision_k_bridge_on_vision.weight_B,
                                 a.vision_v_bridge_on_language.weight_B, a.vision_v_bridge_on_vision.weight_B, meta)
-        h = h + LF.routed_linear(o, nl, a.o_proj.weight, a.vision_o_proj.weight_A, a.vision_o_proj.weight_B)
-        n2 = LF.rmsnorm(h, self.post_attention_layernorm.weight, self.vision_post_attention_layernorm.weight, flag, eps)
-        g = LF.routed_linear(n2, nl, m.gate_proj.weight, m.vision_gate_proj.weight_A, m.vision_gate_proj.weight_B)
-        u = LF.routed_linear(n2, nl, m.up_proj.weight, m.vision_up_proj.weight_A, m.vision_up_proj.weight_B)
+        # residual add fused into the output-projection GEMMs (beta = 1)
+        h = LF.routed_linear(o, nl, a.o_proj.weight, a.vision_o_proj.weight_A, a.vision_o_proj.weight_B, residual=hr)
+        hr, n2 = LF.residual_rmsnorm(h, self.post_attention_layernorm.weight, self.vision_post_attention_layernorm.weight, flag, eps)
+        g, u = LF.routed_fanout(n2, nl, ("lin", "lin"),
+                                m.gate_proj.weight, m.vision_gate_proj.weight_A, m.vision_gate_proj.weight_B,
+                                m.up_proj.weight, m.vision_up_proj.weight_A, m.vision_up_proj.weight_B)
         act = LF.swiglu(g, u)
-        return h + LF.routed_linear(act, nl, m.down_proj.weight, m.vision_down_proj.weight_A, m.vision_down_proj.weight_B)
+        return LF.routed_linear(act, nl, m.down_proj.weight, m.vision_down_proj.weight_A, m.vision_down_proj.weight_B, residual=hr)
 
 
 class LibraPreTrainedModel(PreTrainedModel):
@@ -306,7 +311,12 @@ class LibraModel(LibraPreTrainedModel):
         """Returns the final-normed hidden states in sorted rows [N, C] (and per-layer inputs if requested)."""
         h = self.embed_sorted(input_ids, meta, contiguous_signal)
         hiddens = [h] if collect_hidden else None
-        for layer in self.layers:
+        hook = getattr(self, "layer_grad_ready_hook", None)
+        for li, layer in enumerate(self.layers):
+            if hook is not None and h.requires_grad:
+                # fires when d(loss)/d(input of layer li) has been produced, i.e. after every gradient of layer li has been
+                # enqueued: lets a data-parallel driver start reducing that layer's slice of the flat gradient buffer
+                h.register_hook(lambda g, _li=li: hook(_li))
             if self.gradient_checkpointing and self.training and torch.is_grad_enabled():
                 h = torch.utils.checkpoint.checkpoint(layer, h, meta, use_reentrant=False)
             else:

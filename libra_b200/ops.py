@@ -279,7 +279,7 @@ def attn_bwd_prepare(O, dO, row_of, batch, seqlen, heads, head_dim, want_dO_orig
 
 def attn_bwd_dq(Q, K0, V0, K1, V1, dO, lse, delta, qflag, work, kv_start, kv_end, batch, seqlen, heads, head_dim, causal,
                 scale):
-    dQ = torch.zeros_like(Q)
+    dQ = torch.empty_like(Q)          # every token row belongs to exactly one (tile, variant) work item
     _timed_call("lb_attn_bwd_dq", _p(Q), _p(K0), _p(V0), _p(K1), _p(V1), _p(dO), _p(lse), _p(delta), _p(qflag), _p(work),
               work.shape[0], _p(kv_start), _p(kv_end), _p(dQ), batch, seqlen, heads, head_dim, int(causal), float(scale),
               _st())
@@ -287,10 +287,12 @@ def attn_bwd_dq(Q, K0, V0, K1, V1, dO, lse, delta, qflag, work, kv_start, kv_end
 
 
 def attn_bwd_dkv(Q, K0, V0, K1, V1, dO, lse, delta, qflag, qtile_has, work_kv, kv_start, kv_end, batch, seqlen, heads,
-                 head_dim, causal, scale, two_variants=True):
-    dK0, dV0 = torch.zeros_like(K0), torch.zeros_like(V0)
-    dK1 = torch.zeros_like(K0) if two_variants else None
-    dV1 = torch.zeros_like(V0) if two_variants else None
+                 head_dim, causal, scale, two_variants=True, kv_cover=(False, False)):
+    """kv_cover[v]: every kv tile has a work item for variant v (host knowledge) => no zero fill needed for dK_v/dV_v."""
+    mk = lambda full: torch.empty_like(K0) if full else torch.zeros_like(K0)
+    dK0, dV0 = mk(kv_cover[0]), mk(kv_cover[0])
+    dK1 = mk(kv_cover[1]) if two_variants else None
+    dV1 = mk(kv_cover[1]) if two_variants else None
     _timed_call("lb_attn_bwd_dkv", _p(Q), _p(K0), _p(V0), _p(K1), _p(V1), _p(dO), _p(lse), _p(delta), _p(qflag),
               _p(qtile_has), _p(work_kv), work_kv.shape[0], _p(kv_start), _p(kv_end), _p(dK0), _p(dV0), _p(dK1), _p(dV1), batch, seqlen,
               heads, head_dim, int(causal), float(scale), _st())

@@ -48,6 +48,7 @@ class AttnWork:
     qtile_has: torch.Tensor     # [B,2,n_qtiles] uint8: q tile holds rows of modality v
     kv_start: Optional[torch.Tensor]
     kv_end: Optional[torch.Tensor]
+    kv_cover: tuple = (False, False)   # per variant: every kv tile of every sample has a dK/dV work item
 
 
 def build_attn_work(vision_flag_cpu: Optional[torch.Tensor], batch: int, seqlen: int, causal: bool, device,
@@ -66,6 +67,7 @@ def build_attn_work(vision_flag_cpu: Optional[torch.Tensor], batch: int, seqlen:
     ks = [0] * batch if kv_start is None else [int(x) for x in kv_start]
     ke = [seqlen] * batch if kv_end is None else [int(x) for x in kv_end]
     items_q, items_kv = [], []
+    cover = [True, True]
     for b in range(batch):
         first_kv, last_kv = ks[b] // TILE, (ke[b] + TILE - 1) // TILE
         for v in range(2):
@@ -79,9 +81,13 @@ def build_attn_work(vision_flag_cpu: Optional[torch.Tensor], batch: int, seqlen:
                 n_q = int(has[b, v, first_q:].sum())
                 if n_q > 0:
                     items_kv.append((n_q, b, kt, v, first_q))
+                else:
+                    cover[v] = False
+            if first_kv > 0 or last_kv < nt:
+                cover[v] = False
     items_q.sort(key=lambda t: -t[0])
     items_kv.sort(key=lambda t: -t[0])
     wq = torch.tensor([[b, qt, v, 0] for _, b, qt, v in items_q], dtype=torch.int32).reshape(-1, 4)
     wkv = torch.tensor([[b, kt, v, fq] for _, b, kt, v, fq in items_kv], dtype=torch.int32).reshape(-1, 4)
     to = lambda t: None if t is None else torch.as_tensor(t, dtype=torch.int32).to(device)
-    return AttnWork(wq.to(device), wkv.to(device), has.to(device), to(kv_start), to(kv_end))
+    return AttnWork(wq.to(device), wkv.to(device), has.to(device), to(kv_start), to(kv_end), (cover[0], cover[1]))
