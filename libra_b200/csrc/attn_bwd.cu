@@ -36,64 +36,58 @@ struct AttnBwdParams {
     float scale;
 };
 
-// ---- score-tile helpers with the mask as a template parameter (the common unmasked path carries no index arithmetic)
-// dQ kernel: thread = query row; 32 key columns at TMEM `ts` (S) / `tdp` (dP); dS (bf16) is written over S.
+// ---- score-tile helpers with the mask as a template parameter (the common unmasked path carries no index arithmetic).
+// All TMEM reads of a tile are issued up front and waited for once; results are packed in place.
+// dQ kernel: thread = query row; 32 key columns at TMEM `ts` (S) / `tdp` (dP); dS (bf16, 16 columns) is written over S.
 template <bool MASK, bool CAUSAL>
 __device__ __forceinline__ void dq_tile(uint32_t ts, uint32_t tdp, float sl2, float lse2, float dlt, float scale, int kv0, int qi,
                                         int kvs, int kve) {
+    uint32_t s[32], dp[32];
+    tmem_ld32(ts, s);
+    tmem_ld32(tdp, dp);
+    tc_wait_ld();
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        uint32_t s[16], dp[16];
-        tmem_ld16(ts + c * 16, s);
-        tmem_ld16(tdp + c * 16, dp);
-        tc_wait_ld();
-        uint32_t pk[8];
-#pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-            float p0 = fast_ex2(fmaf(__uint_as_float(s[j]), sl2, -lse2));
-            float p1 = fast_ex2(fmaf(__uint_as_float(s[j + 1]), sl2, -lse2));
-            if (MASK) {
-                const int kj = kv0 + c * 16 + j;
-                p0 = ((!CAUSAL || kj <= qi) && kj < kve && kj >= kvs) ? p0 : 0.f;
-                p1 = ((!CAUSAL || kj + 1 <= qi) && kj + 1 < kve && kj + 1 >= kvs) ? p1 : 0.f;
-            }
-            const float d0 = p0 * (__uint_as_float(dp[j]) - dlt) * scale;
-            const float d1 = p1 * (__uint_as_float(dp[j + 1]) - dlt) * scale;
-            pk[j >> 1] = pack_bf16(d0, d1);
+    for (int j = 0; j < 32; j += 2) {
+        float p0 = fast_ex2(fmaf(__uint_as_float(s[j]), sl2, -lse2));
+        float p1 = fast_ex2(fmaf(__uint_as_float(s[j + 1]), sl2, -lse2));
+        if (MASK) {
+            const int kj = kv0 + j;
+            p0 = ((!CAUSAL || kj <= qi) && kj < kve && kj >= kvs) ? p0 : 0.f;
+            p1 = ((!CAUSAL || kj + 1 <= qi) && kj + 1 < kve && kj + 1 >= kvs) ? p1 : 0.f;
         }
-        tmem_st8(ts + c * 8, pk);       // dS (bf16) over my own, already consumed S columns
+        const float d0 = p0 * (__uint_as_float(dp[j]) - dlt) * scale;
+        const float d1 = p1 * (__uint_as_float(dp[j + 1]) - dlt) * scale;
+        s[j >> 1] = pack_bf16(d0, d1);
     }
+    tmem_st16(ts, s);       // dS (bf16) over my own, already consumed S columns
 }
 
 // dK/dV kernel: thread = key row; 64 query columns at TMEM `ts` (S^T) / `tdp` (dP^T); per-column lse2 / delta in smem.
 template <bool MASK, bool CAUSAL>
 __device__ __forceinline__ void dkv_tile(uint32_t ts, uint32_t tdp, const float* __restrict__ st, float sl2, float scale, int kj,
                                          int qbase, bool key_ok) {
+    uint32_t s[64], dp[64];
+    tmem_ld32(ts, s);
+    tmem_ld32(ts + 32, s + 32);
+    tmem_ld32(tdp, dp);
+    tmem_ld32(tdp + 32, dp + 32);
+    tc_wait_ld();
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        uint32_t s[32], dp[32];
-        tmem_ld32(ts + c * 32, s);
-        tmem_ld32(tdp + c * 32, dp);
-        tc_wait_ld();
-        uint32_t pp[16], pd[16];
-        const float* lse_c = st + c * 32;
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-            float p0 = fast_ex2(fmaf(__uint_as_float(s[j]), sl2, -lse_c[j]));          // lse = +inf on excluded query rows
-            float p1 = fast_ex2(fmaf(__uint_as_float(s[j + 1]), sl2, -lse_c[j + 1]));
-            if (MASK) {
-                const int qa = qbase + c * 32 + j;
-                p0 = (key_ok && (!CAUSAL || kj <= qa)) ? p0 : 0.f;
-                p1 = (key_ok && (!CAUSAL || kj <= qa + 1)) ? p1 : 0.f;
-            }
-            const float d0 = p0 * (__uint_as_float(dp[j]) - lse_c[128 + j]) * scale;
-            const float d1 = p1 * (__uint_as_float(dp[j + 1]) - lse_c[128 + j + 1]) * scale;
-            pp[j >> 1] = pack_bf16(p0, p1);
-            pd[j >> 1] = pack_bf16(d0, d1);
+    for (int j = 0; j < 64; j += 2) {
+        float p0 = fast_ex2(fmaf(__uint_as_float(s[j]), sl2, -st[j]));          // lse = +inf on excluded query rows
+        float p1 = fast_ex2(fmaf(__uint_as_float(s[j + 1]), sl2, -st[j + 1]));
+        if (MASK) {
+            const int qa = qbase + j;
+            p0 = (key_ok && (!CAUSAL || kj <= qa)) ? p0 : 0.f;
+            p1 = (key_ok && (!CAUSAL || kj <= qa + 1)) ? p1 : 0.f;
         }
-        tmem_st16(ts + c * 16, pp);       // P^T over my own, already consumed S^T columns
-        tmem_st16(tdp + c * 16, pd);      // dS^T over dP^T
+        const float d0 = p0 * (__uint_as_float(dp[j]) - st[128 + j]) * scale;
+        const float d1 = p1 * (__uint_as_float(dp[j + 1]) - st[128 + j + 1]) * scale;
+        s[j >> 1] = pack_bf16(p0, p1);
+        dp[j >> 1] = pack_bf16(d0, d1);
     }
+    tmem_st32(ts, s);        // P^T (bf16, 32 columns) over my own, already consumed S^T columns
+    tmem_st32(tdp, dp);      // dS^T over dP^T
 }
 
 // =====================================================================================================

@@ -52,54 +52,43 @@ enum { B_Q = 0, B_KFULL, B_KEMPTY, B_VFULL, B_VEMPTY, B_SFULL, B_PFULL, B_OREADY
 
 // ---- softmax tile helpers: MASK is a template parameter so the (common) unmasked path carries no index arithmetic.
 // Each thread owns one query row (TMEM lane) and 64 key columns starting at TMEM address `ts` / key index `kv0`.
+// The 64 scores are read from TMEM ONCE and stay in registers across the max exchange.
 template <bool MASK, bool CAUSAL>
-__device__ __forceinline__ float softmax_tile_max(uint32_t ts, int kv0, int qi, int kvs, int kve) {
-    float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F;
+__device__ __forceinline__ float softmax_load_max(uint32_t ts, uint32_t (&v)[64], int kv0, int qi, int kvs, int kve) {
+    tmem_ld32(ts, v);
+    tmem_ld32(ts + 32, v + 32);
+    tc_wait_ld();
+    float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F, mx2 = -CUDART_INF_F, mx3 = -CUDART_INF_F;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld32(ts + c * 32, v);
-        tc_wait_ld();
+    for (int j = 0; j < 64; j += 4) {
+        if (MASK) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-            float a = __uint_as_float(v[j]), b = __uint_as_float(v[j + 1]);
-            if (MASK) {
-                const int kj = kv0 + c * 32 + j;
-                a = ((!CAUSAL || kj <= qi) && kj < kve && kj >= kvs) ? a : -CUDART_INF_F;
-                b = ((!CAUSAL || kj + 1 <= qi) && kj + 1 < kve && kj + 1 >= kvs) ? b : -CUDART_INF_F;
+            for (int e = 0; e < 4; ++e) {
+                const int kj = kv0 + j + e;
+                const bool ok = (!CAUSAL || kj <= qi) && kj < kve && kj >= kvs;
+                v[j + e] = ok ? v[j + e] : 0xff800000u;          // -inf: masked scores vanish in both max and exp
             }
-            mx0 = fmaxf(mx0, a);
-            mx1 = fmaxf(mx1, b);
         }
+        mx0 = fmaxf(mx0, __uint_as_float(v[j]));
+        mx1 = fmaxf(mx1, __uint_as_float(v[j + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(v[j + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(v[j + 3]));
     }
-    return fmaxf(mx0, mx1);
+    return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
 }
 
-// P = 2^(S*sl2 - m_off) for my 64 columns, written as bf16 over the first 32 of my own S columns; returns the row-sum part
-template <bool MASK, bool CAUSAL>
-__device__ __forceinline__ float softmax_tile_exp(uint32_t ts, float sl2, float m_off, int kv0, int qi, int kvs, int kve) {
+// P = 2^(S*sl2 - m_off) in place, packed to bf16 (32 registers) and stored over the first 32 of my own S columns.
+__device__ __forceinline__ float softmax_exp_store(uint32_t ts, uint32_t (&v)[64], float sl2, float m_off) {
     float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld32(ts + c * 32, v);
-        tc_wait_ld();
-        uint32_t pk[16];
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-            float p0 = fast_ex2(fmaf(__uint_as_float(v[j]), sl2, -m_off));
-            float p1 = fast_ex2(fmaf(__uint_as_float(v[j + 1]), sl2, -m_off));
-            if (MASK) {
-                const int kj = kv0 + c * 32 + j;
-                p0 = ((!CAUSAL || kj <= qi) && kj < kve && kj >= kvs) ? p0 : 0.f;
-                p1 = ((!CAUSAL || kj + 1 <= qi) && kj + 1 < kve && kj + 1 >= kvs) ? p1 : 0.f;
-            }
-            l0 += p0;
-            l1 += p1;
-            pk[j >> 1] = pack_bf16(p0, p1);
-        }
-        tmem_st16(ts + c * 16, pk);       // chunk c of P overwrites S columns already consumed
+    for (int j = 0; j < 64; j += 2) {
+        const float p0 = fast_ex2(fmaf(__uint_as_float(v[j]), sl2, -m_off));
+        const float p1 = fast_ex2(fmaf(__uint_as_float(v[j + 1]), sl2, -m_off));
+        l0 += p0;
+        l1 += p1;
+        v[j >> 1] = pack_bf16(p0, p1);
     }
+    tmem_st32(ts, v);
     return l0 + l1;
 }
 
@@ -227,9 +216,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const bool need_mask = (CAUSAL && kv0 + 63 > q0) || (kv0 + 64 > kve) || (kv0 < kvs);
             mbar_wait(bars + B_SFULL, ph);
             tc_fence_after_sync();
-            // ---- pass 1: max over my 64 columns
-            const float mx = need_mask ? softmax_tile_max<true, CAUSAL>(lane_addr + colS, kv0, qi, kvs, kve)
-                                       : softmax_tile_max<false, CAUSAL>(lane_addr + colS, kv0, qi, kvs, kve);
+            // ---- scores -> registers (one TMEM read), masked, partial max over my 64 columns
+            uint32_t sv[64];
+            const float mx = need_mask ? softmax_load_max<true, CAUSAL>(lane_addr + colS, sv, kv0, qi, kvs, kve)
+                                       : softmax_load_max<false, CAUSAL>(lane_addr + colS, sv, kv0, qi, kvs, kve);
             // ---- exchange the partial max with the thread owning the other half of this row
             float* rbuf = red + (it & 1) * 256;
             rbuf[half * 128 + r] = mx;
@@ -248,20 +238,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     l *= alpha;
                 }
 #pragma unroll 1
-                for (int c = 0; c < DH / 32; ++c) {
-                    uint32_t v[32];
-                    tmem_ld32(lane_addr + colO + c * 32, v);
+                for (int c = 0; c < DH / 8; ++c) {               // small chunks: the scores stay live in registers
+                    uint32_t v[8];
+                    tmem_ld8(lane_addr + colO + c * 8, v);
                     tc_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * alpha);
-                    tmem_st32(lane_addr + colO + c * 32, v);
+                    for (int j = 0; j < 8; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * alpha);
+                    tmem_st8(lane_addr + colO + c * 8, v);
                 }
                 tc_wait_st();
             }
             const float m_off = (m_used == -CUDART_INF_F) ? 0.f : m_used * sl2;
-            // ---- pass 2: P = 2^(S*sl2 - m), partial row sum, P (bf16) over my own S columns
-            l += need_mask ? softmax_tile_exp<true, CAUSAL>(lane_addr + colS, sl2, m_off, kv0, qi, kvs, kve)
-                           : softmax_tile_exp<false, CAUSAL>(lane_addr + colS, sl2, m_off, kv0, qi, kvs, kve);
+            // ---- P = 2^(S*sl2 - m) from the registers, partial row sum, P (bf16) over my own S columns
+            l += softmax_exp_store(lane_addr + colS, sv, sl2, m_off);
             tc_wait_st();
             tc_fence_before_sync();
             mbar_arrive(bars + B_PFULL);

@@ -101,85 +101,72 @@ __global__ void __launch_bounds__(NT) rmsnorm_fwd_kernel(const __nv_bfloat16* __
 }
 
 // ---------------------------------------------------------------- RMSNorm bwd
-// dx = rs * (g - x * rs^2 * mean(g . x)),  g = w . dy ;  dw[m] += sum_rows dy . x . rs
-__global__ void __launch_bounds__(NT) rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
-                                                         const __nv_bfloat16* __restrict__ x,
-                                                         const __nv_bfloat16* __restrict__ w_lang,
-                                                         const __nv_bfloat16* __restrict__ w_vis,
-                                                         const uint8_t* __restrict__ flag, const float* __restrict__ rstd,
-                                                         const __nv_bfloat16* __restrict__ resid,
-                                                         __nv_bfloat16* __restrict__ dx, float* __restrict__ partial,
-                                                         int64_t rows, int cols) {
-    __shared__ float red[16];
-    const int nvec = cols >> 3;
-    float accL[MAXV][8], accV[MAXV][8];
-#pragma unroll
-    for (int i = 0; i < MAXV; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) accL[i][j] = accV[i][j] = 0.f;
+// dx = rs * (g - x * rs^2 * mean(g . x)) (+ residual grad),  g = w . dy ;  dw[m] += sum_rows dy . x . rs
+// One WARP per row (no block barriers): pass 1 reduces mean(g.x) with shuffles, pass 2 re-reads the row (L1/L2 hit),
+// writes dx and adds the row's dw contribution into a per-CTA shared-memory accumulator (bank-conflict-free layout
+// [element-in-vector][vector]); the CTA's accumulator goes to `partial`, folded by reduce_partials_kernel.
+constexpr int RB_WARPS = 8;
 
-    for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+__global__ void __launch_bounds__(RB_WARPS * 32) rmsnorm_bwd_kernel(
+    const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w_lang,
+    const __nv_bfloat16* __restrict__ w_vis, const uint8_t* __restrict__ flag, const float* __restrict__ rstd,
+    const __nv_bfloat16* __restrict__ resid, __nv_bfloat16* __restrict__ dx, float* __restrict__ partial, int64_t rows,
+    int cols) {
+    extern __shared__ float dwacc[];                    // [2 modalities][8][nvec]
+    const int nvec = cols >> 3;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < 2 * cols; i += blockDim.x) dwacc[i] = 0.f;
+    __syncthreads();
+    const int64_t warps_total = (int64_t)gridDim.x * RB_WARPS;
+    for (int64_t r = (int64_t)blockIdx.x * RB_WARPS + warp; r < rows; r += warps_total) {
         const bool vis = flag ? (flag[r] != 0) : false;
         const uint4* xr = reinterpret_cast<const uint4*>(x + r * cols);
         const uint4* dr = reinterpret_cast<const uint4*>(dy + r * cols);
         const uint4* wr = reinterpret_cast<const uint4*>(vis ? w_vis : w_lang);
         const float rs = rstd[r];
-        uint4 xv[MAXV], dv[MAXV];
         float dot = 0.f;
+#pragma unroll 4
+        for (int v = lane; v < nvec; v += 32) {
+            float fx[8], fd[8], fw[8];
+            unpack8(__ldg(xr + v), fx);
+            unpack8(__ldg(dr + v), fd);
+            unpack8(__ldg(wr + v), fw);
 #pragma unroll
-        for (int i = 0; i < MAXV; ++i) {
-            const int v = threadIdx.x + i * NT;
-            if (v < nvec) {
-                xv[i] = __ldg(xr + v);
-                dv[i] = __ldg(dr + v);
-                float fx[8], fd[8], fw[8];
-                unpack8(xv[i], fx);
-                unpack8(dv[i], fd);
-                unpack8(__ldg(wr + v), fw);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    dot += fw[j] * fd[j] * fx[j];
-                    const float c = fd[j] * fx[j] * rs;
-                    if (vis) accV[i][j] += c; else accL[i][j] += c;
-                }
-            }
+            for (int j = 0; j < 8; ++j) dot += fw[j] * fd[j] * fx[j];
         }
-        const float tot = block_sum2(dot, 0.f, red).x;
-        const float coef = tot / (float)cols * rs * rs * rs;
+        dot = warp_sum(dot);
+        const float coef = dot / (float)cols * rs * rs * rs;
         uint4* oxr = reinterpret_cast<uint4*>(dx + r * cols);
         const uint4* rr = resid ? reinterpret_cast<const uint4*>(resid + r * cols) : nullptr;
+        float* acc = dwacc + (vis ? cols : 0);
+#pragma unroll 2
+        for (int v = lane; v < nvec; v += 32) {
+            float fx[8], fd[8], fw[8], o[8];
+            unpack8(__ldg(xr + v), fx);
+            unpack8(__ldg(dr + v), fd);
+            unpack8(__ldg(wr + v), fw);
 #pragma unroll
-        for (int i = 0; i < MAXV; ++i) {
-            const int v = threadIdx.x + i * NT;
-            if (v < nvec) {
-                float fx[8], fd[8], fw[8], o[8];
-                unpack8(xv[i], fx);
-                unpack8(dv[i], fd);
-                unpack8(__ldg(wr + v), fw);
+            for (int j = 0; j < 8; ++j) o[j] = rs * fw[j] * fd[j] - fx[j] * coef;
+            if (rr) {
+                float fr[8];
+                unpack8(__ldg(rr + v), fr);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = rs * fw[j] * fd[j] - fx[j] * coef;
-                if (rr) {
-                    float fr[8];
-                    unpack8(__ldg(rr + v), fr);
+                for (int j = 0; j < 8; ++j) o[j] += fr[j];
+            }
+            oxr[v] = pack8(o);
+            if (partial) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) o[j] += fr[j];
-                }
-                oxr[v] = pack8(o);
+                for (int j = 0; j < 8; ++j) atomicAdd(acc + j * nvec + v, fd[j] * fx[j] * rs);
             }
         }
     }
-    // partial[block][2][cols]
-    float* pl = partial + (int64_t)blockIdx.x * 2 * cols;
-    float* pv = pl + cols;
-#pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-        const int v = threadIdx.x + i * NT;
-        if (v < nvec) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                pl[v * 8 + j] = accL[i][j];
-                pv[v * 8 + j] = accV[i][j];
-            }
+    __syncthreads();
+    if (partial) {
+        // partial[block][2][cols] in natural column order
+        float* out = partial + (int64_t)blockIdx.x * 2 * cols;
+        for (int i = threadIdx.x; i < 2 * cols; i += blockDim.x) {
+            const int m = i / cols, c = i - m * cols;
+            out[i] = dwacc[m * cols + (c & 7) * nvec + (c >> 3)];
         }
     }
 }
@@ -345,6 +332,12 @@ static int norm_grid(int64_t rows) {
     return (int)(rows < g ? (rows > 0 ? rows : 1) : g);
 }
 
+static int rms_bwd_grid(int64_t rows) {
+    int64_t g = (int64_t)sm_count() * 4;
+    const int64_t need = (rows + RB_WARPS - 1) / RB_WARPS;
+    return (int)(need < g ? (need > 0 ? need : 1) : g);
+}
+
 static int check_norm_args(const void* x, const void* y, int64_t rows, int cols) {
     LB_REQUIRE(rows >= 0 && cols > 0, LB_EINVAL, "norm: bad shape rows=%lld cols=%d", (long long)rows, cols);
     LB_REQUIRE(cols % 8 == 0 && cols <= NT * MAXV * 8, LB_EINVAL, "norm: cols=%d must be a multiple of 8 and <= %d", cols,
@@ -372,7 +365,8 @@ int lb_rmsnorm_fwd(const void* x, const void* w_lang, const void* w_vis, const u
 }
 
 int64_t lb_rmsnorm_bwd_workspace(int64_t rows, int cols) {
-    return (int64_t)norm_grid(rows) * 2 * cols * (int64_t)sizeof(float);
+    const int64_t g = norm_grid(rows) > rms_bwd_grid(rows) ? norm_grid(rows) : rms_bwd_grid(rows);
+    return g * 2 * cols * (int64_t)sizeof(float);
 }
 
 int lb_rmsnorm_bwd(const void* dy, const void* x, const void* w_lang, const void* w_vis, const uint8_t* flag,
@@ -382,12 +376,21 @@ int lb_rmsnorm_bwd(const void* dy, const void* x, const void* w_lang, const void
     if (rc) return rc;
     LB_REQUIRE(dy && rstd && partial && w_lang, LB_EINVAL, "rmsnorm_bwd: null argument");
     if (rows == 0) return LB_OK;
-    const int grid = norm_grid(rows);
+    const int grid = rms_bwd_grid(rows);
     cudaStream_t st = (cudaStream_t)stream;
-    rmsnorm_bwd_kernel<<<grid, NT, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
-                                            (const __nv_bfloat16*)w_lang, (const __nv_bfloat16*)(w_vis ? w_vis : w_lang),
-                                            flag, rstd, (const __nv_bfloat16*)residual_grad, (__nv_bfloat16*)dx,
-                                            (float*)partial, rows, cols);
+    const int smem = 2 * cols * (int)sizeof(float);
+    static int configured_smem = 0;
+    if (smem > configured_smem) {
+        cudaError_t e = cudaFuncSetAttribute(rmsnorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return fail(LB_ELAUNCH, "rmsnorm_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        configured_smem = smem;
+    }
+    const bool need_dw = dw_lang || dw_vis;
+    rmsnorm_bwd_kernel<<<grid, RB_WARPS * 32, smem, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
+                                                          (const __nv_bfloat16*)w_lang,
+                                                          (const __nv_bfloat16*)(w_vis ? w_vis : w_lang), flag, rstd,
+                                                          (const __nv_bfloat16*)residual_grad, (__nv_bfloat16*)dx,
+                                                          need_dw ? (float*)partial : nullptr, rows, cols);
     rc = check_launch("rmsnorm_bwd");
     if (rc) return rc;
     const int tb = 256, gb = ceil_div(cols, 32);
