@@ -153,6 +153,10 @@ int lb_attn_fwd(const void* Q, const void* K0, const void* V0, const void* K1, c
                 const int32_t* out_row, void* O, float* lse, int batch, int seqlen, int heads, int head_dim, int causal,
                 float scale, void* stream);
 
+/* diagnostics: CTA (0,0) of subsequent lb_attn_fwd launches writes clock64 stamps into buf ([64][8] int64, device
+ * memory; slots: MMA K-ready / QK-issued / P-seen / PV-issued, softmax S-seen / max-done / exchanged / P-arrived). NULL = off */
+int lb_attn_fwd_set_trace(void* buf);
+
 /* delta[b,h,t] = sum_d dO*O per head, plus dO gathered to original order.
  * O_rows/dO_rows are indexed by row_of[bt] (NULL = identity). */
 int lb_attn_bwd_prepare(const void* O, const void* dO, const int32_t* row_of, void* dO_orig, float* delta, int batch,

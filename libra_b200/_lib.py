@@ -41,6 +41,7 @@ SIGNATURES = {
     "lb_attn_prep_fwd": (I, [P] * 15 + [L, I, I, P]),
     "lb_attn_prep_bwd": (I, [P] * 15 + [L, I, I, P]),
     "lb_attn_fwd": (I, [P, P, P, P, P, P, P, I, P, P, P, P, P, I, I, I, I, I, F, P]),
+    "lb_attn_fwd_set_trace": (I, [P]),
     "lb_attn_bwd_prepare": (I, [P, P, P, P, P, I, I, I, I, P]),
     "lb_attn_bwd_dq": (I, [P] * 10 + [I, P, P, P, I, I, I, I, I, F, P]),
     "lb_attn_bwd_dkv": (I, [P] * 11 + [I, P, P, P, P, P, P, I, I, I, I, I, F, P]),

@@ -179,7 +179,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (elect_one() && n_tiles > 0) {
             constexpr uint32_t idesc_s = make_idesc_bf16(128, BN, 0, 0);
             constexpr uint32_t idesc_dq = make_idesc_bf16(128, D, 0, 1);
-            const uint32_t aQ = smem_u32(sQ), adO = smem_u32(sdO), aK = smem_u32(sK), aV = smem_u32(sV);
+            const uint32_t dQ0 = desc_lo_kmajor(smem_u32(sQ)), ddO0 = desc_lo_kmajor(smem_u32(sdO));
+            const uint32_t dK0 = desc_lo_kmajor(smem_u32(sK)), dV0 = desc_lo_kmajor(smem_u32(sV));
+            const uint32_t dKmn0 = desc_lo_mnmajor(smem_u32(sK), BN * 128);
             mbar_wait(bars + DQ_QDO, 0);
             for (int it = 0; it < n_tiles; ++it) {
                 const uint32_t ph = (uint32_t)it & 1u;
@@ -187,17 +189,17 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 tc_fence_after_sync();
 #pragma unroll
                 for (int kk = 0; kk < D / 16; ++kk) {
-                    const uint32_t offA = (uint32_t)(kk / 4) * (128 * 128) + (uint32_t)(kk % 4) * 32;
-                    const uint32_t offB = (uint32_t)(kk / 4) * (BN * 128) + (uint32_t)(kk % 4) * 32;
-                    umma_ss(tmem_base + COL_S, desc_kmajor(aQ + offA), desc_kmajor(aK + offB), idesc_s, kk ? 1u : 0u);
+                    const uint32_t offA = ((uint32_t)(kk / 4) * (128 * 128) + (uint32_t)(kk % 4) * 32) >> 4;
+                    const uint32_t offB = ((uint32_t)(kk / 4) * (BN * 128) + (uint32_t)(kk % 4) * 32) >> 4;
+                    umma_ss_lo(tmem_base + COL_S, dQ0 + offA, dK0 + offB, idesc_s, kk ? 1u : 0u);
                 }
                 mbar_wait(bars + DQ_VFULL, ph);
                 tc_fence_after_sync();
 #pragma unroll
                 for (int kk = 0; kk < D / 16; ++kk) {
-                    const uint32_t offA = (uint32_t)(kk / 4) * (128 * 128) + (uint32_t)(kk % 4) * 32;
-                    const uint32_t offB = (uint32_t)(kk / 4) * (BN * 128) + (uint32_t)(kk % 4) * 32;
-                    umma_ss(tmem_base + COL_DP, desc_kmajor(adO + offA), desc_kmajor(aV + offB), idesc_s, kk ? 1u : 0u);
+                    const uint32_t offA = ((uint32_t)(kk / 4) * (128 * 128) + (uint32_t)(kk % 4) * 32) >> 4;
+                    const uint32_t offB = ((uint32_t)(kk / 4) * (BN * 128) + (uint32_t)(kk % 4) * 32) >> 4;
+                    umma_ss_lo(tmem_base + COL_DP, ddO0 + offA, dV0 + offB, idesc_s, kk ? 1u : 0u);
                 }
                 tc_commit(bars + DQ_VEMPTY);
                 tc_commit(bars + DQ_SDP);
@@ -205,8 +207,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 tc_fence_after_sync();
 #pragma unroll
                 for (int kk = 0; kk < BN / 16; ++kk)     // dS of keys 16kk.. lives at column 32*(kk/2) + 8*(kk%2)
-                    umma_ts(tmem_base + COL_DQ, tmem_base + COL_S + (uint32_t)(kk / 2) * 32 + (uint32_t)(kk % 2) * 8,
-                            desc_mnmajor(aK + kk * 2048, BN * 128), idesc_dq, (it | kk) ? 1u : 0u);
+                    umma_ts_lo(tmem_base + COL_DQ, tmem_base + COL_S + (uint32_t)(kk / 2) * 32 + (uint32_t)(kk % 2) * 8,
+                               dKmn0 + (uint32_t)kk * (2048 >> 4), idesc_dq, (it | kk) ? 1u : 0u);
                 tc_commit(bars + DQ_KEMPTY);
                 tc_commit(bars + DQ_READY);
             }
@@ -379,7 +381,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (elect_one() && n_tiles > 0) {
             constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
             constexpr uint32_t idesc_g = make_idesc_bf16(128, D, 0, 1);
-            const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
+            const uint32_t dK0 = desc_lo_kmajor(smem_u32(sK)), dV0 = desc_lo_kmajor(smem_u32(sV));
             mbar_wait(bars + KV_KV, 0);
             for (int it = 0; it < n_tiles; ++it) {
                 const int st = it & 1;
@@ -387,29 +389,31 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 const uint32_t ph = (uint32_t)it & 1u;
                 const uint32_t aQ = smem_u32(sQ0 + st * (S::Q_BYTES + S::DO_BYTES));
                 const uint32_t adO = aQ + S::Q_BYTES;
+                const uint32_t dQk = desc_lo_kmajor(aQ), ddOk = desc_lo_kmajor(adO);
+                const uint32_t dQmn = desc_lo_mnmajor(aQ, 128 * 128), ddOmn = desc_lo_mnmajor(adO, 128 * 128);
                 mbar_wait(bars + KV_QFULL0 + st, phq);
                 tc_fence_after_sync();
 #pragma unroll
                 for (int kk = 0; kk < D / 16; ++kk) {
-                    const uint32_t off = (uint32_t)(kk / 4) * (128 * 128) + (uint32_t)(kk % 4) * 32;
-                    umma_ss(tmem_base + COL_S, desc_kmajor(aK + off), desc_kmajor(aQ + off), idesc_s, kk ? 1u : 0u);
+                    const uint32_t off = ((uint32_t)(kk / 4) * (128 * 128) + (uint32_t)(kk % 4) * 32) >> 4;
+                    umma_ss_lo(tmem_base + COL_S, dK0 + off, dQk + off, idesc_s, kk ? 1u : 0u);
                 }
 #pragma unroll
                 for (int kk = 0; kk < D / 16; ++kk) {
-                    const uint32_t off = (uint32_t)(kk / 4) * (128 * 128) + (uint32_t)(kk % 4) * 32;
-                    umma_ss(tmem_base + COL_DP, desc_kmajor(aV + off), desc_kmajor(adO + off), idesc_s, kk ? 1u : 0u);
+                    const uint32_t off = ((uint32_t)(kk / 4) * (128 * 128) + (uint32_t)(kk % 4) * 32) >> 4;
+                    umma_ss_lo(tmem_base + COL_DP, dV0 + off, ddOk + off, idesc_s, kk ? 1u : 0u);
                 }
                 tc_commit(bars + KV_SDP);
                 mbar_wait(bars + KV_PDS, ph);
                 tc_fence_after_sync();
 #pragma unroll
                 for (int kk = 0; kk < 128 / 16; ++kk)    // P^T of queries 16kk.. lives at column 64*(kk/4) + 8*(kk%4)
-                    umma_ts(tmem_base + COL_DV, tmem_base + COL_S + (uint32_t)(kk / 4) * 64 + (uint32_t)(kk % 4) * 8,
-                            desc_mnmajor(adO + kk * 2048, 128 * 128), idesc_g, (it | kk) ? 1u : 0u);
+                    umma_ts_lo(tmem_base + COL_DV, tmem_base + COL_S + (uint32_t)(kk / 4) * 64 + (uint32_t)(kk % 4) * 8,
+                               ddOmn + (uint32_t)kk * (2048 >> 4), idesc_g, (it | kk) ? 1u : 0u);
 #pragma unroll
                 for (int kk = 0; kk < 128 / 16; ++kk)
-                    umma_ts(tmem_base + COL_DK, tmem_base + COL_DP + (uint32_t)(kk / 4) * 64 + (uint32_t)(kk % 4) * 8,
-                            desc_mnmajor(aQ + kk * 2048, 128 * 128), idesc_g, (it | kk) ? 1u : 0u);
+                    umma_ts_lo(tmem_base + COL_DK, tmem_base + COL_DP + (uint32_t)(kk / 4) * 64 + (uint32_t)(kk % 4) * 8,
+                               dQmn + (uint32_t)kk * (2048 >> 4), idesc_g, (it | kk) ? 1u : 0u);
                 tc_commit(bars + KV_QEMPTY0 + st);
             }
             tc_commit(bars + KV_DONE);

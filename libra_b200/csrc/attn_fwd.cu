@@ -12,6 +12,7 @@
 // TMEM columns: [0,128) S (fp32), P (bf16) aliased over the start of each half; [128,128+D) O accumulator.
 // Two CTAs per SM (<= 100 KB smem, 256 TMEM columns each): while one CTA runs its softmax the other owns the tensor pipe.
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -35,7 +36,13 @@ struct AttnFwdParams {
     float* lse;                  // [B,H,T]
     int batch, seqlen, heads;
     float scale;
+    long long* trace;            // optional [64][8] clock64 stamps of CTA (0,0) (diagnostics, LB_ATTN_TRACE env)
 };
+
+#define LB_TRACE(slot, it)                                                                        \
+    do {                                                                                          \
+        if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && (it) < 64) p.trace[(it) * 8 + (slot)] = clock64(); \
+    } while (0)
 
 template <int D>
 struct AttnFwdSmem {
@@ -78,12 +85,15 @@ __device__ __forceinline__ float softmax_load_max(uint32_t ts, uint32_t (&v)[64]
 }
 
 // P = 2^(S*sl2 - m_off) in place, packed to bf16 (32 registers) and stored over the first 32 of my own S columns.
+// POLY: one exponential in every POLY runs on the FMA pipes (poly_ex2) instead of the SFU; 0 = all on the SFU.
+template <int POLY>
 __device__ __forceinline__ float softmax_exp_store(uint32_t ts, uint32_t (&v)[64], float sl2, float m_off) {
     float l0 = 0.f, l1 = 0.f;
 #pragma unroll
     for (int j = 0; j < 64; j += 2) {
-        const float p0 = fast_ex2(fmaf(__uint_as_float(v[j]), sl2, -m_off));
-        const float p1 = fast_ex2(fmaf(__uint_as_float(v[j + 1]), sl2, -m_off));
+        const float x0 = fmaf(__uint_as_float(v[j]), sl2, -m_off), x1 = fmaf(__uint_as_float(v[j + 1]), sl2, -m_off);
+        const float p0 = (POLY > 0 && (j % POLY) == 0) ? poly_ex2(x0) : fast_ex2(x0);
+        const float p1 = (POLY > 0 && ((j + 1) % POLY) == 0) ? poly_ex2(x1) : fast_ex2(x1);
         l0 += p0;
         l1 += p1;
         v[j >> 1] = pack_bf16(p0, p1);
@@ -94,7 +104,7 @@ __device__ __forceinline__ float softmax_exp_store(uint32_t ts, uint32_t (&v)[64
 
 // TMEM columns: S (fp32) at [0,128); each softmax warpgroup h writes its half of P (bf16, 32 columns) over the start of
 // ITS OWN half of S: P(keys 64h .. 64h+63) at [64h, 64h+32).  O accumulator at [128, 128+D).
-template <int D, bool CAUSAL>
+template <int D, bool CAUSAL, int POLY>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
                 const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
@@ -173,30 +183,36 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (elect_one() && n_tiles > 0) {
             constexpr uint32_t idesc_qk = make_idesc_bf16(AT_BM, AT_BN, 0, 0);
             constexpr uint32_t idesc_pv = make_idesc_bf16(AT_BM, D, 0, 1);
-            const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV);
+            // descriptor low words (start address >> 4 | LBO); K steps only add constants to them
+            const uint32_t dQ0 = desc_lo_kmajor(smem_u32(sQ)), dK0 = desc_lo_kmajor(smem_u32(sK));
+            const uint32_t dV0 = desc_lo_mnmajor(smem_u32(sV), AT_BN * 128);
             mbar_wait(bars + B_Q, 0);
             for (int it = 0; it < n_tiles; ++it) {
                 const uint32_t ph = (uint32_t)it & 1u;
                 mbar_wait(bars + B_KFULL, ph);
                 tc_fence_after_sync();
+                LB_TRACE(0, it);                                 // MMA: K landed, issuing QK
 #pragma unroll
                 for (int kk = 0; kk < D / 16; ++kk) {
-                    const uint32_t off = (uint32_t)(kk / 4) * (AT_BM * 128) + (uint32_t)(kk % 4) * 32;
-                    umma_ss(tmem_base + COL_S, desc_kmajor(aQ + off), desc_kmajor(aK + off), idesc_qk, kk ? 1u : 0u);
+                    const uint32_t off = ((uint32_t)(kk / 4) * (AT_BM * 128) + (uint32_t)(kk % 4) * 32) >> 4;
+                    umma_ss_lo(tmem_base + COL_S, dQ0 + off, dK0 + off, idesc_qk, kk ? 1u : 0u);
                 }
                 tc_commit(bars + B_KEMPTY);
                 tc_commit(bars + B_SFULL);
+                LB_TRACE(1, it);                                 // MMA: QK issued + committed
                 mbar_wait(bars + B_PFULL, ph);
+                LB_TRACE(2, it);                                 // MMA: P seen
                 mbar_wait(bars + B_VFULL, ph);
                 tc_fence_after_sync();
 #pragma unroll
                 for (int kk = 0; kk < AT_BN / 16; ++kk) {
                     // A = P in TMEM: keys 16kk.. live at column 64*(kk/4) + 8*(kk%4); B = V as MN-major (16 key rows = 2048 B)
-                    umma_ts(tmem_base + COL_O, tmem_base + COL_S + (uint32_t)(kk / 4) * 64 + (uint32_t)(kk % 4) * 8,
-                            desc_mnmajor(aV + kk * 2048, AT_BN * 128), idesc_pv, (it | kk) ? 1u : 0u);
+                    umma_ts_lo(tmem_base + COL_O, tmem_base + COL_S + (uint32_t)(kk / 4) * 64 + (uint32_t)(kk % 4) * 8,
+                               dV0 + (uint32_t)kk * (2048 >> 4), idesc_pv, (it | kk) ? 1u : 0u);
                 }
                 tc_commit(bars + B_VEMPTY);
                 tc_commit(bars + B_OREADY);
+                LB_TRACE(3, it);                                 // MMA: PV issued + committed
             }
         }
     } else {
@@ -216,6 +232,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const bool need_mask = (CAUSAL && kv0 + 63 > q0) || (kv0 + 64 > kve) || (kv0 < kvs);
             mbar_wait(bars + B_SFULL, ph);
             tc_fence_after_sync();
+            if (threadIdx.x == 0) LB_TRACE(4, it);               // softmax: S seen
             // ---- scores -> registers (one TMEM read), masked, partial max over my 64 columns
             uint32_t sv[64];
             const float mx = need_mask ? softmax_load_max<true, CAUSAL>(lane_addr + colS, sv, kv0, qi, kvs, kve)
@@ -223,7 +240,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             // ---- exchange the partial max with the thread owning the other half of this row
             float* rbuf = red + (it & 1) * 256;
             rbuf[half * 128 + r] = mx;
+            if (threadIdx.x == 0) LB_TRACE(5, it);               // softmax: scores loaded, max done
             named_bar_sync(1, AT_SOFTMAX_THREADS);
+            if (threadIdx.x == 0) LB_TRACE(6, it);               // softmax: exchange done
             const float m_new = fmaxf(m_used, fmaxf(rbuf[r], rbuf[128 + r]));
             // ---- lazy correction: rescale O only when the running max moved by more than 2^8 (both halves decide alike)
             const bool grow = (m_new - m_used) * sl2 > 8.f;      // also true when m_used == -inf and m_new finite
@@ -250,10 +269,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
             const float m_off = (m_used == -CUDART_INF_F) ? 0.f : m_used * sl2;
             // ---- P = 2^(S*sl2 - m) from the registers, partial row sum, P (bf16) over my own S columns
-            l += softmax_exp_store(lane_addr + colS, sv, sl2, m_off);
+            l += softmax_exp_store<POLY>(lane_addr + colS, sv, sl2, m_off);
             tc_wait_st();
             tc_fence_before_sync();
             mbar_arrive(bars + B_PFULL);
+            if (threadIdx.x == 0) LB_TRACE(7, it);               // softmax: P stored, arrived
         }
         // ---- epilogue: combine the two partial row sums, normalise, write my half of the O columns
         float* rbuf = red + (n_tiles & 1) * 256;
@@ -305,10 +325,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
 }
 
-template <int D, bool CAUSAL>
-static int launch_attn_fwd(const CUtensorMap* tm, const AttnFwdParams& p, int n_work, cudaStream_t st) {
+template <int D, bool CAUSAL, int POLY>
+static int launch_attn_fwd_p(const CUtensorMap* tm, const AttnFwdParams& p, int n_work, cudaStream_t st) {
     using S = AttnFwdSmem<D>;
-    auto kern = attn_fwd_kernel<D, CAUSAL>;
+    auto kern = attn_fwd_kernel<D, CAUSAL, POLY>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
@@ -318,6 +338,27 @@ static int launch_attn_fwd(const CUtensorMap* tm, const AttnFwdParams& p, int n_
     dim3 grid((unsigned)n_work, (unsigned)p.heads);
     kern<<<grid, AT_THREADS, S::TOTAL, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], p);
     return check_launch("attn_fwd");
+}
+
+// fraction of exponentials evaluated on the FMA pipes: 1/POLY (LB_EXP_POLY=0|2|3|4 overrides the default for experiments)
+static int exp_poly_mod() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("LB_EXP_POLY");
+        v = e ? atoi(e) : 0;       // measured on B200 (scripts/attn_bench.py): 0 -> 232 us, 4 -> 243 us, 2 -> 253 us per launch:
+        if (v != 0 && v != 2 && v != 3 && v != 4) v = 0;   // the FMA pipe has no slack here, so the SFU-only path is the default
+    }
+    return v;
+}
+
+template <int D, bool CAUSAL>
+static int launch_attn_fwd(const CUtensorMap* tm, const AttnFwdParams& p, int n_work, cudaStream_t st) {
+    switch (exp_poly_mod()) {
+        case 3: return launch_attn_fwd_p<D, CAUSAL, 3>(tm, p, n_work, st);
+        case 4: return launch_attn_fwd_p<D, CAUSAL, 4>(tm, p, n_work, st);
+        case 2: return launch_attn_fwd_p<D, CAUSAL, 2>(tm, p, n_work, st);
+        default: return launch_attn_fwd_p<D, CAUSAL, 0>(tm, p, n_work, st);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -403,7 +444,15 @@ __global__ void __launch_bounds__(128) probe_ts_kernel(const __grid_constant__ C
 
 using namespace lb;
 
+static long long* g_attn_trace = nullptr;
+
 extern "C" {
+
+/* diagnostics: clock64 stamps of CTA (0,0) of subsequent lb_attn_fwd launches go to `buf` ([64][8] int64, device); NULL = off */
+int lb_attn_fwd_set_trace(void* buf) {
+    g_attn_trace = (long long*)buf;
+    return LB_OK;
+}
 
 int lb_attn_fwd(const void* Q, const void* K0, const void* V0, const void* K1, const void* V1, const uint8_t* qflag,
                 const int32_t* work, int n_work, const int32_t* kv_start, const int32_t* kv_end,
@@ -426,6 +475,7 @@ int lb_attn_fwd(const void* Q, const void* K0, const void* V0, const void* K1, c
     AttnFwdParams p;
     p.qflag = qflag; p.work = work; p.kv_start = kv_start; p.kv_end = kv_end; p.out_row = out_row;
     p.O = (__nv_bfloat16*)O; p.lse = lse; p.batch = batch; p.seqlen = seqlen; p.heads = heads; p.scale = scale;
+    p.trace = g_attn_trace;
     cudaStream_t st = (cudaStream_t)stream;
     if (head_dim == 128) return causal ? launch_attn_fwd<128, true>(tm, p, n_work, st) : launch_attn_fwd<128, false>(tm, p, n_work, st);
     return causal ? launch_attn_fwd<64, true>(tm, p, n_work, st) : launch_attn_fwd<64, false>(tm, p, n_work, st);

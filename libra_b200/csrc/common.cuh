@@ -68,6 +68,20 @@ __device__ __forceinline__ float fast_ex2(float x) {
     return y;
 }
 
+// 2^x on the FMA/ALU pipes (no SFU): Cody-Waite split x = n + f, f in [-0.5, 0.5], degree-3 minimax polynomial for 2^f
+// (max relative error 7.5e-5, far below bf16 resolution), 2^n applied by an integer add to the exponent field.
+// The softmax / score-recompute loops run a fraction of their exponentials through this to relieve the 16-lane/clk SFU,
+// which is the measured bottleneck of those phases (FlashAttention-4's trick).  Inputs below -126 give ~1e-38 (~0).
+__device__ __forceinline__ float poly_ex2(float x) {
+    x = fmaxf(x, -126.f);
+    const float r = x + 12582912.f;                 // 1.5 * 2^23: the integer part of x lands in the low mantissa bits
+    const float f = x - (r - 12582912.f);
+    float p = fmaf(f, 0.055171650f, 0.24261113f);
+    p = fmaf(p, f, 0.69326097f);
+    p = fmaf(p, f, 0.99992806f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(r) << 23));
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -224,6 +238,18 @@ __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t smem_addr, uint32_t ch
     return make_smem_desc(smem_addr, chunk_stride_bytes, 1024);
 }
 
+// Split (lo, hi) form of the same descriptor for issue loops: the high word is a per-kernel constant and stepping
+// through K only adds a small constant to the low word (start address >> 4), so issuing an MMA costs two integer adds
+// instead of rebuilding two 64-bit descriptors (measured: ~37 cycles per tcgen05.mma with the 64-bit form).
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+    return ((smem_addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+constexpr uint32_t DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);     // SBO = 1024 B, version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t desc_lo_kmajor(uint32_t smem_addr) { return desc_lo(smem_addr, 16); }
+__device__ __forceinline__ uint32_t desc_lo_mnmajor(uint32_t smem_addr, uint32_t chunk_stride_bytes) {
+    return desc_lo(smem_addr, chunk_stride_bytes);
+}
+
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32:
 //   [4,6) D fmt (1 = f32)  [7,10) A fmt (1 = bf16)  [10,13) B fmt (1 = bf16)
 //   [15] A major (0 = K, 1 = MN)   [16] B major   [17,23) N>>3   [24,29) M>>4
@@ -244,6 +270,33 @@ __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same, descriptors passed as (lo, DESC_HI_SW128) pairs
+__device__ __forceinline__ void umma_ss_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(DESC_HI_SW128), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_ts_lo(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(b_lo), "r"(DESC_HI_SW128), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // D[tmem] (+)= A[tmem] * B[smem]   (A: lane = row, one 32-bit column = 2 consecutive-K bf16)
 __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                         uint32_t accumulate) {
