@@ -422,7 +422,7 @@ def main():
                    "l2": "working set (>= 22 GB of weights per step) far exceeds the 126 MB L2; no explicit flush",
                    "tiny": bool(args.tiny)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cb,
-        "loss": float(last_loss.item()) if last_loss is not None else None,
+        "loss": float(last_loss.item()) * world if last_loss is not None else None,      # rank 0's mean loss over its samples
         "model_tflops_per_gpu": model_flops_step / (ms / args.steps * 1e-3) / 1e12, "peak_mem_gb": mem_gb,
     }
     print(json.dumps(line))

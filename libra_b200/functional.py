@@ -126,6 +126,53 @@ def bias_quick_gelu(x, bias):
     return BiasQuickGelu.apply(x, bias)
 
 
+# ----------------------------------------------------------------------------- two-stream routing
+# The language GEMMs (M = n_lang rows, N = 4096..11008) and the vision low-rank GEMMs (M = n_vis rows, N = 1024/2752 then
+# 4096/11008) of one routed projection are independent.  The vision ones are small: x_v A^T has only ~40 output tiles of
+# 256x256 for 148 SMs, so on one stream they leave most of the machine idle (and the language GEMM's last wave is partial
+# too).  Issuing the vision path on a side stream lets the hardware co-schedule the two tile sets; fork/join are events.
+USE_SIDE_STREAM = True
+_side = {}
+
+
+def _side_stream():
+    dev = torch.cuda.current_device()
+    st = _side.get(dev)
+    if st is None:
+        st = _side[dev] = torch.cuda.Stream(device=dev)
+    return st
+
+
+class _Fork:
+    """with _Fork() as f:  ...main-stream work...;  with f.side(): ...side-stream work...   (join on exit)"""
+
+    def __init__(self, enabled=True):
+        self.on = bool(enabled and USE_SIDE_STREAM and torch.cuda.is_available())
+
+    def __enter__(self):
+        if self.on:
+            self.main = torch.cuda.current_stream()
+            self.st = _side_stream()
+            self.st.wait_event(self.main.record_event())
+        return self
+
+    def side(self):
+        return torch.cuda.stream(self.st) if self.on else _Null()
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.main.wait_event(self.st.record_event())
+        return False
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
 # ----------------------------------------------------------------------------- routed linear
 # Weight-gradient accumulation fusion: when a parameter already owns a .grad buffer (e.g. a view into the flat
 # data-parallel gradient buffer, libra_b200.dist.FlatGradBuffer), dW is accumulated straight into it by the GEMM
@@ -151,18 +198,20 @@ class RoutedLinear(torch.autograd.Function):
     def forward(ctx, x, n_lang, W, A, B, residual):
         N = x.shape[0]
         y = torch.empty(N, W.shape[0], dtype=x.dtype, device=x.device)
-        if n_lang > 0:
-            if residual is None:
-                torch.matmul(x[:n_lang], W.t(), out=y[:n_lang])
-            else:
-                torch.addmm(residual[:n_lang], x[:n_lang], W.t(), out=y[:n_lang])
-        mid = None
-        if N - n_lang > 0:
-            mid = torch.matmul(x[n_lang:], A.t())
-            if residual is None:
-                torch.matmul(mid, B.t(), out=y[n_lang:])
-            else:
-                torch.addmm(residual[n_lang:], mid, B.t(), out=y[n_lang:])
+        mid = torch.empty(N - n_lang, A.shape[0], dtype=x.dtype, device=x.device) if N - n_lang > 0 else None
+        with _Fork(n_lang > 0 and N - n_lang > 0) as f:
+            if N - n_lang > 0:
+                with f.side():
+                    torch.matmul(x[n_lang:], A.t(), out=mid)
+                    if residual is None:
+                        torch.matmul(mid, B.t(), out=y[n_lang:])
+                    else:
+                        torch.addmm(residual[n_lang:], mid, B.t(), out=y[n_lang:])
+            if n_lang > 0:
+                if residual is None:
+                    torch.matmul(x[:n_lang], W.t(), out=y[:n_lang])
+                else:
+                    torch.addmm(residual[:n_lang], x[:n_lang], W.t(), out=y[:n_lang])
         ctx.n_lang = n_lang
         ctx.save_for_backward(x, W, A, B, mid)
         return y
@@ -175,23 +224,39 @@ class RoutedLinear(torch.autograd.Function):
         dy = dy.contiguous()
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         dW = dA = dB = None
-        if n_lang > 0:
-            if dx is not None:
-                torch.matmul(dy[:n_lang], W, out=dx[:n_lang])
-            if ctx.needs_input_grad[2]:
-                dW = _wgrad(W, dy[:n_lang].t(), x[:n_lang])
-        elif ctx.needs_input_grad[2]:
-            dW = torch.zeros_like(W)
+        dmid = torch.empty_like(mid) if mid is not None else None
+        fusable = lambda P_: FUSE_WGRAD_ACCUMULATE and P_.grad is not None and P_.grad.dtype == dy.dtype
+        # non-fused weight gradients are allocated here, on the main stream, before any side-stream work
         if N - n_lang > 0:
-            dyv = dy[n_lang:]
-            dmid = torch.matmul(dyv, B)
-            if dx is not None:
-                torch.matmul(dmid, A, out=dx[n_lang:])
-            if ctx.needs_input_grad[4]:
-                dB = _wgrad(B, dyv.t(), mid)
-            if ctx.needs_input_grad[3]:
-                dA = _wgrad(A, dmid.t(), x[n_lang:])
-        else:
+            if ctx.needs_input_grad[4] and not fusable(B):
+                dB = torch.empty_like(B)
+            if ctx.needs_input_grad[3] and not fusable(A):
+                dA = torch.empty_like(A)
+        with _Fork(n_lang > 0 and N - n_lang > 0) as f:
+            if N - n_lang > 0:
+                with f.side():
+                    dyv = dy[n_lang:]
+                    torch.matmul(dyv, B, out=dmid)
+                    if dx is not None:
+                        torch.matmul(dmid, A, out=dx[n_lang:])
+                    if ctx.needs_input_grad[4]:
+                        if dB is None:
+                            B.grad.addmm_(dyv.t(), mid)
+                        else:
+                            torch.matmul(dyv.t(), mid, out=dB)
+                    if ctx.needs_input_grad[3]:
+                        if dA is None:
+                            A.grad.addmm_(dmid.t(), x[n_lang:])
+                        else:
+                            torch.matmul(dmid.t(), x[n_lang:], out=dA)
+            if n_lang > 0:
+                if dx is not None:
+                    torch.matmul(dy[:n_lang], W, out=dx[:n_lang])
+                if ctx.needs_input_grad[2]:
+                    dW = _wgrad(W, dy[:n_lang].t(), x[:n_lang])
+        if n_lang == 0 and ctx.needs_input_grad[2]:
+            dW = torch.zeros_like(W)
+        if N - n_lang == 0:
             if ctx.needs_input_grad[3]:
                 dA = torch.zeros_like(A)
             if ctx.needs_input_grad[4]:
@@ -207,36 +272,43 @@ class RoutedFanout(torch.autograd.Function):
     """Several routed projections of the SAME input in one autograd node (q/k/v + the two bridge down-projections, or
     gate + up).  Forward is the same GEMMs as RoutedLinear / RoutedDown; backward accumulates every branch's input
     gradient into one buffer through the GEMM (beta = 1), replacing autograd's N-1 full-size gradient additions.
+    Language GEMMs run on the current stream, vision GEMMs on the side stream (see _Fork).
     kinds[i] == "lin":  weights (W, A, B) -> y = [x_l W^T ; (x_v A^T) B^T];   "down": weights (A_lang, A_vis)."""
 
     @staticmethod
     def forward(ctx, x, n_lang, kinds, *weights):
         N = x.shape[0]
+        nv = N - n_lang
         xl, xv = x[:n_lang], x[n_lang:]
-        outs, mids, wi = [], [], 0
-        for kind in kinds:
+        outs, mids, specs, wi = [], [], [], 0
+        for kind in kinds:                      # allocate everything on the main stream first
             if kind == "lin":
                 W, A, B = weights[wi:wi + 3]
                 wi += 3
                 y = torch.empty(N, W.shape[0], dtype=x.dtype, device=x.device)
-                mid = None
-                if n_lang > 0:
-                    torch.matmul(xl, W.t(), out=y[:n_lang])
-                if N - n_lang > 0:
-                    mid = torch.matmul(xv, A.t())
-                    torch.matmul(mid, B.t(), out=y[n_lang:])
-                mids.append(mid)
+                mid = torch.empty(nv, A.shape[0], dtype=x.dtype, device=x.device) if nv > 0 else None
+                specs.append((kind, y, mid, W, A, B))
             else:
                 Al, Av = weights[wi:wi + 2]
                 wi += 2
                 y = torch.empty(N, Al.shape[0], dtype=x.dtype, device=x.device)
-                if n_lang > 0:
-                    torch.matmul(xl, Al.t(), out=y[:n_lang])
-                if N - n_lang > 0:
-                    torch.matmul(xv, Av.t(), out=y[n_lang:])
-                mids.append(None)
+                mid = None
+                specs.append((kind, y, None, Al, Av, None))
             outs.append(y)
-        ctx.n_lang, ctx.kinds, ctx.n_mid = n_lang, kinds, len(mids)
+            mids.append(mid)
+        with _Fork(n_lang > 0 and nv > 0) as f:
+            if nv > 0:
+                with f.side():
+                    for kind, y, mid, W0, W1, W2 in specs:
+                        if kind == "lin":
+                            torch.matmul(xv, W1.t(), out=mid)
+                            torch.matmul(mid, W2.t(), out=y[n_lang:])
+                        else:
+                            torch.matmul(xv, W1.t(), out=y[n_lang:])
+            if n_lang > 0:
+                for kind, y, mid, W0, W1, W2 in specs:
+                    torch.matmul(xl, W0.t(), out=y[:n_lang])
+        ctx.n_lang, ctx.kinds = n_lang, kinds
         ctx.mid_present = [m is not None for m in mids]
         ctx.save_for_backward(x, *weights, *[m for m in mids if m is not None])
         return tuple(outs)
@@ -249,12 +321,35 @@ class RoutedFanout(torch.autograd.Function):
         weights = saved[1:1 + nw]
         mids_saved = list(saved[1 + nw:])
         n, N = ctx.n_lang, x.shape[0]
-        need_dx = ctx.needs_input_grad[0]
-        dx = torch.empty_like(x) if need_dx else None
-        first_l, first_v = True, True
-        grads = []
-        wi = 0
+        nv = N - n
         ng = ctx.needs_input_grad
+        need_dx = ng[0]
+        dx = torch.empty_like(x) if need_dx else None
+        fusable = lambda P_: FUSE_WGRAD_ACCUMULATE and P_.grad is not None and P_.grad.dtype == x.dtype
+        # plan (and allocate on the main stream) per branch
+        plan, grads, wi = [], [], 0
+        for oi, kind in enumerate(ctx.kinds):
+            dy = douts[oi]
+            dy = dy.contiguous() if dy is not None else None
+            if kind == "lin":
+                W, A, B = weights[wi:wi + 3]
+                mid = mids_saved.pop(0) if ctx.mid_present[oi] else None
+                e = dict(kind=kind, dy=dy, W=W, A=A, B=B, mid=mid, gi=len(grads),
+                         needW=ng[3 + wi], needA=ng[3 + wi + 1], needB=ng[3 + wi + 2])
+                if dy is not None and nv > 0:
+                    e["dmid"] = torch.empty_like(mid)
+                    e["gA"] = torch.empty_like(A) if (e["needA"] and not fusable(A)) else None
+                    e["gB"] = torch.empty_like(B) if (e["needB"] and not fusable(B)) else None
+                grads += [None, None, None]
+                wi += 3
+            else:
+                Al, Av = weights[wi:wi + 2]
+                e = dict(kind=kind, dy=dy, Al=Al, Av=Av, gi=len(grads), needL=ng[3 + wi], needV=ng[3 + wi + 1])
+                if dy is not None and nv > 0:
+                    e["gV"] = torch.empty_like(Av) if (e["needV"] and not fusable(Av)) else None
+                grads += [None, None]
+                wi += 2
+            plan.append(e)
 
         def acc(dst, a, b, first):
             if first:
@@ -262,54 +357,62 @@ class RoutedFanout(torch.autograd.Function):
             else:
                 dst.addmm_(a, b)
 
-        for oi, kind in enumerate(ctx.kinds):
-            dy = douts[oi]
-            if kind == "lin":
-                W, A, B = weights[wi:wi + 3]
-                gW = gA = gB = None
-                mid = mids_saved.pop(0) if ctx.mid_present[oi] else None
-                if dy is not None:
-                    dy = dy.contiguous()
-                    if n > 0:
+        first_l = first_v = True
+        with _Fork(n > 0 and nv > 0) as f:
+            if nv > 0:
+                with f.side():
+                    for e in plan:
+                        dy = e["dy"]
+                        if dy is None:
+                            continue
+                        if e["kind"] == "lin":
+                            torch.matmul(dy[n:], e["B"], out=e["dmid"])
+                            if need_dx:
+                                acc(dx[n:], e["dmid"], e["A"], first_v)
+                                first_v = False
+                            if e["needB"]:
+                                if e["gB"] is None:
+                                    e["B"].grad.addmm_(dy[n:].t(), e["mid"])
+                                else:
+                                    torch.matmul(dy[n:].t(), e["mid"], out=e["gB"])
+                                    grads[e["gi"] + 2] = e["gB"]
+                            if e["needA"]:
+                                if e["gA"] is None:
+                                    e["A"].grad.addmm_(e["dmid"].t(), x[n:])
+                                else:
+                                    torch.matmul(e["dmid"].t(), x[n:], out=e["gA"])
+                                    grads[e["gi"] + 1] = e["gA"]
+                        else:
+                            if need_dx:
+                                acc(dx[n:], dy[n:], e["Av"], first_v)
+                                first_v = False
+                            if e["needV"]:
+                                if e["gV"] is None:
+                                    e["Av"].grad.addmm_(dy[n:].t(), x[n:])
+                                else:
+                                    torch.matmul(dy[n:].t(), x[n:], out=e["gV"])
+                                    grads[e["gi"] + 1] = e["gV"]
+            if n > 0:
+                for e in plan:
+                    dy = e["dy"]
+                    if dy is None:
+                        continue
+                    if e["kind"] == "lin":
                         if need_dx:
-                            acc(dx[:n], dy[:n], W, first_l)
+                            acc(dx[:n], dy[:n], e["W"], first_l)
                             first_l = False
-                        if ng[3 + wi]:
-                            gW = _wgrad(W, dy[:n].t(), x[:n])
-                    if N - n > 0:
-                        dmid = torch.matmul(dy[n:], B)
+                        if e["needW"]:
+                            grads[e["gi"]] = _wgrad(e["W"], dy[:n].t(), x[:n])
+                    else:
                         if need_dx:
-                            acc(dx[n:], dmid, A, first_v)
-                            first_v = False
-                        if ng[3 + wi + 2]:
-                            gB = _wgrad(B, dy[n:].t(), mid)
-                        if ng[3 + wi + 1]:
-                            gA = _wgrad(A, dmid.t(), x[n:])
-                grads += [gW, gA, gB]
-                wi += 3
-            else:
-                Al, Av = weights[wi:wi + 2]
-                gl = gv = None
-                if dy is not None:
-                    dy = dy.contiguous()
-                    if n > 0:
-                        if need_dx:
-                            acc(dx[:n], dy[:n], Al, first_l)
+                            acc(dx[:n], dy[:n], e["Al"], first_l)
                             first_l = False
-                        if ng[3 + wi]:
-                            gl = _wgrad(Al, dy[:n].t(), x[:n])
-                    if N - n > 0:
-                        if need_dx:
-                            acc(dx[n:], dy[n:], Av, first_v)
-                            first_v = False
-                        if ng[3 + wi + 1]:
-                            gv = _wgrad(Av, dy[n:].t(), x[n:])
-                grads += [gl, gv]
-                wi += 2
+                        if e["needL"]:
+                            grads[e["gi"]] = _wgrad(e["Al"], dy[:n].t(), x[:n])
         if need_dx:
             if first_l and n > 0:
                 dx[:n].zero_()
-            if first_v and N - n > 0:
+            if first_v and nv > 0:
                 dx[n:].zero_()
         return (dx, None, None, *grads)
 

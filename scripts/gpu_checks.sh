@@ -32,6 +32,7 @@ for s in $suites; do
       run attn_vit 300 tests/test_gpu_attention.py -k "vit"
       ;;
     attn_bwd) run attn_bwd 600 tests/test_gpu_attention.py -k "backward" ;;
+    attn_prop) run attn_prop 600 tests/test_gpu_attention.py -k "properties or property" ;;
     model) run model 900 tests/test_gpu_model.py ;;
     vision) run vision 600 tests/test_gpu_vision.py ;;
     all) run all 1800 tests ;;
