@@ -115,7 +115,8 @@ class CpuReference:
     def __init__(self, n_layers: int = 1, threads: int = 0, dtype=torch.float32):
         from oracle import libra_oracle as O
         self.O = O
-        self.threads = threads or (os.cpu_count() or 1)
+        # MKL/oneDNN GEMMs of this size stop scaling (and start thrashing) well before 128 threads: cap at 64
+        self.threads = threads or min(os.cpu_count() or 1, 64)
         torch.set_num_threads(self.threads)
         self.n_layers, self.dtype = n_layers, dtype
         self.d = d = O.LibraDims()
@@ -180,11 +181,22 @@ def run_reference_arm(args):
         return 0
     ref = CpuReference(n_layers=1)
     secs = []
+    t_start = time.perf_counter()
+    budget_s = 150.0                      # the whole arm must end within a few minutes on any host
+    done_w = 0
     for i in range(args.warmup + args.steps):
         t = ref.step()
         if i >= args.warmup:
             secs.append(t)
+        else:
+            done_w += 1
+        if time.perf_counter() - t_start > budget_s and (secs or i + 1 >= args.warmup):
+            if not secs:
+                secs.append(t)            # budget exhausted during warm-up: report the last warm-up sample
+            break
     cb = ref.result(statistics.median(secs)) if secs else None
+    if cb is not None and len(secs) < args.steps:
+        cb["sample"] += f"; time budget {budget_s:.0f} s reached after {done_w} warm-up + {len(secs)} timed samples"
     v = cb["value"] if cb else float("nan")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": (statistics.median(secs) * 1e3 if secs else None), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
