@@ -63,6 +63,19 @@ def parse():
     return ap.parse_args()
 
 
+def attn_traffic(mb, T, cfg):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the attention forward kernel from the committed
+    `ncu --set full` capture (profiles/attn_fwd_traffic.json); only valid for the shape it was captured on."""
+    p = os.path.join(ROOT, "profiles", "attn_fwd_traffic.json")
+    try:
+        d = json.load(open(p))
+        if d["shape"].startswith(f"B={mb},T={T},H={cfg.num_attention_heads},"):
+            return d["dram_bytes_read"] + d["dram_bytes_write"]
+    except Exception:
+        pass
+    return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -411,7 +424,7 @@ def main():
         roof = {"kernel": "attn_fwd_kernel<128,causal> (bridge attention forward)", "bound": "tensor", "achieved": ach,
                 "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tflops_sustained"],
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']}); kernel timed inside a long step",
-                "traffic": None, "avg_launch_ms": t_ms,
+                "traffic": attn_traffic(MB, T, cfg), "avg_launch_ms": t_ms,
                 "algorithmic_flops_per_launch": fl["attn_per_layer_fwd"],
                 "other_kernels_ms": {k: v for k, v in kern.items() if k != "lb_attn_fwd"},
                 "bwd_achieved_tflops": (2.5 * fl["attn_per_layer_fwd"] / ((kern.get("lb_attn_bwd_dq", 0) + kern.get("lb_attn_bwd_dkv", 0)) * 1e-3) / 1e12)
