@@ -2,11 +2,9 @@
 //
 //   lb_attn_bwd_dq : CTA = (sample, 128-row q tile, variant, head); loops over 64-wide kv tiles:
 //                    S = Q.K^T, dP = dO.V^T (SS MMAs) -> dS = P*(dP-delta)*scale (threads) -> dQ += dS.K (TS MMA, K as MN-major B)
-//                    two score stages in TMEM: tile t+1's S/dP MMAs overlap the dS computation of tile t (16 compute warps)
 //   lb_attn_bwd_dkv: CTA = (sample, 128-row kv tile, variant, head); loops over 128-row q tiles that contain rows of the
 //                    variant: S^T = K.Q^T, dP^T = V.dO^T -> P^T, dS^T (threads) -> dV += P^T.dO, dK += dS^T.Q (TS MMAs,
-//                    dO / Q as MN-major B); software-pipelined by 64-query halves (16 compute warps).
-// Both kernels own the SM (512 TMEM columns) and overlap tensor-pipe work with the exp/pack phase inside the CTA.
+//                    dO / Q as MN-major B).
 // P is recomputed from the saved log-sum-exp; delta = rowsum(dO*O) comes from lb_attn_bwd_prepare.
 // Gradients w.r.t. the two operand variants (K0/V0 seen by qflag==0 rows, K1/V1 by qflag==1 rows) are written to
 // separate buffers; the prologue's adjoint (lb_attn_prep_bwd) folds them into dk, dv and the bridge gradients.
@@ -16,11 +14,11 @@
 
 namespace lb {
 
+constexpr int BW_COMPUTE_WARPS = 8;              // two warpgroups, each owns half of the score columns of a tile
+constexpr int BW_COMPUTE_THREADS = BW_COMPUTE_WARPS * 32;
+constexpr int BW_WARP_TMA = BW_COMPUTE_WARPS, BW_WARP_MMA = BW_COMPUTE_WARPS + 1;
+constexpr int BW_THREADS = (BW_COMPUTE_WARPS + 2) * 32;
 constexpr float LOG2E_F = 1.4426950408889634f;
-// dK/dV kernel: 16 compute warps (4 warpgroups; two per 64-query half, 32 query columns per thread), 1 CTA per SM
-constexpr int KV_COMPUTE_WARPS = 16;
-constexpr int KV_WARP_TMA = KV_COMPUTE_WARPS, KV_WARP_MMA = KV_COMPUTE_WARPS + 1;
-constexpr int KV_THREADS = (KV_COMPUTE_WARPS + 2) * 32;
 
 struct AttnBwdParams {
     const uint8_t* qflag;      // [B*T] or null
@@ -64,16 +62,18 @@ __device__ __forceinline__ void dq_tile(uint32_t ts, uint32_t tdp, float sl2, fl
     tmem_st16(ts, s);       // dS (bf16) over my own, already consumed S columns
 }
 
-// dK/dV kernel: thread = key row; 32 query columns at TMEM `ts` (S^T) / `tdp` (dP^T); per-column lse2 / delta in smem.
+// dK/dV kernel: thread = key row; 64 query columns at TMEM `ts` (S^T) / `tdp` (dP^T); per-column lse2 / delta in smem.
 template <bool MASK, bool CAUSAL>
 __device__ __forceinline__ void dkv_tile(uint32_t ts, uint32_t tdp, const float* __restrict__ st, float sl2, float scale, int kj,
                                          int qbase, bool key_ok) {
-    uint32_t s[32], dp[32];
+    uint32_t s[64], dp[64];
     tmem_ld32(ts, s);
+    tmem_ld32(ts + 32, s + 32);
     tmem_ld32(tdp, dp);
+    tmem_ld32(tdp + 32, dp + 32);
     tc_wait_ld();
 #pragma unroll
-    for (int j = 0; j < 32; j += 2) {
+    for (int j = 0; j < 64; j += 2) {
         float p0 = fast_ex2(fmaf(__uint_as_float(s[j]), sl2, -st[j]));          // lse = +inf on excluded query rows
         float p1 = fast_ex2(fmaf(__uint_as_float(s[j + 1]), sl2, -st[j + 1]));
         if (MASK) {
@@ -86,8 +86,8 @@ __device__ __forceinline__ void dkv_tile(uint32_t ts, uint32_t tdp, const float*
         s[j >> 1] = pack_bf16(p0, p1);
         dp[j >> 1] = pack_bf16(d0, d1);
     }
-    tmem_st16(ts, s);        // P^T (bf16, 16 columns) over my own, already consumed S^T columns
-    tmem_st16(tdp, dp);      // dS^T over dP^T
+    tmem_st32(ts, s);        // P^T (bf16, 32 columns) over my own, already consumed S^T columns
+    tmem_st32(tdp, dp);      // dS^T over dP^T
 }
 
 // =====================================================================================================
@@ -96,25 +96,17 @@ __device__ __forceinline__ void dkv_tile(uint32_t ts, uint32_t tdp, const float*
 template <int D>
 struct DqSmem {
     static constexpr int BN = 64;
-    static constexpr int STAGES = 2;
     static constexpr int Q_BYTES = 128 * D * 2;
     static constexpr int DO_BYTES = 128 * D * 2;
-    static constexpr int K_BYTES = BN * D * 2;       // per stage
-    static constexpr int V_BYTES = BN * D * 2;       // per stage
-    static constexpr int BAR_OFF = Q_BYTES + DO_BYTES + STAGES * (K_BYTES + V_BYTES);
-    static constexpr int TOTAL = BAR_OFF + 1024 + 256;
+    static constexpr int K_BYTES = BN * D * 2;
+    static constexpr int V_BYTES = BN * D * 2;
+    static constexpr int BAR_OFF = Q_BYTES + DO_BYTES + K_BYTES + V_BYTES;
+    static constexpr int TOTAL = BAR_OFF + 1024 + 128;
 };
-// per stage s in {0,1}: K/V full/empty, SDP (scores ready), DS (dS written: 256 arrivals)
-enum { DQ_QDO = 0, DQ_KFULL0, DQ_KFULL1, DQ_KEMPTY0, DQ_KEMPTY1, DQ_VFULL0, DQ_VFULL1, DQ_VEMPTY0, DQ_VEMPTY1, DQ_SDP0, DQ_SDP1,
-       DQ_DS0, DQ_DS1, DQ_READY, DQ_NBAR };
-constexpr int DQ_COMPUTE_WARPS = 16;      // warpgroups 0,1 work on even kv tiles (score stage 0), warpgroups 2,3 on odd tiles
-constexpr int DQ_WARP_TMA = DQ_COMPUTE_WARPS, DQ_WARP_MMA = DQ_COMPUTE_WARPS + 1;
-constexpr int DQ_THREADS = (DQ_COMPUTE_WARPS + 2) * 32;
+enum { DQ_QDO = 0, DQ_KFULL, DQ_KEMPTY, DQ_VFULL, DQ_VEMPTY, DQ_SDP, DQ_DS, DQ_READY, DQ_NBAR };
 
-// One CTA per SM, 512 TMEM columns: [0,128) score stage 0 = S | dP, [128,256) score stage 1, [256,256+D) dQ accumulator.
-// The tensor pipe computes S/dP of kv tile t+1 into the other stage while two warpgroups turn tile t's scores into dS.
 template <int D, bool CAUSAL>
-__global__ void __launch_bounds__(DQ_THREADS, 1)
+__global__ void __launch_bounds__(BW_THREADS, 2)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                    const __grid_constant__ CUtensorMap tmK0, const __grid_constant__ CUtensorMap tmV0,
                    const __grid_constant__ CUtensorMap tmK1, const __grid_constant__ CUtensorMap tmV1,
@@ -125,7 +117,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     constexpr int BN = S::BN;
     uint8_t* sQ = smem;
     uint8_t* sdO = sQ + S::Q_BYTES;
-    uint8_t* sKV = sdO + S::DO_BYTES;                 // stage s: K at sKV + s*(K+V), V right after K
+    uint8_t* sK = sdO + S::DO_BYTES;
+    uint8_t* sV = sK + S::K_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + DQ_NBAR);
 
@@ -143,13 +136,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     if (CAUSAL && last_tile > (q0 + 128) / BN) last_tile = (q0 + 128) / BN;
     const int n_tiles = last_tile > first_tile ? last_tile - first_tile : 0;
 
-    constexpr uint32_t TMEM_COLS = 512, COL_SC = 0, COL_DQ = 256;      // score stage s at COL_SC + 128 s: S [0,64) dP [64,128)
+    constexpr uint32_t TMEM_COLS = 256, COL_S = 0, COL_DP = 64, COL_DQ = 128;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < DQ_NBAR; ++i) mbar_init(bars + i, (i == DQ_DS0 || i == DQ_DS1) ? 256 : 1);
+        for (int i = 0; i < DQ_NBAR; ++i) mbar_init(bars + i, i == DQ_DS ? BW_COMPUTE_THREADS : 1);
         fence_barrier_init();
     }
-    if (warp == DQ_WARP_MMA) {
+    if (warp == BW_WARP_MMA) {
         tmem_alloc(tmem_slot, TMEM_COLS);
         tmem_relinquish();
     }
@@ -158,7 +151,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == DQ_WARP_TMA) {
+    if (warp == BW_WARP_TMA) {
         if (elect_one() && n_tiles > 0) {
             const CUtensorMap* tK = variant ? &tmK1 : &tmK0;
             const CUtensorMap* tV = variant ? &tmV1 : &tmV0;
@@ -170,123 +163,105 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 tma_load_2d(sdO + c * (128 * 128), &tmdO, bars + DQ_QDO, h * D + c * 64, row_q);
             }
             for (int it = 0; it < n_tiles; ++it) {
-                const int st = it & 1;
-                const uint32_t ph = (uint32_t)(it >> 1) & 1u;
-                uint8_t* sK = sKV + st * (S::K_BYTES + S::V_BYTES);
-                uint8_t* sV = sK + S::K_BYTES;
                 const int row_k = b * T + (first_tile + it) * BN;
-                mbar_wait(bars + DQ_KEMPTY0 + st, ph ^ 1u);
-                mbar_arrive_expect_tx(bars + DQ_KFULL0 + st, S::K_BYTES);
+                const uint32_t ph = (uint32_t)it & 1u;
+                mbar_wait(bars + DQ_KEMPTY, ph ^ 1u);
+                mbar_arrive_expect_tx(bars + DQ_KFULL, S::K_BYTES);
 #pragma unroll
-                for (int c = 0; c < D / 64; ++c) tma_load_2d(sK + c * (BN * 128), tK, bars + DQ_KFULL0 + st, h * D + c * 64, row_k);
-                mbar_wait(bars + DQ_VEMPTY0 + st, ph ^ 1u);
-                mbar_arrive_expect_tx(bars + DQ_VFULL0 + st, S::V_BYTES);
+                for (int c = 0; c < D / 64; ++c) tma_load_2d(sK + c * (BN * 128), tK, bars + DQ_KFULL, h * D + c * 64, row_k);
+                mbar_wait(bars + DQ_VEMPTY, ph ^ 1u);
+                mbar_arrive_expect_tx(bars + DQ_VFULL, S::V_BYTES);
 #pragma unroll
-                for (int c = 0; c < D / 64; ++c) tma_load_2d(sV + c * (BN * 128), tV, bars + DQ_VFULL0 + st, h * D + c * 64, row_k);
+                for (int c = 0; c < D / 64; ++c) tma_load_2d(sV + c * (BN * 128), tV, bars + DQ_VFULL, h * D + c * 64, row_k);
             }
         }
-    } else if (warp == DQ_WARP_MMA) {
+    } else if (warp == BW_WARP_MMA) {
         if (elect_one() && n_tiles > 0) {
             constexpr uint32_t idesc_s = make_idesc_bf16(128, BN, 0, 0);
             constexpr uint32_t idesc_dq = make_idesc_bf16(128, D, 0, 1);
             const uint32_t dQ0 = desc_lo_kmajor(smem_u32(sQ)), ddO0 = desc_lo_kmajor(smem_u32(sdO));
-            auto issue_dq = [&](int t) {        // dQ += dS(t) . K(t): dS of keys 16kk.. at column 32*(kk/2) + 8*(kk%2) of the stage
-                const int st = t & 1;
-                const uint32_t dKmn = desc_lo_mnmajor(smem_u32(sKV + st * (S::K_BYTES + S::V_BYTES)), BN * 128);
-#pragma unroll
-                for (int kk = 0; kk < BN / 16; ++kk)
-                    umma_ts_lo(tmem_base + COL_DQ, tmem_base + COL_SC + st * 128 + (uint32_t)(kk / 2) * 32 + (uint32_t)(kk % 2) * 8,
-                               dKmn + (uint32_t)kk * (2048 >> 4), idesc_dq, (t | kk) ? 1u : 0u);
-                tc_commit(bars + DQ_KEMPTY0 + st);
-            };
+            const uint32_t dK0 = desc_lo_kmajor(smem_u32(sK)), dV0 = desc_lo_kmajor(smem_u32(sV));
+            const uint32_t dKmn0 = desc_lo_mnmajor(smem_u32(sK), BN * 128);
             mbar_wait(bars + DQ_QDO, 0);
             for (int it = 0; it < n_tiles; ++it) {
-                const int st = it & 1;
-                const uint32_t ph = (uint32_t)(it >> 1) & 1u;
-                const uint32_t aK = smem_u32(sKV + st * (S::K_BYTES + S::V_BYTES));
-                const uint32_t dK0 = desc_lo_kmajor(aK), dV0 = desc_lo_kmajor(aK + S::K_BYTES);
-                const uint32_t colS = COL_SC + st * 128, colDP = colS + 64;
-                mbar_wait(bars + DQ_KFULL0 + st, ph);
+                const uint32_t ph = (uint32_t)it & 1u;
+                mbar_wait(bars + DQ_KFULL, ph);
                 tc_fence_after_sync();
 #pragma unroll
                 for (int kk = 0; kk < D / 16; ++kk) {
                     const uint32_t offA = ((uint32_t)(kk / 4) * (128 * 128) + (uint32_t)(kk % 4) * 32) >> 4;
                     const uint32_t offB = ((uint32_t)(kk / 4) * (BN * 128) + (uint32_t)(kk % 4) * 32) >> 4;
-                    umma_ss_lo(tmem_base + colS, dQ0 + offA, dK0 + offB, idesc_s, kk ? 1u : 0u);
+                    umma_ss_lo(tmem_base + COL_S, dQ0 + offA, dK0 + offB, idesc_s, kk ? 1u : 0u);
                 }
-                mbar_wait(bars + DQ_VFULL0 + st, ph);
+                mbar_wait(bars + DQ_VFULL, ph);
                 tc_fence_after_sync();
 #pragma unroll
                 for (int kk = 0; kk < D / 16; ++kk) {
                     const uint32_t offA = ((uint32_t)(kk / 4) * (128 * 128) + (uint32_t)(kk % 4) * 32) >> 4;
                     const uint32_t offB = ((uint32_t)(kk / 4) * (BN * 128) + (uint32_t)(kk % 4) * 32) >> 4;
-                    umma_ss_lo(tmem_base + colDP, ddO0 + offA, dV0 + offB, idesc_s, kk ? 1u : 0u);
+                    umma_ss_lo(tmem_base + COL_DP, ddO0 + offA, dV0 + offB, idesc_s, kk ? 1u : 0u);
                 }
-                tc_commit(bars + DQ_VEMPTY0 + st);
-                tc_commit(bars + DQ_SDP0 + st);
-                if (it > 0) {                                   // tile it-1 lives in the other stage
-                    mbar_wait(bars + DQ_DS0 + (st ^ 1), (uint32_t)((it - 1) >> 1) & 1u);
-                    tc_fence_after_sync();
-                    issue_dq(it - 1);
-                }
-            }
-            {
-                const int last = n_tiles - 1;
-                mbar_wait(bars + DQ_DS0 + (last & 1), (uint32_t)(last >> 1) & 1u);
+                tc_commit(bars + DQ_VEMPTY);
+                tc_commit(bars + DQ_SDP);
+                mbar_wait(bars + DQ_DS, ph);
                 tc_fence_after_sync();
-                issue_dq(last);
+#pragma unroll
+                for (int kk = 0; kk < BN / 16; ++kk)     // dS of keys 16kk.. lives at column 32*(kk/2) + 8*(kk%2)
+                    umma_ts_lo(tmem_base + COL_DQ, tmem_base + COL_S + (uint32_t)(kk / 2) * 32 + (uint32_t)(kk % 2) * 8,
+                               dKmn0 + (uint32_t)kk * (2048 >> 4), idesc_dq, (it | kk) ? 1u : 0u);
+                tc_commit(bars + DQ_KEMPTY);
+                tc_commit(bars + DQ_READY);
             }
-            tc_commit(bars + DQ_READY);
         }
     } else {
-        // ---------------- compute warps: thread = query row (TMEM lane); warpgroup g: score stage g/2, 32 key columns (g%2)
-        const int wg = warp >> 2, stage = wg >> 1, halfc = wg & 1;
+        // ---------------- compute warps: dS = P * (dP - delta) * scale for my 32 of the tile's 64 key columns
+        const int half = warp >> 2;
         const int r = (warp & 3) * 32 + (threadIdx.x & 31);
         const int qi = q0 + r;
         const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        const uint32_t colS = COL_SC + stage * 128 + halfc * 32, colDP = colS + 64;   // my dS (bf16) goes to [colS, colS+16)
+        const uint32_t colS = COL_S + half * 32, colDP = COL_DP + half * 32;      // my dS (bf16) goes to [colS, colS+16)
         const float sl2 = p.scale * LOG2E_F;
         const int64_t stat_idx = ((int64_t)b * p.heads + h) * T + (qi < T ? qi : 0);
         const bool row_ok = (qi < T) && (!p.qflag || (int)p.qflag[(int64_t)b * T + (qi < T ? qi : 0)] == variant);
         const float lse2 = row_ok ? p.lse[stat_idx] * LOG2E_F : CUDART_INF_F;
         const float dlt = row_ok ? p.delta[stat_idx] : 0.f;
-        for (int it = stage; it < n_tiles; it += 2) {
-            const uint32_t ph = (uint32_t)(it >> 1) & 1u;
-            const int kv0 = (first_tile + it) * BN + halfc * 32;
+        for (int it = 0; it < n_tiles; ++it) {
+            const uint32_t ph = (uint32_t)it & 1u;
+            const int kv0 = (first_tile + it) * BN + half * 32;
             const bool need_mask = (CAUSAL && kv0 + 31 > q0) || (kv0 + 32 > kve) || (kv0 < kvs);
-            mbar_wait(bars + DQ_SDP0 + stage, ph);
+            mbar_wait(bars + DQ_SDP, ph);
             tc_fence_after_sync();
             if (need_mask) dq_tile<true, CAUSAL>(lane_addr + colS, lane_addr + colDP, sl2, lse2, dlt, p.scale, kv0, qi, kvs, kve);
             else           dq_tile<false, CAUSAL>(lane_addr + colS, lane_addr + colDP, sl2, lse2, dlt, p.scale, kv0, qi, kvs, kve);
             tc_wait_st();
             tc_fence_before_sync();
-            mbar_arrive(bars + DQ_DS0 + stage);
+            mbar_arrive(bars + DQ_DS);
         }
         if (n_tiles > 0) {
-            mbar_wait(bars + DQ_READY, 0);
+            mbar_wait(bars + DQ_READY, (uint32_t)(n_tiles - 1) & 1u);
             tc_fence_after_sync();
         }
-        constexpr int DQC = D / 4;                 // dQ columns stored by each of the 4 warpgroups
-        __nv_bfloat16* orow = p.out0 + ((int64_t)b * T + (qi < T ? qi : 0)) * ((int64_t)p.heads * D) + (int64_t)h * D + wg * DQC;
+        constexpr int DH = D / 2;
+        __nv_bfloat16* orow = p.out0 + ((int64_t)b * T + (qi < T ? qi : 0)) * ((int64_t)p.heads * D) + (int64_t)h * D + half * DH;
 #pragma unroll 1
-        for (int c = 0; c < DQC / 16; ++c) {
-            uint32_t v[16];
+        for (int c = 0; c < DH / 32; ++c) {
+            uint32_t v[32];
             if (n_tiles > 0) {
-                tmem_ld16(lane_addr + COL_DQ + wg * DQC + c * 16, v);
+                tmem_ld32(lane_addr + COL_DQ + half * DH + c * 32, v);
                 tc_wait_ld();
             } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = 0u;
+                for (int j = 0; j < 32; ++j) v[j] = 0u;
             }
             if (row_ok) {
 #pragma unroll
-                for (int j = 0; j < 16; j += 8) {
+                for (int j = 0; j < 32; j += 8) {
                     uint4 o;
                     o.x = pack_bf16(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
                     o.y = pack_bf16(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
                     o.z = pack_bf16(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
                     o.w = pack_bf16(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
-                    *reinterpret_cast<uint4*>(orow + c * 16 + j) = o;
+                    *reinterpret_cast<uint4*>(orow + c * 32 + j) = o;
                 }
             }
             __syncwarp();
@@ -294,7 +269,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc_fence_before_sync();
     }
     __syncthreads();
-    if (warp == DQ_WARP_MMA) {
+    if (warp == BW_WARP_MMA) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
@@ -315,11 +290,10 @@ struct DkvSmem {
     static constexpr int BAR_OFF = STAT_OFF + STAT_BYTES;
     static constexpr int TOTAL = BAR_OFF + 1024 + 256;
 };
-// SDP_h / PDS_h: scores ready / probabilities written, per 64-query-column half h (each half is an independent pipeline)
-enum { KV_KV = 0, KV_QFULL0, KV_QFULL1, KV_QEMPTY0, KV_QEMPTY1, KV_SDP0, KV_SDP1, KV_PDS0, KV_PDS1, KV_DONE, KV_NBAR };
+enum { KV_KV = 0, KV_QFULL0, KV_QFULL1, KV_QEMPTY0, KV_QEMPTY1, KV_SDP, KV_PDS, KV_DONE, KV_NBAR };
 
 template <int D, bool CAUSAL>
-__global__ void __launch_bounds__(KV_THREADS, 1)
+__global__ void __launch_bounds__(BW_THREADS, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
                     const __grid_constant__ CUtensorMap tmK0, const __grid_constant__ CUtensorMap tmV0,
                     const __grid_constant__ CUtensorMap tmK1, const __grid_constant__ CUtensorMap tmV1,
@@ -355,10 +329,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     };
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < KV_NBAR; ++i) mbar_init(bars + i, (i == KV_PDS0 || i == KV_PDS1) ? 256 : 1);
+        for (int i = 0; i < KV_NBAR; ++i) mbar_init(bars + i, i == KV_PDS ? BW_COMPUTE_THREADS : 1);
         fence_barrier_init();
     }
-    if (warp == KV_WARP_MMA) {
+    if (warp == BW_WARP_MMA) {
         tmem_alloc(tmem_slot, TMEM_COLS);
         tmem_relinquish();
     }
@@ -377,7 +351,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t tmem_base = *tmem_slot;
     const int n_tiles = s_ntiles;
 
-    if (warp == KV_WARP_TMA) {
+    if (warp == BW_WARP_TMA) {
         if (elect_one() && n_tiles > 0) {
             const CUtensorMap* tK = variant ? &tmK1 : &tmK0;
             const CUtensorMap* tV = variant ? &tmV1 : &tmV0;
@@ -403,41 +377,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 }
             }
         }
-    } else if (warp == KV_WARP_MMA) {
+    } else if (warp == BW_WARP_MMA) {
         if (elect_one() && n_tiles > 0) {
+            constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
             constexpr uint32_t idesc_g = make_idesc_bf16(128, D, 0, 1);
             const uint32_t dK0 = desc_lo_kmajor(smem_u32(sK)), dV0 = desc_lo_kmajor(smem_u32(sV));
-            constexpr uint32_t idesc_h = make_idesc_bf16(128, 64, 0, 0);      // S^T / dP^T for one 64-query half
-            // Software pipeline over (q tile, half): the tensor pipe computes the scores of the next half while the compute
-            // warpgroup of the previous half turns its scores into P^T / dS^T, and the dV/dK MMAs of a half are issued as
-            // soon as that half's probabilities are back in TMEM.  Issue order per tile `it`:
-            //   S_A dP_A | [dV_B dK_B of tile it-1] | S_B dP_B | dV_A dK_A
-            auto issue_scores = [&](int half, uint32_t dQk, uint32_t ddOk) {
-                const uint32_t hoff = (uint32_t)(half * 64 * 128) >> 4;           // 64 query rows further down each 16 KB chunk
-#pragma unroll
-                for (int kk = 0; kk < D / 16; ++kk) {
-                    const uint32_t off = ((uint32_t)(kk / 4) * (128 * 128) + (uint32_t)(kk % 4) * 32) >> 4;
-                    umma_ss_lo(tmem_base + COL_S + half * 64, dK0 + off, dQk + off + hoff, idesc_h, kk ? 1u : 0u);
-                }
-#pragma unroll
-                for (int kk = 0; kk < D / 16; ++kk) {
-                    const uint32_t off = ((uint32_t)(kk / 4) * (128 * 128) + (uint32_t)(kk % 4) * 32) >> 4;
-                    umma_ss_lo(tmem_base + COL_DP + half * 64, dV0 + off, ddOk + off + hoff, idesc_h, kk ? 1u : 0u);
-                }
-                tc_commit(bars + KV_SDP0 + half);
-            };
-            auto issue_grads = [&](int half, uint32_t dQmn, uint32_t ddOmn, bool first) {
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk)      // 64 queries of this half = 4 K steps; P^T of quarter kk/2 at 64*half + 32*(kk/2) + 8*(kk%2)
-                    umma_ts_lo(tmem_base + COL_DV, tmem_base + COL_S + (uint32_t)half * 64 + (uint32_t)(kk / 2) * 32 + (uint32_t)(kk % 2) * 8,
-                               ddOmn + (uint32_t)(half * 4 + kk) * (2048 >> 4), idesc_g, (first && kk == 0) ? 0u : 1u);
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk)
-                    umma_ts_lo(tmem_base + COL_DK, tmem_base + COL_DP + (uint32_t)half * 64 + (uint32_t)(kk / 2) * 32 + (uint32_t)(kk % 2) * 8,
-                               dQmn + (uint32_t)(half * 4 + kk) * (2048 >> 4), idesc_g, (first && kk == 0) ? 0u : 1u);
-            };
             mbar_wait(bars + KV_KV, 0);
-            uint32_t pQmn = 0, pdOmn = 0;            // MN-major descriptors of the previous tile's stage
             for (int it = 0; it < n_tiles; ++it) {
                 const int st = it & 1;
                 const uint32_t phq = (uint32_t)(it >> 1) & 1u;
@@ -448,77 +393,80 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 const uint32_t dQmn = desc_lo_mnmajor(aQ, 128 * 128), ddOmn = desc_lo_mnmajor(adO, 128 * 128);
                 mbar_wait(bars + KV_QFULL0 + st, phq);
                 tc_fence_after_sync();
-                issue_scores(0, dQk, ddOk);
-                if (it > 0) {
-                    mbar_wait(bars + KV_PDS1, ph ^ 1u);                  // half B of the previous tile
-                    tc_fence_after_sync();
-                    issue_grads(1, pQmn, pdOmn, false);
-                    tc_commit(bars + KV_QEMPTY0 + (st ^ 1));             // previous tile's Q/dO stage is free
+#pragma unroll
+                for (int kk = 0; kk < D / 16; ++kk) {
+                    const uint32_t off = ((uint32_t)(kk / 4) * (128 * 128) + (uint32_t)(kk % 4) * 32) >> 4;
+                    umma_ss_lo(tmem_base + COL_S, dK0 + off, dQk + off, idesc_s, kk ? 1u : 0u);
                 }
-                issue_scores(1, dQk, ddOk);
-                mbar_wait(bars + KV_PDS0, ph);
+#pragma unroll
+                for (int kk = 0; kk < D / 16; ++kk) {
+                    const uint32_t off = ((uint32_t)(kk / 4) * (128 * 128) + (uint32_t)(kk % 4) * 32) >> 4;
+                    umma_ss_lo(tmem_base + COL_DP, dV0 + off, ddOk + off, idesc_s, kk ? 1u : 0u);
+                }
+                tc_commit(bars + KV_SDP);
+                mbar_wait(bars + KV_PDS, ph);
                 tc_fence_after_sync();
-                issue_grads(0, dQmn, ddOmn, it == 0);
-                pQmn = dQmn;
-                pdOmn = ddOmn;
-            }
-            {
-                const int last = n_tiles - 1;
-                mbar_wait(bars + KV_PDS1, (uint32_t)last & 1u);
-                tc_fence_after_sync();
-                issue_grads(1, pQmn, pdOmn, false);
-                tc_commit(bars + KV_QEMPTY0 + (last & 1));
+#pragma unroll
+                for (int kk = 0; kk < 128 / 16; ++kk)    // P^T of queries 16kk.. lives at column 64*(kk/4) + 8*(kk%4)
+                    umma_ts_lo(tmem_base + COL_DV, tmem_base + COL_S + (uint32_t)(kk / 4) * 64 + (uint32_t)(kk % 4) * 8,
+                               ddOmn + (uint32_t)kk * (2048 >> 4), idesc_g, (it | kk) ? 1u : 0u);
+#pragma unroll
+                for (int kk = 0; kk < 128 / 16; ++kk)
+                    umma_ts_lo(tmem_base + COL_DK, tmem_base + COL_DP + (uint32_t)(kk / 4) * 64 + (uint32_t)(kk % 4) * 8,
+                               dQmn + (uint32_t)kk * (2048 >> 4), idesc_g, (it | kk) ? 1u : 0u);
+                tc_commit(bars + KV_QEMPTY0 + st);
             }
             tc_commit(bars + KV_DONE);
         }
     } else {
-        // ---------------- compute warps: thread <-> kv row (TMEM lane).  Warpgroup g = warp/4 owns query columns [32g, 32g+32);
-        // the two warpgroups of a 64-column half share that half's pipeline (statistics buffer, named barrier, SDP/PDS).
-        const int wg = warp >> 2, half = wg >> 1, quarter = wg & 1;
+        // ---------------- compute warps: thread <-> kv row (TMEM lane); warpgroup `half` owns 64 of the 128 query columns
+        const int half = warp >> 2;
         const int r = (warp & 3) * 32 + (threadIdx.x & 31);
         const int kj = kv0 + r;
         const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        const uint32_t colS = COL_S + wg * 32, colDP = COL_DP + wg * 32;
+        const uint32_t colS = COL_S + half * 64, colDP = COL_DP + half * 64;
         const float sl2 = p.scale * LOG2E_F;
         const bool key_ok = kj < kve && kj >= kvs;
-        const int t256 = threadIdx.x & 255;      // thread within the half's 256-thread group
+        const int tid = threadIdx.x;             // 0..255
         for (int it = 0; it < n_tiles; ++it) {
+            const int st = it & 1;
             const uint32_t ph = (uint32_t)it & 1u;
             const int q0 = s_tiles[it] * 128;
-            const int qhalf = q0 + half * 64;
-            // per-column statistics of this half's 64 query columns: [parity][half][lse2 x 64 | (delta at +128) x 64]
-            float* sl = stats + (it & 1) * 384 + half * 64;
-            if (t256 < 128) {
-                const int col = t256 & 63;
-                const int qi = qhalf + col;
+            float* sl = stats + st * 384;        // [lse2 | delta | ok] x 128 query columns
+            {
+                const int col = tid & 127;
+                const int qi = q0 + col;
                 const bool ok = qi < T && (!p.qflag || (int)p.qflag[(int64_t)b * T + (qi < T ? qi : 0)] == variant);
                 const int64_t si = ((int64_t)b * p.heads + h) * T + (qi < T ? qi : 0);
-                if (t256 < 64) sl[col] = ok ? p.lse[si] * LOG2E_F : CUDART_INF_F;
-                else           sl[128 + col] = ok ? p.delta[si] : 0.f;
+                if (tid < 128) {
+                    sl[col] = ok ? p.lse[si] * LOG2E_F : CUDART_INF_F;
+                    sl[256 + col] = ok ? 1.f : 0.f;
+                } else {
+                    sl[128 + col] = ok ? p.delta[si] : 0.f;
+                }
             }
-            named_bar_sync(1 + half, 256);
-            mbar_wait(bars + KV_SDP0 + half, ph);
+            named_bar_sync(1, BW_COMPUTE_THREADS);
+            mbar_wait(bars + KV_SDP, ph);
             tc_fence_after_sync();
-            const int qbase = qhalf + quarter * 32;
+            const int qbase = q0 + half * 64;
             // warp-uniform: tile straddles the key range or the causal diagonal (excluded query rows carry lse = +inf)
             const bool need_mask = (kv0 + 128 > kve) || (kv0 < kvs) || (CAUSAL && kv0 + 127 > qbase);
-            if (need_mask) dkv_tile<true, CAUSAL>(lane_addr + colS, lane_addr + colDP, sl + quarter * 32, sl2, p.scale, kj, qbase, key_ok);
-            else           dkv_tile<false, CAUSAL>(lane_addr + colS, lane_addr + colDP, sl + quarter * 32, sl2, p.scale, kj, qbase, key_ok);
+            if (need_mask) dkv_tile<true, CAUSAL>(lane_addr + colS, lane_addr + colDP, sl + half * 64, sl2, p.scale, kj, qbase, key_ok);
+            else           dkv_tile<false, CAUSAL>(lane_addr + colS, lane_addr + colDP, sl + half * 64, sl2, p.scale, kj, qbase, key_ok);
             tc_wait_st();
             tc_fence_before_sync();
-            mbar_arrive(bars + KV_PDS0 + half);
+            mbar_arrive(bars + KV_PDS);
         }
         if (n_tiles > 0) {
             mbar_wait(bars + KV_DONE, 0);
             tc_fence_after_sync();
             const bool row_ok = kj < T;
             const int64_t off = ((int64_t)b * T + (row_ok ? kj : 0)) * ((int64_t)p.heads * D) + (int64_t)h * D;
-            // warpgroups 0,1 store the two halves of dV (TMEM columns [COL_DV, +D)), warpgroups 2,3 those of dK
-            constexpr int DH = D / 2;
-            __nv_bfloat16* dst_row = (wg < 2 ? (variant ? p.out3 : p.out1) : (variant ? p.out2 : p.out0)) + off + (wg & 1) * DH;
-            const uint32_t col0 = (wg < 2 ? COL_DV : COL_DK) + (wg & 1) * DH;
+            // warpgroup 0 stores dV (columns [COL_DV, +D)), warpgroup 1 stores dK (columns [COL_DK, +D))
+            __nv_bfloat16* dst_row = (half == 0 ? (variant ? p.out3 : p.out1) : (variant ? p.out2 : p.out0)) + off;
+            const uint32_t col0 = half == 0 ? COL_DV : COL_DK;
 #pragma unroll 1
-            for (int c = 0; c < DH / 32; ++c) {
+            for (int c = 0; c < D / 32; ++c) {
                 uint32_t v[32];
                 tmem_ld32(lane_addr + col0 + c * 32, v);
                 tc_wait_ld();
@@ -539,7 +487,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tc_fence_before_sync();
     }
     __syncthreads();
-    if (warp == KV_WARP_MMA) {
+    if (warp == BW_WARP_MMA) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
@@ -561,7 +509,7 @@ static int launch_dq(const CUtensorMap* tm, const AttnBwdParams& p, int n_work, 
         if (rc) return rc;
         configured = true;
     }
-    kern<<<dim3((unsigned)n_work, (unsigned)p.heads), DQ_THREADS, DqSmem<D>::TOTAL, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4],
+    kern<<<dim3((unsigned)n_work, (unsigned)p.heads), BW_THREADS, DqSmem<D>::TOTAL, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4],
                                                                                        tm[5], p);
     return check_launch("attn_bwd_dq");
 }
@@ -575,7 +523,7 @@ static int launch_dkv(const CUtensorMap* tm, const AttnBwdParams& p, int n_work,
         if (rc) return rc;
         configured = true;
     }
-    kern<<<dim3((unsigned)n_work, (unsigned)p.heads), KV_THREADS, DkvSmem<D>::TOTAL, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4],
+    kern<<<dim3((unsigned)n_work, (unsigned)p.heads), BW_THREADS, DkvSmem<D>::TOTAL, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4],
                                                                                         tm[5], p);
     return check_launch("attn_bwd_dkv");
 }
