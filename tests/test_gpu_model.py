@@ -145,3 +145,41 @@ def test_mislabelled_targets_give_inf_like_the_reference(golden):
     out = model(input_ids=inp["input_ids"], attention_mask=inp["attention_mask"], vision_indices=inp["vision_indices"],
                 contiguous_signal=inp["contiguous_signal"], labels=labels)
     assert torch.isinf(out.loss)
+
+
+def test_left_padding_with_position_ids_vs_oracle(golden):
+    """generation-style batch: sample 1 left padded, position_ids = cumsum(mask)-1 with pads at 1
+    (libra/models/libra/modeling_libra.py:1204-1205); compared on the valid positions."""
+    need_gpu()
+    from oracle.make_golden import make_libra_inputs
+    g = golden("decoder_tiny")
+    cfg = g["config"]
+    model = build(g).eval()
+    inp = make_libra_inputs(cfg["vocab_size"], cfg["contiguous_signal_size"], B=2, n_text=20, pad_last=0, seed=9)
+    am = inp["attention_mask"].clone()
+    ids, vi = inp["input_ids"].clone(), inp["vision_indices"].clone()
+    npad = 5
+    # shift sample 1 right by npad: pads (id 0, language) in front
+    ids[:, 1] = torch.cat([torch.zeros(2, npad, dtype=ids.dtype), ids[:, 1, :-npad]], dim=1)
+    vi[1] = torch.cat([torch.full((npad,), 578), vi[1, :-npad]])
+    sig = inp["contiguous_signal"].clone()
+    sig[1] = torch.cat([torch.zeros(npad, sig.shape[-1]), sig[1, :-npad]], dim=0)
+    am[1, :npad] = 0
+    # the shifted image lost its tail: keep flags consistent (truncated image tokens are still vision ids)
+    assert torch.equal(vi < 578, ids[0] >= cfg["vocab_size"])
+    pos = am.long().cumsum(-1) - 1
+    pos.masked_fill_(am == 0, 1)
+    with torch.no_grad():
+        out = model(input_ids=ids.to(dev), attention_mask=am.to(dev), vision_indices=vi.to(dev), position_ids=pos.to(dev),
+                    contiguous_signal=sig.to(dev))
+        sd32 = {k: v.to(dev) for k, v in g["state_dict"].items()}
+        o32 = O.libra_forward(sd32, O.LibraDims.from_config(cfg), ids.to(dev), vi.to(dev), attention_mask=am.to(dev),
+                              contiguous_signal=sig.to(dev), position_ids=pos.to(dev))
+        sd16 = {k: (v.bfloat16() if v.is_floating_point() else v) for k, v in sd32.items()}
+        o16 = O.libra_forward(sd16, O.LibraDims.from_config(cfg), ids.to(dev), vi.to(dev), attention_mask=am.to(dev),
+                              contiguous_signal=sig.to(dev).bfloat16(), position_ids=pos.to(dev))
+    m = am.to(dev).bool()[None, :, :, None]
+    fin = torch.isfinite(o32["logits"]) & m
+    e_ours = rel_err(out.logits.float()[fin], o32["logits"][fin])
+    e_orc = rel_err(o16["logits"].float()[fin], o32["logits"][fin])
+    assert e_ours <= 1.5 * e_orc + 5e-3, (e_ours, e_orc)
