@@ -153,6 +153,15 @@ int lb_attn_fwd(const void* Q, const void* K0, const void* V0, const void* K1, c
                 const int32_t* out_row, void* O, float* lse, int batch, int seqlen, int heads, int head_dim, int causal,
                 float scale, void* stream);
 
+/* Same operation and arguments as lb_attn_fwd with a PAIRED work list: work int32 [n_work,4] =
+ * {batch, q_tile of lane A, variant, q_tile of lane B or -1}.  One CTA per SM carries both q tiles through one shared
+ * K/V tile stream with a fixed A/B interleave of the tcgen05 issue order (see csrc/attn_fwd_pair.cu); every (sample,
+ * q tile, variant) that holds rows must appear in exactly one lane. */
+int lb_attn_fwd_pair(const void* Q, const void* K0, const void* V0, const void* K1, const void* V1, const uint8_t* qflag,
+                     const int32_t* work, int n_work, const int32_t* kv_start, const int32_t* kv_end,
+                     const int32_t* out_row, void* O, float* lse, int batch, int seqlen, int heads, int head_dim,
+                     int causal, float scale, void* stream);
+
 /* diagnostics: CTA (0,0) of subsequent lb_attn_fwd launches writes clock64 stamps into buf ([64][8] int64, device
  * memory; slots: MMA K-ready / QK-issued / P-seen / PV-issued, softmax S-seen / max-done / exchanged / P-arrived). NULL = off */
 int lb_attn_fwd_set_trace(void* buf);

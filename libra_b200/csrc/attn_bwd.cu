@@ -2,9 +2,8 @@
 //
 //   lb_attn_bwd_dq : CTA = (sample, 128-row q tile, variant, head); loops over 64-wide kv tiles:
 //                    S = Q.K^T, dP = dO.V^T (SS MMAs) -> dS = P*(dP-delta)*scale (threads) -> dQ += dS.K (TS MMA, K as MN-major B)
-//   lb_attn_bwd_dkv: CTA = (sample, 128-row kv tile, variant, head); loops over 128-row q tiles that contain rows of the
-//                    variant: S^T = K.Q^T, dP^T = V.dO^T -> P^T, dS^T (threads) -> dV += P^T.dO, dK += dS^T.Q (TS MMAs,
-//                    dO / Q as MN-major B).
+//                    (two CTAs per SM, 256 TMEM columns each)
+//   lb_attn_bwd_dkv: attn_bwd_dkv.cu
 // P is recomputed from the saved log-sum-exp; delta = rowsum(dO*O) comes from lb_attn_bwd_prepare.
 // Gradients w.r.t. the two operand variants (K0/V0 seen by qflag==0 rows, K1/V1 by qflag==1 rows) are written to
 // separate buffers; the prologue's adjoint (lb_attn_prep_bwd) folds them into dk, dv and the bridge gradients.
@@ -33,6 +32,7 @@ struct AttnBwdParams {
     __nv_bfloat16* out2;       //               | dK1
     __nv_bfloat16* out3;       //               | dV1
     int batch, seqlen, heads;
+    int n_work, head_group;
     float scale;
 };
 
@@ -60,34 +60,6 @@ __device__ __forceinline__ void dq_tile(uint32_t ts, uint32_t tdp, float sl2, fl
         s[j >> 1] = pack_bf16(d0, d1);
     }
     tmem_st16(ts, s);       // dS (bf16) over my own, already consumed S columns
-}
-
-// dK/dV kernel: thread = key row; 64 query columns at TMEM `ts` (S^T) / `tdp` (dP^T); per-column lse2 / delta in smem.
-template <bool MASK, bool CAUSAL>
-__device__ __forceinline__ void dkv_tile(uint32_t ts, uint32_t tdp, const float* __restrict__ st, float sl2, float scale, int kj,
-                                         int qbase, bool key_ok) {
-    uint32_t s[64], dp[64];
-    tmem_ld32(ts, s);
-    tmem_ld32(ts + 32, s + 32);
-    tmem_ld32(tdp, dp);
-    tmem_ld32(tdp + 32, dp + 32);
-    tc_wait_ld();
-#pragma unroll
-    for (int j = 0; j < 64; j += 2) {
-        float p0 = fast_ex2(fmaf(__uint_as_float(s[j]), sl2, -st[j]));          // lse = +inf on excluded query rows
-        float p1 = fast_ex2(fmaf(__uint_as_float(s[j + 1]), sl2, -st[j + 1]));
-        if (MASK) {
-            const int qa = qbase + j;
-            p0 = (key_ok && (!CAUSAL || kj <= qa)) ? p0 : 0.f;
-            p1 = (key_ok && (!CAUSAL || kj <= qa + 1)) ? p1 : 0.f;
-        }
-        const float d0 = p0 * (__uint_as_float(dp[j]) - st[128 + j]) * scale;
-        const float d1 = p1 * (__uint_as_float(dp[j + 1]) - st[128 + j + 1]) * scale;
-        s[j >> 1] = pack_bf16(p0, p1);
-        dp[j >> 1] = pack_bf16(d0, d1);
-    }
-    tmem_st32(ts, s);        // P^T (bf16, 32 columns) over my own, already consumed S^T columns
-    tmem_st32(tdp, dp);      // dS^T over dP^T
 }
 
 // =====================================================================================================
@@ -123,10 +95,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + DQ_NBAR);
 
     const int warp = threadIdx.x >> 5;
-    const int b = p.work[blockIdx.x * 4 + 0];
-    const int q_tile = p.work[blockIdx.x * 4 + 1];
-    const int variant = p.work[blockIdx.x * 4 + 2];
-    const int h = blockIdx.y;
+    int item, h;
+    attn_cta_order(p.n_work, p.heads, p.head_group, item, h);
+    const int b = p.work[item * 4 + 0];
+    const int q_tile = p.work[item * 4 + 1];
+    const int variant = p.work[item * 4 + 2];
     const int T = p.seqlen;
     const int q0 = q_tile * 128;
     const int kvs = p.kv_start ? p.kv_start[b] : 0;
@@ -275,224 +248,6 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
 }
 
-// =====================================================================================================
-// dK/dV kernel
-// =====================================================================================================
-template <int D>
-struct DkvSmem {
-    static constexpr int K_BYTES = 128 * D * 2;
-    static constexpr int V_BYTES = 128 * D * 2;
-    static constexpr int Q_BYTES = 128 * D * 2;      // per stage
-    static constexpr int DO_BYTES = 128 * D * 2;     // per stage
-    static constexpr int STAGES = 2;
-    static constexpr int STAT_OFF = K_BYTES + V_BYTES + STAGES * (Q_BYTES + DO_BYTES);
-    static constexpr int STAT_BYTES = 2 * 128 * 12;  // [stage][lse2, delta, ok] x 128
-    static constexpr int BAR_OFF = STAT_OFF + STAT_BYTES;
-    static constexpr int TOTAL = BAR_OFF + 1024 + 256;
-};
-enum { KV_KV = 0, KV_QFULL0, KV_QFULL1, KV_QEMPTY0, KV_QEMPTY1, KV_SDP, KV_PDS, KV_DONE, KV_NBAR };
-
-template <int D, bool CAUSAL>
-__global__ void __launch_bounds__(BW_THREADS, 1)
-attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmdO,
-                    const __grid_constant__ CUtensorMap tmK0, const __grid_constant__ CUtensorMap tmV0,
-                    const __grid_constant__ CUtensorMap tmK1, const __grid_constant__ CUtensorMap tmV1,
-                    const AttnBwdParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    using S = DkvSmem<D>;
-    uint8_t* sK = smem;
-    uint8_t* sV = sK + S::K_BYTES;
-    uint8_t* sQ0 = sV + S::V_BYTES;                       // stage s: sQ0 + s*(Q+dO), dO right after Q
-    float* stats = reinterpret_cast<float*>(smem + S::STAT_OFF);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + KV_NBAR);
-
-    const int warp = threadIdx.x >> 5;
-    const int b = p.work[blockIdx.x * 4 + 0];
-    const int kv_tile = p.work[blockIdx.x * 4 + 1];
-    const int variant = p.work[blockIdx.x * 4 + 2];
-    const int first_q = p.work[blockIdx.x * 4 + 3];
-    const int h = blockIdx.y;
-    const int T = p.seqlen;
-    const int kv0 = kv_tile * 128;
-    const int kvs = p.kv_start ? p.kv_start[b] : 0;
-    const int kve = p.kv_end ? p.kv_end[b] : T;
-    const int nqt = (T + 127) / 128;
-
-    constexpr uint32_t TMEM_COLS = 512, COL_S = 0, COL_DP = 128, COL_DV = 256, COL_DK = 256 + D;
-
-    // q tiles that hold rows of this variant (host-computed bitmap; without it every tile is visited and the
-    // per-row flags alone do the masking)
-    auto tile_has = [&](int qt) -> bool {
-        return p.qtile_has ? p.qtile_has[((int64_t)b * 2 + variant) * nqt + qt] != 0 : true;
-    };
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < KV_NBAR; ++i) mbar_init(bars + i, i == KV_PDS ? BW_COMPUTE_THREADS : 1);
-        fence_barrier_init();
-    }
-    if (warp == BW_WARP_MMA) {
-        tmem_alloc(tmem_slot, TMEM_COLS);
-        tmem_relinquish();
-    }
-    // tile list in shared memory (<= 64 q tiles, T <= 8192)
-    __shared__ int s_tiles[64];
-    __shared__ int s_ntiles;
-    if (threadIdx.x == 32) {
-        int n = 0;
-        for (int qt = first_q; qt < nqt && n < 64; ++qt)
-            if (tile_has(qt)) s_tiles[n++] = qt;
-        s_ntiles = n;
-    }
-    tc_fence_before_sync();
-    __syncthreads();
-    tc_fence_after_sync();
-    const uint32_t tmem_base = *tmem_slot;
-    const int n_tiles = s_ntiles;
-
-    if (warp == BW_WARP_TMA) {
-        if (elect_one() && n_tiles > 0) {
-            const CUtensorMap* tK = variant ? &tmK1 : &tmK0;
-            const CUtensorMap* tV = variant ? &tmV1 : &tmV0;
-            const int row_k = b * T + kv0;
-            mbar_arrive_expect_tx(bars + KV_KV, S::K_BYTES + S::V_BYTES);
-#pragma unroll
-            for (int c = 0; c < D / 64; ++c) {
-                tma_load_2d(sK + c * (128 * 128), tK, bars + KV_KV, h * D + c * 64, row_k);
-                tma_load_2d(sV + c * (128 * 128), tV, bars + KV_KV, h * D + c * 64, row_k);
-            }
-            for (int it = 0; it < n_tiles; ++it) {
-                const int st = it & 1;
-                const uint32_t ph = (uint32_t)(it >> 1) & 1u;
-                const int row_q = b * T + s_tiles[it] * 128;
-                uint8_t* q = sQ0 + st * (S::Q_BYTES + S::DO_BYTES);
-                uint8_t* d = q + S::Q_BYTES;
-                mbar_wait(bars + KV_QEMPTY0 + st, ph ^ 1u);
-                mbar_arrive_expect_tx(bars + KV_QFULL0 + st, S::Q_BYTES + S::DO_BYTES);
-#pragma unroll
-                for (int c = 0; c < D / 64; ++c) {
-                    tma_load_2d(q + c * (128 * 128), &tmQ, bars + KV_QFULL0 + st, h * D + c * 64, row_q);
-                    tma_load_2d(d + c * (128 * 128), &tmdO, bars + KV_QFULL0 + st, h * D + c * 64, row_q);
-                }
-            }
-        }
-    } else if (warp == BW_WARP_MMA) {
-        if (elect_one() && n_tiles > 0) {
-            constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
-            constexpr uint32_t idesc_g = make_idesc_bf16(128, D, 0, 1);
-            const uint32_t dK0 = desc_lo_kmajor(smem_u32(sK)), dV0 = desc_lo_kmajor(smem_u32(sV));
-            mbar_wait(bars + KV_KV, 0);
-            for (int it = 0; it < n_tiles; ++it) {
-                const int st = it & 1;
-                const uint32_t phq = (uint32_t)(it >> 1) & 1u;
-                const uint32_t ph = (uint32_t)it & 1u;
-                const uint32_t aQ = smem_u32(sQ0 + st * (S::Q_BYTES + S::DO_BYTES));
-                const uint32_t adO = aQ + S::Q_BYTES;
-                const uint32_t dQk = desc_lo_kmajor(aQ), ddOk = desc_lo_kmajor(adO);
-                const uint32_t dQmn = desc_lo_mnmajor(aQ, 128 * 128), ddOmn = desc_lo_mnmajor(adO, 128 * 128);
-                mbar_wait(bars + KV_QFULL0 + st, phq);
-                tc_fence_after_sync();
-#pragma unroll
-                for (int kk = 0; kk < D / 16; ++kk) {
-                    const uint32_t off = ((uint32_t)(kk / 4) * (128 * 128) + (uint32_t)(kk % 4) * 32) >> 4;
-                    umma_ss_lo(tmem_base + COL_S, dK0 + off, dQk + off, idesc_s, kk ? 1u : 0u);
-                }
-#pragma unroll
-                for (int kk = 0; kk < D / 16; ++kk) {
-                    const uint32_t off = ((uint32_t)(kk / 4) * (128 * 128) + (uint32_t)(kk % 4) * 32) >> 4;
-                    umma_ss_lo(tmem_base + COL_DP, dV0 + off, ddOk + off, idesc_s, kk ? 1u : 0u);
-                }
-                tc_commit(bars + KV_SDP);
-                mbar_wait(bars + KV_PDS, ph);
-                tc_fence_after_sync();
-#pragma unroll
-                for (int kk = 0; kk < 128 / 16; ++kk)    // P^T of queries 16kk.. lives at column 64*(kk/4) + 8*(kk%4)
-                    umma_ts_lo(tmem_base + COL_DV, tmem_base + COL_S + (uint32_t)(kk / 4) * 64 + (uint32_t)(kk % 4) * 8,
-                               ddOmn + (uint32_t)kk * (2048 >> 4), idesc_g, (it | kk) ? 1u : 0u);
-#pragma unroll
-                for (int kk = 0; kk < 128 / 16; ++kk)
-                    umma_ts_lo(tmem_base + COL_DK, tmem_base + COL_DP + (uint32_t)(kk / 4) * 64 + (uint32_t)(kk % 4) * 8,
-                               dQmn + (uint32_t)kk * (2048 >> 4), idesc_g, (it | kk) ? 1u : 0u);
-                tc_commit(bars + KV_QEMPTY0 + st);
-            }
-            tc_commit(bars + KV_DONE);
-        }
-    } else {
-        // ---------------- compute warps: thread <-> kv row (TMEM lane); warpgroup `half` owns 64 of the 128 query columns
-        const int half = warp >> 2;
-        const int r = (warp & 3) * 32 + (threadIdx.x & 31);
-        const int kj = kv0 + r;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        const uint32_t colS = COL_S + half * 64, colDP = COL_DP + half * 64;
-        const float sl2 = p.scale * LOG2E_F;
-        const bool key_ok = kj < kve && kj >= kvs;
-        const int tid = threadIdx.x;             // 0..255
-        for (int it = 0; it < n_tiles; ++it) {
-            const int st = it & 1;
-            const uint32_t ph = (uint32_t)it & 1u;
-            const int q0 = s_tiles[it] * 128;
-            float* sl = stats + st * 384;        // [lse2 | delta | ok] x 128 query columns
-            {
-                const int col = tid & 127;
-                const int qi = q0 + col;
-                const bool ok = qi < T && (!p.qflag || (int)p.qflag[(int64_t)b * T + (qi < T ? qi : 0)] == variant);
-                const int64_t si = ((int64_t)b * p.heads + h) * T + (qi < T ? qi : 0);
-                if (tid < 128) {
-                    sl[col] = ok ? p.lse[si] * LOG2E_F : CUDART_INF_F;
-                    sl[256 + col] = ok ? 1.f : 0.f;
-                } else {
-                    sl[128 + col] = ok ? p.delta[si] : 0.f;
-                }
-            }
-            named_bar_sync(1, BW_COMPUTE_THREADS);
-            mbar_wait(bars + KV_SDP, ph);
-            tc_fence_after_sync();
-            const int qbase = q0 + half * 64;
-            // warp-uniform: tile straddles the key range or the causal diagonal (excluded query rows carry lse = +inf)
-            const bool need_mask = (kv0 + 128 > kve) || (kv0 < kvs) || (CAUSAL && kv0 + 127 > qbase);
-            if (need_mask) dkv_tile<true, CAUSAL>(lane_addr + colS, lane_addr + colDP, sl + half * 64, sl2, p.scale, kj, qbase, key_ok);
-            else           dkv_tile<false, CAUSAL>(lane_addr + colS, lane_addr + colDP, sl + half * 64, sl2, p.scale, kj, qbase, key_ok);
-            tc_wait_st();
-            tc_fence_before_sync();
-            mbar_arrive(bars + KV_PDS);
-        }
-        if (n_tiles > 0) {
-            mbar_wait(bars + KV_DONE, 0);
-            tc_fence_after_sync();
-            const bool row_ok = kj < T;
-            const int64_t off = ((int64_t)b * T + (row_ok ? kj : 0)) * ((int64_t)p.heads * D) + (int64_t)h * D;
-            // warpgroup 0 stores dV (columns [COL_DV, +D)), warpgroup 1 stores dK (columns [COL_DK, +D))
-            __nv_bfloat16* dst_row = (half == 0 ? (variant ? p.out3 : p.out1) : (variant ? p.out2 : p.out0)) + off;
-            const uint32_t col0 = half == 0 ? COL_DV : COL_DK;
-#pragma unroll 1
-            for (int c = 0; c < D / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld32(lane_addr + col0 + c * 32, v);
-                tc_wait_ld();
-                if (row_ok) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        uint4 o;
-                        o.x = pack_bf16(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
-                        o.y = pack_bf16(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                        o.z = pack_bf16(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
-                        o.w = pack_bf16(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
-                        *reinterpret_cast<uint4*>(dst_row + c * 32 + j) = o;
-                    }
-                }
-                __syncwarp();
-            }
-        }
-        tc_fence_before_sync();
-    }
-    __syncthreads();
-    if (warp == BW_WARP_MMA) {
-        tc_fence_after_sync();
-        tmem_dealloc(tmem_base, TMEM_COLS);
-    }
-}
-
 template <typename KernT>
 static int configure(KernT kern, int smem, const char* what) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -509,23 +264,9 @@ static int launch_dq(const CUtensorMap* tm, const AttnBwdParams& p, int n_work, 
         if (rc) return rc;
         configured = true;
     }
-    kern<<<dim3((unsigned)n_work, (unsigned)p.heads), BW_THREADS, DqSmem<D>::TOTAL, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4],
+    kern<<<(unsigned)(n_work * p.heads), BW_THREADS, DqSmem<D>::TOTAL, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4],
                                                                                        tm[5], p);
     return check_launch("attn_bwd_dq");
-}
-
-template <int D, bool CAUSAL>
-static int launch_dkv(const CUtensorMap* tm, const AttnBwdParams& p, int n_work, cudaStream_t st) {
-    auto kern = attn_bwd_dkv_kernel<D, CAUSAL>;
-    static bool configured = false;
-    if (!configured) {
-        int rc = configure(kern, DkvSmem<D>::TOTAL, "attn_bwd_dkv");
-        if (rc) return rc;
-        configured = true;
-    }
-    kern<<<dim3((unsigned)n_work, (unsigned)p.heads), BW_THREADS, DkvSmem<D>::TOTAL, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4],
-                                                                                        tm[5], p);
-    return check_launch("attn_bwd_dkv");
 }
 
 static int make_maps(CUtensorMap* tm, const void* Q, const void* dO, const void* K0, const void* V0, const void* K1,
@@ -561,34 +302,11 @@ int lb_attn_bwd_dq(const void* Q, const void* K0, const void* V0, const void* K1
     AttnBwdParams p{};
     p.qflag = qflag; p.work = work; p.kv_start = kv_start; p.kv_end = kv_end; p.lse = lse; p.delta = delta;
     p.out0 = (__nv_bfloat16*)dQ; p.batch = batch; p.seqlen = seqlen; p.heads = heads; p.scale = scale;
+    p.n_work = n_work; p.head_group = attn_head_group();
     cudaStream_t st = (cudaStream_t)stream;
     if (head_dim == 128) return causal ? launch_dq<128, true>(tm, p, n_work, st) : launch_dq<128, false>(tm, p, n_work, st);
     return causal ? launch_dq<64, true>(tm, p, n_work, st) : launch_dq<64, false>(tm, p, n_work, st);
 }
 
-int lb_attn_bwd_dkv(const void* Q, const void* K0, const void* V0, const void* K1, const void* V1, const void* dO,
-                    const float* lse, const float* delta, const uint8_t* qflag, const uint8_t* qtile_has,
-                    const int32_t* work_kv, int n_work, const int32_t* kv_start, const int32_t* kv_end, void* dK0,
-                    void* dV0, void* dK1, void* dV1, int batch, int seqlen, int heads, int head_dim, int causal,
-                    float scale, void* stream) {
-    LB_REQUIRE(batch > 0 && seqlen > 0 && heads > 0 && n_work >= 0, LB_EINVAL, "attn_bwd_dkv: bad shape");
-    LB_REQUIRE(head_dim == 64 || head_dim == 128, LB_EINVAL, "attn_bwd_dkv: head_dim %d (64 or 128 supported)", head_dim);
-    LB_REQUIRE(seqlen <= 8192, LB_EINVAL, "attn_bwd_dkv: seqlen %d > 8192", seqlen);
-    LB_REQUIRE(Q && K0 && V0 && dO && lse && delta && work_kv && dK0 && dV0, LB_EINVAL, "attn_bwd_dkv: null argument");
-    if (n_work == 0) return LB_OK;
-    int rc = require_sm100();
-    if (rc) return rc;
-    CUtensorMap tm[6];
-    rc = make_maps(tm, Q, dO, K0, V0, K1, V1, batch, seqlen, heads, head_dim, 128, 128);
-    if (rc) return rc;
-    AttnBwdParams p{};
-    p.qflag = qflag; p.qtile_has = qtile_has; p.work = work_kv; p.kv_start = kv_start; p.kv_end = kv_end; p.lse = lse; p.delta = delta;
-    p.out0 = (__nv_bfloat16*)dK0; p.out1 = (__nv_bfloat16*)dV0;
-    p.out2 = (__nv_bfloat16*)(dK1 ? dK1 : dK0); p.out3 = (__nv_bfloat16*)(dV1 ? dV1 : dV0);
-    p.batch = batch; p.seqlen = seqlen; p.heads = heads; p.scale = scale;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (head_dim == 128) return causal ? launch_dkv<128, true>(tm, p, n_work, st) : launch_dkv<128, false>(tm, p, n_work, st);
-    return causal ? launch_dkv<64, true>(tm, p, n_work, st) : launch_dkv<64, false>(tm, p, n_work, st);
-}
 
 }

@@ -35,13 +35,14 @@ struct AttnFwdParams {
     __nv_bfloat16* O;
     float* lse;                  // [B,H,T]
     int batch, seqlen, heads;
+    int n_work, head_group;
     float scale;
     long long* trace;            // optional [64][8] clock64 stamps of CTA (0,0) (diagnostics, LB_ATTN_TRACE env)
 };
 
 #define LB_TRACE(slot, it)                                                                        \
     do {                                                                                          \
-        if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && (it) < 64) p.trace[(it) * 8 + (slot)] = clock64(); \
+        if (p.trace && blockIdx.x == 0 && (it) < 64) p.trace[(it) * 8 + (slot)] = clock64(); \
     } while (0)
 
 template <int D>
@@ -120,10 +121,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
 
     const int warp = threadIdx.x >> 5;
-    const int b = p.work[blockIdx.x * 4 + 0];
-    const int q_tile = p.work[blockIdx.x * 4 + 1];
-    const int variant = p.work[blockIdx.x * 4 + 2];
-    const int h = blockIdx.y;
+    int item, h;
+    attn_cta_order(p.n_work, p.heads, p.head_group, item, h);
+    const int b = p.work[item * 4 + 0];
+    const int q_tile = p.work[item * 4 + 1];
+    const int variant = p.work[item * 4 + 2];
     const int T = p.seqlen;
     const int q0 = q_tile * AT_BM;
     const int kvs = p.kv_start ? p.kv_start[b] : 0;
@@ -335,8 +337,7 @@ static int launch_attn_fwd_p(const CUtensorMap* tm, const AttnFwdParams& p, int 
         if (e != cudaSuccess) return fail(LB_ELAUNCH, "attn_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         configured = true;
     }
-    dim3 grid((unsigned)n_work, (unsigned)p.heads);
-    kern<<<grid, AT_THREADS, S::TOTAL, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], p);
+    kern<<<(unsigned)(n_work * p.heads), AT_THREADS, S::TOTAL, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], p);
     return check_launch("attn_fwd");
 }
 
@@ -475,6 +476,7 @@ int lb_attn_fwd(const void* Q, const void* K0, const void* V0, const void* K1, c
     AttnFwdParams p;
     p.qflag = qflag; p.work = work; p.kv_start = kv_start; p.kv_end = kv_end; p.out_row = out_row;
     p.O = (__nv_bfloat16*)O; p.lse = lse; p.batch = batch; p.seqlen = seqlen; p.heads = heads; p.scale = scale;
+    p.n_work = n_work; p.head_group = attn_head_group();
     p.trace = g_attn_trace;
     cudaStream_t st = (cudaStream_t)stream;
     if (head_dim == 128) return causal ? launch_attn_fwd<128, true>(tm, p, n_work, st) : launch_attn_fwd<128, false>(tm, p, n_work, st);

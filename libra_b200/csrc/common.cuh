@@ -23,6 +23,7 @@ namespace lb {
 void set_error(const char* fmt, ...);
 int fail(int code, const char* fmt, ...);
 int check_launch(const char* what);
+int attn_head_group();   // heads per CTA-order group of the attention kernels (LB_ATTN_HEAD_GROUP, default 8)
 
 #define LB_REQUIRE(cond, code, ...)                    \
     do {                                               \
@@ -134,11 +135,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
         if (++spins > LB_MBAR_SPIN_LIMIT) {
-            printf("libra_b200: mbarrier timeout block=(%d,%d,%d) thread=%d parity=%u\n", blockIdx.x, blockIdx.y,
-                   blockIdx.z, threadIdx.x, parity);
+            printf("libra_b200: mbarrier timeout block=%d thread=%d parity=%u\n", blockIdx.x, threadIdx.x, parity);
             __trap();
         }
     }
+}
+
+// Attention CTA order.  The grid is 1-D over (work item, head); work items are sorted heaviest first.  Heads run in
+// groups of `group`: inside a group all heads of the heaviest item come first, so (a) the CTAs resident at one time
+// touch the K/V of `group` heads only (L2-resident working set) and (b) the grid ends with the lightest items of the
+// last group -- with a plain (item, head) grid the heaviest items of the last head START in the last wave.
+__device__ __forceinline__ void attn_cta_order(int n_work, int heads, int group, int& item, int& head) {
+    const int L = (int)blockIdx.x;
+    const int per_group = group * n_work;
+    const int g = L / per_group;
+    const int rem = L - g * per_group;
+    const int gl = min(group, heads - g * group);
+    item = rem / gl;
+    head = g * group + (rem - item * gl);
 }
 
 // ----------------------------------------------------------------------------

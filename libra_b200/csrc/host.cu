@@ -1,5 +1,6 @@
 // Host-side plumbing of the C ABI: thread-local error text, device checks and
 // TMA tensor-map encoding through the driver entry point.
+#include <stdlib.h>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -24,6 +25,16 @@ int fail(int code, const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
     return code;
+}
+
+int attn_head_group() {
+    static int g = -1;
+    if (g < 0) {
+        const char* e = getenv("LB_ATTN_HEAD_GROUP");
+        g = e ? atoi(e) : 8;
+        if (g < 1) g = 1;
+    }
+    return g;
 }
 
 int check_launch(const char* what) {

@@ -8,6 +8,7 @@ this library's own sm_100a code.  There is no non-CUDA fallback anywhere in this
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -15,6 +16,9 @@ import torch
 
 from . import ops
 from .schedule import AttnWork, Routing
+
+# attention forward kernel: the paired-tile one-CTA-per-SM kernel (csrc/attn_fwd_pair.cu) or the single-tile kernel
+FWD_PAIRED = os.environ.get("LB_ATTN_FWD_PAIR", "0") == "1"
 
 BF16 = torch.bfloat16
 
@@ -490,8 +494,9 @@ class BridgeAttention(torch.autograd.Function):
         scale = 1.0 / math.sqrt(meta.head_dim)
         o = torch.empty_like(q)
         # variant 0 = language queries (see Kfl/Vfl), variant 1 = vision queries (see Kfv/Vfv); rows land in sorted order
-        o, lse = ops.attn_fwd(Q, Kfl, Vfl, Kfv, Vfv, rt.flag_orig, w.work_q, w.kv_start, w.kv_end, rt.inv, meta.batch,
-                              meta.seqlen, meta.heads, meta.head_dim, True, scale, out=o)
+        o, lse = ops.attn_fwd(Q, Kfl, Vfl, Kfv, Vfv, rt.flag_orig, w.work_q2 if FWD_PAIRED else w.work_q, w.kv_start, w.kv_end,
+                              rt.inv, meta.batch, meta.seqlen, meta.heads, meta.head_dim, True, scale, out=o,
+                              paired=FWD_PAIRED)
         ctx.meta = meta
         ctx.scale = scale
         ctx.save_for_backward(Q, Kfv, Kfl, Vfv, Vfl, o, lse, tk, tv, Bk_l, Bk_v, Bv_l, Bv_v)
@@ -536,8 +541,8 @@ class PlainAttention(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, q, k, v, work: AttnWork, batch, seqlen, heads, head_dim, scale):
-        o, lse = ops.attn_fwd(q, k, v, None, None, None, work.work_q, None, None, None, batch, seqlen, heads, head_dim, False,
-                              scale)
+        o, lse = ops.attn_fwd(q, k, v, None, None, None, work.work_q2 if FWD_PAIRED else work.work_q, None, None, None, batch,
+                              seqlen, heads, head_dim, False, scale, paired=FWD_PAIRED)
         ctx.args = (work, batch, seqlen, heads, head_dim, scale)
         ctx.save_for_backward(q, k, v, o, lse)
         return o

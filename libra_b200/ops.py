@@ -30,7 +30,7 @@ def _st():
 TIMED = None
 
 
-def enable_timing(names=("lb_attn_fwd", "lb_attn_bwd_dq", "lb_attn_bwd_dkv")):
+def enable_timing(names=("lb_attn_fwd", "lb_attn_fwd_pair", "lb_attn_bwd_dq", "lb_attn_bwd_dkv")):
     global TIMED
     TIMED = {n: [] for n in names}
 
@@ -259,12 +259,13 @@ def attn_prep_bwd(dQ, dKfv, dKfl, dVfv, dVfl, flag_sorted, sorted_of, pos, cos_t
 
 
 def attn_fwd(Q, K0, V0, K1, V1, qflag, work, kv_start, kv_end, out_row, batch, seqlen, heads, head_dim, causal, scale,
-             out=None):
+             out=None, paired=False):
+    """paired=True: `work` is the paired-tile list (AttnWork.work_q2) and the one-CTA-per-SM kernel runs."""
     C = heads * head_dim
     if out is None:
         out = torch.zeros(batch * seqlen, C, dtype=BF16, device=Q.device)
     lse = torch.full((batch, heads, seqlen), float("inf"), dtype=torch.float32, device=Q.device)
-    _timed_call("lb_attn_fwd", _p(Q), _p(K0), _p(V0), _p(K1), _p(V1), _p(qflag), _p(work), work.shape[0], _p(kv_start),
+    _timed_call("lb_attn_fwd_pair" if paired else "lb_attn_fwd", _p(Q), _p(K0), _p(V0), _p(K1), _p(V1), _p(qflag), _p(work), work.shape[0], _p(kv_start),
               _p(kv_end), _p(out_row), _p(out), _p(lse), batch, seqlen, heads, head_dim, int(causal), float(scale), _st())
     return out, lse
 

@@ -56,6 +56,17 @@ def oracle_out(c, causal=True, grads=None):
     return o
 
 
+PAIRED = False        # which forward kernel run_fwd launches; the `fwd_kernel` fixture runs a test once with each
+
+
+@pytest.fixture(params=[False, True], ids=["single", "paired"])
+def fwd_kernel(request):
+    global PAIRED
+    PAIRED = request.param
+    yield request.param
+    PAIRED = False
+
+
 def run_fwd(c, causal=True, out_row=None):
     from libra_b200 import ops, schedule
     B, T, H, D = c["B"], c["T"], c["H"], c["D"]
@@ -64,8 +75,9 @@ def run_fwd(c, causal=True, out_row=None):
     flat = lambda t: t.reshape(B * T, H * D)
     qflag = c["flag"].reshape(-1).to(torch.uint8) if causal else None
     o, lse = ops.attn_fwd(flat(c["q"]), flat(c["Kfl"]) if causal else flat(c["k"]), flat(c["Vfl"]) if causal else flat(c["v"]),
-                          flat(c["Kfv"]) if causal else None, flat(c["Vfv"]) if causal else None, qflag, w.work_q,
-                          w.kv_start, w.kv_end, out_row, B, T, H, D, causal, 1.0 / math.sqrt(D))
+                          flat(c["Kfv"]) if causal else None, flat(c["Vfv"]) if causal else None, qflag,
+                          w.work_q2 if PAIRED else w.work_q, w.kv_start, w.kv_end, out_row, B, T, H, D, causal,
+                          1.0 / math.sqrt(D), paired=PAIRED)
     torch.cuda.synchronize()
     return o.view(B, T, H * D), lse, w
 
@@ -80,7 +92,7 @@ CASES = [
 
 
 @pytest.mark.parametrize("case", CASES, ids=lambda c: f"B{c['B']}T{c['T']}H{c['H']}")
-def test_bridge_attention_forward(case):
+def test_bridge_attention_forward(case, fwd_kernel):
     need_gpu()
     c = make_case(case["B"], case["T"], case["H"], case["D"], 17, case["spans"], case["pad"])
     o, lse, _ = run_fwd(c)
@@ -91,7 +103,7 @@ def test_bridge_attention_forward(case):
     assert torch.isfinite(o.float()).all()
 
 
-def test_bridge_attention_matches_reference_golden(golden):
+def test_bridge_attention_matches_reference_golden(golden, fwd_kernel):
     """The reference LibraAttention output (tests/golden/attention_hd128.pt), core kernel in the loop:
     projections/bridge/rope by the oracle in fp32, attention core by the CUDA kernel."""
     need_gpu()
@@ -128,7 +140,7 @@ def test_bridge_attention_matches_reference_golden(golden):
         assert rel_err(y[b, :e], want[b, :e]) < 2e-2, rel_err(y[b, :e], want[b, :e])
 
 
-def test_out_row_scatter_and_lse():
+def test_out_row_scatter_and_lse(fwd_kernel):
     need_gpu()
     c = make_case(2, 300, 2, 128, 5, [(0, 1, 200), (1, 100, 290)])
     N = 600
@@ -146,7 +158,7 @@ def test_out_row_scatter_and_lse():
 
 
 @pytest.mark.parametrize("B,T,H", [(2, 577, 4), (1, 128, 2), (3, 200, 1)])
-def test_vit_attention_forward(B, T, H):
+def test_vit_attention_forward(B, T, H, fwd_kernel):
     need_gpu()
     c = make_case(B, T, H, 64, 23, [], bridge=False)
     o, _, _ = run_fwd(c, causal=False)
@@ -212,7 +224,7 @@ def test_vit_attention_backward(B, T, H):
     assert_close(dV0.view(B, T, -1), gv, rtol=3e-2, atol=3e-2, msg="dV")
 
 
-def test_full_size_properties_T4096():
+def test_full_size_properties_T4096(fwd_kernel):
     """Size-independent properties at BASELINE.json's largest sequence (T=4096, 4 images back to back), where the O(T^2)
     oracle is too slow to be the checker: softmax rows sum to one, linearity in V, causality, bridge-free equivalence."""
     need_gpu()
