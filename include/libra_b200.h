@@ -162,6 +162,32 @@ int lb_attn_fwd_pair(const void* Q, const void* K0, const void* V0, const void* 
                      const int32_t* out_row, void* O, float* lse, int batch, int seqlen, int heads, int head_dim,
                      int causal, float scale, void* stream);
 
+/* Same operation and work list as lb_attn_fwd, persistent streaming kernel (csrc/attn_fwd_stream.cu): one CTA per SM
+ * walks its share of the (work item, head) list; scores are triple-buffered in TMEM, two softmax warpgroups take
+ * alternate kv tiles.  List position L of (work item w, head h): heads run in groups of head_group, inside group g
+ * (gl = heads in the group) L = g*head_group*n_work + w*gl + (h - g*head_group).
+ * plan_items [n_work*heads] / plan_off [n_cta+1] (int32, device): the list positions each of the n_cta CTAs handles, in
+ * order (host-side balanced split, libra_b200/schedule.py: stream_plan).  Both NULL: a static snake split over one CTA
+ * per SM.  head_group <= 0: library default (LB_ATTN_HEAD_GROUP, 8). */
+int lb_attn_fwd_stream(const void* Q, const void* K0, const void* V0, const void* K1, const void* V1, const uint8_t* qflag,
+                       const int32_t* work, int n_work, const int32_t* plan_items, const int32_t* plan_off, int n_cta,
+                       int head_group, const int32_t* kv_start, const int32_t* kv_end, const int32_t* out_row, void* O,
+                       float* lse, int batch, int seqlen, int heads, int head_dim, int causal, float scale, void* stream);
+/* diagnostics: every CTA logs {smid, items, tiles, clock64 at entry, first Q landed, exit, -, -} into buf
+ * ([number of SMs][8] int64, device memory).  NULL = off */
+int lb_attn_fwd_stream_set_cta_log(void* buf);
+/* diagnostics: CTA 0 writes clock64 stamps into buf ([64][8] int64, device; one row per kv tile: MMA wait-P / P seen /
+ * issued, softmax wait-S / S seen / max done / max published / P arrived).  NULL = off */
+int lb_attn_fwd_stream_set_trace(void* buf);
+
+/* diagnostics: CTA 0 of subsequent lb_attn_fwd_pair launches writes clock64 stamps into buf ([64][16] int64, device
+ * memory; per kv tile: slots 0-3 MMA thread (P_A seen, A issued, P_B seen, B issued), 4-6 lane A softmax (S seen,
+ * max done, P arrived), 7-9 lane B softmax).  NULL = off */
+int lb_attn_fwd_pair_set_trace(void* buf);
+/* diagnostics: every CTA logs {smid, steps A, steps B, clock64 at entry, Q landed, last MMA issued, exit, -} into buf
+ * ([n_work*heads][8] int64, device memory).  NULL = off */
+int lb_attn_fwd_pair_set_cta_log(void* buf);
+
 /* diagnostics: CTA (0,0) of subsequent lb_attn_fwd launches writes clock64 stamps into buf ([64][8] int64, device
  * memory; slots: MMA K-ready / QK-issued / P-seen / PV-issued, softmax S-seen / max-done / exchanged / P-arrived). NULL = off */
 int lb_attn_fwd_set_trace(void* buf);

@@ -1,20 +1,23 @@
 // Bridge attention forward, paired-tile kernel (A10; same maths and operand formulation as attn_fwd.cu).
 //
 // One CTA per SM works on TWO 128-row query tiles ("lanes") of the same (sample, head, variant) at once and streams the
-// K/V tiles they share through a 2-stage TMA ring.  The point is the schedule of the single tcgen05 issuer:
+// 64-key K/V tiles they share through TMA rings.  Per lane the score tile is DOUBLE-BUFFERED in TMEM, so the single
+// tcgen05 issuer always runs two steps ahead of the softmax:
 //
-//     ... PV_A(j)  QK_A(j+1)  PV_B(j)  QK_B(j+1)  PV_A(j+1) ...
+//     step j of lane L:   wait P_L(j)  ->  O_L += P_L(j).V(j)  ;  S_L[j&1] = Q_L.K(j+2)^T
 //
-// While lane A's softmax warpgroup turns S_A(j+1) into P_A(j+1) the tensor pipe runs lane B's two MMAs and vice versa,
-// so neither the tensor pipe nor the SFU waits for the other for long.  (attn_fwd.cu relies on two independent CTAs per
-// SM drifting into that anti-phase; measured there: 34 % tensor-pipe activity.)
+// S_L(j+1) was produced while the softmax warpgroup of lane L was still busy with step j, so that warpgroup never waits
+// for the tensor pipe: its chain is only load -> max -> exp -> store, back to back, and the two lanes keep the SFU (the
+// slowest unit: 16 ex2/clk/SM = 1024 clk per 128x128 scores, the same as the two MMAs) permanently fed.  Measured
+// motivation (profiles/r01_attn_pair_trace.md): with one S buffer per lane the chain exp -> P -> PV -> QK -> S
+// serialises inside a lane (3660 clk per pair of 128x128 tiles, tensor pipe idle 44 %).
 //
-// Softmax: one thread per query row (TMEM lane) and all 128 key columns of the tile -> the row max and row sum need no
-// cross-thread exchange at all.  P (bf16) is written over the first 64 columns of the lane's S and consumed as the
-// TMEM A operand of O += P.V.  The running max uses the lazy-rescale rule of attn_fwd.cu.
+// Softmax: one thread per query row (TMEM lane) and all 64 key columns of the step -> the row max and row sum need no
+// cross-thread exchange.  P (bf16, 32 columns) is written over the start of its own S buffer and consumed as the TMEM
+// A operand of O += P.V.  The running max uses the lazy-rescale rule of attn_fwd.cu.
 //
 // CTA = 320 threads: warps 0-3 softmax/epilogue of lane A, warps 4-7 of lane B, warp 8 TMA, warp 9 MMA (+TMEM alloc).
-// TMEM (512 columns): S_A [0,128)  S_B [128,256)  O_A [256,256+D)  O_B [256+D,256+2D).
+// TMEM (512 columns), lane L at 256 L:  S buffer 0 [0,64)   S buffer 1 [64,128)   O [128,128+D).
 #include <math_constants.h>
 #include <stdlib.h>
 
@@ -22,7 +25,8 @@
 
 namespace lb {
 
-constexpr int PF_BM = 128, PF_BN = 128;
+constexpr int PF_BM = 128, PF_BN = 64;
+constexpr int PF_KST = 4, PF_VST = 4;                 // K / V ring depth (64-key tiles)
 constexpr int PF_WARP_TMA = 8, PF_WARP_MMA = 9, PF_THREADS = 320;
 constexpr float PF_LOG2E = 1.4426950408889634f;
 
@@ -37,29 +41,46 @@ struct AttnPairParams {
     int batch, seqlen, heads;
     int n_work, head_group;
     float scale;
+    long long* trace;            // optional [64][16] clock64 stamps of CTA 0 (diagnostics, lb_attn_fwd_pair_set_trace)
+    long long* cta_log;          // optional [n_cta][8]: smid, steps A, steps B, clock64 at entry / Q landed / last MMA issued / exit
 };
+
+#define PF_TRACE(slot, it)                                                                                  \
+    do {                                                                                                    \
+        if (p.trace && blockIdx.x == 0 && (it) < 64) p.trace[(it) * 16 + (slot)] = clock64();               \
+    } while (0)
 
 template <int D>
 struct PairSmem {
-    static constexpr int TILE = 128 * D * 2;                          // one Q / K / V tile
-    static constexpr int Q_OFF = 0, K_OFF = 2 * TILE, V_OFF = 4 * TILE, BAR_OFF = 6 * TILE;
-    static constexpr int NEEDED = BAR_OFF + 256 + 1024;
+    static constexpr int QTILE = PF_BM * D * 2;                       // one Q tile
+    static constexpr int KVTILE = PF_BN * D * 2;                      // one K or V tile (64 keys)
+    static constexpr int Q_OFF = 0, K_OFF = 2 * QTILE, V_OFF = K_OFF + PF_KST * KVTILE, BAR_OFF = V_OFF + PF_VST * KVTILE;
+    static constexpr int NEEDED = BAR_OFF + 512 + 1024;
     static constexpr int TOTAL = NEEDED > 120 * 1024 ? NEEDED : 120 * 1024;     // > half an SM: exactly one CTA per SM (512 TMEM columns)
 };
 
-enum { PB_Q = 0, PB_KFULL = 1, PB_KEMPTY = 3, PB_VFULL = 5, PB_VEMPTY = 7, PB_SFULL = 9, PB_PFULL = 11, PB_OREADY = 13, PB_COUNT = 15 };
+// barrier indices: S/P barriers are [lane][buffer]
+enum {
+    PB_Q = 0,
+    PB_KFULL = 1,
+    PB_KEMPTY = PB_KFULL + PF_KST,
+    PB_VFULL = PB_KEMPTY + PF_KST,
+    PB_VEMPTY = PB_VFULL + PF_VST,
+    PB_SFULL = PB_VEMPTY + PF_VST,
+    PB_PFULL = PB_SFULL + 4,
+    PB_OREADY = PB_PFULL + 4,
+    PB_COUNT = PB_OREADY + 2
+};
 
-// scores of one row (128 columns at TMEM `ts`) -> registers, optionally masked; returns the row maximum
+// scores of one row (64 columns at TMEM `ts`) -> registers, optionally masked; returns the row maximum
 template <bool MASK, bool CAUSAL>
-__device__ __forceinline__ float pair_load_max(uint32_t ts, uint32_t (&v)[128], int kv0, int qi, int kvs, int kve) {
+__device__ __forceinline__ float pair_load_max(uint32_t ts, uint32_t (&v)[64], int kv0, int qi, int kvs, int kve) {
     tmem_ld32(ts, v);
     tmem_ld32(ts + 32, v + 32);
-    tmem_ld32(ts + 64, v + 64);
-    tmem_ld32(ts + 96, v + 96);
     tc_wait_ld();
     float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F, mx2 = -CUDART_INF_F, mx3 = -CUDART_INF_F;
 #pragma unroll
-    for (int j = 0; j < 128; j += 4) {
+    for (int j = 0; j < 64; j += 4) {
         if (MASK) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -76,24 +97,21 @@ __device__ __forceinline__ float pair_load_max(uint32_t ts, uint32_t (&v)[128], 
     return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
 }
 
-// P = 2^(S*sl2 - m_off), packed to bf16 over the first 64 columns of the row's S; one exponential in every POLY runs on
-// the FMA pipes (poly_ex2), 0 = all on the SFU.  Returns the row sum.
+// P = 2^(S*sl2 - m_off), packed to bf16 over the first 32 columns of the row's S buffer; one exponential in every POLY
+// runs on the FMA pipes (poly_ex2), 0 = all on the SFU.  Returns the row sum.
 template <int POLY>
-__device__ __forceinline__ float pair_exp_store(uint32_t ts, uint32_t (&v)[128], float sl2, float m_off) {
+__device__ __forceinline__ float pair_exp_store(uint32_t ts, uint32_t (&v)[64], float sl2, float m_off) {
     float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-#pragma unroll
-        for (int j = c * 32; j < c * 32 + 32; j += 2) {
-            const float x0 = fmaf(__uint_as_float(v[j]), sl2, -m_off), x1 = fmaf(__uint_as_float(v[j + 1]), sl2, -m_off);
-            const float p0 = (POLY > 0 && (j % POLY) == 0) ? poly_ex2(x0) : fast_ex2(x0);
-            const float p1 = (POLY > 0 && ((j + 1) % POLY) == 0) ? poly_ex2(x1) : fast_ex2(x1);
-            l0 += p0;
-            l1 += p1;
-            v[j >> 1] = pack_bf16(p0, p1);
-        }
-        tmem_st16(ts + c * 16, v + c * 16);
+    for (int j = 0; j < 64; j += 2) {
+        const float x0 = fmaf(__uint_as_float(v[j]), sl2, -m_off), x1 = fmaf(__uint_as_float(v[j + 1]), sl2, -m_off);
+        const float p0 = (POLY > 0 && (j % POLY) == 0) ? poly_ex2(x0) : fast_ex2(x0);
+        const float p1 = (POLY > 0 && ((j + 1) % POLY) == 0) ? poly_ex2(x1) : fast_ex2(x1);
+        l0 += p0;
+        l1 += p1;
+        v[j >> 1] = pack_bf16(p0, p1);
     }
+    tmem_st32(ts, v);
     return l0 + l1;
 }
 
@@ -109,6 +127,7 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + PB_COUNT);
 
     const int warp = threadIdx.x >> 5;
+    const long long t_entry = p.cta_log ? clock64() : 0;
     int item, h;
     attn_cta_order(p.n_work, p.heads, p.head_group, item, h);
     const int b = p.work[item * 4 + 0];
@@ -117,22 +136,22 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     const int T = p.seqlen;
     const int kvs = p.kv_start ? p.kv_start[b] : 0;
     const int kve = p.kv_end ? p.kv_end[b] : T;
-    const int first_tile = kvs / PF_BN;
-    const int end_tile = (kve + PF_BN - 1) / PF_BN;                   // exclusive
-    int nt[2];
+    const int first_step = kvs / PF_BN;
+    const int end_step = (kve + PF_BN - 1) / PF_BN;                   // exclusive
+    int ns[2];                                                        // 64-key steps per lane
 #pragma unroll
     for (int L = 0; L < 2; ++L) {
-        int last = end_tile;
-        if (CAUSAL && last > qt[L] + 1) last = qt[L] + 1;
-        nt[L] = (qt[L] >= 0 && last > first_tile) ? last - first_tile : 0;
+        int last = end_step;
+        if (CAUSAL && last > 2 * (qt[L] + 1)) last = 2 * (qt[L] + 1);
+        ns[L] = (qt[L] >= 0 && last > first_step) ? last - first_step : 0;
     }
-    const int n_max = nt[0] > nt[1] ? nt[0] : nt[1];
+    const int n_max = ns[0] > ns[1] ? ns[0] : ns[1];
 
     constexpr uint32_t TMEM_COLS = 512;
-    constexpr uint32_t COL_O = 256;
+    constexpr uint32_t LANE_COLS = 256, COL_O = 128;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < PB_COUNT; ++i) mbar_init(bars + i, (i == PB_PFULL || i == PB_PFULL + 1) ? 128 : 1);
+        for (int i = 0; i < PB_COUNT; ++i) mbar_init(bars + i, (i >= PB_PFULL && i < PB_PFULL + 4) ? 128 : 1);
         fence_barrier_init();
     }
     if (warp == PF_WARP_TMA && elect_one()) {
@@ -154,93 +173,110 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         if (elect_one() && n_max > 0) {
             const CUtensorMap* tK = variant ? &tmK1 : &tmK0;
             const CUtensorMap* tV = variant ? &tmV1 : &tmV0;
-            mbar_arrive_expect_tx(bars + PB_Q, (uint32_t)S::TILE * ((nt[0] > 0) + (nt[1] > 0)));
+            mbar_arrive_expect_tx(bars + PB_Q, (uint32_t)S::QTILE * ((ns[0] > 0) + (ns[1] > 0)));
 #pragma unroll
             for (int L = 0; L < 2; ++L) {
-                if (nt[L] > 0) {
+                if (ns[L] > 0) {
 #pragma unroll
                     for (int c = 0; c < D / 64; ++c)
-                        tma_load_2d(smem + S::Q_OFF + L * S::TILE + c * (PF_BM * 128), &tmQ, bars + PB_Q, h * D + c * 64,
+                        tma_load_2d(smem + S::Q_OFF + L * S::QTILE + c * (PF_BM * 128), &tmQ, bars + PB_Q, h * D + c * 64,
                                     b * T + qt[L] * PF_BM);
                 }
             }
+            auto load_k = [&](int j) {
+                const int s = j % PF_KST;
+                mbar_wait(bars + PB_KEMPTY + s, ((uint32_t)(j / PF_KST) & 1u) ^ 1u);
+                mbar_arrive_expect_tx(bars + PB_KFULL + s, S::KVTILE);
+#pragma unroll
+                for (int c = 0; c < D / 64; ++c)
+                    tma_load_2d(smem + S::K_OFF + s * S::KVTILE + c * (PF_BN * 128), tK, bars + PB_KFULL + s, h * D + c * 64,
+                                b * T + (first_step + j) * PF_BN);
+            };
+            auto load_v = [&](int j) {
+                const int s = j % PF_VST;
+                mbar_wait(bars + PB_VEMPTY + s, ((uint32_t)(j / PF_VST) & 1u) ^ 1u);
+                mbar_arrive_expect_tx(bars + PB_VFULL + s, S::KVTILE);
+#pragma unroll
+                for (int c = 0; c < D / 64; ++c)
+                    tma_load_2d(smem + S::V_OFF + s * S::KVTILE + c * (PF_BN * 128), tV, bars + PB_VFULL + s, h * D + c * 64,
+                                b * T + (first_step + j) * PF_BN);
+            };
+            load_k(0);
+            if (n_max > 1) load_k(1);
             for (int j = 0; j < n_max; ++j) {
-                const int s = j & 1;
-                const uint32_t ph = (uint32_t)(j >> 1) & 1u;
-                const int row_k = b * T + (first_tile + j) * PF_BN;
-                mbar_wait(bars + PB_KEMPTY + s, ph ^ 1u);
-                mbar_arrive_expect_tx(bars + PB_KFULL + s, S::TILE);
-#pragma unroll
-                for (int c = 0; c < D / 64; ++c)
-                    tma_load_2d(smem + S::K_OFF + s * S::TILE + c * (PF_BN * 128), tK, bars + PB_KFULL + s, h * D + c * 64, row_k);
-                mbar_wait(bars + PB_VEMPTY + s, ph ^ 1u);
-                mbar_arrive_expect_tx(bars + PB_VFULL + s, S::TILE);
-#pragma unroll
-                for (int c = 0; c < D / 64; ++c)
-                    tma_load_2d(smem + S::V_OFF + s * S::TILE + c * (PF_BN * 128), tV, bars + PB_VFULL + s, h * D + c * 64, row_k);
+                load_v(j);
+                if (j + 2 < n_max) load_k(j + 2);
             }
         }
     } else if (warp == PF_WARP_MMA) {
-        // ------------------------------------------------------------ MMA issuer (both lanes, fixed interleave)
+        // ------------------------------------------------------------ MMA issuer (both lanes, two steps ahead of the softmax)
         if (elect_one() && n_max > 0) {
             constexpr uint32_t idesc_qk = make_idesc_bf16(PF_BM, PF_BN, 0, 0);
             constexpr uint32_t idesc_pv = make_idesc_bf16(PF_BM, D, 0, 1);
-            const uint32_t dQ[2] = {desc_lo_kmajor(smem_u32(smem + S::Q_OFF)), desc_lo_kmajor(smem_u32(smem + S::Q_OFF + S::TILE))};
-            const uint32_t dK[2] = {desc_lo_kmajor(smem_u32(smem + S::K_OFF)), desc_lo_kmajor(smem_u32(smem + S::K_OFF + S::TILE))};
-            const uint32_t dV[2] = {desc_lo_mnmajor(smem_u32(smem + S::V_OFF), PF_BN * 128),
-                                    desc_lo_mnmajor(smem_u32(smem + S::V_OFF + S::TILE), PF_BN * 128)};
-            auto issue_qk = [&](int L, int s) {
+            const uint32_t dQ[2] = {desc_lo_kmajor(smem_u32(smem + S::Q_OFF)), desc_lo_kmajor(smem_u32(smem + S::Q_OFF + S::QTILE))};
+            const uint32_t dK0 = desc_lo_kmajor(smem_u32(smem + S::K_OFF));
+            const uint32_t dV0 = desc_lo_mnmajor(smem_u32(smem + S::V_OFF), PF_BN * 128);
+            auto issue_qk = [&](int L, int j) {                       // S_L[j&1] = Q_L . K(j)^T
+                const uint32_t dK = dK0 + (uint32_t)((j % PF_KST) * (S::KVTILE >> 4));
+                const uint32_t d_s = tmem_base + (uint32_t)L * LANE_COLS + (uint32_t)(j & 1) * 64;
 #pragma unroll
                 for (int kk = 0; kk < D / 16; ++kk) {
-                    const uint32_t off = ((uint32_t)(kk / 4) * (PF_BM * 128) + (uint32_t)(kk % 4) * 32) >> 4;
-                    umma_ss_lo(tmem_base + (uint32_t)L * 128, dQ[L] + off, dK[s] + off, idesc_qk, kk ? 1u : 0u);
+                    const uint32_t offq = ((uint32_t)(kk / 4) * (PF_BM * 128) + (uint32_t)(kk % 4) * 32) >> 4;
+                    const uint32_t offk = ((uint32_t)(kk / 4) * (PF_BN * 128) + (uint32_t)(kk % 4) * 32) >> 4;
+                    umma_ss_lo(d_s, dQ[L] + offq, dK + offk, idesc_qk, kk ? 1u : 0u);
                 }
-                tc_commit(bars + PB_SFULL + L);
+                tc_commit(bars + PB_SFULL + L * 2 + (j & 1));
             };
-            auto issue_pv = [&](int L, int s, int j) {
+            auto issue_pv = [&](int L, int j) {                       // O_L += P_L(j) . V(j)
+                const uint32_t dV = dV0 + (uint32_t)((j % PF_VST) * (S::KVTILE >> 4));
+                const uint32_t a_p = tmem_base + (uint32_t)L * LANE_COLS + (uint32_t)(j & 1) * 64;
 #pragma unroll
                 for (int kk = 0; kk < PF_BN / 16; ++kk) {
-                    // A = P in TMEM: keys 16kk.. at column 8kk of the lane's S; B = V as MN-major (16 key rows = 2048 B)
-                    umma_ts_lo(tmem_base + COL_O + (uint32_t)L * D, tmem_base + (uint32_t)L * 128 + (uint32_t)kk * 8,
-                               dV[s] + (uint32_t)kk * (2048 >> 4), idesc_pv, (j | kk) ? 1u : 0u);
+                    // A = P in TMEM: keys 16kk.. at column 8kk of the S buffer; B = V as MN-major (16 key rows = 2048 B)
+                    umma_ts_lo(tmem_base + (uint32_t)L * LANE_COLS + COL_O, a_p + (uint32_t)kk * 8, dV + (uint32_t)kk * (2048 >> 4),
+                               idesc_pv, (j | kk) ? 1u : 0u);
                 }
                 tc_commit(bars + PB_OREADY + L);
             };
             mbar_wait(bars + PB_Q, 0);
-            mbar_wait(bars + PB_KFULL + 0, 0);
-            tc_fence_after_sync();
-            if (nt[0] > 0) issue_qk(0, 0);
-            if (nt[1] > 0) issue_qk(1, 0);
-            tc_commit(bars + PB_KEMPTY + 0);
+            if (p.cta_log) p.cta_log[(int64_t)blockIdx.x * 8 + 4] = clock64();
+            for (int j = 0; j < 2 && j < n_max; ++j) {                // prologue: S(0), S(1) of both lanes
+                mbar_wait(bars + PB_KFULL + j, 0);
+                tc_fence_after_sync();
+                if (j < ns[0]) issue_qk(0, j);
+                if (j < ns[1]) issue_qk(1, j);
+                tc_commit(bars + PB_KEMPTY + j);
+            }
             for (int j = 0; j < n_max; ++j) {
-                const int s = j & 1, s1 = s ^ 1;
-                const uint32_t ph_p = (uint32_t)j & 1u;                     // P/S/O barriers flip every tile
-                const uint32_t ph_s = (uint32_t)(j >> 1) & 1u;              // stage barriers every other tile
-                const uint32_t ph_s1 = (uint32_t)((j + 1) >> 1) & 1u;
+                const uint32_t ph_p = (uint32_t)(j >> 1) & 1u;                       // S/P buffers: every other step
+                const int sv = j % PF_VST, sk = (j + 2) % PF_KST;
                 bool v_seen = false, k_seen = false;
 #pragma unroll
                 for (int L = 0; L < 2; ++L) {
-                    if (j < nt[L]) {
-                        mbar_wait(bars + PB_PFULL + L, ph_p);
+                    if (j < ns[L]) {
+                        mbar_wait(bars + PB_PFULL + L * 2 + (j & 1), ph_p);
+                        PF_TRACE(2 * L, j);                                  // MMA: P of lane L seen
                         if (!v_seen) {
-                            mbar_wait(bars + PB_VFULL + s, ph_s);
+                            mbar_wait(bars + PB_VFULL + sv, (uint32_t)(j / PF_VST) & 1u);
                             v_seen = true;
                         }
                         tc_fence_after_sync();
-                        issue_pv(L, s, j);
-                        if (j + 1 < nt[L]) {
+                        issue_pv(L, j);
+                        if (j + 2 < ns[L]) {
                             if (!k_seen) {
-                                mbar_wait(bars + PB_KFULL + s1, ph_s1);
+                                mbar_wait(bars + PB_KFULL + sk, (uint32_t)((j + 2) / PF_KST) & 1u);
                                 tc_fence_after_sync();
                                 k_seen = true;
                             }
-                            issue_qk(L, s1);
+                            issue_qk(L, j + 2);
                         }
+                        PF_TRACE(2 * L + 1, j);                              // MMA: PV (+ QK two steps ahead) of lane L issued
                     }
                 }
-                tc_commit(bars + PB_VEMPTY + s);
-                if (j + 1 < n_max) tc_commit(bars + PB_KEMPTY + s1);
+                tc_commit(bars + PB_VEMPTY + sv);
+                if (j + 2 < n_max) tc_commit(bars + PB_KEMPTY + sk);
             }
+            if (p.cta_log) p.cta_log[(int64_t)blockIdx.x * 8 + 5] = clock64();
         }
     } else {
         // ------------------------------------------------------------ softmax / correction / epilogue (one lane per warpgroup)
@@ -248,28 +284,29 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const int r = (warp & 3) * 32 + (threadIdx.x & 31);       // query row in tile == TMEM lane
         const int q0 = qt[L] * PF_BM;
         const int qi = q0 + r;
-        const int n_tiles = nt[L];
-        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        const uint32_t colS = (uint32_t)L * 128;
-        const uint32_t colO = COL_O + (uint32_t)L * D;
+        const int n_steps = ns[L];
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)L * LANE_COLS;
         const float sl2 = p.scale * PF_LOG2E;
         float m_used = -CUDART_INF_F, l = 0.f;
-        for (int j = 0; j < n_tiles; ++j) {
-            const uint32_t ph = (uint32_t)j & 1u;
-            const int kv0 = (first_tile + j) * PF_BN;
+        for (int j = 0; j < n_steps; ++j) {
+            const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+            const uint32_t colS = (uint32_t)(j & 1) * 64;
+            const int kv0 = (first_step + j) * PF_BN;
             const bool need_mask = (CAUSAL && kv0 + PF_BN - 1 > q0) || (kv0 + PF_BN > kve) || (kv0 < kvs);
-            mbar_wait(bars + PB_SFULL + L, ph);
+            mbar_wait(bars + PB_SFULL + L * 2 + (j & 1), ph);
             tc_fence_after_sync();
-            uint32_t sv[128];
+            if ((threadIdx.x & 127) == 0) PF_TRACE(4 + 3 * L, j);            // softmax: S seen
+            uint32_t sv[64];
             const float mx = need_mask ? pair_load_max<true, CAUSAL>(lane_addr + colS, sv, kv0, qi, kvs, kve)
                                        : pair_load_max<false, CAUSAL>(lane_addr + colS, sv, kv0, qi, kvs, kve);
             const float m_new = fmaxf(m_used, mx);
+            if ((threadIdx.x & 127) == 0) PF_TRACE(5 + 3 * L, j);            // softmax: scores loaded, max done
             // lazy correction: rescale O only when the running max moved by more than 2^8
             const bool grow = (m_new - m_used) * sl2 > 8.f;      // also true when m_used == -inf and m_new finite
             if (j == 0) {
                 m_used = m_new;
             } else if (__any_sync(0xffffffffu, grow)) {
-                mbar_wait(bars + PB_OREADY + L, ph ^ 1u);         // PV of the previous tile has landed in O
+                mbar_wait(bars + PB_OREADY + L, (uint32_t)(j - 1) & 1u);     // PV of the previous step has landed in O
                 tc_fence_after_sync();
                 const float alpha = grow ? ((m_used == -CUDART_INF_F) ? 0.f : fast_ex2((m_used - m_new) * sl2)) : 1.f;
                 if (grow) {
@@ -277,13 +314,13 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
                     l *= alpha;
                 }
 #pragma unroll 1
-                for (int c = 0; c < D / 8; ++c) {                // small chunks: the scores stay live in registers
-                    uint32_t v[8];
-                    tmem_ld8(lane_addr + colO + c * 8, v);
+                for (int c = 0; c < D / 16; ++c) {
+                    uint32_t v[16];
+                    tmem_ld16(lane_addr + COL_O + c * 16, v);
                     tc_wait_ld();
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
-                    tmem_st8(lane_addr + colO + c * 8, v);
+                    for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+                    tmem_st16(lane_addr + COL_O + c * 16, v);
                 }
                 tc_wait_st();
             }
@@ -291,14 +328,15 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             l += pair_exp_store<POLY>(lane_addr + colS, sv, sl2, m_off);
             tc_wait_st();
             tc_fence_before_sync();
-            mbar_arrive(bars + PB_PFULL + L);
+            mbar_arrive(bars + PB_PFULL + L * 2 + (j & 1));
+            if ((threadIdx.x & 127) == 0) PF_TRACE(6 + 3 * L, j);            // softmax: P stored, arrived
         }
         // ---- epilogue: normalise and write the rows of this variant
         if (qt[L] >= 0) {
             const int64_t bt = (int64_t)b * T + qi;
             const bool row_ok = (qi < T) && (!p.qflag || (int)p.qflag[qi < T ? bt : 0] == variant);
-            if (n_tiles > 0) {
-                mbar_wait(bars + PB_OREADY + L, (uint32_t)(n_tiles - 1) & 1u);
+            if (n_steps > 0) {
+                mbar_wait(bars + PB_OREADY + L, (uint32_t)(n_steps - 1) & 1u);
                 tc_fence_after_sync();
             }
             const float inv_l = l > 0.f ? 1.f / l : 0.f;
@@ -307,8 +345,8 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll 1
             for (int c = 0; c < D / 32; ++c) {
                 uint32_t v[32];
-                if (n_tiles > 0) {
-                    tmem_ld32(lane_addr + colO + c * 32, v);
+                if (n_steps > 0) {
+                    tmem_ld32(lane_addr + COL_O + c * 32, v);
                     tc_wait_ld();
                 } else {
 #pragma unroll
@@ -338,6 +376,12 @@ attn_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     if (warp == PF_WARP_MMA) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+    if (p.cta_log && threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        long long* e = p.cta_log + (int64_t)blockIdx.x * 8;
+        e[0] = smid; e[1] = ns[0]; e[2] = ns[1]; e[3] = t_entry; e[6] = clock64();
     }
 }
 
@@ -380,6 +424,22 @@ static int launch_pair(const CUtensorMap* tm, const AttnPairParams& p, cudaStrea
 
 using namespace lb;
 
+static long long* g_pair_trace = nullptr;
+static long long* g_pair_cta_log = nullptr;
+
+/* diagnostics: every CTA of subsequent lb_attn_fwd_pair launches logs {smid, steps A, steps B, clock64 at entry, Q landed,
+ * last MMA issued, exit, -} into `buf` ([n_work*heads][8] int64, device); NULL = off */
+extern "C" int lb_attn_fwd_pair_set_cta_log(void* buf) {
+    g_pair_cta_log = (long long*)buf;
+    return LB_OK;
+}
+
+/* diagnostics: clock64 stamps of CTA 0 of subsequent lb_attn_fwd_pair launches go to `buf` ([64][16] int64, device); NULL = off */
+extern "C" int lb_attn_fwd_pair_set_trace(void* buf) {
+    g_pair_trace = (long long*)buf;
+    return LB_OK;
+}
+
 extern "C" int lb_attn_fwd_pair(const void* Q, const void* K0, const void* V0, const void* K1, const void* V1,
                                 const uint8_t* qflag, const int32_t* work, int n_work, const int32_t* kv_start,
                                 const int32_t* kv_end, const int32_t* out_row, void* O, float* lse, int batch, int seqlen,
@@ -395,13 +455,15 @@ extern "C" int lb_attn_fwd_pair(const void* Q, const void* K0, const void* V0, c
     CUtensorMap tm[5];
     const void* ptrs[5] = {Q, K0, V0, K1 ? K1 : K0, V1 ? V1 : V0};
     for (int i = 0; i < 5; ++i) {
-        rc = make_tmap_bf16_2d(&tm[i], ptrs[i], rows, cols, cols, 128, 64);
+        rc = make_tmap_bf16_2d(&tm[i], ptrs[i], rows, cols, cols, i == 0 ? PF_BM : PF_BN, 64);    // Q: 128-row boxes, K/V: 64
         if (rc) return rc;
     }
     AttnPairParams p;
     p.qflag = qflag; p.work = work; p.kv_start = kv_start; p.kv_end = kv_end; p.out_row = out_row;
     p.O = (__nv_bfloat16*)O; p.lse = lse; p.batch = batch; p.seqlen = seqlen; p.heads = heads; p.scale = scale;
     p.n_work = n_work; p.head_group = attn_head_group();
+    p.trace = g_pair_trace;
+    p.cta_log = g_pair_cta_log;
     cudaStream_t st = (cudaStream_t)stream;
     if (head_dim == 128) return causal ? launch_pair<128, true>(tm, p, st) : launch_pair<128, false>(tm, p, st);
     return causal ? launch_pair<64, true>(tm, p, st) : launch_pair<64, false>(tm, p, st);

@@ -17,8 +17,14 @@ import torch
 from . import ops
 from .schedule import AttnWork, Routing
 
-# attention forward kernel: the paired-tile one-CTA-per-SM kernel (csrc/attn_fwd_pair.cu) or the single-tile kernel
-FWD_PAIRED = os.environ.get("LB_ATTN_FWD_PAIR", "0") == "1"
+# attention forward kernel: "single" (csrc/attn_fwd.cu), "pair" (attn_fwd_pair.cu) or "stream" (attn_fwd_stream.cu)
+FWD_KERNEL = os.environ.get("LB_ATTN_FWD_KERNEL", "single")
+
+
+def _stream_plan(work: AttnWork, heads: int):
+    if FWD_KERNEL != "stream":
+        return None
+    return work.stream_plan(heads, ops.sm_count(), ops.STREAM_HEAD_GROUP)
 
 BF16 = torch.bfloat16
 
@@ -494,9 +500,9 @@ class BridgeAttention(torch.autograd.Function):
         scale = 1.0 / math.sqrt(meta.head_dim)
         o = torch.empty_like(q)
         # variant 0 = language queries (see Kfl/Vfl), variant 1 = vision queries (see Kfv/Vfv); rows land in sorted order
-        o, lse = ops.attn_fwd(Q, Kfl, Vfl, Kfv, Vfv, rt.flag_orig, w.work_q2 if FWD_PAIRED else w.work_q, w.kv_start, w.kv_end,
-                              rt.inv, meta.batch, meta.seqlen, meta.heads, meta.head_dim, True, scale, out=o,
-                              paired=FWD_PAIRED)
+        o, lse = ops.attn_fwd(Q, Kfl, Vfl, Kfv, Vfv, rt.flag_orig, w.work_q2 if FWD_KERNEL == "pair" else w.work_q, w.kv_start,
+                              w.kv_end, rt.inv, meta.batch, meta.seqlen, meta.heads, meta.head_dim, True, scale, out=o,
+                              kernel=FWD_KERNEL, plan=_stream_plan(w, meta.heads))
         ctx.meta = meta
         ctx.scale = scale
         ctx.save_for_backward(Q, Kfv, Kfl, Vfv, Vfl, o, lse, tk, tv, Bk_l, Bk_v, Bv_l, Bv_v)
@@ -541,8 +547,8 @@ class PlainAttention(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, q, k, v, work: AttnWork, batch, seqlen, heads, head_dim, scale):
-        o, lse = ops.attn_fwd(q, k, v, None, None, None, work.work_q2 if FWD_PAIRED else work.work_q, None, None, None, batch,
-                              seqlen, heads, head_dim, False, scale, paired=FWD_PAIRED)
+        o, lse = ops.attn_fwd(q, k, v, None, None, None, work.work_q2 if FWD_KERNEL == "pair" else work.work_q, None, None,
+                              None, batch, seqlen, heads, head_dim, False, scale, kernel=FWD_KERNEL, plan=_stream_plan(work, heads))
         ctx.args = (work, batch, seqlen, heads, head_dim, scale)
         ctx.save_for_backward(q, k, v, o, lse)
         return o

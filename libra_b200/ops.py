@@ -30,7 +30,21 @@ def _st():
 TIMED = None
 
 
-def enable_timing(names=("lb_attn_fwd", "lb_attn_fwd_pair", "lb_attn_bwd_dq", "lb_attn_bwd_dkv")):
+STREAM_HEAD_GROUP = 8          # heads per CTA-order group of the persistent attention forward (see schedule.stream_plan)
+
+
+_SM_COUNT = None
+
+
+def sm_count() -> int:
+    global _SM_COUNT
+    if _SM_COUNT is None:
+        _lib.require_device()
+        _SM_COUNT = int(_lib.load().lb_sm_count())
+    return _SM_COUNT
+
+
+def enable_timing(names=("lb_attn_fwd", "lb_attn_fwd_pair", "lb_attn_fwd_stream", "lb_attn_bwd_dq", "lb_attn_bwd_dkv")):
     global TIMED
     TIMED = {n: [] for n in names}
 
@@ -259,14 +273,22 @@ def attn_prep_bwd(dQ, dKfv, dKfl, dVfv, dVfl, flag_sorted, sorted_of, pos, cos_t
 
 
 def attn_fwd(Q, K0, V0, K1, V1, qflag, work, kv_start, kv_end, out_row, batch, seqlen, heads, head_dim, causal, scale,
-             out=None, paired=False):
-    """paired=True: `work` is the paired-tile list (AttnWork.work_q2) and the one-CTA-per-SM kernel runs."""
+             out=None, paired=False, kernel=None, plan=None):
+    """kernel: "single" (two CTAs per SM, one q tile each), "pair" (`work` is the paired-tile list AttnWork.work_q2) or
+    "stream" (persistent, same work list as "single"; `plan` = AttnWork.stream_plan(...) or None for the built-in
+    snake split).  paired=True is shorthand for kernel="pair"."""
+    kernel = kernel or ("pair" if paired else "single")
     C = heads * head_dim
     if out is None:
         out = torch.zeros(batch * seqlen, C, dtype=BF16, device=Q.device)
     lse = torch.full((batch, heads, seqlen), float("inf"), dtype=torch.float32, device=Q.device)
-    _timed_call("lb_attn_fwd_pair" if paired else "lb_attn_fwd", _p(Q), _p(K0), _p(V0), _p(K1), _p(V1), _p(qflag), _p(work), work.shape[0], _p(kv_start),
-              _p(kv_end), _p(out_row), _p(out), _p(lse), batch, seqlen, heads, head_dim, int(causal), float(scale), _st())
+    tail = (_p(kv_start), _p(kv_end), _p(out_row), _p(out), _p(lse), batch, seqlen, heads, head_dim, int(causal), float(scale), _st())
+    head = (_p(Q), _p(K0), _p(V0), _p(K1), _p(V1), _p(qflag), _p(work), work.shape[0])
+    if kernel == "stream":
+        items, off, n_cta = plan if plan is not None else (None, None, 0)
+        _timed_call("lb_attn_fwd_stream", *head, _p(items), _p(off), n_cta, STREAM_HEAD_GROUP, *tail)
+    else:
+        _timed_call({"single": "lb_attn_fwd", "pair": "lb_attn_fwd_pair"}[kernel], *head, *tail)
     return out, lse
 
 

@@ -50,6 +50,41 @@ class AttnWork:
     kv_end: Optional[torch.Tensor]
     kv_cover: tuple = (False, False)   # per variant: every kv tile of every sample has a dK/dV work item
     work_q2: Optional[torch.Tensor] = None   # [n,4] int32 {b, q_tile A, variant, q_tile B or -1}: paired-tile forward
+    q_tiles: Optional[list] = None           # kv tiles of every work_q item (host copy, for stream_plan)
+    _plans: Optional[dict] = None
+
+    def stream_plan(self, heads: int, n_cta: int, head_group: int = 8, overhead: float = 2.0):
+        """Balanced split of the (work item, head) list over n_cta persistent CTAs (lb_attn_fwd_stream).
+        Head groups are dealt in order (the K/V of one group stay L2-resident); inside a group the items go heaviest
+        first to the least-loaded CTA, the load carried over from group to group.  weight = kv tiles + `overhead`
+        (per-item prologue/epilogue in tile units).  Returns (plan_items [n_items], plan_off [n_cta+1]) int32 on the
+        work list's device; cached per (heads, n_cta, head_group)."""
+        import heapq
+        if self._plans is None:
+            self._plans = {}
+        key = (heads, n_cta, head_group)
+        if key not in self._plans:
+            n_work = len(self.q_tiles)
+            n_cta = max(1, min(n_cta, n_work * heads))
+            loads = [(0.0, c) for c in range(n_cta)]
+            heapq.heapify(loads)
+            per_cta = [[] for _ in range(n_cta)]
+            base = 0
+            for g0 in range(0, heads, head_group):
+                gl = min(head_group, heads - g0)
+                for w in range(n_work):                       # work_q is sorted heaviest first
+                    for hh in range(gl):
+                        load, c = heapq.heappop(loads)
+                        per_cta[c].append(base + w * gl + hh)
+                        heapq.heappush(loads, (load + self.q_tiles[w] + overhead, c))
+                base += head_group * n_work
+            off = [0]
+            for lst in per_cta:
+                off.append(off[-1] + len(lst))
+            items = torch.tensor([x for lst in per_cta for x in lst], dtype=torch.int32)
+            dev = self.work_q.device
+            self._plans[key] = (items.to(dev), torch.tensor(off, dtype=torch.int32).to(dev), n_cta)
+        return self._plans[key]
 
 
 def build_attn_work(vision_flag_cpu: Optional[torch.Tensor], batch: int, seqlen: int, causal: bool, device,
@@ -102,4 +137,4 @@ def build_attn_work(vision_flag_cpu: Optional[torch.Tensor], batch: int, seqlen:
     wkv = torch.tensor([[b, kt, v, fq] for _, b, kt, v, fq in items_kv], dtype=torch.int32).reshape(-1, 4)
     to = lambda t: None if t is None else torch.as_tensor(t, dtype=torch.int32).to(device)
     return AttnWork(wq.to(device), wkv.to(device), has.to(device), to(kv_start), to(kv_end), (cover[0], cover[1]),
-                    wq2.to(device))
+                    wq2.to(device), [w for w, _, _, _ in items_q])

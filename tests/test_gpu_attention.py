@@ -56,15 +56,23 @@ def oracle_out(c, causal=True, grads=None):
     return o
 
 
-PAIRED = False        # which forward kernel run_fwd launches; the `fwd_kernel` fixture runs a test once with each
+KERNEL = "single"      # which forward kernel run_fwd launches; the `fwd_kernel` fixture runs a test once with each
 
 
-@pytest.fixture(params=[False, True], ids=["single", "paired"])
+@pytest.fixture(params=["single", "pair", "stream"])
 def fwd_kernel(request):
-    global PAIRED
-    PAIRED = request.param
+    global KERNEL
+    KERNEL = request.param
     yield request.param
-    PAIRED = False
+    KERNEL = "single"
+
+
+def stream_plan(w, heads):
+    """Balanced split for the persistent kernel; odd CTA counts and the built-in snake split get exercised too."""
+    if KERNEL != "stream":
+        return None
+    from libra_b200 import ops
+    return w.stream_plan(heads, ops.sm_count()) if (len(w.q_tiles) * heads) % 3 else None
 
 
 def run_fwd(c, causal=True, out_row=None):
@@ -76,8 +84,8 @@ def run_fwd(c, causal=True, out_row=None):
     qflag = c["flag"].reshape(-1).to(torch.uint8) if causal else None
     o, lse = ops.attn_fwd(flat(c["q"]), flat(c["Kfl"]) if causal else flat(c["k"]), flat(c["Vfl"]) if causal else flat(c["v"]),
                           flat(c["Kfv"]) if causal else None, flat(c["Vfv"]) if causal else None, qflag,
-                          w.work_q2 if PAIRED else w.work_q, w.kv_start, w.kv_end, out_row, B, T, H, D, causal,
-                          1.0 / math.sqrt(D), paired=PAIRED)
+                          w.work_q2 if KERNEL == "pair" else w.work_q, w.kv_start, w.kv_end, out_row, B, T, H, D, causal,
+                          1.0 / math.sqrt(D), kernel=KERNEL, plan=stream_plan(w, H))
     torch.cuda.synchronize()
     return o.view(B, T, H * D), lse, w
 
