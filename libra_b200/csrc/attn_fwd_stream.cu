@@ -18,7 +18,7 @@
 //
 // CTA = 384 threads: warps 0-3 softmax warpgroup 0 (even kv tiles), warps 4-7 warpgroup 1 (odd kv tiles), warp 8 TMA,
 // warp 9 tcgen05 issuer (+ TMEM alloc); warps 10-11 idle (they complete the producer warpgroup for setmaxnreg: the softmax
-// warpgroups run with 224 registers per thread, the producer warpgroup with 64).  TMEM (512 columns): S buffers [0,128) [128,256) [256,384), O [384,384+D).
+// warpgroups run with 216 registers per thread, the producer warpgroup with 64).  TMEM (512 columns): S buffers [0,128) [128,256) [256,384), O [384,384+D).
 // P (bf16, 64 columns) is written over the start of its own S buffer and is the TMEM A operand of O += P.V.
 #include <math_constants.h>
 #include <stdlib.h>
@@ -31,7 +31,7 @@ namespace fs {
 constexpr int BM = 128, BN = 128;
 constexpr int KST = 3, VST = 2;                        // K / V ring depth
 constexpr int WARP_TMA = 8, WARP_MMA = 9, THREADS = 384;   // warps 10, 11 only complete the third warpgroup (setmaxnreg)
-constexpr int REGS_SOFTMAX = 224, REGS_PRODUCER = 64;       // per SM sub-partition: 2 x 224 + 64 = 512 = 16384 / 32
+constexpr int REGS_SOFTMAX = 216, REGS_PRODUCER = 64;       // the CTA pool is what the launch allocated: 3 x 168 = 504 >= 2 x 216 + 64
 constexpr float LOG2E = 1.4426950408889634f;
 
 struct Params {

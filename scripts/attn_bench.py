@@ -36,11 +36,23 @@ def timeit(fn, n=10):
     return ts[len(ts) // 2]
 
 fl = B * 4 * T * T * H * D / 2
-t_f = timeit(lambda: ops.attn_fwd(Q, K0, V0, K1, V1, qf, w.work_q, None, None, None, B, T, H, D, True, scale, out=o))
-t_p = timeit(lambda: ops.attn_fwd(Q, K0, V0, K1, V1, qf, w.work_q2, None, None, None, B, T, H, D, True, scale, out=o, paired=True))
-t_s = timeit(lambda: ops.attn_fwd(Q, K0, V0, K1, V1, qf, w.work_q, None, None, None, B, T, H, D, True, scale, out=o, kernel="stream", plan=PLAN))
-t_q = timeit(lambda: ops.attn_bwd_dq(Q, K0, V0, K1, V1, dO, lse, delta, qf, w.work_q, None, None, B, T, H, D, True, scale))
-t_k = timeit(lambda: ops.attn_bwd_dkv(Q, K0, V0, K1, V1, dO, lse, delta, qf, w.qtile_has, w.work_kv, None, None, B, T, H, D, True,
-                                      scale, kv_cover=(True, True)))
-print(f"LB_EXP_POLY={os.environ.get('LB_EXP_POLY', 'default')}  fwd {t_f*1e3:.0f} us = {fl/t_f/1e9:.0f} TF/s | fwd-pair(poly={os.environ.get('LB_PAIR_EXP_POLY', '0')}) {t_p*1e3:.0f} us = {fl/t_p/1e9:.0f} TF/s | fwd-stream(poly={os.environ.get('LB_STREAM_EXP_POLY', '0')}) {t_s*1e3:.0f} us = {fl/t_s/1e9:.0f} TF/s | dq {t_q*1e3:.0f} us | "
-      f"dkv {t_k*1e3:.0f} us | bwd {2.5*fl/(t_q+t_k)/1e9:.0f} TF/s (algorithmic, causal)")
+# kernels to time: argv (default: the product kernels).  An experimental kernel goes in its own process.
+which = sys.argv[1:] or ["single", "dq", "dkv"]
+res = {}
+if "single" in which:
+    res["fwd"] = timeit(lambda: ops.attn_fwd(Q, K0, V0, K1, V1, qf, w.work_q, None, None, None, B, T, H, D, True, scale, out=o))
+if "pair" in which:
+    res["fwd-pair"] = timeit(lambda: ops.attn_fwd(Q, K0, V0, K1, V1, qf, w.work_q2, None, None, None, B, T, H, D, True, scale, out=o, paired=True))
+if "stream" in which:
+    o_ref, lse_ref = o.clone(), lse.clone()
+    o2, lse2 = ops.attn_fwd(Q, K0, V0, K1, V1, qf, w.work_q, None, None, None, B, T, H, D, True, scale, kernel="stream", plan=PLAN)
+    torch.cuda.synchronize()
+    print("stream vs single: max|dO| %.3e  max|dlse| %.3e" % ((o2.float() - o_ref.float()).abs().max().item(), (lse2 - lse_ref).abs().max().item()))
+    res["fwd-stream"] = timeit(lambda: ops.attn_fwd(Q, K0, V0, K1, V1, qf, w.work_q, None, None, None, B, T, H, D, True, scale, out=o, kernel="stream", plan=PLAN))
+for k, t in res.items():
+    print(f"{k} {t*1e3:.0f} us = {fl/t/1e9:.0f} TF/s (algorithmic, causal)")
+if "dq" in which and "dkv" in which:
+    t_q = timeit(lambda: ops.attn_bwd_dq(Q, K0, V0, K1, V1, dO, lse, delta, qf, w.work_q, None, None, B, T, H, D, True, scale))
+    t_k = timeit(lambda: ops.attn_bwd_dkv(Q, K0, V0, K1, V1, dO, lse, delta, qf, w.qtile_has, w.work_kv, None, None, B, T, H, D, True,
+                                          scale, kv_cover=(True, True)))
+    print(f"dq {t_q*1e3:.0f} us | dkv {t_k*1e3:.0f} us | bwd {2.5*fl/(t_q+t_k)/1e9:.0f} TF/s (algorithmic, causal)")
