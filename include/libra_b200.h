@@ -163,21 +163,26 @@ int lb_attn_fwd_pair(const void* Q, const void* K0, const void* V0, const void* 
                      int causal, float scale, void* stream);
 
 /* Same operation and work list as lb_attn_fwd, persistent streaming kernel (csrc/attn_fwd_stream.cu): one CTA per SM
- * walks its share of the (work item, head) list; scores are triple-buffered in TMEM, two softmax warpgroups take
- * alternate kv tiles.  List position L of (work item w, head h): heads run in groups of head_group, inside group g
- * (gl = heads in the group) L = g*head_group*n_work + w*gl + (h - g*head_group).
+ * walks its share of the (work item, head) list as one stream of score tiles; S and P are double-buffered in TMEM (QK^T
+ * runs two tiles ahead of PV), two softmax warpgroups take alternate tiles, a separate warpgroup writes O out.
+ * List position L of (work item w, head h): heads run in groups of head_group, inside group g (gl = heads in the group)
+ * L = g*head_group*n_work + w*gl + (h - g*head_group).
  * plan_items [n_work*heads] / plan_off [n_cta+1] (int32, device): the list positions each of the n_cta CTAs handles, in
- * order (host-side balanced split, libra_b200/schedule.py: stream_plan).  Both NULL: a static snake split over one CTA
- * per SM.  head_group <= 0: library default (LB_ATTN_HEAD_GROUP, 8). */
+ * order (host-side balanced split, libra_b200/schedule.py: stream_plan); max_cta_items = the longest per-CTA list of the
+ * plan.  Both NULL: a static snake split over one CTA per SM (n_cta, max_cta_items ignored).  A CTA holds at most
+ * lb_attn_fwd_stream_max_cta_items() decoded items (LB_EINVAL beyond; use lb_attn_fwd then).
+ * head_group <= 0: library default (LB_ATTN_HEAD_GROUP, 8). */
 int lb_attn_fwd_stream(const void* Q, const void* K0, const void* V0, const void* K1, const void* V1, const uint8_t* qflag,
                        const int32_t* work, int n_work, const int32_t* plan_items, const int32_t* plan_off, int n_cta,
-                       int head_group, const int32_t* kv_start, const int32_t* kv_end, const int32_t* out_row, void* O,
-                       float* lse, int batch, int seqlen, int heads, int head_dim, int causal, float scale, void* stream);
+                       int max_cta_items, int head_group, const int32_t* kv_start, const int32_t* kv_end,
+                       const int32_t* out_row, void* O, float* lse, int batch, int seqlen, int heads, int head_dim,
+                       int causal, float scale, void* stream);
+int lb_attn_fwd_stream_max_cta_items(void);
 /* diagnostics: every CTA logs {smid, items, tiles, clock64 at entry, first Q landed, exit, -, -} into buf
  * ([number of SMs][8] int64, device memory).  NULL = off */
 int lb_attn_fwd_stream_set_cta_log(void* buf);
-/* diagnostics: CTA 0 writes clock64 stamps into buf ([64][8] int64, device; one row per kv tile: MMA wait-P / P seen /
- * issued, softmax wait-S / S seen / max done / max published / P arrived).  NULL = off */
+/* diagnostics: CTA 0 writes clock64 stamps into buf ([64][32] int64, device; one row per kv tile: slots 0-9 tcgen05 thread, 10-17
+ * softmax thread 0 of the tile's warpgroup).  NULL = off */
 int lb_attn_fwd_stream_set_trace(void* buf);
 
 /* diagnostics: CTA 0 of subsequent lb_attn_fwd_pair launches writes clock64 stamps into buf ([64][16] int64, device

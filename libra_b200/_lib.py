@@ -42,7 +42,8 @@ SIGNATURES = {
     "lb_attn_prep_bwd": (I, [P] * 15 + [L, I, I, P]),
     "lb_attn_fwd": (I, [P, P, P, P, P, P, P, I, P, P, P, P, P, I, I, I, I, I, F, P]),
     "lb_attn_fwd_pair": (I, [P, P, P, P, P, P, P, I, P, P, P, P, P, I, I, I, I, I, F, P]),
-    "lb_attn_fwd_stream": (I, [P, P, P, P, P, P, P, I, P, P, I, I, P, P, P, P, P, I, I, I, I, I, F, P]),
+    "lb_attn_fwd_stream": (I, [P, P, P, P, P, P, P, I, P, P, I, I, I, P, P, P, P, P, I, I, I, I, I, F, P]),
+    "lb_attn_fwd_stream_max_cta_items": (I, []),
     "lb_attn_fwd_stream_set_cta_log": (I, [P]),
     "lb_attn_fwd_stream_set_trace": (I, [P]),
     "lb_attn_fwd_set_trace": (I, [P]),

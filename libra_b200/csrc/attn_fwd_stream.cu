@@ -1,25 +1,33 @@
 // Bridge attention forward, persistent streaming kernel (A10; same maths and operand formulation as attn_fwd.cu).
 //
-// One CTA per SM walks a static share of the (work item, head) list.  What the measurements of the earlier kernels said
-// (profiles/r01_attn_fwd_design_notes.md) and how this kernel answers:
-//   * per 128x128 score tile the tensor pipe needs 1024 clk (QK^T 512 + PV 512; the SS-mode QK^T is also exactly at the
-//     128 B/clk shared-memory limit, so narrower key tiles are slower) and the SFU needs 1024 clk (16 ex2/clk/SM).  With
-//     one S buffer the chain  S -> exp -> P -> PV -> next S  serialises them (34 % tensor activity).  Here S is
-//     TRIPLE-buffered in TMEM: the issuer runs   wait P(j);  O += P(j).V(j);  S[j%3] = Q.K(j+3)^T   so S(j+2) is
-//     complete long before a softmax warpgroup asks for it.
-//   * two softmax warpgroups take ALTERNATE kv tiles (thread = query row, all 128 key columns, no cross-thread max/sum
-//     exchange inside a tile).  While one warpgroup is in its SFU-bound exp phase the other does its TMEM load + max,
-//     so the SFU stays busy.  The only coupling between consecutive tiles is the running row maximum, handed over
-//     through shared memory right after the (short) max phase; O is rescaled lazily (FlashAttention-4 rule: only when
-//     the maximum grew by more than 2^8), each warpgroup keeps its own partial row sum.
-//   * prologue (TMEM alloc, barrier init, tensor-map fetch, first loads) and epilogue cost ~7 k clk per CTA when a CTA
-//     handles one item.  The CTA is persistent: TMEM and barriers are set up once, the TMA warp prefetches the next
-//     item's Q/K/V as ring slots free up, and the next item's first three QK^T run under the current item's epilogue.
+// One CTA per SM walks a static share of the (work item, head) list as ONE stream of 128x128 score tiles (global tile
+// index G), independent of where the items begin and end.  What the measurements of the earlier kernels said
+// (profiles/r01_attn_fwd_stream_notes.md) and how this kernel answers:
+//   * per score tile the tensor pipe needs 1024 clk (QK^T 512 + PV 512) and the SFU needs 1024 clk (16 ex2/clk/SM), so
+//     any dependency loop between the two shows up directly as idle pipe.  With P written over its own S buffer the loop
+//     P(G) -> PV(G) -> QK^T(G+3) -> softmax(G+3) was the limit (1650 clk per tile in steady state).  Here S is
+//     double-buffered and P has its OWN two TMEM buffers: an S buffer is free as soon as the softmax warpgroup has pulled
+//     the scores into registers, so QK^T(G+2) is issued at the START of softmax(G) and the scores of a tile are always
+//     complete long before a warpgroup asks for them.  QK^T and PV are issued by two different threads: a single issuing
+//     thread executes one dependent instruction every ~5 clk, and its waits / descriptor arithmetic / commits between two
+//     batches of MMAs were the critical path (~2100 clk per tile for both products from one general loop).
+//   * two softmax warpgroups take alternate tiles of the stream (thread = query row, all 128 key columns, no cross-thread
+//     max/sum exchange inside a tile).  The only coupling between consecutive tiles is the running row maximum, handed
+//     over through shared memory right after the (short) max phase; O is rescaled lazily (FlashAttention-4 rule: only
+//     when the maximum grew by more than 2^8), each warpgroup keeps its own partial row sum.
+//   * an item switch cost ~6.5 k clk (4 tiles' worth, 30 % of the kernel at 15 items per CTA) when the softmax warpgroups
+//     wrote O out themselves and every role decoded the next item from global memory (a chain of dependent loads).  Now
+//     (a) the CTA's item list is decoded once into shared memory, (b) a separate EPILOGUE warpgroup reads O from TMEM,
+//     normalises and stores it while the softmax warpgroups are already on the next item -- they only deposit their
+//     (reference max, partial sum) pair per item in a 4-deep shared-memory ring, (c) the loaders and the tcgen05 thread
+//     run across item boundaries (Q for the next item is fetched as soon as the last QK^T of the current one retired).
 //
-// CTA = 384 threads: warps 0-3 softmax warpgroup 0 (even kv tiles), warps 4-7 warpgroup 1 (odd kv tiles), warp 8 TMA,
-// warp 9 tcgen05 issuer (+ TMEM alloc); warps 10-11 idle (they complete the producer warpgroup for setmaxnreg: the softmax
-// warpgroups run with 216 registers per thread, the producer warpgroup with 64).  TMEM (512 columns): S buffers [0,128) [128,256) [256,384), O [384,384+D).
-// P (bf16, 64 columns) is written over the start of its own S buffer and is the TMEM A operand of O += P.V.
+// CTA = 512 threads: warps 0-3 softmax warpgroup 0 (even tiles of the stream), warps 4-7 warpgroup 1 (odd tiles),
+// warp 8 TMA for Q and K, warp 9 tcgen05 issuer for QK^T (+ TMEM alloc), warp 10 TMA for V, warp 11 tcgen05 issuer for
+// PV, warps 12-15 epilogue.
+// setmaxnreg: softmax warpgroups 200 registers per thread, producers 72, epilogue 40 (2 x 200 + 72 + 40 = 4 x 128).
+// TMEM (512 columns): S0 [0,128) S1 [128,256) P0 [256,320) P1 [320,384) O [384,384+D).  P (bf16, 64 columns) is the
+// TMEM A operand of O += P.V.
 #include <math_constants.h>
 #include <stdlib.h>
 
@@ -29,10 +37,13 @@ namespace lb {
 namespace fs {
 
 constexpr int BM = 128, BN = 128;
-constexpr int KST = 3, VST = 2;                        // K / V ring depth
-constexpr int WARP_TMA = 8, WARP_MMA = 9, THREADS = 384;   // warps 10, 11 only complete the third warpgroup (setmaxnreg)
-constexpr int REGS_SOFTMAX = 216, REGS_PRODUCER = 64;       // the CTA pool is what the launch allocated: 3 x 168 = 504 >= 2 x 216 + 64
+constexpr int QST = 2, KST = 2, VST = 2;                         // Q / K / V ring depth; K slot == S slot, V slot == P slot (G & 1)
+constexpr int WARP_KLOAD = 8, WARP_QK = 9, WARP_VLOAD = 10, WARP_PV = 11, WARP_EPI0 = 12, THREADS = 512;
+constexpr int REGS_SOFTMAX = 200, REGS_PRODUCER = 72, REGS_EPILOGUE = 40;   // launch allocation is 128 per thread: 2 x 200 + 72 + 40 = 512
+constexpr int MAX_ITEMS = 256;                                   // decoded items per CTA held in shared memory
+constexpr int DEP = 4;                                           // depth of the (m_ref, l) deposit ring
 constexpr float LOG2E = 1.4426950408889634f;
+constexpr uint32_t COL_P = 256, COL_O = 384, TMEM_COLS = 512;
 
 struct Params {
     const uint8_t* qflag;        // [B*T] or null
@@ -48,42 +59,81 @@ struct Params {
     const int32_t* plan_off;     // [gridDim.x + 1]
     float scale;
     long long* cta_log;          // optional [gridDim.x][8]: smid, items, tiles, clock64 at entry / first Q landed / exit
-    long long* trace;            // optional [64][8] clock64 stamps of CTA 0, one row per kv tile (global index)
+    long long* trace;            // optional [64][32] clock64 stamps of CTA 0, one row per kv tile (global index)
 };
 
 #define FS_TRACE(slot, G)                                                                              \
     do {                                                                                               \
-        if (p.trace && blockIdx.x == 0 && (G) < 64) p.trace[(G) * 8 + (slot)] = clock64();             \
+        if (TRACE && blockIdx.x == 0 && (G) < 64) p.trace[(G) * 32 + (slot)] = clock64();              \
     } while (0)
+
+struct __align__(16) Item {
+    int b, q_tile, variant, h, kvs, kve, first_tile, n_tiles;       // b < 0 (and n_tiles < 0): end of the CTA's list
+};
 
 template <int D>
 struct Smem {
     static constexpr int TILE = 128 * D * 2;                          // one Q / K / V tile
-    static constexpr int Q_OFF = 0, K_OFF = TILE, V_OFF = K_OFF + KST * TILE;
-    static constexpr int STAT_OFF = V_OFF + VST * TILE;               // float m_sh[2][128], l_sh[2 item parity][2 wg][128]
-    static constexpr int BAR_OFF = STAT_OFF + (2 + 4) * 128 * 4;
+    static constexpr int Q_OFF = 0, K_OFF = QST * TILE, V_OFF = K_OFF + KST * TILE;
+    static constexpr int ITEM_OFF = V_OFF + VST * TILE;               // Item[MAX_ITEMS + 1]
+    static constexpr int M_OFF = ITEM_OFF + (MAX_ITEMS + 1) * 32;     // float m_sh[2 tile parity][128]
+    static constexpr int DEP_OFF = M_OFF + 2 * 128 * 4;               // float dep[DEP][2 wg][2: m_ref, l][128]
+    static constexpr int DONE_OFF = DEP_OFF + DEP * 2 * 2 * 128 * 4;  // int epi_done[128]: items whose deposit row r was read
+    static constexpr int BAR_OFF = DONE_OFF + 128 * 4;
     static constexpr int NEEDED = BAR_OFF + 512 + 1024;
     static constexpr int TOTAL = NEEDED > 120 * 1024 ? NEEDED : 120 * 1024;     // > half an SM: one CTA per SM (512 TMEM columns)
 };
 
 enum {
-    B_QFULL = 0,
-    B_QEMPTY,
-    B_KFULL,
-    B_KEMPTY = B_KFULL + KST,
-    B_VFULL = B_KEMPTY + KST,
-    B_VEMPTY = B_VFULL + VST,
-    B_SFULL = B_VEMPTY + VST,        // [3] scores of a tile landed in S buffer
-    B_PFULL = B_SFULL + 3,           // [3] probabilities written (128 arrivals: one warpgroup)
-    B_OREADY = B_PFULL + 3,          // [2] PV of a tile done, by parity of the global PV index
-    B_OFINAL = B_OREADY + 2,         // all MMAs of an item done
-    B_OFREE,                         // the epilogue has read O (256 arrivals)
-    B_MPUB,                          // [2] running max of a tile published, by tile parity (128 arrivals)
-    B_COUNT = B_MPUB + 2
+    B_QFULL = 0,                     // [2] Q of an item landed (items with tiles alternate between the two Q buffers)
+    B_QEMPTY = B_QFULL + QST,        // [2] last QK^T of the item retired
+    B_KFULL = B_QEMPTY + QST,        // [2] K(G) landed in slot G & 1
+    B_VFULL = B_KFULL + KST,         // [2] V(G) landed in slot G & 1
+    B_SFULL = B_VFULL + VST,         // [2] scores of tile G landed in S[G & 1]  (== K slot G & 1 free again)
+    B_SFREE = B_SFULL + 2,           // [2] the softmax warpgroup holds S[G & 1] in registers (128 arrivals)
+    B_PFULL = B_SFREE + 2,           // [2] probabilities of tile G written to P[G & 1] (128 arrivals)
+    B_PFREE = B_PFULL + 2,           // [2] PV of tile G retired: P[G & 1] and V slot G & 1 reusable, O holds tile G
+    B_OFINAL = B_PFREE + 2,          // all MMAs of an item done (items with tiles only)
+    B_OFREE,                         // the epilogue has read O (128 arrivals; items with tiles only)
+    B_MPUB,                          // [2] running max of tile G published in m_sh[G & 1] (128 arrivals)
+    B_LDEP = B_MPUB + 2,             // [DEP] both softmax warpgroups deposited (m_ref, l) of an item (256 arrivals)
+    B_COUNT = B_LDEP + DEP
 };
 
-// the items of this CTA: round k takes list position k*G + c, alternating direction (the list is sorted heaviest
-// first inside a head group, so the snake keeps the per-CTA sums close)
+// spin on an mbarrier phase (shared-window address).  Lean on the fast path: the single-thread roles execute one
+// dependent instruction every ~5 clk, so every instruction between two tcgen05.mma batches is tensor-pipe idle time.
+__device__ __forceinline__ void wait_bar(uint32_t bar_addr, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar_addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    uint32_t spins = 0;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, P;\n\t"
+            "}\n"
+            : "=r"(ok)
+            : "r"(bar_addr), "r"(parity)
+            : "memory");
+        if (++spins > LB_MBAR_SPIN_LIMIT) __trap();              // protocol bug: fail instead of hanging the device
+    } while (!ok);
+}
+__device__ __forceinline__ void commit_bar(uint32_t bar_addr) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+}
+
+// list position of the CTA's k-th item, or -1.  Without a plan: round k takes list position k*G + c, alternating
+// direction (the list is sorted heaviest first inside a head group, so the snake keeps the per-CTA sums close)
 __device__ __forceinline__ int item_of_round(const Params& p, int k) {
     if (p.plan_items) {
         const int i = p.plan_off[blockIdx.x] + k;
@@ -91,18 +141,19 @@ __device__ __forceinline__ int item_of_round(const Params& p, int k) {
     }
     const int n_items = p.n_items;
     const int G = (int)gridDim.x, c = (int)blockIdx.x;
-    if (k * G >= n_items) return -1;
+    if ((int64_t)k * G >= n_items) return -1;
     const int L = k * G + ((k & 1) ? G - 1 - c : c);
     return L < n_items ? L : -1;
 }
 
-struct Item {
-    int b, q_tile, variant, h, kvs, kve, first_tile, n_tiles;
-};
-
 template <bool CAUSAL>
 __device__ __forceinline__ Item decode_item(const Params& p, int L) {
     Item it;
+    if (L < 0) {                                                     // end marker: b < 0 and n_tiles < 0
+        it.b = it.n_tiles = -1;
+        it.q_tile = it.variant = it.h = it.kvs = it.kve = it.first_tile = 0;
+        return it;
+    }
     const int per_group = p.head_group * p.n_work;
     const int g = L / per_group;
     const int rem = L - g * per_group;
@@ -121,29 +172,26 @@ __device__ __forceinline__ Item decode_item(const Params& p, int L) {
     return it;
 }
 
-// scores of one row (128 columns at TMEM `ts`) -> registers; returns the row maximum.
-// MASK: keys outside [kvs, min(kve-1, qi)] become -inf.  The test is classified per 32-column chunk with warp votes: a
-// chunk in which every lane sees all 32 keys needs no work, a chunk no lane sees is set to -inf wholesale, only the
-// rest is tested element-wise -- on the causal diagonal tile that is one chunk of four per warp.
+__device__ __forceinline__ Item load_item(const Item* tab, int k) {
+    const int4 a = reinterpret_cast<const int4*>(tab + k)[0], b = reinterpret_cast<const int4*>(tab + k)[1];
+    Item it;
+    it.b = a.x; it.q_tile = a.y; it.variant = a.z; it.h = a.w;
+    it.kvs = b.x; it.kve = b.y; it.first_tile = b.z; it.n_tiles = b.w;
+    return it;
+}
+
+// row maximum of the 128 scores in v.  MASK: keys outside [kvs, min(kve-1, qi)] become -inf first.  The test is
+// classified per 32-column chunk with a warp vote: a chunk in which every lane sees all 32 keys needs no work, the rest
+// is tested element-wise (a third, "set the chunk to -inf wholesale" variant made ptxas spill the score registers).
 template <bool MASK, bool CAUSAL>
-__device__ __forceinline__ float load_max(uint32_t ts, uint32_t (&v)[128], int kv0, int qi, int kvs, int kve) {
-    tmem_ld32(ts, v);
-    tmem_ld32(ts + 32, v + 32);
-    tmem_ld32(ts + 64, v + 64);
-    tmem_ld32(ts + 96, v + 96);
-    tc_wait_ld();
+__device__ __forceinline__ float mask_max(uint32_t (&v)[128], int kv0, int qi, int kvs, int kve) {
     if (MASK) {
         const int hi_key = CAUSAL ? min(qi, kve - 1) : kve - 1;      // last visible key of this row
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const int lo = kvs - (kv0 + 32 * c), hi = hi_key - (kv0 + 32 * c);      // visible columns of the chunk: [lo, hi]
-            const bool full = lo <= 0 && hi >= 31, none = hi < 0 || lo > 31 || hi < lo;
+            const bool full = lo <= 0 && hi >= 31;
             if (__all_sync(0xffffffffu, full)) continue;
-            if (__all_sync(0xffffffffu, none)) {
-#pragma unroll
-                for (int e = 0; e < 32; ++e) v[32 * c + e] = 0xff800000u;
-                continue;
-            }
 #pragma unroll
             for (int e = 0; e < 32; ++e) v[32 * c + e] = (e >= lo && e <= hi) ? v[32 * c + e] : 0xff800000u;
         }
@@ -159,10 +207,10 @@ __device__ __forceinline__ float load_max(uint32_t ts, uint32_t (&v)[128], int k
     return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
 }
 
-// P = 2^(S*sl2 - m_off), packed to bf16 over the first 64 columns of the S buffer; one exponential in every POLY runs
-// on the FMA pipes (poly_ex2), 0 = all on the SFU.  Returns the row sum.
+// P = 2^(S*sl2 - m_off), packed to bf16 into the 64 columns at TMEM `tp`; one exponential in every POLY runs on the FMA
+// pipes (poly_ex2), 0 = all on the SFU.  Returns the row sum.
 template <int POLY>
-__device__ __forceinline__ float exp_store(uint32_t ts, uint32_t (&v)[128], float sl2, float m_off) {
+__device__ __forceinline__ float exp_store(uint32_t tp, uint32_t (&v)[128], float sl2, float m_off) {
     float l0 = 0.f, l1 = 0.f;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -175,12 +223,12 @@ __device__ __forceinline__ float exp_store(uint32_t ts, uint32_t (&v)[128], floa
             l1 += p1;
             v[j >> 1] = pack_bf16(p0, p1);
         }
-        tmem_st16(ts + c * 16, v + c * 16);
+        tmem_st16(tp + c * 16, v + c * 16);
     }
     return l0 + l1;
 }
 
-template <int D, bool CAUSAL, int POLY>
+template <int D, bool CAUSAL, int POLY, bool TRACE>
 __global__ void __launch_bounds__(THREADS, 1)
 attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
                        const __grid_constant__ CUtensorMap tmV0, const __grid_constant__ CUtensorMap tmK1,
@@ -188,31 +236,39 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     using S = Smem<D>;
-    float* m_sh = reinterpret_cast<float*>(smem + S::STAT_OFF);       // [2][128]
-    float* l_sh = m_sh + 256;                                         // [2][2][128]
+    Item* items = reinterpret_cast<Item*>(smem + S::ITEM_OFF);
+    float* m_sh = reinterpret_cast<float*>(smem + S::M_OFF);          // [2][128]
+    float* dep_sh = reinterpret_cast<float*>(smem + S::DEP_OFF);      // [DEP][2][2][128]
+    volatile int* epi_done = reinterpret_cast<volatile int*>(smem + S::DONE_OFF);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
 
     const int warp = threadIdx.x >> 5;
     const long long t_entry = p.cta_log ? clock64() : 0;
     const int T = p.seqlen;
-    constexpr uint32_t TMEM_COLS = 512, COL_O = 384;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < B_COUNT; ++i) {
-            const bool wg = (i >= B_PFULL && i < B_PFULL + 3) || i >= B_MPUB;
-            mbar_init(bars + i, wg ? 128 : (i == B_OFREE ? 256 : 1));
+            int count = 1;
+            if ((i >= B_SFREE && i < B_PFREE) || i == B_OFREE || (i >= B_MPUB && i < B_MPUB + 2)) count = 128;
+            if (i >= B_LDEP) count = 256;
+            mbar_init(bars + i, count);
         }
         fence_barrier_init();
     }
-    if (warp == WARP_TMA && elect_one()) {
+    if (threadIdx.x < 128) epi_done[threadIdx.x] = 0;
+    // the CTA's items, decoded once (every role walks this table; an entry with b < 0 ends it)
+    for (int k = threadIdx.x; k <= MAX_ITEMS; k += THREADS) items[k] = decode_item<CAUSAL>(p, item_of_round(p, k));
+    if (warp == WARP_KLOAD && elect_one()) {
         tma_prefetch_desc(&tmQ);
         tma_prefetch_desc(&tmK0);
-        tma_prefetch_desc(&tmV0);
         tma_prefetch_desc(&tmK1);
+    }
+    if (warp == WARP_VLOAD && elect_one()) {
+        tma_prefetch_desc(&tmV0);
         tma_prefetch_desc(&tmV1);
     }
-    if (warp == WARP_MMA) {
+    if (warp == WARP_QK) {
         tmem_alloc(tmem_slot, TMEM_COLS);
         tmem_relinquish();
     }
@@ -220,171 +276,300 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
-    // register budget: the softmax warpgroups hold 128 scores per thread, the producer warpgroup needs almost nothing.
+
+    // register budget: the softmax warpgroups hold 128 scores per thread, the others need almost nothing.
     // (setmaxnreg sits at the top of each role's own branch so that ptxas budgets the branch with it.)
-    if (warp >= 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PRODUCER));
-    if (warp == WARP_TMA) {
-        // ------------------------------------------------------------ TMA producer (runs ahead across items)
-        if (elect_one()) {
-            uint32_t kl = 0, vl = 0, ic = 0;                          // K / V tiles loaded, items started
-            for (int k = 0;; ++k) {
-                const int L = item_of_round(p, k);
-                if (L < 0) break;
-                const Item it = decode_item<CAUSAL>(p, L);
-                const int n = it.n_tiles;
-                if (n > 0) {
+    if (warp >= 8 && warp < 12) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PRODUCER));
+        const uint32_t bar0 = smem_u32(bars);                         // barrier i lives at bar0 + 8 i
+        if (warp == WARP_KLOAD) {
+            // ------------------------------------------------------------ TMA producer for Q and K (runs ahead across items)
+            if (elect_one()) {
+                uint32_t G = 0, iq = 0;                               // K tiles loaded, items with tiles started
+                for (int k = 0;; ++k) {
+                    const Item it = load_item(items, k);
+                    if (it.b < 0) break;
+                    if (it.n_tiles == 0) continue;
                     const CUtensorMap* tK = it.variant ? &tmK1 : &tmK0;
-                    const CUtensorMap* tV = it.variant ? &tmV1 : &tmV0;
-                    auto load_k = [&](int j) {
-                        const uint32_t s = kl % KST;
-                        mbar_wait(bars + B_KEMPTY + s, ((kl / KST) & 1u) ^ 1u);
+                    const uint32_t qb = iq & 1u;
+                    wait_bar(bar0 + 8 * (B_QEMPTY + qb), ((iq >> 1) & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(bars + B_QFULL + qb, S::TILE);
+#pragma unroll
+                    for (int c = 0; c < D / 64; ++c)
+                        tma_load_2d(smem + S::Q_OFF + qb * S::TILE + c * (BM * 128), &tmQ, bars + B_QFULL + qb, it.h * D + c * 64,
+                                    it.b * T + it.q_tile * BM);
+                    ++iq;
+                    for (int j = 0; j < it.n_tiles; ++j, ++G) {
+                        const uint32_t s = G & 1u;                    // free again once QK(G-2) retired: that is SFULL's phase
+                        wait_bar(bar0 + 8 * (B_SFULL + s), ((G >> 1) & 1u) ^ 1u);
                         mbar_arrive_expect_tx(bars + B_KFULL + s, S::TILE);
 #pragma unroll
                         for (int c = 0; c < D / 64; ++c)
                             tma_load_2d(smem + S::K_OFF + s * S::TILE + c * (BN * 128), tK, bars + B_KFULL + s, it.h * D + c * 64,
                                         it.b * T + (it.first_tile + j) * BN);
-                        ++kl;
-                    };
-                    mbar_wait(bars + B_QEMPTY, (ic & 1u) ^ 1u);
-                    mbar_arrive_expect_tx(bars + B_QFULL, S::TILE);
-#pragma unroll
-                    for (int c = 0; c < D / 64; ++c)
-                        tma_load_2d(smem + S::Q_OFF + c * (BM * 128), &tmQ, bars + B_QFULL, it.h * D + c * 64, it.b * T + it.q_tile * BM);
-                    for (int j = 0; j < 3 && j < n; ++j) load_k(j);
-                    for (int j = 0; j < n; ++j) {
-                        const uint32_t s = vl % VST;
-                        mbar_wait(bars + B_VEMPTY + s, ((vl / VST) & 1u) ^ 1u);
+                    }
+                }
+            }
+        } else if (warp == WARP_VLOAD) {
+            // ------------------------------------------------------------ TMA producer for V
+            if (elect_one()) {
+                uint32_t G = 0;
+                for (int k = 0;; ++k) {
+                    const Item it = load_item(items, k);
+                    if (it.b < 0) break;
+                    const CUtensorMap* tV = it.variant ? &tmV1 : &tmV0;
+                    for (int j = 0; j < it.n_tiles; ++j, ++G) {
+                        const uint32_t s = G & 1u;                    // free again once PV(G-2) retired: that is PFREE's phase
+                        wait_bar(bar0 + 8 * (B_PFREE + s), ((G >> 1) & 1u) ^ 1u);
                         mbar_arrive_expect_tx(bars + B_VFULL + s, S::TILE);
 #pragma unroll
                         for (int c = 0; c < D / 64; ++c)
                             tma_load_2d(smem + S::V_OFF + s * S::TILE + c * (BN * 128), tV, bars + B_VFULL + s, it.h * D + c * 64,
                                         it.b * T + (it.first_tile + j) * BN);
-                        ++vl;
-                        if (j + 3 < n) load_k(j + 3);
                     }
-                    ++ic;                                            // items with n == 0 use no Q slot
                 }
             }
-        }
-    } else if (warp == WARP_MMA) {
-        // ------------------------------------------------------------ tcgen05 issuer: three score tiles ahead of the softmax
-        if (elect_one()) {
-            constexpr uint32_t idesc_qk = make_idesc_bf16(BM, BN, 0, 0);
-            constexpr uint32_t idesc_pv = make_idesc_bf16(BM, D, 0, 1);
-            const uint32_t dQ = desc_lo_kmajor(smem_u32(smem + S::Q_OFF));
-            const uint32_t dK0 = desc_lo_kmajor(smem_u32(smem + S::K_OFF));
-            const uint32_t dV0 = desc_lo_mnmajor(smem_u32(smem + S::V_OFF), BN * 128);
-            uint32_t g = 0, kc = 0, vc = 0, ic = 0, iq = 0;          // tiles, K / V tiles consumed, items, items with tiles
-            bool logged = false;
-            auto issue_qk = [&](uint32_t G, bool last_of_item) {      // S[G%3] = Q . K^T
-                const uint32_t s = kc % KST;
-                mbar_wait(bars + B_KFULL + s, (kc / KST) & 1u);
-                tc_fence_after_sync();
-                const uint32_t dK = dK0 + s * (uint32_t)(S::TILE >> 4);
-                const uint32_t d_s = tmem_base + (G % 3) * 128;
-#pragma unroll
-                for (int kk = 0; kk < D / 16; ++kk) {
-                    const uint32_t off = ((uint32_t)(kk / 4) * (BM * 128) + (uint32_t)(kk % 4) * 32) >> 4;
-                    umma_ss_lo(d_s, dQ + off, dK + off, idesc_qk, kk ? 1u : 0u);
-                }
-                tc_commit(bars + B_SFULL + G % 3);
-                tc_commit(bars + B_KEMPTY + s);
-                if (last_of_item) tc_commit(bars + B_QEMPTY);        // Q may be replaced by the next item's
-                ++kc;
-            };
-            for (int k = 0;; ++k) {
-                const int L = item_of_round(p, k);
-                if (L < 0) break;
-                const Item it = decode_item<CAUSAL>(p, L);
-                const int n = it.n_tiles;
-                if (n > 0) {
-                    mbar_wait(bars + B_QFULL, iq & 1u);
-                    if (p.cta_log && !logged) {
-                        p.cta_log[(int64_t)blockIdx.x * 8 + 4] = clock64();
-                        logged = true;
-                    }
-                    for (int j = 0; j < 3 && j < n; ++j) issue_qk(g + j, j == n - 1);      // overlaps the previous epilogue
-                    for (int j = 0; j < n; ++j) {
-                        const uint32_t G = g + j;
-                        FS_TRACE(0, G);                                  // MMA: start waiting for P
-                        mbar_wait(bars + B_PFULL + G % 3, (G / 3) & 1u);
-                        FS_TRACE(1, G);                                  // MMA: P seen
-                        if (j == 0 && ic > 0) mbar_wait(bars + B_OFREE, (ic - 1) & 1u);    // previous epilogue has read O
-                        const uint32_t s = vc % VST;
-                        mbar_wait(bars + B_VFULL + s, (vc / VST) & 1u);
-                        tc_fence_after_sync();
-                        const uint32_t dV = dV0 + s * (uint32_t)(S::TILE >> 4);
-                        const uint32_t a_p = tmem_base + (G % 3) * 128;
-#pragma unroll
-                        for (int kk = 0; kk < BN / 16; ++kk) {
-                            // A = P in TMEM: keys 16kk.. at column 8kk of the S buffer; B = V as MN-major (16 key rows = 2048 B)
-                            umma_ts_lo(tmem_base + COL_O, a_p + (uint32_t)kk * 8, dV + (uint32_t)kk * (2048 >> 4), idesc_pv,
-                                       (j | kk) ? 1u : 0u);
+        } else if (warp == WARP_QK) {
+            // ------------------------------------------------------------ tcgen05 issuer 1: S = Q . K^T, two tiles ahead of PV.
+            // Everything an issuing thread executes between two batches of MMAs is serial latency on the tensor pipe's
+            // critical path (a dependent instruction every ~5 clk; measured ~2100 clk per tile with ONE thread running a
+            // general two-cursor loop for both products).  So QK^T and PV have their own issuing threads (the hardware
+            // orders them through the barriers they already wait on), each loop is unrolled over the slot bit G & 1 --
+            // barrier addresses, TMEM columns and K / V descriptors become constants -- and the items are reduced to their
+            // tile counts.
+            if (elect_one()) {
+                constexpr uint32_t idesc_qk = make_idesc_bf16(BM, BN, 0, 0);
+                constexpr uint32_t TILE16 = (uint32_t)(S::TILE >> 4);
+                const uint32_t dQ0 = desc_lo_kmajor(smem_u32(smem + S::Q_OFF));
+                const uint32_t dK0 = desc_lo_kmajor(smem_u32(smem + S::K_OFF));
+                const int* ntile = &items[0].n_tiles;                 // stride 8 ints
+                int k = 0;
+                auto next_count = [&]() {                             // tiles of the next item that has any; -1 at the end
+                    int n;
+                    do {
+                        n = ntile[8 * k];
+                        ++k;
+                    } while (n == 0);
+                    return n;
+                };
+                int left = next_count();
+                bool first = true, logged = false;
+                uint32_t iq = 0, qph0 = 0, qph1 = 0, dQ = dQ0, Gq = 0;   // items started; phase parity of each slot's next use
+                auto do_qk = [&](const uint32_t b, uint32_t& qph, const bool wait_sfree) {     // S[b] = Q . K(Gq)^T, b == Gq & 1
+                    FS_TRACE(0, Gq);                                  // QK: start waiting for the S buffer
+                    if (wait_sfree) wait_bar(bar0 + 8 * (B_SFREE + b), qph ^ 1u);             // S(Gq-2) is in registers
+                    FS_TRACE(1, Gq);                                  // QK: S buffer free
+                    if (first) {
+                        const uint32_t qb = iq & 1u;
+                        wait_bar(bar0 + 8 * (B_QFULL + qb), (iq >> 1) & 1u);
+                        dQ = dQ0 + qb * TILE16;
+                        if (p.cta_log && !logged) {
+                            p.cta_log[(int64_t)blockIdx.x * 8 + 4] = clock64();
+                            logged = true;
                         }
-                        tc_commit(bars + B_OREADY + (G & 1u));
-                        tc_commit(bars + B_VEMPTY + s);
-                        ++vc;
-                        if (j + 3 < n) issue_qk(G + 3, j + 3 == n - 1);
-                        FS_TRACE(2, G);                                  // MMA: PV + QK(+3) issued
                     }
-                    ++iq;
-                } else if (ic > 0) {
-                    mbar_wait(bars + B_OFREE, (ic - 1) & 1u);        // keep the per-item waits consecutive
+                    wait_bar(bar0 + 8 * (B_KFULL + b), qph);
+                    tc_fence_after_sync();
+                    FS_TRACE(2, Gq);                                  // QK: Q, K landed
+                    const uint32_t dK = dK0 + b * TILE16;
+                    const uint32_t d_s = tmem_base + b * 128;
+#pragma unroll
+                    for (int kk = 0; kk < D / 16; ++kk) {
+                        const uint32_t off = ((uint32_t)(kk / 4) * (BM * 128) + (uint32_t)(kk % 4) * 32) >> 4;
+                        umma_ss_lo(d_s, dQ + off, dK + off, idesc_qk, kk ? 1u : 0u);
+                    }
+                    FS_TRACE(3, Gq);                                  // QK: issued
+                    commit_bar(bar0 + 8 * (B_SFULL + b));             // scores landed; K slot b free
+                    qph ^= 1u;
+                    first = false;
+                    if (--left == 0) {                                // Q buffer may be replaced by the item after next
+                        commit_bar(bar0 + 8 * (B_QEMPTY + (iq & 1u)));
+                        ++iq;
+                        left = next_count();
+                        first = true;
+                    }
+                    FS_TRACE(4, Gq);                                  // QK: committed
+                    ++Gq;
+                };
+                if (left > 0) do_qk(0u, qph0, false);                 // QK(0), QK(1): both S buffers start out free
+                if (left > 0) do_qk(1u, qph1, false);
+                while (left > 0) {
+                    do_qk(0u, qph0, true);
+                    if (left <= 0) break;
+                    do_qk(1u, qph1, true);
                 }
-                tc_commit(bars + B_OFINAL);
-                g += (uint32_t)n;
-                ++ic;
+            }
+        } else if (warp == WARP_PV) {
+            // ------------------------------------------------------------ tcgen05 issuer 2: O (+)= P . V
+            if (elect_one()) {
+                constexpr uint32_t idesc_pv = make_idesc_bf16(BM, D, 0, 1);
+                constexpr uint32_t TILE16 = (uint32_t)(S::TILE >> 4);
+                const uint32_t dV0 = desc_lo_mnmajor(smem_u32(smem + S::V_OFF), BN * 128);
+                const int* ntile = &items[0].n_tiles;
+                int k = 0;
+                auto next_count = [&]() {
+                    int n;
+                    do {
+                        n = ntile[8 * k];
+                        ++k;
+                    } while (n == 0);
+                    return n;
+                };
+                int left = next_count();
+                bool first = true;
+                uint32_t ic = 0, pph0 = 0, pph1 = 0, Gp = 0;          // items (with tiles) started
+                auto do_pv = [&](const uint32_t b, uint32_t& pph) {   // O (+)= P[b] . V(Gp), b == Gp & 1
+                    FS_TRACE(5, Gp);                                  // PV: start waiting for P
+                    wait_bar(bar0 + 8 * (B_PFULL + b), pph);
+                    FS_TRACE(6, Gp);                                  // PV: P seen
+                    if (first && ic > 0) wait_bar(bar0 + 8 * B_OFREE, (ic - 1) & 1u);        // previous epilogue has read O
+                    wait_bar(bar0 + 8 * (B_VFULL + b), pph);
+                    tc_fence_after_sync();
+                    FS_TRACE(7, Gp);                                  // PV: O free, V landed
+                    const uint32_t dV = dV0 + b * TILE16;
+                    const uint32_t a_p = tmem_base + COL_P + b * 64;
+                    const uint32_t acc0 = first ? 0u : 1u;
+#pragma unroll
+                    for (int kk = 0; kk < BN / 16; ++kk) {
+                        // A = P in TMEM: keys 16kk.. at column 8kk of the P buffer; B = V as MN-major (16 key rows = 2048 B)
+                        umma_ts_lo(tmem_base + COL_O, a_p + (uint32_t)kk * 8, dV + (uint32_t)kk * (2048 >> 4), idesc_pv,
+                                   kk ? 1u : acc0);
+                    }
+                    FS_TRACE(8, Gp);                                  // PV: issued
+                    commit_bar(bar0 + 8 * (B_PFREE + b));             // P[b], V slot b free; O holds tile Gp
+                    pph ^= 1u;
+                    first = false;
+                    if (--left == 0) {
+                        commit_bar(bar0 + 8 * B_OFINAL);
+                        ++ic;
+                        left = next_count();
+                        first = true;
+                    }
+                    FS_TRACE(9, Gp);                                  // PV: committed
+                    ++Gp;
+                };
+                while (left > 0) {
+                    do_pv(0u, pph0);
+                    if (left <= 0) break;
+                    do_pv(1u, pph1);
+                }
             }
         }
-    }
-    } else {
-        // ------------------------------------------------------------ softmax warpgroups: alternate kv tiles, shared running max
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_SOFTMAX));
-        const int w = warp >> 2;                                  // warpgroup = parity of the kv tiles it takes
+    } else if (warp >= WARP_EPI0) {
+        // ------------------------------------------------------------ epilogue warpgroup: O / l -> global, LSE
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_EPILOGUE));
         const int r = (warp & 3) * 32 + (threadIdx.x & 31);       // query row in tile == TMEM lane
         const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        constexpr int DH = D / 2;
         const float sl2 = p.scale * LOG2E;
-        uint32_t g = 0, ic = 0, mpc0 = 0, mpc1 = 0;               // tiles / items so far, completions of MPUB[0], MPUB[1]
-        for (int k = 0;; ++k) {
-            const int L = item_of_round(p, k);
-            if (L < 0) break;
-            const Item it = decode_item<CAUSAL>(p, L);
+        uint32_t ne = 0;                                          // items with tiles so far (phase of OFINAL / OFREE)
+        for (uint32_t ic = 0;; ++ic) {
+            const Item it = load_item(items, (int)ic);
+            if (it.b < 0) break;
+            const int qi = it.q_tile * BM + r;
+            const int64_t bt = (int64_t)it.b * T + qi;
+            const bool row_ok = (qi < T) && (!p.qflag || (int)p.qflag[bt] == it.variant);
+            const int64_t dst = row_ok ? (p.out_row ? (int64_t)p.out_row[bt] : bt) : 0;
+            const uint32_t slot = ic % DEP;
+            mbar_wait(bars + B_LDEP + slot, (ic / DEP) & 1u);
+            const float* d = dep_sh + slot * 512;
+            const float m0 = d[r], l0 = d[128 + r], m1 = d[256 + r], l1 = d[384 + r];
+            __threadfence_block();
+            epi_done[r] = (int)ic + 1;                            // row r of this slot may be overwritten (item ic + DEP)
+            // the last reference maximum is the larger of the two (references only grow); O is relative to it
+            const float m_fin = fmaxf(m0, m1);
+            const float a0 = (m0 == -CUDART_INF_F) ? 0.f : l0 * fast_ex2((m0 - m_fin) * sl2);
+            const float a1 = (m1 == -CUDART_INF_F) ? 0.f : l1 * fast_ex2((m1 - m_fin) * sl2);
+            const float l_tot = a0 + a1;
+            const float inv_l = l_tot > 0.f ? 1.f / l_tot : 0.f;
+            if (it.n_tiles > 0) {
+                mbar_wait(bars + B_OFINAL, ne & 1u);
+                tc_fence_after_sync();
+            }
+            __nv_bfloat16* orow = p.O + dst * ((int64_t)p.heads * D) + (int64_t)it.h * D;
+#pragma unroll 1
+            for (int c = 0; c < D / 16; ++c) {
+                uint32_t v[16];
+                if (it.n_tiles > 0) {
+                    tmem_ld16(lane_addr + COL_O + c * 16, v);
+                    tc_wait_ld();
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] = 0u;
+                }
+                if (row_ok) {
+#pragma unroll
+                    for (int e = 0; e < 16; e += 8) {
+                        uint4 o;
+                        o.x = pack_bf16(__uint_as_float(v[e + 0]) * inv_l, __uint_as_float(v[e + 1]) * inv_l);
+                        o.y = pack_bf16(__uint_as_float(v[e + 2]) * inv_l, __uint_as_float(v[e + 3]) * inv_l);
+                        o.z = pack_bf16(__uint_as_float(v[e + 4]) * inv_l, __uint_as_float(v[e + 5]) * inv_l);
+                        o.w = pack_bf16(__uint_as_float(v[e + 6]) * inv_l, __uint_as_float(v[e + 7]) * inv_l);
+                        *reinterpret_cast<uint4*>(orow + c * 16 + e) = o;
+                    }
+                }
+                __syncwarp();
+            }
+            if (it.n_tiles > 0) {
+                tc_fence_before_sync();
+                mbar_arrive(bars + B_OFREE);                      // O may be overwritten by the next item
+                ++ne;
+            }
+            if (row_ok && p.lse) {
+                // natural-log LSE of the scaled scores; +inf marks a row with no visible key (P == 0 in backward)
+                p.lse[((int64_t)it.b * p.heads + it.h) * T + qi] = l_tot > 0.f ? (m_fin * p.scale + __logf(l_tot)) : CUDART_INF_F;
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ softmax warpgroups: alternate tiles of the CTA's tile stream
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_SOFTMAX));
+        const int w = warp >> 2;                                  // warpgroup = parity of the global tile indices it takes
+        const int r = (warp & 3) * 32 + (threadIdx.x & 31);       // query row in tile == TMEM lane
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        const float sl2 = p.scale * LOG2E;
+        uint32_t g = 0;                                           // tiles of the items before this one
+        for (uint32_t ic = 0;; ++ic) {
+            const Item it = load_item(items, (int)ic);
+            if (it.b < 0) break;
             const int n = it.n_tiles;
             const int q0 = it.q_tile * BM, qi = q0 + r;
             float m_ref = -CUDART_INF_F, l = 0.f;                 // l is relative to m_ref
-            // destination of my row: loaded now, used by the epilogue (keeps two dependent global loads off its path)
-            const int64_t bt = (int64_t)it.b * T + qi;
-            const bool row_ok = (qi < T) && (!p.qflag || (int)p.qflag[qi < T ? bt : 0] == it.variant);
-            const int64_t dst = row_ok ? (p.out_row ? (int64_t)p.out_row[bt] : bt) : 0;
-            for (int j = w; j < n; j += 2) {
+            for (int j = (int)((g & 1u) ^ (uint32_t)w); j < n; j += 2) {
                 const uint32_t G = g + (uint32_t)j;
-                const uint32_t colS = (G % 3) * 128;
+                const uint32_t colS = (G & 1u) * 128;
                 const int kv0 = (it.first_tile + j) * BN;
                 const bool need_mask = (CAUSAL && kv0 + BN - 1 > q0) || (kv0 + BN > it.kve) || (kv0 < it.kvs);
-                if ((threadIdx.x & 127) == 0) FS_TRACE(3, G);         // softmax: start waiting for S
-                mbar_wait(bars + B_SFULL + G % 3, (G / 3) & 1u);
+                if ((threadIdx.x & 127) == 0) FS_TRACE(10, G);        // softmax: start waiting for S
+                mbar_wait(bars + B_SFULL + (G & 1u), (G >> 1) & 1u);
                 tc_fence_after_sync();
-                if ((threadIdx.x & 127) == 0) FS_TRACE(4, G);         // softmax: S seen
+                if ((threadIdx.x & 127) == 0) FS_TRACE(11, G);        // softmax: S seen
                 uint32_t sv[128];
-                const float mx = need_mask ? load_max<true, CAUSAL>(lane_addr + colS, sv, kv0, qi, it.kvs, it.kve)
-                                           : load_max<false, CAUSAL>(lane_addr + colS, sv, kv0, qi, it.kvs, it.kve);
-                // ---- running max of the row after tile j-1 (the other warpgroup's tile)
+                tmem_ld32(lane_addr + colS, sv);
+                tmem_ld32(lane_addr + colS + 32, sv + 32);
+                tmem_ld32(lane_addr + colS + 64, sv + 64);
+                tmem_ld32(lane_addr + colS + 96, sv + 96);
+                tc_wait_ld();
+                if ((threadIdx.x & 127) == 0) FS_TRACE(12, G);        // softmax: scores in registers
+                tc_fence_before_sync();
+                mbar_arrive(bars + B_SFREE + (G & 1u));               // S(G) is in registers: QK(G+2) may overwrite the buffer
+                const float mx = need_mask ? mask_max<true, CAUSAL>(sv, kv0, qi, it.kvs, it.kve)
+                                           : mask_max<false, CAUSAL>(sv, kv0, qi, it.kvs, it.kve);
+                if ((threadIdx.x & 127) == 0) FS_TRACE(13, G);        // softmax: max done
+                // ---- running max of the row after the previous tile of the stream (the other warpgroup's).  Every tile waits
+                // for its predecessor's publication, also across items (value unused then): that keeps the two m_sh slots and
+                // the two barriers strictly alternating.
+                if (G > 0) mbar_wait(bars + B_MPUB + ((G - 1) & 1u), ((G - 1) >> 1) & 1u);
+                if ((threadIdx.x & 127) == 0) FS_TRACE(14, G);        // softmax: previous tile's max seen
                 float m_cur;
-                if ((threadIdx.x & 127) == 0) FS_TRACE(5, G);         // softmax: scores loaded, max done
                 if (j == 0) {
                     m_cur = mx;
                 } else {
-                    const int pb = (j - 1) & 1;
-                    mbar_wait(bars + B_MPUB + pb, ((pb ? mpc1 : mpc0) + (uint32_t)((j - 1) >> 1)) & 1u);
-                    const float m_prev = m_sh[pb * 128 + r];
+                    const float m_prev = m_sh[((G - 1) & 1u) * 128 + r];
                     const float m_new = fmaxf(m_prev, mx);
                     // lazy correction: rescale O only when the running max moved by more than 2^8
                     const bool grow = (m_new - m_prev) * sl2 > 8.f;       // also true when m_prev == -inf and m_new finite
                     m_cur = grow ? m_new : m_prev;
                     if (__any_sync(0xffffffffu, grow)) {
-                        mbar_wait(bars + B_OREADY + ((G - 1) & 1u), ((G - 1) >> 1) & 1u);   // PV of tile j-1 has landed in O
+                        mbar_wait(bars + B_PFREE + ((G - 1) & 1u), ((G - 1) >> 1) & 1u);   // PV of tile j-1 has landed in O
                         tc_fence_after_sync();
                         const float alpha = grow ? ((m_prev == -CUDART_INF_F) ? 0.f : fast_ex2((m_prev - m_new) * sl2)) : 1.f;
 #pragma unroll 1
@@ -399,97 +584,61 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                         tc_wait_st();
                     }
                 }
-                m_sh[(j & 1) * 128 + r] = m_cur;
-                mbar_arrive(bars + B_MPUB + (j & 1));
-                if ((threadIdx.x & 127) == 0) FS_TRACE(6, G);         // softmax: running max published
+                m_sh[(G & 1u) * 128 + r] = m_cur;
+                mbar_arrive(bars + B_MPUB + (G & 1u));
+                if ((threadIdx.x & 127) == 0) FS_TRACE(15, G);        // softmax: running max published
                 // ---- my partial row sum follows the reference maximum
                 if (m_ref != m_cur) {
                     l = (m_ref == -CUDART_INF_F) ? 0.f : l * fast_ex2((m_ref - m_cur) * sl2);
                     m_ref = m_cur;
                 }
                 const float m_off = (m_cur == -CUDART_INF_F) ? 0.f : m_cur * sl2;
-                l += exp_store<POLY>(lane_addr + colS, sv, sl2, m_off);
+                if (G >= 2) {                                         // PV(G-2) has consumed P[G & 1]
+                    mbar_wait(bars + B_PFREE + (G & 1u), ((G - 2) >> 1) & 1u);
+                    tc_fence_after_sync();
+                }
+                if ((threadIdx.x & 127) == 0) FS_TRACE(16, G);        // softmax: P buffer free
+                l += exp_store<POLY>(lane_addr + COL_P + (G & 1u) * 64, sv, sl2, m_off);
                 tc_wait_st();
                 tc_fence_before_sync();
-                mbar_arrive(bars + B_PFULL + G % 3);
-                if ((threadIdx.x & 127) == 0) FS_TRACE(7, G);         // softmax: P stored, arrived
+                mbar_arrive(bars + B_PFULL + (G & 1u));
+                if ((threadIdx.x & 127) == 0) FS_TRACE(17, G);        // softmax: P stored, arrived
             }
-            // ---- end of the item: final maximum, combine the two partial sums
-            float m_fin = -CUDART_INF_F;
-            if (n > 0) {
-                const int pb = (n - 1) & 1;
-                mbar_wait(bars + B_MPUB + pb, ((pb ? mpc1 : mpc0) + (uint32_t)((n - 1) >> 1)) & 1u);
-                m_fin = m_sh[pb * 128 + r];
-                if (m_ref != m_fin) l = (m_ref == -CUDART_INF_F) ? 0.f : l * fast_ex2((m_ref - m_fin) * sl2);
+            // ---- hand my (reference max, partial sum) of the item to the epilogue warpgroup; ring slot ic % DEP is free once
+            // the epilogue has read row r of item ic - DEP
+            while (epi_done[r] + DEP <= (int)ic) {
             }
-            float* lbuf = l_sh + (ic & 1u) * 256;
-            lbuf[w * 128 + r] = l;
-            named_bar_sync(1, 256);
-            const float l_tot = lbuf[r] + lbuf[128 + r];
-            mbar_wait(bars + B_OFINAL, ic & 1u);
-            tc_fence_after_sync();
-            const float inv_l = l_tot > 0.f ? 1.f / l_tot : 0.f;
-            __nv_bfloat16* orow = p.O + dst * ((int64_t)p.heads * D) + (int64_t)it.h * D + w * DH;
-#pragma unroll 1
-            for (int c = 0; c < DH / 32; ++c) {
-                uint32_t v[32];
-                if (n > 0) {
-                    tmem_ld32(lane_addr + COL_O + w * DH + c * 32, v);
-                    tc_wait_ld();
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) v[e] = 0u;
-                }
-                if (row_ok) {
-#pragma unroll
-                    for (int e = 0; e < 32; e += 8) {
-                        uint4 o;
-                        o.x = pack_bf16(__uint_as_float(v[e + 0]) * inv_l, __uint_as_float(v[e + 1]) * inv_l);
-                        o.y = pack_bf16(__uint_as_float(v[e + 2]) * inv_l, __uint_as_float(v[e + 3]) * inv_l);
-                        o.z = pack_bf16(__uint_as_float(v[e + 4]) * inv_l, __uint_as_float(v[e + 5]) * inv_l);
-                        o.w = pack_bf16(__uint_as_float(v[e + 6]) * inv_l, __uint_as_float(v[e + 7]) * inv_l);
-                        *reinterpret_cast<uint4*>(orow + c * 32 + e) = o;
-                    }
-                }
-                __syncwarp();
-            }
-            tc_fence_before_sync();
-            mbar_arrive(bars + B_OFREE);                          // O may be overwritten by the next item
-            if (row_ok && p.lse && w == 0) {
-                // natural-log LSE of the scaled scores; +inf marks a row with no visible key (P == 0 in backward)
-                p.lse[((int64_t)it.b * p.heads + it.h) * T + qi] = l_tot > 0.f ? (m_fin * p.scale + __logf(l_tot)) : CUDART_INF_F;
-            }
+            __threadfence_block();
+            float* d = dep_sh + (ic % DEP) * 512 + w * 256;
+            d[r] = m_ref;
+            d[128 + r] = l;
+            mbar_arrive(bars + B_LDEP + ic % DEP);
             g += (uint32_t)n;
-            mpc0 += (uint32_t)((n + 1) >> 1);
-            mpc1 += (uint32_t)(n >> 1);
-            ++ic;
         }
     }
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == WARP_MMA) {
+    if (warp == WARP_QK) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
     if (p.cta_log && threadIdx.x == 0) {
         unsigned smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        int items = 0, tiles = 0;
-        for (int k = 0;; ++k) {
-            const int L = item_of_round(p, k);
-            if (L < 0) break;
-            ++items;
-            tiles += decode_item<CAUSAL>(p, L).n_tiles;
+        int n_it = 0, tiles = 0;
+        for (int k = 0; k < MAX_ITEMS && items[k].b >= 0; ++k) {
+            ++n_it;
+            tiles += items[k].n_tiles;
         }
         long long* e = p.cta_log + (int64_t)blockIdx.x * 8;
-        e[0] = smid; e[1] = items; e[2] = tiles; e[3] = t_entry; e[5] = clock64();
+        e[0] = smid; e[1] = n_it; e[2] = tiles; e[3] = t_entry; e[5] = clock64();
     }
 }
 
-template <int D, bool CAUSAL, int POLY>
-static int launch_p(const CUtensorMap* tm, const Params& p, cudaStream_t st) {
+template <int D, bool CAUSAL, int POLY, bool TRACE>
+static int launch_t(const CUtensorMap* tm, const Params& p, cudaStream_t st) {
     using S = Smem<D>;
-    auto kern = attn_fwd_stream_kernel<D, CAUSAL, POLY>;
+    auto kern = attn_fwd_stream_kernel<D, CAUSAL, POLY, TRACE>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
@@ -498,6 +647,13 @@ static int launch_p(const CUtensorMap* tm, const Params& p, cudaStream_t st) {
     }
     kern<<<(unsigned)p.n_cta, THREADS, S::TOTAL, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], p);
     return check_launch("attn_fwd_stream");
+}
+
+template <int D, bool CAUSAL, int POLY>
+static int launch_p(const CUtensorMap* tm, const Params& p, cudaStream_t st) {
+    // the clock64 stamps are compiled into a separate instantiation (diagnostics; only the plain SFU variant has one)
+    if (POLY == 0 && p.trace) return launch_t<D, CAUSAL, 0, true>(tm, p, st);
+    return launch_t<D, CAUSAL, POLY, false>(tm, p, st);
 }
 
 // fraction of exponentials evaluated on the FMA pipes: 1/POLY (LB_STREAM_EXP_POLY=0|2|3|4 for experiments)
@@ -529,8 +685,8 @@ using namespace lb;
 static long long* g_stream_cta_log = nullptr;
 static long long* g_stream_trace = nullptr;
 
-/* diagnostics: CTA 0 of subsequent lb_attn_fwd_stream launches writes clock64 stamps into `buf` ([64][8] int64, device; one
- * row per kv tile: MMA wait-P / P seen / issued, softmax wait-S / S seen / max done / max published / P arrived). NULL = off */
+/* diagnostics: CTA 0 of subsequent lb_attn_fwd_stream launches writes clock64 stamps into `buf` ([64][32] int64, device; one
+ * row per kv tile; slots 0-9 tcgen05 thread, 10-17 softmax thread 0 of the tile's warpgroup, see FS_TRACE sites). NULL = off */
 extern "C" int lb_attn_fwd_stream_set_trace(void* buf) {
     g_stream_trace = (long long*)buf;
     return LB_OK;
@@ -543,16 +699,19 @@ extern "C" int lb_attn_fwd_stream_set_cta_log(void* buf) {
     return LB_OK;
 }
 
+extern "C" int lb_attn_fwd_stream_max_cta_items(void) { return fs::MAX_ITEMS; }
+
 extern "C" int lb_attn_fwd_stream(const void* Q, const void* K0, const void* V0, const void* K1, const void* V1,
                                   const uint8_t* qflag, const int32_t* work, int n_work, const int32_t* plan_items,
-                                  const int32_t* plan_off, int n_cta, int head_group, const int32_t* kv_start,
-                                  const int32_t* kv_end, const int32_t* out_row, void* O, float* lse, int batch, int seqlen,
-                                  int heads, int head_dim, int causal, float scale, void* stream) {
+                                  const int32_t* plan_off, int n_cta, int max_cta_items, int head_group,
+                                  const int32_t* kv_start, const int32_t* kv_end, const int32_t* out_row, void* O, float* lse,
+                                  int batch, int seqlen, int heads, int head_dim, int causal, float scale, void* stream) {
     LB_REQUIRE(batch > 0 && seqlen > 0 && heads > 0 && n_work >= 0, LB_EINVAL, "attn_fwd_stream: bad shape");
     LB_REQUIRE(head_dim == 64 || head_dim == 128, LB_EINVAL, "attn_fwd_stream: head_dim %d (64 or 128 supported)", head_dim);
     LB_REQUIRE(Q && K0 && V0 && O && work, LB_EINVAL, "attn_fwd_stream: null argument");
     LB_REQUIRE((plan_items == nullptr) == (plan_off == nullptr), LB_EINVAL, "attn_fwd_stream: plan_items and plan_off go together");
-    LB_REQUIRE(!plan_items || n_cta > 0, LB_EINVAL, "attn_fwd_stream: n_cta %d with a plan", n_cta);
+    LB_REQUIRE(!plan_items || (n_cta > 0 && max_cta_items > 0), LB_EINVAL,
+               "attn_fwd_stream: a plan needs n_cta (%d) and max_cta_items (%d)", n_cta, max_cta_items);
     LB_REQUIRE(((uintptr_t)O & 15) == 0, LB_EALIGN, "attn_fwd_stream: O must be 16-byte aligned");
     if (n_work == 0) return LB_OK;
     int rc = require_sm100();
@@ -569,13 +728,19 @@ extern "C" int lb_attn_fwd_stream(const void* Q, const void* K0, const void* V0,
     p.O = (__nv_bfloat16*)O; p.lse = lse; p.batch = batch; p.seqlen = seqlen; p.heads = heads; p.scale = scale;
     p.n_work = n_work; p.head_group = head_group > 0 ? head_group : attn_head_group(); p.n_items = n_work * heads;
     p.plan_items = plan_items; p.plan_off = plan_off;
+    int per_cta;
     if (plan_items) {
         p.n_cta = n_cta;
+        per_cta = max_cta_items;
     } else {
         const int sms = sm_count();
         if (sms <= 0) return fail(LB_ELAUNCH, "attn_fwd_stream: no SM count");
         p.n_cta = p.n_items < sms ? p.n_items : sms;
+        per_cta = (p.n_items + p.n_cta - 1) / p.n_cta;
     }
+    LB_REQUIRE(per_cta <= fs::MAX_ITEMS, LB_EINVAL,
+               "attn_fwd_stream: %d items per CTA exceed the in-kernel table (%d); use lb_attn_fwd for this shape", per_cta,
+               fs::MAX_ITEMS);
     p.cta_log = g_stream_cta_log;
     p.trace = g_stream_trace;
     cudaStream_t st = (cudaStream_t)stream;

@@ -285,8 +285,8 @@ def attn_fwd(Q, K0, V0, K1, V1, qflag, work, kv_start, kv_end, out_row, batch, s
     tail = (_p(kv_start), _p(kv_end), _p(out_row), _p(out), _p(lse), batch, seqlen, heads, head_dim, int(causal), float(scale), _st())
     head = (_p(Q), _p(K0), _p(V0), _p(K1), _p(V1), _p(qflag), _p(work), work.shape[0])
     if kernel == "stream":
-        items, off, n_cta = plan if plan is not None else (None, None, 0)
-        _timed_call("lb_attn_fwd_stream", *head, _p(items), _p(off), n_cta, STREAM_HEAD_GROUP, *tail)
+        items, off, n_cta, max_items = plan if plan is not None else (None, None, 0, 0)
+        _timed_call("lb_attn_fwd_stream", *head, _p(items), _p(off), n_cta, max_items, STREAM_HEAD_GROUP, *tail)
     else:
         _timed_call({"single": "lb_attn_fwd", "pair": "lb_attn_fwd_pair"}[kernel], *head, *tail)
     return out, lse

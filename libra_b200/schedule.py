@@ -57,8 +57,8 @@ class AttnWork:
         """Balanced split of the (work item, head) list over n_cta persistent CTAs (lb_attn_fwd_stream).
         Head groups are dealt in order (the K/V of one group stay L2-resident); inside a group the items go heaviest
         first to the least-loaded CTA, the load carried over from group to group.  weight = kv tiles + `overhead`
-        (per-item prologue/epilogue in tile units).  Returns (plan_items [n_items], plan_off [n_cta+1]) int32 on the
-        work list's device; cached per (heads, n_cta, head_group)."""
+        (per-item switch cost in tile units).  Returns (plan_items [n_items], plan_off [n_cta+1] -- int32 on the work
+        list's device --, n_cta, longest per-CTA list); cached per (heads, n_cta, head_group)."""
         import heapq
         if self._plans is None:
             self._plans = {}
@@ -83,7 +83,8 @@ class AttnWork:
                 off.append(off[-1] + len(lst))
             items = torch.tensor([x for lst in per_cta for x in lst], dtype=torch.int32)
             dev = self.work_q.device
-            self._plans[key] = (items.to(dev), torch.tensor(off, dtype=torch.int32).to(dev), n_cta)
+            self._plans[key] = (items.to(dev), torch.tensor(off, dtype=torch.int32).to(dev), n_cta,
+                                max(len(lst) for lst in per_cta))
         return self._plans[key]
 
 

@@ -15,7 +15,7 @@ flag[:, 1:579] = True
 w = schedule.build_attn_work(flag, B, T, True, dev)
 qf = flag.reshape(-1).to(torch.uint8).to(dev)
 PLAN = None if os.environ.get("LB_STREAM_SNAKE") else w.stream_plan(H, ops.sm_count(), ops.STREAM_HEAD_GROUP, float(os.environ.get("LB_PLAN_OVERHEAD", "2.0")))
-trace = torch.zeros(64, 8, dtype=torch.int64, device=dev)
+trace = torch.zeros(64, 32, dtype=torch.int64, device=dev)
 run = lambda: ops.attn_fwd(Q, K0, V0, K1, V1, qf, w.work_q, None, None, None, B, T, H, D, True, 1 / math.sqrt(D), kernel="stream", plan=PLAN)
 for _ in range(3):
     run()
@@ -24,9 +24,10 @@ run()
 torch.cuda.synchronize()
 _lib.call("lb_attn_fwd_stream_set_trace", None)
 t = trace.cpu()
-names = ["mma:waitP", "mma:P seen", "mma:issued", "sm:waitS", "sm:S seen", "sm:max", "sm:pub", "sm:P arr"]
-t0 = int(t[0, 4])
-for it in range(40):
-    if int(t[it, 4]) == 0:
+names = ["q:waitS", "q:Sfree", "q:KQ ok", "q:issued", "q:commit", "p:waitP", "p:P seen", "p:OV ok", "p:issued", "p:commit",
+         "s:waitS", "s:S seen", "s:loaded", "s:max", "s:prevmax", "s:pub", "s:Pfree", "s:P arr"]
+t0 = int(t[0, 11])
+for it in range(48):
+    if int(t[it, 11]) == 0:
         break
-    print(f"tile {it:2d} (wg {it & 1}): " + "  ".join(f"{n}={int(t[it, s]) - t0}" for s, n in enumerate(names)))
+    print(f"tile {it:2d} (wg {it & 1}): " + " ".join(f"{n}={int(t[it, s]) - t0 if int(t[it, s]) else -1}" for s, n in enumerate(names)))
