@@ -25,7 +25,7 @@
 // CTA = 512 threads: warps 0-3 softmax warpgroup 0 (even tiles of the stream), warps 4-7 warpgroup 1 (odd tiles),
 // warp 8 TMA for Q and K, warp 9 tcgen05 issuer for QK^T (+ TMEM alloc), warp 10 TMA for V, warp 11 tcgen05 issuer for
 // PV, warps 12-15 epilogue.
-// setmaxnreg: softmax warpgroups 200 registers per thread, producers 72, epilogue 40 (2 x 200 + 72 + 40 = 4 x 128).
+// setmaxnreg: softmax warpgroups 200 registers per thread, producers 56, epilogue 56 (2 x 200 + 56 + 56 = 4 x 128).
 // TMEM (512 columns): S0 [0,128) S1 [128,256) P0 [256,320) P1 [320,384) O [384,384+D).  P (bf16, 64 columns) is the
 // TMEM A operand of O += P.V.
 #include <math_constants.h>
@@ -39,8 +39,8 @@ namespace fs {
 constexpr int BM = 128, BN = 128;
 constexpr int QST = 2, KST = 2, VST = 2;                         // Q / K / V ring depth; K slot == S slot, V slot == P slot (G & 1)
 constexpr int WARP_KLOAD = 8, WARP_QK = 9, WARP_VLOAD = 10, WARP_PV = 11, WARP_EPI0 = 12, THREADS = 512;
-constexpr int REGS_SOFTMAX = 200, REGS_PRODUCER = 72, REGS_EPILOGUE = 40;   // launch allocation is 128 per thread: 2 x 200 + 72 + 40 = 512
-constexpr int MAX_ITEMS = 256;                                   // decoded items per CTA held in shared memory
+constexpr int REGS_SOFTMAX = 200, REGS_PRODUCER = 56, REGS_EPILOGUE = 56;   // launch allocation is 128 per thread: 2 x 200 + 56 + 56 = 512
+constexpr int MAX_ITEMS = 128;                                   // decoded items per CTA held in shared memory
 constexpr int DEP = 4;                                           // depth of the (m_ref, l) deposit ring
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr uint32_t COL_P = 256, COL_O = 384, TMEM_COLS = 512;
@@ -79,8 +79,10 @@ struct Smem {
     static constexpr int M_OFF = ITEM_OFF + (MAX_ITEMS + 1) * 32;     // float m_sh[2 tile parity][128]
     static constexpr int DEP_OFF = M_OFF + 2 * 128 * 4;               // float dep[DEP][2 wg][2: m_ref, l][128]
     static constexpr int DONE_OFF = DEP_OFF + DEP * 2 * 2 * 128 * 4;  // int epi_done[128]: items whose deposit row r was read
-    static constexpr int BAR_OFF = DONE_OFF + 128 * 4;
+    static constexpr int STAGE_OFF = DONE_OFF + 128 * 4;              // epilogue staging: 4 warps x 32 rows x 128 B (64 bf16 columns)
+    static constexpr int BAR_OFF = STAGE_OFF + 4 * 32 * 128;
     static constexpr int NEEDED = BAR_OFF + 512 + 1024;
+    static_assert(NEEDED <= 227 * 1024, "shared memory budget");
     static constexpr int TOTAL = NEEDED > 120 * 1024 ? NEEDED : 120 * 1024;     // > half an SM: one CTA per SM (512 TMEM columns)
 };
 
@@ -419,13 +421,13 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                 bool first = true;
                 uint32_t ic = 0, pph0 = 0, pph1 = 0, Gp = 0;          // items (with tiles) started
                 auto do_pv = [&](const uint32_t b, uint32_t& pph) {   // O (+)= P[b] . V(Gp), b == Gp & 1
-                    FS_TRACE(5, Gp);                                  // PV: start waiting for P
-                    wait_bar(bar0 + 8 * (B_PFULL + b), pph);
-                    FS_TRACE(6, Gp);                                  // PV: P seen
-                    if (first && ic > 0) wait_bar(bar0 + 8 * B_OFREE, (ic - 1) & 1u);        // previous epilogue has read O
+                    FS_TRACE(5, Gp);                                  // PV: start waiting for V, O, P (the last to arrive last)
                     wait_bar(bar0 + 8 * (B_VFULL + b), pph);
+                    if (first && ic > 0) wait_bar(bar0 + 8 * B_OFREE, (ic - 1) & 1u);        // previous epilogue has read O
+                    FS_TRACE(6, Gp);                                  // PV: V landed, O free
+                    wait_bar(bar0 + 8 * (B_PFULL + b), pph);
                     tc_fence_after_sync();
-                    FS_TRACE(7, Gp);                                  // PV: O free, V landed
+                    FS_TRACE(7, Gp);                                  // PV: P seen
                     const uint32_t dV = dV0 + b * TILE16;
                     const uint32_t a_p = tmem_base + COL_P + b * 64;
                     const uint32_t acc0 = first ? 0u : 1u;
@@ -461,6 +463,8 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         const int r = (warp & 3) * 32 + (threadIdx.x & 31);       // query row in tile == TMEM lane
         const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         const float sl2 = p.scale * LOG2E;
+        const uint32_t bar0 = smem_u32(bars);
+        uint8_t* stage = smem + S::STAGE_OFF + (warp & 3) * (32 * 128);
         uint32_t ne = 0;                                          // items with tiles so far (phase of OFINAL / OFREE)
         for (uint32_t ic = 0;; ++ic) {
             const Item it = load_item(items, (int)ic);
@@ -470,7 +474,9 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             const bool row_ok = (qi < T) && (!p.qflag || (int)p.qflag[bt] == it.variant);
             const int64_t dst = row_ok ? (p.out_row ? (int64_t)p.out_row[bt] : bt) : 0;
             const uint32_t slot = ic % DEP;
-            mbar_wait(bars + B_LDEP + slot, (ic / DEP) & 1u);
+            if (threadIdx.x == WARP_EPI0 * 32) FS_TRACE(18, ic);   // epilogue (row = item): start waiting for the deposits
+            wait_bar(bar0 + 8 * (B_LDEP + slot), (ic / DEP) & 1u);
+            if (threadIdx.x == WARP_EPI0 * 32) FS_TRACE(19, ic);   // epilogue: deposits seen
             const float* d = dep_sh + slot * 512;
             const float m0 = d[r], l0 = d[128 + r], m1 = d[256 + r], l1 = d[384 + r];
             __threadfence_block();
@@ -482,21 +488,27 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             const float l_tot = a0 + a1;
             const float inv_l = l_tot > 0.f ? 1.f / l_tot : 0.f;
             if (it.n_tiles > 0) {
-                mbar_wait(bars + B_OFINAL, ne & 1u);
+                wait_bar(bar0 + 8 * B_OFINAL, ne & 1u);
                 tc_fence_after_sync();
             }
-            __nv_bfloat16* orow = p.O + dst * ((int64_t)p.heads * D) + (int64_t)it.h * D;
+            if (threadIdx.x == WARP_EPI0 * 32) FS_TRACE(20, ic);   // epilogue: O final
+            // O leaves through a per-warp staging tile (32 rows x 64 columns bf16, 16-byte chunks XOR-swizzled by row) so
+            // that the global stores are 128 contiguous bytes per row (a store of one row per lane costs 32 LSU wavefronts
+            // per instruction; it made the epilogue ~3.9 k clk long, and the next item's first PV waits for it).
+            const int32_t dst32 = row_ok ? (int32_t)dst : -1;
+            const int lane = threadIdx.x & 31;
 #pragma unroll 1
-            for (int c = 0; c < D / 16; ++c) {
-                uint32_t v[16];
-                if (it.n_tiles > 0) {
-                    tmem_ld16(lane_addr + COL_O + c * 16, v);
-                    tc_wait_ld();
-                } else {
+            for (int half = 0; half < D / 64; ++half) {
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t v[16];
+                    if (it.n_tiles > 0) {
+                        tmem_ld16(lane_addr + COL_O + half * 64 + c * 16, v);
+                        tc_wait_ld();
+                    } else {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) v[e] = 0u;
-                }
-                if (row_ok) {
+                        for (int e = 0; e < 16; ++e) v[e] = 0u;
+                    }
 #pragma unroll
                     for (int e = 0; e < 16; e += 8) {
                         uint4 o;
@@ -504,16 +516,28 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                         o.y = pack_bf16(__uint_as_float(v[e + 2]) * inv_l, __uint_as_float(v[e + 3]) * inv_l);
                         o.z = pack_bf16(__uint_as_float(v[e + 4]) * inv_l, __uint_as_float(v[e + 5]) * inv_l);
                         o.w = pack_bf16(__uint_as_float(v[e + 6]) * inv_l, __uint_as_float(v[e + 7]) * inv_l);
-                        *reinterpret_cast<uint4*>(orow + c * 16 + e) = o;
+                        const int chunk = c * 2 + (e >> 3);
+                        *reinterpret_cast<uint4*>(stage + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = o;
                     }
+                }
+                if (half == D / 64 - 1 && it.n_tiles > 0) {
+                    tc_fence_before_sync();
+                    mbar_arrive(bars + B_OFREE);                  // O is out of TMEM: the next item's PV may start
+                    if (threadIdx.x == WARP_EPI0 * 32) FS_TRACE(21, ic);   // epilogue: O released
+                }
+                __syncwarp();
+#pragma unroll 4
+                for (int i = 0; i < 8; ++i) {                     // 4 rows x 128 B per store instruction
+                    const int row = i * 4 + (lane >> 3), chunk = lane & 7;
+                    const int32_t drow = __shfl_sync(0xffffffffu, dst32, row);
+                    const uint4 o = *reinterpret_cast<const uint4*>(stage + row * 128 + ((chunk ^ (row & 7)) << 4));
+                    if (drow >= 0)
+                        *reinterpret_cast<uint4*>(p.O + (int64_t)drow * ((int64_t)p.heads * D) + (int64_t)it.h * D + half * 64 + chunk * 8) = o;
                 }
                 __syncwarp();
             }
-            if (it.n_tiles > 0) {
-                tc_fence_before_sync();
-                mbar_arrive(bars + B_OFREE);                      // O may be overwritten by the next item
-                ++ne;
-            }
+            if (threadIdx.x == WARP_EPI0 * 32) FS_TRACE(22, ic);   // epilogue: stores issued
+            if (it.n_tiles > 0) ++ne;
             if (row_ok && p.lse) {
                 // natural-log LSE of the scaled scores; +inf marks a row with no visible key (P == 0 in backward)
                 p.lse[((int64_t)it.b * p.heads + it.h) * T + qi] = l_tot > 0.f ? (m_fin * p.scale + __logf(l_tot)) : CUDART_INF_F;
@@ -526,6 +550,7 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         const int r = (warp & 3) * 32 + (threadIdx.x & 31);       // query row in tile == TMEM lane
         const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         const float sl2 = p.scale * LOG2E;
+        const uint32_t bar0 = smem_u32(bars);
         uint32_t g = 0;                                           // tiles of the items before this one
         for (uint32_t ic = 0;; ++ic) {
             const Item it = load_item(items, (int)ic);
@@ -539,7 +564,7 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                 const int kv0 = (it.first_tile + j) * BN;
                 const bool need_mask = (CAUSAL && kv0 + BN - 1 > q0) || (kv0 + BN > it.kve) || (kv0 < it.kvs);
                 if ((threadIdx.x & 127) == 0) FS_TRACE(10, G);        // softmax: start waiting for S
-                mbar_wait(bars + B_SFULL + (G & 1u), (G >> 1) & 1u);
+                wait_bar(bar0 + 8 * (B_SFULL + (G & 1u)), (G >> 1) & 1u);
                 tc_fence_after_sync();
                 if ((threadIdx.x & 127) == 0) FS_TRACE(11, G);        // softmax: S seen
                 uint32_t sv[128];
@@ -557,7 +582,7 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                 // ---- running max of the row after the previous tile of the stream (the other warpgroup's).  Every tile waits
                 // for its predecessor's publication, also across items (value unused then): that keeps the two m_sh slots and
                 // the two barriers strictly alternating.
-                if (G > 0) mbar_wait(bars + B_MPUB + ((G - 1) & 1u), ((G - 1) >> 1) & 1u);
+                if (G > 0) wait_bar(bar0 + 8 * (B_MPUB + ((G - 1) & 1u)), ((G - 1) >> 1) & 1u);
                 if ((threadIdx.x & 127) == 0) FS_TRACE(14, G);        // softmax: previous tile's max seen
                 float m_cur;
                 if (j == 0) {
@@ -569,7 +594,7 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                     const bool grow = (m_new - m_prev) * sl2 > 8.f;       // also true when m_prev == -inf and m_new finite
                     m_cur = grow ? m_new : m_prev;
                     if (__any_sync(0xffffffffu, grow)) {
-                        mbar_wait(bars + B_PFREE + ((G - 1) & 1u), ((G - 1) >> 1) & 1u);   // PV of tile j-1 has landed in O
+                        wait_bar(bar0 + 8 * (B_PFREE + ((G - 1) & 1u)), ((G - 1) >> 1) & 1u);   // PV of tile j-1 has landed in O
                         tc_fence_after_sync();
                         const float alpha = grow ? ((m_prev == -CUDART_INF_F) ? 0.f : fast_ex2((m_prev - m_new) * sl2)) : 1.f;
 #pragma unroll 1
@@ -594,7 +619,7 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                 }
                 const float m_off = (m_cur == -CUDART_INF_F) ? 0.f : m_cur * sl2;
                 if (G >= 2) {                                         // PV(G-2) has consumed P[G & 1]
-                    mbar_wait(bars + B_PFREE + (G & 1u), ((G - 2) >> 1) & 1u);
+                    wait_bar(bar0 + 8 * (B_PFREE + (G & 1u)), ((G - 2) >> 1) & 1u);
                     tc_fence_after_sync();
                 }
                 if ((threadIdx.x & 127) == 0) FS_TRACE(16, G);        // softmax: P buffer free

@@ -24,10 +24,15 @@ run()
 torch.cuda.synchronize()
 _lib.call("lb_attn_fwd_stream_set_trace", None)
 t = trace.cpu()
-names = ["q:waitS", "q:Sfree", "q:KQ ok", "q:issued", "q:commit", "p:waitP", "p:P seen", "p:OV ok", "p:issued", "p:commit",
+names = ["q:waitS", "q:Sfree", "q:KQ ok", "q:issued", "q:commit", "p:wait", "p:VO ok", "p:P seen", "p:issued", "p:commit",
          "s:waitS", "s:S seen", "s:loaded", "s:max", "s:prevmax", "s:pub", "s:Pfree", "s:P arr"]
 t0 = int(t[0, 11])
 for it in range(48):
     if int(t[it, 11]) == 0:
         break
     print(f"tile {it:2d} (wg {it & 1}): " + " ".join(f"{n}={int(t[it, s]) - t0 if int(t[it, s]) else -1}" for s, n in enumerate(names)))
+enames = ["e:waitdep", "e:dep", "e:Ofinal", "e:Ofree", "e:stored"]
+for it in range(8):
+    if int(t[it, 19]) == 0:
+        break
+    print(f"item {it}: " + " ".join(f"{n}={int(t[it, 18 + s]) - t0}" for s, n in enumerate(enames)))
