@@ -153,15 +153,6 @@ int lb_attn_fwd(const void* Q, const void* K0, const void* V0, const void* K1, c
                 const int32_t* out_row, void* O, float* lse, int batch, int seqlen, int heads, int head_dim, int causal,
                 float scale, void* stream);
 
-/* Same operation and arguments as lb_attn_fwd with a PAIRED work list: work int32 [n_work,4] =
- * {batch, q_tile of lane A, variant, q_tile of lane B or -1}.  One CTA per SM carries both q tiles through one shared
- * K/V tile stream with a fixed A/B interleave of the tcgen05 issue order (see csrc/attn_fwd_pair.cu); every (sample,
- * q tile, variant) that holds rows must appear in exactly one lane. */
-int lb_attn_fwd_pair(const void* Q, const void* K0, const void* V0, const void* K1, const void* V1, const uint8_t* qflag,
-                     const int32_t* work, int n_work, const int32_t* kv_start, const int32_t* kv_end,
-                     const int32_t* out_row, void* O, float* lse, int batch, int seqlen, int heads, int head_dim,
-                     int causal, float scale, void* stream);
-
 /* Same operation and work list as lb_attn_fwd, persistent streaming kernel (csrc/attn_fwd_stream.cu): one CTA per SM
  * walks its share of the (work item, head) list as one stream of score tiles; S and P are double-buffered in TMEM (QK^T
  * runs two tiles ahead of PV), two softmax warpgroups take alternate tiles, a separate warpgroup writes O out.
@@ -184,14 +175,6 @@ int lb_attn_fwd_stream_set_cta_log(void* buf);
 /* diagnostics: CTA 0 writes clock64 stamps into buf ([64][32] int64, device; one row per kv tile: slots 0-9 tcgen05 thread, 10-17
  * softmax thread 0 of the tile's warpgroup).  NULL = off */
 int lb_attn_fwd_stream_set_trace(void* buf);
-
-/* diagnostics: CTA 0 of subsequent lb_attn_fwd_pair launches writes clock64 stamps into buf ([64][16] int64, device
- * memory; per kv tile: slots 0-3 MMA thread (P_A seen, A issued, P_B seen, B issued), 4-6 lane A softmax (S seen,
- * max done, P arrived), 7-9 lane B softmax).  NULL = off */
-int lb_attn_fwd_pair_set_trace(void* buf);
-/* diagnostics: every CTA logs {smid, steps A, steps B, clock64 at entry, Q landed, last MMA issued, exit, -} into buf
- * ([n_work*heads][8] int64, device memory).  NULL = off */
-int lb_attn_fwd_pair_set_cta_log(void* buf);
 
 /* diagnostics: CTA (0,0) of subsequent lb_attn_fwd launches writes clock64 stamps into buf ([64][8] int64, device
  * memory; slots: MMA K-ready / QK-issued / P-seen / PV-issued, softmax S-seen / max-done / exchanged / P-arrived). NULL = off */

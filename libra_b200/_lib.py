@@ -41,14 +41,11 @@ SIGNATURES = {
     "lb_attn_prep_fwd": (I, [P] * 15 + [L, I, I, P]),
     "lb_attn_prep_bwd": (I, [P] * 15 + [L, I, I, P]),
     "lb_attn_fwd": (I, [P, P, P, P, P, P, P, I, P, P, P, P, P, I, I, I, I, I, F, P]),
-    "lb_attn_fwd_pair": (I, [P, P, P, P, P, P, P, I, P, P, P, P, P, I, I, I, I, I, F, P]),
     "lb_attn_fwd_stream": (I, [P, P, P, P, P, P, P, I, P, P, I, I, I, P, P, P, P, P, I, I, I, I, I, F, P]),
     "lb_attn_fwd_stream_max_cta_items": (I, []),
     "lb_attn_fwd_stream_set_cta_log": (I, [P]),
     "lb_attn_fwd_stream_set_trace": (I, [P]),
     "lb_attn_fwd_set_trace": (I, [P]),
-    "lb_attn_fwd_pair_set_trace": (I, [P]),
-    "lb_attn_fwd_pair_set_cta_log": (I, [P]),
     "lb_attn_bwd_prepare": (I, [P, P, P, P, P, I, I, I, I, P]),
     "lb_attn_bwd_dq": (I, [P] * 10 + [I, P, P, P, I, I, I, I, I, F, P]),
     "lb_attn_bwd_dkv": (I, [P] * 11 + [I, P, P, P, P, P, P, I, I, I, I, I, F, P]),
@@ -103,7 +100,7 @@ KERNELS_PER_CALL = {
     "lb_rmsnorm_fwd": 1, "lb_rmsnorm_bwd": 3, "lb_layernorm_fwd": 1, "lb_layernorm_bwd": 3, "lb_swiglu_fwd": 1,
     "lb_swiglu_bwd": 1, "lb_bias_quick_gelu_fwd": 1, "lb_bias_quick_gelu_bwd": 1, "lb_gather_rows": 1,
     "lb_embed_lang_fwd": 1, "lb_embed_vision_cat_fwd": 3, "lb_embed_bwd": 1, "lb_lfq_pack": 1, "lb_lfq_unpack": 1,
-    "lb_attn_prep_fwd": 1, "lb_attn_prep_bwd": 1, "lb_attn_fwd": 1, "lb_attn_fwd_pair": 1, "lb_attn_fwd_stream": 1, "lb_attn_bwd_prepare": 1, "lb_attn_bwd_dq": 1,
+    "lb_attn_prep_fwd": 1, "lb_attn_prep_bwd": 1, "lb_attn_fwd": 1, "lb_attn_fwd_stream": 1, "lb_attn_bwd_prepare": 1, "lb_attn_bwd_dq": 1,
     "lb_attn_bwd_dkv": 1, "lb_gemm_bf16": 1, "lb_patch_embed_fwd": 1, "lb_patch_embed_pack_weight": 1, "lb_cross_entropy_fwd_bwd": 1, "lb_probe_umma": 1, "lb_adamw_bf16": 1,
 }
 launch_counts: dict = {}

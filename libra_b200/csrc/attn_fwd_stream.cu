@@ -15,17 +15,23 @@
 //     max/sum exchange inside a tile).  The only coupling between consecutive tiles is the running row maximum, handed
 //     over through shared memory right after the (short) max phase; O is rescaled lazily (FlashAttention-4 rule: only
 //     when the maximum grew by more than 2^8), each warpgroup keeps its own partial row sum.
-//   * an item switch cost ~6.5 k clk (4 tiles' worth, 30 % of the kernel at 15 items per CTA) when the softmax warpgroups
-//     wrote O out themselves and every role decoded the next item from global memory (a chain of dependent loads).  Now
-//     (a) the CTA's item list is decoded once into shared memory, (b) a separate EPILOGUE warpgroup reads O from TMEM,
-//     normalises and stores it while the softmax warpgroups are already on the next item -- they only deposit their
-//     (reference max, partial sum) pair per item in a 4-deep shared-memory ring, (c) the loaders and the tcgen05 thread
-//     run across item boundaries (Q for the next item is fetched as soon as the last QK^T of the current one retired).
+//   * an item switch cost ~6.5 k clk (4 tiles' worth, 30 % of the kernel at 15 items per CTA) when both softmax
+//     warpgroups met at a barrier for a joint, chunked epilogue and every role decoded the next item from global memory
+//     (a chain of dependent loads).  Now (a) the CTA's item list is decoded once into shared memory; (b) the warpgroup
+//     that took the item's LAST tile writes the item out alone, and it releases O first: all D accumulator columns go
+//     TMEM -> registers in one go (the score registers are free between tiles), O is handed back to the PV thread
+//     ~200 clk after the last PV retired, and only then is the row normalised, packed and stored; the other warpgroup
+//     has deposited its (reference max, partial sum) pair in shared memory and is already on the next item; (c) the
+//     loaders and the tcgen05 threads run across item boundaries.  (A separate epilogue warpgroup was tried: with the
+//     56 registers the budget leaves it, its chunked TMEM -> staging -> global loop held O for ~3 k clk, longer than the
+//     two tiles the P double buffer lets the softmax run ahead.)
+//   * V is needed right after P(G) is written (PV is on the critical path P -> PV -> P buffer free), and a TMA load
+//     takes ~1.5-2 k clk here: the V ring is 3 deep (load issued when PV(G-3) retired); K is consumed two tiles ahead
+//     of the softmax anyway and shares the S double buffer's phase (K slot == S slot).
 //
-// CTA = 512 threads: warps 0-3 softmax warpgroup 0 (even tiles of the stream), warps 4-7 warpgroup 1 (odd tiles),
+// CTA = 384 threads: warps 0-3 softmax warpgroup 0 (even tiles of the stream), warps 4-7 warpgroup 1 (odd tiles),
 // warp 8 TMA for Q and K, warp 9 tcgen05 issuer for QK^T (+ TMEM alloc), warp 10 TMA for V, warp 11 tcgen05 issuer for
-// PV, warps 12-15 epilogue.
-// setmaxnreg: softmax warpgroups 200 registers per thread, producers 56, epilogue 56 (2 x 200 + 56 + 56 = 4 x 128).
+// PV.  setmaxnreg: softmax warpgroups 216 registers per thread, the producer warpgroup 64 (2 x 216 + 64 <= 3 x 168).
 // TMEM (512 columns): S0 [0,128) S1 [128,256) P0 [256,320) P1 [320,384) O [384,384+D).  P (bf16, 64 columns) is the
 // TMEM A operand of O += P.V.
 #include <math_constants.h>
@@ -37,11 +43,10 @@ namespace lb {
 namespace fs {
 
 constexpr int BM = 128, BN = 128;
-constexpr int QST = 2, KST = 2, VST = 2;                         // Q / K / V ring depth; K slot == S slot, V slot == P slot (G & 1)
-constexpr int WARP_KLOAD = 8, WARP_QK = 9, WARP_VLOAD = 10, WARP_PV = 11, WARP_EPI0 = 12, THREADS = 512;
-constexpr int REGS_SOFTMAX = 200, REGS_PRODUCER = 56, REGS_EPILOGUE = 56;   // launch allocation is 128 per thread: 2 x 200 + 56 + 56 = 512
+constexpr int KST = 2, VST = 3;                                  // K / V ring depth; K slot == S slot (G & 1)
+constexpr int WARP_KLOAD = 8, WARP_QK = 9, WARP_VLOAD = 10, WARP_PV = 11, THREADS = 384;
+constexpr int REGS_SOFTMAX = 216, REGS_PRODUCER = 64;            // the CTA pool is what the launch allocated: 3 x 168 = 504 >= 2 x 216 + 64
 constexpr int MAX_ITEMS = 128;                                   // decoded items per CTA held in shared memory
-constexpr int DEP = 4;                                           // depth of the (m_ref, l) deposit ring
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr uint32_t COL_P = 256, COL_O = 384, TMEM_COLS = 512;
 
@@ -74,34 +79,40 @@ struct __align__(16) Item {
 template <int D>
 struct Smem {
     static constexpr int TILE = 128 * D * 2;                          // one Q / K / V tile
-    static constexpr int Q_OFF = 0, K_OFF = QST * TILE, V_OFF = K_OFF + KST * TILE;
+    static constexpr int Q_OFF = 0, K_OFF = TILE, V_OFF = K_OFF + KST * TILE;
     static constexpr int ITEM_OFF = V_OFF + VST * TILE;               // Item[MAX_ITEMS + 1]
     static constexpr int M_OFF = ITEM_OFF + (MAX_ITEMS + 1) * 32;     // float m_sh[2 tile parity][128]
-    static constexpr int DEP_OFF = M_OFF + 2 * 128 * 4;               // float dep[DEP][2 wg][2: m_ref, l][128]
-    static constexpr int DONE_OFF = DEP_OFF + DEP * 2 * 2 * 128 * 4;  // int epi_done[128]: items whose deposit row r was read
-    static constexpr int STAGE_OFF = DONE_OFF + 128 * 4;              // epilogue staging: 4 warps x 32 rows x 128 B (64 bf16 columns)
-    static constexpr int BAR_OFF = STAGE_OFF + 4 * 32 * 128;
+    static constexpr int DEP_OFF = M_OFF + 2 * 128 * 4;               // float lm_sh[2: m_ref, l][128] of the depositing warpgroup
+    static constexpr int STAGE_OFF = DEP_OFF + 2 * 128 * 4;           // epilogue staging: 2 wg x 4 warps x 32 rows x 64 B
+    static constexpr int BAR_OFF = STAGE_OFF + 8 * 32 * 64;
     static constexpr int NEEDED = BAR_OFF + 512 + 1024;
     static_assert(NEEDED <= 227 * 1024, "shared memory budget");
     static constexpr int TOTAL = NEEDED > 120 * 1024 ? NEEDED : 120 * 1024;     // > half an SM: one CTA per SM (512 TMEM columns)
 };
 
 enum {
-    B_QFULL = 0,                     // [2] Q of an item landed (items with tiles alternate between the two Q buffers)
-    B_QEMPTY = B_QFULL + QST,        // [2] last QK^T of the item retired
-    B_KFULL = B_QEMPTY + QST,        // [2] K(G) landed in slot G & 1
-    B_VFULL = B_KFULL + KST,         // [2] V(G) landed in slot G & 1
-    B_SFULL = B_VFULL + VST,         // [2] scores of tile G landed in S[G & 1]  (== K slot G & 1 free again)
+    B_QFULL = 0,                     // Q of an item landed
+    B_QEMPTY,                        // last QK^T of the item retired
+    B_KFULL,                         // [2] K(G) landed in slot G & 1
+    B_VFULL = B_KFULL + KST,         // [3] V(G) landed in slot G % 3
+    B_VEMPTY = B_VFULL + VST,        // [3] PV(G) retired: V slot free
+    B_SFULL = B_VEMPTY + VST,        // [2] scores of tile G landed in S[G & 1]  (== K slot G & 1 free again)
     B_SFREE = B_SFULL + 2,           // [2] the softmax warpgroup holds S[G & 1] in registers (128 arrivals)
     B_PFULL = B_SFREE + 2,           // [2] probabilities of tile G written to P[G & 1] (128 arrivals)
-    B_PFREE = B_PFULL + 2,           // [2] PV of tile G retired: P[G & 1] and V slot G & 1 reusable, O holds tile G
-    B_OFINAL = B_PFREE + 2,          // all MMAs of an item done (items with tiles only)
-    B_OFREE,                         // the epilogue has read O (128 arrivals; items with tiles only)
+    B_PFREE = B_PFULL + 2,           // [2] PV of tile G retired: P[G & 1] reusable, O holds tile G
+    B_OFREE = B_PFREE + 2,           // the item's owner holds O in registers (128 arrivals; items with tiles only)
     B_MPUB,                          // [2] running max of tile G published in m_sh[G & 1] (128 arrivals)
-    B_LDEP = B_MPUB + 2,             // [DEP] both softmax warpgroups deposited (m_ref, l) of an item (256 arrivals)
-    B_COUNT = B_LDEP + DEP
+    B_LDEP = B_MPUB + 2,             // the other warpgroup's (m_ref, l) of an item deposited in lm_sh (128 arrivals)
+    B_LFREE,                         // ... and read by the item's owner (128 arrivals)
+    B_COUNT
 };
 
+// NOTE on parity waits: mbarrier.try_wait.parity(p) is true whenever the barrier's CURRENT phase has parity != p, so a
+// waiter that is two phases ahead of the barrier gets a false positive.  Every wait in this kernel is therefore on a
+// barrier whose previous phase the waiter (or something it has already synchronised with) is known to have seen
+// complete; where the stream would allow a role to run further ahead (the owner of a one-tile item, the rescale path)
+// the wait goes through a barrier that cannot be more than one phase behind (PFREE of the role's own tile).
+//
 // spin on an mbarrier phase (shared-window address).  Lean on the fast path: the single-thread roles execute one
 // dependent instruction every ~5 clk, so every instruction between two tcgen05.mma batches is tensor-pipe idle time.
 __device__ __forceinline__ void wait_bar(uint32_t bar_addr, uint32_t parity) {
@@ -182,20 +193,21 @@ __device__ __forceinline__ Item load_item(const Item* tab, int k) {
     return it;
 }
 
-// row maximum of the 128 scores in v.  MASK: keys outside [kvs, min(kve-1, qi)] become -inf first.  The test is
+// row maximum of the 128 scores in v.  MASK: keys outside [kvs, min(kve-1, qi)] become -inf first (NEED_LO: the tile starts
+// before kvs -- left padding only; without it the test is one compare + select per element).  The test is
 // classified per 32-column chunk with a warp vote: a chunk in which every lane sees all 32 keys needs no work, the rest
 // is tested element-wise (a third, "set the chunk to -inf wholesale" variant made ptxas spill the score registers).
-template <bool MASK, bool CAUSAL>
+template <bool MASK, bool CAUSAL, bool NEED_LO>
 __device__ __forceinline__ float mask_max(uint32_t (&v)[128], int kv0, int qi, int kvs, int kve) {
     if (MASK) {
         const int hi_key = CAUSAL ? min(qi, kve - 1) : kve - 1;      // last visible key of this row
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const int lo = kvs - (kv0 + 32 * c), hi = hi_key - (kv0 + 32 * c);      // visible columns of the chunk: [lo, hi]
-            const bool full = lo <= 0 && hi >= 31;
+            const bool full = (!NEED_LO || lo <= 0) && hi >= 31;
             if (__all_sync(0xffffffffu, full)) continue;
 #pragma unroll
-            for (int e = 0; e < 32; ++e) v[32 * c + e] = (e >= lo && e <= hi) ? v[32 * c + e] : 0xff800000u;
+            for (int e = 0; e < 32; ++e) v[32 * c + e] = ((!NEED_LO || e >= lo) && e <= hi) ? v[32 * c + e] : 0xff800000u;
         }
     }
     float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F, mx2 = -CUDART_INF_F, mx3 = -CUDART_INF_F;
@@ -240,8 +252,7 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     using S = Smem<D>;
     Item* items = reinterpret_cast<Item*>(smem + S::ITEM_OFF);
     float* m_sh = reinterpret_cast<float*>(smem + S::M_OFF);          // [2][128]
-    float* dep_sh = reinterpret_cast<float*>(smem + S::DEP_OFF);      // [DEP][2][2][128]
-    volatile int* epi_done = reinterpret_cast<volatile int*>(smem + S::DONE_OFF);
+    float* lm_sh = reinterpret_cast<float*>(smem + S::DEP_OFF);       // [2][128]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
 
@@ -251,14 +262,11 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < B_COUNT; ++i) {
-            int count = 1;
-            if ((i >= B_SFREE && i < B_PFREE) || i == B_OFREE || (i >= B_MPUB && i < B_MPUB + 2)) count = 128;
-            if (i >= B_LDEP) count = 256;
-            mbar_init(bars + i, count);
+            const bool wg = (i >= B_SFREE && i < B_PFREE) || i == B_OFREE || i >= B_MPUB;
+            mbar_init(bars + i, wg ? 128 : 1);
         }
         fence_barrier_init();
     }
-    if (threadIdx.x < 128) epi_done[threadIdx.x] = 0;
     // the CTA's items, decoded once (every role walks this table; an entry with b < 0 ends it)
     for (int k = threadIdx.x; k <= MAX_ITEMS; k += THREADS) items[k] = decode_item<CAUSAL>(p, item_of_round(p, k));
     if (warp == WARP_KLOAD && elect_one()) {
@@ -278,12 +286,12 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t bar0 = smem_u32(bars);                             // barrier i lives at bar0 + 8 i
 
-    // register budget: the softmax warpgroups hold 128 scores per thread, the others need almost nothing.
+    // register budget: the softmax warpgroups hold 128 scores per thread, the producer warpgroup needs almost nothing.
     // (setmaxnreg sits at the top of each role's own branch so that ptxas budgets the branch with it.)
-    if (warp >= 8 && warp < 12) {
+    if (warp >= 8) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PRODUCER));
-        const uint32_t bar0 = smem_u32(bars);                         // barrier i lives at bar0 + 8 i
         if (warp == WARP_KLOAD) {
             // ------------------------------------------------------------ TMA producer for Q and K (runs ahead across items)
             if (elect_one()) {
@@ -293,13 +301,11 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                     if (it.b < 0) break;
                     if (it.n_tiles == 0) continue;
                     const CUtensorMap* tK = it.variant ? &tmK1 : &tmK0;
-                    const uint32_t qb = iq & 1u;
-                    wait_bar(bar0 + 8 * (B_QEMPTY + qb), ((iq >> 1) & 1u) ^ 1u);
-                    mbar_arrive_expect_tx(bars + B_QFULL + qb, S::TILE);
+                    wait_bar(bar0 + 8 * B_QEMPTY, (iq & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(bars + B_QFULL, S::TILE);
 #pragma unroll
                     for (int c = 0; c < D / 64; ++c)
-                        tma_load_2d(smem + S::Q_OFF + qb * S::TILE + c * (BM * 128), &tmQ, bars + B_QFULL + qb, it.h * D + c * 64,
-                                    it.b * T + it.q_tile * BM);
+                        tma_load_2d(smem + S::Q_OFF + c * (BM * 128), &tmQ, bars + B_QFULL, it.h * D + c * 64, it.b * T + it.q_tile * BM);
                     ++iq;
                     for (int j = 0; j < it.n_tiles; ++j, ++G) {
                         const uint32_t s = G & 1u;                    // free again once QK(G-2) retired: that is SFULL's phase
@@ -315,34 +321,37 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         } else if (warp == WARP_VLOAD) {
             // ------------------------------------------------------------ TMA producer for V
             if (elect_one()) {
-                uint32_t G = 0;
+                uint32_t vs = 0, vph = 1;                             // ring slot, parity of the "slot empty" phase to wait for
                 for (int k = 0;; ++k) {
                     const Item it = load_item(items, k);
                     if (it.b < 0) break;
                     const CUtensorMap* tV = it.variant ? &tmV1 : &tmV0;
-                    for (int j = 0; j < it.n_tiles; ++j, ++G) {
-                        const uint32_t s = G & 1u;                    // free again once PV(G-2) retired: that is PFREE's phase
-                        wait_bar(bar0 + 8 * (B_PFREE + s), ((G >> 1) & 1u) ^ 1u);
-                        mbar_arrive_expect_tx(bars + B_VFULL + s, S::TILE);
+                    for (int j = 0; j < it.n_tiles; ++j) {
+                        wait_bar(bar0 + 8 * (B_VEMPTY + vs), vph);
+                        mbar_arrive_expect_tx(bars + B_VFULL + vs, S::TILE);
 #pragma unroll
                         for (int c = 0; c < D / 64; ++c)
-                            tma_load_2d(smem + S::V_OFF + s * S::TILE + c * (BN * 128), tV, bars + B_VFULL + s, it.h * D + c * 64,
+                            tma_load_2d(smem + S::V_OFF + vs * S::TILE + c * (BN * 128), tV, bars + B_VFULL + vs, it.h * D + c * 64,
                                         it.b * T + (it.first_tile + j) * BN);
+                        if (++vs == VST) {
+                            vs = 0;
+                            vph ^= 1u;
+                        }
                     }
                 }
             }
         } else if (warp == WARP_QK) {
             // ------------------------------------------------------------ tcgen05 issuer 1: S = Q . K^T, two tiles ahead of PV.
             // Everything an issuing thread executes between two batches of MMAs is serial latency on the tensor pipe's
-            // critical path (a dependent instruction every ~5 clk; measured ~2100 clk per tile with ONE thread running a
-            // general two-cursor loop for both products).  So QK^T and PV have their own issuing threads (the hardware
-            // orders them through the barriers they already wait on), each loop is unrolled over the slot bit G & 1 --
-            // barrier addresses, TMEM columns and K / V descriptors become constants -- and the items are reduced to their
-            // tile counts.
+            // critical path (a dependent instruction every ~5-10 clk while the softmax warps keep the issue ports busy;
+            // measured ~2100 clk per tile with ONE thread running a general two-cursor loop for both products).  So QK^T
+            // and PV have their own issuing threads (the hardware orders them through the barriers they already wait on),
+            // the loops are unrolled over the slot bit G & 1 -- barrier addresses, TMEM columns and K descriptors become
+            // constants -- and the items are reduced to their tile counts.
             if (elect_one()) {
                 constexpr uint32_t idesc_qk = make_idesc_bf16(BM, BN, 0, 0);
                 constexpr uint32_t TILE16 = (uint32_t)(S::TILE >> 4);
-                const uint32_t dQ0 = desc_lo_kmajor(smem_u32(smem + S::Q_OFF));
+                const uint32_t dQ = desc_lo_kmajor(smem_u32(smem + S::Q_OFF));
                 const uint32_t dK0 = desc_lo_kmajor(smem_u32(smem + S::K_OFF));
                 const int* ntile = &items[0].n_tiles;                 // stride 8 ints
                 int k = 0;
@@ -356,15 +365,13 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                 };
                 int left = next_count();
                 bool first = true, logged = false;
-                uint32_t iq = 0, qph0 = 0, qph1 = 0, dQ = dQ0, Gq = 0;   // items started; phase parity of each slot's next use
+                uint32_t iq = 0, qph0 = 0, qph1 = 0, Gq = 0;          // items started; phase parity of each slot's next use
                 auto do_qk = [&](const uint32_t b, uint32_t& qph, const bool wait_sfree) {     // S[b] = Q . K(Gq)^T, b == Gq & 1
                     FS_TRACE(0, Gq);                                  // QK: start waiting for the S buffer
                     if (wait_sfree) wait_bar(bar0 + 8 * (B_SFREE + b), qph ^ 1u);             // S(Gq-2) is in registers
                     FS_TRACE(1, Gq);                                  // QK: S buffer free
                     if (first) {
-                        const uint32_t qb = iq & 1u;
-                        wait_bar(bar0 + 8 * (B_QFULL + qb), (iq >> 1) & 1u);
-                        dQ = dQ0 + qb * TILE16;
+                        wait_bar(bar0 + 8 * B_QFULL, iq & 1u);
                         if (p.cta_log && !logged) {
                             p.cta_log[(int64_t)blockIdx.x * 8 + 4] = clock64();
                             logged = true;
@@ -384,8 +391,8 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                     commit_bar(bar0 + 8 * (B_SFULL + b));             // scores landed; K slot b free
                     qph ^= 1u;
                     first = false;
-                    if (--left == 0) {                                // Q buffer may be replaced by the item after next
-                        commit_bar(bar0 + 8 * (B_QEMPTY + (iq & 1u)));
+                    if (--left == 0) {                                // Q may be replaced by the next item's
+                        commit_bar(bar0 + 8 * B_QEMPTY);
                         ++iq;
                         left = next_count();
                         first = true;
@@ -401,7 +408,7 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                     do_qk(1u, qph1, true);
                 }
             }
-        } else if (warp == WARP_PV) {
+        } else {
             // ------------------------------------------------------------ tcgen05 issuer 2: O (+)= P . V
             if (elect_one()) {
                 constexpr uint32_t idesc_pv = make_idesc_bf16(BM, D, 0, 1);
@@ -419,16 +426,17 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                 };
                 int left = next_count();
                 bool first = true;
-                uint32_t ic = 0, pph0 = 0, pph1 = 0, Gp = 0;          // items (with tiles) started
+                uint32_t ne = 0, pph0 = 0, pph1 = 0, Gp = 0;          // items (with tiles) started
+                uint32_t vs = 0, vph = 0;                             // V ring slot and its "full" phase parity
                 auto do_pv = [&](const uint32_t b, uint32_t& pph) {   // O (+)= P[b] . V(Gp), b == Gp & 1
                     FS_TRACE(5, Gp);                                  // PV: start waiting for V, O, P (the last to arrive last)
-                    wait_bar(bar0 + 8 * (B_VFULL + b), pph);
-                    if (first && ic > 0) wait_bar(bar0 + 8 * B_OFREE, (ic - 1) & 1u);        // previous epilogue has read O
+                    wait_bar(bar0 + 8 * (B_VFULL + vs), vph);
+                    if (first && ne > 0) wait_bar(bar0 + 8 * B_OFREE, (ne - 1) & 1u);        // the previous item's O is out of TMEM
                     FS_TRACE(6, Gp);                                  // PV: V landed, O free
                     wait_bar(bar0 + 8 * (B_PFULL + b), pph);
                     tc_fence_after_sync();
                     FS_TRACE(7, Gp);                                  // PV: P seen
-                    const uint32_t dV = dV0 + b * TILE16;
+                    const uint32_t dV = dV0 + vs * TILE16;
                     const uint32_t a_p = tmem_base + COL_P + b * 64;
                     const uint32_t acc0 = first ? 0u : 1u;
 #pragma unroll
@@ -438,12 +446,16 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                                    kk ? 1u : acc0);
                     }
                     FS_TRACE(8, Gp);                                  // PV: issued
-                    commit_bar(bar0 + 8 * (B_PFREE + b));             // P[b], V slot b free; O holds tile Gp
+                    commit_bar(bar0 + 8 * (B_PFREE + b));             // P[b] free; O holds tile Gp
+                    commit_bar(bar0 + 8 * (B_VEMPTY + vs));
                     pph ^= 1u;
+                    if (++vs == VST) {
+                        vs = 0;
+                        vph ^= 1u;
+                    }
                     first = false;
-                    if (--left == 0) {
-                        commit_bar(bar0 + 8 * B_OFINAL);
-                        ++ic;
+                    if (--left == 0) {                                // the commit on PFREE above also tells the item's owner that O is final
+                        ++ne;
                         left = next_count();
                         first = true;
                     }
@@ -457,92 +469,6 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                 }
             }
         }
-    } else if (warp >= WARP_EPI0) {
-        // ------------------------------------------------------------ epilogue warpgroup: O / l -> global, LSE
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_EPILOGUE));
-        const int r = (warp & 3) * 32 + (threadIdx.x & 31);       // query row in tile == TMEM lane
-        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        const float sl2 = p.scale * LOG2E;
-        const uint32_t bar0 = smem_u32(bars);
-        uint8_t* stage = smem + S::STAGE_OFF + (warp & 3) * (32 * 128);
-        uint32_t ne = 0;                                          // items with tiles so far (phase of OFINAL / OFREE)
-        for (uint32_t ic = 0;; ++ic) {
-            const Item it = load_item(items, (int)ic);
-            if (it.b < 0) break;
-            const int qi = it.q_tile * BM + r;
-            const int64_t bt = (int64_t)it.b * T + qi;
-            const bool row_ok = (qi < T) && (!p.qflag || (int)p.qflag[bt] == it.variant);
-            const int64_t dst = row_ok ? (p.out_row ? (int64_t)p.out_row[bt] : bt) : 0;
-            const uint32_t slot = ic % DEP;
-            if (threadIdx.x == WARP_EPI0 * 32) FS_TRACE(18, ic);   // epilogue (row = item): start waiting for the deposits
-            wait_bar(bar0 + 8 * (B_LDEP + slot), (ic / DEP) & 1u);
-            if (threadIdx.x == WARP_EPI0 * 32) FS_TRACE(19, ic);   // epilogue: deposits seen
-            const float* d = dep_sh + slot * 512;
-            const float m0 = d[r], l0 = d[128 + r], m1 = d[256 + r], l1 = d[384 + r];
-            __threadfence_block();
-            epi_done[r] = (int)ic + 1;                            // row r of this slot may be overwritten (item ic + DEP)
-            // the last reference maximum is the larger of the two (references only grow); O is relative to it
-            const float m_fin = fmaxf(m0, m1);
-            const float a0 = (m0 == -CUDART_INF_F) ? 0.f : l0 * fast_ex2((m0 - m_fin) * sl2);
-            const float a1 = (m1 == -CUDART_INF_F) ? 0.f : l1 * fast_ex2((m1 - m_fin) * sl2);
-            const float l_tot = a0 + a1;
-            const float inv_l = l_tot > 0.f ? 1.f / l_tot : 0.f;
-            if (it.n_tiles > 0) {
-                wait_bar(bar0 + 8 * B_OFINAL, ne & 1u);
-                tc_fence_after_sync();
-            }
-            if (threadIdx.x == WARP_EPI0 * 32) FS_TRACE(20, ic);   // epilogue: O final
-            // O leaves through a per-warp staging tile (32 rows x 64 columns bf16, 16-byte chunks XOR-swizzled by row) so
-            // that the global stores are 128 contiguous bytes per row (a store of one row per lane costs 32 LSU wavefronts
-            // per instruction; it made the epilogue ~3.9 k clk long, and the next item's first PV waits for it).
-            const int32_t dst32 = row_ok ? (int32_t)dst : -1;
-            const int lane = threadIdx.x & 31;
-#pragma unroll 1
-            for (int half = 0; half < D / 64; ++half) {
-#pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t v[16];
-                    if (it.n_tiles > 0) {
-                        tmem_ld16(lane_addr + COL_O + half * 64 + c * 16, v);
-                        tc_wait_ld();
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) v[e] = 0u;
-                    }
-#pragma unroll
-                    for (int e = 0; e < 16; e += 8) {
-                        uint4 o;
-                        o.x = pack_bf16(__uint_as_float(v[e + 0]) * inv_l, __uint_as_float(v[e + 1]) * inv_l);
-                        o.y = pack_bf16(__uint_as_float(v[e + 2]) * inv_l, __uint_as_float(v[e + 3]) * inv_l);
-                        o.z = pack_bf16(__uint_as_float(v[e + 4]) * inv_l, __uint_as_float(v[e + 5]) * inv_l);
-                        o.w = pack_bf16(__uint_as_float(v[e + 6]) * inv_l, __uint_as_float(v[e + 7]) * inv_l);
-                        const int chunk = c * 2 + (e >> 3);
-                        *reinterpret_cast<uint4*>(stage + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = o;
-                    }
-                }
-                if (half == D / 64 - 1 && it.n_tiles > 0) {
-                    tc_fence_before_sync();
-                    mbar_arrive(bars + B_OFREE);                  // O is out of TMEM: the next item's PV may start
-                    if (threadIdx.x == WARP_EPI0 * 32) FS_TRACE(21, ic);   // epilogue: O released
-                }
-                __syncwarp();
-#pragma unroll 4
-                for (int i = 0; i < 8; ++i) {                     // 4 rows x 128 B per store instruction
-                    const int row = i * 4 + (lane >> 3), chunk = lane & 7;
-                    const int32_t drow = __shfl_sync(0xffffffffu, dst32, row);
-                    const uint4 o = *reinterpret_cast<const uint4*>(stage + row * 128 + ((chunk ^ (row & 7)) << 4));
-                    if (drow >= 0)
-                        *reinterpret_cast<uint4*>(p.O + (int64_t)drow * ((int64_t)p.heads * D) + (int64_t)it.h * D + half * 64 + chunk * 8) = o;
-                }
-                __syncwarp();
-            }
-            if (threadIdx.x == WARP_EPI0 * 32) FS_TRACE(22, ic);   // epilogue: stores issued
-            if (it.n_tiles > 0) ++ne;
-            if (row_ok && p.lse) {
-                // natural-log LSE of the scaled scores; +inf marks a row with no visible key (P == 0 in backward)
-                p.lse[((int64_t)it.b * p.heads + it.h) * T + qi] = l_tot > 0.f ? (m_fin * p.scale + __logf(l_tot)) : CUDART_INF_F;
-            }
-        }
     } else {
         // ------------------------------------------------------------ softmax warpgroups: alternate tiles of the CTA's tile stream
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_SOFTMAX));
@@ -550,14 +476,24 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         const int r = (warp & 3) * 32 + (threadIdx.x & 31);       // query row in tile == TMEM lane
         const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         const float sl2 = p.scale * LOG2E;
-        const uint32_t bar0 = smem_u32(bars);
-        uint32_t g = 0;                                           // tiles of the items before this one
-        for (uint32_t ic = 0;; ++ic) {
-            const Item it = load_item(items, (int)ic);
+        uint32_t g = 0, dep = 0;                                  // tiles / deposits (items with >= 2 tiles) so far
+        for (int ic = 0;; ++ic) {
+            const Item it = load_item(items, ic);
             if (it.b < 0) break;
             const int n = it.n_tiles;
             const int q0 = it.q_tile * BM, qi = q0 + r;
+            // the warpgroup that takes the item's last tile writes the item out; the other one (if it has tiles at all)
+            // deposits its partial row sum and moves on
+            const bool owner = n > 0 ? (int)((g + (uint32_t)n - 1u) & 1u) == w : w == 0;
             float m_ref = -CUDART_INF_F, l = 0.f;                 // l is relative to m_ref
+            // destination of my row: loaded now, used by the epilogue (keeps two dependent global loads off its path)
+            bool row_ok = false;
+            int64_t dst = 0;
+            if (owner) {
+                const int64_t bt = (int64_t)it.b * T + qi;
+                row_ok = (qi < T) && (!p.qflag || (int)p.qflag[bt] == it.variant);
+                dst = row_ok ? (p.out_row ? (int64_t)p.out_row[bt] : bt) : 0;
+            }
             for (int j = (int)((g & 1u) ^ (uint32_t)w); j < n; j += 2) {
                 const uint32_t G = g + (uint32_t)j;
                 const uint32_t colS = (G & 1u) * 128;
@@ -576,8 +512,10 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                 if ((threadIdx.x & 127) == 0) FS_TRACE(12, G);        // softmax: scores in registers
                 tc_fence_before_sync();
                 mbar_arrive(bars + B_SFREE + (G & 1u));               // S(G) is in registers: QK(G+2) may overwrite the buffer
-                const float mx = need_mask ? mask_max<true, CAUSAL>(sv, kv0, qi, it.kvs, it.kve)
-                                           : mask_max<false, CAUSAL>(sv, kv0, qi, it.kvs, it.kve);
+                float mx;
+                if (!need_mask) mx = mask_max<false, CAUSAL, false>(sv, kv0, qi, it.kvs, it.kve);
+                else if (kv0 >= it.kvs) mx = mask_max<true, CAUSAL, false>(sv, kv0, qi, it.kvs, it.kve);
+                else mx = mask_max<true, CAUSAL, true>(sv, kv0, qi, it.kvs, it.kve);
                 if ((threadIdx.x & 127) == 0) FS_TRACE(13, G);        // softmax: max done
                 // ---- running max of the row after the previous tile of the stream (the other warpgroup's).  Every tile waits
                 // for its predecessor's publication, also across items (value unused then): that keeps the two m_sh slots and
@@ -594,7 +532,12 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                     const bool grow = (m_new - m_prev) * sl2 > 8.f;       // also true when m_prev == -inf and m_new finite
                     m_cur = grow ? m_new : m_prev;
                     if (__any_sync(0xffffffffu, grow)) {
-                        wait_bar(bar0 + 8 * (B_PFREE + ((G - 1) & 1u)), ((G - 1) >> 1) & 1u);   // PV of tile j-1 has landed in O
+                        // PV of tile j-1 has landed in O.  The other warpgroup's barrier could still be in PV(G-3)'s phase (a
+                        // false positive for the wait below, see the parity note); MMAs of one thread retire in order, so
+                        // seeing my own PV(G-2) retired first rules that out.  (Waiting for PV(G-3)'s phase instead would
+                        // deadlock whenever PV(G-1) has already retired.)
+                        if (G >= 2) wait_bar(bar0 + 8 * (B_PFREE + (G & 1u)), ((G - 2) >> 1) & 1u);
+                        wait_bar(bar0 + 8 * (B_PFREE + ((G - 1) & 1u)), ((G - 1) >> 1) & 1u);
                         tc_fence_after_sync();
                         const float alpha = grow ? ((m_prev == -CUDART_INF_F) ? 0.f : fast_ex2((m_prev - m_new) * sl2)) : 1.f;
 #pragma unroll 1
@@ -629,15 +572,84 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                 mbar_arrive(bars + B_PFULL + (G & 1u));
                 if ((threadIdx.x & 127) == 0) FS_TRACE(17, G);        // softmax: P stored, arrived
             }
-            // ---- hand my (reference max, partial sum) of the item to the epilogue warpgroup; ring slot ic % DEP is free once
-            // the epilogue has read row r of item ic - DEP
-            while (epi_done[r] + DEP <= (int)ic) {
+            if (n >= 2 && !owner) {
+                // ---- hand my (reference max, partial sum) to the owner; the slot is free once the previous deposit was read
+                if (dep > 0) wait_bar(bar0 + 8 * B_LFREE, (dep - 1) & 1u);
+                lm_sh[r] = m_ref;
+                lm_sh[128 + r] = l;
+                mbar_arrive(bars + B_LDEP);
             }
-            __threadfence_block();
-            float* d = dep_sh + (ic % DEP) * 512 + w * 256;
-            d[r] = m_ref;
-            d[128 + r] = l;
-            mbar_arrive(bars + B_LDEP + ic % DEP);
+            if (owner) {
+                // ---- end of the item: the last reference maximum is the larger of the two (references only grow); O is
+                // relative to it
+                if (threadIdx.x == w * 128) FS_TRACE(18, ic);         // epilogue (row = item): start
+                float m_fin = m_ref, l_tot = l;
+                if (n >= 2) {
+                    wait_bar(bar0 + 8 * B_LDEP, dep & 1u);
+                    const float m_o = lm_sh[r], l_o = lm_sh[128 + r];
+                    mbar_arrive(bars + B_LFREE);
+                    m_fin = fmaxf(m_ref, m_o);
+                    const float a = (m_ref == -CUDART_INF_F) ? 0.f : l * fast_ex2((m_ref - m_fin) * sl2);
+                    const float b = (m_o == -CUDART_INF_F) ? 0.f : l_o * fast_ex2((m_o - m_fin) * sl2);
+                    l_tot = a + b;
+                }
+                const float inv_l = l_tot > 0.f ? 1.f / l_tot : 0.f;
+                if (threadIdx.x == w * 128) FS_TRACE(19, ic);         // epilogue: deposit seen
+                uint32_t ov[D];
+                if (n > 0) {
+                    const uint32_t Gl = g + (uint32_t)n - 1u;             // my last tile: its PV is the item's last MMA
+                    wait_bar(bar0 + 8 * (B_PFREE + (Gl & 1u)), (Gl >> 1) & 1u);
+                    tc_fence_after_sync();
+                    if (threadIdx.x == w * 128) FS_TRACE(20, ic);     // epilogue: O final
+#pragma unroll
+                    for (int c = 0; c < D / 32; ++c) tmem_ld32(lane_addr + COL_O + c * 32, ov + c * 32);
+                    tc_wait_ld();
+                    tc_fence_before_sync();
+                    mbar_arrive(bars + B_OFREE);                      // O is in registers: the next item's PV may start
+                    if (threadIdx.x == w * 128) FS_TRACE(21, ic);     // epilogue: O released
+                } else {
+#pragma unroll
+                    for (int e = 0; e < D; ++e) ov[e] = 0u;
+                }
+                // O leaves through a per-warp staging tile (32 rows x 32 columns bf16 at a time, 16-byte chunks XOR-swizzled by
+                // row) so that a store instruction covers 8 rows x 64 contiguous bytes; one row per lane costs 32 LSU
+                // wavefronts per instruction and held the owner for ~3.2 k clk per item.
+                {
+                    uint8_t* stage = smem + S::STAGE_OFF + (w * 4 + (warp & 3)) * (32 * 64);
+                    const int lane = threadIdx.x & 31;
+                    const int32_t dst32 = row_ok ? (int32_t)dst : -1;
+                    __nv_bfloat16* obase = p.O + (int64_t)it.h * D;
+                    const int64_t ld_o = (int64_t)p.heads * D;
+#pragma unroll
+                    for (int q = 0; q < D / 32; ++q) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const int e = q * 32 + c * 8;
+                            uint4 o;
+                            o.x = pack_bf16(__uint_as_float(ov[e + 0]) * inv_l, __uint_as_float(ov[e + 1]) * inv_l);
+                            o.y = pack_bf16(__uint_as_float(ov[e + 2]) * inv_l, __uint_as_float(ov[e + 3]) * inv_l);
+                            o.z = pack_bf16(__uint_as_float(ov[e + 4]) * inv_l, __uint_as_float(ov[e + 5]) * inv_l);
+                            o.w = pack_bf16(__uint_as_float(ov[e + 6]) * inv_l, __uint_as_float(ov[e + 7]) * inv_l);
+                            *reinterpret_cast<uint4*>(stage + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) = o;
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int row = i * 8 + (lane >> 2), chunk = lane & 3;
+                            const int32_t drow = __shfl_sync(0xffffffffu, dst32, row);
+                            const uint4 o = *reinterpret_cast<const uint4*>(stage + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
+                            if (drow >= 0) *reinterpret_cast<uint4*>(obase + (int64_t)drow * ld_o + q * 32 + chunk * 8) = o;
+                        }
+                        __syncwarp();
+                    }
+                }
+                if (row_ok && p.lse) {
+                    // natural-log LSE of the scaled scores; +inf marks a row with no visible key (P == 0 in backward)
+                    p.lse[((int64_t)it.b * p.heads + it.h) * T + qi] = l_tot > 0.f ? (m_fin * p.scale + __logf(l_tot)) : CUDART_INF_F;
+                }
+                if (threadIdx.x == w * 128) FS_TRACE(22, ic);         // epilogue: stores issued
+            }
+            if (n >= 2) ++dep;
             g += (uint32_t)n;
         }
     }

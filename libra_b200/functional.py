@@ -17,14 +17,20 @@ import torch
 from . import ops
 from .schedule import AttnWork, Routing
 
-# attention forward kernel: "single" (csrc/attn_fwd.cu), "pair" (attn_fwd_pair.cu) or "stream" (attn_fwd_stream.cu)
-FWD_KERNEL = os.environ.get("LB_ATTN_FWD_KERNEL", "single")
+# attention forward kernel: "stream" (csrc/attn_fwd_stream.cu: persistent, the default) or "single" (attn_fwd.cu).  A work
+# list whose per-CTA share exceeds the persistent kernel's in-kernel item table runs on "single" (same work list, same
+# results).
+FWD_KERNEL = os.environ.get("LB_ATTN_FWD_KERNEL", "stream")
 
 
-def _stream_plan(work: AttnWork, heads: int):
-    if FWD_KERNEL != "stream":
-        return None
-    return work.stream_plan(heads, ops.sm_count(), ops.STREAM_HEAD_GROUP)
+def _fwd_choice(work: AttnWork, heads: int):
+    """(kernel, work list, plan) for this work list."""
+    if FWD_KERNEL == "stream":
+        plan = work.stream_plan(heads, ops.sm_count(), ops.STREAM_HEAD_GROUP)
+        if plan[3] <= ops.stream_max_cta_items():
+            return "stream", work.work_q, plan
+        return "single", work.work_q, None
+    return FWD_KERNEL, work.work_q, None
 
 BF16 = torch.bfloat16
 
@@ -500,9 +506,10 @@ class BridgeAttention(torch.autograd.Function):
         scale = 1.0 / math.sqrt(meta.head_dim)
         o = torch.empty_like(q)
         # variant 0 = language queries (see Kfl/Vfl), variant 1 = vision queries (see Kfv/Vfv); rows land in sorted order
-        o, lse = ops.attn_fwd(Q, Kfl, Vfl, Kfv, Vfv, rt.flag_orig, w.work_q2 if FWD_KERNEL == "pair" else w.work_q, w.kv_start,
+        kern, wlist, plan = _fwd_choice(w, meta.heads)
+        o, lse = ops.attn_fwd(Q, Kfl, Vfl, Kfv, Vfv, rt.flag_orig, wlist, w.kv_start,
                               w.kv_end, rt.inv, meta.batch, meta.seqlen, meta.heads, meta.head_dim, True, scale, out=o,
-                              kernel=FWD_KERNEL, plan=_stream_plan(w, meta.heads))
+                              kernel=kern, plan=plan)
         ctx.meta = meta
         ctx.scale = scale
         ctx.save_for_backward(Q, Kfv, Kfl, Vfv, Vfl, o, lse, tk, tv, Bk_l, Bk_v, Bv_l, Bv_v)
@@ -547,8 +554,9 @@ class PlainAttention(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, q, k, v, work: AttnWork, batch, seqlen, heads, head_dim, scale):
-        o, lse = ops.attn_fwd(q, k, v, None, None, None, work.work_q2 if FWD_KERNEL == "pair" else work.work_q, None, None,
-                              None, batch, seqlen, heads, head_dim, False, scale, kernel=FWD_KERNEL, plan=_stream_plan(work, heads))
+        kern, wlist, plan = _fwd_choice(work, heads)
+        o, lse = ops.attn_fwd(q, k, v, None, None, None, wlist, None, None,
+                              None, batch, seqlen, heads, head_dim, False, scale, kernel=kern, plan=plan)
         ctx.args = (work, batch, seqlen, heads, head_dim, scale)
         ctx.save_for_backward(q, k, v, o, lse)
         return o

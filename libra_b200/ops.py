@@ -44,7 +44,7 @@ def sm_count() -> int:
     return _SM_COUNT
 
 
-def enable_timing(names=("lb_attn_fwd", "lb_attn_fwd_pair", "lb_attn_fwd_stream", "lb_attn_bwd_dq", "lb_attn_bwd_dkv")):
+def enable_timing(names=("lb_attn_fwd", "lb_attn_fwd_stream", "lb_attn_bwd_dq", "lb_attn_bwd_dkv")):
     global TIMED
     TIMED = {n: [] for n in names}
 
@@ -272,12 +272,22 @@ def attn_prep_bwd(dQ, dKfv, dKfl, dVfv, dVfl, flag_sorted, sorted_of, pos, cos_t
     return dq, dk, dv, dkb, dvb
 
 
+_STREAM_MAX_ITEMS = None
+
+
+def stream_max_cta_items() -> int:
+    """Items one CTA of the persistent forward can hold (lb_attn_fwd_stream_max_cta_items)."""
+    global _STREAM_MAX_ITEMS
+    if _STREAM_MAX_ITEMS is None:
+        _STREAM_MAX_ITEMS = int(_lib.load().lb_attn_fwd_stream_max_cta_items())
+    return _STREAM_MAX_ITEMS
+
+
 def attn_fwd(Q, K0, V0, K1, V1, qflag, work, kv_start, kv_end, out_row, batch, seqlen, heads, head_dim, causal, scale,
-             out=None, paired=False, kernel=None, plan=None):
-    """kernel: "single" (two CTAs per SM, one q tile each), "pair" (`work` is the paired-tile list AttnWork.work_q2) or
-    "stream" (persistent, same work list as "single"; `plan` = AttnWork.stream_plan(...) or None for the built-in
-    snake split).  paired=True is shorthand for kernel="pair"."""
-    kernel = kernel or ("pair" if paired else "single")
+             out=None, kernel=None, plan=None):
+    """kernel: "single" (two CTAs per SM, one q tile each; the default of this low-level call) or "stream" (persistent;
+    `plan` = AttnWork.stream_plan(...) or None for the built-in snake split)."""
+    kernel = kernel or "single"
     C = heads * head_dim
     if out is None:
         out = torch.zeros(batch * seqlen, C, dtype=BF16, device=Q.device)
@@ -288,7 +298,7 @@ def attn_fwd(Q, K0, V0, K1, V1, qflag, work, kv_start, kv_end, out_row, batch, s
         items, off, n_cta, max_items = plan if plan is not None else (None, None, 0, 0)
         _timed_call("lb_attn_fwd_stream", *head, _p(items), _p(off), n_cta, max_items, STREAM_HEAD_GROUP, *tail)
     else:
-        _timed_call({"single": "lb_attn_fwd", "pair": "lb_attn_fwd_pair"}[kernel], *head, *tail)
+        _timed_call({"single": "lb_attn_fwd"}[kernel], *head, *tail)
     return out, lse
 
 

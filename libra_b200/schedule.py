@@ -49,7 +49,6 @@ class AttnWork:
     kv_start: Optional[torch.Tensor]
     kv_end: Optional[torch.Tensor]
     kv_cover: tuple = (False, False)   # per variant: every kv tile of every sample has a dK/dV work item
-    work_q2: Optional[torch.Tensor] = None   # [n,4] int32 {b, q_tile A, variant, q_tile B or -1}: paired-tile forward
     q_tiles: Optional[list] = None           # kv tiles of every work_q item (host copy, for stream_plan)
     _plans: Optional[dict] = None
 
@@ -103,7 +102,7 @@ def build_attn_work(vision_flag_cpu: Optional[torch.Tensor], batch: int, seqlen:
         has[:, 1] = (fl == 1).any(-1).to(torch.uint8)
     ks = [0] * batch if kv_start is None else [int(x) for x in kv_start]
     ke = [seqlen] * batch if kv_end is None else [int(x) for x in kv_end]
-    items_q, items_kv, items_q2 = [], [], []
+    items_q, items_kv = [], []
     cover = [True, True]
     for b in range(batch):
         first_kv, last_kv = ks[b] // TILE, (ke[b] + TILE - 1) // TILE
@@ -113,14 +112,6 @@ def build_attn_work(vision_flag_cpu: Optional[torch.Tensor], batch: int, seqlen:
                     continue
                 n_kv = (min(last_kv, qt + 1) if causal else last_kv) - first_kv
                 items_q.append((max(n_kv, 0), b, qt, v))
-            # paired-tile forward: neighbouring q tiles of one (sample, variant) share the K/V tile stream of a CTA
-            mine = [(w, qt) for w, bb, qt, vv in items_q if bb == b and vv == v]
-            mine.sort(key=lambda t: -t[1])
-            for i in range(0, len(mine), 2):
-                if i + 1 < len(mine):
-                    items_q2.append((mine[i][0] + mine[i + 1][0], b, mine[i + 1][1], v, mine[i][1]))
-                else:
-                    items_q2.append((mine[i][0], b, mine[i][1], v, -1))
             for kt in range(first_kv, last_kv):
                 first_q = kt if causal else 0
                 n_q = int(has[b, v, first_q:].sum())
@@ -132,10 +123,8 @@ def build_attn_work(vision_flag_cpu: Optional[torch.Tensor], batch: int, seqlen:
                 cover[v] = False
     items_q.sort(key=lambda t: -t[0])
     items_kv.sort(key=lambda t: -t[0])
-    items_q2.sort(key=lambda t: -t[0])
-    wq2 = torch.tensor([[b, qa, v, qb] for _, b, qa, v, qb in items_q2], dtype=torch.int32).reshape(-1, 4)
     wq = torch.tensor([[b, qt, v, 0] for _, b, qt, v in items_q], dtype=torch.int32).reshape(-1, 4)
     wkv = torch.tensor([[b, kt, v, fq] for _, b, kt, v, fq in items_kv], dtype=torch.int32).reshape(-1, 4)
     to = lambda t: None if t is None else torch.as_tensor(t, dtype=torch.int32).to(device)
     return AttnWork(wq.to(device), wkv.to(device), has.to(device), to(kv_start), to(kv_end), (cover[0], cover[1]),
-                    wq2.to(device), [w for w, _, _, _ in items_q])
+                    [w for w, _, _, _ in items_q])

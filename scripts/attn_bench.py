@@ -41,8 +41,6 @@ which = sys.argv[1:] or ["single", "dq", "dkv"]
 res = {}
 if "single" in which:
     res["fwd"] = timeit(lambda: ops.attn_fwd(Q, K0, V0, K1, V1, qf, w.work_q, None, None, None, B, T, H, D, True, scale, out=o))
-if "pair" in which:
-    res["fwd-pair"] = timeit(lambda: ops.attn_fwd(Q, K0, V0, K1, V1, qf, w.work_q2, None, None, None, B, T, H, D, True, scale, out=o, paired=True))
 if "stream" in which:
     o_ref, lse_ref = o.clone(), lse.clone()
     o2, lse2 = ops.attn_fwd(Q, K0, V0, K1, V1, qf, w.work_q, None, None, None, B, T, H, D, True, scale, kernel="stream", plan=PLAN)

@@ -31,7 +31,7 @@ for it in range(48):
     if int(t[it, 11]) == 0:
         break
     print(f"tile {it:2d} (wg {it & 1}): " + " ".join(f"{n}={int(t[it, s]) - t0 if int(t[it, s]) else -1}" for s, n in enumerate(names)))
-enames = ["e:waitdep", "e:dep", "e:Ofinal", "e:Ofree", "e:stored"]
+enames = ["e:start", "e:dep", "e:Ofinal", "e:Ofree", "e:stored"]
 for it in range(8):
     if int(t[it, 19]) == 0:
         break
