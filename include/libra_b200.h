@@ -199,6 +199,9 @@ int lb_attn_bwd_dkv(const void* Q, const void* K0, const void* V0, const void* K
                     const int32_t* work_kv, int n_work, const int32_t* kv_start, const int32_t* kv_end, void* dK0,
                     void* dV0, void* dK1, void* dV1, int batch, int seqlen, int heads, int head_dim, int causal,
                     float scale, void* stream);
+/* diagnostics: every CTA of subsequent lb_attn_bwd_dkv launches logs {q tiles, clock64 at entry, tile list ready, K/V
+ * landed, last MMA issued, all MMAs done, exit, -} into buf ([n_work*heads][8] int64, device memory).  NULL = off */
+int lb_attn_bwd_dkv_set_cta_log(void* buf);
 
 /* ---- tcgen05 GEMM ---------------------------------------------------------
  * C[M,N] = op(A) . op(B) (+ C when accumulate), bf16 inputs, fp32 accumulation in TMEM.

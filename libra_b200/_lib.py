@@ -44,6 +44,7 @@ SIGNATURES = {
     "lb_attn_fwd_stream": (I, [P, P, P, P, P, P, P, I, P, P, I, I, I, P, P, P, P, P, I, I, I, I, I, F, P]),
     "lb_attn_fwd_stream_max_cta_items": (I, []),
     "lb_attn_fwd_stream_set_cta_log": (I, [P]),
+    "lb_attn_bwd_dkv_set_cta_log": (I, [P]),
     "lb_attn_fwd_stream_set_trace": (I, [P]),
     "lb_attn_fwd_set_trace": (I, [P]),
     "lb_attn_bwd_prepare": (I, [P, P, P, P, P, I, I, I, I, P]),

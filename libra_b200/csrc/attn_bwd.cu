@@ -93,6 +93,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     uint8_t* sV = sK + S::K_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + DQ_NBAR);
+    const uint32_t bar0 = smem_u32(bars);                 // barrier i lives at bar0 + 8 i
 
     const int warp = threadIdx.x >> 5;
     int item, h;
@@ -138,11 +139,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             for (int it = 0; it < n_tiles; ++it) {
                 const int row_k = b * T + (first_tile + it) * BN;
                 const uint32_t ph = (uint32_t)it & 1u;
-                mbar_wait(bars + DQ_KEMPTY, ph ^ 1u);
+                wait_bar(bar0 + 8 * (DQ_KEMPTY), ph ^ 1u);
                 mbar_arrive_expect_tx(bars + DQ_KFULL, S::K_BYTES);
 #pragma unroll
                 for (int c = 0; c < D / 64; ++c) tma_load_2d(sK + c * (BN * 128), tK, bars + DQ_KFULL, h * D + c * 64, row_k);
-                mbar_wait(bars + DQ_VEMPTY, ph ^ 1u);
+                wait_bar(bar0 + 8 * (DQ_VEMPTY), ph ^ 1u);
                 mbar_arrive_expect_tx(bars + DQ_VFULL, S::V_BYTES);
 #pragma unroll
                 for (int c = 0; c < D / 64; ++c) tma_load_2d(sV + c * (BN * 128), tV, bars + DQ_VFULL, h * D + c * 64, row_k);
@@ -155,10 +156,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const uint32_t dQ0 = desc_lo_kmajor(smem_u32(sQ)), ddO0 = desc_lo_kmajor(smem_u32(sdO));
             const uint32_t dK0 = desc_lo_kmajor(smem_u32(sK)), dV0 = desc_lo_kmajor(smem_u32(sV));
             const uint32_t dKmn0 = desc_lo_mnmajor(smem_u32(sK), BN * 128);
-            mbar_wait(bars + DQ_QDO, 0);
+            wait_bar(bar0 + 8 * (DQ_QDO), 0);
             for (int it = 0; it < n_tiles; ++it) {
                 const uint32_t ph = (uint32_t)it & 1u;
-                mbar_wait(bars + DQ_KFULL, ph);
+                wait_bar(bar0 + 8 * (DQ_KFULL), ph);
                 tc_fence_after_sync();
 #pragma unroll
                 for (int kk = 0; kk < D / 16; ++kk) {
@@ -166,7 +167,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     const uint32_t offB = ((uint32_t)(kk / 4) * (BN * 128) + (uint32_t)(kk % 4) * 32) >> 4;
                     umma_ss_lo(tmem_base + COL_S, dQ0 + offA, dK0 + offB, idesc_s, kk ? 1u : 0u);
                 }
-                mbar_wait(bars + DQ_VFULL, ph);
+                wait_bar(bar0 + 8 * (DQ_VFULL), ph);
                 tc_fence_after_sync();
 #pragma unroll
                 for (int kk = 0; kk < D / 16; ++kk) {
@@ -174,16 +175,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                     const uint32_t offB = ((uint32_t)(kk / 4) * (BN * 128) + (uint32_t)(kk % 4) * 32) >> 4;
                     umma_ss_lo(tmem_base + COL_DP, ddO0 + offA, dV0 + offB, idesc_s, kk ? 1u : 0u);
                 }
-                tc_commit(bars + DQ_VEMPTY);
-                tc_commit(bars + DQ_SDP);
-                mbar_wait(bars + DQ_DS, ph);
+                commit_bar(bar0 + 8 * (DQ_VEMPTY));
+                commit_bar(bar0 + 8 * (DQ_SDP));
+                wait_bar(bar0 + 8 * (DQ_DS), ph);
                 tc_fence_after_sync();
 #pragma unroll
                 for (int kk = 0; kk < BN / 16; ++kk)     // dS of keys 16kk.. lives at column 32*(kk/2) + 8*(kk%2)
                     umma_ts_lo(tmem_base + COL_DQ, tmem_base + COL_S + (uint32_t)(kk / 2) * 32 + (uint32_t)(kk % 2) * 8,
                                dKmn0 + (uint32_t)kk * (2048 >> 4), idesc_dq, (it | kk) ? 1u : 0u);
-                tc_commit(bars + DQ_KEMPTY);
-                tc_commit(bars + DQ_READY);
+                commit_bar(bar0 + 8 * (DQ_KEMPTY));
+                commit_bar(bar0 + 8 * (DQ_READY));
             }
         }
     } else {
@@ -202,7 +203,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const uint32_t ph = (uint32_t)it & 1u;
             const int kv0 = (first_tile + it) * BN + half * 32;
             const bool need_mask = (CAUSAL && kv0 + 31 > q0) || (kv0 + 32 > kve) || (kv0 < kvs);
-            mbar_wait(bars + DQ_SDP, ph);
+            wait_bar(bar0 + 8 * (DQ_SDP), ph);
             tc_fence_after_sync();
             if (need_mask) dq_tile<true, CAUSAL>(lane_addr + colS, lane_addr + colDP, sl2, lse2, dlt, p.scale, kv0, qi, kvs, kve);
             else           dq_tile<false, CAUSAL>(lane_addr + colS, lane_addr + colDP, sl2, lse2, dlt, p.scale, kv0, qi, kvs, kve);
@@ -211,12 +212,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             mbar_arrive(bars + DQ_DS);
         }
         if (n_tiles > 0) {
-            mbar_wait(bars + DQ_READY, (uint32_t)(n_tiles - 1) & 1u);
+            wait_bar(bar0 + 8 * (DQ_READY), (uint32_t)(n_tiles - 1) & 1u);
             tc_fence_after_sync();
         }
-        constexpr int DH = D / 2;
-        __nv_bfloat16* orow = p.out0 + ((int64_t)b * T + (qi < T ? qi : 0)) * ((int64_t)p.heads * D) + (int64_t)h * D + half * DH;
-#pragma unroll 1
+        // dQ leaves through a per-warp staging tile (the Q/dO/K/V tiles are dead now): 32 rows x D/2 columns bf16, 16-byte
+        // chunks XOR-swizzled by row, written out as whole row segments (see the dK/dV epilogue in attn_bwd_dkv.cu)
+        constexpr int DH = D / 2, CH = DH / 8, RPI = 32 / CH;
+        const int lane = threadIdx.x & 31;
+        uint8_t* stage = smem + warp * (32 * DH * 2);
+        auto swz = [](int row, int chunk) { return CH == 8 ? (chunk ^ (row & 7)) : (chunk ^ ((row >> 1) & 3)); };
+#pragma unroll
         for (int c = 0; c < DH / 32; ++c) {
             uint32_t v[32];
             if (n_tiles > 0) {
@@ -226,18 +231,24 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = 0u;
             }
-            if (row_ok) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                    uint4 o;
-                    o.x = pack_bf16(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
-                    o.y = pack_bf16(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                    o.z = pack_bf16(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
-                    o.w = pack_bf16(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
-                    *reinterpret_cast<uint4*>(orow + c * 32 + j) = o;
-                }
+            for (int j = 0; j < 32; j += 8) {
+                uint4 o;
+                o.x = pack_bf16(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
+                o.y = pack_bf16(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                o.z = pack_bf16(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+                o.w = pack_bf16(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+                *reinterpret_cast<uint4*>(stage + lane * (DH * 2) + (swz(lane, c * 4 + (j >> 3)) << 4)) = o;
             }
-            __syncwarp();
+        }
+        __syncwarp();
+        const unsigned ok_mask = __ballot_sync(0xffffffffu, row_ok);
+        __nv_bfloat16* dst = p.out0 + ((int64_t)b * T + q0 + (warp & 3) * 32) * ((int64_t)p.heads * D) + (int64_t)h * D + half * DH;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            const int row = i * RPI + lane / CH, chunk = lane % CH;
+            const uint4 o = *reinterpret_cast<const uint4*>(stage + row * (DH * 2) + (swz(row, chunk) << 4));
+            if ((ok_mask >> row) & 1u) *reinterpret_cast<uint4*>(dst + (int64_t)row * ((int64_t)p.heads * D) + chunk * 8) = o;
         }
         tc_fence_before_sync();
     }

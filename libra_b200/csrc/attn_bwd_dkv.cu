@@ -35,6 +35,7 @@ struct AttnBwdParams {
     int batch, seqlen, heads;
     int n_work, head_group;
     float scale;
+    long long* cta_log;        // optional [grid][8]: q tiles, clock64 at entry / tile list ready / K,V landed / last MMA issued / all MMAs done / exit
 };
 
 // Score-tile helper with the mask as a template parameter (the common unmasked path carries no index arithmetic).
@@ -98,8 +99,11 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     float* stats = reinterpret_cast<float*>(smem + S::STAT_OFF);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + KV_NBAR);
+    const uint32_t bar0 = smem_u32(bars);                 // barrier i lives at bar0 + 8 i
 
     const int warp = threadIdx.x >> 5;
+    long long* clog = p.cta_log ? p.cta_log + (int64_t)blockIdx.x * 8 : nullptr;
+    if (clog && threadIdx.x == 0) clog[1] = clock64();
     int item, h;
     attn_cta_order(p.n_work, p.heads, p.head_group, item, h);
     const int b = p.work[item * 4 + 0];
@@ -121,46 +125,63 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     };
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < KV_NBAR; ++i) mbar_init(bars + i, (i == KV_PDS0 || i == KV_PDS1) ? 256 : 1);
+        for (int i = 0; i < KV_NBAR; ++i)
+            if (i != KV_KV) mbar_init(bars + i, (i == KV_PDS0 || i == KV_PDS1) ? 256 : 1);
         fence_barrier_init();
+    }
+    if (warp == KV_WARP_TMA && elect_one()) {
+        // K and V of this CTA's kv tile go out before anything else (their barrier is initialised right here): the load
+        // latency (~2-3 k clk) then overlaps the TMEM allocation, the tile list and the CTA-wide barrier below
+        mbar_init(bars + KV_KV, 1);
+        fence_barrier_init();
+        const CUtensorMap* tK = variant ? &tmK1 : &tmK0;
+        const CUtensorMap* tV = variant ? &tmV1 : &tmV0;
+        const int row_k = b * T + kv0;
+        mbar_arrive_expect_tx(bars + KV_KV, S::K_BYTES + S::V_BYTES);
+#pragma unroll
+        for (int c = 0; c < D / 64; ++c) {
+            tma_load_2d(sK + c * (128 * 128), tK, bars + KV_KV, h * D + c * 64, row_k);
+            tma_load_2d(sV + c * (128 * 128), tV, bars + KV_KV, h * D + c * 64, row_k);
+        }
     }
     if (warp == KV_WARP_MMA) {
         tmem_alloc(tmem_slot, TMEM_COLS);
         tmem_relinquish();
     }
-    // tile list in shared memory (<= 64 q tiles, T <= 8192)
+    // tile list in shared memory (<= 64 q tiles, T <= 8192): warps 0 and 1 read one flag per lane and compact them with
+    // ballots (one thread walking the bitmap cost a dependent global load per q tile: ~10 k clk for the first kv tiles)
     __shared__ int s_tiles[64];
     __shared__ int s_ntiles;
-    if (threadIdx.x == 32) {
-        int n = 0;
-        for (int qt = first_q; qt < nqt && n < 64; ++qt)
-            if (tile_has(qt)) s_tiles[n++] = qt;
-        s_ntiles = n;
+    __shared__ int s_cnt0;
+    if (warp < 2) {
+        const int qt = first_q + (int)threadIdx.x;
+        const bool has = qt < nqt && tile_has(qt);
+        const unsigned m = __ballot_sync(0xffffffffu, has);
+        if (threadIdx.x == 0) s_cnt0 = __popc(m);
+        asm volatile("bar.sync 15, 64;" ::: "memory");
+        const int base = warp ? s_cnt0 : 0;
+        if (has) s_tiles[base + __popc(m & ((1u << (threadIdx.x & 31)) - 1u))] = qt;
+        if (threadIdx.x == 32) s_ntiles = s_cnt0 + __popc(m);
     }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
     const int n_tiles = s_ntiles;
+    if (clog && threadIdx.x == 0) {
+        clog[0] = n_tiles;
+        clog[2] = clock64();
+    }
 
     if (warp == KV_WARP_TMA) {
         if (elect_one() && n_tiles > 0) {
-            const CUtensorMap* tK = variant ? &tmK1 : &tmK0;
-            const CUtensorMap* tV = variant ? &tmV1 : &tmV0;
-            const int row_k = b * T + kv0;
-            mbar_arrive_expect_tx(bars + KV_KV, S::K_BYTES + S::V_BYTES);
-#pragma unroll
-            for (int c = 0; c < D / 64; ++c) {
-                tma_load_2d(sK + c * (128 * 128), tK, bars + KV_KV, h * D + c * 64, row_k);
-                tma_load_2d(sV + c * (128 * 128), tV, bars + KV_KV, h * D + c * 64, row_k);
-            }
             for (int it = 0; it < n_tiles; ++it) {
                 const int st = it & 1;
                 const uint32_t ph = (uint32_t)(it >> 1) & 1u;
                 const int row_q = b * T + s_tiles[it] * 128;
                 uint8_t* q = sQ0 + st * (S::Q_BYTES + S::DO_BYTES);
                 uint8_t* d = q + S::Q_BYTES;
-                mbar_wait(bars + KV_QEMPTY0 + st, ph ^ 1u);
+                wait_bar(bar0 + 8 * (KV_QEMPTY0 + st), ph ^ 1u);
                 mbar_arrive_expect_tx(bars + KV_QFULL0 + st, S::Q_BYTES + S::DO_BYTES);
 #pragma unroll
                 for (int c = 0; c < D / 64; ++c) {
@@ -170,6 +191,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
         }
     } else if (warp == KV_WARP_MMA) {
+        if (n_tiles == 0 && elect_one()) wait_bar(bar0 + 8 * (KV_KV), 0);        // never exit with the K/V load in flight
         if (elect_one() && n_tiles > 0) {
             constexpr uint32_t idesc_g = make_idesc_bf16(128, D, 0, 1);
             const uint32_t dK0 = desc_lo_kmajor(smem_u32(sK)), dV0 = desc_lo_kmajor(smem_u32(sV));
@@ -190,7 +212,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     const uint32_t off = ((uint32_t)(kk / 4) * (128 * 128) + (uint32_t)(kk % 4) * 32) >> 4;
                     umma_ss_lo(tmem_base + COL_DP + half * 64, dV0 + off, ddOk + off + hoff, idesc_h, kk ? 1u : 0u);
                 }
-                tc_commit(bars + KV_SDP0 + half);
+                commit_bar(bar0 + 8 * (KV_SDP0 + half));
             };
             auto issue_grads = [&](int half, uint32_t dQmn, uint32_t ddOmn, bool first) {
 #pragma unroll
@@ -202,7 +224,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     umma_ts_lo(tmem_base + COL_DK, tmem_base + COL_DP + (uint32_t)half * 64 + (uint32_t)(kk / 2) * 32 + (uint32_t)(kk % 2) * 8,
                                dQmn + (uint32_t)(half * 4 + kk) * (2048 >> 4), idesc_g, (first && kk == 0) ? 0u : 1u);
             };
-            mbar_wait(bars + KV_KV, 0);
+            wait_bar(bar0 + 8 * (KV_KV), 0);
+            if (clog) clog[3] = clock64();
             uint32_t pQmn = 0, pdOmn = 0;            // MN-major descriptors of the previous tile's stage
             for (int it = 0; it < n_tiles; ++it) {
                 const int st = it & 1;
@@ -212,17 +235,17 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 const uint32_t adO = aQ + S::Q_BYTES;
                 const uint32_t dQk = desc_lo_kmajor(aQ), ddOk = desc_lo_kmajor(adO);
                 const uint32_t dQmn = desc_lo_mnmajor(aQ, 128 * 128), ddOmn = desc_lo_mnmajor(adO, 128 * 128);
-                mbar_wait(bars + KV_QFULL0 + st, phq);
+                wait_bar(bar0 + 8 * (KV_QFULL0 + st), phq);
                 tc_fence_after_sync();
                 issue_scores(0, dQk, ddOk);
                 if (it > 0) {
-                    mbar_wait(bars + KV_PDS1, ph ^ 1u);                  // half B of the previous tile
+                    wait_bar(bar0 + 8 * (KV_PDS1), ph ^ 1u);                  // half B of the previous tile
                     tc_fence_after_sync();
                     issue_grads(1, pQmn, pdOmn, false);
-                    tc_commit(bars + KV_QEMPTY0 + (st ^ 1));             // previous tile's Q/dO stage is free
+                    commit_bar(bar0 + 8 * (KV_QEMPTY0 + (st ^ 1)));             // previous tile's Q/dO stage is free
                 }
                 issue_scores(1, dQk, ddOk);
-                mbar_wait(bars + KV_PDS0, ph);
+                wait_bar(bar0 + 8 * (KV_PDS0), ph);
                 tc_fence_after_sync();
                 issue_grads(0, dQmn, ddOmn, it == 0);
                 pQmn = dQmn;
@@ -230,12 +253,13 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             }
             {
                 const int last = n_tiles - 1;
-                mbar_wait(bars + KV_PDS1, (uint32_t)last & 1u);
+                wait_bar(bar0 + 8 * (KV_PDS1), (uint32_t)last & 1u);
                 tc_fence_after_sync();
                 issue_grads(1, pQmn, pdOmn, false);
-                tc_commit(bars + KV_QEMPTY0 + (last & 1));
+                commit_bar(bar0 + 8 * (KV_QEMPTY0 + (last & 1)));
             }
-            tc_commit(bars + KV_DONE);
+            commit_bar(bar0 + 8 * (KV_DONE));
+            if (clog) clog[4] = clock64();
         }
     } else {
         // ---------------- compute warps: thread <-> kv row (TMEM lane).  Warpgroup g = warp/4 owns query columns [32g, 32g+32);
@@ -263,7 +287,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 else           sl[128 + col] = ok ? p.delta[si] : 0.f;
             }
             named_bar_sync(1 + half, 256);
-            mbar_wait(bars + KV_SDP0 + half, ph);
+            wait_bar(bar0 + 8 * (KV_SDP0 + half), ph);
             tc_fence_after_sync();
             const int qbase = qhalf + quarter * 32;
             // warp-uniform: tile straddles the key range or the causal diagonal (excluded query rows carry lse = +inf)
@@ -275,31 +299,42 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             mbar_arrive(bars + KV_PDS0 + half);
         }
         if (n_tiles > 0) {
-            mbar_wait(bars + KV_DONE, 0);
+            wait_bar(bar0 + 8 * (KV_DONE), 0);
             tc_fence_after_sync();
-            const bool row_ok = kj < T;
-            const int64_t off = ((int64_t)b * T + (row_ok ? kj : 0)) * ((int64_t)p.heads * D) + (int64_t)h * D;
-            // warpgroups 0,1 store the two halves of dV (TMEM columns [COL_DV, +D)), warpgroups 2,3 those of dK
-            constexpr int DH = D / 2;
-            __nv_bfloat16* dst_row = (wg < 2 ? (variant ? p.out3 : p.out1) : (variant ? p.out2 : p.out0)) + off + (wg & 1) * DH;
+            if (clog && threadIdx.x == 0) clog[5] = clock64();
+            // warpgroups 0,1 store the two halves of dV (TMEM columns [COL_DV, +D)), warpgroups 2,3 those of dK.  The K/V/Q/dO
+            // tiles are dead now: each warp stages its 32 rows x D/2 columns (bf16) in shared memory, 16-byte chunks XOR-
+            // swizzled by row, and writes whole 128-byte (D=128) row segments -- one row per lane costs 32 LSU wavefronts
+            // per store instruction and made this epilogue ~6 k clk of a ~37 k clk CTA.
+            constexpr int DH = D / 2, CH = DH / 8, RPI = 32 / CH;      // 16-byte chunks per row, rows per store instruction
+            const int lane = threadIdx.x & 31;
+            uint8_t* stage = smem + warp * (32 * DH * 2);
+            __nv_bfloat16* dst = (wg < 2 ? (variant ? p.out3 : p.out1) : (variant ? p.out2 : p.out0)) + (int64_t)h * D + (wg & 1) * DH;
             const uint32_t col0 = (wg < 2 ? COL_DV : COL_DK) + (wg & 1) * DH;
-#pragma unroll 1
+            auto swz = [](int row, int chunk) { return CH == 8 ? (chunk ^ (row & 7)) : (chunk ^ ((row >> 1) & 3)); };
+#pragma unroll
             for (int c = 0; c < DH / 32; ++c) {
                 uint32_t v[32];
                 tmem_ld32(lane_addr + col0 + c * 32, v);
                 tc_wait_ld();
-                if (row_ok) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        uint4 o;
-                        o.x = pack_bf16(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
-                        o.y = pack_bf16(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-                        o.z = pack_bf16(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
-                        o.w = pack_bf16(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
-                        *reinterpret_cast<uint4*>(dst_row + c * 32 + j) = o;
-                    }
+                for (int j = 0; j < 32; j += 8) {
+                    uint4 o;
+                    o.x = pack_bf16(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
+                    o.y = pack_bf16(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                    o.z = pack_bf16(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+                    o.w = pack_bf16(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+                    *reinterpret_cast<uint4*>(stage + lane * (DH * 2) + (swz(lane, c * 4 + (j >> 3)) << 4)) = o;
                 }
-                __syncwarp();
+            }
+            __syncwarp();
+            const int row0 = kv0 + (warp & 3) * 32;
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+                const int row = i * RPI + lane / CH, chunk = lane % CH;
+                const uint4 o = *reinterpret_cast<const uint4*>(stage + row * (DH * 2) + (swz(row, chunk) << 4));
+                if (row0 + row < T)
+                    *reinterpret_cast<uint4*>(dst + ((int64_t)b * T + row0 + row) * ((int64_t)p.heads * D) + chunk * 8) = o;
             }
         }
         tc_fence_before_sync();
@@ -309,6 +344,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
+    if (clog && threadIdx.x == 0) clog[6] = clock64();
 }
 
 template <typename KernT>
@@ -349,7 +385,16 @@ static int make_maps(CUtensorMap* tm, const void* Q, const void* dO, const void*
 using namespace lb;
 using namespace lb::dkv;
 
+static long long* g_dkv_cta_log = nullptr;
+
 extern "C" {
+
+/* diagnostics: every CTA of subsequent lb_attn_bwd_dkv launches logs {q tiles, clock64 at entry, tile list ready, K/V
+ * landed, last MMA issued, all MMAs done, exit, -} into buf ([n_work*heads][8] int64, device memory).  NULL = off */
+int lb_attn_bwd_dkv_set_cta_log(void* buf) {
+    g_dkv_cta_log = (long long*)buf;
+    return LB_OK;
+}
 
 int lb_attn_bwd_dkv(const void* Q, const void* K0, const void* V0, const void* K1, const void* V1, const void* dO,
                     const float* lse, const float* delta, const uint8_t* qflag, const uint8_t* qtile_has,
@@ -372,6 +417,7 @@ int lb_attn_bwd_dkv(const void* Q, const void* K0, const void* V0, const void* K
     p.out2 = (__nv_bfloat16*)(dK1 ? dK1 : dK0); p.out3 = (__nv_bfloat16*)(dV1 ? dV1 : dV0);
     p.batch = batch; p.seqlen = seqlen; p.heads = heads; p.scale = scale;
     p.n_work = n_work; p.head_group = attn_head_group();
+    p.cta_log = g_dkv_cta_log;
     cudaStream_t st = (cudaStream_t)stream;
     if (head_dim == 128) return causal ? launch_dkv<128, true>(tm, p, n_work, st) : launch_dkv<128, false>(tm, p, n_work, st);
     return causal ? launch_dkv<64, true>(tm, p, n_work, st) : launch_dkv<64, false>(tm, p, n_work, st);

@@ -113,38 +113,6 @@ enum {
 // complete; where the stream would allow a role to run further ahead (the owner of a one-tile item, the rescale path)
 // the wait goes through a barrier that cannot be more than one phase behind (PFREE of the role's own tile).
 //
-// spin on an mbarrier phase (shared-window address).  Lean on the fast path: the single-thread roles execute one
-// dependent instruction every ~5 clk, so every instruction between two tcgen05.mma batches is tensor-pipe idle time.
-__device__ __forceinline__ void wait_bar(uint32_t bar_addr, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, P;\n\t"
-        "}\n"
-        : "=r"(ok)
-        : "r"(bar_addr), "r"(parity)
-        : "memory");
-    if (ok) return;
-    uint32_t spins = 0;
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred P;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
-            "selp.b32 %0, 1, 0, P;\n\t"
-            "}\n"
-            : "=r"(ok)
-            : "r"(bar_addr), "r"(parity)
-            : "memory");
-        if (++spins > LB_MBAR_SPIN_LIMIT) __trap();              // protocol bug: fail instead of hanging the device
-    } while (!ok);
-}
-__device__ __forceinline__ void commit_bar(uint32_t bar_addr) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
-}
-
 // list position of the CTA's k-th item, or -1.  Without a plan: round k takes list position k*G + c, alternating
 // direction (the list is sorted heaviest first inside a head group, so the snake keeps the per-CTA sums close)
 __device__ __forceinline__ int item_of_round(const Params& p, int k) {

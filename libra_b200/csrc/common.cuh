@@ -141,6 +141,39 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Lean variants for the attention kernels' hot loops (shared-window barrier address precomputed by the caller, no printf
+// on the slow path): a single-thread role executes one dependent instruction every ~5-10 clk, so every instruction between
+// two tcgen05.mma batches is tensor-pipe idle time (profiles/r01_attn_fwd_stream_notes.md).
+__device__ __forceinline__ void wait_bar(uint32_t bar_addr, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar_addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    uint32_t spins = 0;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, P;\n\t"
+            "}\n"
+            : "=r"(ok)
+            : "r"(bar_addr), "r"(parity)
+            : "memory");
+        if (++spins > LB_MBAR_SPIN_LIMIT) __trap();              // protocol bug: fail instead of hanging the device
+    } while (!ok);
+}
+__device__ __forceinline__ void commit_bar(uint32_t bar_addr) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
+}
+
 // Attention CTA order.  The grid is 1-D over (work item, head); work items are sorted heaviest first.  Heads run in
 // groups of `group`: inside a group all heads of the heaviest item come first, so (a) the CTAs resident at one time
 // touch the K/V of `group` heads only (L2-resident working set) and (b) the grid ends with the lightest items of the
