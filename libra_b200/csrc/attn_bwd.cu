@@ -219,7 +219,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         // chunks XOR-swizzled by row, written out as whole row segments (see the dK/dV epilogue in attn_bwd_dkv.cu)
         constexpr int DH = D / 2, CH = DH / 8, RPI = 32 / CH;
         const int lane = threadIdx.x & 31;
-        uint8_t* stage = smem + warp * (32 * DH * 2);
+        const uint32_t stage_s = smem_u32(smem) + warp * (32 * DH * 2);
         auto swz = [](int row, int chunk) { return CH == 8 ? (chunk ^ (row & 7)) : (chunk ^ ((row >> 1) & 3)); };
 #pragma unroll
         for (int c = 0; c < DH / 32; ++c) {
@@ -238,7 +238,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 o.y = pack_bf16(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
                 o.z = pack_bf16(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
                 o.w = pack_bf16(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
-                *reinterpret_cast<uint4*>(stage + lane * (DH * 2) + (swz(lane, c * 4 + (j >> 3)) << 4)) = o;
+                sts128(stage_s + lane * (DH * 2) + (swz(lane, c * 4 + (j >> 3)) << 4), o);
             }
         }
         __syncwarp();
@@ -247,7 +247,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
         for (int i = 0; i < CH; ++i) {
             const int row = i * RPI + lane / CH, chunk = lane % CH;
-            const uint4 o = *reinterpret_cast<const uint4*>(stage + row * (DH * 2) + (swz(row, chunk) << 4));
+            const uint4 o = lds128(stage_s + row * (DH * 2) + (swz(row, chunk) << 4));
             if ((ok_mask >> row) & 1u) *reinterpret_cast<uint4*>(dst + (int64_t)row * ((int64_t)p.heads * D) + chunk * 8) = o;
         }
         tc_fence_before_sync();

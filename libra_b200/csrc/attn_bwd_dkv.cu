@@ -42,25 +42,34 @@ struct AttnBwdParams {
 // All TMEM reads of a tile are issued up front and waited for once; results are packed in place.
 // dK/dV kernel: thread = key row; 32 query columns at TMEM `ts` (S^T) / `tdp` (dP^T); per-column lse2 / delta in smem.
 template <bool MASK, bool CAUSAL>
-__device__ __forceinline__ void dkv_tile(uint32_t ts, uint32_t tdp, const float* __restrict__ st, float sl2, float scale, int kj,
+__device__ __forceinline__ void dkv_tile(uint32_t ts, uint32_t tdp, uint32_t st_s, float sl2, float scale, int kj,
                                          int qbase, bool key_ok) {
+    // st_s: shared-window address of this thread's 32 lse2 values; the 32 deltas sit 512 bytes further (LDS.128 instead of
+    // one generic load per column)
     uint32_t s[32], dp[32];
     tmem_ld32(ts, s);
     tmem_ld32(tdp, dp);
     tc_wait_ld();
 #pragma unroll
-    for (int j = 0; j < 32; j += 2) {
-        float p0 = fast_ex2(fmaf(__uint_as_float(s[j]), sl2, -st[j]));          // lse = +inf on excluded query rows
-        float p1 = fast_ex2(fmaf(__uint_as_float(s[j + 1]), sl2, -st[j + 1]));
-        if (MASK) {
-            const int qa = qbase + j;
-            p0 = (key_ok && (!CAUSAL || kj <= qa)) ? p0 : 0.f;
-            p1 = (key_ok && (!CAUSAL || kj <= qa + 1)) ? p1 : 0.f;
+    for (int j = 0; j < 32; j += 4) {
+        float4 ls, dl;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(ls.x), "=f"(ls.y), "=f"(ls.z), "=f"(ls.w) : "r"(st_s + j * 4));
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(dl.x), "=f"(dl.y), "=f"(dl.z), "=f"(dl.w) : "r"(st_s + 512 + j * 4));
+        const float lse4[4] = {ls.x, ls.y, ls.z, ls.w}, dl4[4] = {dl.x, dl.y, dl.z, dl.w};
+#pragma unroll
+        for (int u = 0; u < 4; u += 2) {
+            float p0 = fast_ex2(fmaf(__uint_as_float(s[j + u]), sl2, -lse4[u]));          // lse = +inf on excluded query rows
+            float p1 = fast_ex2(fmaf(__uint_as_float(s[j + u + 1]), sl2, -lse4[u + 1]));
+            if (MASK) {
+                const int qa = qbase + j + u;
+                p0 = (key_ok && (!CAUSAL || kj <= qa)) ? p0 : 0.f;
+                p1 = (key_ok && (!CAUSAL || kj <= qa + 1)) ? p1 : 0.f;
+            }
+            const float d0 = p0 * (__uint_as_float(dp[j + u]) - dl4[u]) * scale;
+            const float d1 = p1 * (__uint_as_float(dp[j + u + 1]) - dl4[u + 1]) * scale;
+            s[(j + u) >> 1] = pack_bf16(p0, p1);
+            dp[(j + u) >> 1] = pack_bf16(d0, d1);
         }
-        const float d0 = p0 * (__uint_as_float(dp[j]) - st[128 + j]) * scale;
-        const float d1 = p1 * (__uint_as_float(dp[j + 1]) - st[128 + j + 1]) * scale;
-        s[j >> 1] = pack_bf16(p0, p1);
-        dp[j >> 1] = pack_bf16(d0, d1);
     }
     tmem_st16(ts, s);        // P^T (bf16, 16 columns) over my own, already consumed S^T columns
     tmem_st16(tdp, dp);      // dS^T over dP^T
@@ -292,8 +301,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const int qbase = qhalf + quarter * 32;
             // warp-uniform: tile straddles the key range or the causal diagonal (excluded query rows carry lse = +inf)
             const bool need_mask = (kv0 + 128 > kve) || (kv0 < kvs) || (CAUSAL && kv0 + 127 > qbase);
-            if (need_mask) dkv_tile<true, CAUSAL>(lane_addr + colS, lane_addr + colDP, sl + quarter * 32, sl2, p.scale, kj, qbase, key_ok);
-            else           dkv_tile<false, CAUSAL>(lane_addr + colS, lane_addr + colDP, sl + quarter * 32, sl2, p.scale, kj, qbase, key_ok);
+            const uint32_t st_s = smem_u32(sl + quarter * 32);
+            if (need_mask) dkv_tile<true, CAUSAL>(lane_addr + colS, lane_addr + colDP, st_s, sl2, p.scale, kj, qbase, key_ok);
+            else           dkv_tile<false, CAUSAL>(lane_addr + colS, lane_addr + colDP, st_s, sl2, p.scale, kj, qbase, key_ok);
             tc_wait_st();
             tc_fence_before_sync();
             mbar_arrive(bars + KV_PDS0 + half);
@@ -308,7 +318,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             // per store instruction and made this epilogue ~6 k clk of a ~37 k clk CTA.
             constexpr int DH = D / 2, CH = DH / 8, RPI = 32 / CH;      // 16-byte chunks per row, rows per store instruction
             const int lane = threadIdx.x & 31;
-            uint8_t* stage = smem + warp * (32 * DH * 2);
+            const uint32_t stage_s = smem_u32(smem) + warp * (32 * DH * 2);
             __nv_bfloat16* dst = (wg < 2 ? (variant ? p.out3 : p.out1) : (variant ? p.out2 : p.out0)) + (int64_t)h * D + (wg & 1) * DH;
             const uint32_t col0 = (wg < 2 ? COL_DV : COL_DK) + (wg & 1) * DH;
             auto swz = [](int row, int chunk) { return CH == 8 ? (chunk ^ (row & 7)) : (chunk ^ ((row >> 1) & 3)); };
@@ -324,7 +334,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                     o.y = pack_bf16(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
                     o.z = pack_bf16(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
                     o.w = pack_bf16(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
-                    *reinterpret_cast<uint4*>(stage + lane * (DH * 2) + (swz(lane, c * 4 + (j >> 3)) << 4)) = o;
+                    sts128(stage_s + lane * (DH * 2) + (swz(lane, c * 4 + (j >> 3)) << 4), o);
                 }
             }
             __syncwarp();
@@ -332,7 +342,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
             for (int i = 0; i < CH; ++i) {
                 const int row = i * RPI + lane / CH, chunk = lane % CH;
-                const uint4 o = *reinterpret_cast<const uint4*>(stage + row * (DH * 2) + (swz(row, chunk) << 4));
+                const uint4 o = lds128(stage_s + row * (DH * 2) + (swz(row, chunk) << 4));
                 if (row0 + row < T)
                     *reinterpret_cast<uint4*>(dst + ((int64_t)b * T + row0 + row) * ((int64_t)p.heads * D) + chunk * 8) = o;
             }

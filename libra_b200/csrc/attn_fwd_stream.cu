@@ -563,8 +563,8 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                 }
                 const float inv_l = l_tot > 0.f ? 1.f / l_tot : 0.f;
                 if (threadIdx.x == w * 128) FS_TRACE(19, ic);         // epilogue: deposit seen
-                uint32_t ov[D];
                 if (n > 0) {
+                    uint32_t ov[D];
                     const uint32_t Gl = g + (uint32_t)n - 1u;             // my last tile: its PV is the item's last MMA
                     wait_bar(bar0 + 8 * (B_PFREE + (Gl & 1u)), (Gl >> 1) & 1u);
                     tc_fence_after_sync();
@@ -575,19 +575,26 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                     tc_fence_before_sync();
                     mbar_arrive(bars + B_OFREE);                      // O is in registers: the next item's PV may start
                     if (threadIdx.x == w * 128) FS_TRACE(21, ic);     // epilogue: O released
-                } else {
-#pragma unroll
-                    for (int e = 0; e < D; ++e) ov[e] = 0u;
-                }
-                // O leaves through a per-warp staging tile (32 rows x 32 columns bf16 at a time, 16-byte chunks XOR-swizzled by
-                // row) so that a store instruction covers 8 rows x 64 contiguous bytes; one row per lane costs 32 LSU
-                // wavefronts per instruction and held the owner for ~3.2 k clk per item.
-                {
-                    uint8_t* stage = smem + S::STAGE_OFF + (w * 4 + (warp & 3)) * (32 * 64);
+                    // O leaves through a per-warp staging tile (32 rows x 32 columns bf16 at a time, 16-byte chunks XOR-swizzled
+                    // by row) so that a store instruction covers 8 rows x 64 contiguous bytes.  Shared-window addresses and the
+                    // four destination pointers are set up once per item: the first version of this block compiled to ~2400
+                    // instructions of generic LD/ST and 64-bit address arithmetic and held the owner for ~3 k clk per item.
                     const int lane = threadIdx.x & 31;
+                    const uint32_t stage_s = smem_u32(smem + S::STAGE_OFF) + (uint32_t)(w * 4 + (warp & 3)) * (32 * 64);
+                    const uint32_t my_row_s = stage_s + (uint32_t)lane * 64;
+                    const uint32_t my_swz = (uint32_t)(lane >> 1) & 3u;
                     const int32_t dst32 = row_ok ? (int32_t)dst : -1;
-                    __nv_bfloat16* obase = p.O + (int64_t)it.h * D;
                     const int64_t ld_o = (int64_t)p.heads * D;
+                    __nv_bfloat16* obase = p.O + (int64_t)it.h * D + (lane & 3) * 8;
+                    uint32_t rd_s[4];
+                    __nv_bfloat16* gp[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int row = i * 8 + (lane >> 2);
+                        const int32_t drow = __shfl_sync(0xffffffffu, dst32, row);
+                        rd_s[i] = stage_s + (uint32_t)row * 64 + ((((uint32_t)lane & 3u) ^ ((uint32_t)(row >> 1) & 3u)) << 4);
+                        gp[i] = drow >= 0 ? obase + (int64_t)drow * ld_o : nullptr;
+                    }
 #pragma unroll
                     for (int q = 0; q < D / 32; ++q) {
 #pragma unroll
@@ -598,18 +605,20 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                             o.y = pack_bf16(__uint_as_float(ov[e + 2]) * inv_l, __uint_as_float(ov[e + 3]) * inv_l);
                             o.z = pack_bf16(__uint_as_float(ov[e + 4]) * inv_l, __uint_as_float(ov[e + 5]) * inv_l);
                             o.w = pack_bf16(__uint_as_float(ov[e + 6]) * inv_l, __uint_as_float(ov[e + 7]) * inv_l);
-                            *reinterpret_cast<uint4*>(stage + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) = o;
+                            sts128(my_row_s + (((uint32_t)c ^ my_swz) << 4), o);
                         }
                         __syncwarp();
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            const int row = i * 8 + (lane >> 2), chunk = lane & 3;
-                            const int32_t drow = __shfl_sync(0xffffffffu, dst32, row);
-                            const uint4 o = *reinterpret_cast<const uint4*>(stage + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
-                            if (drow >= 0) *reinterpret_cast<uint4*>(obase + (int64_t)drow * ld_o + q * 32 + chunk * 8) = o;
+                            const uint4 o = lds128(rd_s[i]);
+                            if (gp[i]) *reinterpret_cast<uint4*>(gp[i] + q * 32) = o;
                         }
                         __syncwarp();
                     }
+                } else if (row_ok) {                                  // no visible key at all: the row is zero
+                    uint4* orow = reinterpret_cast<uint4*>(p.O + dst * ((int64_t)p.heads * D) + (int64_t)it.h * D);
+#pragma unroll
+                    for (int e = 0; e < D / 8; ++e) orow[e] = make_uint4(0u, 0u, 0u, 0u);
                 }
                 if (row_ok && p.lse) {
                     // natural-log LSE of the scaled scores; +inf marks a row with no visible key (P == 0 in backward)
@@ -631,6 +640,7 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         unsigned smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         int n_it = 0, tiles = 0;
+#pragma unroll 1
         for (int k = 0; k < MAX_ITEMS && items[k].b >= 0; ++k) {
             ++n_it;
             tiles += items[k].n_tiles;

@@ -174,6 +174,17 @@ __device__ __forceinline__ void commit_bar(uint32_t bar_addr) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
 }
 
+// 16-byte shared-memory accesses by shared-window address (generic pointers into dynamic shared memory make nvcc emit
+// generic LD/ST with 64-bit address arithmetic; in the once-per-item epilogues that was most of the instruction count)
+__device__ __forceinline__ void sts128(uint32_t saddr, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t saddr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
+    return v;
+}
+
 // Attention CTA order.  The grid is 1-D over (work item, head); work items are sorted heaviest first.  Heads run in
 // groups of `group`: inside a group all heads of the heaviest item come first, so (a) the CTAs resident at one time
 // touch the K/V of `group` heads only (L2-resident working set) and (b) the grid ends with the lightest items of the

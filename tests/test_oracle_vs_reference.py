@@ -102,3 +102,47 @@ def test_clip_full_depth_shapes(ref):
     got = O.clip_vision_hidden_states(dict(model.state_dict()), O.ClipDims(**{k: v for k, v in TINY_CLIP.items() if k != "num_channels"}), px)
     for a, b in zip(got, want):
         assert (a - b).abs().max() < 3e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_cached_decode_matches_reference(ref, dtype):
+    """N1: prefill with use_cache=True, then one-token steps (text, <img>, grid tokens, </img>) through the reference's own
+    cache tuple; the oracle's libra_forward_cached must give the same logits and the same cache at every step, and the
+    stepwise logits must equal the full-sequence forward's last-position logits."""
+    from oracle.make_golden import make_libra_inputs
+    cfg, model = _tiny(ref, 11)
+    model = model.to(dtype)
+    d = O.LibraDims.from_config(cfg)
+    sd = dict(model.state_dict())
+    inp = make_libra_inputs(cfg.vocab_size, cfg.contiguous_signal_size, B=2, n_text=9, pad_last=0, seed=5)
+    ids, vi, am = inp["input_ids"], inp["vision_indices"], inp["attention_mask"]
+    sig = inp["contiguous_signal"].to(dtype)
+    tol = 3e-6 if dtype == torch.float32 else 8e-2
+    V, L = cfg.vocab_size, cfg.max_vision_token_length
+    with torch.no_grad():
+        r = model(input_ids=ids, attention_mask=am, vision_indices=vi, contiguous_signal=sig, use_cache=True)
+        o = O.libra_forward_cached(sd, d, ids, vi, attention_mask=am, contiguous_signal=sig, newline_token_id=cfg.newline_token_id)
+        fin = torch.isfinite(r.logits)
+        assert torch.equal(fin, torch.isfinite(o["logits"]))
+        assert (r.logits[fin].float() - o["logits"][fin].float()).abs().max() < tol
+        rp, op = r.past_key_values, o["past_key_values"]
+        # new tokens: sample 0 continues with text, sample 1 opens an image; then both advance (grid tokens / text), ...
+        g = torch.Generator().manual_seed(3)
+        steps = [([7, V + 512], [L, 0]), ([9, V + 3], [L, 1]), ([11, V + 200], [L, 2]), ([5, V + 513], [L, L - 1]), ([8, 13], [L, L])]
+        for tok, vidx in steps:
+            nid = torch.tensor(tok)[None, :, None].repeat(2, 1, 1)
+            nid[1] = torch.where(nid[0] >= V, torch.randint(V, V + 512, nid[0].shape, generator=g), nid[0])
+            nvi = torch.tensor(vidx)[:, None]
+            am = torch.cat([am, am.new_ones(am.shape[0], 1)], dim=1)
+            pos = (am.long().cumsum(-1) - 1)[:, -1:]
+            r = model(input_ids=nid, attention_mask=am, vision_indices=nvi, position_ids=pos, past_key_values=rp, use_cache=True)
+            o = O.libra_forward_cached(sd, d, nid, nvi, attention_mask=am, position_ids=pos, past_key_values=op,
+                                       newline_token_id=cfg.newline_token_id)
+            fin = torch.isfinite(r.logits)
+            assert torch.equal(fin, torch.isfinite(o["logits"]))
+            assert (r.logits[fin].float() - o["logits"][fin].float()).abs().max() < tol
+            rp, op = r.past_key_values, o["past_key_values"]
+            for lr, lo in zip(rp, op):
+                assert (lr[0][0].float() - lo[0][0].float()).abs().max() < tol and (lr[0][1].float() - lo[0][1].float()).abs().max() < tol
+                assert (lr[1].float() - lo[1].float()).abs().max() < tol and (lr[2].float() - lo[2].float()).abs().max() < tol
+                assert torch.equal(lr[3], lo[3])
