@@ -203,6 +203,20 @@ int lb_attn_bwd_dkv(const void* Q, const void* K0, const void* V0, const void* K
  * landed, last MMA issued, all MMAs done, exit, -} into buf ([n_work*heads][8] int64, device memory).  NULL = off */
 int lb_attn_bwd_dkv_set_cta_log(void* buf);
 
+/* ---- N1: KV-cached decode step of the bridge attention ---------------------
+ * libra/models/libra/modeling_libra.py:343-397 with past_key_value, q_len = 1 (prepare_inputs_for_generation :1190-1231).
+ * q [B, H*D] = rope(q) of the new tokens; the cache holds the operand tensors of lb_attn_prep_fwd for every position so
+ * far, new token included: K0/V0 = Kfl/Vfl (what language queries see), K1/V1 = Kfv/Vfv (what vision queries see), each
+ * [B, capacity, H*D] bf16, positions [0, kv_len) filled.  qflag[b] = 1 if sample b's new token is a vision token (NULL:
+ * all language).  kv_start/kv_end [B]: the sample's visible key range (left padding / shorter samples; NULL: [0, kv_len)).
+ * out [B, H*D] bf16, sample b at row out_row[b] (NULL: b).  The keys are split n_split ways; workspace = fp32
+ * [lb_attn_decode_workspace_floats(...)] owned by the caller.  HBM-bound: 2 * (kv_end-kv_start) * H*D * 2 bytes read
+ * per sample. */
+int lb_attn_decode_workspace_floats(int batch, int heads, int head_dim, int n_split);
+int lb_attn_decode(const void* q, const void* K0, const void* V0, const void* K1, const void* V1, const uint8_t* qflag,
+                   const int32_t* kv_start, const int32_t* kv_end, const int32_t* out_row, float* workspace, void* out,
+                   int batch, int heads, int head_dim, int capacity, int kv_len, int n_split, float scale, void* stream);
+
 /* ---- tcgen05 GEMM ---------------------------------------------------------
  * C[M,N] = op(A) . op(B) (+ C when accumulate), bf16 inputs, fp32 accumulation in TMEM.
  *  trans_a = 0: A stored [M,K] (K contiguous);  1: A stored [K,M]

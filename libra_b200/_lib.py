@@ -45,6 +45,8 @@ SIGNATURES = {
     "lb_attn_fwd_stream_max_cta_items": (I, []),
     "lb_attn_fwd_stream_set_cta_log": (I, [P]),
     "lb_attn_bwd_dkv_set_cta_log": (I, [P]),
+    "lb_attn_decode_workspace_floats": (I, [I, I, I, I]),
+    "lb_attn_decode": (I, [P, P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, F, P]),
     "lb_attn_fwd_stream_set_trace": (I, [P]),
     "lb_attn_fwd_set_trace": (I, [P]),
     "lb_attn_bwd_prepare": (I, [P, P, P, P, P, I, I, I, I, P]),
@@ -102,7 +104,7 @@ KERNELS_PER_CALL = {
     "lb_swiglu_bwd": 1, "lb_bias_quick_gelu_fwd": 1, "lb_bias_quick_gelu_bwd": 1, "lb_gather_rows": 1,
     "lb_embed_lang_fwd": 1, "lb_embed_vision_cat_fwd": 3, "lb_embed_bwd": 1, "lb_lfq_pack": 1, "lb_lfq_unpack": 1,
     "lb_attn_prep_fwd": 1, "lb_attn_prep_bwd": 1, "lb_attn_fwd": 1, "lb_attn_fwd_stream": 1, "lb_attn_bwd_prepare": 1, "lb_attn_bwd_dq": 1,
-    "lb_attn_bwd_dkv": 1, "lb_gemm_bf16": 1, "lb_patch_embed_fwd": 1, "lb_patch_embed_pack_weight": 1, "lb_cross_entropy_fwd_bwd": 1, "lb_probe_umma": 1, "lb_adamw_bf16": 1,
+    "lb_attn_bwd_dkv": 1, "lb_attn_decode": 2, "lb_gemm_bf16": 1, "lb_patch_embed_fwd": 1, "lb_patch_embed_pack_weight": 1, "lb_cross_entropy_fwd_bwd": 1, "lb_probe_umma": 1, "lb_adamw_bf16": 1,
 }
 launch_counts: dict = {}
 

@@ -482,6 +482,13 @@ class AttnMeta:
     seqlen: int
     heads: int
     head_dim: int
+    # decode path (N1): the cache the layers append their key/value operands to, the layer in flight, and -- for a one-token
+    # step -- the visible key range per sample (int32 [B] or None)
+    kv_cache: Optional[object] = None
+    layer_idx: int = 0
+    decode: bool = False
+    dec_kv_start: Optional[torch.Tensor] = None
+    dec_kv_end: Optional[torch.Tensor] = None
 
 
 class BridgeAttention(torch.autograd.Function):
@@ -505,6 +512,14 @@ class BridgeAttention(torch.autograd.Function):
         del kc, vc
         scale = 1.0 / math.sqrt(meta.head_dim)
         o = torch.empty_like(q)
+        if meta.kv_cache is not None:                      # use_cache=True (modeling_libra.py:343-361): inference only
+            cache = meta.kv_cache
+            cache.append(meta.layer_idx, Kfv, Kfl, Vfv, Vfl, meta.seqlen)
+            if meta.decode:
+                i = meta.layer_idx
+                ops.attn_decode(Q, cache.k_fl[i], cache.v_fl[i], cache.k_fv[i], cache.v_fv[i], rt.flag_orig, meta.dec_kv_start,
+                                meta.dec_kv_end, rt.inv, meta.batch, meta.heads, meta.head_dim, cache.length + 1, scale, out=o)
+                return o
         # variant 0 = language queries (see Kfl/Vfl), variant 1 = vision queries (see Kfv/Vfv); rows land in sorted order
         kern, wlist, plan = _fwd_choice(w, meta.heads)
         o, lse = ops.attn_fwd(Q, Kfl, Vfl, Kfv, Vfv, rt.flag_orig, wlist, w.kv_start,

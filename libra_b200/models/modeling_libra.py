@@ -285,6 +285,36 @@ class LibraModel(LibraPreTrainedModel):
         H = self.config.num_attention_heads
         return LF.AttnMeta(rt, work, pos, cos, sin, B, T, H, self.config.hidden_size // H)
 
+    def build_decode_meta(self, vision_flag: torch.Tensor, attention_mask: Optional[torch.Tensor],
+                          position_ids: Optional[torch.Tensor], cache) -> LF.AttnMeta:
+        """Metadata of a one-token step (N1): B rows, one per sample (language rows first), the visible key range of every
+        sample from its attention mask over past + new positions (modeling_libra.py:761-763 with a past)."""
+        B = vision_flag.shape[0]
+        dev = vision_flag.device
+        Tk = cache.length + 1
+        rt_cpu = schedule.build_routing(vision_flag.detach().to("cpu"))
+        rt = schedule.Routing(rt_cpu.n_tokens, rt_cpu.n_lang, rt_cpu.n_vis, rt_cpu.perm.to(dev), rt_cpu.inv.to(dev),
+                              rt_cpu.flag_sorted.to(dev), rt_cpu.flag_orig.to(dev))
+        kv_start = kv_end = None
+        if attention_mask is not None:
+            am = attention_mask.to(dev).to(torch.bool)
+            if am.shape != (B, Tk):
+                raise ValueError(f"attention_mask must cover past and new positions: expected {(B, Tk)}, got {tuple(am.shape)}")
+            if not bool(am.all()):
+                idx = torch.arange(Tk, device=dev)[None]
+                kv_start = torch.where(am, idx, Tk).amin(dim=1).to(torch.int32)
+                kv_end = (torch.where(am, idx, -1).amax(dim=1) + 1).to(torch.int32)
+                if not bool((am.sum(dim=1) == (kv_end - kv_start).clamp(min=0)).all()):
+                    raise NotImplementedError("attention_mask must be one contiguous run of ones per sample")
+        if position_ids is None:
+            pos = torch.full((B,), cache.length, device=dev, dtype=torch.int32)
+        else:
+            pos = position_ids.to(dev).reshape(-1).to(torch.int32).contiguous()
+        cos, sin = self._rope_tables(int(pos.max().item()) + 1, dev)
+        H = self.config.num_attention_heads
+        return LF.AttnMeta(rt, None, pos, cos, sin, B, 1, H, self.config.hidden_size // H, kv_cache=cache, decode=True,
+                           dec_kv_start=kv_start, dec_kv_end=kv_end)
+
     # -------------------------------------------------------------- embeddings (sorted rows)
     def embed_sorted(self, input_ids: torch.Tensor, meta: LF.AttnMeta, contiguous_signal: Optional[torch.Tensor]):
         """get_inputs_embeds_from_multicodebook (modeling_libra.py:625-661, :746-748) producing sorted rows."""
@@ -317,6 +347,7 @@ class LibraModel(LibraPreTrainedModel):
                 # fires when d(loss)/d(input of layer li) has been produced, i.e. after every gradient of layer li has been
                 # enqueued: lets a data-parallel driver start reducing that layer's slice of the flat gradient buffer
                 h.register_hook(lambda g, _li=li: hook(_li))
+            meta.layer_idx = li
             if self.gradient_checkpointing and self.training and torch.is_grad_enabled():
                 h = torch.utils.checkpoint.checkpoint(layer, h, meta, use_reentrant=False)
             else:
@@ -432,7 +463,8 @@ class LibraForCausalLM(LibraPreTrainedModel):
         .loss); True/False force it."""
         _lib.require_device()
         if past_key_values is not None or use_cache:
-            raise NotImplementedError("KV-cached decoding is outside the training hot path (SURVEY.md section 8f N1)")
+            return self._forward_cached(input_ids, attention_mask, position_ids, past_key_values, vision_indices,
+                                        contiguous_signal, labels, inputs_embeds, output_attentions, return_dict)
         if inputs_embeds is not None or output_attentions:
             raise NotImplementedError("inputs_embeds / output_attentions are not supported by the fused path")
         if input_ids is None or vision_indices is None:
@@ -463,6 +495,98 @@ class LibraForCausalLM(LibraPreTrainedModel):
             return ((loss,) + out) if loss is not None else out
         return LibraCausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=None, hidden_states=hs,
                                            attentions=None, past_hidden_states=None, past_vision_flag=None)
+
+
+    # -------------------------------------------------------------- N1: use_cache=True (prefill and one-token steps)
+    @torch.no_grad()
+    def _forward_cached(self, input_ids, attention_mask, position_ids, past, vision_indices, contiguous_signal, labels,
+                        inputs_embeds, output_attentions, return_dict):
+        """forward(..., use_cache=True) of the reference (modeling_libra.py:1118-1145 over :680-831, :343-361).  Without a past:
+        the whole prompt through the training kernels, every layer's key/value operands kept in a LibraKVCache.  With a
+        past: ONE new token per sample (what prepare_inputs_for_generation :1190-1231 feeds) through lb_attn_decode."""
+        from ..kv_cache import LibraKVCache
+        if labels is not None or inputs_embeds is not None or output_attentions:
+            raise NotImplementedError("use_cache=True is the inference path: no labels / inputs_embeds / output_attentions")
+        if self.training:
+            raise RuntimeError("use_cache=True needs model.eval() (the reference asserts `not self.training`, :1142)")
+        if input_ids is None or vision_indices is None:
+            raise ValueError("input_ids [Q,B,T] and vision_indices [B,T] are required")
+        if self.lm_head.weight.dtype != BF16:
+            raise TypeError("libra_b200 computes in bf16: call model.to(torch.bfloat16)")
+        assert len(input_ids) == self.vision_codebook_num
+        vision_flag = vision_indices < self.max_vision_token_length
+        if not torch.equal(vision_flag, input_ids[0] >= self.config.vocab_size):
+            raise AssertionError("Inconsistent input_ids and vision_flag")
+        B, q_len = vision_flag.shape
+        cfg = self.config
+        if past is None:
+            meta = self.model.build_meta(vision_flag, attention_mask, position_ids)
+            cache = LibraKVCache(cfg.num_hidden_layers, B, q_len + 256, cfg.num_attention_heads,
+                                 cfg.hidden_size // cfg.num_attention_heads, vision_flag.device)
+            meta.kv_cache = cache
+        else:
+            if not isinstance(past, LibraKVCache):
+                raise TypeError("past_key_values must be the LibraKVCache a previous use_cache=True call returned")
+            if q_len != 1:
+                raise NotImplementedError("with a past, one new token per sample (prepare_inputs_for_generation, :1190-1194)")
+            cache = past
+            cache.reserve(1)
+            meta = self.model.build_decode_meta(vision_flag, attention_mask, position_ids, cache)
+        try:
+            hn, _ = self.model.forward_sorted(input_ids, meta, contiguous_signal)
+        finally:
+            meta.kv_cache = None                       # the (cached) train-path metadata must not keep the cache alive
+        cache.commit(vision_flag)
+        logits = self._materialize_logits(hn, meta)
+        if past is not None:
+            # a row that just consumed </img> predicts nothing: "just append a newline" (:1142-1144)
+            eoi = vision_indices[:, -1] == self.max_vision_token_length - 1
+            if bool(eoi.any()):
+                logits[:, eoi, -1, :] = self.eoi_to_newline_logits_placeholder.to(logits.dtype).view(-1)
+        if return_dict is False:
+            return (logits, cache)
+        return LibraCausalLMOutputWithPast(loss=None, logits=logits, past_key_values=cache, hidden_states=None,
+                                           attentions=None, past_hidden_states=None, past_vision_flag=None)
+
+    @torch.no_grad()
+    def generate(self, input_ids, attention_mask=None, vision_indices=None, contiguous_signal=None, max_new_tokens=32,
+                 eos_token_id=None, use_cache=True, do_sample=False, **unused):
+        """Greedy decoding with the KV cache, following the reference's generation plumbing: position_ids = cumsum(mask)-1
+        (:1204-1205), the next token's vision index = previous + 1 inside an image, 578 after </img> or on text
+        (:1273-1281), both codebook planes argmax'ed independently (modeling_libra_utils.py:263-296).  Returns the extended
+        input_ids [Q,B,T+n].  Sampling, beam search and logits processors are HF machinery outside this path."""
+        if do_sample:
+            raise NotImplementedError("greedy decoding only")
+        Q, B, T = input_ids.shape
+        dev = input_ids.device
+        am = torch.ones(B, T, dtype=torch.long, device=dev) if attention_mask is None else attention_mask.to(dev).long()
+        L = self.max_vision_token_length
+        pos = am.cumsum(-1) - 1
+        pos.masked_fill_(am == 0, 1)
+        out = self.forward(input_ids=input_ids, attention_mask=am, position_ids=pos, vision_indices=vision_indices,
+                           contiguous_signal=contiguous_signal, use_cache=True)
+        done = torch.zeros(B, dtype=torch.bool, device=dev)
+        vi_last = vision_indices[:, -1]
+        for _ in range(max_new_tokens):
+            nxt = out.logits[:, :, -1, :].float().argmax(dim=-1)                  # [Q, B]
+            if eos_token_id is not None:
+                nxt = torch.where(done[None], torch.full_like(nxt, eos_token_id), nxt)
+                done = done | (nxt[0] == eos_token_id)
+            input_ids = torch.cat([input_ids, nxt[:, :, None]], dim=2)
+            vi_next = vi_last + 1
+            vi_next = torch.where(vi_next >= L, torch.full_like(vi_next, L), vi_next)
+            # a language token can open an image (<img> has vision index 0); keep flags consistent with the token
+            is_vis_tok = nxt[0] >= self.config.vocab_size
+            vi_next = torch.where(is_vis_tok & (vi_next >= L), torch.zeros_like(vi_next), vi_next)
+            vi_next = torch.where(~is_vis_tok, torch.full_like(vi_next, L), vi_next)
+            vi_last = vi_next
+            am = torch.cat([am, am.new_ones(B, 1)], dim=1)
+            if eos_token_id is not None and bool(done.all()):
+                break
+            p1 = (am.cumsum(-1) - 1)[:, -1:]
+            out = self.forward(input_ids=nxt[:, :, None], attention_mask=am, position_ids=p1, vision_indices=vi_next[:, None],
+                               past_key_values=out.past_key_values, use_cache=True)
+        return input_ids
 
 
 class LibraTrainWrapper(LibraPreTrainedModel):

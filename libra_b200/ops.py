@@ -302,6 +302,20 @@ def attn_fwd(Q, K0, V0, K1, V1, qflag, work, kv_start, kv_end, out_row, batch, s
     return out, lse
 
 
+def attn_decode(Q, K_fl, V_fl, K_fv, V_fv, qflag, kv_start, kv_end, out_row, batch, heads, head_dim, kv_len, scale, out=None):
+    """One new query per sample against the cached operands (lb_attn_decode).  K_*/V_*: [B, capacity, H*D]."""
+    C = heads * head_dim
+    capacity = K_fl.shape[1]
+    if out is None:
+        out = torch.empty(batch, C, dtype=BF16, device=Q.device)
+    # enough CTAs to fill the machine, chunks of at least 256 keys
+    n_split = max(1, min((kv_len + 255) // 256, (4 * sm_count() + batch * heads - 1) // (batch * heads)))
+    ws = torch.empty(batch * heads * n_split * (head_dim + 2), dtype=torch.float32, device=Q.device)
+    _timed_call("lb_attn_decode", _p(Q), _p(K_fl), _p(V_fl), _p(K_fv), _p(V_fv), _p(qflag), _p(kv_start), _p(kv_end), _p(out_row),
+                _p(ws), _p(out), batch, heads, head_dim, capacity, kv_len, n_split, float(scale), _st())
+    return out
+
+
 def attn_bwd_prepare(O, dO, row_of, batch, seqlen, heads, head_dim, want_dO_orig=True):
     C = heads * head_dim
     dO_orig = torch.empty(batch * seqlen, C, dtype=BF16, device=O.device) if want_dO_orig else None

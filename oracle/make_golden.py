@@ -101,6 +101,43 @@ def golden_decoder(m):
                 last_hidden=out.hidden_states[-1].detach().clone(), grads=grads)
 
 
+DECODE_STEPS = [([7, 320 + 512], [578, 0]), ([9, 320 + 3], [578, 1]), ([11, 320 + 200], [578, 2]),
+                ([5, 320 + 513], [578, 577]), ([8, 13], [578, 578])]
+
+
+def golden_decode(m):
+    """N1: the reference's KV-cached generation path on the decoder_tiny model (same construction => same weights as
+    golden_decoder): prompt with use_cache=True, then one-token steps -- text continuation on sample 0; <img>, two grid
+    tokens, </img> (which must predict "newline") and a text token on sample 1.  Keeps the logits of the last prompt
+    position and of every step (fp32)."""
+    torch.manual_seed(0)
+    cfg = m.configuration_libra.LibraConfig(**TINY_LIBRA)
+    model = m.modeling_libra.LibraForCausalLM(cfg).eval()
+    randomize_like_bench(model, 11)
+    inp = make_libra_inputs(cfg.vocab_size, cfg.contiguous_signal_size, B=2, n_text=9, pad_last=0, seed=5)
+    ids, vi, am = inp["input_ids"], inp["vision_indices"], inp["attention_mask"]
+    g = torch.Generator().manual_seed(3)
+    logits, tokens = [], []
+    with torch.no_grad():
+        r = model(input_ids=ids, attention_mask=am, vision_indices=vi, contiguous_signal=inp["contiguous_signal"], use_cache=True)
+        logits.append(r.logits[:, :, -1].clone())
+        past = r.past_key_values
+        for tok, vidx in DECODE_STEPS:
+            nid = torch.tensor(tok)[None, :, None].repeat(2, 1, 1)
+            nid[1] = torch.where(nid[0] >= cfg.vocab_size, torch.randint(cfg.vocab_size, cfg.vocab_size + 512, nid[0].shape, generator=g), nid[0])
+            nvi = torch.tensor(vidx)[:, None]
+            am = torch.cat([am, am.new_ones(am.shape[0], 1)], dim=1)
+            pos = (am.long().cumsum(-1) - 1)[:, -1:]
+            r = model(input_ids=nid, attention_mask=am, vision_indices=nvi, position_ids=pos, past_key_values=past, use_cache=True)
+            past = r.past_key_values
+            logits.append(r.logits[:, :, -1].clone())
+            tokens.append((nid.clone(), nvi.clone()))
+    return dict(config=TINY_LIBRA, inputs={k: inp[k] for k in ("input_ids", "attention_mask", "vision_indices", "contiguous_signal")},
+                step_input_ids=torch.stack([t[0] for t in tokens]), step_vision_indices=torch.stack([t[1] for t in tokens]),
+                logits=torch.stack(logits), k_for_language_l1=past[1][0][1][:, :, -8:].clone(),
+                k_for_vision_l1=past[1][0][0][:, :, -8:].clone())
+
+
 def golden_attention(m):
     """One LibraAttention module at the production head_dim (128), 2 heads."""
     torch.manual_seed(1)
@@ -189,8 +226,11 @@ def golden_norms_rope(m):
 def main():
     m = refshim.import_reference()
     os.makedirs(OUT, exist_ok=True)
-    for name, fn in (("decoder_tiny", golden_decoder), ("attention_hd128", golden_attention),
+    only = sys.argv[1:]
+    for name, fn in (("decoder_tiny", golden_decoder), ("decode_tiny", golden_decode), ("attention_hd128", golden_attention),
                      ("clip_tiny", golden_clip), ("lfq", golden_lfq), ("norms_rope", golden_norms_rope)):
+        if only and name not in only:
+            continue
         obj = fn(m)
         path = os.path.join(OUT, name + ".pt")
         torch.save(obj, path)
