@@ -8,9 +8,9 @@
 // token's modality picks the pair -- the bridge select costs nothing here.
 //
 //   lb_attn_decode:  grid = (B*H, n_split).  A CTA of 256 threads takes a contiguous chunk of the sample's visible keys
-//     [kv_start, kv_end): thread = key for the scores (row of 2*D bytes, 16-byte loads, q broadcast from shared memory),
-//     block max / sum, then thread = (key quarter, 2 value columns) for P.V (a warp reads 128 contiguous bytes of one V
-//     row).  Writes the chunk's (max, sum, unnormalised O[D]) in fp32 to the caller's workspace.
+//     [kv_start, kv_end); each of its 8 warps streams every 8th batch of keys with its own online softmax (D/8 lanes per
+//     row, 16-byte loads, whole rows per instruction), the warps are merged through shared memory.  Writes the chunk's
+//     (max, sum, unnormalised O[D]) in fp32 to the caller's workspace.
 //   combine (same call):  grid = B*H, merges the n_split partials, normalises, writes bf16 O [B, H*D] (row out_row[b]).
 #include <math_constants.h>
 
@@ -20,7 +20,6 @@ namespace lb {
 namespace dec {
 
 constexpr int THREADS = 256;
-constexpr int CHUNK = 256;                 // keys per CTA pass
 constexpr float LOG2E = 1.4426950408889634f;
 
 struct Params {
@@ -37,96 +36,120 @@ struct Params {
     float scale;
 };
 
-__device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    v = is_max ? warp_max(v) : warp_sum(v);
-    __syncthreads();                       // red may still be read from the previous reduction
-    if (lane == 0) red[warp] = v;
-    __syncthreads();
-    float r = red[0];
-#pragma unroll
-    for (int i = 1; i < THREADS / 32; ++i) r = is_max ? fmaxf(r, red[i]) : r + red[i];
-    return r;
+__device__ __forceinline__ float dot8(const uint4& u, const float (&q)[8]) {
+    float a = bf16_lo(u.x) * q[0];
+    a = fmaf(bf16_hi(u.x), q[1], a);
+    a = fmaf(bf16_lo(u.y), q[2], a); a = fmaf(bf16_hi(u.y), q[3], a);
+    a = fmaf(bf16_lo(u.z), q[4], a); a = fmaf(bf16_hi(u.z), q[5], a);
+    a = fmaf(bf16_lo(u.w), q[6], a); a = fmaf(bf16_hi(u.w), q[7], a);
+    return a;
 }
 
+// Each warp streams its own subset of the CTA's keys with an online softmax of its own: D/8 lanes cover one K (or V) row with
+// one 16-byte load each, so a warp instruction reads 32/(D/8) whole rows = 512 contiguous-per-row bytes, NB instructions are
+// in flight per batch, and nothing inside the loop needs a block-wide barrier.  The warps are merged through shared memory
+// once at the end.  (The first version took one key per THREAD: 32 different rows per load instruction, 0.27-0.46 of the
+// HBM peak.)
 template <int D>
 __global__ void __launch_bounds__(THREADS) attn_decode_kernel(const Params p) {
-    __shared__ float q_sh[D];
-    __shared__ float p_sh[CHUNK];
-    __shared__ float red[THREADS / 32];
-    constexpr int COLS = D / 2, NG = THREADS / COLS;                 // column pairs; key groups for P.V
-    __shared__ float o_sh[NG][D];
+    constexpr int LPK = D / 8, KPI = 32 / LPK, NB = 4, NW = THREADS / 32;      // lanes per key, keys per instruction, batch depth
+    __shared__ float m_sh[NW], l_sh[NW];
+    __shared__ float o_sh[NW][D];
     const int bh = blockIdx.x, b = bh / p.heads, h = bh - b * p.heads;
     const int C = p.heads * D;
     const int variant = p.qflag ? (int)p.qflag[b] : 0;
     const int kvs = p.kv_start ? p.kv_start[b] : 0;
     const int kve = p.kv_end ? p.kv_end[b] : p.kv_len;
     const int n_keys = kve > kvs ? kve - kvs : 0;
-    // this CTA's share of the visible keys (whole multiples of 8 keys so that splits stay sector aligned)
+    // this CTA's share of the visible keys
     const int per = ((n_keys + p.n_split - 1) / p.n_split + 7) & ~7;
     const int j0 = kvs + blockIdx.y * per, j1 = min(kve, j0 + per);
-    const __nv_bfloat16* K = p.k[variant] + ((int64_t)b * p.capacity) * C + (int64_t)h * D;
-    const __nv_bfloat16* V = p.v[variant] + ((int64_t)b * p.capacity) * C + (int64_t)h * D;
-    if (threadIdx.x < D) q_sh[threadIdx.x] = __bfloat162float(p.q[(int64_t)b * C + h * D + threadIdx.x]) * p.scale * LOG2E;
-    __syncthreads();
-
-    float m_run = -CUDART_INF_F, l_run = 0.f;
-    float acc0 = 0.f, acc1 = 0.f;                                  // my 2 value columns, my quarter of the chunk's keys
-    const int grp_d = threadIdx.x / COLS, col_d = (threadIdx.x % COLS) * 2;
-    for (int c0 = j0; c0 < j1; c0 += CHUNK) {
-        const int j = c0 + (int)threadIdx.x;
-        float s = -CUDART_INF_F;
-        if (j < j1) {
-            const uint4* row = reinterpret_cast<const uint4*>(K + (int64_t)j * C);
-            float a = 0.f;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, sub = lane / LPK, dc = lane % LPK;
+    const __nv_bfloat16* K = p.k[variant] + ((int64_t)b * p.capacity) * C + (int64_t)h * D + dc * 8;
+    const __nv_bfloat16* V = p.v[variant] + ((int64_t)b * p.capacity) * C + (int64_t)h * D + dc * 8;
+    float qf[8];
+    {
+        const uint4 u = *reinterpret_cast<const uint4*>(p.q + (int64_t)b * C + h * D + dc * 8);
+        const float sc = p.scale * LOG2E;                          // scores in the log2 domain
+        qf[0] = bf16_lo(u.x) * sc; qf[1] = bf16_hi(u.x) * sc; qf[2] = bf16_lo(u.y) * sc; qf[3] = bf16_hi(u.y) * sc;
+        qf[4] = bf16_lo(u.z) * sc; qf[5] = bf16_hi(u.z) * sc; qf[6] = bf16_lo(u.w) * sc; qf[7] = bf16_hi(u.w) * sc;
+    }
+    float m_run = -CUDART_INF_F, l_run = 0.f, acc[8];
 #pragma unroll
-            for (int i = 0; i < D / 8; ++i) {
-                const uint4 u = row[i];
-                const float* qq = q_sh + i * 8;
-                a = fmaf(bf16_lo(u.x), qq[0], a); a = fmaf(bf16_hi(u.x), qq[1], a);
-                a = fmaf(bf16_lo(u.y), qq[2], a); a = fmaf(bf16_hi(u.y), qq[3], a);
-                a = fmaf(bf16_lo(u.z), qq[4], a); a = fmaf(bf16_hi(u.z), qq[5], a);
-                a = fmaf(bf16_lo(u.w), qq[6], a); a = fmaf(bf16_hi(u.w), qq[7], a);
-            }
-            s = a;                                                 // log2 domain, scaled
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int jb = j0 + warp * (NB * KPI); jb < j1; jb += NW * NB * KPI) {
+        uint4 kk[NB], vv[NB];
+        float s[NB];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const int j = jb + i * KPI + sub;
+            kk[i] = j < j1 ? *reinterpret_cast<const uint4*>(K + (int64_t)j * C) : make_uint4(0u, 0u, 0u, 0u);
         }
-        const float m_c = block_reduce(s, red, true);
-        const float m_new = fmaxf(m_run, m_c);
-        const float pj = (j < j1) ? fast_ex2(s - m_new) : 0.f;
-        // the reference rounds the probabilities to the activation dtype before P.V (modeling_libra.py:391)
-        p_sh[threadIdx.x] = __bfloat162float(__float2bfloat16(pj));
-        const float l_c = block_reduce(pj, red, false);            // (also orders the p_sh writes before the reads below)
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const int j = jb + i * KPI + sub;
+            vv[i] = j < j1 ? *reinterpret_cast<const uint4*>(V + (int64_t)j * C) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        float m_new = m_run;
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            float a = dot8(kk[i], qf);
+#pragma unroll
+            for (int o = LPK / 2; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);     // the key's LPK lanes
+            s[i] = (jb + i * KPI + sub < j1) ? a : -CUDART_INF_F;
+            m_new = fmaxf(m_new, s[i]);
+        }
+#pragma unroll
+        for (int o = LPK; o < 32; o <<= 1) m_new = fmaxf(m_new, __shfl_xor_sync(0xffffffffu, m_new, o));   // the other keys of the batch
         const float alpha = (m_run == -CUDART_INF_F) ? 0.f : fast_ex2(m_run - m_new);
-        l_run = l_run * alpha + l_c;
-        acc0 *= alpha;
-        acc1 *= alpha;
+        l_run *= alpha;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] *= alpha;
         m_run = m_new;
-        const int n_here = min(CHUNK, j1 - c0);
-        for (int t = grp_d; t < n_here; t += NG) {
-            const __nv_bfloat162 vv = *reinterpret_cast<const __nv_bfloat162*>(V + (int64_t)(c0 + t) * C + col_d);
-            const float pt = p_sh[t];
-            acc0 = fmaf(pt, __bfloat162float(vv.x), acc0);
-            acc1 = fmaf(pt, __bfloat162float(vv.y), acc1);
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const float pj = (s[i] == -CUDART_INF_F) ? 0.f : fast_ex2(s[i] - m_new);
+            l_run += pj;                                           // (every lane of the key's group counts it; only sub-group leaders are summed below)
+            // the reference rounds the probabilities to the activation dtype before P.V (modeling_libra.py:391)
+            const float pr = __bfloat162float(__float2bfloat16(pj));
+            acc[0] = fmaf(pr, bf16_lo(vv[i].x), acc[0]); acc[1] = fmaf(pr, bf16_hi(vv[i].x), acc[1]);
+            acc[2] = fmaf(pr, bf16_lo(vv[i].y), acc[2]); acc[3] = fmaf(pr, bf16_hi(vv[i].y), acc[3]);
+            acc[4] = fmaf(pr, bf16_lo(vv[i].z), acc[4]); acc[5] = fmaf(pr, bf16_hi(vv[i].z), acc[5]);
+            acc[6] = fmaf(pr, bf16_lo(vv[i].w), acc[6]); acc[7] = fmaf(pr, bf16_hi(vv[i].w), acc[7]);
         }
     }
-    // fold the key groups
-    __syncthreads();
-    if (grp_d > 0) {
-        o_sh[grp_d][col_d] = acc0;
-        o_sh[grp_d][col_d + 1] = acc1;
+    // fold the key sub-groups of the warp (same running max in every lane)
+#pragma unroll
+    for (int o = LPK; o < 32; o <<= 1) {
+        l_run += __shfl_xor_sync(0xffffffffu, l_run, o);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], o);
+    }
+    if (sub == 0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o_sh[warp][dc * 8 + e] = acc[e];
+    }
+    if (lane == 0) {
+        m_sh[warp] = m_run;
+        l_sh[warp] = l_run;
     }
     __syncthreads();
-    if (grp_d == 0) {
-        for (int g = 1; g < NG; ++g) {
-            acc0 += o_sh[g][col_d];
-            acc1 += o_sh[g][col_d + 1];
+    if (threadIdx.x < D) {
+        float m = -CUDART_INF_F;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) m = fmaxf(m, m_sh[w]);
+        float l = 0.f, o = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const float sc = (m_sh[w] == -CUDART_INF_F) ? 0.f : fast_ex2(m_sh[w] - m);
+            l += sc * l_sh[w];
+            o += sc * o_sh[w][threadIdx.x];
         }
         float* dst = p.partial + ((int64_t)bh * p.n_split + blockIdx.y) * (D + 2);
-        dst[col_d] = acc0;
-        dst[col_d + 1] = acc1;
+        dst[threadIdx.x] = o;
         if (threadIdx.x == 0) {
-            dst[D] = m_run;
-            dst[D + 1] = l_run;
+            dst[D] = m;
+            dst[D + 1] = l;
         }
     }
 }

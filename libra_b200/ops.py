@@ -7,6 +7,7 @@ These are the leaves; `libra_b200.functional` wraps them in torch.autograd.Funct
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -308,8 +309,10 @@ def attn_decode(Q, K_fl, V_fl, K_fv, V_fv, qflag, kv_start, kv_end, out_row, bat
     capacity = K_fl.shape[1]
     if out is None:
         out = torch.empty(batch, C, dtype=BF16, device=Q.device)
-    # enough CTAs to fill the machine, chunks of at least 256 keys
-    n_split = max(1, min((kv_len + 255) // 256, (4 * sm_count() + batch * heads - 1) // (batch * heads)))
+    # chunks of ~256 keys, but not more CTAs than ~16 per SM (4 fit at a time: 256 threads x 64 registers)
+    n_split = max(1, min((kv_len + 255) // 256, (16 * sm_count() + batch * heads - 1) // (batch * heads)))
+    if os.environ.get("LB_DECODE_SPLIT"):
+        n_split = max(1, int(os.environ["LB_DECODE_SPLIT"]))
     ws = torch.empty(batch * heads * n_split * (head_dim + 2), dtype=torch.float32, device=Q.device)
     _timed_call("lb_attn_decode", _p(Q), _p(K_fl), _p(V_fl), _p(K_fv), _p(V_fv), _p(qflag), _p(kv_start), _p(kv_end), _p(out_row),
                 _p(ws), _p(out), batch, heads, head_dim, capacity, kv_len, n_split, float(scale), _st())
