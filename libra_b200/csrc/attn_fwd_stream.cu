@@ -178,15 +178,16 @@ __device__ __forceinline__ float mask_max(uint32_t (&v)[128], int kv0, int qi, i
             for (int e = 0; e < 32; ++e) v[32 * c + e] = ((!NEED_LO || e >= lo) && e <= hi) ? v[32 * c + e] : 0xff800000u;
         }
     }
-    float mx0 = -CUDART_INF_F, mx1 = -CUDART_INF_F, mx2 = -CUDART_INF_F, mx3 = -CUDART_INF_F;
+    // eight independent chains of 3-input maxima (16 deep each would be the critical path of the phase with four)
+    float mx[8];
 #pragma unroll
-    for (int j = 0; j < 128; j += 8) {                               // pairs of maxima: one 3-input FMNMX each
-        mx0 = fmaxf(mx0, fmaxf(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
-        mx1 = fmaxf(mx1, fmaxf(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
-        mx2 = fmaxf(mx2, fmaxf(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5])));
-        mx3 = fmaxf(mx3, fmaxf(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7])));
+    for (int c = 0; c < 8; ++c) mx[c] = fmaxf(__uint_as_float(v[2 * c]), __uint_as_float(v[2 * c + 1]));
+#pragma unroll
+    for (int j = 16; j < 128; j += 16) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) mx[c] = fmaxf(mx[c], fmaxf(__uint_as_float(v[j + 2 * c]), __uint_as_float(v[j + 2 * c + 1])));
     }
-    return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+    return fmaxf(fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])), fmaxf(fmaxf(mx[4], mx[5]), fmaxf(mx[6], mx[7])));
 }
 
 // P = 2^(S*sl2 - m_off), packed to bf16 into the 64 columns at TMEM `tp`; one exponential in every POLY runs on the FMA
@@ -444,6 +445,7 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         const int r = (warp & 3) * 32 + (threadIdx.x & 31);       // query row in tile == TMEM lane
         const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         const float sl2 = p.scale * LOG2E;
+        const uint32_t m_sh_s = smem_u32(m_sh);
         uint32_t g = 0, dep = 0;                                  // tiles / deposits (items with >= 2 tiles) so far
         for (int ic = 0;; ++ic) {
             const Item it = load_item(items, ic);
@@ -494,7 +496,7 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                 if (j == 0) {
                     m_cur = mx;
                 } else {
-                    const float m_prev = m_sh[((G - 1) & 1u) * 128 + r];
+                    const float m_prev = lds_f32(m_sh_s + (((G - 1) & 1u) * 128 + r) * 4);
                     const float m_new = fmaxf(m_prev, mx);
                     // lazy correction: rescale O only when the running max moved by more than 2^8
                     const bool grow = (m_new - m_prev) * sl2 > 8.f;       // also true when m_prev == -inf and m_new finite
@@ -520,7 +522,7 @@ attn_fwd_stream_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                         tc_wait_st();
                     }
                 }
-                m_sh[(G & 1u) * 128 + r] = m_cur;
+                sts_f32(m_sh_s + ((G & 1u) * 128 + r) * 4, m_cur);
                 mbar_arrive(bars + B_MPUB + (G & 1u));
                 if ((threadIdx.x & 127) == 0) FS_TRACE(15, G);        // softmax: running max published
                 // ---- my partial row sum follows the reference maximum

@@ -185,6 +185,15 @@ __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
     return v;
 }
 
+__device__ __forceinline__ void sts_f32(uint32_t saddr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");
+    return v;
+}
+
 // Attention CTA order.  The grid is 1-D over (work item, head); work items are sorted heaviest first.  Heads run in
 // groups of `group`: inside a group all heads of the heaviest item come first, so (a) the CTAs resident at one time
 // touch the K/V of `group` heads only (L2-resident working set) and (b) the grid ends with the lightest items of the

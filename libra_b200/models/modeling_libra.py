@@ -292,25 +292,31 @@ class LibraModel(LibraPreTrainedModel):
         B = vision_flag.shape[0]
         dev = vision_flag.device
         Tk = cache.length + 1
-        rt_cpu = schedule.build_routing(vision_flag.detach().to("cpu"))
-        rt = schedule.Routing(rt_cpu.n_tokens, rt_cpu.n_lang, rt_cpu.n_vis, rt_cpu.perm.to(dev), rt_cpu.inv.to(dev),
-                              rt_cpu.flag_sorted.to(dev), rt_cpu.flag_orig.to(dev))
+        flag_cpu = vision_flag.detach().to("cpu")
+        key = ("decode", B, flag_cpu.numpy().tobytes())
+        rt = self._meta_cache.get(key)
+        if rt is None:                                   # one entry per modality pattern of the B new tokens
+            rt_cpu = schedule.build_routing(flag_cpu)
+            rt = schedule.Routing(rt_cpu.n_tokens, rt_cpu.n_lang, rt_cpu.n_vis, rt_cpu.perm.to(dev), rt_cpu.inv.to(dev),
+                                  rt_cpu.flag_sorted.to(dev), rt_cpu.flag_orig.to(dev))
+            if len(self._meta_cache) > 64:
+                self._meta_cache.clear()
+            self._meta_cache[key] = rt
         kv_start = kv_end = None
         if attention_mask is not None:
-            am = attention_mask.to(dev).to(torch.bool)
+            am = attention_mask.to(dev)
             if am.shape != (B, Tk):
                 raise ValueError(f"attention_mask must cover past and new positions: expected {(B, Tk)}, got {tuple(am.shape)}")
-            if not bool(am.all()):
-                idx = torch.arange(Tk, device=dev)[None]
-                kv_start = torch.where(am, idx, Tk).amin(dim=1).to(torch.int32)
-                kv_end = (torch.where(am, idx, -1).amax(dim=1) + 1).to(torch.int32)
-                if not bool((am.sum(dim=1) == (kv_end - kv_start).clamp(min=0)).all()):
-                    raise NotImplementedError("attention_mask must be one contiguous run of ones per sample")
+            # first / last visible position per sample, computed on the device (no host round trip in the decode loop; that
+            # the ones form one contiguous run was checked when the prompt went through build_meta)
+            am8 = am.to(torch.int8)
+            kv_start = am8.argmax(dim=1).to(torch.int32)
+            kv_end = (Tk - am8.flip(1).argmax(dim=1)).to(torch.int32)
         if position_ids is None:
             pos = torch.full((B,), cache.length, device=dev, dtype=torch.int32)
         else:
             pos = position_ids.to(dev).reshape(-1).to(torch.int32).contiguous()
-        cos, sin = self._rope_tables(int(pos.max().item()) + 1, dev)
+        cos, sin = self._rope_tables(cache.capacity + 1, dev)          # positions never exceed the cache length
         H = self.config.num_attention_heads
         return LF.AttnMeta(rt, None, pos, cos, sin, B, 1, H, self.config.hidden_size // H, kv_cache=cache, decode=True,
                            dec_kv_start=kv_start, dec_kv_end=kv_end)
@@ -541,8 +547,7 @@ class LibraForCausalLM(LibraPreTrainedModel):
         if past is not None:
             # a row that just consumed </img> predicts nothing: "just append a newline" (:1142-1144)
             eoi = vision_indices[:, -1] == self.max_vision_token_length - 1
-            if bool(eoi.any()):
-                logits[:, eoi, -1, :] = self.eoi_to_newline_logits_placeholder.to(logits.dtype).view(-1)
+            logits = torch.where(eoi[None, :, None, None], self.eoi_to_newline_logits_placeholder.to(logits.dtype), logits)
         if return_dict is False:
             return (logits, cache)
         return LibraCausalLMOutputWithPast(loss=None, logits=logits, past_key_values=cache, hidden_states=None,
