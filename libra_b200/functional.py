@@ -517,8 +517,10 @@ class BridgeAttention(torch.autograd.Function):
             cache.append(meta.layer_idx, Kfv, Kfl, Vfv, Vfl, meta.seqlen)
             if meta.decode:
                 i = meta.layer_idx
+                # with a device-side key range the host-side length only sizes the split: keep it static (graph replay)
+                kv_len = cache.capacity if meta.dec_kv_end is not None else cache.length + 1
                 ops.attn_decode(Q, cache.k_fl[i], cache.v_fl[i], cache.k_fv[i], cache.v_fv[i], rt.flag_orig, meta.dec_kv_start,
-                                meta.dec_kv_end, rt.inv, meta.batch, meta.heads, meta.head_dim, cache.length + 1, scale, out=o)
+                                meta.dec_kv_end, rt.inv, meta.batch, meta.heads, meta.head_dim, kv_len, scale, out=o)
                 return o
         # variant 0 = language queries (see Kfl/Vfl), variant 1 = vision queries (see Kfv/Vfv); rows land in sorted order
         kern, wlist, plan = _fwd_choice(w, meta.heads)

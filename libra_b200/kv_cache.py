@@ -22,6 +22,8 @@ class LibraKVCache:
         self.k_fl, self.v_fl, self.k_fv, self.v_fv = mk(), mk(), mk(), mk()
         self.flag = torch.zeros(batch, capacity, dtype=torch.bool, device=device)
         self.length = 0                  # positions filled in every layer
+        self.len_dev = torch.zeros(1, dtype=torch.int64, device=device)      # the same number on the device: one-token
+        # steps address the cache through it, so that a step can be captured in a CUDA graph and replayed
         self._pending = 0                # positions written by the layers of the step in flight
 
     # ---- HF-style accessors
@@ -49,20 +51,33 @@ class LibraKVCache:
         nf = torch.zeros(self.batch, cap, dtype=torch.bool, device=self.flag.device)
         nf[:, :self.length] = self.flag[:, :self.length]
         self.flag, self.capacity = nf, cap
+        return True
 
     def append(self, layer: int, k_fv, k_fl, v_fv, v_fl, q_len: int):
         """Rows [B*q_len, C] in original token order (what lb_attn_prep_fwd writes) -> positions [length, length+q_len)."""
         B, s = self.batch, self.length
         for dst, src in ((self.k_fv, k_fv), (self.k_fl, k_fl), (self.v_fv, v_fv), (self.v_fl, v_fl)):
-            dst[layer][:, s:s + q_len].copy_(src.view(B, q_len, -1))
+            if q_len == 1:
+                dst[layer].index_copy_(1, self.len_dev, src.view(B, 1, -1))
+            else:
+                dst[layer][:, s:s + q_len].copy_(src.view(B, q_len, -1))
         self._pending = q_len
 
     def commit(self, flag_new: torch.Tensor):
         """All layers have appended the step's positions; flag_new [B, q_len] bool."""
         q = flag_new.shape[1]
-        self.flag[:, self.length:self.length + q] = flag_new
+        if q == 1:
+            self.commit_device(flag_new)
+        else:
+            self.flag[:, self.length:self.length + q] = flag_new
+            self.len_dev += q
         self.length += q
         self._pending = 0
+
+    def commit_device(self, flag_new: torch.Tensor):
+        """The device half of commit() for a one-token step (graph-capturable: no host state is touched)."""
+        self.flag.index_copy_(1, self.len_dev, flag_new)
+        self.len_dev += 1
 
     # ---- the reference's layout
     def to_reference(self) -> Tuple:

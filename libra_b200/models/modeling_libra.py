@@ -555,11 +555,15 @@ class LibraForCausalLM(LibraPreTrainedModel):
 
     @torch.no_grad()
     def generate(self, input_ids, attention_mask=None, vision_indices=None, contiguous_signal=None, max_new_tokens=32,
-                 eos_token_id=None, use_cache=True, do_sample=False, **unused):
+                 eos_token_id=None, use_cache=True, do_sample=False, cuda_graph=True, **unused):
         """Greedy decoding with the KV cache, following the reference's generation plumbing: position_ids = cumsum(mask)-1
         (:1204-1205), the next token's vision index = previous + 1 inside an image, 578 after </img> or on text
         (:1273-1281), both codebook planes argmax'ed independently (modeling_libra_utils.py:263-296).  Returns the extended
-        input_ids [Q,B,T+n].  Sampling, beam search and logits processors are HF machinery outside this path."""
+        input_ids [Q,B,T+n].  Sampling, beam search and logits processors are HF machinery outside this path.
+
+        cuda_graph: once every sample is generating text (a language row can only predict text ids: the vision block of its
+        logits is -inf), the one-token step -- ~800 tiny launches, launch-bound from Python -- is captured once in a CUDA
+        graph with the cache addressed through its device-side length and the argmax fed back on the device, and replayed."""
         if do_sample:
             raise NotImplementedError("greedy decoding only")
         Q, B, T = input_ids.shape
@@ -572,12 +576,14 @@ class LibraForCausalLM(LibraPreTrainedModel):
                            contiguous_signal=contiguous_signal, use_cache=True)
         done = torch.zeros(B, dtype=torch.bool, device=dev)
         vi_last = vision_indices[:, -1]
-        for _ in range(max_new_tokens):
+        n_done = 0
+        while n_done < max_new_tokens:
             nxt = out.logits[:, :, -1, :].float().argmax(dim=-1)                  # [Q, B]
             if eos_token_id is not None:
                 nxt = torch.where(done[None], torch.full_like(nxt, eos_token_id), nxt)
                 done = done | (nxt[0] == eos_token_id)
             input_ids = torch.cat([input_ids, nxt[:, :, None]], dim=2)
+            n_done += 1
             vi_next = vi_last + 1
             vi_next = torch.where(vi_next >= L, torch.full_like(vi_next, L), vi_next)
             # a language token can open an image (<img> has vision index 0); keep flags consistent with the token
@@ -586,12 +592,74 @@ class LibraForCausalLM(LibraPreTrainedModel):
             vi_next = torch.where(~is_vis_tok, torch.full_like(vi_next, L), vi_next)
             vi_last = vi_next
             am = torch.cat([am, am.new_ones(B, 1)], dim=1)
-            if eos_token_id is not None and bool(done.all()):
+            if n_done >= max_new_tokens or (eos_token_id is not None and bool(done.all())):
                 break
+            if cuda_graph and eos_token_id is None and max_new_tokens - n_done >= 4 and not bool(is_vis_tok.any()):
+                # text from here on: replay the captured step for all remaining tokens
+                toks = self._graph_decode(out.past_key_values, nxt, am, max_new_tokens - n_done)
+                return torch.cat([input_ids, toks], dim=2)
             p1 = (am.cumsum(-1) - 1)[:, -1:]
             out = self.forward(input_ids=nxt[:, :, None], attention_mask=am, position_ids=p1, vision_indices=vi_next[:, None],
                                past_key_values=out.past_key_values, use_cache=True)
         return input_ids
+
+    @torch.no_grad()
+    def _graph_decode(self, cache, tokens, attention_mask, n_steps: int):
+        """n_steps greedy one-token steps on language tokens, starting from `tokens` [Q,B] (already appended to the sequence
+        but not yet to the cache).  The first step runs eagerly on a side stream (torch's capture warm-up, and a real step),
+        the second is captured, the rest are replays.  Returns the generated ids [Q,B,n_steps]."""
+        from .. import schedule as _sch
+        dev = tokens.device
+        Q, B = tokens.shape
+        cfg = self.config
+        cache.reserve(n_steps + 1)                                   # capacity (and every address) is fixed from here on
+        H = cfg.num_attention_heads
+        flag = torch.zeros(B, 1, dtype=torch.bool, device=dev)
+        rt_cpu = _sch.build_routing(flag.cpu())
+        rt = _sch.Routing(rt_cpu.n_tokens, rt_cpu.n_lang, rt_cpu.n_vis, rt_cpu.perm.to(dev), rt_cpu.inv.to(dev),
+                          rt_cpu.flag_sorted.to(dev), rt_cpu.flag_orig.to(dev))
+        am8 = attention_mask.to(torch.int8)
+        kv_start = am8.argmax(dim=1).to(torch.int32)                 # left padding stays where it is
+        kv_end = torch.zeros(B, dtype=torch.int32, device=dev)
+        ids = tokens[:, :, None].clone()                             # static input of the step
+        pos = ((attention_mask.cumsum(-1) - 1)[:, -1]).to(torch.int32).contiguous()
+        outbuf = torch.zeros(Q, B, n_steps, dtype=torch.long, device=dev)
+        step = torch.zeros(1, dtype=torch.long, device=dev)
+        cos, sin = self.model._rope_tables(cache.capacity + 1, dev)
+        meta = LF.AttnMeta(rt, None, pos, cos, sin, B, 1, H, cfg.hidden_size // H, kv_cache=cache, decode=True,
+                           dec_kv_start=kv_start, dec_kv_end=kv_end)
+
+        def body():
+            kv_end.copy_((cache.len_dev + 1).to(torch.int32).expand(B))
+            hn, _ = self.model.forward_sorted(ids, meta, None)
+            cache.commit_device(flag)
+            nxt = self._materialize_logits(hn, meta)[:, :, -1].float().argmax(dim=-1)
+            outbuf.index_copy_(2, step, nxt[:, :, None])
+            ids.copy_(nxt[:, :, None])
+            pos.add_(1)
+            step.add_(1)
+
+        side_was = LF.USE_SIDE_STREAM
+        LF.USE_SIDE_STREAM = False                                   # B rows: nothing to co-schedule, and no cross-stream events in the graph
+        try:
+            cur = torch.cuda.current_stream()
+            s = torch.cuda.Stream()
+            s.wait_stream(cur)
+            with torch.cuda.stream(s):
+                body()                                               # step 1 (eager)
+            cur.wait_stream(s)
+            cache.length += 1
+            if n_steps > 1:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    body()
+                for _ in range(n_steps - 1):
+                    g.replay()
+                    cache.length += 1
+        finally:
+            LF.USE_SIDE_STREAM = side_was
+            meta.kv_cache = None
+        return outbuf
 
 
 class LibraTrainWrapper(LibraPreTrainedModel):

@@ -139,8 +139,12 @@ def test_left_padded_batch_and_greedy_generate(golden):
     ids[1, :7] = 0
     ids = ids[None].repeat(2, 1, 1).to(dev)
     vi = torch.full((2, T), 578, device=dev)
-    out = model.generate(ids, attention_mask=am.to(dev), vision_indices=vi, max_new_tokens=6)
+    out = model.generate(ids, attention_mask=am.to(dev), vision_indices=vi, max_new_tokens=6)       # CUDA-graph replay of the step
     assert out.shape == (2, 2, T + 6)
+    eager = model.generate(ids, attention_mask=am.to(dev), vision_indices=vi, max_new_tokens=6, cuda_graph=False)
+    assert torch.equal(out, eager), "the captured step must reproduce the eager one-token steps bit for bit"
+    longer = model.generate(ids, attention_mask=am.to(dev), vision_indices=vi, max_new_tokens=300)   # forces the cache to grow
+    assert torch.equal(longer[:, :, :T + 6], out)
     # the same continuation without the cache: greedy on the full forward, one token at a time
     cur, cam = ids, am.to(dev)
     for _ in range(6):
