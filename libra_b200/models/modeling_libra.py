@@ -594,9 +594,9 @@ class LibraForCausalLM(LibraPreTrainedModel):
             am = torch.cat([am, am.new_ones(B, 1)], dim=1)
             if n_done >= max_new_tokens or (eos_token_id is not None and bool(done.all())):
                 break
-            if cuda_graph and eos_token_id is None and max_new_tokens - n_done >= 4 and not bool(is_vis_tok.any()):
-                # text from here on: replay the captured step for all remaining tokens
-                toks = self._graph_decode(out.past_key_values, nxt, am, max_new_tokens - n_done)
+            if cuda_graph and max_new_tokens - n_done >= 4 and not bool(is_vis_tok.any()):
+                # text from here on: replay the captured step for the remaining tokens
+                toks = self._graph_decode(out.past_key_values, nxt, am, max_new_tokens - n_done, eos_token_id, done)
                 return torch.cat([input_ids, toks], dim=2)
             p1 = (am.cumsum(-1) - 1)[:, -1:]
             out = self.forward(input_ids=nxt[:, :, None], attention_mask=am, position_ids=p1, vision_indices=vi_next[:, None],
@@ -604,10 +604,12 @@ class LibraForCausalLM(LibraPreTrainedModel):
         return input_ids
 
     @torch.no_grad()
-    def _graph_decode(self, cache, tokens, attention_mask, n_steps: int):
-        """n_steps greedy one-token steps on language tokens, starting from `tokens` [Q,B] (already appended to the sequence
-        but not yet to the cache).  The first step runs eagerly on a side stream (torch's capture warm-up, and a real step),
-        the second is captured, the rest are replays.  Returns the generated ids [Q,B,n_steps]."""
+    def _graph_decode(self, cache, tokens, attention_mask, n_steps: int, eos_token_id=None, done=None):
+        """Up to n_steps greedy one-token steps on language tokens, starting from `tokens` [Q,B] (already appended to the
+        sequence but not yet to the cache).  The first step runs eagerly on a side stream (torch's capture warm-up, and a real
+        step), the second is captured, the rest are replays.  With an EOS id the finished-sample bookkeeping runs inside the
+        graph (a finished sample keeps emitting EOS, as in the eager loop) and the host looks at it every 16 replays.
+        Returns the generated ids [Q,B,n] (n <= n_steps)."""
         from .. import schedule as _sch
         dev = tokens.device
         Q, B = tokens.shape
@@ -625,6 +627,7 @@ class LibraForCausalLM(LibraPreTrainedModel):
         pos = ((attention_mask.cumsum(-1) - 1)[:, -1]).to(torch.int32).contiguous()
         outbuf = torch.zeros(Q, B, n_steps, dtype=torch.long, device=dev)
         step = torch.zeros(1, dtype=torch.long, device=dev)
+        done = torch.zeros(B, dtype=torch.bool, device=dev) if done is None else done.clone()
         cos, sin = self.model._rope_tables(cache.capacity + 1, dev)
         meta = LF.AttnMeta(rt, None, pos, cos, sin, B, 1, H, cfg.hidden_size // H, kv_cache=cache, decode=True,
                            dec_kv_start=kv_start, dec_kv_end=kv_end)
@@ -634,6 +637,9 @@ class LibraForCausalLM(LibraPreTrainedModel):
             hn, _ = self.model.forward_sorted(ids, meta, None)
             cache.commit_device(flag)
             nxt = self._materialize_logits(hn, meta)[:, :, -1].float().argmax(dim=-1)
+            if eos_token_id is not None:
+                nxt = torch.where(done[None], torch.full_like(nxt, eos_token_id), nxt)
+                done.logical_or_(nxt[0] == eos_token_id)
             outbuf.index_copy_(2, step, nxt[:, :, None])
             ids.copy_(nxt[:, :, None])
             pos.add_(1)
@@ -649,17 +655,26 @@ class LibraForCausalLM(LibraPreTrainedModel):
                 body()                                               # step 1 (eager)
             cur.wait_stream(s)
             cache.length += 1
+            n_run = 1
             if n_steps > 1:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     body()
-                for _ in range(n_steps - 1):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                n_first = n_run
+                while n_run < n_steps:
+                    if eos_token_id is not None and n_run % 16 == 0 and bool(done.all()):
+                        break
                     g.replay()
                     cache.length += 1
+                    n_run += 1
+                e1.record()
+                self.last_graph_decode = (n_run - n_first, e0, e1)      # (replays, events around them): for benchmarks
         finally:
             LF.USE_SIDE_STREAM = side_was
             meta.kv_cache = None
-        return outbuf
+        return outbuf[:, :, :n_run]
 
 
 class LibraTrainWrapper(LibraPreTrainedModel):

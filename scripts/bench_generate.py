@@ -56,18 +56,13 @@ with torch.no_grad():
         decode_ms = t0.elapsed_time(t1) / steps
 kt = ops.disable_timing() or {}
 # ---- the same decoding through generate(): the one-token step captured in a CUDA graph and replayed
-def timed_generate(n_new, graph):
-    s0, s1 = ev(), ev()
-    torch.cuda.synchronize()
-    s0.record()
-    model.generate(inp["input_ids"], attention_mask=inp["attention_mask"], vision_indices=inp["vision_indices"],
-                   contiguous_signal=inp["contiguous_signal"], max_new_tokens=n_new, cuda_graph=graph)
-    s1.record()
-    torch.cuda.synchronize()
-    return s0.elapsed_time(s1)
-timed_generate(12, True)                                   # warm-up
-g_short, g_long = timed_generate(12, True), timed_generate(12 + a.new, True)
-graph_ms = (g_long - g_short) / a.new
+model.generate(inp["input_ids"], attention_mask=inp["attention_mask"], vision_indices=inp["vision_indices"],
+               contiguous_signal=inp["contiguous_signal"], max_new_tokens=8)                       # warm-up
+model.generate(inp["input_ids"], attention_mask=inp["attention_mask"], vision_indices=inp["vision_indices"],
+               contiguous_signal=inp["contiguous_signal"], max_new_tokens=a.new + 2)
+torch.cuda.synchronize()
+n_rep, e0, e1 = model.last_graph_decode                     # CUDA events around the replays only
+graph_ms = e0.elapsed_time(e1) / n_rep
 evs = kt.get("lb_attn_decode", [])
 attn_ms = sum(s.elapsed_time(e) for s, e in evs) / max(len(evs), 1)
 kv = a.prompt + a.new / 2

@@ -145,6 +145,14 @@ def test_left_padded_batch_and_greedy_generate(golden):
     assert torch.equal(out, eager), "the captured step must reproduce the eager one-token steps bit for bit"
     longer = model.generate(ids, attention_mask=am.to(dev), vision_indices=vi, max_new_tokens=300)   # forces the cache to grow
     assert torch.equal(longer[:, :, :T + 6], out)
+    # EOS bookkeeping inside the graph: pick a token the greedy path emits for sample 0 and call it EOS
+    eos = int(out[0, 0, T + 2])
+    a = model.generate(ids, attention_mask=am.to(dev), vision_indices=vi, max_new_tokens=40, eos_token_id=eos)
+    b = model.generate(ids, attention_mask=am.to(dev), vision_indices=vi, max_new_tokens=40, eos_token_id=eos, cuda_graph=False)
+    n = min(a.shape[2], b.shape[2])
+    assert torch.equal(a[:, :, :n], b[:, :, :n])
+    first = (a[0, 0, T:] == eos).nonzero()[0, 0]
+    assert (a[:, 0, T + first:] == eos).all()          # a finished sample keeps emitting EOS
     # the same continuation without the cache: greedy on the full forward, one token at a time
     cur, cam = ids, am.to(dev)
     for _ in range(6):
