@@ -136,6 +136,42 @@ def test_other_layouts_vs_oracle(golden):
     assert abs(float(out.loss) - float(o32["loss"])) < 5e-2
 
 
+def test_text_only_batch_forward_backward(golden):
+    """No image in the batch (instruction-tuning samples without pictures): the vision segment of every routed op is empty.
+    Loss and the gradients of the language weights against the bf16 oracle's autograd; the vision experts get no gradient."""
+    need_gpu()
+    g = golden("decoder_tiny")
+    cfg = g["config"]
+    V = cfg["vocab_size"]
+    gen = torch.Generator().manual_seed(31)
+    B, T = 2, 150
+    ids = torch.randint(3, V, (B, T), generator=gen)
+    ids[:, 0] = 1
+    ids = ids[None].repeat(2, 1, 1).to(dev)
+    am = torch.ones(B, T, dtype=torch.long)
+    am[1, -13:] = 0
+    am = am.to(dev)
+    vi = torch.full((B, T), 578, device=dev)
+    labels = ids.clone()
+    labels[:, am == 0] = -100
+    labels[labels == 1] = -100
+    model = build(g).train()
+    out = model(input_ids=ids, attention_mask=am, vision_indices=vi, labels=labels)
+    out.loss.backward()
+    sd = {k: (v.to(dev).bfloat16().requires_grad_(True) if v.is_floating_point() else v.to(dev)) for k, v in g["state_dict"].items()}
+    o = O.libra_forward(sd, O.LibraDims.from_config(cfg), ids, vi, attention_mask=am, labels=labels)
+    o["loss"].backward()
+    assert abs(float(out.loss) - float(o["loss"])) < 5e-2
+    params = dict(model.named_parameters())
+    for name in ("model.layers.1.self_attn.q_proj.weight", "model.layers.0.mlp.down_proj.weight", "model.layers.1.input_layernorm.weight",
+                 "lm_head.weight"):
+        got, want = params[name].grad.float(), sd[name].grad.float()
+        assert rel_err(got, want) < 8e-2, (name, rel_err(got, want))
+    for name, p in params.items():
+        if "vision" in name and p.grad is not None:
+            assert float(p.grad.float().abs().max()) == 0.0, name
+
+
 def test_mislabelled_targets_give_inf_like_the_reference(golden):
     need_gpu()
     g = golden("decoder_tiny")
