@@ -126,11 +126,13 @@ int lb_lfq_unpack(const int64_t* idx, int64_t n, int num_codebooks, int bits, vo
  *   Kfv  = rope(lang j ? kc : k)    Vfv = lang j ? vc : v      (what VISION queries see)
  *   Kfl  = rope(vis  j ? kc : k)    Vfl = vis  j ? vc : v      (what LANGUAGE queries see)
  * sorted_of[bt] = sorted row of original token bt; pos[bt] = rotary position; cos/sin: fp32 tables [n_pos, D/2];
- * flag_sorted[r] = 1 for vision rows. */
+ * flag_sorted[r] = 1 for vision rows.  kv_row (int32 [n_tokens], NULL = identity): row of Kfv/Kfl/Vfv/Vfl that token bt's
+ * key/value operands go to -- the decode step writes them straight into the token's slot of the KV cache
+ * ([B*capacity, H*D] views, kv_row[b] = b*capacity + length). */
 int lb_attn_prep_fwd(const void* q, const void* k, const void* kc, const void* v, const void* vc,
                      const uint8_t* flag_sorted, const int32_t* sorted_of, const int32_t* pos, const float* cos_t,
                      const float* sin_t, void* Q, void* Kfv, void* Kfl, void* Vfv, void* Vfl, int64_t n_tokens, int heads,
-                     int head_dim, void* stream);
+                     int head_dim, const int32_t* kv_row, void* stream);
 /* adjoint: from dQ,dKfv,dKfl,dVfv,dVfl (original order) to dq,dk,dv,dkb,dvb (sorted rows, [N,H*D]) */
 int lb_attn_prep_bwd(const void* dQ, const void* dKfv, const void* dKfl, const void* dVfv, const void* dVfl,
                      const uint8_t* flag_sorted, const int32_t* sorted_of, const int32_t* pos, const float* cos_t,

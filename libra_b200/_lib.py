@@ -38,7 +38,7 @@ SIGNATURES = {
     "lb_embed_bwd": (I, [P, P, L, I, P, L, I, P]),
     "lb_lfq_pack": (I, [P, I, L, I, I, I, L, L, L, P, P]),
     "lb_lfq_unpack": (I, [P, L, I, I, P, I, P]),
-    "lb_attn_prep_fwd": (I, [P] * 15 + [L, I, I, P]),
+    "lb_attn_prep_fwd": (I, [P] * 15 + [L, I, I, P, P]),
     "lb_attn_prep_bwd": (I, [P] * 15 + [L, I, I, P]),
     "lb_attn_fwd": (I, [P, P, P, P, P, P, P, I, P, P, P, P, P, I, I, I, I, I, F, P]),
     "lb_attn_fwd_stream": (I, [P, P, P, P, P, P, P, I, P, P, I, I, I, P, P, P, P, P, I, I, I, I, I, F, P]),

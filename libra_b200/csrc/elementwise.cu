@@ -190,8 +190,10 @@ __global__ void __launch_bounds__(256) attn_prep_fwd_kernel(
     const __nv_bfloat16* __restrict__ v, const __nv_bfloat16* __restrict__ vc, const uint8_t* __restrict__ flag_sorted,
     const int32_t* __restrict__ sorted_of, const int32_t* __restrict__ pos, const float* __restrict__ cos_t,
     const float* __restrict__ sin_t, __nv_bfloat16* __restrict__ Q, __nv_bfloat16* __restrict__ Kfv,
-    __nv_bfloat16* __restrict__ Kfl, __nv_bfloat16* __restrict__ Vfv, __nv_bfloat16* __restrict__ Vfl, int heads, int D) {
+    __nv_bfloat16* __restrict__ Kfl, __nv_bfloat16* __restrict__ Vfv, __nv_bfloat16* __restrict__ Vfl, int heads, int D,
+    const int32_t* __restrict__ kv_row) {
     const int64_t bt = blockIdx.x;
+    const int64_t kr = kv_row ? (int64_t)kv_row[bt] : bt;      // row of the K/V outputs (decode: the token's slot in the KV cache)
     const int64_t s = sorted_of[bt];
     const bool vis = flag_sorted[s] != 0;
     const int C = heads * D, half = D >> 1, upH = D >> 4;      // units per head
@@ -227,18 +229,18 @@ __global__ void __launch_bounds__(256) attn_prep_fwd_kernel(
         rope(k, kp_lo, kp_hi);
         if (kc) rope(kc, kc_lo, kc_hi); else { kc_lo = kp_lo; kc_hi = kp_hi; }
         // vision token: vision queries (fv) see plain, language queries (fl) see bridged; language token: the reverse
-        *reinterpret_cast<uint4*>(Kfv + bt * C + c_lo) = vis ? kp_lo : kc_lo;
-        *reinterpret_cast<uint4*>(Kfv + bt * C + c_hi) = vis ? kp_hi : kc_hi;
-        *reinterpret_cast<uint4*>(Kfl + bt * C + c_lo) = vis ? kc_lo : kp_lo;
-        *reinterpret_cast<uint4*>(Kfl + bt * C + c_hi) = vis ? kc_hi : kp_hi;
+        *reinterpret_cast<uint4*>(Kfv + kr * C + c_lo) = vis ? kp_lo : kc_lo;
+        *reinterpret_cast<uint4*>(Kfv + kr * C + c_hi) = vis ? kp_hi : kc_hi;
+        *reinterpret_cast<uint4*>(Kfl + kr * C + c_lo) = vis ? kc_lo : kp_lo;
+        *reinterpret_cast<uint4*>(Kfl + kr * C + c_hi) = vis ? kc_hi : kp_hi;
         const uint4 vp_lo = __ldg(reinterpret_cast<const uint4*>(v + s * C + c_lo));
         const uint4 vp_hi = __ldg(reinterpret_cast<const uint4*>(v + s * C + c_hi));
         const uint4 vc_lo = vc ? __ldg(reinterpret_cast<const uint4*>(vc + s * C + c_lo)) : vp_lo;
         const uint4 vc_hi = vc ? __ldg(reinterpret_cast<const uint4*>(vc + s * C + c_hi)) : vp_hi;
-        *reinterpret_cast<uint4*>(Vfv + bt * C + c_lo) = vis ? vp_lo : vc_lo;
-        *reinterpret_cast<uint4*>(Vfv + bt * C + c_hi) = vis ? vp_hi : vc_hi;
-        *reinterpret_cast<uint4*>(Vfl + bt * C + c_lo) = vis ? vc_lo : vp_lo;
-        *reinterpret_cast<uint4*>(Vfl + bt * C + c_hi) = vis ? vc_hi : vp_hi;
+        *reinterpret_cast<uint4*>(Vfv + kr * C + c_lo) = vis ? vp_lo : vc_lo;
+        *reinterpret_cast<uint4*>(Vfv + kr * C + c_hi) = vis ? vp_hi : vc_hi;
+        *reinterpret_cast<uint4*>(Vfl + kr * C + c_lo) = vis ? vc_lo : vp_lo;
+        *reinterpret_cast<uint4*>(Vfl + kr * C + c_hi) = vis ? vc_hi : vp_hi;
     }
 }
 
@@ -618,7 +620,7 @@ int lb_lfq_unpack(const int64_t* idx, int64_t n, int num_codebooks, int bits, vo
 int lb_attn_prep_fwd(const void* q, const void* k, const void* kc, const void* v, const void* vc,
                      const uint8_t* flag_sorted, const int32_t* sorted_of, const int32_t* pos, const float* cos_t,
                      const float* sin_t, void* Q, void* Kfv, void* Kfl, void* Vfv, void* Vfl, int64_t n_tokens, int heads,
-                     int head_dim, void* stream) {
+                     int head_dim, const int32_t* kv_row, void* stream) {
     LB_REQUIRE(n_tokens >= 0 && heads > 0 && head_dim >= 16 && head_dim % 16 == 0, LB_EINVAL,
                "attn_prep: head_dim=%d must be a multiple of 16", head_dim);
     LB_REQUIRE(q && k && v && flag_sorted && sorted_of && pos && cos_t && sin_t && Q && Kfv && Kfl && Vfv && Vfl,
@@ -630,7 +632,7 @@ int lb_attn_prep_fwd(const void* q, const void* k, const void* kc, const void* v
     attn_prep_fwd_kernel<<<(unsigned)n_tokens, 256, 0, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)kc, (const __nv_bfloat16*)v,
         (const __nv_bfloat16*)vc, flag_sorted, sorted_of, pos, cos_t, sin_t, (__nv_bfloat16*)Q, (__nv_bfloat16*)Kfv,
-        (__nv_bfloat16*)Kfl, (__nv_bfloat16*)Vfv, (__nv_bfloat16*)Vfl, heads, head_dim);
+        (__nv_bfloat16*)Kfl, (__nv_bfloat16*)Vfv, (__nv_bfloat16*)Vfl, heads, head_dim, kv_row);
     return check_launch("attn_prep_fwd");
 }
 

@@ -489,6 +489,7 @@ class AttnMeta:
     decode: bool = False
     dec_kv_start: Optional[torch.Tensor] = None
     dec_kv_end: Optional[torch.Tensor] = None
+    dec_kv_row: Optional[torch.Tensor] = None          # int32 [B]: b * capacity + length, the new token's row of the cache
 
 
 class BridgeAttention(torch.autograd.Function):
@@ -507,14 +508,21 @@ class BridgeAttention(torch.autograd.Function):
         if rt.n_vis > 0:
             torch.addmm(k[n:], tk[n:], Bk_v.t(), out=kc[n:])
             torch.addmm(v[n:], tv[n:], Bv_v.t(), out=vc[n:])
-        Q, Kfv, Kfl, Vfv, Vfl = ops.attn_prep_fwd(q, k, kc, v, vc, rt.flag_sorted, rt.inv, meta.pos, meta.cos, meta.sin,
-                                                 meta.heads, meta.head_dim)
-        del kc, vc
         scale = 1.0 / math.sqrt(meta.head_dim)
         o = torch.empty_like(q)
+        if meta.decode:
+            # one-token step (N1): the prologue writes the new key/value operands straight into the token's cache slot
+            cache, i = meta.kv_cache, meta.layer_idx
+            Q = ops.attn_prep_fwd(q, k, kc, v, vc, rt.flag_sorted, rt.inv, meta.pos, meta.cos, meta.sin, meta.heads, meta.head_dim,
+                                  kv_out=(cache.k_fv[i], cache.k_fl[i], cache.v_fv[i], cache.v_fl[i]), kv_row=meta.dec_kv_row)[0]
+        else:
+            Q, Kfv, Kfl, Vfv, Vfl = ops.attn_prep_fwd(q, k, kc, v, vc, rt.flag_sorted, rt.inv, meta.pos, meta.cos, meta.sin,
+                                                     meta.heads, meta.head_dim)
+        del kc, vc
         if meta.kv_cache is not None:                      # use_cache=True (modeling_libra.py:343-361): inference only
             cache = meta.kv_cache
-            cache.append(meta.layer_idx, Kfv, Kfl, Vfv, Vfl, meta.seqlen)
+            if not meta.decode:
+                cache.append(meta.layer_idx, Kfv, Kfl, Vfv, Vfl, meta.seqlen)
             if meta.decode:
                 i = meta.layer_idx
                 # with a device-side key range the host-side length only sizes the split: keep it static (graph replay)

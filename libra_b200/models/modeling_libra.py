@@ -318,8 +318,9 @@ class LibraModel(LibraPreTrainedModel):
             pos = position_ids.to(dev).reshape(-1).to(torch.int32).contiguous()
         cos, sin = self._rope_tables(cache.capacity + 1, dev)          # positions never exceed the cache length
         H = self.config.num_attention_heads
+        kv_row = (torch.arange(B, device=dev, dtype=torch.int64) * cache.capacity + cache.len_dev).to(torch.int32)
         return LF.AttnMeta(rt, None, pos, cos, sin, B, 1, H, self.config.hidden_size // H, kv_cache=cache, decode=True,
-                           dec_kv_start=kv_start, dec_kv_end=kv_end)
+                           dec_kv_start=kv_start, dec_kv_end=kv_end, dec_kv_row=kv_row)
 
     # -------------------------------------------------------------- embeddings (sorted rows)
     def embed_sorted(self, input_ids: torch.Tensor, meta: LF.AttnMeta, contiguous_signal: Optional[torch.Tensor]):
@@ -629,11 +630,14 @@ class LibraForCausalLM(LibraPreTrainedModel):
         step = torch.zeros(1, dtype=torch.long, device=dev)
         done = torch.zeros(B, dtype=torch.bool, device=dev) if done is None else done.clone()
         cos, sin = self.model._rope_tables(cache.capacity + 1, dev)
+        kv_row = torch.zeros(B, dtype=torch.int32, device=dev)
+        row0 = torch.arange(B, device=dev, dtype=torch.int64) * cache.capacity
         meta = LF.AttnMeta(rt, None, pos, cos, sin, B, 1, H, cfg.hidden_size // H, kv_cache=cache, decode=True,
-                           dec_kv_start=kv_start, dec_kv_end=kv_end)
+                           dec_kv_start=kv_start, dec_kv_end=kv_end, dec_kv_row=kv_row)
 
         def body():
             kv_end.copy_((cache.len_dev + 1).to(torch.int32).expand(B))
+            kv_row.copy_((row0 + cache.len_dev).to(torch.int32))
             hn, _ = self.model.forward_sorted(ids, meta, None)
             cache.commit_device(flag)
             nxt = self._materialize_logits(hn, meta)[:, :, -1].float().argmax(dim=-1)

@@ -252,13 +252,15 @@ def probe_umma(mode, a, b):
 
 
 # ------------------------------------------------------------ attention
-def attn_prep_fwd(q, k, kc, v, vc, flag_sorted, sorted_of, pos, cos_t, sin_t, heads, head_dim):
-    """kc/vc: bridged variants (k + kb, v + vb) or None."""
+def attn_prep_fwd(q, k, kc, v, vc, flag_sorted, sorted_of, pos, cos_t, sin_t, heads, head_dim, kv_out=None, kv_row=None):
+    """kc/vc: bridged variants (k + kb, v + vb) or None.  kv_out = (Kfv, Kfl, Vfv, Vfl) destination tensors with row map
+    kv_row (decode: the KV cache and the tokens' slots); default: fresh [n, C] tensors, identity rows."""
     n = q.shape[0]
     C = heads * head_dim
-    outs = [torch.empty(n, C, dtype=BF16, device=q.device) for _ in range(5)]
+    Q = torch.empty(n, C, dtype=BF16, device=q.device)
+    outs = [Q] + (list(kv_out) if kv_out is not None else [torch.empty(n, C, dtype=BF16, device=q.device) for _ in range(4)])
     _lib.call("lb_attn_prep_fwd", _p(q), _p(k), _p(kc), _p(v), _p(vc), _p(flag_sorted), _p(sorted_of), _p(pos), _p(cos_t),
-              _p(sin_t), *[_p(o) for o in outs], n, heads, head_dim, _st())
+              _p(sin_t), *[_p(o) for o in outs], n, heads, head_dim, _p(kv_row), _st())
     return outs   # Q, Kfv, Kfl, Vfv, Vfl
 
 
