@@ -112,7 +112,7 @@ enum {
 // barrier whose previous phase the waiter (or something it has already synchronised with) is known to have seen
 // complete; where the stream would allow a role to run further ahead (the owner of a one-tile item, the rescale path)
 // the wait goes through a barrier that cannot be more than one phase behind (PFREE of the role's own tile).
-//
+
 // list position of the CTA's k-th item, or -1.  Without a plan: round k takes list position k*G + c, alternating
 // direction (the list is sorted heaviest first inside a head group, so the snake keeps the per-CTA sums close)
 __device__ __forceinline__ int item_of_round(const Params& p, int k) {
