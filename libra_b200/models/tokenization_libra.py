@@ -90,40 +90,53 @@ class VisionTokenizer(nn.Module):
 def assemble_inputs(text_ids: torch.Tensor, attention_mask: torch.Tensor, img_ph_token_id: int, image_ids: Optional[torch.Tensor],
                     encoder_feat: Optional[torch.Tensor], max_vision_token_length: int = 578,
                     contiguous_ignore: Optional[torch.Tensor] = None, truncation: bool = False,
-                    max_length: Optional[int] = None) -> Dict[str, torch.Tensor]:
+                    max_length: Optional[int] = None, check: bool = False) -> Dict[str, torch.Tensor]:
     """tokenization_libra.py:250-316 on already-tokenised text: text_ids [B,T] hold `img_ph_token_id` at the 578
     placeholder positions of every image (batch-major image order).  Output keys as the reference, including the
-    misspelt `coninous_signal`."""
+    misspelt `coninous_signal`.
+
+    The reference scatters through boolean masks (`ids[:, ph] = ...`: a `nonzero` and a device->host sync each, three per
+    batch, between the vision tokenizer and the decoder).  Here the k-th placeholder position of the flattened batch reads
+    element k of the flattened image tensors: k = cumsum(ph) - 1, gathers and `where`s only -- nothing leaves the device
+    (SURVEY.md section 8f, N4).  check=True verifies that the placeholder count equals the number of image tokens (one
+    sync; the reference's scatter raises on a mismatch)."""
     Q = 2 if image_ids is None else image_ids.shape[0]
-    ids = text_ids[None].repeat(Q, 1, 1)
-    vi = torch.full(text_ids.shape, max_vision_token_length, dtype=torch.long, device=text_ids.device)
-    sig = None
-    if image_ids is not None:
+    L = max_vision_token_length
+    B, T = text_ids.shape
+    if image_ids is None:
+        ids = text_ids[None].repeat(Q, 1, 1)
+        vi = torch.full(text_ids.shape, L, dtype=torch.long, device=text_ids.device)
+        sig = None
+    else:
         ph = text_ids == img_ph_token_id
-        ids[:, ph] = image_ids.flatten(1, 2)
-        vi[ph] = torch.arange(max_vision_token_length, device=text_ids.device).repeat(image_ids.shape[1])
+        n_tok = image_ids.shape[1] * image_ids.shape[2]
+        if check and int(ph.sum()) != n_tok:
+            raise ValueError(f"{int(ph.sum())} placeholder positions for {n_tok} image tokens")
+        rank = (ph.reshape(-1).cumsum(0) - 1).clamp_(0, max(n_tok - 1, 0)).view(B, T)        # k-th placeholder -> image token k
+        ids = torch.where(ph[None], image_ids.flatten(1, 2)[:, rank.reshape(-1)].view(Q, B, T), text_ids[None])
+        vi = torch.where(ph, rank % L, torch.full_like(rank, L))
         z = encoder_feat.new_zeros(encoder_feat.shape[0], 1, encoder_feat.shape[2])
-        cont = torch.cat([z, encoder_feat, z], dim=1)
+        cont = torch.cat([z, encoder_feat, z], dim=1)                                          # zero rows at <img> and </img>
         if contiguous_ignore is not None:
-            cont[contiguous_ignore] = 0
-        sig = encoder_feat.new_zeros(text_ids.shape[0], text_ids.shape[1], encoder_feat.shape[2])
-        sig[ph] = cont.flatten(0, 1)
+            cont = torch.where(contiguous_ignore.view(-1, 1, 1).to(torch.bool), torch.zeros_like(cont), cont)
+        sig = torch.where(ph[..., None], cont.flatten(0, 1)[rank.reshape(-1)].view(B, T, -1), torch.zeros((), dtype=cont.dtype, device=cont.device))
     if truncation and max_length is not None:
         ids, attention_mask, vi = ids[:, :, :max_length], attention_mask[:, :max_length], vi[:, :max_length]
         sig = None if sig is None else sig[:, :max_length]
     return {"input_ids": ids.contiguous(), "attention_mask": attention_mask.contiguous(), "vision_indices": vi.contiguous(),
-            "coninous_signal": sig}
+            "coninous_signal": None if sig is None else sig.contiguous()}
 
 
 @torch.no_grad()
 def get_labels(input_ids: torch.Tensor, attention_mask: torch.Tensor, boi_token_id: int, bos_token_id: int,
                label_mask_position_map: Sequence[Sequence[Sequence[int]]]) -> torch.Tensor:
-    """LibraTrainWrapper.get_labels (modeling_libra.py:1397-1411)."""
-    labels = input_ids.clone()
-    labels[:, attention_mask == 0] = -100
-    labels[labels == boi_token_id] = -100
-    labels[labels == bos_token_id] = -100
+    """LibraTrainWrapper.get_labels (modeling_libra.py:1397-1411).  The span list is host data: it becomes ONE boolean mask
+    built on the host and one `where` on the device, instead of a slice assignment (kernel launch) per span."""
+    B, T = attention_mask.shape
+    span = torch.zeros(B, T, dtype=torch.bool)
     for b, spans in enumerate(label_mask_position_map):
         for (s, e) in spans:
-            labels[:, b, s:e] = -100
-    return labels
+            span[b, s:e] = True
+    drop = (attention_mask == 0) | span.to(input_ids.device, non_blocking=True)
+    drop = drop[None] | (input_ids == boi_token_id) | (input_ids == bos_token_id)
+    return torch.where(drop, torch.full_like(input_ids, -100), input_ids)
