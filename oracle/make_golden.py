@@ -138,6 +138,37 @@ def golden_decode(m):
                 k_for_vision_l1=past[1][0][0][:, :, -8:].clone())
 
 
+TINY_VQ_DECODER = dict(ch=32, out_ch=3, ch_mult=(1, 2, 2), num_res_blocks=1, attn_resolutions=(6,), dropout=0.0, in_channels=3,
+                       resolution=48, z_channels=32, initial_resolution=6, num_attn_head=1)
+
+
+def golden_vq_decode(m):
+    """N2: ids -> pixels through the reference's taming Decoder + LFQ.indices_to_codes + post_quant_conv, chained as
+    VQModel.decode_code does (taming/models/vqgan.py:122-130) behind ImageTokenizer.decode (image_tokenizer.py:97-124).
+    embed_dim 24 so that the LFQ's project_out Linear is exercised."""
+    import importlib
+    dm = importlib.import_module("libra.models.libra.taming.modules.diffusionmodules.model")
+    lfq = importlib.import_module("libra.models.libra.taming.modules.quantization.lookup_free_quantization")
+    torch.manual_seed(7)
+    dec = dm.Decoder(**TINY_VQ_DECODER).eval()
+    quant = lfq.LFQ(dim=24, codebook_size=512, num_codebooks=2, entropy_loss_weight=0.1, commitment_loss_weight=1.,
+                    diversity_gamma=2.5).eval()
+    pqc = torch.nn.Conv2d(24, TINY_VQ_DECODER["z_channels"], 1)
+    offset, boi = 32000, 32512
+    g = torch.Generator().manual_seed(1)
+    ids = torch.randint(0, 512, (2, 2, 36), generator=g) + offset
+    ids = torch.cat([torch.full((2, 2, 1), boi), ids, torch.full((2, 2, 1), boi + 1)], dim=2)
+    with torch.no_grad():
+        code = (ids[:, :, 1:-1].reshape(2, 2, 6, 6).permute(1, 2, 3, 0) - offset)
+        z = quant.indices_to_codes(code)
+        pixels = dec(pqc(z))
+    sd = {f"decoder.{k}": v.clone() for k, v in dec.state_dict().items()}
+    sd.update({f"post_quant_conv.{k}": v.clone() for k, v in pqc.state_dict().items()})
+    sd.update({f"quantize.{k}": v.clone() for k, v in quant.state_dict().items() if k.startswith("project_out")})
+    return dict(config=TINY_VQ_DECODER, state_dict=sd, ids=ids, token_offset=offset, boi_token_id=boi, codebook_size=512,
+                codes=z.clone(), pixels=pixels.clone())
+
+
 def golden_attention(m):
     """One LibraAttention module at the production head_dim (128), 2 heads."""
     torch.manual_seed(1)
@@ -227,7 +258,8 @@ def main():
     m = refshim.import_reference()
     os.makedirs(OUT, exist_ok=True)
     only = sys.argv[1:]
-    for name, fn in (("decoder_tiny", golden_decoder), ("decode_tiny", golden_decode), ("attention_hd128", golden_attention),
+    for name, fn in (("decoder_tiny", golden_decoder), ("decode_tiny", golden_decode), ("vq_decode_tiny", golden_vq_decode),
+                     ("attention_hd128", golden_attention),
                      ("clip_tiny", golden_clip), ("lfq", golden_lfq), ("norms_rope", golden_norms_rope)):
         if only and name not in only:
             continue

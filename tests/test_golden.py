@@ -78,3 +78,17 @@ def test_rmsnorm_rope(golden):
     assert torch.equal(O.rope_apply(g["q"], c, s), g["q_rot"])
     assert torch.equal(O.rope_apply(g["k"], c, s), g["k_rot"])
     assert torch.equal(O.rope_apply(g["k"] * 2, c, s), g["k2_rot"])
+
+
+def test_oracle_vq_decode_matches_reference_golden(golden):
+    """N2 oracle (ids -> pixels) against the fixture the reference's taming Decoder produced (oracle/make_golden.py)."""
+    g = golden("vq_decode_tiny")
+    cfg = g["config"]
+    d = O.VQDecoderDims(**{k: v for k, v in cfg.items() if k not in ("dropout", "in_channels")})
+    got = O.vq_decode(g["state_dict"], d, g["ids"], g["token_offset"], g["codebook_size"], boi_token_id=g["boi_token_id"])
+    assert got.shape == g["pixels"].shape and (got - g["pixels"]).abs().max() < 2e-5
+    code = g["ids"][:, :, 1:-1].reshape(2, 2, 6, 6).permute(1, 2, 3, 0) - g["token_offset"]
+    z = O.lfq_indices_to_codes(code, 9)
+    import torch.nn.functional as F
+    z = F.linear(z.permute(0, 2, 3, 1), g["state_dict"]["quantize.project_out.weight"], g["state_dict"]["quantize.project_out.bias"]).permute(0, 3, 1, 2)
+    assert (z - g["codes"]).abs().max() < 1e-6

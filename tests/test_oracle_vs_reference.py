@@ -146,3 +146,40 @@ def test_cached_decode_matches_reference(ref, dtype):
                 assert (lr[0][0].float() - lo[0][0].float()).abs().max() < tol and (lr[0][1].float() - lo[0][1].float()).abs().max() < tol
                 assert (lr[1].float() - lo[1].float()).abs().max() < tol and (lr[2].float() - lo[2].float()).abs().max() < tol
                 assert torch.equal(lr[3], lo[3])
+
+
+TINY_VQ_DECODER = dict(ch=32, out_ch=3, ch_mult=(1, 2, 2), num_res_blocks=1, attn_resolutions=(6,), dropout=0.0, in_channels=3,
+                       resolution=48, z_channels=32, initial_resolution=6, num_attn_head=1)
+
+
+@pytest.mark.parametrize("embed_dim,heads", [(18, 1), (24, 2)])
+def test_vq_decode_matches_reference(ref, embed_dim, heads):
+    """N2: ids -> pixels.  The reference's own taming Decoder, LFQ.indices_to_codes and a post_quant_conv, chained as
+    VQModel.decode_code does (vqgan.py:122-130) behind ImageTokenizer.decode's id handling (image_tokenizer.py:97-124)."""
+    import importlib
+    dm = importlib.import_module("libra.models.libra.taming.modules.diffusionmodules.model")
+    lfq = importlib.import_module("libra.models.libra.taming.modules.quantization.lookup_free_quantization")
+    torch.manual_seed(7)
+    cfg = dict(TINY_VQ_DECODER, num_attn_head=heads)
+    dec = dm.Decoder(**cfg).eval()
+    quant = lfq.LFQ(dim=embed_dim, codebook_size=512, num_codebooks=2, entropy_loss_weight=0.1, commitment_loss_weight=1.,
+                    diversity_gamma=2.5).eval()
+    pqc = torch.nn.Conv2d(embed_dim, cfg["z_channels"], 1)
+    offset, boi = 32000, 32512
+    g = torch.Generator().manual_seed(1)
+    ids = torch.randint(0, 512, (2, 3, 36), generator=g) + offset                      # [Q, B, 6*6]
+    with_marks = torch.cat([torch.full((2, 3, 1), boi), ids, torch.full((2, 3, 1), boi + 1)], dim=2)
+    with torch.no_grad():
+        code = (ids.reshape(2, 3, 6, 6).permute(1, 2, 3, 0) - offset)
+        want = dec(pqc(quant.indices_to_codes(code)))
+        sd = {f"decoder.{k}": v for k, v in dec.state_dict().items()}
+        sd.update({f"post_quant_conv.{k}": v for k, v in pqc.state_dict().items()})
+        sd.update({f"quantize.{k}": v for k, v in quant.state_dict().items() if k.startswith("project_out")})
+        d = O.VQDecoderDims(**{k: v for k, v in cfg.items() if k not in ("dropout", "in_channels")})
+        got = O.vq_decode(sd, d, with_marks, offset, 512, boi_token_id=boi)
+        got2 = O.vq_decode(sd, d, ids, offset, 512, boi_token_id=boi)
+    assert want.shape == (3, 3, 48, 48) == got.shape
+    assert (got - want).abs().max() < 2e-5 and torch.equal(got, got2)
+    # bit unpacking is exact: most significant bit first, +-1
+    codes = O.lfq_indices_to_codes(torch.tensor([[[[0b100000001, 0b011111110]]]]), 9)
+    assert codes.flatten().tolist() == [1, -1, -1, -1, -1, -1, -1, -1, 1, -1, 1, 1, 1, 1, 1, 1, 1, -1]
