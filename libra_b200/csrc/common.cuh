@@ -129,7 +129,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Bounded spin: a protocol bug traps (error reported through the C ABI)
 // instead of hanging the device.
 #ifndef LB_MBAR_SPIN_LIMIT
-#define LB_MBAR_SPIN_LIMIT (1u << 22)      // ~1 s: a protocol bug must not hold a GPU for minutes
+#define LB_MBAR_SPIN_LIMIT (1u << 24)      // a failed try_wait returns after ~30-60 clk (measured): ~0.5 s at full clock.
+                                           // Long enough for any legitimate wait (< 1 ms) even under a profiler or at idle
+                                           // clocks, short enough that a protocol bug does not hold a GPU for minutes
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
