@@ -567,6 +567,10 @@ class LibraForCausalLM(LibraPreTrainedModel):
         graph with the cache addressed through its device-side length and the argmax fed back on the device, and replayed."""
         if do_sample:
             raise NotImplementedError("greedy decoding only")
+        if vision_indices is None:
+            raise ValueError("vision_indices [B,T] is required (578 on text positions), as in the reference's generate kwargs")
+        if not use_cache:
+            raise NotImplementedError("generate() decodes with the KV cache")
         Q, B, T = input_ids.shape
         dev = input_ids.device
         am = torch.ones(B, T, dtype=torch.long, device=dev) if attention_mask is None else attention_mask.to(dev).long()
