@@ -229,6 +229,47 @@ int lb_gemm_bf16(const void* A, const void* B, void* C, const void* bias, int64_
                  int64_t ldb, int64_t ldc, int trans_a, int trans_b, int out_dtype, int accumulate, int act,
                  void* stream);
 
+/* ---- grouped persistent tcgen05 GEMM (the decoder's / ViT's / heads' dense products) ----------------------
+ * Replaces every nn.Linear / F.linear product the reference sends to cuBLAS:
+ *   LlamaAttention / LlamaMLP projections     libra/models/llama/modeling_llama.py:185-201
+ *   LibraLinear chain F.linear(F.linear(x,A),B)  libra/models/libra/modeling_libra.py:192-199 (routed by :129-147, :310-319)
+ *   SwiGLU product silu(gate x) * up x        modeling_libra.py:232-233
+ *   CLIP q/k/v/out/fc1/fc2 (+bias, quick_gelu)  libra/models/clip/modeling_clip.py:279-282, 371-378
+ *   lm_head / vision heads                    modeling_libra.py:1018-1052
+ * and their dgrad / wgrad products in backward (all four operand layouts, no transposes materialised).
+ * Up to 16 problems run in ONE persistent launch (CTA pairs, tcgen05 cta_group::2, 256 x 256 tiles, fp32 accumulation
+ * in TMEM, TMA-store epilogue); for problem i
+ *     C_i[M,N] = epi( op(A_i) . op(B_i) [+ bias_i] ) [+ D_i]          all bf16, row pitches ld* in elements (x8)
+ *   trans_a = 0: A stored [M,K];  1: A stored [K,M]        trans_b = 0: B stored [N,K] (nn.Linear weight);  1: [K,N]
+ *   D (optional, may alias C): addend, added after C was rounded to bf16 (`residual + linear(x)` of eager PyTorch;
+ *     with D == C this is beta = 1 accumulation into a gradient buffer)
+ *   epilogue LB_EPI_NONE; LB_EPI_QGELU: C = quick_gelu(.), G (optional) receives the pre-activation;
+ *     LB_EPI_SWIGLU: B = gate weight, B2 = up weight (both [N,K]); C = silu(x B^T) * (x B2^T), G / U (optional)
+ *     receive the gate / up pre-activations
+ *   wait_on = j (< i, -1 none): A_i is C_j (same M): tiles of problem i start once the row block of C_j they read is
+ *     complete -- the LibraLinear chain in one launch.  Needs lb_gemm_grouped_workspace_bytes() bytes of workspace.
+ * Problems with M == 0 or N == 0 are skipped (an empty modality segment). */
+#define LB_EPI_NONE 0
+#define LB_EPI_QGELU 1
+#define LB_EPI_SWIGLU 2
+typedef struct lb_gemm_problem {
+    const void* A;
+    const void* B;
+    void* C;
+    const void* D;
+    const void* bias;
+    const void* B2;
+    void* G;
+    void* U;
+    int64_t M, N, K;
+    int64_t lda, ldb, ldc, ldd;
+    int32_t trans_a, trans_b, epilogue, wait_on;
+} lb_gemm_problem;
+int lb_gemm_grouped_workspace_bytes(const lb_gemm_problem* problems, int n);
+int lb_gemm_grouped(const lb_gemm_problem* problems, int n, void* workspace, int64_t workspace_bytes, void* stream);
+/* encoded TMA descriptors are cached by (pointer, shape, pitch, box): counters for the "no per-call encode" check */
+int lb_gemm_tmap_cache_stats(int64_t* hits, int64_t* misses);
+
 /* ---- A1 patch embedding (im2col-free, TMA-staged) ----------------------------
  * libra/models/clip/modeling_clip.py:193-228.  pixels [B,3,S,S] bf16 (NCHW), class_emb [C], pos_emb [(S/14)^2+1, C];
  * writes emb [B, (S/14)^2+1, C] = cat(cls, conv14x14/s14(pixels)) + pos.  The conv weight [C,3,14,14] is K-packed

@@ -126,26 +126,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded spin: a protocol bug traps (error reported through the C ABI)
-// instead of hanging the device.
-#ifndef LB_MBAR_SPIN_LIMIT
-#define LB_MBAR_SPIN_LIMIT (1u << 24)      // a failed try_wait returns after ~30-60 clk (measured): ~0.5 s at full clock.
-                                           // Long enough for any legitimate wait (< 1 ms) even under a profiler or at idle
-                                           // clocks, short enough that a protocol bug does not hold a GPU for minutes
+// Bounded wait: a protocol bug traps (error reported through the C ABI) instead of hanging the device.  The bound is
+// wall time on the SM clock (checked every 4096 failed polls), not a poll count: ~2^34 clk = 8-12 s at 1.4-2 GHz, orders of
+// magnitude above any legitimate wait (< 10 ms even under a profiler, a debugger single-step excepted), so slow clocks or
+// compute-sanitizer cannot turn a slow run into an abort.  -DLB_MBAR_TIMEOUT_CLK=0 removes the check.
+#ifndef LB_MBAR_TIMEOUT_CLK
+#define LB_MBAR_TIMEOUT_CLK (1ll << 34)
 #endif
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if (++spins > LB_MBAR_SPIN_LIMIT) {
-            printf("libra_b200: mbarrier timeout block=%d thread=%d parity=%u\n", blockIdx.x, threadIdx.x, parity);
-            __trap();
-        }
-    }
-}
-
-// Lean variants for the attention kernels' hot loops (shared-window barrier address precomputed by the caller, no printf
-// on the slow path): a single-thread role executes one dependent instruction every ~5-10 clk, so every instruction between
-// two tcgen05.mma batches is tensor-pipe idle time (profiles/r01_attn_fwd_stream_notes.md).
+// `bar_addr`: shared-window address of the barrier.  The fast path is one try_wait (a single-thread role executes one
+// dependent instruction every ~5-10 clk, so every instruction between two tcgen05.mma batches is tensor-pipe idle time,
+// profiles/r01_attn_fwd_stream_notes.md); no printf on the slow path (keeps the callers' register allocation lean).
 __device__ __forceinline__ void wait_bar(uint32_t bar_addr, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -158,6 +148,7 @@ __device__ __forceinline__ void wait_bar(uint32_t bar_addr, uint32_t parity) {
         : "r"(bar_addr), "r"(parity)
         : "memory");
     if (ok) return;
+    const long long t0 = clock64();
     uint32_t spins = 0;
     do {
         asm volatile(
@@ -169,9 +160,10 @@ __device__ __forceinline__ void wait_bar(uint32_t bar_addr, uint32_t parity) {
             : "=r"(ok)
             : "r"(bar_addr), "r"(parity)
             : "memory");
-        if (++spins > LB_MBAR_SPIN_LIMIT) __trap();              // protocol bug: fail instead of hanging the device
+        if (LB_MBAR_TIMEOUT_CLK > 0 && (++spins & 4095u) == 0 && clock64() - t0 > LB_MBAR_TIMEOUT_CLK) __trap();
     } while (!ok);
 }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { wait_bar(smem_u32(bar), parity); }
 __device__ __forceinline__ void commit_bar(uint32_t bar_addr) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_addr) : "memory");
 }
@@ -429,6 +421,85 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
         "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
         "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
         "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+
+// ----------------------------------------------------------------------------
+// thread-block clusters and the 2-CTA (cta_group::2) forms of the above
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// all threads of every CTA of the cluster
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `saddr` (a shared::cta window address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load issued by either CTA of a pair; `bar_cluster_addr` may be the partner's barrier
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
+                                                int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_addr(uint32_t smem_dst, const CUtensorMap* m, uint32_t bar_addr, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_addr(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t* smem_result, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+                 "r"(cols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_cg2() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// arrive (count 1) on the barrier at the same shared-memory offset in every CTA of `cta_mask` once the MMAs issued so far
+// by this thread have completed
+__device__ __forceinline__ void commit_bar_cg2(uint32_t bar_addr, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     bar_addr),
+                 "h"(cta_mask)
+                 : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B with M = 256 split over the pair, issued by the leader CTA only
+__device__ __forceinline__ void umma_ss_lo_cg2(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 da, {%1, %3};\n\t"
+        "mov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_lo), "r"(b_lo), "r"(DESC_HI_SW128), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 

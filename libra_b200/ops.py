@@ -120,11 +120,13 @@ def layernorm_bwd(dy, x, w, mean, rstd):
 
 
 # ------------------------------------------------------------ elementwise
-def swiglu_fwd(gate, up):
-    """gate/up: [rows, cols] views (last dim contiguous, row pitch arbitrary multiple of 8)."""
+def swiglu_fwd(gate, up, out=None):
+    """gate/up/out: [rows, cols] views (last dim contiguous, row pitch arbitrary multiple of 8)."""
     rows, cols = gate.shape
-    out = torch.empty(rows, cols, dtype=BF16, device=gate.device)
-    _lib.call("lb_swiglu_fwd", _p(gate), _p(up), _p(out), rows, cols, gate.stride(0), up.stride(0), cols, _st())
+    if out is None:
+        out = torch.empty(rows, cols, dtype=BF16, device=gate.device)
+    if rows > 0:
+        _lib.call("lb_swiglu_fwd", _p(gate), _p(up), _p(out), rows, cols, gate.stride(0), up.stride(0), out.stride(0), _st())
     return out
 
 
@@ -222,6 +224,84 @@ def gemm(a, b, trans_a=False, trans_b=False, out=None, out_dtype=BF16, bias=None
         out = torch.empty(M, N, dtype=out_dtype, device=a.device)
     _lib.call("lb_gemm_bf16", _p(a), _p(b), _p(out), _p(bias), M, N, K, a.stride(0), b.stride(0), out.stride(0),
               int(trans_a), int(trans_b), DT_BF16 if out.dtype == BF16 else DT_F32, int(accumulate), int(act), _st())
+    return out
+
+
+class GemmProblem(ctypes.Structure):
+    """lb_gemm_problem (include/libra_b200.h)."""
+    _fields_ = [("A", ctypes.c_void_p), ("B", ctypes.c_void_p), ("C", ctypes.c_void_p), ("D", ctypes.c_void_p),
+                ("bias", ctypes.c_void_p), ("B2", ctypes.c_void_p), ("G", ctypes.c_void_p), ("U", ctypes.c_void_p),
+                ("M", ctypes.c_int64), ("N", ctypes.c_int64), ("K", ctypes.c_int64),
+                ("lda", ctypes.c_int64), ("ldb", ctypes.c_int64), ("ldc", ctypes.c_int64), ("ldd", ctypes.c_int64),
+                ("trans_a", ctypes.c_int32), ("trans_b", ctypes.c_int32), ("epilogue", ctypes.c_int32),
+                ("wait_on", ctypes.c_int32)]
+
+
+EPI_NONE, EPI_QGELU, EPI_SWIGLU = 0, 1, 2
+
+
+def _ld(t: torch.Tensor, name: str) -> int:
+    if t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1) or t.dtype != BF16 or not t.is_cuda:
+        raise ValueError(f"gemm operand {name}: need a 2-D bf16 CUDA tensor with unit inner stride, got "
+                         f"{tuple(t.shape)} strides {t.stride()} {t.dtype} {t.device}")
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+def gp(a, b, c, *, ta=False, tb=False, d=None, bias=None, epi=EPI_NONE, b2=None, g=None, u=None, wait_on=-1):
+    """One problem of a grouped launch:  c[M,N] = epi(op(a) . op(b) [+ bias]) [+ d].
+    a: [M,K] (ta: [K,M]);  b: [N,K], the nn.Linear weight layout (tb: [K,N]);  c, d, g, u: [M,N] row-major views."""
+    M = a.shape[1] if ta else a.shape[0]
+    K = a.shape[0] if ta else a.shape[1]
+    N = b.shape[1] if tb else b.shape[0]
+    if (b.shape[0] if tb else b.shape[1]) != K or tuple(c.shape) != (M, N):
+        raise ValueError(f"gemm shape mismatch: a {tuple(a.shape)} ta={ta}, b {tuple(b.shape)} tb={tb}, c {tuple(c.shape)}")
+    q = GemmProblem()
+    q.A, q.B, q.C = a.data_ptr(), b.data_ptr(), c.data_ptr()
+    q.M, q.N, q.K = M, N, K
+    q.lda, q.ldb, q.ldc = _ld(a, "a"), _ld(b, "b"), _ld(c, "c")
+    q.trans_a, q.trans_b, q.epilogue, q.wait_on = int(ta), int(tb), int(epi), int(wait_on)
+    if d is not None:
+        if tuple(d.shape) != (M, N):
+            raise ValueError("gemm addend shape")
+        q.D, q.ldd = d.data_ptr(), _ld(d, "d")
+    if bias is not None:
+        q.bias = bias.data_ptr()
+    if b2 is not None:
+        if tuple(b2.shape) != tuple(b.shape) or _ld(b2, "b2") != q.ldb:
+            raise ValueError("gemm b2 must match b")
+        q.B2 = b2.data_ptr()
+    for nm, t in (("G", g), ("U", u)):
+        if t is not None:
+            if tuple(t.shape) != (M, N) or _ld(t, nm) != q.ldc:
+                raise ValueError(f"gemm extra output {nm} must match c (shape and pitch)")
+            setattr(q, nm, t.data_ptr())
+    return q
+
+
+_GG_WS = {}
+
+
+def gemm_grouped(problems):
+    """Run up to 16 problems (see gp()) as ONE persistent tcgen05 launch on the current stream (csrc/gemm_grouped.cu)."""
+    n = len(problems)
+    if n == 0:
+        return
+    arr = (GemmProblem * n)(*problems)
+    ws = None
+    if any(q.wait_on >= 0 for q in problems):
+        dev = torch.cuda.current_device()
+        key = (dev, torch.cuda.current_stream().cuda_stream)
+        ws = _GG_WS.get(key)
+        if ws is None:                      # per-stream counters of the chained problems (zeroed by the library per launch)
+            ws = _GG_WS[key] = torch.zeros(4096, dtype=torch.int32, device=f"cuda:{dev}")
+    _timed_call("lb_gemm_grouped", arr, n, _p(ws), 0 if ws is None else ws.numel() * 4, _st())
+
+
+def linear(x, w, out=None, *, bias=None, epi=EPI_NONE, d=None, g=None):
+    """y = x w^T (+bias, activation, addend) through the grouped kernel (single problem)."""
+    if out is None:
+        out = torch.empty(x.shape[0], w.shape[0], dtype=BF16, device=x.device)
+    gemm_grouped([gp(x, w, out, bias=bias, epi=epi, d=d, g=g)])
     return out
 
 
