@@ -233,6 +233,7 @@ def main():
     if world != args.gpus and not (world == 1 and args.gpus == 1):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
     from libra_b200 import _lib, ops, synthetic
+    from libra_b200 import functional as LF
     from libra_b200.models import LibraConfig, LibraForCausalLM
 
     torch.cuda.set_device(local)
@@ -272,6 +273,9 @@ def main():
             p.data = flat_w[off:off + n].view_as(p)
             p.grad = flat[off:off + n].view_as(p)
             off += n
+    # the flat buffer is owned here: weight gradients are written into it by the GEMM epilogues (the first micro-batch of a
+    # step overwrites, later ones add) -- no zeroing pass and no autograd accumulation pass over 22 GB
+    LF.mark_fused_grad(params)
     opt = None
     if args.optimizer == "adamw":
         from libra_b200.optim import FlatAdamW
@@ -342,7 +346,7 @@ def main():
     def step(inp, from_host: bool):
         if from_host:
             inp = {k: v.to(dev, non_blocking=True) for k, v in inp.items()}
-        flat.zero_()
+        LF.begin_grad_step(params)
         total = None
         n_micro = B // MB
         for i in range(n_micro):

@@ -248,7 +248,15 @@ int lb_gemm_bf16(const void* A, const void* B, void* C, const void* bias, int64_
  *     receive the gate / up pre-activations
  *   wait_on = j (< i, -1 none): A_i is C_j (same M): tiles of problem i start once the row block of C_j they read is
  *     complete -- the LibraLinear chain in one launch.  Needs lb_gemm_grouped_workspace_bytes() bytes of workspace.
- * Problems with M == 0 or N == 0 are skipped (an empty modality segment). */
+ * Problems with M == 0 or N == 0 are skipped (an empty modality segment).
+ *   flags & LB_GEMM_ACCUMULATE_PREV: this entry is one more product A_i . B_i summed (in the fp32 accumulator, before
+ *     the epilogue) into the PREVIOUS entry's problem -- same M, N and operand layouts, own K; C / D / bias / epilogue
+ *     are taken from the first entry of the chain.  dx = dq.Wq + dk.Wk + dv.Wv of a fan-out is one problem of three
+ *     segments instead of three beta = 1 passes over dx.
+ *   A dependent whose A is read transposed (or has another M) waits for the whole producer instead of one row block.
+ *   When N is not a multiple of 8 the 16-byte unit holding the last columns of each row is written whole (zeros in
+ *     the padding), so ldc must cover N rounded up to 8. */
+#define LB_GEMM_ACCUMULATE_PREV 1
 #define LB_EPI_NONE 0
 #define LB_EPI_QGELU 1
 #define LB_EPI_SWIGLU 2
@@ -264,6 +272,8 @@ typedef struct lb_gemm_problem {
     int64_t M, N, K;
     int64_t lda, ldb, ldc, ldd;
     int32_t trans_a, trans_b, epilogue, wait_on;
+    const float* alpha;   /* optional device fp32 scalar: C = epi(alpha * (A.B) + bias) + D */
+    int64_t flags;        /* LB_GEMM_* bits */
 } lb_gemm_problem;
 int lb_gemm_grouped_workspace_bytes(const lb_gemm_problem* problems, int n);
 int lb_gemm_grouped(const lb_gemm_problem* problems, int n, void* workspace, int64_t workspace_bytes, void* stream);

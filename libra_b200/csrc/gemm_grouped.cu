@@ -37,8 +37,10 @@ namespace lb {
 
 constexpr int GG_BM = 128;              // accumulator rows per CTA (TMEM lanes)
 constexpr int GG_BK = 64;               // K elements per ring stage (one 128 B swizzle row)
-constexpr int GG_MAXG = 16;             // problems per launch
-constexpr int GG_MAXAUX = 16;           // extra tensor maps per launch (addends, SwiGLU up-weights, extra outputs)
+constexpr int GG_MAXG = 24;             // output problems per launch (after merging accumulation chains)
+constexpr int GG_MAXIN = 32;            // entries of the caller's list per launch
+constexpr int GG_MAXSEG = 6;            // K segments (A_s . B_s products summed into one accumulator) per problem
+constexpr int GG_MAXMAPS = 112;         // tensor maps per launch
 constexpr int GG_THREADS = 192;
 constexpr int GG_A_BYTES = GG_BM * GG_BK * 2;          // 16 KB
 constexpr int GG_CHUNK_BYTES = GG_BM * 64 * 2;         // epilogue staging tile: 128 rows x 64 bf16
@@ -55,29 +57,34 @@ struct GGCfg {
 
 enum { GG_EPI_NONE = 0, GG_EPI_QGELU = 1, GG_EPI_SWIGLU = 2 };
 
+struct GGSeg {
+    short a_map, b_map;      // indices into GGParams::maps
+    short wait_on;           // problem whose C is this segment's A, or -1
+    short wait_all;          // 0: wait for the row block this tile reads; 1: wait for the whole problem (A read transposed)
+    int num_kb;
+};
+
 struct GGProb {
-    int M, N, K;
+    int M, N;
     int tile_n;              // accumulator columns per tile
     int tiles_m, tiles_n;
     int tile_begin;          // first global tile index of this problem
-    int num_kb;
-    int a_mn, b_mn;          // operand is MN-major (stored transposed)
+    int a_mn, b_mn;          // operands are MN-major (stored transposed); the same for every segment
     int epi;
-    int aux_d, aux_b2, aux_g, aux_u;    // indices into GGParams::aux or -1
-    int wait_on;             // problem whose C is this problem's A (same row blocks), or -1
-    int signal;              // this problem's epilogue bumps counters[counter_off + row block]
+    int nseg;
+    short c_map, aux_d, aux_b2, aux_g, aux_u;    // indices into GGParams::maps or -1
+    short signal;            // this problem's epilogue bumps counters[counter_off + row block]
     int counter_off;
     int b_part_rows;         // rows (K-major) or columns (MN-major) of B each CTA loads per part
     int b_parts;             // parts per CTA (2: SwiGLU on CG = 1)
     int b_tx_bytes;          // bytes of B per stage per CTA
     const __nv_bfloat16* bias;
+    const float* alpha;      // optional device scalar multiplying the accumulator
+    GGSeg seg[GG_MAXSEG];
 };
 
 struct GGParams {
-    CUtensorMap tmA[GG_MAXG];
-    CUtensorMap tmB[GG_MAXG];
-    CUtensorMap tmC[GG_MAXG];
-    CUtensorMap aux[GG_MAXAUX];
+    CUtensorMap maps[GG_MAXMAPS];
     GGProb prob[GG_MAXG];
     int n_prob, total_tiles;
     int* counters;
@@ -203,60 +210,67 @@ __global__ void __launch_bounds__(GG_THREADS, 1) gemm_grouped_kernel(const __gri
             for (int t = first_tile; t < p.total_tiles; t += tile_stride) {
                 const GGTile tl = gg_decode(p, t);
                 const GGProb& pb = p.prob[tl.g];
-                const CUtensorMap* tmA = &p.tmA[tl.g];
-                if (pb.wait_on >= 0) {
-                    const GGProb& src = p.prob[pb.wait_on];
-                    const int* ctr = p.counters + src.counter_off + tl.mt;
-                    const int target = src.tiles_n * CG;
-                    const long long t0 = clock64();
-                    while (ld_acquire_gpu(ctr) < target) {
-                        __nanosleep(100);
-                        if (LB_MBAR_TIMEOUT_CLK > 0 && clock64() - t0 > LB_MBAR_TIMEOUT_CLK) {
-                            printf("libra_b200 gemm_grouped: dependency timeout problem=%d row block=%d\n", tl.g, tl.mt);
-                            __trap();
-                        }
-                    }
-                    fence_proxy_async_all();
-                }
                 const int m0 = tl.mt * (GG_BM * CG) + (int)rank * GG_BM;
                 const bool dual = pb.epi == GG_EPI_SWIGLU;
                 const int n_base = dual ? tl.nt * (pb.tile_n / 2) : tl.nt * pb.tile_n + (int)rank * pb.b_part_rows;
                 const uint32_t tx = (uint32_t)(GG_A_BYTES + pb.b_tx_bytes) * CG;
-                for (int kb = 0; kb < pb.num_kb; ++kb) {
-                    gg_wait(empty_a + 8 * stage, phase ^ 1u, 100 + stage);
-                    if (rank == 0) {
-                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_a + 8 * stage), "r"(tx)
-                                     : "memory");
+                for (int sg = 0; sg < pb.nseg; ++sg) {
+                    const GGSeg& sgm = pb.seg[sg];
+                    if (sgm.wait_on >= 0) {
+                        // the A operand of this segment is another problem's output: wait until its tiles were published
+                        const GGProb& src = p.prob[sgm.wait_on];
+                        const int target = src.tiles_n * CG;
+                        const int r0 = sgm.wait_all ? 0 : tl.mt, r1 = sgm.wait_all ? src.tiles_m : tl.mt + 1;
+                        const long long t0 = clock64();
+                        for (int r = r0; r < r1; ++r) {
+                            const int* ctr = p.counters + src.counter_off + r;
+                            while (ld_acquire_gpu(ctr) < target) {
+                                __nanosleep(100);
+                                if (LB_MBAR_TIMEOUT_CLK > 0 && clock64() - t0 > LB_MBAR_TIMEOUT_CLK) {
+                                    printf("libra_b200 gemm_grouped: dependency timeout problem=%d segment=%d row block=%d\n", tl.g, sg, r);
+                                    __trap();
+                                }
+                            }
+                        }
+                        fence_proxy_async_all();
                     }
-                    const uint32_t bar = full_leader + 8 * stage;
-                    const uint32_t sa = stage_base + stage * Cfg::STAGE_BYTES;
-                    const uint32_t sb = sa + GG_A_BYTES;
-                    const int k0 = kb * GG_BK;
-                    if (!pb.a_mn) {
-                        if (CG == 2) tma_load_2d_cg2(sa, tmA, bar, k0, m0); else tma_load_2d_addr(sa, tmA, bar, k0, m0);
-                    } else {
+                    const CUtensorMap* tmA = &p.maps[sgm.a_map];
+                    const CUtensorMap* tmB0 = &p.maps[sgm.b_map];
+                    for (int kb = 0; kb < sgm.num_kb; ++kb) {
+                        gg_wait(empty_a + 8 * stage, phase ^ 1u, 100 + stage);
+                        if (rank == 0) {
+                            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_a + 8 * stage), "r"(tx)
+                                         : "memory");
+                        }
+                        const uint32_t bar = full_leader + 8 * stage;
+                        const uint32_t sa = stage_base + stage * Cfg::STAGE_BYTES;
+                        const uint32_t sb = sa + GG_A_BYTES;
+                        const int k0 = kb * GG_BK;
+                        if (!pb.a_mn) {
+                            if (CG == 2) tma_load_2d_cg2(sa, tmA, bar, k0, m0); else tma_load_2d_addr(sa, tmA, bar, k0, m0);
+                        } else {
 #pragma unroll
-                        for (int c = 0; c < GG_BM / 64; ++c) {
-                            if (CG == 2) tma_load_2d_cg2(sa + c * (GG_BK * 128), tmA, bar, m0 + c * 64, k0);
-                            else tma_load_2d_addr(sa + c * (GG_BK * 128), tmA, bar, m0 + c * 64, k0);
+                            for (int c = 0; c < GG_BM / 64; ++c) {
+                                if (CG == 2) tma_load_2d_cg2(sa + c * (GG_BK * 128), tmA, bar, m0 + c * 64, k0);
+                                else tma_load_2d_addr(sa + c * (GG_BK * 128), tmA, bar, m0 + c * 64, k0);
+                            }
                         }
+                        if (!pb.b_mn) {
+                            for (int part = 0; part < pb.b_parts; ++part) {
+                                const int which = dual ? (CG == 2 ? (int)rank : part) : 0;
+                                const CUtensorMap* tmB = which ? &p.maps[pb.aux_b2] : tmB0;
+                                const uint32_t dst = sb + part * pb.b_part_rows * 128;
+                                if (CG == 2) tma_load_2d_cg2(dst, tmB, bar, k0, n_base); else tma_load_2d_addr(dst, tmB, bar, k0, n_base);
+                            }
+                        } else {
+                            const int nchunk = (pb.b_part_rows + 63) >> 6;
+                            for (int c = 0; c < nchunk; ++c) {
+                                if (CG == 2) tma_load_2d_cg2(sb + c * (GG_BK * 128), tmB0, bar, n_base + c * 64, k0);
+                                else tma_load_2d_addr(sb + c * (GG_BK * 128), tmB0, bar, n_base + c * 64, k0);
+                            }
+                        }
+                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                     }
-                    if (!pb.b_mn) {
-                        for (int part = 0; part < pb.b_parts; ++part) {
-                            const int which = dual ? (CG == 2 ? (int)rank : part) : 0;
-                            const CUtensorMap* tmB = which ? &p.aux[pb.aux_b2] : &p.tmB[tl.g];
-                            const uint32_t dst = sb + part * pb.b_part_rows * 128;
-                            if (CG == 2) tma_load_2d_cg2(dst, tmB, bar, k0, n_base); else tma_load_2d_addr(dst, tmB, bar, k0, n_base);
-                        }
-                    } else {
-                        const CUtensorMap* tmB = &p.tmB[tl.g];
-                        const int nchunk = (pb.b_part_rows + 63) >> 6;
-                        for (int c = 0; c < nchunk; ++c) {
-                            if (CG == 2) tma_load_2d_cg2(sb + c * (GG_BK * 128), tmB, bar, n_base + c * 64, k0);
-                            else tma_load_2d_addr(sb + c * (GG_BK * 128), tmB, bar, n_base + c * 64, k0);
-                        }
-                    }
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
         }
@@ -276,7 +290,9 @@ __global__ void __launch_bounds__(GG_THREADS, 1) gemm_grouped_kernel(const __gri
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
                 const uint32_t a_step = pb.a_mn ? 128u : 2u;          // +2048 B / +32 B per 16 K elements, in 16 B units
                 const uint32_t b_step = pb.b_mn ? 128u : 2u;
-                for (int kb = 0; kb < pb.num_kb; ++kb) {
+                int total_kb = 0;
+                for (int sg = 0; sg < pb.nseg; ++sg) total_kb += pb.seg[sg].num_kb;
+                for (int kb = 0; kb < total_kb; ++kb) {
                     gg_wait(full_a + 8 * stage, phase, 300 + stage);
                     tc_fence_after_sync();
                     const uint32_t sa = stage_base + stage * Cfg::STAGE_BYTES;
@@ -332,7 +348,7 @@ __global__ void __launch_bounds__(GG_THREADS, 1) gemm_grouped_kernel(const __gri
             const int m0 = tl.mt * (GG_BM * CG) + (int)rank * GG_BM;
             const uint32_t tacc = tmem_base + (uint32_t)acc * 256u + lane_sel;
             const bool has_d = pb.aux_d >= 0;
-            const CUtensorMap* tmC = &p.tmC[tl.g];
+            const CUtensorMap* tmC = &p.maps[pb.c_map];
 
             if (pb.epi == GG_EPI_SWIGLU) {
                 // accumulator columns [0,128) = gate, [128,256) = up, of output columns n0 .. n0+127
@@ -364,8 +380,8 @@ __global__ void __launch_bounds__(GG_THREADS, 1) gemm_grouped_kernel(const __gri
                         __syncwarp();
                         if (lane == 0) { if (CG == 2) mbar_arrive_cluster(tempty_leader + 8 * acc); else mbar_arrive(bars + 2 * STAGES + 2 + acc); }
                     }
-                    if (pb.aux_g >= 0) emit(pg, &p.aux[pb.aux_g], n0 + c * 64, m0);
-                    if (pb.aux_u >= 0) emit(pu, &p.aux[pb.aux_u], n0 + c * 64, m0);
+                    if (pb.aux_g >= 0) emit(pg, &p.maps[pb.aux_g], n0 + c * 64, m0);
+                    if (pb.aux_u >= 0) emit(pu, &p.maps[pb.aux_u], n0 + c * 64, m0);
                     emit(ph, tmC, n0 + c * 64, m0);
                 }
             } else {
@@ -375,7 +391,7 @@ __global__ void __launch_bounds__(GG_THREADS, 1) gemm_grouped_kernel(const __gri
                     tma_store_wait_read1();
                     const uint32_t b = cc & 1u;
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dbar_a + 8 * b), "r"(GG_CHUNK_BYTES) : "memory");
-                    tma_load_2d_addr(chunk_base + b * GG_CHUNK_BYTES, &p.aux[pb.aux_d], dbar_a + 8 * b, n0, m0);
+                    tma_load_2d_addr(chunk_base + b * GG_CHUNK_BYTES, &p.maps[pb.aux_d], dbar_a + 8 * b, n0, m0);
                 }
                 gg_wait(tfull_a + 8 * acc, ((uint32_t)it >> 1) & 1u, 400 + acc);
                 tc_fence_after_sync();
@@ -391,12 +407,17 @@ __global__ void __launch_bounds__(GG_THREADS, 1) gemm_grouped_kernel(const __gri
                         if (lane == 0) { if (CG == 2) mbar_arrive_cluster(tempty_leader + 8 * acc); else mbar_arrive(bars + 2 * STAGES + 2 + acc); }
                     }
                     const int col0 = n0 + c * 64;
+                    if (pb.alpha) {
+                        const float al = __ldg(pb.alpha);
+#pragma unroll
+                        for (int j = 0; j < 64; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * al);
+                    }
                     if (pb.bias) {
                         const uint4* bp = reinterpret_cast<const uint4*>(pb.bias + col0);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             uint4 bv = make_uint4(0, 0, 0, 0);
-                            if (col0 + j * 8 < pb.N) bv = __ldg(bp + j);        // N is a multiple of 8 when a bias is given
+                            if (col0 + j * 8 < pb.N) bv = __ldg(bp + j);        // the bias buffer holds N rounded up to 8 elements
                             r[8 * j + 0] = __float_as_uint(__uint_as_float(r[8 * j + 0]) + bf16_lo(bv.x));
                             r[8 * j + 1] = __float_as_uint(__uint_as_float(r[8 * j + 1]) + bf16_hi(bv.x));
                             r[8 * j + 2] = __float_as_uint(__uint_as_float(r[8 * j + 2]) + bf16_lo(bv.y));
@@ -412,7 +433,7 @@ __global__ void __launch_bounds__(GG_THREADS, 1) gemm_grouped_kernel(const __gri
                     for (int j = 0; j < 32; ++j) pk[j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
                     if (pb.epi == GG_EPI_QGELU) {
                         // pre-activation (rounded to bf16, what nn.Linear returns) is kept for backward when asked for
-                        if (pb.aux_g >= 0) emit(pk, &p.aux[pb.aux_g], col0, m0);
+                        if (pb.aux_g >= 0) emit(pk, &p.maps[pb.aux_g], col0, m0);
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const float x0 = bf16_lo(pk[j]), x1 = bf16_hi(pk[j]);
@@ -447,7 +468,7 @@ __global__ void __launch_bounds__(GG_THREADS, 1) gemm_grouped_kernel(const __gri
                                 tma_store_wait_read1();
                                 const uint32_t nb = b ^ 1u;
                                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dbar_a + 8 * nb), "r"(GG_CHUNK_BYTES) : "memory");
-                                tma_load_2d_addr(chunk_base + nb * GG_CHUNK_BYTES, &p.aux[pb.aux_d], dbar_a + 8 * nb, col0 + 64, m0);
+                                tma_load_2d_addr(chunk_base + nb * GG_CHUNK_BYTES, &p.maps[pb.aux_d], dbar_a + 8 * nb, col0 + 64, m0);
                             }
                         }
                         ++cc;
@@ -583,7 +604,7 @@ extern "C" int lb_gemm_tmap_cache_stats(int64_t* hits, int64_t* misses) {
 }
 
 extern "C" int lb_gemm_grouped(const lb_gemm_problem* probs, int n, void* workspace, int64_t workspace_bytes, void* stream) {
-    LB_REQUIRE(probs && n > 0 && n <= GG_MAXG, LB_EINVAL, "gemm_grouped: 1..%d problems per launch, got %d", GG_MAXG, n);
+    LB_REQUIRE(probs && n > 0 && n <= GG_MAXIN, LB_EINVAL, "gemm_grouped: 1..%d entries per launch, got %d", GG_MAXIN, n);
     int rc = require_sm100();
     if (rc) return rc;
     const int cg = gemm_cg();
@@ -591,114 +612,133 @@ extern "C" int lb_gemm_grouped(const lb_gemm_problem* probs, int n, void* worksp
     P.n_prob = 0;
     P.total_tiles = 0;
     P.counters = (int*)workspace;
-    int n_aux = 0, ctr_off = 0, n_live = 0;
-    int remap[GG_MAXG];
+    int n_maps = 0, ctr_off = 0, n_live = 0;
+    int remap[GG_MAXIN];
+    auto add_map = [&](const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t brow, short* idx) -> int {
+        if (n_maps >= GG_MAXMAPS) return fail(LB_EINVAL, "gemm_grouped: more than %d tensor maps in one launch", GG_MAXMAPS);
+        int r = cached_tmap_2d(&P.maps[n_maps], ptr, rows, cols, ld, brow, 64);
+        if (r) return r;
+        *idx = (short)n_maps++;
+        return LB_OK;
+    };
     for (int i = 0; i < n; ++i) {
         const lb_gemm_problem& q = probs[i];
         remap[i] = -1;
         LB_REQUIRE(q.M >= 0 && q.N >= 0 && q.K >= 0, LB_EINVAL, "gemm_grouped[%d]: bad shape M=%lld N=%lld K=%lld", i,
                    (long long)q.M, (long long)q.N, (long long)q.K);
+        const bool chained = (q.flags & LB_GEMM_ACCUMULATE_PREV) != 0;
         if (q.M == 0 || q.N == 0) continue;             // empty modality segment: nothing to do
-        LB_REQUIRE(q.K > 0, LB_EINVAL, "gemm_grouped[%d]: K = 0", i);
-        LB_REQUIRE(q.A && q.B && q.C, LB_EINVAL, "gemm_grouped[%d]: null pointer", i);
-        LB_REQUIRE(q.lda % 8 == 0 && q.ldb % 8 == 0 && q.ldc % 8 == 0, LB_EALIGN,
-                   "gemm_grouped[%d]: lda=%lld ldb=%lld ldc=%lld must be multiples of 8 elements", i, (long long)q.lda,
-                   (long long)q.ldb, (long long)q.ldc);
+        LB_REQUIRE(q.A && q.B, LB_EINVAL, "gemm_grouped[%d]: null operand", i);
+        LB_REQUIRE(q.lda % 8 == 0 && q.ldb % 8 == 0, LB_EALIGN, "gemm_grouped[%d]: lda=%lld ldb=%lld must be multiples of 8 elements",
+                   i, (long long)q.lda, (long long)q.ldb);
         LB_REQUIRE(q.M < (1ll << 31) && q.N < (1ll << 31) && q.K < (1ll << 31), LB_EINVAL, "gemm_grouped[%d]: dimension too large", i);
-        GGProb& g = P.prob[n_live];
-        memset(&g, 0, sizeof(g));
-        g.M = (int)q.M; g.N = (int)q.N; g.K = (int)q.K;
-        g.a_mn = q.trans_a ? 1 : 0;
-        g.b_mn = q.trans_b ? 1 : 0;
-        g.epi = q.epilogue;
-        g.bias = (const __nv_bfloat16*)q.bias;
-        g.aux_d = g.aux_b2 = g.aux_g = g.aux_u = -1;
-        g.wait_on = -1;
-        LB_REQUIRE(g.epi == GG_EPI_NONE || g.epi == GG_EPI_QGELU || g.epi == GG_EPI_SWIGLU, LB_EINVAL,
-                   "gemm_grouped[%d]: unknown epilogue %d", i, g.epi);
-        LB_REQUIRE(!g.bias || (q.N % 8 == 0 && ((uintptr_t)q.bias & 15) == 0), LB_EALIGN,
-                   "gemm_grouped[%d]: bias needs N %% 8 == 0 and a 16-byte aligned pointer", i);
-        const bool dual = g.epi == GG_EPI_SWIGLU;
-        if (dual) {
-            LB_REQUIRE(q.B2 && !q.trans_b && !q.D && !q.bias, LB_EINVAL,
-                       "gemm_grouped[%d]: SwiGLU needs B2 (up weight), K-major weights, no addend/bias", i);
-            g.tile_n = 256;
-            g.tiles_n = ceil_div(q.N, 128);
-        } else if (q.N <= 48) {
-            g.tile_n = (int)((q.N + 15) / 16 * 16);
-            if (cg == 2 && g.tile_n % 32) g.tile_n += 16;         // each CTA of a pair supplies tile_n / 2 rows of B (>= 8, x16 total)
-            g.tiles_n = 1;
+        if (chained) {
+            // another A_s . B_s product summed into the accumulator of the previous entry's problem
+            LB_REQUIRE(i > 0 && remap[i - 1] >= 0, LB_EINVAL, "gemm_grouped[%d]: ACCUMULATE_PREV needs a preceding non-empty entry", i);
+            GGProb& g = P.prob[remap[i - 1]];
+            LB_REQUIRE(g.M == q.M && g.N == q.N && g.a_mn == (q.trans_a ? 1 : 0) && g.b_mn == (q.trans_b ? 1 : 0) && q.K > 0,
+                       LB_EINVAL, "gemm_grouped[%d]: ACCUMULATE_PREV entries must share M, N and operand layouts", i);
+            LB_REQUIRE(g.nseg < GG_MAXSEG && g.epi != GG_EPI_SWIGLU, LB_EINVAL, "gemm_grouped[%d]: too many accumulation segments", i);
+            remap[i] = remap[i - 1];
         } else {
-            // widest tile that does not waste a whole 64-column chunk on the last tile
-            g.tile_n = q.N >= 256 ? 256 : (int)((q.N + 63) / 64 * 64);
-            g.tiles_n = ceil_div(q.N, g.tile_n);
+            LB_REQUIRE(n_live < GG_MAXG, LB_EINVAL, "gemm_grouped: more than %d output problems", GG_MAXG);
+            LB_REQUIRE(q.K > 0 && q.C, LB_EINVAL, "gemm_grouped[%d]: K = 0 or null C", i);
+            LB_REQUIRE(q.ldc % 8 == 0, LB_EALIGN, "gemm_grouped[%d]: ldc=%lld must be a multiple of 8 elements", i, (long long)q.ldc);
+            LB_REQUIRE(q.N % 8 == 0 || q.ldc >= (q.N + 7) / 8 * 8, LB_EALIGN,
+                       "gemm_grouped[%d]: N=%lld is not a multiple of 8: the row pitch must cover the padded row (TMA stores whole 16-byte units)",
+                       i, (long long)q.N);
+            GGProb& g = P.prob[n_live];
+            memset(&g, 0, sizeof(g));
+            g.M = (int)q.M; g.N = (int)q.N;
+            g.a_mn = q.trans_a ? 1 : 0;
+            g.b_mn = q.trans_b ? 1 : 0;
+            g.epi = q.epilogue;
+            g.bias = (const __nv_bfloat16*)q.bias;
+            g.alpha = (const float*)q.alpha;
+            g.c_map = g.aux_d = g.aux_b2 = g.aux_g = g.aux_u = -1;
+            LB_REQUIRE(g.epi == GG_EPI_NONE || g.epi == GG_EPI_QGELU || g.epi == GG_EPI_SWIGLU, LB_EINVAL,
+                       "gemm_grouped[%d]: unknown epilogue %d", i, g.epi);
+            LB_REQUIRE(!g.bias || ((uintptr_t)q.bias & 15) == 0, LB_EALIGN,
+                       "gemm_grouped[%d]: bias must be 16-byte aligned (and hold N rounded up to 8 elements)", i);
+            const bool dual = g.epi == GG_EPI_SWIGLU;
+            if (dual) {
+                LB_REQUIRE(q.B2 && !q.trans_b && !q.D && !q.bias && !q.alpha, LB_EINVAL,
+                           "gemm_grouped[%d]: SwiGLU needs B2 (up weight), K-major weights, no addend/bias/alpha", i);
+                g.tile_n = 256;
+                g.tiles_n = ceil_div(q.N, 128);
+            } else if (q.N <= 48) {
+                g.tile_n = (int)((q.N + 15) / 16 * 16);
+                if (cg == 2 && g.tile_n % 32) g.tile_n += 16;     // each CTA of a pair supplies tile_n / 2 rows of B
+                g.tiles_n = 1;
+            } else {
+                g.tile_n = q.N >= 256 ? 256 : (int)((q.N + 63) / 64 * 64);
+                g.tiles_n = ceil_div(q.N, g.tile_n);
+            }
+            g.tiles_m = ceil_div(q.M, GG_BM * cg);
+            g.tile_begin = P.total_tiles;
+            P.total_tiles += g.tiles_m * g.tiles_n;
+            if (dual) {
+                g.b_part_rows = 128;
+                g.b_parts = cg == 2 ? 1 : 2;
+                g.b_tx_bytes = g.b_parts * 128 * 128;
+            } else if (!g.b_mn) {
+                g.b_part_rows = g.tile_n / cg;
+                g.b_parts = 1;
+                g.b_tx_bytes = g.b_part_rows * 128;
+            } else {
+                g.b_part_rows = g.tile_n / cg;
+                g.b_parts = 1;
+                g.b_tx_bytes = ((g.b_part_rows + 63) / 64) * (GG_BK * 128);
+            }
+            rc = add_map(q.C, (uint64_t)q.M, (uint64_t)q.N, (uint64_t)q.ldc, GG_BM, &g.c_map);
+            if (rc) return rc;
+            if (q.D) {
+                LB_REQUIRE(q.ldd % 8 == 0, LB_EALIGN, "gemm_grouped[%d]: ldd=%lld must be a multiple of 8", i, (long long)q.ldd);
+                rc = add_map(q.D, (uint64_t)q.M, (uint64_t)q.N, (uint64_t)q.ldd, GG_BM, &g.aux_d);
+                if (rc) return rc;
+            }
+            if (dual) {
+                rc = add_map(q.B2, (uint64_t)q.N, (uint64_t)q.K, (uint64_t)q.ldb, 128, &g.aux_b2);
+                if (rc) return rc;
+            }
+            if (q.G) {
+                LB_REQUIRE(g.epi != GG_EPI_NONE && !q.D, LB_EINVAL, "gemm_grouped[%d]: G output needs an activation epilogue and no addend", i);
+                rc = add_map(q.G, (uint64_t)q.M, (uint64_t)q.N, (uint64_t)q.ldc, GG_BM, &g.aux_g);
+                if (rc) return rc;
+            }
+            if (q.U) {
+                LB_REQUIRE(dual, LB_EINVAL, "gemm_grouped[%d]: U output is SwiGLU only", i);
+                rc = add_map(q.U, (uint64_t)q.M, (uint64_t)q.N, (uint64_t)q.ldc, GG_BM, &g.aux_u);
+                if (rc) return rc;
+            }
+            remap[i] = n_live++;
         }
-        g.tiles_m = ceil_div(q.M, GG_BM * cg);
-        g.num_kb = ceil_div(q.K, GG_BK);
-        g.tile_begin = P.total_tiles;
-        P.total_tiles += g.tiles_m * g.tiles_n;
-        // ---- B loading plan per CTA
-        if (dual) {
-            g.b_part_rows = 128;
-            g.b_parts = cg == 2 ? 1 : 2;
-            g.b_tx_bytes = g.b_parts * 128 * 128;
-        } else if (!g.b_mn) {
-            g.b_part_rows = g.tile_n / cg;
-            g.b_parts = 1;
-            g.b_tx_bytes = g.b_part_rows * 128;
-        } else {
-            g.b_part_rows = g.tile_n / cg;
-            g.b_parts = 1;
-            g.b_tx_bytes = ((g.b_part_rows + 63) / 64) * (GG_BK * 128);
-        }
-        // ---- tensor maps
-        if (!g.a_mn) rc = cached_tmap_2d(&P.tmA[n_live], q.A, (uint64_t)q.M, (uint64_t)q.K, (uint64_t)q.lda, GG_BM, 64);
-        else         rc = cached_tmap_2d(&P.tmA[n_live], q.A, (uint64_t)q.K, (uint64_t)q.M, (uint64_t)q.lda, GG_BK, 64);
+        // ---- this entry's K segment
+        GGProb& g = P.prob[remap[i]];
+        GGSeg& sg = g.seg[g.nseg++];
+        sg.num_kb = ceil_div(q.K, GG_BK);
+        sg.wait_on = -1;
+        sg.wait_all = 0;
+        if (!g.a_mn) rc = add_map(q.A, (uint64_t)q.M, (uint64_t)q.K, (uint64_t)q.lda, GG_BM, &sg.a_map);
+        else         rc = add_map(q.A, (uint64_t)q.K, (uint64_t)q.M, (uint64_t)q.lda, GG_BK, &sg.a_map);
         if (rc) return rc;
-        if (!g.b_mn) rc = cached_tmap_2d(&P.tmB[n_live], q.B, (uint64_t)q.N, (uint64_t)q.K, (uint64_t)q.ldb, (uint32_t)g.b_part_rows, 64);
-        else         rc = cached_tmap_2d(&P.tmB[n_live], q.B, (uint64_t)q.K, (uint64_t)q.N, (uint64_t)q.ldb, GG_BK, 64);
+        if (!g.b_mn) rc = add_map(q.B, (uint64_t)q.N, (uint64_t)q.K, (uint64_t)q.ldb, (uint32_t)g.b_part_rows, &sg.b_map);
+        else         rc = add_map(q.B, (uint64_t)q.K, (uint64_t)q.N, (uint64_t)q.ldb, GG_BK, &sg.b_map);
         if (rc) return rc;
-        rc = cached_tmap_2d(&P.tmC[n_live], q.C, (uint64_t)q.M, (uint64_t)q.N, (uint64_t)q.ldc, GG_BM, 64);
-        if (rc) return rc;
-        auto add_aux = [&](const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t brow, int* idx) -> int {
-            if (n_aux >= GG_MAXAUX) return fail(LB_EINVAL, "gemm_grouped: more than %d auxiliary tensors in one launch", GG_MAXAUX);
-            int r = cached_tmap_2d(&P.aux[n_aux], ptr, rows, cols, ld, brow, 64);
-            if (r) return r;
-            *idx = n_aux++;
-            return LB_OK;
-        };
-        if (q.D) {
-            LB_REQUIRE(q.ldd % 8 == 0, LB_EALIGN, "gemm_grouped[%d]: ldd=%lld must be a multiple of 8", i, (long long)q.ldd);
-            rc = add_aux(q.D, (uint64_t)q.M, (uint64_t)q.N, (uint64_t)q.ldd, GG_BM, &g.aux_d);
-            if (rc) return rc;
-        }
-        if (dual) {
-            rc = add_aux(q.B2, (uint64_t)q.N, (uint64_t)q.K, (uint64_t)q.ldb, 128, &g.aux_b2);
-            if (rc) return rc;
-        }
-        if (q.G) {
-            LB_REQUIRE(g.epi != GG_EPI_NONE && !q.D, LB_EINVAL, "gemm_grouped[%d]: G output needs an activation epilogue and no addend", i);
-            rc = add_aux(q.G, (uint64_t)q.M, (uint64_t)q.N, (uint64_t)q.ldc, GG_BM, &g.aux_g);
-            if (rc) return rc;
-        }
-        if (q.U) {
-            LB_REQUIRE(dual, LB_EINVAL, "gemm_grouped[%d]: U output is SwiGLU only", i);
-            rc = add_aux(q.U, (uint64_t)q.M, (uint64_t)q.N, (uint64_t)q.ldc, GG_BM, &g.aux_u);
-            if (rc) return rc;
-        }
         if (q.wait_on >= 0) {
-            LB_REQUIRE(q.wait_on < i && remap[q.wait_on] >= 0, LB_EINVAL,
+            LB_REQUIRE(q.wait_on < i && remap[q.wait_on] >= 0 && remap[q.wait_on] != remap[i], LB_EINVAL,
                        "gemm_grouped[%d]: wait_on=%d must name an earlier, non-empty problem", i, q.wait_on);
             GGProb& src = P.prob[remap[q.wait_on]];
-            LB_REQUIRE(src.M == g.M && !g.a_mn, LB_EINVAL, "gemm_grouped[%d]: chained problems must share M (row blocks)", i);
             if (!src.signal) {
                 src.signal = 1;
                 src.counter_off = ctr_off;
                 ctr_off += src.tiles_m;
             }
-            g.wait_on = remap[q.wait_on];
+            sg.wait_on = (short)remap[q.wait_on];
+            // A read row block by row block (same rows as the producer's C) can start per row block; anything else
+            // (A transposed: the contraction runs over the producer's rows) waits for the whole producer
+            sg.wait_all = (g.a_mn || src.M != g.M) ? 1 : 0;
         }
-        remap[i] = n_live++;
     }
     if (n_live == 0) return LB_OK;
     P.n_prob = n_live;

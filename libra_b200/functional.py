@@ -1,9 +1,9 @@
 """Differentiable ops (torch.autograd.Function) over the CUDA kernels, in the decoder's *sorted-row* layout:
 rows [0, n_lang) are language tokens, rows [n_lang, N) vision tokens (libra_b200.schedule.build_routing).
 
-Plain dense GEMMs (nn.Linear-shaped products) go through cuBLAS via torch.matmul; everything else on the
-hot path -- norms, SwiGLU, bridge/RoPE prologue, attention forward/backward, cross-entropy, embeddings -- is
-this library's own sm_100a code.  There is no non-CUDA fallback anywhere in this module.
+Everything on the hot path -- every dense product (grouped persistent tcgen05 GEMM, csrc/gemm_grouped.cu), norms,
+SwiGLU, bridge/RoPE prologue, attention forward/backward, cross-entropy, embeddings -- is this library's own sm_100a
+code; nothing here calls cuBLAS.  There is no non-CUDA fallback anywhere in this module.
 """
 from __future__ import annotations
 
@@ -50,8 +50,8 @@ class RoutedRMSNorm(torch.autograd.Function):
         x, w_lang, w_vis, flag, rstd = ctx.saved_tensors
         need_dw = ctx.needs_input_grad[1] or (w_vis is not None and ctx.needs_input_grad[2])
         dx, dwl, dwv = ops.rmsnorm_bwd(dy.contiguous(), x, w_lang, w_vis, flag, rstd, need_dw=need_dw)
-        gl = dwl.to(w_lang.dtype) if (need_dw and ctx.needs_input_grad[1]) else None
-        gv = dwv.to(w_vis.dtype) if (need_dw and w_vis is not None and ctx.needs_input_grad[2]) else None
+        gl = _param_grad(w_lang, dwl.to(w_lang.dtype)) if (need_dw and ctx.needs_input_grad[1]) else None
+        gv = _param_grad(w_vis, dwv.to(w_vis.dtype)) if (need_dw and w_vis is not None and ctx.needs_input_grad[2]) else None
         return dx, gl, gv, None, None
 
 
@@ -78,8 +78,8 @@ class ResidualRMSNorm(torch.autograd.Function):
             return dres, None, None, None, None
         res = None if dres is None else dres.contiguous()
         dx, dwl, dwv = ops.rmsnorm_bwd(dy.contiguous(), x, w_lang, w_vis, flag, rstd, residual_grad=res, need_dw=need_dw)
-        gl = dwl.to(w_lang.dtype) if (need_dw and ctx.needs_input_grad[1]) else None
-        gv = dwv.to(w_vis.dtype) if (need_dw and w_vis is not None and ctx.needs_input_grad[2]) else None
+        gl = _param_grad(w_lang, dwl.to(w_lang.dtype)) if (need_dw and ctx.needs_input_grad[1]) else None
+        gv = _param_grad(w_vis, dwv.to(w_vis.dtype)) if (need_dw and w_vis is not None and ctx.needs_input_grad[2]) else None
         return dx, gl, gv, None, None
 
 
@@ -142,92 +142,116 @@ def bias_quick_gelu(x, bias):
     return BiasQuickGelu.apply(x, bias)
 
 
-# ----------------------------------------------------------------------------- two-stream routing
-# The language GEMMs (M = n_lang rows, N = 4096..11008) and the vision low-rank GEMMs (M = n_vis rows, N = 1024/2752 then
-# 4096/11008) of one routed projection are independent.  The vision ones are small: x_v A^T has only ~40 output tiles of
-# 256x256 for 148 SMs, so on one stream they leave most of the machine idle (and the language GEMM's last wave is partial
-# too).  Issuing the vision path on a side stream lets the hardware co-schedule the two tile sets; fork/join are events.
-USE_SIDE_STREAM = True
-_side = {}
+# ----------------------------------------------------------------------------- dense products
+# Every nn.Linear-shaped product of the decoder runs on this library's grouped persistent tcgen05 kernel
+# (csrc/gemm_grouped.cu, ops.gemm_grouped): one launch per routed projection holds the dense language problem, the
+# chained low-rank vision problems (mid = x_v A^T, y_v = mid B^T, the second waiting on the first per row block) and, in
+# backward, every dgrad / wgrad product of the node.  Input gradients of a fan-out are ONE problem whose K loop runs
+# over the branches (no beta = 1 passes over dx); weight gradients accumulate straight into a parameter's gradient
+# buffer when the owner of that buffer asked for it (see mark_fused_grad).
+G = ops.gp
 
 
-def _side_stream():
-    dev = torch.cuda.current_device()
-    st = _side.get(dev)
-    if st is None:
-        st = _side[dev] = torch.cuda.Stream(device=dev)
-    return st
+def mark_fused_grad(params, fresh: bool = True):
+    """Opt parameters in to fused weight-gradient accumulation: backward then adds dW into the existing `.grad` buffer
+    inside the GEMM epilogue and returns None to autograd for that parameter.  Only the owner of the gradient buffers
+    may do this (libra_b200.dist.FlatGradBuffer, bench.py): no AccumulateGrad hook fires for such a parameter, so it is
+    incompatible with hook-based gradient synchronisation (DDP, FSDP) and with torch.autograd.grad -- which is why it is
+    off unless asked for.  fresh=True: the buffers hold no gradient yet (start of an optimizer step); the first
+    backward OVERWRITES them (beta = 0), which replaces zeroing the buffer."""
+    for p_ in params:
+        p_._lb_fused_grad = True
+        p_._lb_grad_fresh = bool(fresh)
 
 
-class _Fork:
-    """with _Fork() as f:  ...main-stream work...;  with f.side(): ...side-stream work...   (join on exit)"""
-
-    def __init__(self, enabled=True):
-        self.on = bool(enabled and USE_SIDE_STREAM and torch.cuda.is_available())
-
-    def __enter__(self):
-        if self.on:
-            self.main = torch.cuda.current_stream()
-            self.st = _side_stream()
-            self.st.wait_event(self.main.record_event())
-        return self
-
-    def side(self):
-        return torch.cuda.stream(self.st) if self.on else _Null()
-
-    def __exit__(self, *exc):
-        if self.on:
-            self.main.wait_event(self.st.record_event())
-        return False
+def begin_grad_step(params):
+    """Start of an optimizer step for fused-grad parameters: the next weight gradient overwrites instead of adding."""
+    for p_ in params:
+        if getattr(p_, "_lb_fused_grad", False):
+            p_._lb_grad_fresh = True
 
 
-class _Null:
-    def __enter__(self):
-        return self
-
-    def __exit__(self, *exc):
-        return False
+def _fused(P_: torch.Tensor, dtype) -> bool:
+    g = P_.grad
+    return bool(getattr(P_, "_lb_fused_grad", False)) and g is not None and g.dtype == dtype and g.is_contiguous()
 
 
-# ----------------------------------------------------------------------------- routed linear
-# Weight-gradient accumulation fusion: when a parameter already owns a .grad buffer (e.g. a view into the flat
-# data-parallel gradient buffer, libra_b200.dist.FlatGradBuffer), dW is accumulated straight into it by the GEMM
-# (beta = 1) instead of being materialised and added by autograd afterwards (saves ~3 passes over the weight size).
-FUSE_WGRAD_ACCUMULATE = True
+def _param_grad(P_, g):
+    """Hand a materialised parameter gradient to autograd, or (fused-grad parameters) put it into the buffer here."""
+    if g is None or not _fused(P_, P_.dtype):
+        return g
+    if getattr(P_, "_lb_grad_fresh", False):
+        P_._lb_grad_fresh = False
+        P_.grad.copy_(g)
+    else:
+        P_.grad.add_(g.to(P_.grad.dtype))
+    return None
 
 
-def _wgrad(W: torch.Tensor, a_t: torch.Tensor, b: torch.Tensor):
-    """dW = a_t @ b, either returned (autograd accumulates) or accumulated in place into W.grad (returns None)."""
-    g = W.grad
-    if FUSE_WGRAD_ACCUMULATE and g is not None and g.dtype == a_t.dtype and g.is_contiguous():
-        g.addmm_(a_t, b)
+def _no_grad_contribution(P_):
+    """A needed parameter gradient that is identically zero (empty modality segment, unused branch)."""
+    if _fused(P_, P_.dtype):
+        if getattr(P_, "_lb_grad_fresh", False):
+            P_._lb_grad_fresh = False
+            P_.grad.zero_()
         return None
-    return torch.matmul(a_t, b)
+    return torch.zeros_like(P_)
+
+
+def _wgrad_entry(P_, a, b, need, **kw):
+    """(entry, grad to hand to autograd): dP = a^T . b  with a: [rows, out], b: [rows, in].  None, None if not needed."""
+    if not need:
+        return None, None
+    if _fused(P_, a.dtype):
+        g = P_.grad
+        if getattr(P_, "_lb_grad_fresh", False):
+            P_._lb_grad_fresh = False
+            return G(a, b, g, ta=True, tb=True, **kw), None
+        return G(a, b, g, ta=True, tb=True, d=g, **kw), None
+    g = torch.empty_like(P_)
+    return G(a, b, g, ta=True, tb=True, **kw), g
+
+
+class _Launch:
+    """Collects the entries of one grouped launch; entry indices are what `wait_on` refers to."""
+
+    def __init__(self):
+        self.entries = []
+
+    def add(self, e):
+        if e is None:
+            return -1
+        self.entries.append(e)
+        return len(self.entries) - 1
+
+    def run(self):
+        es = self.entries
+        # the kernel takes 32 entries per launch; more (never on the decoder's shapes) would need a split that keeps
+        # wait_on / acc_prev groups together
+        if len(es) > 32:
+            raise RuntimeError(f"grouped GEMM launch with {len(es)} entries")
+        ops.gemm_grouped(es)
 
 
 class RoutedLinear(torch.autograd.Function):
-    """y[:n_lang] = x[:n_lang] W^T ;  y[n_lang:] = (x[n_lang:] A^T) B^T   (+ residual, fused into the GEMM as beta = 1)
+    """y[:n_lang] = x[:n_lang] W^T ;  y[n_lang:] = (x[n_lang:] A^T) B^T   (+ residual, added in the GEMM epilogue)
     (language nn.Linear | vision LibraLinear, modeling_libra.py:192-199, routed by :129-147).
-    The two row ranges are contiguous, so there is no gather/scatter and no boolean indexing."""
+    The two row ranges are contiguous, so there is no gather/scatter and no boolean indexing; one launch."""
 
     @staticmethod
     def forward(ctx, x, n_lang, W, A, B, residual):
         N = x.shape[0]
+        nv = N - n_lang
         y = torch.empty(N, W.shape[0], dtype=x.dtype, device=x.device)
-        mid = torch.empty(N - n_lang, A.shape[0], dtype=x.dtype, device=x.device) if N - n_lang > 0 else None
-        with _Fork(n_lang > 0 and N - n_lang > 0) as f:
-            if N - n_lang > 0:
-                with f.side():
-                    torch.matmul(x[n_lang:], A.t(), out=mid)
-                    if residual is None:
-                        torch.matmul(mid, B.t(), out=y[n_lang:])
-                    else:
-                        torch.addmm(residual[n_lang:], mid, B.t(), out=y[n_lang:])
-            if n_lang > 0:
-                if residual is None:
-                    torch.matmul(x[:n_lang], W.t(), out=y[:n_lang])
-                else:
-                    torch.addmm(residual[:n_lang], x[:n_lang], W.t(), out=y[:n_lang])
+        mid = torch.empty(nv, A.shape[0], dtype=x.dtype, device=x.device) if nv > 0 else None
+        L = _Launch()
+        if nv > 0:
+            i1 = L.add(G(x[n_lang:], A, mid))
+        if n_lang > 0:
+            L.add(G(x[:n_lang], W, y[:n_lang], d=None if residual is None else residual[:n_lang]))
+        if nv > 0:
+            L.add(G(mid, B, y[n_lang:], d=None if residual is None else residual[n_lang:], wait_on=i1))
+        L.run()
         ctx.n_lang = n_lang
         ctx.save_for_backward(x, W, A, B, mid)
         return y
@@ -235,95 +259,178 @@ class RoutedLinear(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, W, A, B, mid = ctx.saved_tensors
-        n_lang = ctx.n_lang
+        n = ctx.n_lang
         N = x.shape[0]
+        nv = N - n
         dy = dy.contiguous()
-        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        ng = ctx.needs_input_grad
+        dx = torch.empty_like(x) if ng[0] else None
         dW = dA = dB = None
-        dmid = torch.empty_like(mid) if mid is not None else None
-        fusable = lambda P_: FUSE_WGRAD_ACCUMULATE and P_.grad is not None and P_.grad.dtype == dy.dtype
-        # non-fused weight gradients are allocated here, on the main stream, before any side-stream work
-        if N - n_lang > 0:
-            if ctx.needs_input_grad[4] and not fusable(B):
-                dB = torch.empty_like(B)
-            if ctx.needs_input_grad[3] and not fusable(A):
-                dA = torch.empty_like(A)
-        with _Fork(n_lang > 0 and N - n_lang > 0) as f:
-            if N - n_lang > 0:
-                with f.side():
-                    dyv = dy[n_lang:]
-                    torch.matmul(dyv, B, out=dmid)
-                    if dx is not None:
-                        torch.matmul(dmid, A, out=dx[n_lang:])
-                    if ctx.needs_input_grad[4]:
-                        if dB is None:
-                            B.grad.addmm_(dyv.t(), mid)
-                        else:
-                            torch.matmul(dyv.t(), mid, out=dB)
-                    if ctx.needs_input_grad[3]:
-                        if dA is None:
-                            A.grad.addmm_(dmid.t(), x[n_lang:])
-                        else:
-                            torch.matmul(dmid.t(), x[n_lang:], out=dA)
-            if n_lang > 0:
-                if dx is not None:
-                    torch.matmul(dy[:n_lang], W, out=dx[:n_lang])
-                if ctx.needs_input_grad[2]:
-                    dW = _wgrad(W, dy[:n_lang].t(), x[:n_lang])
-        if n_lang == 0 and ctx.needs_input_grad[2]:
-            dW = torch.zeros_like(W)
-        if N - n_lang == 0:
-            if ctx.needs_input_grad[3]:
-                dA = torch.zeros_like(A)
-            if ctx.needs_input_grad[4]:
-                dB = torch.zeros_like(B)
-        return dx, None, dW, dA, dB, (dy if ctx.needs_input_grad[5] else None)
+        L = _Launch()
+        if nv > 0:
+            dmid = torch.empty_like(mid)
+            i1 = L.add(G(dy[n:], B, dmid, tb=True))
+        if n > 0:
+            if dx is not None:
+                L.add(G(dy[:n], W, dx[:n], tb=True))
+            e, dW = _wgrad_entry(W, dy[:n], x[:n], ng[2])
+            L.add(e)
+        elif ng[2]:
+            dW = _no_grad_contribution(W)
+        if nv > 0:
+            if dx is not None:
+                L.add(G(dmid, A, dx[n:], tb=True, wait_on=i1))
+            e, dB = _wgrad_entry(B, dy[n:], mid, ng[4])
+            L.add(e)
+            e, dA = _wgrad_entry(A, dmid, x[n:], ng[3], wait_on=i1)
+            L.add(e)
+        else:
+            dA = _no_grad_contribution(A) if ng[3] else None
+            dB = _no_grad_contribution(B) if ng[4] else None
+        L.run()
+        return dx, None, dW, dA, dB, (dy if ng[5] else None)
 
 
 def routed_linear(x, n_lang, W, A, B, residual=None):
     return RoutedLinear.apply(x, n_lang, W, A, B, residual)
 
 
+def _fanout_forward(x, n_lang, kinds, weights, swiglu_pair=None):
+    """The forward launch of a fan-out.  Returns (outs, mids).  swiglu_pair = (i, j, act): branches i (gate) and j (up)
+    additionally produce act = silu(gate) * up for the language rows in the same tile pass (SwiGLU epilogue)."""
+    N = x.shape[0]
+    nv = N - n_lang
+    xl, xv = x[:n_lang], x[n_lang:]
+    outs, mids, specs, wi = [], [], [], 0
+    for kind in kinds:
+        if kind == "lin":
+            W, A, B = weights[wi:wi + 3]
+            wi += 3
+            y = torch.empty(N, W.shape[0], dtype=x.dtype, device=x.device)
+            mid = torch.empty(nv, A.shape[0], dtype=x.dtype, device=x.device) if nv > 0 else None
+            specs.append((kind, y, mid, W, A, B))
+        else:
+            Al, Av = weights[wi:wi + 2]
+            wi += 2
+            y = torch.empty(N, Al.shape[0], dtype=x.dtype, device=x.device)
+            mid = None
+            specs.append((kind, y, None, Al, Av, None))
+        outs.append(y)
+        mids.append(mid)
+    L = _Launch()
+    stage1 = {}
+    if nv > 0:                                   # producers of the chains first: their dependents come last
+        for bi, (kind, y, mid, W0, W1, W2) in enumerate(specs):
+            if kind == "lin":
+                stage1[bi] = L.add(G(xv, W1, mid))
+        for kind, y, mid, W0, W1, W2 in specs:
+            if kind == "down":
+                L.add(G(xv, W1, y[n_lang:]))
+    if n_lang > 0:
+        skip = set()
+        if swiglu_pair is not None:
+            gi, ui, act = swiglu_pair
+            L.add(G(xl, specs[gi][3], act[:n_lang], b2=specs[ui][3], epi=ops.EPI_SWIGLU, g=specs[gi][1][:n_lang],
+                    u=specs[ui][1][:n_lang]))
+            skip = {gi, ui}
+        for bi, (kind, y, mid, W0, W1, W2) in enumerate(specs):
+            if bi not in skip:
+                L.add(G(xl, W0, y[:n_lang]))
+    if nv > 0:
+        for bi, (kind, y, mid, W0, W1, W2) in enumerate(specs):
+            if kind == "lin":
+                L.add(G(mid, W2, y[n_lang:], wait_on=stage1[bi]))
+    L.run()
+    return outs, mids
+
+
+def _fanout_backward(x, n, kinds, weights, mids, douts, ng_x, ng_w):
+    """One launch: dx (one K-segmented problem per modality), every weight gradient, the chains' dmid."""
+    N = x.shape[0]
+    nv = N - n
+    dx = torch.empty_like(x) if ng_x else None
+    grads = []
+    L = _Launch()
+    plan, wi = [], 0
+    for oi, kind in enumerate(kinds):
+        dy = douts[oi]
+        dy = dy.contiguous() if dy is not None else None
+        if kind == "lin":
+            W, A, B = weights[wi:wi + 3]
+            plan.append(dict(kind=kind, dy=dy, W=W, A=A, B=B, mid=mids[oi], need=ng_w[wi:wi + 3], gi=len(grads)))
+            grads += [None, None, None]
+            wi += 3
+        else:
+            Al, Av = weights[wi:wi + 2]
+            plan.append(dict(kind=kind, dy=dy, Al=Al, Av=Av, need=ng_w[wi:wi + 2], gi=len(grads)))
+            grads += [None, None]
+            wi += 2
+    live = [e for e in plan if e["dy"] is not None]
+    # ---- vision: dmid producers first
+    if nv > 0:
+        for e in live:
+            if e["kind"] == "lin":
+                e["dmid"] = torch.empty_like(e["mid"])
+                e["i_dmid"] = L.add(G(e["dy"][n:], e["B"], e["dmid"], tb=True))
+    # ---- language
+    if n > 0:
+        if dx is not None:
+            first = True
+            for e in live:
+                Wl = e["W"] if e["kind"] == "lin" else e["Al"]
+                L.add(G(e["dy"][:n], Wl, dx[:n], tb=True, acc_prev=not first))
+                first = False
+        for e in live:
+            Wl = e["W"] if e["kind"] == "lin" else e["Al"]
+            ent, g = _wgrad_entry(Wl, e["dy"][:n], x[:n], e["need"][0])
+            L.add(ent)
+            grads[e["gi"]] = g
+    # ---- vision dependents
+    if nv > 0:
+        if dx is not None:
+            first = True
+            for e in live:
+                if e["kind"] == "lin":
+                    L.add(G(e["dmid"], e["A"], dx[n:], tb=True, wait_on=e["i_dmid"], acc_prev=not first))
+                else:
+                    L.add(G(e["dy"][n:], e["Av"], dx[n:], tb=True, acc_prev=not first))
+                first = False
+        for e in live:
+            if e["kind"] == "lin":
+                ent, g = _wgrad_entry(e["B"], e["dy"][n:], e["mid"], e["need"][2])
+                L.add(ent)
+                grads[e["gi"] + 2] = g
+                ent, g = _wgrad_entry(e["A"], e["dmid"], x[n:], e["need"][1], wait_on=e["i_dmid"])
+                L.add(ent)
+                grads[e["gi"] + 1] = g
+            else:
+                ent, g = _wgrad_entry(e["Av"], e["dy"][n:], x[n:], e["need"][1])
+                L.add(ent)
+                grads[e["gi"] + 1] = g
+    L.run()
+    if dx is not None and not live:
+        dx.zero_()
+    # parameters of an empty modality segment / of branches without an incoming gradient
+    wi = 0
+    for e in plan:
+        k = 3 if e["kind"] == "lin" else 2
+        for j in range(k):
+            if ng_w[wi + j] and grads[e["gi"] + j] is None:
+                seg_empty = (n == 0) if j == 0 else (nv == 0)
+                if e["dy"] is None or seg_empty:
+                    grads[e["gi"] + j] = _no_grad_contribution(weights[wi + j])
+        wi += k
+    return dx, grads
+
+
 class RoutedFanout(torch.autograd.Function):
-    """Several routed projections of the SAME input in one autograd node (q/k/v + the two bridge down-projections, or
-    gate + up).  Forward is the same GEMMs as RoutedLinear / RoutedDown; backward accumulates every branch's input
-    gradient into one buffer through the GEMM (beta = 1), replacing autograd's N-1 full-size gradient additions.
-    Language GEMMs run on the current stream, vision GEMMs on the side stream (see _Fork).
-    kinds[i] == "lin":  weights (W, A, B) -> y = [x_l W^T ; (x_v A^T) B^T];   "down": weights (A_lang, A_vis)."""
+    """Several routed projections of the SAME input in one autograd node and one launch per direction (q/k/v + the two
+    bridge down-projections).  kinds[i] == "lin": weights (W, A, B) -> y = [x_l W^T ; (x_v A^T) B^T];
+    "down": weights (A_lang, A_vis) -> [x_l A_lang^T ; x_v A_vis^T]."""
 
     @staticmethod
     def forward(ctx, x, n_lang, kinds, *weights):
-        N = x.shape[0]
-        nv = N - n_lang
-        xl, xv = x[:n_lang], x[n_lang:]
-        outs, mids, specs, wi = [], [], [], 0
-        for kind in kinds:                      # allocate everything on the main stream first
-            if kind == "lin":
-                W, A, B = weights[wi:wi + 3]
-                wi += 3
-                y = torch.empty(N, W.shape[0], dtype=x.dtype, device=x.device)
-                mid = torch.empty(nv, A.shape[0], dtype=x.dtype, device=x.device) if nv > 0 else None
-                specs.append((kind, y, mid, W, A, B))
-            else:
-                Al, Av = weights[wi:wi + 2]
-                wi += 2
-                y = torch.empty(N, Al.shape[0], dtype=x.dtype, device=x.device)
-                mid = None
-                specs.append((kind, y, None, Al, Av, None))
-            outs.append(y)
-            mids.append(mid)
-        with _Fork(n_lang > 0 and nv > 0) as f:
-            if nv > 0:
-                with f.side():
-                    for kind, y, mid, W0, W1, W2 in specs:
-                        if kind == "lin":
-                            torch.matmul(xv, W1.t(), out=mid)
-                            torch.matmul(mid, W2.t(), out=y[n_lang:])
-                        else:
-                            torch.matmul(xv, W1.t(), out=y[n_lang:])
-            if n_lang > 0:
-                for kind, y, mid, W0, W1, W2 in specs:
-                    torch.matmul(xl, W0.t(), out=y[:n_lang])
+        outs, mids = _fanout_forward(x, n_lang, kinds, weights)
         ctx.n_lang, ctx.kinds = n_lang, kinds
         ctx.mid_present = [m is not None for m in mids]
         ctx.save_for_backward(x, *weights, *[m for m in mids if m is not None])
@@ -335,106 +442,146 @@ class RoutedFanout(torch.autograd.Function):
         x = saved[0]
         nw = sum(3 if k == "lin" else 2 for k in ctx.kinds)
         weights = saved[1:1 + nw]
-        mids_saved = list(saved[1 + nw:])
-        n, N = ctx.n_lang, x.shape[0]
-        nv = N - n
+        ms = list(saved[1 + nw:])
+        mids = [ms.pop(0) if pres else None for pres in ctx.mid_present]
         ng = ctx.needs_input_grad
-        need_dx = ng[0]
-        dx = torch.empty_like(x) if need_dx else None
-        fusable = lambda P_: FUSE_WGRAD_ACCUMULATE and P_.grad is not None and P_.grad.dtype == x.dtype
-        # plan (and allocate on the main stream) per branch
-        plan, grads, wi = [], [], 0
-        for oi, kind in enumerate(ctx.kinds):
-            dy = douts[oi]
-            dy = dy.contiguous() if dy is not None else None
-            if kind == "lin":
-                W, A, B = weights[wi:wi + 3]
-                mid = mids_saved.pop(0) if ctx.mid_present[oi] else None
-                e = dict(kind=kind, dy=dy, W=W, A=A, B=B, mid=mid, gi=len(grads),
-                         needW=ng[3 + wi], needA=ng[3 + wi + 1], needB=ng[3 + wi + 2])
-                if dy is not None and nv > 0:
-                    e["dmid"] = torch.empty_like(mid)
-                    e["gA"] = torch.empty_like(A) if (e["needA"] and not fusable(A)) else None
-                    e["gB"] = torch.empty_like(B) if (e["needB"] and not fusable(B)) else None
-                grads += [None, None, None]
-                wi += 3
-            else:
-                Al, Av = weights[wi:wi + 2]
-                e = dict(kind=kind, dy=dy, Al=Al, Av=Av, gi=len(grads), needL=ng[3 + wi], needV=ng[3 + wi + 1])
-                if dy is not None and nv > 0:
-                    e["gV"] = torch.empty_like(Av) if (e["needV"] and not fusable(Av)) else None
-                grads += [None, None]
-                wi += 2
-            plan.append(e)
-
-        def acc(dst, a, b, first):
-            if first:
-                torch.matmul(a, b, out=dst)
-            else:
-                dst.addmm_(a, b)
-
-        first_l = first_v = True
-        with _Fork(n > 0 and nv > 0) as f:
-            if nv > 0:
-                with f.side():
-                    for e in plan:
-                        dy = e["dy"]
-                        if dy is None:
-                            continue
-                        if e["kind"] == "lin":
-                            torch.matmul(dy[n:], e["B"], out=e["dmid"])
-                            if need_dx:
-                                acc(dx[n:], e["dmid"], e["A"], first_v)
-                                first_v = False
-                            if e["needB"]:
-                                if e["gB"] is None:
-                                    e["B"].grad.addmm_(dy[n:].t(), e["mid"])
-                                else:
-                                    torch.matmul(dy[n:].t(), e["mid"], out=e["gB"])
-                                    grads[e["gi"] + 2] = e["gB"]
-                            if e["needA"]:
-                                if e["gA"] is None:
-                                    e["A"].grad.addmm_(e["dmid"].t(), x[n:])
-                                else:
-                                    torch.matmul(e["dmid"].t(), x[n:], out=e["gA"])
-                                    grads[e["gi"] + 1] = e["gA"]
-                        else:
-                            if need_dx:
-                                acc(dx[n:], dy[n:], e["Av"], first_v)
-                                first_v = False
-                            if e["needV"]:
-                                if e["gV"] is None:
-                                    e["Av"].grad.addmm_(dy[n:].t(), x[n:])
-                                else:
-                                    torch.matmul(dy[n:].t(), x[n:], out=e["gV"])
-                                    grads[e["gi"] + 1] = e["gV"]
-            if n > 0:
-                for e in plan:
-                    dy = e["dy"]
-                    if dy is None:
-                        continue
-                    if e["kind"] == "lin":
-                        if need_dx:
-                            acc(dx[:n], dy[:n], e["W"], first_l)
-                            first_l = False
-                        if e["needW"]:
-                            grads[e["gi"]] = _wgrad(e["W"], dy[:n].t(), x[:n])
-                    else:
-                        if need_dx:
-                            acc(dx[:n], dy[:n], e["Al"], first_l)
-                            first_l = False
-                        if e["needL"]:
-                            grads[e["gi"]] = _wgrad(e["Al"], dy[:n].t(), x[:n])
-        if need_dx:
-            if first_l and n > 0:
-                dx[:n].zero_()
-            if first_v and nv > 0:
-                dx[n:].zero_()
+        dx, grads = _fanout_backward(x, ctx.n_lang, ctx.kinds, weights, mids, douts, ng[0], ng[3:])
         return (dx, None, None, *grads)
 
 
 def routed_fanout(x, n_lang, kinds, *weights):
     return RoutedFanout.apply(x, n_lang, tuple(kinds), *weights)
+
+
+class RoutedGateUp(torch.autograd.Function):
+    """act = silu(gate(x)) * up(x) with routed gate / up projections (LibraMLP.forward, modeling_libra.py:227-238, the
+    product at :232-233).  Language rows: ONE problem whose B tile interleaves the gate and up weights, the SwiGLU product
+    taken in the epilogue (gate / up pre-activations are stored for backward by the same tile pass); vision rows: the two
+    low-rank chains in the same launch, then lb_swiglu_fwd on those rows."""
+
+    @staticmethod
+    def forward(ctx, x, n_lang, Wg, Ag, Bg, Wu, Au, Bu):
+        N = x.shape[0]
+        act = torch.empty(N, Wg.shape[0], dtype=x.dtype, device=x.device)
+        weights = (Wg, Ag, Bg, Wu, Au, Bu)
+        (g, u), mids = _fanout_forward(x, n_lang, ("lin", "lin"), weights, swiglu_pair=(0, 1, act))
+        if N - n_lang > 0:
+            ops.swiglu_fwd(g[n_lang:], u[n_lang:], out=act[n_lang:])
+        ctx.n_lang = n_lang
+        ctx.mid_present = [m is not None for m in mids]
+        ctx.save_for_backward(x, g, u, *weights, *[m for m in mids if m is not None])
+        return act
+
+    @staticmethod
+    def backward(ctx, dact):
+        saved = ctx.saved_tensors
+        x, g, u = saved[:3]
+        weights = saved[3:9]
+        ms = list(saved[9:])
+        mids = [ms.pop(0) if pres else None for pres in ctx.mid_present]
+        dg, du = ops.swiglu_bwd(dact.contiguous(), g, u)
+        ng = ctx.needs_input_grad
+        dx, grads = _fanout_backward(x, ctx.n_lang, ("lin", "lin"), weights, mids, (dg, du), ng[0], ng[2:])
+        return (dx, None, *grads)
+
+
+def routed_gate_up(x, n_lang, Wg, Ag, Bg, Wu, Au, Bu):
+    return RoutedGateUp.apply(x, n_lang, Wg, Ag, Bg, Wu, Au, Bu)
+
+
+class Linear(torch.autograd.Function):
+    """y = x W^T (+ bias) (+ quick_gelu) (+ residual): nn.Linear on the grouped kernel (CLIP projections, modeling_clip.py:
+    279-282, 371-378; the vision signal projection, modeling_libra.py:640-645).  act: 0 none, 1 quick_gelu."""
+
+    @staticmethod
+    def forward(ctx, x, W, bias, residual, act):
+        x2 = x.reshape(-1, x.shape[-1])
+        Nout = W.shape[0]
+        ld = (Nout + 7) // 8 * 8                   # TMA needs a 16-byte row pitch; odd widths (18, 514) get a padded buffer
+        y = torch.empty(x2.shape[0], ld, dtype=x.dtype, device=x.device)[:, :Nout]
+        if bias is not None and Nout % 8:          # the epilogue reads the bias in 8-element vectors
+            bias = torch.cat([bias, bias.new_zeros(ld - Nout)])
+        pre = None
+        need_pre = act == 1 and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+        if need_pre:
+            pre = torch.empty_like(y)
+        res2 = None if residual is None else residual.reshape(-1, Nout)
+        if act == 1:
+            ops.gemm_grouped([G(x2, W, y, bias=bias, epi=ops.EPI_QGELU, g=pre)])
+            if res2 is not None:
+                y = y + res2
+        else:
+            ops.gemm_grouped([G(x2, W, y, bias=bias, d=res2)])
+        ctx.act = act
+        ctx.xshape = x.shape
+        ctx.save_for_backward(x2, W, pre)
+        return y.view(*x.shape[:-1], Nout) if ld == Nout else y.reshape(*x.shape[:-1], Nout)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, W, pre = ctx.saved_tensors
+        ng = ctx.needs_input_grad
+        dy2 = dy.reshape(-1, W.shape[0]).contiguous()
+        dres = dy if ng[3] else None
+        if ctx.act == 1:
+            dy2 = ops.bias_quick_gelu_bwd(dy2, pre, None)
+        dx = dW = db = None
+        es = []
+        if ng[0]:
+            dx = torch.empty_like(x2)
+            es.append(G(dy2, W, dx, tb=True))
+        if ng[1]:
+            e, dW = _wgrad_entry(W, dy2, x2, True)
+            es.append(e)
+        ops.gemm_grouped(es)
+        if ng[2]:
+            db = dy2.sum(0).to(W.dtype)
+        return (None if dx is None else dx.view(ctx.xshape)), dW, db, dres, None
+
+
+def linear(x, W, bias=None, residual=None, act=0):
+    return Linear.apply(x, W, bias, residual, act)
+
+
+class LinearFanout(torch.autograd.Function):
+    """Several biased nn.Linear projections of the same input in one launch (CLIP q/k/v, modeling_clip.py:295-301);
+    backward sums the input gradients in one K-segmented problem."""
+
+    @staticmethod
+    def forward(ctx, x, *wb):
+        x2 = x.reshape(-1, x.shape[-1])
+        Ws, bs = wb[0::2], wb[1::2]
+        ys = [torch.empty(x2.shape[0], W.shape[0], dtype=x.dtype, device=x.device) for W in Ws]
+        ops.gemm_grouped([G(x2, W, y, bias=b) for W, b, y in zip(Ws, bs, ys)])
+        ctx.xshape = x.shape
+        ctx.nb = len(Ws)
+        ctx.save_for_backward(x2, *Ws)
+        return tuple(y.view(*x.shape[:-1], y.shape[1]) for y in ys)
+
+    @staticmethod
+    def backward(ctx, *dys):
+        x2 = ctx.saved_tensors[0]
+        Ws = ctx.saved_tensors[1:]
+        ng = ctx.needs_input_grad
+        dys = [dy.reshape(-1, W.shape[0]).contiguous() for dy, W in zip(dys, Ws)]
+        es, out = [], [None] * (2 * ctx.nb)
+        dx = None
+        if ng[0]:
+            dx = torch.empty_like(x2)
+            for i, (dy, W) in enumerate(zip(dys, Ws)):
+                es.append(G(dy, W, dx, tb=True, acc_prev=i > 0))
+        for i, (dy, W) in enumerate(zip(dys, Ws)):
+            if ng[1 + 2 * i]:
+                e, out[2 * i] = _wgrad_entry(W, dy, x2, True)
+                es.append(e)
+            if ng[2 + 2 * i]:
+                out[2 * i + 1] = dy.sum(0).to(W.dtype)
+        ops.gemm_grouped(es)
+        return ((None if dx is None else dx.view(ctx.xshape)), *out)
+
+
+def linear_fanout(x, *weights_and_biases):
+    return LinearFanout.apply(x, *weights_and_biases)
 
 
 class RoutedDown(torch.autograd.Function):
@@ -443,12 +590,7 @@ class RoutedDown(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, n_lang, A_lang, A_vis):
-        N = x.shape[0]
-        t = torch.empty(N, A_lang.shape[0], dtype=x.dtype, device=x.device)
-        if n_lang > 0:
-            torch.matmul(x[:n_lang], A_lang.t(), out=t[:n_lang])
-        if N - n_lang > 0:
-            torch.matmul(x[n_lang:], A_vis.t(), out=t[n_lang:])
+        (t,), _ = _fanout_forward(x, n_lang, ("down",), (A_lang, A_vis))
         ctx.n_lang = n_lang
         ctx.save_for_backward(x, A_lang, A_vis)
         return t
@@ -456,14 +598,9 @@ class RoutedDown(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dt):
         x, A_lang, A_vis = ctx.saved_tensors
-        n = ctx.n_lang
-        dt = dt.contiguous()
-        dx = torch.empty_like(x)
-        torch.matmul(dt[:n], A_lang, out=dx[:n])
-        torch.matmul(dt[n:], A_vis, out=dx[n:])
-        dAl = torch.matmul(dt[:n].t(), x[:n]) if ctx.needs_input_grad[2] else None
-        dAv = torch.matmul(dt[n:].t(), x[n:]) if ctx.needs_input_grad[3] else None
-        return dx, None, dAl, dAv
+        ng = ctx.needs_input_grad
+        dx, grads = _fanout_backward(x, ctx.n_lang, ("down",), (A_lang, A_vis), [None], (dt,), ng[0], ng[2:])
+        return (dx, None, *grads)
 
 
 def routed_down(x, n_lang, A_lang, A_vis):
@@ -500,14 +637,15 @@ class BridgeAttention(torch.autograd.Function):
     def forward(ctx, q, k, v, tk, tv, Bk_l, Bk_v, Bv_l, Bv_v, meta: AttnMeta):
         rt, w = meta.routing, meta.work
         n = rt.n_lang
-        # bridged variants k + tk.Bk^T, v + tv.Bv^T per modality segment: rank-r GEMMs with beta = 1 (cuBLAS)
+        # bridged variants k + tk.Bk^T, v + tv.Bv^T per modality segment: four rank-r problems with the addend in the
+        # epilogue, one launch
         kc, vc = torch.empty_like(k), torch.empty_like(v)
+        es = []
         if n > 0:
-            torch.addmm(k[:n], tk[:n], Bk_l.t(), out=kc[:n])
-            torch.addmm(v[:n], tv[:n], Bv_l.t(), out=vc[:n])
+            es += [G(tk[:n], Bk_l, kc[:n], d=k[:n]), G(tv[:n], Bv_l, vc[:n], d=v[:n])]
         if rt.n_vis > 0:
-            torch.addmm(k[n:], tk[n:], Bk_v.t(), out=kc[n:])
-            torch.addmm(v[n:], tv[n:], Bv_v.t(), out=vc[n:])
+            es += [G(tk[n:], Bk_v, kc[n:], d=k[n:]), G(tv[n:], Bv_v, vc[n:], d=v[n:])]
+        ops.gemm_grouped(es)
         scale = 1.0 / math.sqrt(meta.head_dim)
         o = torch.empty_like(q)
         if meta.decode:
@@ -554,18 +692,24 @@ class BridgeAttention(torch.autograd.Function):
         dq, dk, dv, dkb, dvb = ops.attn_prep_bwd(dQ, dKfv, dKfl, dVfv, dVfl, rt.flag_sorted, rt.inv, meta.pos, meta.cos,
                                                  meta.sin, H, D)
         n = rt.n_lang
-        # kb = tk . B^T  =>  d_tk = dkb . B ; dB = dkb^T . tk   (per modality segment)
+        # kb = tk . B^T  =>  d_tk = dkb . B ; dB = dkb^T . tk   (per modality segment), one launch
         d_tk = torch.empty_like(tk)
         d_tv = torch.empty_like(tv)
-        torch.matmul(dkb[:n], Bk_l, out=d_tk[:n])
-        torch.matmul(dkb[n:], Bk_v, out=d_tk[n:])
-        torch.matmul(dvb[:n], Bv_l, out=d_tv[:n])
-        torch.matmul(dvb[n:], Bv_v, out=d_tv[n:])
         g = ctx.needs_input_grad
-        dBk_l = torch.matmul(dkb[:n].t(), tk[:n]) if g[5] else None
-        dBk_v = torch.matmul(dkb[n:].t(), tk[n:]) if g[6] else None
-        dBv_l = torch.matmul(dvb[:n].t(), tv[:n]) if g[7] else None
-        dBv_v = torch.matmul(dvb[n:].t(), tv[n:]) if g[8] else None
+        es, dB = [], [None] * 4
+        segs = ((slice(0, n), Bk_l, Bv_l, 0), (slice(n, None), Bk_v, Bv_v, 1))
+        for sl, Bk, Bv, vi in segs:
+            if (n if vi == 0 else rt.n_vis) == 0:
+                dB[vi] = _no_grad_contribution(Bk) if g[5 + vi] else None
+                dB[2 + vi] = _no_grad_contribution(Bv) if g[7 + vi] else None
+                continue
+            es += [G(dkb[sl], Bk, d_tk[sl], tb=True), G(dvb[sl], Bv, d_tv[sl], tb=True)]
+            e, dB[vi] = _wgrad_entry(Bk, dkb[sl], tk[sl], g[5 + vi])
+            es.append(e)
+            e, dB[2 + vi] = _wgrad_entry(Bv, dvb[sl], tv[sl], g[7 + vi])
+            es.append(e)
+        ops.gemm_grouped([e for e in es if e is not None])
+        dBk_l, dBk_v, dBv_l, dBv_v = dB
         return dq, dk, dv, d_tk, d_tv, dBk_l, dBk_v, dBv_l, dBv_v, None
 
 
@@ -608,6 +752,7 @@ class EmbedLang(torch.autograd.Function):
     def forward(ctx, ids, table):
         ctx.save_for_backward(ids)
         ctx.shape = table.shape
+        ctx.table = table                       # the parameter object (its .grad buffer may take the gradient directly)
         return ops.embed_lang(ids, table)
 
     @staticmethod
@@ -616,7 +761,7 @@ class EmbedLang(torch.autograd.Function):
         dt = torch.zeros(ctx.shape, dtype=torch.float32, device=dy.device)
         dy = dy.contiguous()
         ops.embed_bwd(ids, dy, 0, ctx.shape[1], dt)
-        return None, dt.to(dy.dtype)
+        return None, _param_grad(ctx.table, dt.to(dy.dtype))
 
 
 class EmbedVisionCat(torch.autograd.Function):
@@ -626,6 +771,7 @@ class EmbedVisionCat(torch.autograd.Function):
     def forward(ctx, ids0, ids1, table0, table1, signal, signal_row, signal_cols):
         ctx.save_for_backward(ids0, ids1)
         ctx.shapes = (table0.shape, table1.shape)
+        ctx.tables = (table0, table1)
         return ops.embed_vision_cat(ids0, ids1, table0, table1, signal, signal_row, signal_cols)
 
     @staticmethod
@@ -637,7 +783,7 @@ class EmbedVisionCat(torch.autograd.Function):
         d1 = torch.zeros(s1, dtype=torch.float32, device=dy.device)
         ops.embed_bwd(ids0, dy, 0, s0[1], d0)
         ops.embed_bwd(ids1, dy, s0[1], s1[1], d1)
-        return None, None, d0.to(dy.dtype), d1.to(dy.dtype), None, None, None
+        return None, None, _param_grad(ctx.tables[0], d0.to(dy.dtype)), _param_grad(ctx.tables[1], d1.to(dy.dtype)), None, None, None
 
 
 # ----------------------------------------------------------------------------- heads + loss
@@ -645,25 +791,32 @@ class HeadCrossEntropy(torch.autograd.Function):
     """sum over rows of CE(x W^T, labels) * row_scale, fused: logits are produced by one GEMM, reduced and turned
     into their own gradient in place by lb_cross_entropy_fwd_bwd, and never leave bf16 / HBM more than 3 times
     (modeling_libra.py:1018-1052 restricted to the finite vocabulary block of the row's modality, :1159-1174).
-    Returns (loss_sum fp32 scalar tensor, n_valid fp32 scalar tensor)."""
+    The upstream (scalar) gradient multiplies the two backward products inside their epilogues (alpha)."""
 
     @staticmethod
     def forward(ctx, x, W, labels, grad_scale):
-        logits = torch.matmul(x, W.t())
-        row_loss = ops.cross_entropy_fwd_bwd(logits, labels, W.shape[0], grad_scale)
-        ctx.save_for_backward(x, W, logits)
+        V = W.shape[0]
+        ld = (V + 7) // 8 * 8                       # TMA rows: a 16-byte multiple (the 514-wide vision heads pad to 520)
+        buf = torch.empty(x.shape[0], ld, dtype=x.dtype, device=x.device)
+        logits = buf[:, :V]
+        ops.gemm_grouped([G(x, W, logits)])
+        row_loss = ops.cross_entropy_fwd_bwd(logits, labels, V, grad_scale)
+        ctx.save_for_backward(x, W, buf)
         return row_loss.sum()
 
     @staticmethod
     def backward(ctx, g):
-        x, W, dlogits = ctx.saved_tensors
-        dx = torch.matmul(dlogits, W) if ctx.needs_input_grad[0] else None
-        dW = torch.matmul(dlogits.t(), x) if ctx.needs_input_grad[1] else None      # scaled by g below: not fusable
-        # upstream gradient of the (already pre-scaled) partial loss is a scalar
-        if dx is not None:
-            dx = dx * g.to(dx.dtype)
-        if dW is not None:
-            dW = dW * g.to(dW.dtype)
+        x, W, buf = ctx.saved_tensors
+        dlogits = buf[:, :W.shape[0]]
+        alpha = g.detach().to(torch.float32).reshape(1)
+        es, dx, dW = [], None, None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            es.append(G(dlogits, W, dx, tb=True, alpha=alpha))
+        e, dW = _wgrad_entry(W, dlogits, x, ctx.needs_input_grad[1], alpha=alpha)
+        if e is not None:
+            es.append(e)
+        ops.gemm_grouped(es)
         return dx, dW, None, None
 
 

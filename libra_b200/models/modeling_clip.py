@@ -3,7 +3,8 @@
 CLIPEncoder :600-700, CLIPVisionTransformer/CLIPVisionModel :859-972) with identical state-dict keys.
 
 Kernels: im2col-free TMA-staged patch embedding (lb_patch_embed_fwd), LayerNorm fwd/bwd, non-causal tcgen05 flash
-attention (head_dim 64) fwd/bwd, fused bias+quick_gelu; the dense projections are plain cuBLAS GEMMs.
+attention (head_dim 64) fwd/bwd; the dense projections (+bias, quick_gelu, residual in the epilogue) run on the grouped
+tcgen05 GEMM (csrc/gemm_grouped.cu).
 """
 from __future__ import annotations
 
@@ -58,9 +59,14 @@ class _PatchEmbed(torch.autograd.Function):
         C, _, P, _ = ctx.wshape
         B, _, S, _ = pixels.shape
         G = S // P
-        patches = pixels.reshape(B, 3, G, P, G, P).permute(0, 2, 4, 1, 3, 5).reshape(B * G * G, 3 * P * P)
-        dpatch = dy[:, 1:].reshape(B * G * G, C)
-        dW = torch.matmul(dpatch.t(), patches).view(C, 3, P, P)
+        K = 3 * P * P
+        ld = (K + 7) // 8 * 8                                  # TMA row pitch: a multiple of 16 bytes (588 -> 592)
+        patches = torch.zeros(B * G * G, ld, dtype=pixels.dtype, device=pixels.device)
+        patches[:, :K] = pixels.reshape(B, 3, G, P, G, P).permute(0, 2, 4, 1, 3, 5).reshape(B * G * G, K)
+        dpatch = dy[:, 1:].reshape(B * G * G, C).contiguous()
+        dWp = torch.empty(C, ld, dtype=pixels.dtype, device=pixels.device)
+        ops.gemm_grouped([ops.gp(dpatch, patches[:, :K], dWp[:, :K], ta=True, tb=True)])     # dW = dpatch^T . patches
+        dW = dWp[:, :K].reshape(C, 3, P, P)
         return None, dW, dy[:, 0].sum(0), dy.sum(0)
 
 
@@ -114,15 +120,14 @@ class CLIPEncoderLayer(nn.Module):
         """h: [B*T, C] bf16."""
         a, m = self.self_attn, self.mlp
         x = LF.layernorm(h, self.layer_norm1.weight, self.layer_norm1.bias, self.layer_norm1.eps)
-        q = nn.functional.linear(x, a.q_proj.weight, a.q_proj.bias)
-        k = nn.functional.linear(x, a.k_proj.weight, a.k_proj.bias)
-        v = nn.functional.linear(x, a.v_proj.weight, a.v_proj.bias)
+        # q / k / v (+bias): three problems of one grouped tcgen05 launch
+        q, k, v = LF.linear_fanout(x, a.q_proj.weight, a.q_proj.bias, a.k_proj.weight, a.k_proj.bias, a.v_proj.weight, a.v_proj.bias)
         # the reference multiplies q by head_dim**-0.5 before q.k^T (:299); here the factor rides in the softmax scale
         o = LF.plain_attention(q, k, v, work, B, T, a.num_heads, a.head_dim, a.scale)
-        h = h + nn.functional.linear(o, a.out_proj.weight, a.out_proj.bias)
+        h = LF.linear(o, a.out_proj.weight, a.out_proj.bias, residual=h)                # bias + residual in the epilogue
         x = LF.layernorm(h, self.layer_norm2.weight, self.layer_norm2.bias, self.layer_norm2.eps)
-        f = LF.bias_quick_gelu(torch.matmul(x, m.fc1.weight.t()), m.fc1.bias)
-        return h + nn.functional.linear(f, m.fc2.weight, m.fc2.bias)
+        f = LF.linear(x, m.fc1.weight, m.fc1.bias, act=1)                              # bias + quick_gelu in the epilogue
+        return LF.linear(f, m.fc2.weight, m.fc2.bias, residual=h)
 
 
 class CLIPEncoder(nn.Module):

@@ -77,7 +77,7 @@ class LibraLinear(nn.Module):
             nn.init.kaiming_uniform_(self.weight_B, a=math.sqrt(5))
 
     def forward(self, x):
-        return nn.functional.linear(nn.functional.linear(x, self.weight_A), self.weight_B)
+        return LF.linear(LF.linear(x, self.weight_A), self.weight_B)
 
 
 class _RotaryBuffers(nn.Module):
@@ -157,10 +157,9 @@ class LibraDecoderLayer(nn.Module):
         # residual add fused into the output-projection GEMMs (beta = 1)
         h = LF.routed_linear(o, nl, a.o_proj.weight, a.vision_o_proj.weight_A, a.vision_o_proj.weight_B, residual=hr)
         hr, n2 = LF.residual_rmsnorm(h, self.post_attention_layernorm.weight, self.vision_post_attention_layernorm.weight, flag, eps)
-        g, u = LF.routed_fanout(n2, nl, ("lin", "lin"),
-                                m.gate_proj.weight, m.vision_gate_proj.weight_A, m.vision_gate_proj.weight_B,
+        # gate | up with the SwiGLU product taken in the GEMM epilogue (language rows) / right behind the chains (vision rows)
+        act = LF.routed_gate_up(n2, nl, m.gate_proj.weight, m.vision_gate_proj.weight_A, m.vision_gate_proj.weight_B,
                                 m.up_proj.weight, m.vision_up_proj.weight_A, m.vision_up_proj.weight_B)
-        act = LF.swiglu(g, u)
         return LF.routed_linear(act, nl, m.down_proj.weight, m.vision_down_proj.weight_A, m.vision_down_proj.weight_B, residual=hr)
 
 
@@ -341,7 +340,7 @@ class LibraModel(LibraPreTrainedModel):
         cat = LF.EmbedVisionCat.apply(ids0, ids1, self.vision_embed_tokens[0].weight, self.vision_embed_tokens[1].weight, sig,
                                       rt.perm[nl:].contiguous(), self.contiguous_signal_size)
         cat = LF.rmsnorm(cat, self.vision_signal_norm.weight, None, None, self.vision_signal_norm.variance_epsilon)
-        h_vis = nn.functional.linear(cat, self.vision_contiguous_signal_processor.weight)
+        h_vis = LF.linear(cat, self.vision_contiguous_signal_processor.weight)
         return torch.cat([h_lang, h_vis], dim=0)
 
     def forward_sorted(self, input_ids, meta: LF.AttnMeta, contiguous_signal=None, collect_hidden=False):
@@ -440,11 +439,11 @@ class LibraForCausalLM(LibraPreTrainedModel):
         V, Vv, Q = self.config.vocab_size, self.config.vision_vocab_size, self.vision_codebook_num
         out = torch.full((Q, rt.n_tokens, V + Vv), float("-inf"), dtype=hn.dtype, device=hn.device)
         perm = rt.perm.long()
-        ll = nn.functional.linear(hn[:nl], self.lm_head.weight)
+        ll = LF.linear(hn[:nl], self.lm_head.weight)
         for c in range(Q):
             out[c, perm[:nl], :V] = ll
             if rt.n_vis:
-                out[c, perm[nl:], V:] = nn.functional.linear(hn[nl:], self.vision_lm_head.heads[c].weight)
+                out[c, perm[nl:], V:] = LF.linear(hn[nl:], self.vision_lm_head.heads[c].weight)
         return out.view(Q, meta.batch, meta.seqlen, V + Vv)
 
     def forward(
@@ -653,8 +652,6 @@ class LibraForCausalLM(LibraPreTrainedModel):
             pos.add_(1)
             step.add_(1)
 
-        side_was = LF.USE_SIDE_STREAM
-        LF.USE_SIDE_STREAM = False                                   # B rows: nothing to co-schedule, and no cross-stream events in the graph
         try:
             cur = torch.cuda.current_stream()
             s = torch.cuda.Stream()
@@ -680,7 +677,6 @@ class LibraForCausalLM(LibraPreTrainedModel):
                 e1.record()
                 self.last_graph_decode = (n_run - n_first, e0, e1)      # (replays, events around them): for benchmarks
         finally:
-            LF.USE_SIDE_STREAM = side_was
             meta.kv_cache = None
         return outbuf[:, :, :n_run]
 

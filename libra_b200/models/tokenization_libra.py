@@ -16,6 +16,7 @@ import torch
 from torch import nn
 
 from .. import _lib, ops
+from .. import functional as LF
 from .modeling_clip import CLIPVisionConfig, CLIPVisionModel
 
 BF16 = torch.bfloat16
@@ -74,9 +75,9 @@ class VisionTokenizer(nn.Module):
         feat = torch.cat([full(i) for i in self.select_layer], dim=-1)[:, 1:].contiguous()      # [B, 576, C*len]
         B, N, Cin = feat.shape
         w = self.quant_conv.weight.view(self.quant_conv.out_channels, Cin)
-        h = nn.functional.linear(feat.view(B * N, Cin), w, self.quant_conv.bias)              # 1x1 conv == per-token linear
+        h = LF.linear(feat.view(B * N, Cin), w, self.quant_conv.bias).contiguous()            # 1x1 conv == per-token linear
         if self.quantize.has_projections:
-            h = self.quantize.project_in(h)
+            h = LF.linear(h, self.quantize.project_in.weight, self.quantize.project_in.bias)
         ids = ops.lfq_pack(h.contiguous(), B, N, self.num_codebook, self.quantize.codebook_dim, self.offset, self.boi_token_id,
                            self.eoi_token_id)
         return {"input_ids": ids, "image_size": [self.grid, self.grid],

@@ -234,7 +234,7 @@ class GemmProblem(ctypes.Structure):
                 ("M", ctypes.c_int64), ("N", ctypes.c_int64), ("K", ctypes.c_int64),
                 ("lda", ctypes.c_int64), ("ldb", ctypes.c_int64), ("ldc", ctypes.c_int64), ("ldd", ctypes.c_int64),
                 ("trans_a", ctypes.c_int32), ("trans_b", ctypes.c_int32), ("epilogue", ctypes.c_int32),
-                ("wait_on", ctypes.c_int32)]
+                ("wait_on", ctypes.c_int32), ("alpha", ctypes.c_void_p), ("flags", ctypes.c_int64)]
 
 
 EPI_NONE, EPI_QGELU, EPI_SWIGLU = 0, 1, 2
@@ -247,9 +247,12 @@ def _ld(t: torch.Tensor, name: str) -> int:
     return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
 
 
-def gp(a, b, c, *, ta=False, tb=False, d=None, bias=None, epi=EPI_NONE, b2=None, g=None, u=None, wait_on=-1):
-    """One problem of a grouped launch:  c[M,N] = epi(op(a) . op(b) [+ bias]) [+ d].
-    a: [M,K] (ta: [K,M]);  b: [N,K], the nn.Linear weight layout (tb: [K,N]);  c, d, g, u: [M,N] row-major views."""
+def gp(a, b, c, *, ta=False, tb=False, d=None, bias=None, epi=EPI_NONE, b2=None, g=None, u=None, wait_on=-1, alpha=None,
+       acc_prev=False):
+    """One entry of a grouped launch:  c[M,N] = epi(alpha * op(a) . op(b) [+ bias]) [+ d].
+    a: [M,K] (ta: [K,M]);  b: [N,K], the nn.Linear weight layout (tb: [K,N]);  c, d, g, u: [M,N] row-major views.
+    acc_prev: this product is summed into the previous entry's accumulator instead (c = that entry's c).
+    wait_on: index (in the launch's list) of the entry that produces `a`."""
     M = a.shape[1] if ta else a.shape[0]
     K = a.shape[0] if ta else a.shape[1]
     N = b.shape[1] if tb else b.shape[0]
@@ -266,6 +269,11 @@ def gp(a, b, c, *, ta=False, tb=False, d=None, bias=None, epi=EPI_NONE, b2=None,
         q.D, q.ldd = d.data_ptr(), _ld(d, "d")
     if bias is not None:
         q.bias = bias.data_ptr()
+    if alpha is not None:
+        if alpha.dtype != torch.float32 or alpha.numel() != 1 or not alpha.is_cuda:
+            raise ValueError("gemm alpha: a CUDA fp32 scalar tensor")
+        q.alpha = alpha.data_ptr()
+    q.flags = 1 if acc_prev else 0
     if b2 is not None:
         if tuple(b2.shape) != tuple(b.shape) or _ld(b2, "b2") != q.ldb:
             raise ValueError("gemm b2 must match b")

@@ -138,6 +138,26 @@ def correctness(quick):
                         (midr.float() @ Bw.float().t()).to(BF16).float() + res[nl:].float()])
         ok &= check(f"grouped chain rep{rep} mid", mid, midr)
         ok &= check(f"grouped chain rep{rep} y", y, yr)
+    # K segments summed in the accumulator (fan-out dgrad), transposed dependent (wgrad of a chain), alpha
+    M, H2 = 1100, 768
+    dq, dk, dt = rnd(M, 512), rnd(M, 384), rnd(M, 8)
+    Wq, Wk, Al = rnd(512, H2, scale=0.05), rnd(384, H2, scale=0.05), rnd(8, H2, scale=0.05)
+    dx = torch.full((M, H2), float("nan"), device=dev, dtype=BF16)
+    ops.gemm_grouped([ops.gp(dq, Wq, dx, tb=True), ops.gp(dk, Wk, dx, tb=True, acc_prev=True), ops.gp(dt, Al, dx, tb=True, acc_prev=True)])
+    ok &= check("3 K-segments", dx, dq.float() @ Wq.float() + dk.float() @ Wk.float() + dt.float() @ Al.float())
+    dy, Bw2, xv = rnd(M, H2), rnd(H2, 256, scale=0.05), rnd(M, 640)
+    dmid = torch.full((M, 256), float("nan"), device=dev, dtype=BF16)
+    dA = torch.full((256, 640), float("nan"), device=dev, dtype=BF16)
+    dxv = torch.full((M, 640), float("nan"), device=dev, dtype=BF16)
+    A2 = rnd(256, 640, scale=0.05)
+    alpha = torch.tensor([0.5], device=dev, dtype=torch.float32)
+    for rep in range(2):
+        ops.gemm_grouped([ops.gp(dy, Bw2, dmid, tb=True),
+                          ops.gp(dmid, xv, dA, ta=True, tb=True, wait_on=0, alpha=alpha),
+                          ops.gp(dmid, A2, dxv, tb=True, wait_on=0)])
+        dmr = (dy.float() @ Bw2.float()).to(BF16).float()
+        ok &= check(f"transposed dependent (whole-problem wait) rep{rep}", dA, 0.5 * (dmr.t() @ xv.float()))
+        ok &= check(f"row-block dependent rep{rep}", dxv, dmr @ A2.float())
     # empty segments are skipped
     ops.gemm_grouped([ops.gp(x[:0], W, y[:0]), ops.gp(x[:64], W, y[:64])])
     ok &= check("empty segment", y[:64], x[:64].float() @ W.float().t())
