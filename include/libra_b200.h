@@ -301,6 +301,16 @@ int lb_cross_entropy_fwd_bwd(void* logits, int64_t ld, const int64_t* labels, fl
 int lb_adamw_bf16(void* param, const void* grad, void* exp_avg, void* exp_avg_sq, int64_t n, float lr, float beta1, float beta2,
                   float eps, float weight_decay, int step, void* stream);
 
+/* same with the gradient multiplied by *grad_scale (device fp32 scalar, may be NULL): gradient clipping folded into
+ * the optimizer pass (trainer.py / libra_pretrain.yaml:116 max_grad_norm 1.0) */
+int lb_adamw_bf16_scaled(void* param, const void* grad, void* exp_avg, void* exp_avg_sq, int64_t n, float lr, float beta1,
+                         float beta2, float eps, float weight_decay, int step, const float* grad_scale, void* stream);
+/* global L2 norm of a flat bf16 gradient buffer and the clip factor, on the device, deterministic (two stages, no atomics):
+ * out2[0] = ||g||, out2[1] = min(1, max_norm / (||g|| + 1e-6)) -- torch.nn.utils.clip_grad_norm_ semantics.
+ * workspace: >= 64 floats (one partial per CTA; more floats = more CTAs, 2368 saturates a B200). */
+int lb_grad_clip_scale(const void* grad, int64_t n, float max_norm, float* workspace, int workspace_floats, float* out2,
+                       void* stream);
+
 /* ---- diagnostics: single-tile tcgen05 probes (tests/test_umma_probe.py) ---- */
 int lb_probe_umma(int mode, const void* A, const void* B, float* D, int K, void* stream);
 

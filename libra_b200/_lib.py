@@ -61,6 +61,8 @@ SIGNATURES = {
     "lb_cross_entropy_fwd_bwd": (I, [P, L, P, P, L, I, F, P]),
     "lb_probe_umma": (I, [I, P, P, P, I, P]),
     "lb_adamw_bf16": (I, [P, P, P, P, L, F, F, F, F, F, I, P]),
+    "lb_adamw_bf16_scaled": (I, [P, P, P, P, L, F, F, F, F, F, I, P, P]),
+    "lb_grad_clip_scale": (I, [P, L, F, P, I, P, P]),
 }
 
 _lib = None
@@ -107,7 +109,7 @@ KERNELS_PER_CALL = {
     "lb_swiglu_bwd": 1, "lb_bias_quick_gelu_fwd": 1, "lb_bias_quick_gelu_bwd": 1, "lb_gather_rows": 1,
     "lb_embed_lang_fwd": 1, "lb_embed_vision_cat_fwd": 3, "lb_embed_bwd": 1, "lb_lfq_pack": 1, "lb_lfq_unpack": 1,
     "lb_attn_prep_fwd": 1, "lb_attn_prep_bwd": 1, "lb_attn_fwd": 1, "lb_attn_fwd_stream": 1, "lb_attn_bwd_prepare": 1, "lb_attn_bwd_dq": 1,
-    "lb_attn_bwd_dkv": 1, "lb_attn_decode": 2, "lb_gemm_bf16": 1, "lb_gemm_grouped": 1, "lb_patch_embed_fwd": 1, "lb_patch_embed_pack_weight": 1, "lb_cross_entropy_fwd_bwd": 1, "lb_probe_umma": 1, "lb_adamw_bf16": 1,
+    "lb_attn_bwd_dkv": 1, "lb_attn_decode": 2, "lb_gemm_bf16": 1, "lb_gemm_grouped": 1, "lb_patch_embed_fwd": 1, "lb_patch_embed_pack_weight": 1, "lb_cross_entropy_fwd_bwd": 1, "lb_probe_umma": 1, "lb_adamw_bf16": 1, "lb_adamw_bf16_scaled": 1, "lb_grad_clip_scale": 2,
 }
 launch_counts: dict = {}
 

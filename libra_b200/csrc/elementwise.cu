@@ -464,6 +464,75 @@ __global__ void __launch_bounds__(256) adamw_bf16_kernel(__nv_bfloat16* __restri
     }
 }
 
+// same, the gradient multiplied by a device-resident scalar first (gradient clipping without a pass over the buffer)
+__global__ void __launch_bounds__(256) adamw_bf16_scaled_kernel(__nv_bfloat16* __restrict__ p, const __nv_bfloat16* __restrict__ g,
+                                                                __nv_bfloat16* __restrict__ m, __nv_bfloat16* __restrict__ v,
+                                                                int64_t nvec, float lr, float beta1, float beta2, float eps,
+                                                                float weight_decay, float bc1, float bc2_sqrt,
+                                                                const float* __restrict__ grad_scale) {
+    const float gs = grad_scale ? __ldg(grad_scale) : 1.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        float fp[8], fg[8], fm[8], fv[8];
+        unpack8(reinterpret_cast<const uint4*>(p)[i], fp);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(g) + i), fg);
+        unpack8(reinterpret_cast<const uint4*>(m)[i], fm);
+        unpack8(reinterpret_cast<const uint4*>(v)[i], fv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float gj = fg[j] * gs;
+            fp[j] *= (1.f - lr * weight_decay);
+            fm[j] = beta1 * fm[j] + (1.f - beta1) * gj;
+            fv[j] = beta2 * fv[j] + (1.f - beta2) * gj * gj;
+            const float denom = sqrtf(fv[j]) / bc2_sqrt + eps;
+            fp[j] -= (lr / bc1) * (fm[j] / denom);
+        }
+        reinterpret_cast<uint4*>(p)[i] = pack8(fp);
+        reinterpret_cast<uint4*>(m)[i] = pack8(fm);
+        reinterpret_cast<uint4*>(v)[i] = pack8(fv);
+    }
+}
+
+// ------------------------------------------------ global gradient norm -> clip factor, all on the device
+// two deterministic stages (no atomics): per-CTA partial sums of squares, then one CTA folds them and writes
+// out[0] = ||g||_2, out[1] = min(1, max_norm / (||g|| + 1e-6))   (torch.nn.utils.clip_grad_norm_ semantics)
+__global__ void __launch_bounds__(256) sumsq_partial_kernel(const __nv_bfloat16* __restrict__ x, int64_t nvec,
+                                                            float* __restrict__ partial) {
+    __shared__ float red[8];
+    float s = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x) + i), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s = fmaf(f[j], f[j], s);
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i];
+        partial[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(256) clip_scale_kernel(const float* __restrict__ partial, int n, float max_norm,
+                                                         float* __restrict__ out) {
+    __shared__ double red[8];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += (double)partial[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        const float norm = (float)sqrt(t);
+        out[0] = norm;
+        out[1] = max_norm > 0.f ? fminf(1.f, max_norm / (norm + 1e-6f)) : 1.f;
+    }
+}
+
 static int ew_grid(int64_t work_items, int threads) {
     int64_t g = (work_items + threads - 1) / threads;
     const int64_t cap = (int64_t)sm_count() * 16;
@@ -682,6 +751,32 @@ int lb_adamw_bf16(void* param, const void* grad, void* exp_avg, void* exp_avg_sq
                                                                           nvec, lr, beta1, beta2, eps, weight_decay, bc1,
                                                                           bc2_sqrt);
     return check_launch("adamw_bf16");
+}
+
+int lb_adamw_bf16_scaled(void* param, const void* grad, void* exp_avg, void* exp_avg_sq, int64_t n, float lr, float beta1,
+                         float beta2, float eps, float weight_decay, int step, const float* grad_scale, void* stream) {
+    LB_REQUIRE(n >= 0 && n % 8 == 0 && step >= 1, LB_EINVAL, "adamw: n=%lld must be a multiple of 8, step >= 1", (long long)n);
+    LB_REQUIRE(AL16(param) && AL16(grad) && AL16(exp_avg) && AL16(exp_avg_sq), LB_EALIGN, "adamw: buffers must be 16-byte aligned");
+    if (n == 0) return LB_OK;
+    const float bc1 = 1.f - powf(beta1, (float)step);
+    const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+    const int64_t nvec = n / 8;
+    adamw_bf16_scaled_kernel<<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)stream>>>(
+        (__nv_bfloat16*)param, (const __nv_bfloat16*)grad, (__nv_bfloat16*)exp_avg, (__nv_bfloat16*)exp_avg_sq, nvec, lr, beta1,
+        beta2, eps, weight_decay, bc1, bc2_sqrt, grad_scale);
+    return check_launch("adamw_bf16_scaled");
+}
+
+int lb_grad_clip_scale(const void* grad, int64_t n, float max_norm, float* workspace, int workspace_floats, float* out2,
+                       void* stream) {
+    LB_REQUIRE(n >= 0 && n % 8 == 0 && grad && workspace && out2 && workspace_floats >= 64, LB_EINVAL,
+               "grad_clip_scale: n=%lld must be a multiple of 8, workspace >= 64 floats", (long long)n);
+    LB_REQUIRE(AL16(grad), LB_EALIGN, "grad_clip_scale: gradient buffer must be 16-byte aligned");
+    int grid = ew_grid(n / 8, 256);
+    if (grid > workspace_floats) grid = workspace_floats;
+    sumsq_partial_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)grad, n / 8, workspace);
+    clip_scale_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(workspace, grid, max_norm, out2);
+    return check_launch("grad_clip_scale");
 }
 
 int lb_cross_entropy_fwd_bwd(void* logits, int64_t ld, const int64_t* labels, float* row_loss, int64_t rows, int vocab,

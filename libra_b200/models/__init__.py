@@ -4,5 +4,8 @@ from .configuration_libra import LibraConfig
 from .modeling_libra import (LibraCausalLMOutputWithPast, LibraDecoderLayer, LibraForCausalLM, LibraLinear, LibraModel, LibraTrainWrapper,
                              LibraPreTrainedModel)
 
-__all__ = ["LibraConfig", "LibraForCausalLM", "LibraTrainWrapper", "LibraModel", "LibraDecoderLayer", "LibraLinear", "LibraPreTrainedModel",
+from .tokenization_libra import LibraTokenizer, SimpleTextTokenizer, VisionTokenizer
+from .modeling_clip import CLIPVisionConfig, CLIPVisionModel
+
+__all__ = ["LibraTokenizer", "SimpleTextTokenizer", "VisionTokenizer", "CLIPVisionConfig", "CLIPVisionModel", "LibraConfig", "LibraForCausalLM", "LibraTrainWrapper", "LibraModel", "LibraDecoderLayer", "LibraLinear", "LibraPreTrainedModel",
            "LibraCausalLMOutputWithPast"]

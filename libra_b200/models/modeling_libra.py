@@ -25,6 +25,7 @@ from transformers.modeling_utils import PreTrainedModel
 from .. import _lib
 from .. import functional as LF
 from .. import schedule
+from ..registry import registry
 from .configuration_libra import LibraConfig
 
 BF16 = torch.bfloat16
@@ -681,20 +682,49 @@ class LibraForCausalLM(LibraPreTrainedModel):
         return outbuf[:, :, :n_run]
 
 
+@registry.register_model("libra_train_wrapper")
 class LibraTrainWrapper(LibraPreTrainedModel):
-    """Host mirror of LibraTrainWrapper (modeling_libra.py:1292-1437): tokenizer -> labels -> LibraForCausalLM.
+    """LibraTrainWrapper (modeling_libra.py:1292-1437): tokenizer -> labels -> LibraForCausalLM, registered as
+    "libra_train_wrapper" so `registry.get_model_class(arch).from_config(model_cfg)` (train.py:28-30) resolves to it.
 
-    The reference builds its LibraTokenizer from checkpoint files (sentencepiece model + vision_tokenizer_config.yaml)
-    that are not part of the repository; text tokenisation is outside the hot path.  This mirror
-    therefore takes the tokenizer as an object: anything callable as `tokenizer(samples, return_tensors="pt",
-    padding="longest", max_length=..., truncation=True)` that returns `input_ids`, `attention_mask`, `vision_indices`,
-    `coninous_signal` -- the reference's own `LibraTokenizer` qualifies -- and exposes `.image_tokenizer.boi_token_id`,
-    `.text_tokenizer.{bos_token_id, pad_token_id, eos_token_id, model_max_length}`."""
+    Two ways to build it:
+      * the reference's: `LibraTrainWrapper(model_cfg)` with `model_cfg.pretrained` naming a checkpoint directory
+        (config.json + weights + text tokenizer files + vision_tokenizer_config.yaml) and the optional `custom_kwargs`,
+        `tokenizer_kwargs`, `model_kwargs`, `pretrained_weight` entries (:1294-1372); model_cfg may be an OmegaConf node, a
+        dict or any object with `.get`;
+      * injected: `LibraTrainWrapper(LibraConfig, module=..., tokenizer=..., model_kwargs=...)` -- the checkpoints are not
+        part of the repository, synthetic runs and tests build the parts themselves.  The tokenizer is anything callable as
+        `tokenizer(samples, return_tensors="pt", padding="longest", max_length=..., truncation=True)` returning `input_ids`,
+        `attention_mask`, `vision_indices`, `coninous_signal` (libra_b200's LibraTokenizer or the reference's own)."""
 
-    def __init__(self, config: LibraConfig, module: Optional["LibraForCausalLM"] = None, tokenizer=None, model_kwargs=None):
-        super().__init__(config)
-        self.module = module if module is not None else LibraForCausalLM(config)
-        self.tokenizer = tokenizer
+    def __init__(self, config, module: Optional["LibraForCausalLM"] = None, tokenizer=None, model_kwargs=None):
+        from transformers import PretrainedConfig
+        get = (lambda k, d=None: config.get(k, d)) if (hasattr(config, "get") and not isinstance(config, PretrainedConfig)) else None
+        if get is not None and get("pretrained") is not None:
+            import json
+            from pathlib import Path
+            from .tokenization_libra import LibraTokenizer
+            pretrained = str(get("pretrained"))
+            super().__init__(LibraConfig(**json.load(open(Path(pretrained, "config.json"), "r"))))
+            self.module = LibraForCausalLM.from_pretrained(pretrained, **dict(get("custom_kwargs", {}) or {}))
+            self.tokenizer = LibraTokenizer(pretrained, **dict(get("tokenizer_kwargs", {}) or {}))
+            tokenizer = self.tokenizer
+            model_kwargs = dict(get("model_kwargs", {}) or {})
+            weight = get("pretrained_weight", None)
+            if weight is not None:                                             # :1312-1340
+                sd = torch.load(weight, map_location="cpu")
+                for prefix in ("model.model.", "module.model."):
+                    if any(k.startswith(prefix) for k in sd):
+                        cut = len(prefix) - len("model.")
+                        sd = {k[cut:]: v for k, v in sd.items() if k.startswith(prefix[:cut])}
+                        break
+                missing, unexpected = self.module.load_state_dict(sd, strict=False)
+                print("missing keys: ", missing)
+                print("unexpected keys: ", unexpected)
+        else:
+            super().__init__(config)
+            self.module = module if module is not None else LibraForCausalLM(config)
+            self.tokenizer = tokenizer
         if tokenizer is not None:
             self.change_pad_token_to_eos(pad_token_id=tokenizer.text_tokenizer.pad_token_id,
                                          eos_token_id=tokenizer.text_tokenizer.eos_token_id)
@@ -709,6 +739,25 @@ class LibraTrainWrapper(LibraPreTrainedModel):
                 for key, p in self.module.named_parameters():
                     if pat in key:
                         p.requires_grad = False
+        if model_kwargs.get("debug", False):                                 # :1366-1369
+            for key, p in self.module.named_parameters():
+                if "vision_lm_head" not in key:
+                    p.requires_grad = False
+
+    @classmethod
+    def get_model_from_config(cls, config):                                  # :1385-1391
+        from .tokenization_libra import LibraTokenizer
+        model = LibraForCausalLM.from_pretrained(config.pretrained, **dict(config.get("custom_kwargs", {}) or {}))
+        return model, LibraTokenizer(config.pretrained, **dict(config.get("tokenizer_kwargs", {}) or {}))
+
+    def get_optimizer_parameters(self):
+        """Optional hook of LibraTrainer.create_optimizer (trainer.py:46-47, rewritten by :10-25): the default recipe's two
+        groups -- weight decay on everything outside the norm modules that is not a bias."""
+        from ..optim import decay_parameter_names
+        decay = set(decay_parameter_names(self))
+        named = [(n, p) for n, p in self.named_parameters() if p.requires_grad]
+        return [{"params": [p for n, p in named if n in decay], "use_weight_decay": True},
+                {"params": [p for n, p in named if n not in decay], "use_weight_decay": False}]
 
     @classmethod
     def from_config(cls, config, **kw):

@@ -12,7 +12,7 @@ import torch
 import torch.distributed as dist
 
 from libra_b200 import _lib
-from libra_b200.dist import FlatGradBuffer, shard_batch
+from libra_b200.dist import FlatGradBuffer, GradSync, shard_batch
 from libra_b200.models import LibraConfig, LibraForCausalLM
 from libra_b200.synthetic import libra_batch, randomize_for_bench
 
@@ -31,15 +31,19 @@ def main():
     B = 2 * world
     full = libra_batch(B, 700, 1, vocab=cfg.vocab_size, signal=cfg.contiguous_signal_size, seed=3, device=dev)
     mine = shard_batch({k: full[k] for k in ("input_ids", "vision_indices", "contiguous_signal", "labels")}, rank, world)
-    buf = FlatGradBuffer(model.parameters())
-    buf.zero()
+    buf = FlatGradBuffer(model.named_parameters())
+    sync = GradSync(buf, model.model, min_bytes=1 << 16)
+    buf.begin_step()
+    sync.arm(last=True)
     out = model(input_ids=mine["input_ids"], vision_indices=mine["vision_indices"], contiguous_signal=mine["contiguous_signal"],
                 labels=mine["labels"])
-    out.loss.backward()
-    buf.all_reduce_mean(chunks=3)
+    (out.loss / world).backward()
+    sync.finish()
     dp = buf.flat.float().clone()
+    if rank == 0:
+        print(f"[dp_parity] all-reduce pieces: {len(sync.pieces)} over {buf.numel} elements")
     # single-process reference on the whole batch: mean over ranks of per-shard mean losses == loss of equal-size shards
-    buf.zero()
+    buf.begin_step()
     tot = 0.0
     for r in range(world):
         sh = shard_batch({k: full[k] for k in ("input_ids", "vision_indices", "contiguous_signal", "labels")}, r, world)

@@ -27,18 +27,18 @@ def _worker(rank, world, port, ret):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from libra_b200.dist import FlatGradBuffer, shard_batch
     m = _model()
-    buf = FlatGradBuffer(m.parameters())
+    buf = FlatGradBuffer(m.named_parameters())
     g = torch.Generator().manual_seed(7)
     batch = {"x": torch.randn(8, 16, generator=g), "input_ids": torch.randint(0, 9, (2, 8, 5), generator=g), "none": None}
     sh = shard_batch(batch, rank, world)
     assert sh["x"].shape[0] == 4 and sh["input_ids"].shape == (2, 4, 5) and sh["none"] is None
-    buf.zero()
+    buf.begin_step()
     for mb in range(2):                                  # two micro-batches accumulate in place into the flat buffer
         x = sh["x"][mb * 2:(mb + 1) * 2]
         (m(x).pow(2).mean() / 2).backward()
-    buf.all_reduce_mean(chunks=3 if rank >= 0 else 1)
+    buf.all_reduce_mean()
     if rank == 0:
-        ret.put(buf.flat.clone())
+        ret.put(torch.cat([p.grad.reshape(-1) for p in m.parameters()]).clone())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -68,13 +68,100 @@ def test_flat_grad_allreduce_equals_single_process():
 def test_flat_buffer_views_accumulate_in_place():
     from libra_b200.dist import FlatGradBuffer
     m = _model()
-    buf = FlatGradBuffer(m.parameters())
+    buf = FlatGradBuffer(m.named_parameters(), flatten_weights=True)
     ptrs = [p.grad.data_ptr() for p in m.parameters()]
     m(torch.randn(3, 16)).sum().backward()
     m(torch.randn(3, 16)).sum().backward()
     assert [p.grad.data_ptr() for p in m.parameters()] == ptrs        # autograd kept accumulating into the views
     assert buf.flat.abs().sum() > 0
-    off = 0
-    for p in m.parameters():
-        assert torch.equal(buf.flat[off:off + p.numel()].view_as(p), p.grad)
-        off += p.numel()
+    for n, p in m.named_parameters():
+        lo, hi = buf.offsets[n]
+        assert torch.equal(buf.flat[lo:hi].view_as(p), p.grad)
+        assert torch.equal(buf.flat_w[lo:hi].view_as(p), p.data)      # weights are views of the flat weight buffer too
+
+
+class _FakeLayered(torch.nn.Module):
+    """Parameter names of the shape readiness_order() keys on: embedding side, 3 layers, head side."""
+
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(1)
+        self.embed_tokens = torch.nn.Embedding(11, 8)
+        self.layers = torch.nn.ModuleList([torch.nn.Linear(8, 8) for _ in range(3)])
+        self.norm = torch.nn.LayerNorm(8)
+        self.lm_head = torch.nn.Linear(8, 11, bias=False)
+        self.layer_grad_ready_hook = None
+
+    def forward(self, ids):
+        h = self.embed_tokens(ids)
+        for li, l in enumerate(self.layers):
+            if self.layer_grad_ready_hook is not None and h.requires_grad:
+                h.register_hook(lambda g, _li=li: self.layer_grad_ready_hook(_li))
+            h = torch.tanh(l(h))
+        return self.lm_head(self.norm(h))
+
+
+def test_readiness_order_is_backward_order():
+    from libra_b200.dist import FlatGradBuffer
+    m = _FakeLayered()
+    buf = FlatGradBuffer(m.named_parameters())
+    groups = [(n.split(".")[0] + ("." + n.split(".")[1] if n.startswith("layers") else "")) for n in buf.names]
+    # head side first, then layers 2, 1, 0, then the embedding
+    assert groups[0] in ("norm", "lm_head") and groups[-1] == "embed_tokens"
+    layer_pos = [groups.index(f"layers.{i}") for i in range(3)]
+    assert layer_pos[2] < layer_pos[1] < layer_pos[0]
+    assert buf.group_end[max(buf.groups)] == buf.numel
+
+
+def _sync_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from libra_b200.dist import FlatGradBuffer, GradSync
+    m = _FakeLayered()
+    buf = FlatGradBuffer(m.named_parameters())
+    sync = GradSync(buf, m, min_bytes=1)                 # every layer boundary issues a piece
+    g = torch.Generator().manual_seed(100 + rank)
+    crit = torch.nn.CrossEntropyLoss()
+    for step in range(2):                                # the second step checks the per-step reset
+        buf.begin_step()
+        for mb in range(2):
+            ids = torch.randint(0, 11, (4, 5), generator=g)
+            sync.arm(last=(mb == 1))
+            (crit(m(ids).flatten(0, 1), ids.flatten()) / 2 / world).backward()
+        sync.finish()
+    if rank == 0:
+        ret.put((torch.cat([p.grad.reshape(-1) for p in m.parameters()]).clone(), list(sync.pieces)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_overlapped_gradsync_equals_single_process():
+    """GradSync issues the ready prefix piece by piece from the layer hooks during the LAST micro-batch's backward; the sum of
+    the pieces is the all-reduce of the whole buffer."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    ret = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sync_worker, args=(r, world, port, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got, pieces = ret.get()
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    # pieces tile the buffer in order, and there are several of them (head+layer 2, layer 1, layer 0, embeddings)
+    assert pieces[0][0] == 0 and all(a[1] == b[0] for a, b in zip(pieces, pieces[1:])) and len(pieces) >= 4
+    m = _FakeLayered()
+    crit = torch.nn.CrossEntropyLoss()
+    for rank in range(world):
+        g = torch.Generator().manual_seed(100 + rank)
+        for step in range(2):
+            if step == 1:
+                pass
+            for mb in range(2):
+                ids = torch.randint(0, 11, (4, 5), generator=g)
+                if step == 1:
+                    (crit(m(ids).flatten(0, 1), ids.flatten()) / 2 / world).backward()
+    want = torch.cat([p.grad.reshape(-1) for p in m.parameters()])
+    assert pieces[-1][1] == want.numel()
+    assert torch.allclose(got, want, atol=1e-6), (got - want).abs().max()
