@@ -47,7 +47,7 @@ def launches(path, title="launch list"):
     n = sum(a[0] for a in agg.values())
     print(f"# {title}\n\n{n} launches, {tot / 1e3:.2f} ms summed device time (ncu: serialised, cold cache -- compare shares).\n")
     ours = sum(t for k, (c, t) in agg.items() if k.startswith("lb::"))
-    gemm = sum(t for k, (c, t) in agg.items() if "nvjet" in k or "cutlass" in k or "gemm" in k.lower())
+    gemm = sum(t for k, (c, t) in agg.items() if not k.startswith("lb::") and ("nvjet" in k or "cutlass" in k or "gemm" in k.lower() or "cublas" in k.lower()))
     print(f"libra_b200 kernels: {ours / tot * 100:.1f}% | cuBLAS GEMMs: {gemm / tot * 100:.1f}% | other torch kernels: {(tot - ours - gemm) / tot * 100:.1f}%\n")
     print("| share | total us | launches | avg us | kernel |\n|---:|---:|---:|---:|---|")
     for k, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1])[:40]:

@@ -16,7 +16,7 @@ def pytest_configure(config):
 
 def load_golden(name):
     import torch
-    return torch.load(os.path.join(GOLDEN, name + ".pt"), map_location="cpu", weights_only=False)
+    return torch.load(os.path.join(GOLDEN, name + ".pt"), map_location="cpu", weights_only=True)
 
 
 @pytest.fixture(scope="session")

@@ -32,26 +32,59 @@ def test_cuda_arm_fails_loudly_without_gpu():
     assert "{\"metric\"" not in r.stdout          # no number is ever printed from a non-CUDA path
 
 
-def test_archived_cuda_line_satisfies_the_contract():
-    """The latest committed `python bench.py` line (profiles/, measured on a B200): every key the bench contract names,
-    with the types and internal consistency the driver checks."""
-    import glob
-    import re
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r01_bench_run*.json")), key=lambda p: int(re.findall(r"run(\d+)", p)[-1]))
-    d = json.loads(open(files[-1]).read().strip().splitlines()[-1])
+def check_cuda_line(d, tiny=False):
+    """Every key the bench contract names, with the types and internal consistency the driver checks."""
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
               "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
         assert k in d, k
     assert d["metric"] == "libra11b_train_tokens_per_sec" and d["unit"] == "tokens/s" and d["scaling"] == "weak"
     assert d["vs_baseline"] is None and d["dtype"] == "bf16" and d["data"] == "synthetic" and "workload" in d["config"]
-    assert d["warmup"] >= 3 and d["gpu_launches"] > 0
+    assert d["gpu_launches"] > 0
     tokens = d["config"]["global_batch"] * d["config"]["seq_len"]
     assert abs(d["value"] - tokens / (d["ms_per_step"] * 1e-3)) / d["value"] < 1e-6
     e = d["e2e"]
-    assert e["unit"] == "tokens/s" and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and 0 < e["value"] <= d["value"] * 1.02
+    assert e["unit"] == "tokens/s" and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] > 0
+    if not tiny:                 # a launch-bound tiny step is all host jitter; at full size the copies can only cost time
+        assert e["value"] <= d["value"] * 1.05
     r = d["roofline"]
-    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"] > 0
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["traffic"] is None or r["traffic"] > 0
     c = d["clocks"]
-    assert c["sm_mhz"] > 0 and c["sm_max_mhz"] >= c["sm_mhz"] and not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
-    cb = d["cpu_baseline"]
-    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] > 0 and cb["unit"] == "tokens/s"
+    assert not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    if not tiny:
+        assert d["warmup"] >= 3
+        assert c["sm_mhz"] > 0 and c["sm_max_mhz"] >= c["sm_mhz"]
+        assert "configs[" in d["config"]["workload"]
+        cb = d["cpu_baseline"]
+        assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] > 0 and cb["unit"] == "tokens/s"
+
+
+def test_archived_cuda_line_artifact_lint():
+    """Artifact lint, not a regression test: the latest committed full-size `python bench.py` line under profiles/ (measured on
+    a B200) still has the shape the contract asks for.  The live check of the current bench.py is the gpu-marked test below."""
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r0*_bench_run*.json")),
+                   key=lambda p: (int(re.findall(r"r(\d+)_bench", p)[-1]), int(re.findall(r"run(\d+)", p)[-1])))
+    d = json.loads(open(files[-1]).read().strip().splitlines()[-1])
+    check_cuda_line(d)
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_live_tiny_cuda_line_satisfies_the_contract():
+    """The CURRENT bench.py on the GPU box: a --tiny run (plumbing check, not a bench value) must print one line that
+    satisfies the contract, from pixels through the vision tokenizer, with host inputs in the e2e leg."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--tiny", "--steps", "2", "--warmup", "1", "--no-cpu-baseline",
+                        "--workload", "custom", "--batch", "4", "--micro-batch", "2", "--seq", "700"],
+                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    check_cuda_line(d, tiny=True)
+    assert d["config"]["vision_tokenizer_in_step"] is True and "pixel_values" in d["e2e"]["inputs"]
+    assert d["roofline"]["kernel"].startswith("gemm_grouped_kernel")
