@@ -470,6 +470,7 @@ class Workload:
         self.resident = {k: v.to(dev) for k, v in self.host.items()}
         self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.host.values())
         self.opt_events = []
+        self.ar_events = []
 
     def prepare(self, inp):
         """A1-A8 + labels: pixels -> ids / signal -> model inputs (device tensors, no host round trip besides the span mask)."""
@@ -500,10 +501,17 @@ class Workload:
             loss = out.loss * (MB / B) / self.world
             loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
-        if self.args.overlap_allreduce:
-            self.sync.finish()
-        elif self.world > 1:
-            dist.all_reduce(self.buf.flat)
+        if self.world > 1:
+            # device time between "backward fully enqueued" and "every piece of the all-reduce done" = the EXPOSED part of the
+            # gradient reduction (pieces issued from the layer hooks overlap the backward that is still running)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            if self.args.overlap_allreduce:
+                self.sync.finish()
+            else:
+                dist.all_reduce(self.buf.flat)
+            e1.record()
+            self.ar_events.append((e0, e1))
         if self.opt is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -608,6 +616,7 @@ def main():
 
     _lib.reset_launch_counts()
     W.opt_events.clear()
+    W.ar_events.clear()
     ops.enable_timing(("lb_attn_fwd", "lb_attn_fwd_stream", "lb_attn_bwd_dq", "lb_attn_bwd_dkv", "lb_gemm_grouped"))
     sampler = ClockSampler(local) if rank == 0 else None
     if args.cuda_profiler_range:
@@ -623,6 +632,13 @@ def main():
     tokens_step = B * T * world
     value = tokens_step * args.steps / (ms / 1e3)
     opt_ms = (sum(a.elapsed_time(b) for a, b in W.opt_events) / len(W.opt_events)) if W.opt_events else None
+    allreduce = None
+    if world > 1 and W.ar_events:
+        ex = [a.elapsed_time(b) for a, b in W.ar_events[-args.steps:]]
+        allreduce = {"bytes": buf.numel * buf.flat.element_size(), "pieces": [[lo, hi] for lo, hi in sync.pieces],
+                     "n_pieces": len(sync.pieces), "exposed_ms_per_step": sum(ex) / len(ex), "overlapped": bool(args.overlap_allreduce),
+                     "note": "exposed = device time from the end of the last backward to the completion of the last piece (CUDA events); "
+                             "the other pieces run under the last micro-batch's backward"}
 
     e2e = None
     if not args.no_e2e:
@@ -722,7 +738,7 @@ def main():
                    "l2": "working set (>= 22 GB of weights per step) far exceeds the 126 MB L2; no explicit flush",
                    "tiny": bool(args.tiny)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "attention_roofline": attn_roof,
-        "cpu_baseline": cb, "gpu_eager_baseline": gb, "cfg4": cfg4, "optimizer_ms": opt_ms,
+        "cpu_baseline": cb, "gpu_eager_baseline": gb, "cfg4": cfg4, "optimizer_ms": opt_ms, "allreduce": allreduce,
         "loss": float(last_loss.item()) * world if last_loss is not None else None,      # rank 0's mean loss over its samples
         "model_tflops_per_gpu": model_flops_step / (ms / args.steps * 1e-3) / 1e12, "peak_mem_gb": mem_gb,
     }

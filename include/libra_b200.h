@@ -247,7 +247,10 @@ int lb_gemm_bf16(const void* A, const void* B, void* C, const void* bias, int64_
  *     LB_EPI_SWIGLU: B = gate weight, B2 = up weight (both [N,K]); C = silu(x B^T) * (x B2^T), G / U (optional)
  *     receive the gate / up pre-activations
  *   wait_on = j (< i, -1 none): A_i is C_j (same M): tiles of problem i start once the row block of C_j they read is
- *     complete -- the LibraLinear chain in one launch.  Needs lb_gemm_grouped_workspace_bytes() bytes of workspace.
+ *     complete -- the LibraLinear chain in one launch.
+ *   workspace: lb_gemm_grouped_workspace_bytes() bytes of device memory private to the stream (zeroed by the call): the
+ *     launch's tile counter (tiles are claimed dynamically, so CTAs the hardware cannot place while another kernel holds SMs
+ *     -- an overlapped NCCL reduction -- cost throughput in proportion, not a second wave) and the chain counters.
  * Problems with M == 0 or N == 0 are skipped (an empty modality segment).
  *   flags & LB_GEMM_ACCUMULATE_PREV: this entry is one more product A_i . B_i summed (in the fp32 accumulator, before
  *     the epilogue) into the PREVIOUS entry's problem -- same M, N and operand layouts, own K; C / D / bias / epilogue

@@ -41,7 +41,8 @@ constexpr int GG_MAXG = 24;             // output problems per launch (after mer
 constexpr int GG_MAXIN = 32;            // entries of the caller's list per launch
 constexpr int GG_MAXSEG = 6;            // K segments (A_s . B_s products summed into one accumulator) per problem
 constexpr int GG_MAXMAPS = 112;         // tensor maps per launch
-constexpr int GG_THREADS = 192;
+constexpr int GG_THREADS = 224;             // warp 0 TMA, 1 MMA, 2-5 epilogue, 6 tile scheduler
+constexpr int GG_NSLOT = 4;                // claimed-tile ring between the scheduler and the other roles
 constexpr int GG_A_BYTES = GG_BM * GG_BK * 2;          // 16 KB
 constexpr int GG_CHUNK_BYTES = GG_BM * 64 * 2;         // epilogue staging tile: 128 rows x 64 bf16
 constexpr int GG_SUPER_M = 8;                          // row blocks per supertile
@@ -143,6 +144,46 @@ __device__ __forceinline__ void gg_wait(uint32_t bar_addr, uint32_t parity, int 
     } while (!ok);
 }
 
+// wait with cluster-scope acquire: the data guarded by the barrier was written by the partner CTA (st.shared::cluster)
+__device__ __forceinline__ void gg_wait_cluster(uint32_t bar_addr, uint32_t parity, int tag) {
+    uint32_t ok;
+    const long long t0 = clock64();
+    uint32_t spins = 0;
+    for (;;) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, P;\n\t"
+            "}\n"
+            : "=r"(ok)
+            : "r"(bar_addr), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if (LB_MBAR_TIMEOUT_CLK > 0 && (++spins & 1023u) == 0 && clock64() - t0 > LB_MBAR_TIMEOUT_CLK) {
+            printf("libra_b200 gemm_grouped: tile-ring timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x, parity);
+            __trap();
+        }
+    }
+}
+
+// consumer side of the claimed-tile ring: every role of both CTAs sees the same sequence of tile ids, ending with -1
+struct GGFeed {
+    uint32_t slot = 0, phase = 0;
+};
+template <int CG>
+__device__ __forceinline__ int gg_next_tile(GGFeed& f, uint32_t sfull_a, uint32_t ring_a, uint32_t sempty_leader, bool arrive) {
+    gg_wait_cluster(sfull_a + 8 * f.slot, f.phase, 600 + (int)f.slot);
+    int t;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(t) : "r"(ring_a + 4 * f.slot) : "memory");
+    if (arrive) {
+        if (CG == 2) mbar_arrive_cluster(sempty_leader + 8 * f.slot);
+        else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sempty_leader + 8 * f.slot) : "memory");
+    }
+    if (++f.slot == GG_NSLOT) { f.slot = 0; f.phase ^= 1u; }
+    return t;
+}
+
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -166,13 +207,18 @@ __global__ void __launch_bounds__(GG_THREADS, 1) gemm_grouped_kernel(const __gri
     // barrier layout (8 B each): full[STAGES] empty[STAGES] tmem_full[2] tmem_empty[2] dbar[2], then the TMEM base slot
     const uint32_t full_a = bar_base, empty_a = bar_base + 8 * STAGES, tfull_a = bar_base + 16 * STAGES,
                    tempty_a = tfull_a + 16, dbar_a = tfull_a + 32;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
+    // tile ring: sfull[GG_NSLOT] sempty[GG_NSLOT] (8 B each), then the TMEM base slot and GG_NSLOT claimed tile ids
+    const uint32_t sfull_a = tfull_a + 48, sempty_a = sfull_a + 8 * GG_NSLOT;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6 + 2 * GG_NSLOT);
+    int* ring = reinterpret_cast<int*>(tmem_slot + 2);
+    const uint32_t ring_a = sempty_a + 8 * GG_NSLOT + 8;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
-    const int first_tile = (int)blockIdx.x / CG;
-    const int tile_stride = (int)gridDim.x / CG;
+    // Tiles are claimed dynamically (one atomic per tile by the leader CTA's scheduler warp) and handed to every role of both
+    // CTAs through a small ring: CTAs that are resident take work, CTAs that the hardware could not place yet (SMs busy with a
+    // concurrent NCCL kernel during the overlapped gradient reduction) simply find nothing left when they start.
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -185,6 +231,10 @@ __global__ void __launch_bounds__(GG_THREADS, 1) gemm_grouped_kernel(const __gri
         mbar_init(bars + 2 * STAGES + 3, 4 * CG);
         mbar_init(bars + 2 * STAGES + 4, 1);            // dbar (addend tile landed)
         mbar_init(bars + 2 * STAGES + 5, 1);
+        for (int i = 0; i < GG_NSLOT; ++i) {
+            mbar_init(bars + 2 * STAGES + 6 + i, 1);                             // sfull: the scheduler published a tile id
+            mbar_init(bars + 2 * STAGES + 6 + GG_NSLOT + i, CG == 2 ? 11 : 6);   // sempty: every consumer role of the pair read it
+        }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -200,14 +250,39 @@ __global__ void __launch_bounds__(GG_THREADS, 1) gemm_grouped_kernel(const __gri
     if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t sempty_leader = CG == 2 ? mapa_shared(sempty_a, 0) : sempty_a;
+    (void)ring;
 
-    if (warp == 0) {
+    if (warp == 6) {
+        // ------------------------------------------------------------------ tile scheduler (leader CTA)
+        if (rank == 0 && elect_one()) {
+            uint32_t slot = 0, phase = 0;
+            const uint32_t ring_peer = CG == 2 ? mapa_shared(ring_a, 1) : 0u;
+            const uint32_t sfull_peer = CG == 2 ? mapa_shared(sfull_a, 1) : 0u;
+            for (;;) {
+                gg_wait(sempty_a + 8 * slot, phase ^ 1u, 700 + (int)slot);
+                int t = atomicAdd(p.counters, 1);
+                if (t >= p.total_tiles) t = -1;
+                asm volatile("st.shared.s32 [%0], %1;" ::"r"(ring_a + 4 * slot), "r"(t) : "memory");
+                if (CG == 2) {
+                    asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(ring_peer + 4 * slot), "r"(t) : "memory");
+                    mbar_arrive_cluster(sfull_peer + 8 * slot);
+                }
+                asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(sfull_a + 8 * slot) : "memory");
+                if (t < 0) break;
+                if (++slot == GG_NSLOT) { slot = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t full_leader = CG == 2 ? mapa_shared(full_a, 0) : full_a;
-            for (int t = first_tile; t < p.total_tiles; t += tile_stride) {
+            GGFeed feed;
+            for (;;) {
+                const int t = gg_next_tile<CG>(feed, sfull_a, ring_a, sempty_leader, true);
+                if (t < 0) break;
                 const GGTile tl = gg_decode(p, t);
                 const GGProb& pb = p.prob[tl.g];
                 const int m0 = tl.mt * (GG_BM * CG) + (int)rank * GG_BM;
@@ -280,7 +355,10 @@ __global__ void __launch_bounds__(GG_THREADS, 1) gemm_grouped_kernel(const __gri
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int t = first_tile; t < p.total_tiles; t += tile_stride, ++it) {
+            GGFeed feed;
+            for (;; ++it) {
+                const int t = gg_next_tile<CG>(feed, sfull_a, ring_a, sempty_leader, true);
+                if (t < 0) break;
                 const GGTile tl = gg_decode(p, t);
                 const GGProb& pb = p.prob[tl.g];
                 const int acc = it & 1;
@@ -311,7 +389,7 @@ __global__ void __launch_bounds__(GG_THREADS, 1) gemm_grouped_kernel(const __gri
                 if (CG == 2) commit_bar_cg2(tfull_a + 8 * acc, 3); else commit_bar(tfull_a + 8 * acc);
             }
         }
-    } else {
+    } else if (warp >= 2 && warp <= 5) {
         // ------------------------------------------------------------------ epilogue (warps 2..5)
         const int q = warp & 3;                         // TMEM lane quadrant this warp may read
         const int row = q * 32 + lane;                  // accumulator row of this thread
@@ -341,7 +419,15 @@ __global__ void __launch_bounds__(GG_THREADS, 1) gemm_grouped_kernel(const __gri
             ++cc;
         };
 
-        for (int t = first_tile; t < p.total_tiles; t += tile_stride, ++it) {
+        GGFeed feed;
+        for (;; ++it) {
+            const int t = gg_next_tile<CG>(feed, sfull_a, ring_a, sempty_leader, false);
+            __syncwarp();                               // every lane has read the slot before it is handed back
+            if (lane == 0) {
+                if (CG == 2) mbar_arrive_cluster(sempty_leader + 8 * ((feed.slot + GG_NSLOT - 1) % GG_NSLOT));
+                else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sempty_leader + 8 * ((feed.slot + GG_NSLOT - 1) % GG_NSLOT)) : "memory");
+            }
+            if (t < 0) break;
             const GGTile tl = gg_decode(p, t);
             const GGProb& pb = p.prob[tl.g];
             const int acc = it & 1;
@@ -586,7 +672,7 @@ static int launch_grouped(const GGParams& P, cudaStream_t st) {
 using namespace lb;
 
 extern "C" int lb_gemm_grouped_workspace_bytes(const lb_gemm_problem* probs, int n) {
-    int64_t ctr = 0;
+    int64_t ctr = 1;                                        // the tile counter
     const int cg = gemm_cg();
     for (int i = 0; i < n; ++i) {
         bool signals = false;
@@ -612,7 +698,7 @@ extern "C" int lb_gemm_grouped(const lb_gemm_problem* probs, int n, void* worksp
     P.n_prob = 0;
     P.total_tiles = 0;
     P.counters = (int*)workspace;
-    int n_maps = 0, ctr_off = 0, n_live = 0;
+    int n_maps = 0, ctr_off = 1, n_live = 0;                 // counters[0]: the launch's tile counter
     int remap[GG_MAXIN];
     auto add_map = [&](const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t brow, short* idx) -> int {
         if (n_maps >= GG_MAXMAPS) return fail(LB_EINVAL, "gemm_grouped: more than %d tensor maps in one launch", GG_MAXMAPS);
@@ -743,11 +829,9 @@ extern "C" int lb_gemm_grouped(const lb_gemm_problem* probs, int n, void* worksp
     if (n_live == 0) return LB_OK;
     P.n_prob = n_live;
     cudaStream_t st = (cudaStream_t)stream;
-    if (ctr_off > 0) {
-        LB_REQUIRE(workspace && workspace_bytes >= (int64_t)ctr_off * 4, LB_EINVAL,
-                   "gemm_grouped: chained problems need %d bytes of workspace", ctr_off * 4);
-        cudaError_t e = cudaMemsetAsync(workspace, 0, (size_t)ctr_off * 4, st);
-        if (e != cudaSuccess) return fail(LB_ELAUNCH, "gemm_grouped: cudaMemsetAsync: %s", cudaGetErrorString(e));
-    }
+    LB_REQUIRE(workspace && workspace_bytes >= (int64_t)ctr_off * 4, LB_EINVAL,
+               "gemm_grouped: this launch needs %d bytes of workspace (tile counter + chain counters)", ctr_off * 4);
+    cudaError_t e = cudaMemsetAsync(workspace, 0, (size_t)ctr_off * 4, st);
+    if (e != cudaSuccess) return fail(LB_ELAUNCH, "gemm_grouped: cudaMemsetAsync: %s", cudaGetErrorString(e));
     return cg == 2 ? launch_grouped<2>(P, st) : launch_grouped<1>(P, st);
 }

@@ -295,13 +295,11 @@ def gemm_grouped(problems):
     if n == 0:
         return
     arr = (GemmProblem * n)(*problems)
-    ws = None
-    if any(q.wait_on >= 0 for q in problems):
-        dev = torch.cuda.current_device()
-        key = (dev, torch.cuda.current_stream().cuda_stream)
-        ws = _GG_WS.get(key)
-        if ws is None:                      # per-stream counters of the chained problems (zeroed by the library per launch)
-            ws = _GG_WS[key] = torch.zeros(4096, dtype=torch.int32, device=f"cuda:{dev}")
+    dev = torch.cuda.current_device()
+    key = (dev, torch.cuda.current_stream().cuda_stream)
+    ws = _GG_WS.get(key)
+    if ws is None:                          # per-stream tile counter + chain counters (zeroed by the library per launch)
+        ws = _GG_WS[key] = torch.zeros(4096, dtype=torch.int32, device=f"cuda:{dev}")
     _timed_call("lb_gemm_grouped", arr, n, _p(ws), 0 if ws is None else ws.numel() * 4, _st())
 
 
