@@ -431,6 +431,8 @@ class Workload:
     def __init__(self, wl, args, cfg, model, vtok, buf, sync, opt, dev, rank, world):
         from libra_b200 import synthetic
         from libra_b200.models.tokenization_libra import assemble_inputs, get_labels
+        global attach_host_layout
+        from libra_b200.schedule import attach_host_layout
         self.wl, self.args, self.cfg, self.model, self.vtok = wl, args, cfg, model, vtok
         self.buf, self.sync, self.opt, self.dev, self.world = buf, sync, opt, dev, world
         self.assemble_inputs, self.get_labels = assemble_inputs, get_labels
@@ -481,7 +483,7 @@ class Workload:
                                    max_vision_token_length=self.vtok.max_vision_token_length)
         labels = self.get_labels(out["input_ids"], out["attention_mask"], self.vtok.boi_token_id, 1, self.spans)
         return {"input_ids": out["input_ids"], "vision_indices": out["vision_indices"], "contiguous_signal": out["coninous_signal"],
-                "labels": labels}
+                "labels": labels, "flag_cpu": self.host["text_ids"] == self.PH}
 
     def step(self, from_host: bool):
         wl = self.wl
@@ -496,7 +498,10 @@ class Workload:
         for i in range(n_micro):
             sl = slice(i * MB, (i + 1) * MB)
             self.sync.arm(last=(i == n_micro - 1))
-            out = self.model(input_ids=inp["input_ids"][:, sl], attention_mask=None, vision_indices=inp["vision_indices"][sl],
+            vi = inp["vision_indices"][sl]
+            if inp.get("flag_cpu") is not None:         # the layout is known on the host: no device->host copy in the step
+                attach_host_layout(vi, inp["flag_cpu"][sl])
+            out = self.model(input_ids=inp["input_ids"][:, sl], attention_mask=None, vision_indices=vi,
                              contiguous_signal=inp["contiguous_signal"][sl], labels=inp["labels"][:, sl])
             loss = out.loss * (MB / B) / self.world
             loss.backward()

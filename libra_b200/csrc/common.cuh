@@ -514,6 +514,8 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 int make_tmap_bf16_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                       const uint32_t* box, int swizzle128);
 
+int tmap_cache_stats(int64_t* hits, int64_t* misses);      // 2-D maps are cached by (pointer, shape, pitch, box)
+
 int sm_count();
 int require_sm100();
 

@@ -247,7 +247,8 @@ __global__ void __launch_bounds__(GG_THREADS, 1) gemm_grouped_kernel(const __gri
         }
     }
     tc_fence_before_sync();
-    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    if (CG == 2) cluster_sync_all();
+    __syncthreads();      // (the cluster barrier already orders the CTA; compute-sanitizer's racecheck only models bar.sync)
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t sempty_leader = CG == 2 ? mapa_shared(sempty_a, 0) : sempty_a;
@@ -583,49 +584,9 @@ __global__ void __launch_bounds__(GG_THREADS, 1) gemm_grouped_kernel(const __gri
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// host: tensor-map cache.  cuTensorMapEncodeTiled costs ~1 us and the same (pointer, shape) tuples recur every step
-// (weights always, activations through the caching allocator), so encoded maps are kept in a direct-mapped table.
-// ---------------------------------------------------------------------------------------------------------------------
-struct TmapKey {
-    const void* base;
-    uint64_t d0, d1, ld;
-    uint32_t b0, b1;
-};
-struct TmapEntry {
-    TmapKey key;
-    CUtensorMap map;
-    bool valid;
-};
-static constexpr int TMAP_CACHE = 8192;
-static TmapEntry* g_tmap_cache = nullptr;
-static std::mutex g_tmap_mu;
-static uint64_t g_tmap_hits = 0, g_tmap_misses = 0;
-
 static int cached_tmap_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows,
                           uint32_t box_cols) {
-    TmapKey k;
-    memset(&k, 0, sizeof(k));
-    k.base = base; k.d0 = cols; k.d1 = rows; k.ld = ld; k.b0 = box_cols; k.b1 = box_rows;
-    uint64_t h = (uint64_t)(uintptr_t)base * 0x9E3779B97F4A7C15ull;
-    h ^= (rows * 0xC2B2AE3D27D4EB4Full) ^ (cols * 0x165667B19E3779F9ull) ^ (ld << 17) ^ ((uint64_t)box_rows << 40) ^ box_cols;
-    h ^= h >> 29;
-    const int slot = (int)(h % TMAP_CACHE);
-    std::lock_guard<std::mutex> lk(g_tmap_mu);
-    if (!g_tmap_cache) g_tmap_cache = (TmapEntry*)calloc(TMAP_CACHE, sizeof(TmapEntry));
-    TmapEntry& e = g_tmap_cache[slot];
-    if (e.valid && memcmp(&e.key, &k, sizeof(k)) == 0) {
-        *out = e.map;
-        ++g_tmap_hits;
-        return LB_OK;
-    }
-    ++g_tmap_misses;
-    int rc = make_tmap_bf16_2d(out, base, rows, cols, ld, box_rows, box_cols);
-    if (rc) return rc;
-    e.key = k;
-    e.map = *out;
-    e.valid = true;
-    return LB_OK;
+    return make_tmap_bf16_2d(out, base, rows, cols, ld, box_rows, box_cols);      // cached in host.cu
 }
 
 static int gemm_cg() {
@@ -682,12 +643,7 @@ extern "C" int lb_gemm_grouped_workspace_bytes(const lb_gemm_problem* probs, int
     return (int)(ctr * 4);
 }
 
-extern "C" int lb_gemm_tmap_cache_stats(int64_t* hits, int64_t* misses) {
-    std::lock_guard<std::mutex> lk(g_tmap_mu);
-    if (hits) *hits = (int64_t)g_tmap_hits;
-    if (misses) *misses = (int64_t)g_tmap_misses;
-    return LB_OK;
-}
+extern "C" int lb_gemm_tmap_cache_stats(int64_t* hits, int64_t* misses) { return tmap_cache_stats(hits, misses); }
 
 extern "C" int lb_gemm_grouped(const lb_gemm_problem* probs, int n, void* workspace, int64_t workspace_bytes, void* stream) {
     LB_REQUIRE(probs && n > 0 && n <= GG_MAXIN, LB_EINVAL, "gemm_grouped: 1..%d entries per launch, got %d", GG_MAXIN, n);

@@ -108,12 +108,62 @@ int make_tmap_bf16_nd(CUtensorMap* out, const void* base, int rank, const uint64
     return LB_OK;
 }
 
+// Tensor-map cache.  cuTensorMapEncodeTiled costs ~1 us and the same (pointer, shape, pitch, box) tuples recur every step
+// (weights always, activations through the caching allocator), so encoded 2-D maps are kept in a direct-mapped table: a
+// steady-state training step performs no encode at all.  A map is a pure function of its key, so a stale entry cannot exist.
+struct TmapKey {
+    const void* base;
+    uint64_t d0, d1, ld;
+    uint32_t b0, b1;
+};
+struct TmapEntry {
+    TmapKey key;
+    CUtensorMap map;
+    bool valid;
+};
+static constexpr int TMAP_CACHE = 16384;
+static TmapEntry* g_tmap_cache = nullptr;
+static std::mutex g_tmap_mu;
+static uint64_t g_tmap_hits = 0, g_tmap_misses = 0;
+
+int tmap_cache_stats(int64_t* hits, int64_t* misses) {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    if (hits) *hits = (int64_t)g_tmap_hits;
+    if (misses) *misses = (int64_t)g_tmap_misses;
+    return LB_OK;
+}
+
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
                       uint32_t box_rows, uint32_t box_cols) {
+    TmapKey k;
+    memset(&k, 0, sizeof(k));
+    k.base = base; k.d0 = cols; k.d1 = rows; k.ld = ld_elems; k.b0 = box_cols; k.b1 = box_rows;
+    uint64_t h = (uint64_t)(uintptr_t)base * 0x9E3779B97F4A7C15ull;
+    h ^= (rows * 0xC2B2AE3D27D4EB4Full) ^ (cols * 0x165667B19E3779F9ull) ^ (ld_elems << 17) ^ ((uint64_t)box_rows << 40) ^ box_cols;
+    h ^= h >> 29;
+    const int slot = (int)(h % TMAP_CACHE);
+    {
+        std::lock_guard<std::mutex> lk(g_tmap_mu);
+        if (!g_tmap_cache) g_tmap_cache = (TmapEntry*)calloc(TMAP_CACHE, sizeof(TmapEntry));
+        TmapEntry& e = g_tmap_cache[slot];
+        if (e.valid && memcmp(&e.key, &k, sizeof(k)) == 0) {
+            *out = e.map;
+            ++g_tmap_hits;
+            return LB_OK;
+        }
+        ++g_tmap_misses;
+    }
     uint64_t dims[2] = {cols, rows};
     uint64_t strides[1] = {ld_elems * 2};
     uint32_t box[2] = {box_cols, box_rows};
-    return make_tmap_bf16_nd(out, base, 2, dims, strides, box, 1);
+    int rc = make_tmap_bf16_nd(out, base, 2, dims, strides, box, 1);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    TmapEntry& e = g_tmap_cache[slot];
+    e.key = k;
+    e.map = *out;
+    e.valid = true;
+    return LB_OK;
 }
 
 }  // namespace lb

@@ -102,9 +102,11 @@ __global__ void __launch_bounds__(NT) rmsnorm_fwd_kernel(const __nv_bfloat16* __
 
 // ---------------------------------------------------------------- RMSNorm bwd
 // dx = rs * (g - x * rs^2 * mean(g . x)) (+ residual grad),  g = w . dy ;  dw[m] += sum_rows dy . x . rs
-// One WARP per row (no block barriers): pass 1 reduces mean(g.x) with shuffles, pass 2 re-reads the row (L1/L2 hit),
-// writes dx and adds the row's dw contribution into a per-CTA shared-memory accumulator (bank-conflict-free layout
-// [element-in-vector][vector]); the CTA's accumulator goes to `partial`, folded by reduce_partials_kernel.
+// One CTA per row at a time, the row (x, dy) kept in registers: every element crosses HBM once.  The row's mean(g.x) is a
+// block reduction (one barrier per row: the scratch is double buffered).  dw: every thread owns fixed columns and adds its
+// rows' contributions, in row order, into its own slots of a per-CTA shared-memory accumulator -- no atomics, so the result
+// is bit-reproducible run to run (gradient checkpointing's recompute must give identical gradients); the CTA's accumulator
+// goes to `partial`, folded in fixed order by reduce_partials_kernel.
 constexpr int RB_WARPS = 8;
 
 __global__ void __launch_bounds__(RB_WARPS * 32) rmsnorm_bwd_kernel(
@@ -112,62 +114,84 @@ __global__ void __launch_bounds__(RB_WARPS * 32) rmsnorm_bwd_kernel(
     const __nv_bfloat16* __restrict__ w_vis, const uint8_t* __restrict__ flag, const float* __restrict__ rstd,
     const __nv_bfloat16* __restrict__ resid, __nv_bfloat16* __restrict__ dx, float* __restrict__ partial, int64_t rows,
     int cols) {
-    extern __shared__ float dwacc[];                    // [2 modalities][8][nvec]
+    extern __shared__ float dwacc[];                    // [2 modalities][cols], slot (v, j) -> v * 8 + j, owned by thread v % 256
+    __shared__ float red[2][RB_WARPS];
     const int nvec = cols >> 3;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < 2 * cols; i += blockDim.x) dwacc[i] = 0.f;
     __syncthreads();
-    const int64_t warps_total = (int64_t)gridDim.x * RB_WARPS;
-    for (int64_t r = (int64_t)blockIdx.x * RB_WARPS + warp; r < rows; r += warps_total) {
+    int buf = 0;
+    for (int64_t r = blockIdx.x; r < rows; r += gridDim.x, buf ^= 1) {
         const bool vis = flag ? (flag[r] != 0) : false;
         const uint4* xr = reinterpret_cast<const uint4*>(x + r * cols);
         const uint4* dr = reinterpret_cast<const uint4*>(dy + r * cols);
         const uint4* wr = reinterpret_cast<const uint4*>(vis ? w_vis : w_lang);
         const float rs = rstd[r];
+        uint4 xv[MAXV], dv[MAXV], wv[MAXV];
         float dot = 0.f;
-#pragma unroll 4
-        for (int v = lane; v < nvec; v += 32) {
-            float fx[8], fd[8], fw[8];
-            unpack8(__ldg(xr + v), fx);
-            unpack8(__ldg(dr + v), fd);
-            unpack8(__ldg(wr + v), fw);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dot += fw[j] * fd[j] * fx[j];
+        for (int i = 0; i < MAXV; ++i) {
+            const int v = threadIdx.x + i * NT;
+            if (v < nvec) {
+                xv[i] = __ldg(xr + v);
+                dv[i] = __ldg(dr + v);
+                wv[i] = __ldg(wr + v);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int v = threadIdx.x + i * NT;
+            if (v < nvec) {
+                float fx[8], fd[8], fw[8];
+                unpack8(xv[i], fx);
+                unpack8(dv[i], fd);
+                unpack8(wv[i], fw);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dot += fw[j] * fd[j] * fx[j];
+            }
         }
         dot = warp_sum(dot);
-        const float coef = dot / (float)cols * rs * rs * rs;
+        if (lane == 0) red[buf][warp] = dot;
+        __syncthreads();                                 // the other buffer is free again two rows later: one barrier per row
+        float tot = 0.f;
+#pragma unroll
+        for (int i = 0; i < RB_WARPS; ++i) tot += red[buf][i];
+        const float coef = tot / (float)cols * rs * rs * rs;
         uint4* oxr = reinterpret_cast<uint4*>(dx + r * cols);
         const uint4* rr = resid ? reinterpret_cast<const uint4*>(resid + r * cols) : nullptr;
         float* acc = dwacc + (vis ? cols : 0);
-#pragma unroll 2
-        for (int v = lane; v < nvec; v += 32) {
-            float fx[8], fd[8], fw[8], o[8];
-            unpack8(__ldg(xr + v), fx);
-            unpack8(__ldg(dr + v), fd);
-            unpack8(__ldg(wr + v), fw);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = rs * fw[j] * fd[j] - fx[j] * coef;
-            if (rr) {
-                float fr[8];
-                unpack8(__ldg(rr + v), fr);
+        for (int i = 0; i < MAXV; ++i) {
+            const int v = threadIdx.x + i * NT;
+            if (v < nvec) {
+                float fx[8], fd[8], fw[8], o[8];
+                unpack8(xv[i], fx);
+                unpack8(dv[i], fd);
+                unpack8(wv[i], fw);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] += fr[j];
-            }
-            oxr[v] = pack8(o);
-            if (partial) {
+                for (int j = 0; j < 8; ++j) o[j] = rs * fw[j] * fd[j] - fx[j] * coef;
+                if (rr) {
+                    float fr[8];
+                    unpack8(__ldg(rr + v), fr);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) atomicAdd(acc + j * nvec + v, fd[j] * fx[j] * rs);
+                    for (int j = 0; j < 8; ++j) o[j] += fr[j];
+                }
+                oxr[v] = pack8(o);
+                if (partial) {
+                    float4* a4 = reinterpret_cast<float4*>(acc + v * 8);
+                    float4 a0 = a4[0], a1 = a4[1];
+                    a0.x += fd[0] * fx[0] * rs; a0.y += fd[1] * fx[1] * rs; a0.z += fd[2] * fx[2] * rs; a0.w += fd[3] * fx[3] * rs;
+                    a1.x += fd[4] * fx[4] * rs; a1.y += fd[5] * fx[5] * rs; a1.z += fd[6] * fx[6] * rs; a1.w += fd[7] * fx[7] * rs;
+                    a4[0] = a0;
+                    a4[1] = a1;
+                }
             }
         }
     }
     __syncthreads();
     if (partial) {
-        // partial[block][2][cols] in natural column order
-        float* out = partial + (int64_t)blockIdx.x * 2 * cols;
-        for (int i = threadIdx.x; i < 2 * cols; i += blockDim.x) {
-            const int m = i / cols, c = i - m * cols;
-            out[i] = dwacc[m * cols + (c & 7) * nvec + (c >> 3)];
-        }
+        float* out = partial + (int64_t)blockIdx.x * 2 * cols;      // partial[block][2][cols], natural column order
+        for (int i = threadIdx.x; i < 2 * cols; i += blockDim.x) out[i] = dwacc[i];
     }
 }
 
@@ -334,7 +358,7 @@ static int norm_grid(int64_t rows) {
 
 static int rms_bwd_grid(int64_t rows) {
     int64_t g = (int64_t)sm_count() * 4;
-    const int64_t need = (rows + RB_WARPS - 1) / RB_WARPS;
+    const int64_t need = rows;                       // one CTA per row at a time
     return (int)(need < g ? (need > 0 ? need : 1) : g);
 }
 

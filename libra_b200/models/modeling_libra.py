@@ -246,12 +246,21 @@ class LibraModel(LibraPreTrainedModel):
         return c
 
     def build_meta(self, vision_flag: torch.Tensor, attention_mask: Optional[torch.Tensor],
-                   position_ids: Optional[torch.Tensor]) -> LF.AttnMeta:
-        """One host round trip per distinct batch layout: routing permutation, attention work lists, key ranges."""
+                   position_ids: Optional[torch.Tensor], flag_cpu: Optional[torch.Tensor] = None,
+                   am_cpu: Optional[torch.Tensor] = None) -> LF.AttnMeta:
+        """Routing permutation, attention work lists, key ranges: built on the host once per distinct batch layout and
+        cached.  The cache key is the layout itself; when the caller already holds it on the host (`flag_cpu`, `am_cpu`:
+        LibraTokenizer and bench.py attach them to the device tensors, see schedule.attach_host_layout) nothing is copied
+        back from the device, otherwise one device->host copy of the [B,T] flag (and mask) per call."""
         B, T = vision_flag.shape
         dev = vision_flag.device
-        flag_cpu = vision_flag.detach().to("cpu")
-        am_cpu = None if attention_mask is None else attention_mask.detach().to("cpu").to(torch.bool)
+        if flag_cpu is None:
+            flag_cpu = vision_flag.detach().to("cpu")
+        if attention_mask is None:
+            am_cpu = None
+        elif am_cpu is None:
+            am_cpu = attention_mask.detach().to("cpu")
+        am_cpu = None if am_cpu is None else am_cpu.to(torch.bool)
         key = (B, T, flag_cpu.numpy().tobytes(), None if am_cpu is None else am_cpu.numpy().tobytes())
         hit = self._meta_cache.get(key)
         if hit is None:
@@ -480,9 +489,18 @@ class LibraForCausalLM(LibraPreTrainedModel):
             raise TypeError("libra_b200 computes in bf16: call model.to(torch.bfloat16) as train.py:31-32 does")
         assert len(input_ids) == self.vision_codebook_num
         vision_flag = vision_indices < self.max_vision_token_length
-        if not torch.equal(vision_flag, input_ids[0] >= self.config.vocab_size):
-            raise AssertionError("Inconsistent input_ids and vision_flag")
-        meta = self.model.build_meta(vision_flag, attention_mask, position_ids)
+        flag_cpu, am_cpu = schedule.host_layout(vision_indices), schedule.host_layout(attention_mask)
+        inconsistent = None
+        if flag_cpu is None:
+            # the reference's assertion (modeling_libra.py:708-711), eagerly: one host synchronisation
+            if not torch.equal(vision_flag, input_ids[0] >= self.config.vocab_size):
+                raise AssertionError("Inconsistent input_ids and vision_flag")
+        else:
+            # the layout came with a host copy: no device->host traffic in the steady state.  The same assertion is evaluated on
+            # the device and, if violated, turns the loss / logits of this call into NaN (and raises at check_inputs()).
+            inconsistent = (vision_flag != (input_ids[0] >= self.config.vocab_size)).any()
+            self._inconsistent = inconsistent if getattr(self, "_inconsistent", None) is None else (self._inconsistent | inconsistent)
+        meta = self.model.build_meta(vision_flag, attention_mask, position_ids, flag_cpu, am_cpu)
         hn, hiddens = self.model.forward_sorted(input_ids, meta, contiguous_signal, collect_hidden=bool(output_hidden_states))
 
         training_loss = labels is not None and torch.is_grad_enabled() and self.training
@@ -491,7 +509,11 @@ class LibraForCausalLM(LibraPreTrainedModel):
         if labels is not None:
             assert len(labels) == self.vision_codebook_num
             loss = self._fused_loss(hn, meta, labels.to(hn.device))
+            if inconsistent is not None:
+                loss = loss + torch.where(inconsistent, float("nan"), 0.0).to(loss.dtype)
         logits = self._materialize_logits(hn, meta) if want_logits else None
+        if logits is not None and inconsistent is not None:
+            logits = torch.where(inconsistent, torch.full_like(logits, float("nan")), logits)
         hs = None
         if hiddens is not None:
             inv = meta.routing.inv.long()
@@ -503,6 +525,13 @@ class LibraForCausalLM(LibraPreTrainedModel):
         return LibraCausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=None, hidden_states=hs,
                                            attentions=None, past_hidden_states=None, past_vision_flag=None)
 
+
+    def check_inputs(self):
+        """Raise the reference's "Inconsistent input_ids and vision_flag" assertion for calls that deferred it (one sync)."""
+        bad = getattr(self, "_inconsistent", None)
+        self._inconsistent = None
+        if bad is not None and bool(bad):
+            raise AssertionError("Inconsistent input_ids and vision_flag")
 
     # -------------------------------------------------------------- N1: use_cache=True (prefill and one-token steps)
     @torch.no_grad()

@@ -379,9 +379,14 @@ class LibraTokenizer(torch.nn.Module):
             raise ValueError("return_tensors = \"pt\" is fixed, and should not be specified to other values.")
         truncation = kwargs.pop("truncation", False)
         max_length = kwargs.pop("max_length", self.text_tokenizer.model_max_length)
-        text_inputs = self.text_tokenizer(texts, return_tensors="pt", return_length=True, **kwargs).to(dev)
-        input_ids = text_inputs["input_ids"]
+        text_inputs = self.text_tokenizer(texts, return_tensors="pt", return_length=True, **kwargs)
         tt, it = self.text_tokenizer, self.image_tokenizer
+        # the layout (which positions are image tokens, which are padding) is known on the host right here: hand it to the
+        # model with the device tensors so that it never has to be copied back (schedule.attach_host_layout)
+        ids_cpu, am_cpu = text_inputs["input_ids"], text_inputs["attention_mask"]
+        flag_cpu = (ids_cpu == tt.img_ph_token_id) if images is not None else (ids_cpu == tt.img_gen_token_id)
+        text_inputs = text_inputs.to(dev)
+        input_ids = text_inputs["input_ids"]
         input_ids = torch.where(input_ids == tt.img_gen_token_id, torch.full_like(input_ids, it.boi_token_id), input_ids)
         gen_mask = text_inputs["input_ids"] == tt.img_gen_token_id
         image_ids = feat = None
@@ -397,4 +402,8 @@ class LibraTokenizer(torch.nn.Module):
         if images is None:                                                        # generation prompts: <img_gen> opens an image (:274-275)
             out["vision_indices"] = torch.where(gen_mask[:, :out["vision_indices"].shape[1]],
                                                 torch.zeros_like(out["vision_indices"]), out["vision_indices"])
+        from ..schedule import attach_host_layout
+        Tn = out["vision_indices"].shape[1]
+        attach_host_layout(out["vision_indices"], flag_cpu[:, :Tn].contiguous())
+        attach_host_layout(out["attention_mask"], am_cpu[:, :Tn].contiguous())
         return out if self.raw_output else BatchEncoding(out)

@@ -128,3 +128,22 @@ def build_attn_work(vision_flag_cpu: Optional[torch.Tensor], batch: int, seqlen:
     to = lambda t: None if t is None else torch.as_tensor(t, dtype=torch.int32).to(device)
     return AttnWork(wq.to(device), wkv.to(device), has.to(device), to(kv_start), to(kv_end), (cover[0], cover[1]),
                     [w for w, _, _, _ in items_q])
+
+
+# ----------------------------------------------------------------------------- host copies of the batch layout
+def attach_host_layout(dev_tensor: torch.Tensor, host_tensor: torch.Tensor) -> torch.Tensor:
+    """Remember the host copy of a layout tensor (vision flag of `vision_indices`, `attention_mask`) on the device tensor
+    object that is handed to the model, so the model can key its per-layout metadata cache without a device->host copy.
+    The producer of the batch (LibraTokenizer.forward: the text ids are tokenised on the host; bench.py: synthetic layouts)
+    has these values on the host anyway.  For `vision_indices` the host tensor is the boolean vision flag [B,T]."""
+    dev_tensor._lb_host_layout = host_tensor
+    return dev_tensor
+
+
+def host_layout(dev_tensor):
+    if dev_tensor is None:
+        return None
+    h = getattr(dev_tensor, "_lb_host_layout", None)
+    if h is not None and tuple(h.shape) != tuple(dev_tensor.shape):
+        return None
+    return h

@@ -54,3 +54,11 @@ if "dq" in which and "dkv" in which:
     t_k = timeit(lambda: ops.attn_bwd_dkv(Q, K0, V0, K1, V1, dO, lse, delta, qf, w.qtile_has, w.work_kv, None, None, B, T, H, D, True,
                                           scale, kv_cover=(True, True)))
     print(f"dq {t_q*1e3:.0f} us | dkv {t_k*1e3:.0f} us | bwd {2.5*fl/(t_q+t_k)/1e9:.0f} TF/s (algorithmic, causal)")
+if "fa2" in which:
+    # informational: the flash-attn library, plain causal attention (use_bridge=False semantics)
+    from libra_b200.utils.llama_flash_attn_monkey_patch import flash_attn_reference_point
+    r = flash_attn_reference_point(B, T, H, D)
+    if r is None or r[0] == "unavailable":
+        print("fa2 unavailable:", r)
+    else:
+        print(f"fa2 (library, no bridge) fwd {r[0]*1e3:.0f} us = {fl/r[0]/1e9:.0f} TF/s | fwd+bwd {r[1]*1e3:.0f} us")
