@@ -305,9 +305,12 @@ int lb_adamw_bf16(void* param, const void* grad, void* exp_avg, void* exp_avg_sq
                   float eps, float weight_decay, int step, void* stream);
 
 /* same with the gradient multiplied by *grad_scale (device fp32 scalar, may be NULL): gradient clipping folded into
- * the optimizer pass (trainer.py / libra_pretrain.yaml:116 max_grad_norm 1.0) */
+ * the optimizer pass (trainer.py / libra_pretrain.yaml:116 max_grad_norm 1.0); and with weight decay switched off inside
+ * `nodecay_ranges` (device int64 [n_nodecay][2], sorted, disjoint [lo, hi) in units of 8 elements; may be NULL): the
+ * reference's decay exclusions (norm weights, biases; trainer.py:27-37) without splitting the launch. */
 int lb_adamw_bf16_scaled(void* param, const void* grad, void* exp_avg, void* exp_avg_sq, int64_t n, float lr, float beta1,
-                         float beta2, float eps, float weight_decay, int step, const float* grad_scale, void* stream);
+                         float beta2, float eps, float weight_decay, int step, const float* grad_scale,
+                         const int64_t* nodecay_ranges, int n_nodecay, void* stream);
 /* global L2 norm of a flat bf16 gradient buffer and the clip factor, on the device, deterministic (two stages, no atomics):
  * out2[0] = ||g||, out2[1] = min(1, max_norm / (||g|| + 1e-6)) -- torch.nn.utils.clip_grad_norm_ semantics.
  * workspace: >= 64 floats (one partial per CTA; more floats = more CTAs, 2368 saturates a B200). */

@@ -61,7 +61,7 @@ SIGNATURES = {
     "lb_cross_entropy_fwd_bwd": (I, [P, L, P, P, L, I, F, P]),
     "lb_probe_umma": (I, [I, P, P, P, I, P]),
     "lb_adamw_bf16": (I, [P, P, P, P, L, F, F, F, F, F, I, P]),
-    "lb_adamw_bf16_scaled": (I, [P, P, P, P, L, F, F, F, F, F, I, P, P]),
+    "lb_adamw_bf16_scaled": (I, [P, P, P, P, L, F, F, F, F, F, I, P, P, I, P]),
     "lb_grad_clip_scale": (I, [P, L, F, P, I, P, P]),
 }
 
@@ -105,7 +105,7 @@ def last_error() -> str:
 
 # CUDA kernels enqueued by one successful call of each entry point (host-side launch accounting for bench.py)
 KERNELS_PER_CALL = {
-    "lb_rmsnorm_fwd": 1, "lb_rmsnorm_bwd": 3, "lb_layernorm_fwd": 1, "lb_layernorm_bwd": 3, "lb_swiglu_fwd": 1,
+    "lb_rmsnorm_fwd": 1, "lb_rmsnorm_bwd": 2, "lb_layernorm_fwd": 1, "lb_layernorm_bwd": 2, "lb_swiglu_fwd": 1,
     "lb_swiglu_bwd": 1, "lb_bias_quick_gelu_fwd": 1, "lb_bias_quick_gelu_bwd": 1, "lb_gather_rows": 1,
     "lb_embed_lang_fwd": 1, "lb_embed_vision_cat_fwd": 3, "lb_embed_bwd": 1, "lb_lfq_pack": 1, "lb_lfq_unpack": 1,
     "lb_attn_prep_fwd": 1, "lb_attn_prep_bwd": 1, "lb_attn_fwd": 1, "lb_attn_fwd_stream": 1, "lb_attn_bwd_prepare": 1, "lb_attn_bwd_dq": 1,

@@ -469,9 +469,30 @@ __global__ void __launch_bounds__(256) adamw_bf16_scaled_kernel(__nv_bfloat16* _
                                                                 __nv_bfloat16* __restrict__ m, __nv_bfloat16* __restrict__ v,
                                                                 int64_t nvec, float lr, float beta1, float beta2, float eps,
                                                                 float weight_decay, float bc1, float bc2_sqrt,
-                                                                const float* __restrict__ grad_scale) {
+                                                                const float* __restrict__ grad_scale,
+                                                                const int64_t* __restrict__ nodecay, int n_nodecay) {
     const float gs = grad_scale ? __ldg(grad_scale) : 1.f;
+    // weight decay applies outside the sorted [lo, hi) vector ranges of `nodecay` (norm weights, biases).  A thread's index only
+    // grows, so it keeps the end of the constant-decay interval it is in and searches the table again only after leaving it
+    // (intervals are millions of vectors long; the grid stride is ~600 k vectors)
+    float wd = weight_decay;
+    int64_t seg_end = n_nodecay > 0 ? -1 : INT64_MAX;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        if (i >= seg_end) {
+            int lo = 0, hi = n_nodecay;
+            while (lo < hi) {                            // first range whose end is beyond i
+                const int mid = (lo + hi) >> 1;
+                if (__ldg(nodecay + 2 * mid + 1) <= i) lo = mid + 1; else hi = mid;
+            }
+            const int64_t r_lo = lo < n_nodecay ? __ldg(nodecay + 2 * lo) : INT64_MAX;
+            if (r_lo <= i) {
+                wd = 0.f;
+                seg_end = __ldg(nodecay + 2 * lo + 1);
+            } else {
+                wd = weight_decay;
+                seg_end = r_lo;
+            }
+        }
         float fp[8], fg[8], fm[8], fv[8];
         unpack8(reinterpret_cast<const uint4*>(p)[i], fp);
         unpack8(__ldg(reinterpret_cast<const uint4*>(g) + i), fg);
@@ -480,7 +501,7 @@ __global__ void __launch_bounds__(256) adamw_bf16_scaled_kernel(__nv_bfloat16* _
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float gj = fg[j] * gs;
-            fp[j] *= (1.f - lr * weight_decay);
+            fp[j] *= (1.f - lr * wd);
             fm[j] = beta1 * fm[j] + (1.f - beta1) * gj;
             fv[j] = beta2 * fv[j] + (1.f - beta2) * gj * gj;
             const float denom = sqrtf(fv[j]) / bc2_sqrt + eps;
@@ -754,7 +775,8 @@ int lb_adamw_bf16(void* param, const void* grad, void* exp_avg, void* exp_avg_sq
 }
 
 int lb_adamw_bf16_scaled(void* param, const void* grad, void* exp_avg, void* exp_avg_sq, int64_t n, float lr, float beta1,
-                         float beta2, float eps, float weight_decay, int step, const float* grad_scale, void* stream) {
+                         float beta2, float eps, float weight_decay, int step, const float* grad_scale,
+                         const int64_t* nodecay_ranges, int n_nodecay, void* stream) {
     LB_REQUIRE(n >= 0 && n % 8 == 0 && step >= 1, LB_EINVAL, "adamw: n=%lld must be a multiple of 8, step >= 1", (long long)n);
     LB_REQUIRE(AL16(param) && AL16(grad) && AL16(exp_avg) && AL16(exp_avg_sq), LB_EALIGN, "adamw: buffers must be 16-byte aligned");
     if (n == 0) return LB_OK;
@@ -763,7 +785,7 @@ int lb_adamw_bf16_scaled(void* param, const void* grad, void* exp_avg, void* exp
     const int64_t nvec = n / 8;
     adamw_bf16_scaled_kernel<<<ew_grid(nvec, 256), 256, 0, (cudaStream_t)stream>>>(
         (__nv_bfloat16*)param, (const __nv_bfloat16*)grad, (__nv_bfloat16*)exp_avg, (__nv_bfloat16*)exp_avg_sq, nvec, lr, beta1,
-        beta2, eps, weight_decay, bc1, bc2_sqrt, grad_scale);
+        beta2, eps, weight_decay, bc1, bc2_sqrt, grad_scale, nodecay_ranges, nodecay_ranges ? n_nodecay : 0);
     return check_launch("adamw_bf16_scaled");
 }
 

@@ -196,9 +196,16 @@ __global__ void __launch_bounds__(RB_WARPS * 32) rmsnorm_bwd_kernel(
 }
 
 // out[c] += sum_b partial[b][off + c]: CTA = 32 columns x 8 row lanes, rows strided by 8, then a shared-memory fold.
+// blockIdx.y selects (off, out) / (off2, out2): both halves of the partial rows in one launch.
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, int nblocks, int width, int off,
-                                                              int stride, float* __restrict__ out) {
+                                                              int stride, float* __restrict__ out, int off2 = 0,
+                                                              float* __restrict__ out2 = nullptr) {
     __shared__ float sm[8][33];
+    if (blockIdx.y == 1) {
+        off = off2;
+        out = out2;
+    }
+    if (!out) return;
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cx;
     float s = 0.f;
@@ -418,8 +425,8 @@ int lb_rmsnorm_bwd(const void* dy, const void* x, const void* w_lang, const void
     rc = check_launch("rmsnorm_bwd");
     if (rc) return rc;
     const int tb = 256, gb = ceil_div(cols, 32);
-    if (dw_lang) reduce_partials_kernel<<<gb, tb, 0, st>>>((const float*)partial, grid, cols, 0, 2 * cols, dw_lang);
-    if (dw_vis) reduce_partials_kernel<<<gb, tb, 0, st>>>((const float*)partial, grid, cols, cols, 2 * cols, dw_vis);
+    if (dw_lang || dw_vis)
+        reduce_partials_kernel<<<dim3(gb, 2), tb, 0, st>>>((const float*)partial, grid, cols, 0, 2 * cols, dw_lang, cols, dw_vis);
     return check_launch("rmsnorm_bwd_reduce");
 }
 
@@ -450,8 +457,8 @@ int lb_layernorm_bwd(const void* dy, const void* x, const void* w, const float* 
     rc = check_launch("layernorm_bwd");
     if (rc) return rc;
     const int tb = 256, gb = ceil_div(cols, 32);
-    if (dw) reduce_partials_kernel<<<gb, tb, 0, st>>>((const float*)partial, grid, cols, 0, 2 * cols, dw);
-    if (db) reduce_partials_kernel<<<gb, tb, 0, st>>>((const float*)partial, grid, cols, cols, 2 * cols, db);
+    if (dw || db)
+        reduce_partials_kernel<<<dim3(gb, 2), tb, 0, st>>>((const float*)partial, grid, cols, 0, 2 * cols, dw, cols, db);
     return check_launch("layernorm_bwd_reduce");
 }
 

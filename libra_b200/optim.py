@@ -3,9 +3,9 @@
 Reference policy (trainer.py:27-85, libra/configs/libra_pretrain.yaml:81-91,116): AdamW(beta 0.9 / 0.99, eps 1e-8),
 weight decay 0.01 on every parameter that is not inside a LayerNorm / LlamaRMSNorm module and whose name has no "bias"
 (`get_decay_parameter_names`), gradient clipping at max_grad_norm 1.0, cosine schedule with warm-up ratio 0.05.
-Here: one fused kernel launch per contiguous run of equal weight decay over the flat buffers (lb_adamw_bf16_scaled), the
-global gradient norm and the clip factor computed on the device (lb_grad_clip_scale) and folded into that same pass --
-no host synchronisation and no extra pass over the 22 GB gradient buffer.
+Here: ONE fused kernel launch over the flat buffers (lb_adamw_bf16_scaled; the decay exclusions are a device-side range table),
+the global gradient norm and the clip factor computed on the device (lb_grad_clip_scale: one read of the gradient buffer)
+and folded into that same pass -- no host synchronisation and no separate scaling pass over the 22 GB gradient buffer.
 """
 from __future__ import annotations
 
@@ -99,26 +99,57 @@ class FlatAdamW:
         """device tensor [norm, clip factor] of the last step() (no sync until read)."""
         return self.clip_out
 
+    def _plan(self):
+        """One launch over the 8-aligned body of the buffer with weight decay `wd_main`, the no-decay runs as a device range
+        table; what does not fit that form (other decay values, < 8 stray elements at unaligned run edges) goes to `tails`."""
+        if getattr(self, "_planned", None) is not None:
+            return self._planned
+        n = self.p.numel()
+        decays = sorted({wd for _, _, wd in self.runs if wd != 0.0})
+        wd_main = decays[0] if decays else 0.0
+        ranges, tails = [], []
+        for lo, hi, wd in self.runs:
+            lo8, hi8 = (lo + 7) // 8 * 8, hi // 8 * 8
+            if wd == 0.0 and wd_main != 0.0 and hi8 > lo8:
+                ranges.append((lo8 // 8, hi8 // 8))
+            if wd not in (0.0, wd_main):
+                raise NotImplementedError("FlatAdamW: one non-zero weight decay value per buffer")
+        # elements of a run that are not 8-aligned inside their run share a vector with the neighbour run: do them on the side
+        for (lo, hi, wd), nxt in zip(self.runs, self.runs[1:] + [None]):
+            if hi % 8 and nxt is not None and nxt[2] != wd:
+                v0 = hi // 8 * 8
+                tails.append((slice(v0, min(v0 + 8, n)),))
+        n8 = n - n % 8
+        if n % 8:
+            tails.append((slice(n8, n),))
+        tbl = torch.tensor(ranges, dtype=torch.int64, device=self.p.device).reshape(-1, 2) if ranges else None
+        self._planned = (wd_main, tbl, tails, n8)
+        return self._planned
+
     def step(self):
         self.t += 1
         lr = self.lr * (self.schedule(self.t - 1) if self.schedule is not None else 1.0)      # HF steps the scheduler after the update
         self.last_lr = lr
-        n8 = self.p.numel() - self.p.numel() % 8
+        wd_main, tbl, tails, n8 = self._plan()
         scale = None
         if self.max_grad_norm > 0:
             _lib.call("lb_grad_clip_scale", _p(self.g), n8, float(self.max_grad_norm), _p(self.clip_ws), self.clip_ws.numel(),
                       _p(self.clip_out), _st())
             scale = ctypes.c_void_p(self.clip_out.data_ptr() + 4)
-        es = self.p.element_size()
+        saved = [(sl, self.p[sl].clone(), self.m[sl].clone(), self.v[sl].clone()) for (sl,) in tails]
+        _lib.call("lb_adamw_bf16_scaled", _p(self.p), _p(self.g), _p(self.m), _p(self.v), n8, float(lr), float(self.betas[0]),
+                  float(self.betas[1]), float(self.eps), float(wd_main), self.t, scale, _p(tbl), 0 if tbl is None else tbl.shape[0],
+                  _st())
+        for sl, p0, m0, v0 in saved:                      # shared / stray vectors: redo element-wise with each element's own decay
+            self.p[sl], self.m[sl], self.v[sl] = p0, m0, v0
+            for i in range(sl.start, sl.stop):
+                self._tail(slice(i, i + 1), lr, self._wd_of(i))
+
+    def _wd_of(self, i):
         for lo, hi, wd in self.runs:
-            lo8, hi8 = (lo + 7) // 8 * 8, hi // 8 * 8
-            if hi8 > lo8:
-                off = lambda t: ctypes.c_void_p(t.data_ptr() + lo8 * es)
-                _lib.call("lb_adamw_bf16_scaled", off(self.p), off(self.g), off(self.m), off(self.v), hi8 - lo8, float(lr),
-                          float(self.betas[0]), float(self.betas[1]), float(self.eps), float(wd), self.t, scale, _st())
-            for a, b in ((lo, min(lo8, hi)), (max(hi8, lo), hi)):                      # < 8 stray elements at a run edge
-                if b > a:
-                    self._tail(slice(a, b), lr, wd)
+            if lo <= i < hi:
+                return wd
+        return 0.0
 
     def _tail(self, sl, lr, wd):
         gs = self.clip_out[1] if self.max_grad_norm > 0 else 1.0
