@@ -622,7 +622,7 @@ def main():
     _lib.reset_launch_counts()
     W.opt_events.clear()
     W.ar_events.clear()
-    ops.enable_timing(("lb_attn_fwd", "lb_attn_fwd_stream", "lb_attn_bwd_dq", "lb_attn_bwd_dkv", "lb_gemm_grouped"))
+    ops.enable_timing(("lb_attn_fwd", "lb_attn_fwd_stream", "lb_attn_bwd_dq", "lb_attn_bwd_dq_stream", "lb_attn_bwd_dkv", "lb_gemm_grouped"))
     sampler = ClockSampler(local) if rank == 0 else None
     if args.cuda_profiler_range:
         torch.cuda.synchronize()
@@ -717,9 +717,9 @@ def main():
                      "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tflops_sustained"],
                      "traffic": attn_traffic(MB, T, cfg), "avg_launch_ms": t_ms,
                      "algorithmic_flops_per_launch": fl["attn_per_layer_fwd"],
-                     "bwd_ms": {k: v for k, v in kern.items() if k in ("lb_attn_bwd_dq", "lb_attn_bwd_dkv")},
-                     "bwd_achieved_tflops": (2.5 * fl["attn_per_layer_fwd"] / ((kern.get("lb_attn_bwd_dq", 0) + kern.get("lb_attn_bwd_dkv", 0)) * 1e-3) / 1e12)
-                     if kern.get("lb_attn_bwd_dq") else None}
+                     "bwd_ms": {k: v for k, v in kern.items() if k in ("lb_attn_bwd_dq", "lb_attn_bwd_dq_stream", "lb_attn_bwd_dkv")},
+                     "bwd_achieved_tflops": (2.5 * fl["attn_per_layer_fwd"] / ((kern.get("lb_attn_bwd_dq", 0) + kern.get("lb_attn_bwd_dq_stream", 0) + kern.get("lb_attn_bwd_dkv", 0)) * 1e-3) / 1e12)
+                     if (kern.get("lb_attn_bwd_dq") or kern.get("lb_attn_bwd_dq_stream")) else None}
     model_flops_step = 3.0 * fl["total"] * n_micro
     gb = None
     if not args.no_gpu_baseline and world == 1 and not args.tiny:

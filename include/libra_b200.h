@@ -192,6 +192,18 @@ int lb_attn_bwd_dq(const void* Q, const void* K0, const void* V0, const void* K1
                    const float* lse, const float* delta, const uint8_t* qflag, const int32_t* work, int n_work,
                    const int32_t* kv_start, const int32_t* kv_end, void* dQ, int batch, int seqlen, int heads,
                    int head_dim, int causal, float scale, void* stream);
+/* Same operation and work list as lb_attn_bwd_dq, persistent streaming kernel (csrc/attn_bwd_dq_stream.cu): one CTA per SM
+ * walks its share of the (work item, head) list as one stream of 128x64 tiles; S and dP double-buffered in TMEM and issued one
+ * tile ahead of the dS computation, K ring of 4 / V ring of 3, two compute warpgroups on alternate tiles.  plan_* / n_cta /
+ * max_cta_items / head_group: as for lb_attn_fwd_stream (the forward's plan is the balanced split for this kernel too). */
+int lb_attn_bwd_dq_stream(const void* Q, const void* K0, const void* V0, const void* K1, const void* V1, const void* dO,
+                          const float* lse, const float* delta, const uint8_t* qflag, const int32_t* work, int n_work,
+                          const int32_t* plan_items, const int32_t* plan_off, int n_cta, int max_cta_items, int head_group,
+                          const int32_t* kv_start, const int32_t* kv_end, void* dQ, int batch, int seqlen, int heads,
+                          int head_dim, int causal, float scale, void* stream);
+int lb_attn_bwd_dq_stream_max_cta_items(void);
+/* diagnostics: CTA 0 writes clock64 stamps into buf ([64][32] int64, device; see csrc/attn_bwd_dq_stream.cu).  NULL = off */
+int lb_attn_bwd_dq_stream_set_trace(void* buf);
 /* dK0,dV0 (gradient w.r.t. the variant-0 operands, from qflag==0 query rows) and dK1,dV1.
  * work_kv: int32 [n_work,4] = {batch, kv_tile, variant, first_q_tile}; qtile_has: uint8 [B,2,ceil(T/128)]
  * (1 when the q tile holds rows of that modality; NULL = visit every tile).  Rows of kv tiles without a
@@ -316,6 +328,32 @@ int lb_adamw_bf16_scaled(void* param, const void* grad, void* exp_avg, void* exp
  * workspace: >= 64 floats (one partial per CTA; more floats = more CTAs, 2368 saturates a B200). */
 int lb_grad_clip_scale(const void* grad, int64_t n, float max_norm, float* workspace, int workspace_floats, float* out2,
                        void* stream);
+
+/* ---- N2: vision-tokenizer decode (ids -> pixels), the kernels around the grouped GEMM (csrc/vqdec.cu) ---------------
+ * Reference: ImageTokenizer.decode libra/models/libra/image_tokenizer.py:97-124; LFQ.indices_to_codes
+ * taming/modules/quantization/lookup_free_quantization.py:129-158; taming Decoder taming/modules/diffusionmodules/model.py
+ * :34-41 (Normalize = GroupNorm 32, eps 1e-6), :29-31 (swish), :44-60 (Upsample), :85-141 (ResnetBlock), :141-230 (AttnBlock),
+ * :474-588 (Decoder).  Activations are NHWC bf16; "padded" = the padded-row layout row(b,y,x) = (b*(H+2)+y+1)*(W+2)+x+1 in
+ * which a 3x3 / pad 1 convolution is ONE lb_gemm_grouped problem of nine K segments over nine row shifts of its input (the
+ * caller keeps W+3 guard rows before and after the buffer); pointers are to row 0 of that layout.  channels % 8 == 0. */
+/* ids [Q, tokens] (int64 token ids; `offset` is subtracted) -> codes [tokens, ld] bf16: column q*bits+d = +-1 by bit
+ * (bits-1-d) of code q (most significant first), columns >= Q*bits zero (K padding for the GEMM that follows) */
+int lb_vq_codes(const int64_t* ids, int64_t offset, int num_codebooks, int64_t tokens, int bits, void* codes, int ld, void* stream);
+/* y = GroupNorm(groups, eps, gamma, beta)(x) [then swish]; x compact or padded (interior read), y compact or padded (zero
+ * borders written).  workspace: batch * lb_vq_groupnorm_chunks(H, W) * 2 * channels floats.  Deterministic (no atomics). */
+int lb_vq_groupnorm_chunks(int height, int width);
+int lb_vq_groupnorm(const void* x, const void* gamma, const void* beta, void* y, float* workspace, int batch, int height, int width,
+                    int channels, int groups, float eps, int swish, int in_padded, int out_padded, void* stream);
+/* nearest-neighbour resize into the padded layout (zero borders written); src_y [out_height] / src_x [out_width]: source
+ * row / column of every output row / column (the host evaluates torch's index formula once per shape) */
+int lb_vq_upsample_nearest(const void* x, void* y, const int32_t* src_y, const int32_t* src_x, int batch, int height, int width,
+                           int channels, int out_height, int out_width, int in_padded, void* stream);
+/* compact [B*H*W, channels] (row pitch ldx) -> padded with zero borders; addend (padded, may be NULL) is added on the interior */
+int lb_vq_pad(const void* x, int64_t ldx, const void* addend, void* y, int batch, int height, int width, int channels, void* stream);
+/* padded NHWC [.., channels] -> NCHW [B, channels_out, H, W] (the first channels_out channels) */
+int lb_vq_to_nchw(const void* x, void* y, int batch, int height, int width, int channels, int channels_out, void* stream);
+/* in place over bf16 rows: x = softmax(bf16(x * scale)) (fp32 maths; AttnBlock's w_ * c**-0.5 then softmax, :207-209) */
+int lb_softmax_rows(void* x, int64_t rows, int cols, int64_t ld, float scale, void* stream);
 
 /* ---- diagnostics: single-tile tcgen05 probes (tests/test_umma_probe.py) ---- */
 int lb_probe_umma(int mode, const void* A, const void* B, float* D, int K, void* stream);

@@ -51,6 +51,9 @@ SIGNATURES = {
     "lb_attn_fwd_set_trace": (I, [P]),
     "lb_attn_bwd_prepare": (I, [P, P, P, P, P, I, I, I, I, P]),
     "lb_attn_bwd_dq": (I, [P] * 10 + [I, P, P, P, I, I, I, I, I, F, P]),
+    "lb_attn_bwd_dq_stream": (I, [P] * 10 + [I, P, P, I, I, I, P, P, P, I, I, I, I, I, F, P]),
+    "lb_attn_bwd_dq_stream_max_cta_items": (I, []),
+    "lb_attn_bwd_dq_stream_set_trace": (I, [P]),
     "lb_attn_bwd_dkv": (I, [P] * 11 + [I, P, P, P, P, P, P, I, I, I, I, I, F, P]),
     "lb_gemm_bf16": (I, [P, P, P, P, L, L, L, L, L, L, I, I, I, I, I, P]),
     "lb_gemm_grouped_workspace_bytes": (I, [P, I]),
@@ -63,6 +66,13 @@ SIGNATURES = {
     "lb_adamw_bf16": (I, [P, P, P, P, L, F, F, F, F, F, I, P]),
     "lb_adamw_bf16_scaled": (I, [P, P, P, P, L, F, F, F, F, F, I, P, P, I, P]),
     "lb_grad_clip_scale": (I, [P, L, F, P, I, P, P]),
+    "lb_vq_codes": (I, [P, L, I, L, I, P, I, P]),
+    "lb_vq_groupnorm_chunks": (I, [I, I]),
+    "lb_vq_groupnorm": (I, [P, P, P, P, P, I, I, I, I, I, F, I, I, I, P]),
+    "lb_vq_upsample_nearest": (I, [P, P, P, P, I, I, I, I, I, I, I, P]),
+    "lb_vq_pad": (I, [P, L, P, P, I, I, I, I, P]),
+    "lb_vq_to_nchw": (I, [P, P, I, I, I, I, I, P]),
+    "lb_softmax_rows": (I, [P, L, I, L, F, P]),
 }
 
 _lib = None
@@ -108,7 +118,7 @@ KERNELS_PER_CALL = {
     "lb_rmsnorm_fwd": 1, "lb_rmsnorm_bwd": 2, "lb_layernorm_fwd": 1, "lb_layernorm_bwd": 2, "lb_swiglu_fwd": 1,
     "lb_swiglu_bwd": 1, "lb_bias_quick_gelu_fwd": 1, "lb_bias_quick_gelu_bwd": 1, "lb_gather_rows": 1,
     "lb_embed_lang_fwd": 1, "lb_embed_vision_cat_fwd": 3, "lb_embed_bwd": 1, "lb_lfq_pack": 1, "lb_lfq_unpack": 1,
-    "lb_attn_prep_fwd": 1, "lb_attn_prep_bwd": 1, "lb_attn_fwd": 1, "lb_attn_fwd_stream": 1, "lb_attn_bwd_prepare": 1, "lb_attn_bwd_dq": 1,
+    "lb_attn_prep_fwd": 1, "lb_attn_prep_bwd": 1, "lb_attn_fwd": 1, "lb_attn_fwd_stream": 1, "lb_attn_bwd_prepare": 1, "lb_attn_bwd_dq": 1, "lb_attn_bwd_dq_stream": 1,
     "lb_attn_bwd_dkv": 1, "lb_attn_decode": 2, "lb_gemm_bf16": 1, "lb_gemm_grouped": 1, "lb_patch_embed_fwd": 1, "lb_patch_embed_pack_weight": 1, "lb_cross_entropy_fwd_bwd": 1, "lb_probe_umma": 1, "lb_adamw_bf16": 1, "lb_adamw_bf16_scaled": 1, "lb_grad_clip_scale": 2,
 }
 launch_counts: dict = {}

@@ -44,29 +44,33 @@ struct AttnBwdParams {
 template <bool MASK, bool CAUSAL>
 __device__ __forceinline__ void dkv_tile(uint32_t ts, uint32_t tdp, uint32_t st_s, float sl2, float scale, int kj,
                                          int qbase, bool key_ok) {
-    // st_s: shared-window address of this thread's 32 lse2 values; the 32 deltas sit 512 bytes further (LDS.128 instead of
-    // one generic load per column)
+    // st_s: shared-window address of this thread's 32 values of -lse2 (-inf on excluded query rows); the 32 values of
+    // -delta*scale sit 512 bytes further (LDS.128 instead of one generic load per column).  Packed fp32x2 arithmetic: per PAIR
+    // of query columns FFMA2 (exponent), 2 x MUFU.EX2, FFMA2 (dP*scale - delta*scale), FMUL2, two bf16x2 packs.
     uint32_t s[32], dp[32];
     tmem_ld32(ts, s);
     tmem_ld32(tdp, dp);
     tc_wait_ld();
+    const uint64_t sl2_2 = f32x2(sl2, sl2), sc_2 = f32x2(scale, scale);
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
         float4 ls, dl;
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(ls.x), "=f"(ls.y), "=f"(ls.z), "=f"(ls.w) : "r"(st_s + j * 4));
         asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(dl.x), "=f"(dl.y), "=f"(dl.z), "=f"(dl.w) : "r"(st_s + 512 + j * 4));
-        const float lse4[4] = {ls.x, ls.y, ls.z, ls.w}, dl4[4] = {dl.x, dl.y, dl.z, dl.w};
+        const uint64_t nlse[2] = {f32x2(ls.x, ls.y), f32x2(ls.z, ls.w)}, nds[2] = {f32x2(dl.x, dl.y), f32x2(dl.z, dl.w)};
 #pragma unroll
         for (int u = 0; u < 4; u += 2) {
-            float p0 = fast_ex2(fmaf(__uint_as_float(s[j + u]), sl2, -lse4[u]));          // lse = +inf on excluded query rows
-            float p1 = fast_ex2(fmaf(__uint_as_float(s[j + u + 1]), sl2, -lse4[u + 1]));
+            float x0, x1;
+            f32x2_unpack(fma_f32x2(f32x2(__uint_as_float(s[j + u]), __uint_as_float(s[j + u + 1])), sl2_2, nlse[u >> 1]), x0, x1);
+            float p0 = fast_ex2(x0), p1 = fast_ex2(x1);
             if (MASK) {
                 const int qa = qbase + j + u;
                 p0 = (key_ok && (!CAUSAL || kj <= qa)) ? p0 : 0.f;
                 p1 = (key_ok && (!CAUSAL || kj <= qa + 1)) ? p1 : 0.f;
             }
-            const float d0 = p0 * (__uint_as_float(dp[j + u]) - dl4[u]) * scale;
-            const float d1 = p1 * (__uint_as_float(dp[j + u + 1]) - dl4[u + 1]) * scale;
+            const uint64_t t = fma_f32x2(f32x2(__uint_as_float(dp[j + u]), __uint_as_float(dp[j + u + 1])), sc_2, nds[u >> 1]);
+            float d0, d1;
+            f32x2_unpack(mul_f32x2(f32x2(p0, p1), t), d0, d1);
             s[(j + u) >> 1] = pack_bf16(p0, p1);
             dp[(j + u) >> 1] = pack_bf16(d0, d1);
         }
@@ -285,15 +289,15 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const uint32_t ph = (uint32_t)it & 1u;
             const int q0 = s_tiles[it] * 128;
             const int qhalf = q0 + half * 64;
-            // per-column statistics of this half's 64 query columns: [parity][half][lse2 x 64 | (delta at +128) x 64]
+            // per-column statistics of this half's 64 query columns: [parity][half][-lse2 x 64 | (-delta*scale at +128) x 64]
             float* sl = stats + (it & 1) * 384 + half * 64;
             if (t256 < 128) {
                 const int col = t256 & 63;
                 const int qi = qhalf + col;
                 const bool ok = qi < T && (!p.qflag || (int)p.qflag[(int64_t)b * T + (qi < T ? qi : 0)] == variant);
                 const int64_t si = ((int64_t)b * p.heads + h) * T + (qi < T ? qi : 0);
-                if (t256 < 64) sl[col] = ok ? p.lse[si] * LOG2E_F : CUDART_INF_F;
-                else           sl[128 + col] = ok ? p.delta[si] : 0.f;
+                if (t256 < 64) sl[col] = ok ? -p.lse[si] * LOG2E_F : -CUDART_INF_F;       // -lse2 (excluded rows: P = 2^-inf = 0)
+                else           sl[128 + col] = ok ? -p.delta[si] * p.scale : 0.f;         // -delta * scale
             }
             named_bar_sync(1 + half, 256);
             wait_bar(bar0 + 8 * (KV_SDP0 + half), ph);

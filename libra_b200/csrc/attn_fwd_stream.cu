@@ -194,20 +194,24 @@ __device__ __forceinline__ float mask_max(uint32_t (&v)[128], int kv0, int qi, i
 // pipes (poly_ex2), 0 = all on the SFU.  Returns the row sum.
 template <int POLY>
 __device__ __forceinline__ float exp_store(uint32_t tp, uint32_t (&v)[128], float sl2, float m_off) {
-    float l0 = 0.f, l1 = 0.f;
+    // packed fp32x2 arithmetic: per PAIR of keys one FFMA2 (exponent), two MUFU.EX2, one FADD2 (row sum), one bf16x2 pack
+    const uint64_t sl2_2 = f32x2(sl2, sl2), nm_2 = f32x2(-m_off, -m_off);
+    uint64_t l2 = f32x2(0.f, 0.f);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
 #pragma unroll
         for (int j = c * 32; j < c * 32 + 32; j += 2) {
-            const float x0 = fmaf(__uint_as_float(v[j]), sl2, -m_off), x1 = fmaf(__uint_as_float(v[j + 1]), sl2, -m_off);
+            float x0, x1;
+            f32x2_unpack(fma_f32x2(f32x2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), sl2_2, nm_2), x0, x1);
             const float p0 = (POLY > 0 && (j % POLY) == 0) ? poly_ex2(x0) : fast_ex2(x0);
             const float p1 = (POLY > 0 && ((j + 1) % POLY) == 0) ? poly_ex2(x1) : fast_ex2(x1);
-            l0 += p0;
-            l1 += p1;
+            l2 = add_f32x2(l2, f32x2(p0, p1));
             v[j >> 1] = pack_bf16(p0, p1);
         }
         tmem_st16(tp + c * 16, v + c * 16);
     }
+    float l0, l1;
+    f32x2_unpack(l2, l0, l1);
     return l0 + l1;
 }
 

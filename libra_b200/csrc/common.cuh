@@ -91,6 +91,29 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);   // .x = lo (low 16 bits), .y = hi
     return *reinterpret_cast<uint32_t*>(&v);
 }
+// packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2: one issue slot for two lanes of fp32 work; the score-tile loops of the
+// attention kernels are bound by issue slots and the SFU, so every per-element FFMA/FMUL folded into a pair counts)
+__device__ __forceinline__ uint64_t f32x2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f32x2_unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 

@@ -39,7 +39,7 @@ constexpr int GG_BM = 128;              // accumulator rows per CTA (TMEM lanes)
 constexpr int GG_BK = 64;               // K elements per ring stage (one 128 B swizzle row)
 constexpr int GG_MAXG = 24;             // output problems per launch (after merging accumulation chains)
 constexpr int GG_MAXIN = 32;            // entries of the caller's list per launch
-constexpr int GG_MAXSEG = 6;            // K segments (A_s . B_s products summed into one accumulator) per problem
+constexpr int GG_MAXSEG = 9;            // K segments (A_s . B_s products summed into one accumulator) per problem
 constexpr int GG_MAXMAPS = 112;         // tensor maps per launch
 constexpr int GG_THREADS = 224;             // warp 0 TMA, 1 MMA, 2-5 epilogue, 6 tile scheduler
 constexpr int GG_NSLOT = 4;                // claimed-tile ring between the scheduler and the other roles

@@ -32,6 +32,18 @@ def _fwd_choice(work: AttnWork, heads: int):
         return "single", work.work_q, None
     return FWD_KERNEL, work.work_q, None
 
+# dQ kernel of the attention backward: "stream" (csrc/attn_bwd_dq_stream.cu, persistent; shares the forward's plan) or "single"
+DQ_KERNEL = os.environ.get("LB_ATTN_DQ_KERNEL", "stream")
+
+
+def _dq_choice(work: AttnWork, heads: int):
+    if DQ_KERNEL == "stream":
+        plan = work.stream_plan(heads, ops.sm_count(), ops.STREAM_HEAD_GROUP)
+        if plan[3] <= ops.stream_max_cta_items():
+            return "stream", plan
+    return "single", None
+
+
 BF16 = torch.bfloat16
 
 
@@ -685,8 +697,9 @@ class BridgeAttention(torch.autograd.Function):
         Q, Kfv, Kfl, Vfv, Vfl, o, lse, tk, tv, Bk_l, Bk_v, Bv_l, Bv_v = ctx.saved_tensors
         B, T, H, D = meta.batch, meta.seqlen, meta.heads, meta.head_dim
         dO, delta = ops.attn_bwd_prepare(o, do.contiguous(), rt.inv, B, T, H, D)
+        dq_kern, dq_plan = _dq_choice(w, H)
         dQ = ops.attn_bwd_dq(Q, Kfl, Vfl, Kfv, Vfv, dO, lse, delta, rt.flag_orig, w.work_q, w.kv_start, w.kv_end, B, T, H, D,
-                             True, ctx.scale)
+                             True, ctx.scale, kernel=dq_kern, plan=dq_plan)
         dKfl, dVfl, dKfv, dVfv = ops.attn_bwd_dkv(Q, Kfl, Vfl, Kfv, Vfv, dO, lse, delta, rt.flag_orig, w.qtile_has, w.work_kv,
                                                  w.kv_start, w.kv_end, B, T, H, D, True, ctx.scale, kv_cover=w.kv_cover)
         dq, dk, dv, dkb, dvb = ops.attn_prep_bwd(dQ, dKfv, dKfl, dVfv, dVfl, rt.flag_sorted, rt.inv, meta.pos, meta.cos,
@@ -736,7 +749,9 @@ class PlainAttention(torch.autograd.Function):
         q, k, v, o, lse = ctx.saved_tensors
         dO, delta = ops.attn_bwd_prepare(o, do.contiguous(), None, B, T, H, D, want_dO_orig=False)
         dO = do.contiguous()
-        dq = ops.attn_bwd_dq(q, k, v, None, None, dO, lse, delta, None, work.work_q, None, None, B, T, H, D, False, scale)
+        dq_kern, dq_plan = _dq_choice(work, H)
+        dq = ops.attn_bwd_dq(q, k, v, None, None, dO, lse, delta, None, work.work_q, None, None, B, T, H, D, False, scale,
+                             kernel=dq_kern, plan=dq_plan)
         dk, dv, _, _ = ops.attn_bwd_dkv(q, k, v, None, None, dO, lse, delta, None, work.qtile_has, work.work_kv, None, None, B,
                                         T, H, D, False, scale, two_variants=False)
         return dq, dk, dv, None, None, None, None, None, None

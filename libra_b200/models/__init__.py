@@ -6,6 +6,7 @@ from .modeling_libra import (LibraCausalLMOutputWithPast, LibraDecoderLayer, Lib
 
 from .tokenization_libra import LibraTokenizer, SimpleTextTokenizer, VisionTokenizer
 from .modeling_clip import CLIPVisionConfig, CLIPVisionModel
+from .vq_decoder import VQDecoder
 
-__all__ = ["LibraTokenizer", "SimpleTextTokenizer", "VisionTokenizer", "CLIPVisionConfig", "CLIPVisionModel", "LibraConfig", "LibraForCausalLM", "LibraTrainWrapper", "LibraModel", "LibraDecoderLayer", "LibraLinear", "LibraPreTrainedModel",
+__all__ = ["VQDecoder", "LibraTokenizer", "SimpleTextTokenizer", "VisionTokenizer", "CLIPVisionConfig", "CLIPVisionModel", "LibraConfig", "LibraForCausalLM", "LibraTrainWrapper", "LibraModel", "LibraDecoderLayer", "LibraLinear", "LibraPreTrainedModel",
            "LibraCausalLMOutputWithPast"]

@@ -126,6 +126,30 @@ class VisionTokenizer(nn.Module):
 
     forward = encode
 
+    # ------------------------------------------------------------------ N2: ids -> pixels (image_tokenizer.py:97-124)
+    def attach_decoder(self, ddconfig: Dict, state_dict: Optional[Dict[str, torch.Tensor]] = None):
+        """Build the decode side (post_quant_conv + taming Decoder, models/vq_decoder.py) from the `ddconfig` of
+        vision_tokenizer_config.yaml; `state_dict`: VQModel checkpoint keys (decoder.*, post_quant_conv.*, quantize.project_out.*)."""
+        from .vq_decoder import VQDecoder
+        dec = VQDecoder(ddconfig, embed_dim=self.quant_conv.out_channels, codebook_size=self.codebook_size,
+                        num_codebook=self.num_codebook, token_offset=self.offset)
+        if state_dict is not None:
+            own = dec.state_dict()
+            dec.load_state_dict({k: v for k, v in state_dict.items() if k in own}, strict=True)
+        self.vq_decoder = dec.to(self.dtype).to(self.device)
+        return self.vq_decoder
+
+    @torch.no_grad()
+    def decode(self, x):
+        """ImageTokenizer.decode: token ids [Q,B,N] / [Q,N] (list or tensor, with or without <img> </img>) -> pixels."""
+        if len(x) == 0 or len(x[0]) == 0:
+            return x
+        if not isinstance(x, torch.Tensor):
+            x = torch.tensor(x, dtype=torch.long, device=self.device)
+        if getattr(self, "vq_decoder", None) is None:
+            raise RuntimeError("VisionTokenizer.decode: no decoder attached (attach_decoder(ddconfig, state_dict))")
+        return self.vq_decoder.decode_ids(x.to(self.device))
+
 
 @torch.no_grad()
 def assemble_inputs(text_ids: torch.Tensor, attention_mask: torch.Tensor, img_ph_token_id: int, image_ids: Optional[torch.Tensor],

@@ -45,7 +45,7 @@ def sm_count() -> int:
     return _SM_COUNT
 
 
-def enable_timing(names=("lb_attn_fwd", "lb_attn_fwd_stream", "lb_attn_bwd_dq", "lb_attn_bwd_dkv")):
+def enable_timing(names=("lb_attn_fwd", "lb_attn_fwd_stream", "lb_attn_bwd_dq", "lb_attn_bwd_dq_stream", "lb_attn_bwd_dkv")):
     global TIMED
     TIMED = {n: [] for n in names}
 
@@ -416,11 +416,17 @@ def attn_bwd_prepare(O, dO, row_of, batch, seqlen, heads, head_dim, want_dO_orig
 
 
 def attn_bwd_dq(Q, K0, V0, K1, V1, dO, lse, delta, qflag, work, kv_start, kv_end, batch, seqlen, heads, head_dim, causal,
-                scale):
+                scale, kernel=None, plan=None):
+    """kernel: "single" (one CTA per (item, head); the default of this low-level call) or "stream" (persistent, csrc/
+    attn_bwd_dq_stream.cu; `plan` = AttnWork.stream_plan(...) or None for the built-in snake split)."""
     dQ = torch.empty_like(Q)          # every token row belongs to exactly one (tile, variant) work item
-    _timed_call("lb_attn_bwd_dq", _p(Q), _p(K0), _p(V0), _p(K1), _p(V1), _p(dO), _p(lse), _p(delta), _p(qflag), _p(work),
-              work.shape[0], _p(kv_start), _p(kv_end), _p(dQ), batch, seqlen, heads, head_dim, int(causal), float(scale),
-              _st())
+    head = (_p(Q), _p(K0), _p(V0), _p(K1), _p(V1), _p(dO), _p(lse), _p(delta), _p(qflag), _p(work), work.shape[0])
+    tail = (_p(kv_start), _p(kv_end), _p(dQ), batch, seqlen, heads, head_dim, int(causal), float(scale), _st())
+    if (kernel or "single") == "stream":
+        items, off, n_cta, max_items = plan if plan is not None else (None, None, 0, 0)
+        _timed_call("lb_attn_bwd_dq_stream", *head, _p(items), _p(off), n_cta, max_items, STREAM_HEAD_GROUP, *tail)
+    else:
+        _timed_call("lb_attn_bwd_dq", *head, *tail)
     return dQ
 
 

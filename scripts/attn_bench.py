@@ -54,6 +54,14 @@ if "dq" in which and "dkv" in which:
     t_k = timeit(lambda: ops.attn_bwd_dkv(Q, K0, V0, K1, V1, dO, lse, delta, qf, w.qtile_has, w.work_kv, None, None, B, T, H, D, True,
                                           scale, kv_cover=(True, True)))
     print(f"dq {t_q*1e3:.0f} us | dkv {t_k*1e3:.0f} us | bwd {2.5*fl/(t_q+t_k)/1e9:.0f} TF/s (algorithmic, causal)")
+if "dqs" in which:
+    dq_ref = ops.attn_bwd_dq(Q, K0, V0, K1, V1, dO, lse, delta, qf, w.work_q, None, None, B, T, H, D, True, scale)
+    dq_new = ops.attn_bwd_dq(Q, K0, V0, K1, V1, dO, lse, delta, qf, w.work_q, None, None, B, T, H, D, True, scale, kernel="stream", plan=PLAN)
+    torch.cuda.synchronize()
+    d = (dq_new.float() - dq_ref.float()).abs()
+    print("dq stream vs single: max|d| %.3e (max|ref| %.3e), bit-identical %s" % (d.max().item(), dq_ref.float().abs().max().item(), bool(torch.equal(dq_new, dq_ref))))
+    t_s = timeit(lambda: ops.attn_bwd_dq(Q, K0, V0, K1, V1, dO, lse, delta, qf, w.work_q, None, None, B, T, H, D, True, scale, kernel="stream", plan=PLAN))
+    print(f"dq-stream {t_s*1e3:.0f} us = {1.5*fl/t_s/1e9:.0f} TF/s hardware (3 MMAs per tile)")
 if "fa2" in which:
     # informational: the flash-attn library, plain causal attention (use_bridge=False semantics)
     from libra_b200.utils.llama_flash_attn_monkey_patch import flash_attn_reference_point
