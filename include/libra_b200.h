@@ -241,6 +241,22 @@ int lb_gemm_bf16(const void* A, const void* B, void* C, const void* bias, int64_
                  int64_t ldb, int64_t ldc, int trans_a, int trans_b, int out_dtype, int accumulate, int act,
                  void* stream);
 
+/* Same operation and work list as lb_attn_bwd_dkv, persistent streaming kernel (csrc/attn_bwd_dkv_stream.cu): one CTA per SM
+ * walks its share of the (work item, head) list; K/V of the next item are loaded while the current item finishes, dK/dV leave
+ * through a dedicated staging tile and TMA stores, scores and gradients have their own issuing threads.  plan_* / n_cta /
+ * max_cta_items / head_group as for lb_attn_fwd_stream, over the work_kv list (libra_b200/schedule.py: stream_plan(which="kv")).
+ * Every kv tile that has a work item is written whole (rows beyond seqlen clipped); rows without one are not touched.
+ * lb_attn_bwd_dkv_stream_supported(): 0 when the platform's shared-memory window does not start 1024-byte aligned (the kernel's
+ * 224 KB footprint has no room for alignment slack) -- use lb_attn_bwd_dkv then. */
+int lb_attn_bwd_dkv_stream(const void* Q, const void* K0, const void* V0, const void* K1, const void* V1, const void* dO,
+                           const float* lse, const float* delta, const uint8_t* qflag, const uint8_t* qtile_has,
+                           const int32_t* work_kv, int n_work, const int32_t* plan_items, const int32_t* plan_off, int n_cta,
+                           int max_cta_items, int head_group, const int32_t* kv_start, const int32_t* kv_end, void* dK0, void* dV0,
+                           void* dK1, void* dV1, int batch, int seqlen, int heads, int head_dim, int causal, float scale,
+                           void* stream);
+int lb_attn_bwd_dkv_stream_max_cta_items(void);
+int lb_attn_bwd_dkv_stream_supported(void);
+
 /* ---- grouped persistent tcgen05 GEMM (the decoder's / ViT's / heads' dense products) ----------------------
  * Replaces every nn.Linear / F.linear product the reference sends to cuBLAS:
  *   LlamaAttention / LlamaMLP projections     libra/models/llama/modeling_llama.py:185-201

@@ -537,6 +537,8 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 int make_tmap_bf16_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                       const uint32_t* box, int swizzle128);
 
+int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t batch, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                      uint32_t box_cols = 64);      // [batch][rows][cols] view, SWIZZLE_128B, cached
 int tmap_cache_stats(int64_t* hits, int64_t* misses);      // 2-D maps are cached by (pointer, shape, pitch, box)
 
 int sm_count();

@@ -166,6 +166,41 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_
     return LB_OK;
 }
 
+// 3-D view [batch][rows][cols] of a row-major bf16 matrix [batch*rows, cols] (box = [box_rows, box_cols] of one sample,
+// SWIZZLE_128B): TMA stores clip at the END OF THE SAMPLE, which a 2-D [batch*rows, cols] map cannot do.  Cached like the 2-D maps.
+int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t batch, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                      uint32_t box_cols) {
+    TmapKey k;
+    memset(&k, 0, sizeof(k));
+    k.base = base; k.d0 = cols; k.d1 = rows; k.ld = (batch << 20) | 0x3D3D3ull | (1ull << 63); k.b0 = box_cols; k.b1 = box_rows;
+    uint64_t h = (uint64_t)(uintptr_t)base * 0x9E3779B97F4A7C15ull;
+    h ^= (rows * 0xC2B2AE3D27D4EB4Full) ^ (cols * 0x165667B19E3779F9ull) ^ (k.ld << 17) ^ ((uint64_t)box_rows << 40) ^ box_cols;
+    h ^= h >> 29;
+    const int slot = (int)(h % TMAP_CACHE);
+    {
+        std::lock_guard<std::mutex> lk(g_tmap_mu);
+        if (!g_tmap_cache) g_tmap_cache = (TmapEntry*)calloc(TMAP_CACHE, sizeof(TmapEntry));
+        TmapEntry& e = g_tmap_cache[slot];
+        if (e.valid && memcmp(&e.key, &k, sizeof(k)) == 0) {
+            *out = e.map;
+            ++g_tmap_hits;
+            return LB_OK;
+        }
+        ++g_tmap_misses;
+    }
+    uint64_t dims[3] = {cols, rows, batch};
+    uint64_t strides[2] = {cols * 2, rows * cols * 2};
+    uint32_t box[3] = {box_cols, box_rows, 1};
+    int rc = make_tmap_bf16_nd(out, base, 3, dims, strides, box, 1);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    TmapEntry& e = g_tmap_cache[slot];
+    e.key = k;
+    e.map = *out;
+    e.valid = true;
+    return LB_OK;
+}
+
 }  // namespace lb
 
 extern "C" {

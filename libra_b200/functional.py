@@ -44,6 +44,23 @@ def _dq_choice(work: AttnWork, heads: int):
     return "single", None
 
 
+# dK/dV kernel of the attention backward: "stream" (csrc/attn_bwd_dkv_stream.cu, persistent) or "single"
+DKV_KERNEL = os.environ.get("LB_ATTN_DKV_KERNEL", "stream")
+
+
+def _dkv_choice(work: AttnWork, heads: int):
+    if DKV_KERNEL == "stream" and work.kv_tiles is not None:
+        ok, max_items = ops.dkv_stream_limits()
+        if ok:
+            sms = ops.sm_count()
+            n_items = len(work.kv_tiles) * heads
+            waves = max(1, -(-n_items // (sms * max(1, max_items - 8))))          # CTAs beyond one per SM queue up behind the first wave
+            plan = work.stream_plan(heads, sms * waves, ops.STREAM_HEAD_GROUP, which="kv")
+            if plan[3] <= max_items:
+                return "stream", plan
+    return "single", None
+
+
 BF16 = torch.bfloat16
 
 
@@ -700,8 +717,10 @@ class BridgeAttention(torch.autograd.Function):
         dq_kern, dq_plan = _dq_choice(w, H)
         dQ = ops.attn_bwd_dq(Q, Kfl, Vfl, Kfv, Vfv, dO, lse, delta, rt.flag_orig, w.work_q, w.kv_start, w.kv_end, B, T, H, D,
                              True, ctx.scale, kernel=dq_kern, plan=dq_plan)
+        dkv_kern, dkv_plan = _dkv_choice(w, H)
         dKfl, dVfl, dKfv, dVfv = ops.attn_bwd_dkv(Q, Kfl, Vfl, Kfv, Vfv, dO, lse, delta, rt.flag_orig, w.qtile_has, w.work_kv,
-                                                 w.kv_start, w.kv_end, B, T, H, D, True, ctx.scale, kv_cover=w.kv_cover)
+                                                 w.kv_start, w.kv_end, B, T, H, D, True, ctx.scale, kv_cover=w.kv_cover,
+                                                 kernel=dkv_kern, plan=dkv_plan)
         dq, dk, dv, dkb, dvb = ops.attn_prep_bwd(dQ, dKfv, dKfl, dVfv, dVfl, rt.flag_sorted, rt.inv, meta.pos, meta.cos,
                                                  meta.sin, H, D)
         n = rt.n_lang
@@ -752,8 +771,9 @@ class PlainAttention(torch.autograd.Function):
         dq_kern, dq_plan = _dq_choice(work, H)
         dq = ops.attn_bwd_dq(q, k, v, None, None, dO, lse, delta, None, work.work_q, None, None, B, T, H, D, False, scale,
                              kernel=dq_kern, plan=dq_plan)
+        dkv_kern, dkv_plan = _dkv_choice(work, H)
         dk, dv, _, _ = ops.attn_bwd_dkv(q, k, v, None, None, dO, lse, delta, None, work.qtile_has, work.work_kv, None, None, B,
-                                        T, H, D, False, scale, two_variants=False)
+                                        T, H, D, False, scale, two_variants=False, kernel=dkv_kern, plan=dkv_plan)
         return dq, dk, dv, None, None, None, None, None, None
 
 

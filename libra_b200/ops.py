@@ -45,7 +45,7 @@ def sm_count() -> int:
     return _SM_COUNT
 
 
-def enable_timing(names=("lb_attn_fwd", "lb_attn_fwd_stream", "lb_attn_bwd_dq", "lb_attn_bwd_dq_stream", "lb_attn_bwd_dkv")):
+def enable_timing(names=("lb_attn_fwd", "lb_attn_fwd_stream", "lb_attn_bwd_dq", "lb_attn_bwd_dq_stream", "lb_attn_bwd_dkv", "lb_attn_bwd_dkv_stream")):
     global TIMED
     TIMED = {n: [] for n in names}
 
@@ -431,13 +431,31 @@ def attn_bwd_dq(Q, K0, V0, K1, V1, dO, lse, delta, qflag, work, kv_start, kv_end
 
 
 def attn_bwd_dkv(Q, K0, V0, K1, V1, dO, lse, delta, qflag, qtile_has, work_kv, kv_start, kv_end, batch, seqlen, heads,
-                 head_dim, causal, scale, two_variants=True, kv_cover=(False, False)):
-    """kv_cover[v]: every kv tile has a work item for variant v (host knowledge) => no zero fill needed for dK_v/dV_v."""
+                 head_dim, causal, scale, two_variants=True, kv_cover=(False, False), kernel=None, plan=None):
+    """kv_cover[v]: every kv tile has a work item for variant v (host knowledge) => no zero fill needed for dK_v/dV_v.
+    kernel: "single" (one CTA per (item, head); the default of this low-level call) or "stream" (persistent, csrc/
+    attn_bwd_dkv_stream.cu; `plan` = AttnWork.stream_plan(..., which="kv") or None for the built-in split)."""
     mk = lambda full: torch.empty_like(K0) if full else torch.zeros_like(K0)
     dK0, dV0 = mk(kv_cover[0]), mk(kv_cover[0])
     dK1 = mk(kv_cover[1]) if two_variants else None
     dV1 = mk(kv_cover[1]) if two_variants else None
-    _timed_call("lb_attn_bwd_dkv", _p(Q), _p(K0), _p(V0), _p(K1), _p(V1), _p(dO), _p(lse), _p(delta), _p(qflag),
-              _p(qtile_has), _p(work_kv), work_kv.shape[0], _p(kv_start), _p(kv_end), _p(dK0), _p(dV0), _p(dK1), _p(dV1), batch, seqlen,
-              heads, head_dim, int(causal), float(scale), _st())
+    head = (_p(Q), _p(K0), _p(V0), _p(K1), _p(V1), _p(dO), _p(lse), _p(delta), _p(qflag), _p(qtile_has), _p(work_kv), work_kv.shape[0])
+    tail = (_p(kv_start), _p(kv_end), _p(dK0), _p(dV0), _p(dK1), _p(dV1), batch, seqlen, heads, head_dim, int(causal), float(scale), _st())
+    if (kernel or "single") == "stream":
+        items, off, n_cta, max_items = plan if plan is not None else (None, None, 0, 0)
+        _timed_call("lb_attn_bwd_dkv_stream", *head, _p(items), _p(off), n_cta, max_items, STREAM_HEAD_GROUP, *tail)
+    else:
+        _timed_call("lb_attn_bwd_dkv", *head, *tail)
     return dK0, dV0, dK1, dV1
+
+
+_DKV_STREAM = None
+
+
+def dkv_stream_limits():
+    """(supported, max items per CTA) of the persistent dK/dV kernel on this device."""
+    global _DKV_STREAM
+    if _DKV_STREAM is None:
+        lib = _lib.load()
+        _DKV_STREAM = (bool(lib.lb_attn_bwd_dkv_stream_supported()), int(lib.lb_attn_bwd_dkv_stream_max_cta_items()))
+    return _DKV_STREAM

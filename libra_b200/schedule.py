@@ -51,19 +51,22 @@ class AttnWork:
     kv_cover: tuple = (False, False)   # per variant: every kv tile of every sample has a dK/dV work item
     q_tiles: Optional[list] = None           # kv tiles of every work_q item (host copy, for stream_plan)
     _plans: Optional[dict] = None
+    kv_tiles: Optional[list] = None          # q tiles of every work_kv item (host copy, for stream_plan(which="kv"))
 
-    def stream_plan(self, heads: int, n_cta: int, head_group: int = 8, overhead: float = 2.0):
+    def stream_plan(self, heads: int, n_cta: int, head_group: int = 8, overhead: float = 2.0, which: str = "q"):
         """Balanced split of the (work item, head) list over n_cta persistent CTAs (lb_attn_fwd_stream).
         Head groups are dealt in order (the K/V of one group stay L2-resident); inside a group the items go heaviest
         first to the least-loaded CTA, the load carried over from group to group.  weight = kv tiles + `overhead`
         (per-item switch cost in tile units).  Returns (plan_items [n_items], plan_off [n_cta+1] -- int32 on the work
-        list's device --, n_cta, longest per-CTA list); cached per (heads, n_cta, head_group)."""
+        list's device --, n_cta, longest per-CTA list); cached per (heads, n_cta, head_group, which).
+        which = "q": the work_q list (forward, dQ); "kv": the work_kv list (lb_attn_bwd_dkv_stream)."""
         import heapq
         if self._plans is None:
             self._plans = {}
-        key = (heads, n_cta, head_group)
+        key = (heads, n_cta, head_group, which)
+        tiles = self.q_tiles if which == "q" else self.kv_tiles
         if key not in self._plans:
-            n_work = len(self.q_tiles)
+            n_work = len(tiles)
             n_cta = max(1, min(n_cta, n_work * heads))
             loads = [(0.0, c) for c in range(n_cta)]
             heapq.heapify(loads)
@@ -75,7 +78,7 @@ class AttnWork:
                     for hh in range(gl):
                         load, c = heapq.heappop(loads)
                         per_cta[c].append(base + w * gl + hh)
-                        heapq.heappush(loads, (load + self.q_tiles[w] + overhead, c))
+                        heapq.heappush(loads, (load + tiles[w] + overhead, c))
                 base += head_group * n_work
             off = [0]
             for lst in per_cta:
@@ -127,7 +130,7 @@ def build_attn_work(vision_flag_cpu: Optional[torch.Tensor], batch: int, seqlen:
     wkv = torch.tensor([[b, kt, v, fq] for _, b, kt, v, fq in items_kv], dtype=torch.int32).reshape(-1, 4)
     to = lambda t: None if t is None else torch.as_tensor(t, dtype=torch.int32).to(device)
     return AttnWork(wq.to(device), wkv.to(device), has.to(device), to(kv_start), to(kv_end), (cover[0], cover[1]),
-                    [w for w, _, _, _ in items_q])
+                    [w for w, _, _, _ in items_q], None, [w for w, _, _, _, _ in items_kv])
 
 
 # ----------------------------------------------------------------------------- host copies of the batch layout

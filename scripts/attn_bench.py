@@ -62,6 +62,18 @@ if "dqs" in which:
     print("dq stream vs single: max|d| %.3e (max|ref| %.3e), bit-identical %s" % (d.max().item(), dq_ref.float().abs().max().item(), bool(torch.equal(dq_new, dq_ref))))
     t_s = timeit(lambda: ops.attn_bwd_dq(Q, K0, V0, K1, V1, dO, lse, delta, qf, w.work_q, None, None, B, T, H, D, True, scale, kernel="stream", plan=PLAN))
     print(f"dq-stream {t_s*1e3:.0f} us = {1.5*fl/t_s/1e9:.0f} TF/s hardware (3 MMAs per tile)")
+if "dkvs" in which:
+    ref = ops.attn_bwd_dkv(Q, K0, V0, K1, V1, dO, lse, delta, qf, w.qtile_has, w.work_kv, None, None, B, T, H, D, True, scale, kv_cover=(True, True))
+    KPLAN = w.stream_plan(H, ops.sm_count(), ops.STREAM_HEAD_GROUP, float(os.environ.get("LB_PLAN_OVERHEAD", "2.0")), which="kv")
+    print("dkv stream: supported, max items", ops.dkv_stream_limits(), "plan longest list", KPLAN[3])
+    run = lambda: ops.attn_bwd_dkv(Q, K0, V0, K1, V1, dO, lse, delta, qf, w.qtile_has, w.work_kv, None, None, B, T, H, D, True, scale,
+                                   kv_cover=(True, True), kernel="stream", plan=KPLAN)
+    new = run()
+    torch.cuda.synchronize()
+    for nm, a, b_ in zip(("dK0", "dV0", "dK1", "dV1"), new, ref):
+        print(f"dkv stream vs single {nm}: max|d| %.3e (max|ref| %.3e) identical %s" % ((a.float() - b_.float()).abs().max().item(), b_.float().abs().max().item(), bool(torch.equal(a, b_))))
+    t_s = timeit(run)
+    print(f"dkv-stream {t_s*1e3:.0f} us = {2.0*fl/t_s/1e9:.0f} TF/s hardware (4 MMAs per tile)")
 if "fa2" in which:
     # informational: the flash-attn library, plain causal attention (use_bridge=False semantics)
     from libra_b200.utils.llama_flash_attn_monkey_patch import flash_attn_reference_point

@@ -192,7 +192,10 @@ def test_vit_attention_forward(B, T, H, fwd_kernel):
     assert_close(o, want, rtol=2e-2, atol=2e-2)
 
 
-def run_bwd(c, o, lse, w, dO, causal=True):
+BWD_KERNELS = ["single", "stream"]       # one CTA per (item, head) / persistent (attn_bwd_dq_stream.cu, attn_bwd_dkv_stream.cu)
+
+
+def run_bwd(c, o, lse, w, dO, causal=True, kernel="single"):
     from libra_b200 import ops
     B, T, H, D = c["B"], c["T"], c["H"], c["D"]
     flat = lambda t: t.reshape(B * T, H * D).contiguous()
@@ -202,16 +205,23 @@ def run_bwd(c, o, lse, w, dO, causal=True):
     dO_orig, delta = ops.attn_bwd_prepare(flat(o), flat(dO), None, B, T, H, D)
     assert torch.equal(dO_orig, flat(dO))
     scale = 1.0 / math.sqrt(D)
+    qplan = kplan = None
+    if kernel == "stream":
+        assert ops.dkv_stream_limits()[0], "persistent dK/dV kernel unsupported on this device"
+        qplan = w.stream_plan(H, ops.sm_count(), ops.STREAM_HEAD_GROUP)
+        kplan = w.stream_plan(H, ops.sm_count(), ops.STREAM_HEAD_GROUP, which="kv")
     dQ = ops.attn_bwd_dq(flat(c["q"]), K0, V0, K1, V1, dO_orig, lse, delta, qflag, w.work_q, w.kv_start, w.kv_end, B, T, H, D,
-                         causal, scale)
+                         causal, scale, kernel=kernel, plan=qplan)
     dK0, dV0, dK1, dV1 = ops.attn_bwd_dkv(flat(c["q"]), K0, V0, K1, V1, dO_orig, lse, delta, qflag, w.qtile_has, w.work_kv,
-                                         w.kv_start, w.kv_end, B, T, H, D, causal, scale, two_variants=causal)
+                                         w.kv_start, w.kv_end, B, T, H, D, causal, scale, two_variants=causal, kernel=kernel,
+                                         plan=kplan)
     torch.cuda.synchronize()
     return delta, dQ, dK0, dV0, dK1, dV1
 
 
+@pytest.mark.parametrize("bwd_kernel", BWD_KERNELS)
 @pytest.mark.parametrize("case", CASES, ids=lambda c: f"B{c['B']}T{c['T']}H{c['H']}")
-def test_bridge_attention_backward(case):
+def test_bridge_attention_backward(case, bwd_kernel):
     need_gpu()
     c = make_case(case["B"], case["T"], case["H"], case["D"], 29, case["spans"], case["pad"])
     B, T, H, D = c["B"], c["T"], c["H"], c["D"]
@@ -220,7 +230,7 @@ def test_bridge_attention_backward(case):
     dO = torch.randn(B, T, H * D, device=dev, generator=g).bfloat16()
     for b in range(B):
         dO[b, c["kv_end"][b]:] = 0          # padded rows carry no gradient
-    delta, dQ, dK0, dV0, dK1, dV1 = run_bwd(c, o, lse, w, dO)
+    delta, dQ, dK0, dV0, dK1, dV1 = run_bwd(c, o, lse, w, dO, kernel=bwd_kernel)
     _, (gq, gk, gkc, gv, gvc) = oracle_out(c, grads=dO)
     hd = lambda t: t.float().view(B, T, H, D)
     want_delta = (hd(o) * hd(dO)).sum(-1).permute(0, 2, 1)
@@ -236,14 +246,15 @@ def test_bridge_attention_backward(case):
     assert_close(torch.where(fo, r(dV0), r(dV1)), gvc, rtol=3e-2, atol=3e-2, msg="dV cross")
 
 
+@pytest.mark.parametrize("bwd_kernel", BWD_KERNELS)
 @pytest.mark.parametrize("B,T,H", [(2, 577, 4), (1, 128, 2)])
-def test_vit_attention_backward(B, T, H):
+def test_vit_attention_backward(B, T, H, bwd_kernel):
     need_gpu()
     c = make_case(B, T, H, 64, 31, [], bridge=False)
     o, lse, w = run_fwd(c, causal=False)
     g = torch.Generator(device=dev).manual_seed(4)
     dO = torch.randn(B, T, H * 64, device=dev, generator=g).bfloat16()
-    delta, dQ, dK0, dV0, _, _ = run_bwd(c, o, lse, w, dO, causal=False)
+    delta, dQ, dK0, dV0, _, _ = run_bwd(c, o, lse, w, dO, causal=False, kernel=bwd_kernel)
     _, (gq, gk, _, gv, _) = oracle_out(c, causal=False, grads=dO)
     assert_close(dQ.view(B, T, -1), gq, rtol=3e-2, atol=3e-2, msg="dQ")
     assert_close(dK0.view(B, T, -1), gk, rtol=3e-2, atol=3e-2, msg="dK")
@@ -291,7 +302,8 @@ def test_full_size_properties_T4096(fwd_kernel):
     assert torch.equal(o5, o6)
 
 
-def test_backward_gradient_sum_property_T2048():
+@pytest.mark.parametrize("bwd_kernel", BWD_KERNELS)
+def test_backward_gradient_sum_property_T2048(bwd_kernel):
     """dK/dV of the two variants partition the query rows: summed they equal the gradients of a bridge-free run whose
     K/V are shared (property check at the bench shape B=2,T=2048,H=4)."""
     need_gpu()
@@ -300,12 +312,17 @@ def test_backward_gradient_sum_property_T2048():
     o, lse, w = run_fwd(c)
     g = torch.Generator(device=dev).manual_seed(5)
     dO = torch.randn(B, T, H * D, device=dev, generator=g).bfloat16()
-    _, dQ, dK0, dV0, dK1, dV1 = run_bwd(c, o, lse, w, dO)
+    _, dQ, dK0, dV0, dK1, dV1 = run_bwd(c, o, lse, w, dO, kernel=bwd_kernel)
     c2 = dict(c)
     c2["flag"] = torch.zeros_like(c["flag"])                                           # single variant
     o2, lse2, w2 = run_fwd(c2)
     assert torch.equal(o, o2)
-    _, dQ2, dK2, dV2, dK3, dV3 = run_bwd(c2, o2, lse2, w2, dO)
+    _, dQ2, dK2, dV2, dK3, dV3 = run_bwd(c2, o2, lse2, w2, dO, kernel=bwd_kernel)
+    if bwd_kernel == "stream":              # same list, same tile order: the persistent kernels agree with the per-item ones
+        _, dQs, dK0s, dV0s, dK1s, dV1s = run_bwd(c, o, lse, w, dO, kernel="single")
+        assert_close(dQ, dQs, rtol=1e-2, atol=1e-2, msg="dQ stream vs single")
+        for a, b_, nm in ((dK0, dK0s, "dK0"), (dV0, dV0s, "dV0"), (dK1, dK1s, "dK1"), (dV1, dV1s, "dV1")):
+            assert_close(a, b_, rtol=1e-2, atol=1e-2, msg=nm + " stream vs single")
     assert_close(dQ, dQ2, rtol=1e-2, atol=1e-2, msg="dQ")
     assert float(dK3.abs().max()) == 0.0 and float(dV3.abs().max()) == 0.0          # no vision queries => zero
     assert_close(dK0.float() + dK1.float(), dK2, rtol=2e-2, atol=3e-2, msg="dK sum")
