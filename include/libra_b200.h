@@ -308,6 +308,14 @@ typedef struct lb_gemm_problem {
 } lb_gemm_problem;
 int lb_gemm_grouped_workspace_bytes(const lb_gemm_problem* problems, int n);
 int lb_gemm_grouped(const lb_gemm_problem* problems, int n, void* workspace, int64_t workspace_bytes, void* stream);
+/* Skinny form for the one-token decode step (csrc/gemm_skinny.cu): the same problems with M <= 32 rows, restricted to
+ * plain x W^T products (no transposes, chains, alpha, G/U outputs, accumulation segments; epilogue NONE (+bias, +D) or SWIGLU
+ * (+D)), up to 8 per launch.  Swap-AB tcgen05 tiles of 128 output features x (16|32) tokens, split-K over enough CTAs that
+ * every SM streams weights; partial sums are added in split order by the last CTA of a tile (deterministic).
+ * workspace: lb_gemm_skinny_workspace_bytes() bytes = [64 KB tile counters | partials]; the counter region must be ZERO before
+ * the first launch (every launch leaves it zero), so one workspace serves launches with different problem lists. */
+int64_t lb_gemm_skinny_workspace_bytes(const lb_gemm_problem* problems, int n);
+int lb_gemm_skinny(const lb_gemm_problem* problems, int n, void* workspace, int64_t workspace_bytes, void* stream);
 /* encoded TMA descriptors are cached by (pointer, shape, pitch, box): counters for the "no per-call encode" check */
 int lb_gemm_tmap_cache_stats(int64_t* hits, int64_t* misses);
 

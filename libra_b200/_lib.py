@@ -61,6 +61,8 @@ SIGNATURES = {
     "lb_gemm_bf16": (I, [P, P, P, P, L, L, L, L, L, L, I, I, I, I, I, P]),
     "lb_gemm_grouped_workspace_bytes": (I, [P, I]),
     "lb_gemm_grouped": (I, [P, I, P, L, P]),
+    "lb_gemm_skinny_workspace_bytes": (L, [P, I]),
+    "lb_gemm_skinny": (I, [P, I, P, L, P]),
     "lb_gemm_tmap_cache_stats": (I, [P, P]),
     "lb_patch_embed_pack_weight": (I, [P, P, I, I, P]),
     "lb_patch_embed_fwd": (I, [P, P, P, P, P, I, I, I, I, P]),
@@ -122,7 +124,7 @@ KERNELS_PER_CALL = {
     "lb_swiglu_bwd": 1, "lb_bias_quick_gelu_fwd": 1, "lb_bias_quick_gelu_bwd": 1, "lb_gather_rows": 1,
     "lb_embed_lang_fwd": 1, "lb_embed_vision_cat_fwd": 3, "lb_embed_bwd": 1, "lb_lfq_pack": 1, "lb_lfq_unpack": 1,
     "lb_attn_prep_fwd": 1, "lb_attn_prep_bwd": 1, "lb_attn_fwd": 1, "lb_attn_fwd_stream": 1, "lb_attn_bwd_prepare": 1, "lb_attn_bwd_dq": 1, "lb_attn_bwd_dq_stream": 1,
-    "lb_attn_bwd_dkv": 1, "lb_attn_bwd_dkv_stream": 1, "lb_attn_decode": 2, "lb_gemm_bf16": 1, "lb_gemm_grouped": 1, "lb_patch_embed_fwd": 1, "lb_patch_embed_pack_weight": 1, "lb_cross_entropy_fwd_bwd": 1, "lb_probe_umma": 1, "lb_adamw_bf16": 1, "lb_adamw_bf16_scaled": 1, "lb_grad_clip_scale": 2,
+    "lb_attn_bwd_dkv": 1, "lb_attn_bwd_dkv_stream": 1, "lb_attn_decode": 2, "lb_gemm_bf16": 1, "lb_gemm_grouped": 1, "lb_gemm_skinny": 1, "lb_patch_embed_fwd": 1, "lb_patch_embed_pack_weight": 1, "lb_cross_entropy_fwd_bwd": 1, "lb_probe_umma": 1, "lb_adamw_bf16": 1, "lb_adamw_bf16_scaled": 1, "lb_grad_clip_scale": 2,
 }
 launch_counts: dict = {}
 

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "liblibra_b200.so")
-SOURCES = ["host.cu", "norms.cu", "elementwise.cu", "gemm.cu", "gemm_grouped.cu", "attn_fwd.cu", "attn_fwd_stream.cu", "attn_bwd.cu", "attn_bwd_dq_stream.cu", "attn_bwd_dkv.cu", "attn_bwd_dkv_stream.cu", "attn_decode.cu",
+SOURCES = ["host.cu", "norms.cu", "elementwise.cu", "gemm.cu", "gemm_grouped.cu", "gemm_skinny.cu", "attn_fwd.cu", "attn_fwd_stream.cu", "attn_bwd.cu", "attn_bwd_dq_stream.cu", "attn_bwd_dkv.cu", "attn_bwd_dkv_stream.cu", "attn_decode.cu",
            "patch_embed.cu", "vqdec.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

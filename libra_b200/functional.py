@@ -325,8 +325,10 @@ def routed_linear(x, n_lang, W, A, B, residual=None):
 
 
 def _fanout_forward(x, n_lang, kinds, weights, swiglu_pair=None):
-    """The forward launch of a fan-out.  Returns (outs, mids).  swiglu_pair = (i, j, act): branches i (gate) and j (up)
-    additionally produce act = silu(gate) * up for the language rows in the same tile pass (SwiGLU epilogue)."""
+    """The forward launch of a fan-out.  Returns (outs, mids).  swiglu_pair = (i, j, act, keep): branches i (gate) and j (up)
+    additionally produce act = silu(gate) * up for the language rows in the same tile pass (SwiGLU epilogue); keep = the
+    pre-activations of the language rows are stored too (backward needs them; inference does not -- and without them a
+    one-token decode step's gate|up product is a plain problem the weight-streaming kernel takes, ops.gemm_skinny)."""
     N = x.shape[0]
     nv = N - n_lang
     xl, xv = x[:n_lang], x[n_lang:]
@@ -358,9 +360,9 @@ def _fanout_forward(x, n_lang, kinds, weights, swiglu_pair=None):
     if n_lang > 0:
         skip = set()
         if swiglu_pair is not None:
-            gi, ui, act = swiglu_pair
-            L.add(G(xl, specs[gi][3], act[:n_lang], b2=specs[ui][3], epi=ops.EPI_SWIGLU, g=specs[gi][1][:n_lang],
-                    u=specs[ui][1][:n_lang]))
+            gi, ui, act, keep = swiglu_pair
+            L.add(G(xl, specs[gi][3], act[:n_lang], b2=specs[ui][3], epi=ops.EPI_SWIGLU, g=specs[gi][1][:n_lang] if keep else None,
+                    u=specs[ui][1][:n_lang] if keep else None))
             skip = {gi, ui}
         for bi, (kind, y, mid, W0, W1, W2) in enumerate(specs):
             if bi not in skip:
@@ -489,11 +491,11 @@ class RoutedGateUp(torch.autograd.Function):
     low-rank chains in the same launch, then lb_swiglu_fwd on those rows."""
 
     @staticmethod
-    def forward(ctx, x, n_lang, Wg, Ag, Bg, Wu, Au, Bu):
+    def forward(ctx, x, n_lang, keep, Wg, Ag, Bg, Wu, Au, Bu):
         N = x.shape[0]
         act = torch.empty(N, Wg.shape[0], dtype=x.dtype, device=x.device)
         weights = (Wg, Ag, Bg, Wu, Au, Bu)
-        (g, u), mids = _fanout_forward(x, n_lang, ("lin", "lin"), weights, swiglu_pair=(0, 1, act))
+        (g, u), mids = _fanout_forward(x, n_lang, ("lin", "lin"), weights, swiglu_pair=(0, 1, act, keep))
         if N - n_lang > 0:
             ops.swiglu_fwd(g[n_lang:], u[n_lang:], out=act[n_lang:])
         ctx.n_lang = n_lang
@@ -510,12 +512,15 @@ class RoutedGateUp(torch.autograd.Function):
         mids = [ms.pop(0) if pres else None for pres in ctx.mid_present]
         dg, du = ops.swiglu_bwd(dact.contiguous(), g, u)
         ng = ctx.needs_input_grad
-        dx, grads = _fanout_backward(x, ctx.n_lang, ("lin", "lin"), weights, mids, (dg, du), ng[0], ng[2:])
-        return (dx, None, *grads)
+        dx, grads = _fanout_backward(x, ctx.n_lang, ("lin", "lin"), weights, mids, (dg, du), ng[0], ng[3:])
+        return (dx, None, None, *grads)
 
 
 def routed_gate_up(x, n_lang, Wg, Ag, Bg, Wu, Au, Bu):
-    return RoutedGateUp.apply(x, n_lang, Wg, Ag, Bg, Wu, Au, Bu)
+    # the language rows' gate / up pre-activations are written only when a backward pass can follow (inside forward() the grad
+    # mode is always off, so the decision is taken here)
+    keep = torch.is_grad_enabled() and any(t.requires_grad for t in (x, Wg, Ag, Bg, Wu, Au, Bu))
+    return RoutedGateUp.apply(x, n_lang, keep, Wg, Ag, Bg, Wu, Au, Bu)
 
 
 class Linear(torch.autograd.Function):

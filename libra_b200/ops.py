@@ -289,11 +289,42 @@ def gp(a, b, c, *, ta=False, tb=False, d=None, bias=None, epi=EPI_NONE, b2=None,
 _GG_WS = {}
 
 
+SKINNY_MAX_M = 32                # rows up to which a plain x W^T product takes the weight-streaming kernel (csrc/gemm_skinny.cu)
+SKINNY = os.environ.get("LB_GEMM_SKINNY", "1") != "0"
+_SK_WS = {}
+
+
+def _skinny_ok(q) -> bool:
+    return (1 <= q.M <= SKINNY_MAX_M and not q.trans_a and not q.trans_b and q.wait_on < 0 and not q.alpha and not q.G and not q.U
+            and not (q.flags & 1) and (q.epilogue == EPI_NONE or (q.epilogue == EPI_SWIGLU and not q.bias)) and q.K % 8 == 0)
+
+
+def gemm_skinny(problems):
+    """Up to 8 plain products with M <= 32 rows per launch on the weight-streaming kernel (csrc/gemm_skinny.cu)."""
+    lib = _lib.load()
+    dev = torch.cuda.current_device()
+    key = (dev, torch.cuda.current_stream().cuda_stream)
+    for i in range(0, len(problems), 8):
+        chunk = problems[i:i + 8]
+        n = len(chunk)
+        arr = (GemmProblem * n)(*chunk)
+        need = int(lib.lb_gemm_skinny_workspace_bytes(arr, n))
+        if need < 0:
+            raise _lib.LibraB200Error(f"lb_gemm_skinny_workspace_bytes failed: {_lib.last_error()}")
+        ws = _SK_WS.get(key)
+        if ws is None or ws.numel() < need:         # zeroed once: the kernel leaves its tile counters at zero
+            ws = _SK_WS[key] = torch.zeros(max(need, 16 << 20), dtype=torch.uint8, device=f"cuda:{dev}")
+        _timed_call("lb_gemm_skinny", arr, n, _p(ws), ws.numel(), _st())
+
+
 def gemm_grouped(problems):
-    """Run up to 16 problems (see gp()) as ONE persistent tcgen05 launch on the current stream (csrc/gemm_grouped.cu)."""
+    """Run up to 16 problems (see gp()) as ONE persistent tcgen05 launch on the current stream (csrc/gemm_grouped.cu).
+    A list made only of plain products with M <= 32 rows (the one-token decode step) goes to gemm_skinny instead."""
     n = len(problems)
     if n == 0:
         return
+    if SKINNY and all(_skinny_ok(q) for q in problems):
+        return gemm_skinny(problems)
     arr = (GemmProblem * n)(*problems)
     dev = torch.cuda.current_device()
     key = (dev, torch.cuda.current_stream().cuda_stream)

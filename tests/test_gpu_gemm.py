@@ -6,10 +6,14 @@ Tolerance: the kernel and the oracle both accumulate in fp32 and round once, so 
 only: <= 1 bf16 ulp of the result (2^-8 relative) + an absolute term for cancellation.  Written here: |err| <= 2^-7 |want| +
 2^-8 * sqrt(K) * 0.05 element-wise (0.05 = scale of the random operands' products), and rel Frobenius error <= 3e-3.
 Size-independent properties at the BASELINE shapes: row-subset and column-subset invariance are BIT exact."""
+import math
+
 import pytest
 import torch
 
-from gpu_util import need_gpu, rel_err
+from gpu_util import need_gpu, rel_err, assert_close
+
+dev = "cuda"
 
 pytestmark = pytest.mark.gpu
 BF16 = torch.bfloat16
@@ -204,3 +208,56 @@ def test_tensor_map_cache_hits_in_steady_state():
     h1, m1 = ctypes.c_int64(), ctypes.c_int64()
     _lib.load().lb_gemm_tmap_cache_stats(ctypes.byref(h1), ctypes.byref(m1))
     assert m1.value == m0.value and h1.value == h0.value + 15
+
+
+# ----------------------------------------------------------------------------- skinny (decode) form
+@pytest.mark.parametrize("M,N,K", [(8, 4096, 4096), (8, 11008, 4096), (8, 4096, 11008), (1, 4096, 4096), (16, 32000, 4096),
+                                   (32, 514, 4096), (24, 1024, 2752), (5, 136, 72)])
+def test_skinny_matches_fp32_and_grouped(M, N, K):
+    """C[M<=32, N] = x W^T on the weight-streaming kernel (csrc/gemm_skinny.cu): against fp32, against the training kernel on
+    the same operands (same products, fp32 accumulation in another order), with bias and with the residual addend; run twice
+    (the split-K tile counters must come back to zero)."""
+    need_gpu()
+    from libra_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(M * 7 + N)
+    x = torch.randn(M, K, device=dev, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=dev, generator=g) / math.sqrt(K)).bfloat16()
+    bias = torch.randn((N + 7) // 8 * 8, device=dev, generator=g).bfloat16()
+    d = torch.randn(M, N, device=dev, generator=g).bfloat16()
+    ldc = (N + 7) // 8 * 8
+    want = x.float() @ w.float().t()
+    for rep in range(2):
+        c1 = torch.zeros(M, ldc, device=dev, dtype=torch.bfloat16)[:, :N]
+        c2 = torch.zeros(M, ldc, device=dev, dtype=torch.bfloat16)[:, :N]
+        ops.gemm_skinny([ops.gp(x, w, c1), ops.gp(x, w, c2, bias=bias, d=d)])
+        assert_close(c1, want, rtol=1e-2, atol=1e-2, msg=f"plain rep {rep}")
+        want2 = (want + bias[:N].float()).bfloat16().float() + d.float()
+        assert_close(c2, want2, rtol=1e-2, atol=2e-2, msg=f"bias+addend rep {rep}")
+    old = ops.SKINNY
+    try:
+        ops.SKINNY = False
+        cg = torch.zeros(M, ldc, device=dev, dtype=torch.bfloat16)[:, :N]
+        ops.gemm_grouped([ops.gp(x, w, cg)])
+    finally:
+        ops.SKINNY = old
+    assert_close(c1, cg, rtol=1e-2, atol=4e-3, msg="skinny vs grouped")
+    # determinism: split-K partials are added in split order (same launch shape => same splits => same bits)
+    c3 = torch.zeros(M, ldc, device=dev, dtype=torch.bfloat16)[:, :N]
+    c4 = torch.zeros(M, ldc, device=dev, dtype=torch.bfloat16)[:, :N]
+    ops.gemm_skinny([ops.gp(x, w, c3), ops.gp(x, w, c4, bias=bias, d=d)])
+    assert torch.equal(c1, c3) and torch.equal(c2, c4)
+
+
+@pytest.mark.parametrize("M,N,K", [(8, 11008, 4096), (20, 704, 256)])
+def test_skinny_swiglu(M, N, K):
+    need_gpu()
+    from libra_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(N)
+    x = torch.randn(M, K, device=dev, generator=g).bfloat16()
+    wg = (torch.randn(N, K, device=dev, generator=g) / math.sqrt(K)).bfloat16()
+    wu = (torch.randn(N, K, device=dev, generator=g) / math.sqrt(K)).bfloat16()
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    ops.gemm_grouped([ops.gp(x, wg, out, epi=ops.EPI_SWIGLU, b2=wu)])      # dispatches to the skinny kernel (M <= 32)
+    gate, up = (x.float() @ wg.float().t()).bfloat16().float(), (x.float() @ wu.float().t()).bfloat16().float()
+    want = torch.nn.functional.silu(gate).bfloat16().float() * up
+    assert_close(out, want, rtol=2e-2, atol=1e-2)
