@@ -622,7 +622,8 @@ def main():
     _lib.reset_launch_counts()
     W.opt_events.clear()
     W.ar_events.clear()
-    ops.enable_timing(("lb_attn_fwd", "lb_attn_fwd_stream", "lb_attn_bwd_dq", "lb_attn_bwd_dq_stream", "lb_attn_bwd_dkv", "lb_gemm_grouped"))
+    ops.enable_timing(("lb_attn_fwd", "lb_attn_fwd_stream", "lb_attn_bwd_dq", "lb_attn_bwd_dq_stream", "lb_attn_bwd_dkv",
+                       "lb_attn_bwd_dkv_stream", "lb_gemm_grouped"))
     sampler = ClockSampler(local) if rank == 0 else None
     if args.cuda_profiler_range:
         torch.cuda.synchronize()
@@ -710,6 +711,7 @@ def main():
     fwd_names = {"lb_attn_fwd_stream": "attn_fwd_stream_kernel<128,causal> (bridge attention forward, persistent)",
                  "lb_attn_fwd": "attn_fwd_kernel<128,causal> (bridge attention forward)"}
     fwd_key = next((k for k in fwd_names if k in kern), None)
+    BWD_KEYS = ("lb_attn_bwd_dq", "lb_attn_bwd_dq_stream", "lb_attn_bwd_dkv", "lb_attn_bwd_dkv_stream")   # dq family, dkv family
     if fwd_key:
         t_ms = kern[fwd_key]
         ach = fl["attn_per_layer_fwd"] / (t_ms * 1e-3) / 1e12
@@ -717,9 +719,9 @@ def main():
                      "peak": peaks["tflops_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["tflops_sustained"],
                      "traffic": attn_traffic(MB, T, cfg), "avg_launch_ms": t_ms,
                      "algorithmic_flops_per_launch": fl["attn_per_layer_fwd"],
-                     "bwd_ms": {k: v for k, v in kern.items() if k in ("lb_attn_bwd_dq", "lb_attn_bwd_dq_stream", "lb_attn_bwd_dkv")},
-                     "bwd_achieved_tflops": (2.5 * fl["attn_per_layer_fwd"] / ((kern.get("lb_attn_bwd_dq", 0) + kern.get("lb_attn_bwd_dq_stream", 0) + kern.get("lb_attn_bwd_dkv", 0)) * 1e-3) / 1e12)
-                     if (kern.get("lb_attn_bwd_dq") or kern.get("lb_attn_bwd_dq_stream")) else None}
+                     "bwd_ms": {k: kern[k] for k in BWD_KEYS if k in kern},
+                     "bwd_achieved_tflops": (2.5 * fl["attn_per_layer_fwd"] / (sum(kern.get(k, 0) for k in BWD_KEYS) * 1e-3) / 1e12)
+                     if (any(k in kern for k in BWD_KEYS[:2]) and any(k in kern for k in BWD_KEYS[2:])) else None}
     model_flops_step = 3.0 * fl["total"] * n_micro
     gb = None
     if not args.no_gpu_baseline and world == 1 and not args.tiny:

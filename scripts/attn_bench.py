@@ -37,7 +37,7 @@ def timeit(fn, n=10):
 
 fl = B * 4 * T * T * H * D / 2
 # kernels to time: argv (default: the product kernels).  An experimental kernel goes in its own process.
-which = sys.argv[1:] or ["single", "dq", "dkv"]
+which = sys.argv[1:] or ["single", "stream", "dq", "dkv", "dqs", "dkvs"]
 res = {}
 if "single" in which:
     res["fwd"] = timeit(lambda: ops.attn_fwd(Q, K0, V0, K1, V1, qf, w.work_q, None, None, None, B, T, H, D, True, scale, out=o))
