@@ -72,6 +72,9 @@ def parse():
     ap.add_argument("--overlap-allreduce", type=int, default=1,
                     help="N>1: reduce the ready prefix of the flat gradient buffer in pieces during the last micro-batch's backward")
     ap.add_argument("--allreduce-min-mb", type=int, default=1024, help="smallest piece of the overlapped all-reduce, MiB")
+    ap.add_argument("--busy-trace", action="store_true",
+                    help="after the timed region run ONE more step under torch.profiler (CUDA activity) and report which share of "
+                         "the step the GPU had a kernel running, plus device time per kernel family (key 'busy'; not a bench value)")
     ap.add_argument("--cuda-profiler-range", action="store_true",
                     help="bracket the timed region with cudaProfilerStart/Stop (use with ncu --profile-from-start off)")
     return ap.parse_args()
@@ -546,6 +549,41 @@ class Workload:
         return ms, last
 
 
+def busy_trace(W) -> dict:
+    """One step under torch.profiler: the union of the kernel intervals against the step's device span (how much of the step is
+    launch gaps), and device time per kernel family.  Profiler overhead inflates the span, so this is evidence about
+    composition, never a throughput number."""
+    import collections
+    import re
+    from torch.profiler import ProfilerActivity, profile
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        W.step(False)
+        torch.cuda.synchronize()
+    evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range.end > e.time_range.start]
+    if not evs:
+        return {"error": "no CUDA events"}
+    evs.sort(key=lambda e: e.time_range.start)
+    t0, t1 = evs[0].time_range.start, max(e.time_range.end for e in evs)
+    union, cur_s, cur_e = 0.0, evs[0].time_range.start, evs[0].time_range.end
+    fam = collections.defaultdict(lambda: [0.0, 0])
+    for e in evs:
+        s_, e_ = e.time_range.start, e.time_range.end
+        if s_ > cur_e:
+            union += cur_e - cur_s
+            cur_s, cur_e = s_, e_
+        else:
+            cur_e = max(cur_e, e_)
+        name = re.sub(r"<.*", "", re.sub(r"^void ", "", e.name)).split("(")[0]
+        fam[name][0] += e_ - s_
+        fam[name][1] += 1
+    union += cur_e - cur_s
+    top = sorted(fam.items(), key=lambda kv: -kv[1][0])[:24]
+    return {"span_ms": (t1 - t0) / 1e3, "busy_ms": union / 1e3, "busy_frac": union / (t1 - t0), "kernels": len(evs),
+            "summed_kernel_ms": sum(v[0] for v in fam.values()) / 1e3,
+            "top": [{"kernel": k, "ms": v[0] / 1e3, "launches": v[1]} for k, v in top]}
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -645,6 +683,10 @@ def main():
                      "n_pieces": len(sync.pieces), "exposed_ms_per_step": sum(ex) / len(ex), "overlapped": bool(args.overlap_allreduce),
                      "note": "exposed = device time from the end of the last backward to the completion of the last piece (CUDA events); "
                              "the other pieces run under the last micro-batch's backward"}
+
+    busy = None
+    if args.busy_trace and rank == 0:
+        busy = busy_trace(W)
 
     e2e = None
     if not args.no_e2e:
@@ -749,6 +791,8 @@ def main():
         "loss": float(last_loss.item()) * world if last_loss is not None else None,      # rank 0's mean loss over its samples
         "model_tflops_per_gpu": model_flops_step / (ms / args.steps * 1e-3) / 1e12, "peak_mem_gb": mem_gb,
     }
+    if busy is not None:
+        line["busy"] = busy
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -49,6 +49,13 @@ int lb_last_error(char* buf, int n);
 /* LB_OK when the current device can run this library */
 int lb_device_check(void);
 int lb_sm_count(void);
+/* Programmatic dependent launch for the launch-bound one-token decode chain (N1: rmsnorm -> skinny GEMMs -> attention
+ * operand prologue -> decode attention -> combine -> ...; reference path modeling_libra.py:343-361, 437-491 at q_len 1).
+ * on != 0: those kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization, start their prologue (barrier
+ * init, TMEM allocation, WEIGHT streaming into shared memory) while the previous kernel of the stream drains and wait
+ * (griddepcontrol.wait) before touching activations; captured into CUDA graphs as programmatic edges.  Results are
+ * bit-identical to serial launches.  Process-wide switch; returns the previous value. */
+int lb_set_pdl(int on);
 
 /* ---- A13 LlamaRMSNorm routed by modality --------------------------------
  * libra/models/llama/modeling_llama.py:127-132, routed at

@@ -22,6 +22,7 @@ SIGNATURES = {
     "lb_last_error": (I, [c_char_p, I]),
     "lb_device_check": (I, []),
     "lb_sm_count": (I, []),
+    "lb_set_pdl": (I, [I]),
     "lb_rmsnorm_fwd": (I, [P, P, P, P, P, P, L, I, F, P]),
     "lb_rmsnorm_bwd_workspace": (L, [L, I]),
     "lb_rmsnorm_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, L, I, P]),

@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(THREADS) attn_decode_kernel(const Params p) {
     constexpr int LPK = D / 8, KPI = 32 / LPK, NB = 4, NW = THREADS / 32;      // lanes per key, keys per instruction, batch depth
     __shared__ float m_sh[NW], l_sh[NW];
     __shared__ float o_sh[NW][D];
+    pdl_wait();
     const int bh = blockIdx.x, b = bh / p.heads, h = bh - b * p.heads;
     const int C = p.heads * D;
     const int variant = p.qflag ? (int)p.qflag[b] : 0;
@@ -118,6 +119,9 @@ __global__ void __launch_bounds__(THREADS) attn_decode_kernel(const Params p) {
             acc[6] = fmaf(pr, bf16_lo(vv[i].w), acc[6]); acc[7] = fmaf(pr, bf16_hi(vv[i].w), acc[7]);
         }
     }
+    // successors of the dependent-launch chain (combine, then the o-proj GEMM, whose parked CTAs would take registers away
+    // from this bandwidth-bound kernel) may become resident only now, while this CTA merges its warps
+    pdl_trigger();
     // fold the key sub-groups of the warp (same running max in every lane)
 #pragma unroll
     for (int o = LPK; o < 32; o <<= 1) {
@@ -156,6 +160,8 @@ __global__ void __launch_bounds__(THREADS) attn_decode_kernel(const Params p) {
 
 template <int D>
 __global__ void __launch_bounds__(D) attn_decode_combine_kernel(const Params p) {
+    pdl_trigger();
+    pdl_wait();
     const int bh = blockIdx.x, b = bh / p.heads, h = bh - b * p.heads;
     const float* src = p.partial + (int64_t)bh * p.n_split * (D + 2);
     float m = -CUDART_INF_F;
@@ -202,11 +208,11 @@ extern "C" int lb_attn_decode(const void* q, const void* K0, const void* V0, con
     cudaStream_t st = (cudaStream_t)stream;
     dim3 grid((unsigned)(batch * heads), (unsigned)n_split);
     if (head_dim == 128) {
-        dec::attn_decode_kernel<128><<<grid, dec::THREADS, 0, st>>>(p);
-        dec::attn_decode_combine_kernel<128><<<batch * heads, 128, 0, st>>>(p);
+        launch_chain(dec::attn_decode_kernel<128>, grid, dim3(dec::THREADS), 0, st, p);
+        launch_chain(dec::attn_decode_combine_kernel<128>, dim3((unsigned)(batch * heads)), dim3(128), 0, st, p);
     } else {
-        dec::attn_decode_kernel<64><<<grid, dec::THREADS, 0, st>>>(p);
-        dec::attn_decode_combine_kernel<64><<<batch * heads, 64, 0, st>>>(p);
+        launch_chain(dec::attn_decode_kernel<64>, grid, dim3(dec::THREADS), 0, st, p);
+        launch_chain(dec::attn_decode_combine_kernel<64>, dim3((unsigned)(batch * heads)), dim3(64), 0, st, p);
     }
     return check_launch("attn_decode");
 }

@@ -33,6 +33,16 @@ int attn_head_group();   // heads per CTA-order group of the attention kernels (
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // ----------------------------------------------------------------------------
+// programmatic dependent launch (PDL): a kernel launched through launch_chain() with lb_set_pdl(1) may start while its
+// predecessor in the stream is still running.  Contract for every kernel launched that way: pdl_trigger() first (lets the
+// successor's CTAs be scheduled as soon as SM resources free up), then only work that does not depend on -- or overwrite
+// anything read by -- earlier kernels (barrier init, TMEM alloc, streaming WEIGHTS into smem), then pdl_wait() in every
+// thread that touches global activations / workspaces afterwards.  Both are no-ops for a normal launch.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------
 // small device helpers
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -543,5 +553,26 @@ int tmap_cache_stats(int64_t* hits, int64_t* misses);      // 2-D maps are cache
 
 int sm_count();
 int require_sm100();
+bool pdl_on();           // lb_set_pdl state (host.cu)
+
+// Launch `kern` on `st`; with PDL switched on the launch carries cudaLaunchAttributeProgrammaticStreamSerialization (also
+// under stream capture: the edge becomes a programmatic dependency of the graph).  Only for kernels that follow the
+// pdl_trigger / pdl_wait contract above.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    if (pdl_on()) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 }  // namespace lb

@@ -192,6 +192,8 @@ __global__ void __launch_bounds__(256) attn_prep_fwd_kernel(
     const float* __restrict__ sin_t, __nv_bfloat16* __restrict__ Q, __nv_bfloat16* __restrict__ Kfv,
     __nv_bfloat16* __restrict__ Kfl, __nv_bfloat16* __restrict__ Vfv, __nv_bfloat16* __restrict__ Vfl, int heads, int D,
     const int32_t* __restrict__ kv_row) {
+    pdl_trigger();
+    pdl_wait();
     const int64_t bt = blockIdx.x;
     const int64_t kr = kv_row ? (int64_t)kv_row[bt] : bt;      // row of the K/V outputs (decode: the token's slot in the KV cache)
     const int64_t s = sorted_of[bt];
@@ -719,10 +721,10 @@ int lb_attn_prep_fwd(const void* q, const void* k, const void* kc, const void* v
                    AL16(Vfv) && AL16(Vfl) && AL16(cos_t) && AL16(sin_t),
                LB_EALIGN, "attn_prep: pointers must be 16-byte aligned");
     if (n_tokens == 0) return LB_OK;
-    attn_prep_fwd_kernel<<<(unsigned)n_tokens, 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)kc, (const __nv_bfloat16*)v,
-        (const __nv_bfloat16*)vc, flag_sorted, sorted_of, pos, cos_t, sin_t, (__nv_bfloat16*)Q, (__nv_bfloat16*)Kfv,
-        (__nv_bfloat16*)Kfl, (__nv_bfloat16*)Vfv, (__nv_bfloat16*)Vfl, heads, head_dim, kv_row);
+    launch_chain(attn_prep_fwd_kernel, dim3((unsigned)n_tokens), dim3(256), 0, (cudaStream_t)stream,
+                 (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)kc, (const __nv_bfloat16*)v,
+                 (const __nv_bfloat16*)vc, flag_sorted, sorted_of, pos, cos_t, sin_t, (__nv_bfloat16*)Q, (__nv_bfloat16*)Kfv,
+                 (__nv_bfloat16*)Kfl, (__nv_bfloat16*)Vfv, (__nv_bfloat16*)Vfl, heads, head_dim, kv_row);
     return check_launch("attn_prep_fwd");
 }
 

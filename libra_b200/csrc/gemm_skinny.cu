@@ -43,6 +43,37 @@ static int target_units_x2() {
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
 __device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
+// Split-K reduction of one output row: the partials of 16 / NF4 splits are loaded together (each is an L2 round trip of ~1 us;
+// issued one split at a time, nine splits cost ~7 us of the o-proj / down-proj launches), then added in split order, so the
+// sum is the same for every launch.  Row layout of a partial: [acc (TOK) | acc2 (TOK, SwiGLU only)] fp32.
+template <int TOK, bool TWO>
+__device__ __forceinline__ void reduce_splits(const float* __restrict__ src0, int splits, float (&acc)[32], float (&acc2)[32]) {
+    constexpr int NF4 = TOK / 4 * (TWO ? 2 : 1), RB = 16 / NF4, W = TOK * (TWO ? 2 : 1);
+    for (int sp0 = 0; sp0 < splits; sp0 += RB) {
+        float4 buf[RB][NF4];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+            const float* src = src0 + (int64_t)min(sp0 + r, splits - 1) * (BM * W);
+#pragma unroll
+            for (int f = 0; f < NF4; ++f) buf[r][f] = __ldcg(reinterpret_cast<const float4*>(src) + f);
+        }
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+            if (sp0 + r < splits) {
+#pragma unroll
+                for (int f = 0; f < NF4; ++f) {
+                    const float4 v = buf[r][f];
+                    if (4 * f < TOK) {
+                        acc[4 * f] += v.x; acc[4 * f + 1] += v.y; acc[4 * f + 2] += v.z; acc[4 * f + 3] += v.w;
+                    } else {
+                        acc2[4 * f - TOK] += v.x; acc2[4 * f - TOK + 1] += v.y; acc2[4 * f - TOK + 2] += v.z; acc2[4 * f - TOK + 3] += v.w;
+                    }
+                }
+            }
+        }
+    }
+}
+
 struct Prob {
     int M, N, tok;                      // tok = 16 or 32 accumulator columns (tokens padded)
     int num_kb, kb_per_split, splits, tiles_n;
@@ -64,8 +95,12 @@ struct Params {
 };
 
 // DUAL: the launch holds at least one SwiGLU problem (stage = W | W2 | A, fewer stages); plain problems in it skip W2
-template <int STAGES, bool DUAL>
-__global__ void __launch_bounds__(THREADS, 2) gemm_skinny_kernel(const __grid_constant__ Params p) {
+// MINB: resident CTAs per SM the kernel is compiled for.  2 (five / three stages, ~105 KB): the stand-alone optimum.  3 (three /
+// two stages, <= 74 KB): a kernel's two units per SM leave one slot free, so under a programmatic dependent launch the NEXT
+// kernel's CTAs become resident while this one streams, run their prologue and fill their weight ring, and the HBM pipe does
+// not drain between the launches of the decode chain.
+template <int STAGES, bool DUAL, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) gemm_skinny_kernel(const __grid_constant__ Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int A_OFF = (DUAL ? 2 : 1) * W_BYTES;
@@ -86,6 +121,7 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_skinny_kernel(const __grid_co
     const int nkb = kb1 - kb0;                                      // >= 1 by construction
     constexpr uint32_t TMEM_COLS = 64;
 
+    pdl_trigger();
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2 * STAGES + 1; ++i) mbar_init(bars + i, 1);
         fence_barrier_init();
@@ -108,7 +144,19 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_skinny_kernel(const __grid_co
     if (warp == 0) {
         if (elect_one()) {
             const uint32_t tx = (uint32_t)((pb.dual ? 2 : 1) * W_BYTES + pb.tok * BK * 2);
-            for (int i = 0; i < nkb; ++i) {
+            // the first ring pass of WEIGHTS depends on no earlier kernel: under a programmatic dependent launch it streams
+            // while the previous kernel of the chain drains; the activations follow once that kernel's writes are visible
+            const int pre = min(nkb, STAGES);
+            for (int i = 0; i < pre; ++i) {
+                uint8_t* st = smem + i * STAGE_BYTES;
+                mbar_arrive_expect_tx(bars + i, tx);
+                tma_load_2d(st, &p.maps[pb.w_map], bars + i, (kb0 + i) * BK, tile * BM);
+                if (DUAL && pb.dual) tma_load_2d(st + W_BYTES, &p.maps[pb.w2_map], bars + i, (kb0 + i) * BK, tile * BM);
+            }
+            pdl_wait();
+            for (int i = 0; i < pre; ++i)
+                tma_load_2d(smem + i * STAGE_BYTES + A_OFF, &p.maps[pb.a_map], bars + i, (kb0 + i) * BK, 0);
+            for (int i = pre; i < nkb; ++i) {
                 const int s = i % STAGES;
                 wait_bar(bar0 + 8 * (STAGES + s), ((uint32_t)(i / STAGES) & 1u) ^ 1u);
                 uint8_t* st = smem + s * STAGE_BYTES;
@@ -143,6 +191,13 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_skinny_kernel(const __grid_co
         const int tok = pb.tok;
         wait_bar(bar0 + 8 * (2 * STAGES), 0);
         tc_fence_after_sync();
+        pdl_wait();                                                 // these threads read the addend and write C / the shared workspace
+        // the addend row of this thread's output feature, requested before the split-K round trips below (for 16 tokens; the
+        // 32-token form loads it at the end: registers)
+        float dd[16];
+        const int n = tile * BM + row;
+#pragma unroll
+        for (int m = 0; m < 16; ++m) dd[m] = (pb.D && m < pb.M && n < pb.N) ? __bfloat162float(__ldg(pb.D + (int64_t)m * pb.ldd + n)) : 0.f;
         float acc[32], acc2[32];
         {
             uint32_t r[32];
@@ -178,27 +233,15 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_skinny_kernel(const __grid_co
                 __threadfence();
 #pragma unroll
                 for (int j = 0; j < 32; ++j) acc[j] = acc2[j] = 0.f;
-                for (int sp = 0; sp < pb.splits; ++sp) {
-                    const float* src = pb.partial + (((int64_t)tile * pb.splits + sp) * BM + row) * w;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        if (j < tok) {
-                            const float4 v = __ldcg(reinterpret_cast<const float4*>(src + j));
-                            acc[j] += v.x; acc[j + 1] += v.y; acc[j + 2] += v.z; acc[j + 3] += v.w;
-                        }
-                    if (pb.dual) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            if (j < tok) {
-                                const float4 v = __ldcg(reinterpret_cast<const float4*>(src + tok + j));
-                                acc2[j] += v.x; acc2[j + 1] += v.y; acc2[j + 2] += v.z; acc2[j + 3] += v.w;
-                            }
-                    }
+                const float* src0 = pb.partial + ((int64_t)tile * pb.splits * BM + row) * w;
+                if (tok == 16) {
+                    if (pb.dual) reduce_splits<16, true>(src0, pb.splits, acc, acc2); else reduce_splits<16, false>(src0, pb.splits, acc, acc2);
+                } else {
+                    if (pb.dual) reduce_splits<32, true>(src0, pb.splits, acc, acc2); else reduce_splits<32, false>(src0, pb.splits, acc, acc2);
                 }
                 if (threadIdx.x == 64) pb.counters[tile] = 0;       // ready for the next launch
             }
         }
-        const int n = tile * BM + row;
         if (finalize && n < pb.N) {
             const float bias = pb.bias ? __bfloat162float(pb.bias[n]) : 0.f;
 #pragma unroll
@@ -212,7 +255,10 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_skinny_kernel(const __grid_co
                     } else {
                         v = round_bf16(acc[m] + bias);
                     }
-                    if (pb.D) v = round_bf16(v + __bfloat162float(pb.D[(int64_t)m * pb.ldd + n]));      // bf16(bf16(x W^T) + addend)
+                    if (pb.D) {                                                          // bf16(bf16(x W^T) + addend)
+                        const float d = m < 16 ? dd[m & 15] : __bfloat162float(__ldg(pb.D + (int64_t)m * pb.ldd + n));
+                        v = round_bf16(v + d);
+                    }
                     pb.C[(int64_t)m * pb.ldc + n] = __float2bfloat16_rn(v);
                 }
             }
@@ -227,8 +273,31 @@ __global__ void __launch_bounds__(THREADS, 2) gemm_skinny_kernel(const __grid_co
 }
 
 constexpr int STAGES_SINGLE = 5, STAGES_DUAL = 3;       // ~105 KB per CTA: two CTAs per SM, one streaming while the other starts or reduces
+constexpr int STAGES_SINGLE3 = 3, STAGES_DUAL3 = 2;     // <= 74 KB per CTA: three CTAs per SM (see MINB)
+// LB_SKINNY_SLOTS=2|3 selects the variant; default 3 when the launch is part of a dependent-launch chain, else 2
+static int slots_per_sm() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("LB_SKINNY_SLOTS");
+        v = e ? atoi(e) : 0;
+        if (v != 2 && v != 3) v = 0;
+    }
+    return v ? v : (pdl_on() ? 3 : 2);
+}
 template <int STAGES, bool DUAL>
 static constexpr int smem_bytes() { return STAGES * ((DUAL ? 2 : 1) * W_BYTES + A_BYTES) + (2 * STAGES + 1) * 8 + 16 + 1024; }
+
+template <int STAGES, bool DUAL, int MINB>
+static cudaError_t launch_variant(const Params& local, cudaStream_t st) {
+    auto kern = gemm_skinny_kernel<STAGES, DUAL, MINB>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<STAGES, DUAL>());
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    return launch_chain(kern, dim3((unsigned)local.total_units), dim3(THREADS), (size_t)smem_bytes<STAGES, DUAL>(), st, local);
+}
 
 constexpr int64_t CTR_BYTES = 64 * 1024;      // tile counters: fixed region at the start of the workspace
 
@@ -332,25 +401,13 @@ int lb_gemm_skinny(const lb_gemm_problem* problems, int n, void* workspace, int6
         any_dual |= g.dual != 0;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    if (any_dual) {
-        auto kern = sk::gemm_skinny_kernel<sk::STAGES_DUAL, true>;
-        static bool configured = false;
-        if (!configured) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, sk::smem_bytes<sk::STAGES_DUAL, true>());
-            if (e != cudaSuccess) return fail(LB_ELAUNCH, "gemm_skinny: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-            configured = true;
-        }
-        kern<<<(unsigned)local.total_units, sk::THREADS, sk::smem_bytes<sk::STAGES_DUAL, true>(), st>>>(local);
-    } else {
-        auto kern = sk::gemm_skinny_kernel<sk::STAGES_SINGLE, false>;
-        static bool configured = false;
-        if (!configured) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, sk::smem_bytes<sk::STAGES_SINGLE, false>());
-            if (e != cudaSuccess) return fail(LB_ELAUNCH, "gemm_skinny: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-            configured = true;
-        }
-        kern<<<(unsigned)local.total_units, sk::THREADS, sk::smem_bytes<sk::STAGES_SINGLE, false>(), st>>>(local);
-    }
+    const bool three = sk::slots_per_sm() == 3;
+    cudaError_t e = cudaSuccess;
+    if (any_dual && three) e = sk::launch_variant<sk::STAGES_DUAL3, true, 3>(local, st);
+    else if (any_dual) e = sk::launch_variant<sk::STAGES_DUAL, true, 2>(local, st);
+    else if (three) e = sk::launch_variant<sk::STAGES_SINGLE3, false, 3>(local, st);
+    else e = sk::launch_variant<sk::STAGES_SINGLE, false, 2>(local, st);
+    if (e != cudaSuccess) return fail(LB_ELAUNCH, "gemm_skinny: %s", cudaGetErrorString(e));
     return check_launch("gemm_skinny");
 }
 

@@ -43,6 +43,9 @@ int check_launch(const char* what) {
     return LB_OK;
 }
 
+int g_pdl = 0;
+bool pdl_on() { return g_pdl != 0; }
+
 int sm_count() {
     static int cached[64] = {0};
     int dev = 0;
@@ -206,6 +209,12 @@ int make_tmap_bf16_3d(CUtensorMap* out, const void* base, uint64_t batch, uint64
 extern "C" {
 
 int lb_version(void) { return 100; }
+
+int lb_set_pdl(int on) {
+    const int prev = lb::g_pdl;
+    lb::g_pdl = on ? 1 : 0;
+    return prev;
+}
 
 int lb_last_error(char* buf, int n) {
     if (!buf || n <= 0) return LB_EINVAL;

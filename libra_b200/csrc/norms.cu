@@ -63,6 +63,8 @@ __global__ void __launch_bounds__(NT) rmsnorm_fwd_kernel(const __nv_bfloat16* __
                                                          const uint8_t* __restrict__ flag, __nv_bfloat16* __restrict__ y,
                                                          float* __restrict__ rstd, int64_t rows, int cols, float eps) {
     __shared__ float red[16];
+    pdl_trigger();
+    pdl_wait();
     const int nvec = cols >> 3;
     for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
         const uint4* xr = reinterpret_cast<const uint4*>(x + r * cols);
@@ -389,9 +391,9 @@ int lb_rmsnorm_fwd(const void* x, const void* w_lang, const void* w_vis, const u
     if (rc) return rc;
     LB_REQUIRE(w_lang && (w_vis || !flag), LB_EINVAL, "rmsnorm_fwd: missing weight");
     if (rows == 0) return LB_OK;
-    rmsnorm_fwd_kernel<<<norm_grid(rows), NT, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)x, (const __nv_bfloat16*)w_lang, (const __nv_bfloat16*)(w_vis ? w_vis : w_lang), flag,
-        (__nv_bfloat16*)y, rstd, rows, cols, eps);
+    launch_chain(rmsnorm_fwd_kernel, dim3(norm_grid(rows)), dim3(NT), 0, (cudaStream_t)stream,
+                 (const __nv_bfloat16*)x, (const __nv_bfloat16*)w_lang, (const __nv_bfloat16*)(w_vis ? w_vis : w_lang), flag,
+                 (__nv_bfloat16*)y, rstd, rows, cols, eps);
     return check_launch("rmsnorm_fwd");
 }
 

@@ -23,6 +23,7 @@ from transformers.modeling_outputs import CausalLMOutputWithPast
 from transformers.modeling_utils import PreTrainedModel
 
 from .. import _lib
+from .. import ops
 from .. import functional as LF
 from .. import schedule
 from ..registry import registry
@@ -569,11 +570,13 @@ class LibraForCausalLM(LibraPreTrainedModel):
             cache.reserve(1)
             meta = self.model.build_decode_meta(vision_flag, attention_mask, position_ids, cache)
         try:
-            hn, _ = self.model.forward_sorted(input_ids, meta, contiguous_signal)
+            # one-token steps are a chain of ~350 short launches: let each start while its predecessor drains (lb_set_pdl)
+            with ops.pdl(past is not None):
+                hn, _ = self.model.forward_sorted(input_ids, meta, contiguous_signal)
+                cache.commit(vision_flag)
+                logits = self._materialize_logits(hn, meta)
         finally:
             meta.kv_cache = None                       # the (cached) train-path metadata must not keep the cache alive
-        cache.commit(vision_flag)
-        logits = self._materialize_logits(hn, meta)
         if past is not None:
             # a row that just consumed </img> predicts nothing: "just append a newline" (:1142-1144)
             eoi = vision_indices[:, -1] == self.max_vision_token_length - 1
@@ -585,23 +588,46 @@ class LibraForCausalLM(LibraPreTrainedModel):
 
     @torch.no_grad()
     def generate(self, input_ids, attention_mask=None, vision_indices=None, contiguous_signal=None, max_new_tokens=32,
-                 eos_token_id=None, use_cache=True, do_sample=False, cuda_graph=True, **unused):
-        """Greedy decoding with the KV cache, following the reference's generation plumbing: position_ids = cumsum(mask)-1
-        (:1204-1205), the next token's vision index = previous + 1 inside an image, 578 after </img> or on text
-        (:1273-1281), both codebook planes argmax'ed independently (modeling_libra_utils.py:263-296).  Returns the extended
-        input_ids [Q,B,T+n].  Sampling, beam search and logits processors are HF machinery outside this path.
+                 eos_token_id=None, pad_token_id=None, use_cache=True, do_sample=False, temperature=1.0, top_k=0, top_p=1.0,
+                 repetition_penalty=1.0, logits_processor=None, logits_warper=None, generator=None, cuda_graph=True,
+                 return_dict_in_generate=False, output_scores=False, num_beams=1, **unsupported):
+        """Decoding with the KV cache, following the reference's generation plumbing: position_ids = cumsum(mask)-1
+        (modeling_libra.py:1204-1205), the next token's vision index = previous + 1 inside an image, 578 after </img> or on
+        text (:1273-1281), every codebook plane selected independently -- argmax (`greedy_search`,
+        modeling_libra_utils.py:263-296) or, with do_sample=True, processors -> warpers -> softmax -> one multinomial draw
+        per plane (`sample`, :538-564) -- and finished samples padded with pad_token_id (= eos_token_id when not given, as
+        HF's generate does).  temperature / top_k / top_p / repetition_penalty are the transformers warpers
+        (libra_b200/generation.py); `logits_processor` / `logits_warper` take any callables `(input_ids[B,T], scores[B,V])`
+        (e.g. a transformers.LogitsProcessorList), applied per plane.  Returns the extended input_ids [Q,B,T+n], or a
+        GenerateOutput with return_dict_in_generate=True.  Beam search is not part of this path.
 
         cuda_graph: once every sample is generating text (a language row can only predict text ids: the vision block of its
-        logits is -inf), the one-token step -- ~800 tiny launches, launch-bound from Python -- is captured once in a CUDA
-        graph with the cache addressed through its device-side length and the argmax fed back on the device, and replayed."""
-        if do_sample:
-            raise NotImplementedError("greedy decoding only")
+        logits is -inf), the one-token step -- ~350 short launches, launch-bound from Python -- is captured once in a CUDA
+        graph with the cache addressed through its device-side length and the selected token fed back on the device, and
+        replayed.  Caller-supplied processors, a caller-supplied generator and output_scores keep the eager loop (their
+        state cannot be assumed capturable)."""
+        from .. import generation as G
+        if unsupported:
+            raise TypeError(f"generate(): unsupported arguments {sorted(unsupported)} (this path covers greedy decoding and "
+                            "sampling with the KV cache; see the docstring)")
+        if num_beams != 1:
+            raise NotImplementedError("beam search is outside this path (num_beams must be 1)")
         if vision_indices is None:
             raise ValueError("vision_indices [B,T] is required (578 on text positions), as in the reference's generate kwargs")
         if not use_cache:
             raise NotImplementedError("generate() decodes with the KV cache")
+        policy = G.SelectionPolicy(do_sample=bool(do_sample), temperature=temperature, top_k=top_k, top_p=top_p,
+                                   repetition_penalty=repetition_penalty, logits_processor=logits_processor,
+                                   logits_warper=logits_warper, generator=generator)
         Q, B, T = input_ids.shape
         dev = input_ids.device
+        eos_ids = None
+        if eos_token_id is not None:
+            eos_ids = torch.as_tensor([eos_token_id] if isinstance(eos_token_id, int) else list(eos_token_id), device=dev)
+            if pad_token_id is None:
+                pad_token_id = int(eos_ids[0])
+        graph_ok = (cuda_graph and not policy.logits_processor and not policy.logits_warper and generator is None
+                    and not output_scores)
         am = torch.ones(B, T, dtype=torch.long, device=dev) if attention_mask is None else attention_mask.to(dev).long()
         L = self.max_vision_token_length
         pos = am.cumsum(-1) - 1
@@ -611,11 +637,20 @@ class LibraForCausalLM(LibraPreTrainedModel):
         done = torch.zeros(B, dtype=torch.bool, device=dev)
         vi_last = vision_indices[:, -1]
         n_done = 0
+        all_scores = [] if output_scores else None
+
+        def result(seq, cache):
+            if not return_dict_in_generate:
+                return seq
+            return G.GenerateOutput(sequences=seq, scores=tuple(all_scores) if all_scores is not None else None,
+                                    past_key_values=cache)
+
         while n_done < max_new_tokens:
-            nxt = out.logits[:, :, -1, :].float().argmax(dim=-1)                  # [Q, B]
-            if eos_token_id is not None:
-                nxt = torch.where(done[None], torch.full_like(nxt, eos_token_id), nxt)
-                done = done | (nxt[0] == eos_token_id)
+            scores = G.process(policy, input_ids, out.logits[:, :, -1, :])
+            if all_scores is not None:
+                all_scores.append(scores)
+            nxt = G.select(policy, scores)                                        # [Q, B]
+            nxt, done = G.finish_(nxt, done, eos_ids, pad_token_id)
             input_ids = torch.cat([input_ids, nxt[:, :, None]], dim=2)
             n_done += 1
             vi_next = vi_last + 1
@@ -626,28 +661,40 @@ class LibraForCausalLM(LibraPreTrainedModel):
             vi_next = torch.where(~is_vis_tok, torch.full_like(vi_next, L), vi_next)
             vi_last = vi_next
             am = torch.cat([am, am.new_ones(B, 1)], dim=1)
-            if n_done >= max_new_tokens or (eos_token_id is not None and bool(done.all())):
+            if n_done >= max_new_tokens or (eos_ids is not None and bool(done.all())):
                 break
-            if cuda_graph and max_new_tokens - n_done >= 4 and not bool(is_vis_tok.any()):
+            if graph_ok and max_new_tokens - n_done >= 4 and not bool(is_vis_tok.any()):
                 # text from here on: replay the captured step for the remaining tokens
-                toks = self._graph_decode(out.past_key_values, nxt, am, max_new_tokens - n_done, eos_token_id, done)
-                return torch.cat([input_ids, toks], dim=2)
+                toks = self._graph_decode(out.past_key_values, nxt, am, max_new_tokens - n_done, eos_ids, done,
+                                          policy=policy, history=input_ids, pad_token_id=pad_token_id)
+                return result(torch.cat([input_ids, toks], dim=2), out.past_key_values)
             p1 = (am.cumsum(-1) - 1)[:, -1:]
             out = self.forward(input_ids=nxt[:, :, None], attention_mask=am, position_ids=p1, vision_indices=vi_next[:, None],
                                past_key_values=out.past_key_values, use_cache=True)
-        return input_ids
+        return result(input_ids, out.past_key_values)
 
     @torch.no_grad()
-    def _graph_decode(self, cache, tokens, attention_mask, n_steps: int, eos_token_id=None, done=None):
-        """Up to n_steps greedy one-token steps on language tokens, starting from `tokens` [Q,B] (already appended to the
-        sequence but not yet to the cache).  The first step runs eagerly on a side stream (torch's capture warm-up, and a real
+    def _graph_decode(self, cache, tokens, attention_mask, n_steps: int, eos_ids=None, done=None, policy=None, history=None,
+                      pad_token_id=None):
+        """Up to n_steps one-token steps on language tokens (greedy, or sampled under `policy`), starting from `tokens`
+        [Q,B] (already appended to the sequence but not yet to the cache).  `history` [Q,B,T] is the sequence so far (the
+        repetition penalty reads it; inside the graph it lives in a fixed-size buffer whose unused tail repeats each row's
+        first token, which the penalty leaves unchanged).  The first step runs eagerly on a side stream (torch's capture warm-up, and a real
         step), the second is captured, the rest are replays.  With an EOS id the finished-sample bookkeeping runs inside the
         graph (a finished sample keeps emitting EOS, as in the eager loop) and the host looks at it every 16 replays.
         Returns the generated ids [Q,B,n] (n <= n_steps)."""
+        from .. import generation as G
         from .. import schedule as _sch
         dev = tokens.device
         Q, B = tokens.shape
         cfg = self.config
+        policy = policy or G.SelectionPolicy()
+        hist = hist_pos = None
+        if policy.repetition_penalty != 1.0:
+            T0 = history.shape[2]
+            hist = history[:, :, :1].repeat(1, 1, T0 + n_steps)
+            hist[:, :, :T0] = history
+            hist_pos = torch.full((1,), T0, dtype=torch.long, device=dev)
         cache.reserve(n_steps + 1)                                   # capacity (and every address) is fixed from here on
         H = cfg.num_attention_heads
         flag = torch.zeros(B, 1, dtype=torch.bool, device=dev)
@@ -671,12 +718,15 @@ class LibraForCausalLM(LibraPreTrainedModel):
         def body():
             kv_end.copy_((cache.len_dev + 1).to(torch.int32).expand(B))
             kv_row.copy_((row0 + cache.len_dev).to(torch.int32))
-            hn, _ = self.model.forward_sorted(ids, meta, None)
-            cache.commit_device(flag)
-            nxt = self._materialize_logits(hn, meta)[:, :, -1].float().argmax(dim=-1)
-            if eos_token_id is not None:
-                nxt = torch.where(done[None], torch.full_like(nxt, eos_token_id), nxt)
-                done.logical_or_(nxt[0] == eos_token_id)
+            with ops.pdl(True):                                      # captured as programmatic edges of the graph
+                hn, _ = self.model.forward_sorted(ids, meta, None)
+                cache.commit_device(flag)
+                logits = self._materialize_logits(hn, meta)[:, :, -1]
+            nxt = G.select(policy, G.process(policy, hist if hist is not None else ids, logits))
+            G.finish_(nxt, done, eos_ids, pad_token_id)
+            if hist is not None:
+                hist.index_copy_(2, hist_pos, nxt[:, :, None])
+                hist_pos.add_(1)
             outbuf.index_copy_(2, step, nxt[:, :, None])
             ids.copy_(nxt[:, :, None])
             pos.add_(1)
@@ -699,7 +749,7 @@ class LibraForCausalLM(LibraPreTrainedModel):
                 e0.record()
                 n_first = n_run
                 while n_run < n_steps:
-                    if eos_token_id is not None and n_run % 16 == 0 and bool(done.all()):
+                    if eos_ids is not None and n_run % 16 == 0 and bool(done.all()):
                         break
                     g.replay()
                     cache.length += 1

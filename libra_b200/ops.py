@@ -45,6 +45,23 @@ def sm_count() -> int:
     return _SM_COUNT
 
 
+class pdl:
+    """Context manager: programmatic dependent launch for the one-token decode chain (lb_set_pdl; see include/libra_b200.h).
+    LB_PDL=0 in the environment keeps the launches serial (A/B runs)."""
+
+    def __init__(self, on: bool = True):
+        import os
+        self.on = bool(on) and os.environ.get("LB_PDL", "1") != "0"
+
+    def __enter__(self):
+        self.prev = int(_lib.load().lb_set_pdl(1 if self.on else 0))
+        return self
+
+    def __exit__(self, *exc):
+        _lib.load().lb_set_pdl(self.prev)
+        return False
+
+
 def enable_timing(names=("lb_attn_fwd", "lb_attn_fwd_stream", "lb_attn_bwd_dq", "lb_attn_bwd_dq_stream", "lb_attn_bwd_dkv", "lb_attn_bwd_dkv_stream")):
     global TIMED
     TIMED = {n: [] for n in names}

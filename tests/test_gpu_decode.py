@@ -165,3 +165,24 @@ def test_left_padded_batch_and_greedy_generate(golden):
         cam = torch.cat([cam, cam.new_ones(2, 1)], dim=1)
     assert (out < V).all()
     assert (out == cur).float().mean() > 0.95       # bf16 ties aside, cached and uncached greedy paths agree
+
+
+def test_decode_with_and_without_dependent_launch(golden, monkeypatch):
+    """The one-token steps run as a programmatic-dependent-launch chain (lb_set_pdl): LB_PDL=0 (serial launches) and the
+    default give the same tokens, eagerly and through the CUDA graph."""
+    need_gpu()
+    gm = golden("decoder_tiny")
+    model = _build(gm)
+    V = model.config.vocab_size
+    g = torch.Generator().manual_seed(4)
+    T = 33
+    ids = torch.randint(3, V, (3, T), generator=g)[None].repeat(2, 1, 1).to(dev)
+    vi = torch.full((3, T), 578, device=dev)
+    outs = {}
+    for pdl in ("1", "0"):
+        monkeypatch.setenv("LB_PDL", pdl)
+        for cg in (True, False):
+            outs[(pdl, cg)] = model.generate(ids, vision_indices=vi, max_new_tokens=24, cuda_graph=cg)
+    ref = outs[("0", False)]
+    for k, v in outs.items():
+        assert torch.equal(v, ref), k
