@@ -274,7 +274,9 @@ __global__ void __launch_bounds__(THREADS, MINB) gemm_skinny_kernel(const __grid
 
 constexpr int STAGES_SINGLE = 5, STAGES_DUAL = 3;       // ~105 KB per CTA: two CTAs per SM, one streaming while the other starts or reduces
 constexpr int STAGES_SINGLE3 = 3, STAGES_DUAL3 = 2;     // <= 74 KB per CTA: three CTAs per SM (see MINB)
-// LB_SKINNY_SLOTS=2|3 selects the variant; default 3 when the launch is part of a dependent-launch chain, else 2
+// LB_SKINNY_SLOTS=2|3 selects the variant; default 2.  Measured on the Libra-11B decode step (B=8, graph replay, same box):
+// serial launches 5.94 ms; dependent launches with two slots 5.58 ms; with three slots 5.93 ms (the shallower rings cost the
+// streaming phase what the earlier start gains) -- kept selectable for other shapes.
 static int slots_per_sm() {
     static int v = -1;
     if (v < 0) {
@@ -282,7 +284,7 @@ static int slots_per_sm() {
         v = e ? atoi(e) : 0;
         if (v != 2 && v != 3) v = 0;
     }
-    return v ? v : (pdl_on() ? 3 : 2);
+    return v ? v : 2;
 }
 template <int STAGES, bool DUAL>
 static constexpr int smem_bytes() { return STAGES * ((DUAL ? 2 : 1) * W_BYTES + A_BYTES) + (2 * STAGES + 1) * 8 + 16 + 1024; }
