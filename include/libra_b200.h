@@ -389,6 +389,28 @@ int lb_softmax_rows(void* x, int64_t rows, int cols, int64_t ld, float scale, vo
 /* ---- diagnostics: single-tile tcgen05 probes (tests/test_umma_probe.py) ---- */
 int lb_probe_umma(int mode, const void* A, const void* B, float* D, int K, void* stream);
 
+/* ---- N4 (second half): CLIP image preprocessing, raw uint8 RGB -> pixel_values ----------------------------------
+ * libra/data/processors/libra_processor.py:44-60 (Expand2Square), :65-111 (LibraEvalImageProcessor / LibraImageProcessor);
+ * libra/models/clip/image_processing_clip.py:124-217, 296-337 (resize shortest edge -> `size` with Pillow's antialiased
+ * BICUBIC, center crop `crop`, rescale, normalise).  Bit-exact with Pillow's 8-bit two-pass resampler (22-bit fixed point,
+ * clamp after each pass) and with the reference's float32 rounding sequence.
+ * images: DEVICE buffer of packed HWC uint8 RGB images, image i at byte offsets[i]; offsets / heights / widths / pad_rgb /
+ * mean / std are HOST arrays.  pad_to_square != 0: paste on a square canvas of colour pad_rgb first.  out: DEVICE
+ * [n_images, 3, crop, crop] LB_DT_F32 or LB_DT_BF16; out_u8 (optional, may be NULL): the uint8 image after resize + crop,
+ * [n_images, crop, crop, 3].  workspace: lb_clip_preprocess_workspace(...) bytes of device memory. */
+int64_t lb_clip_preprocess_workspace(const int32_t* heights, const int32_t* widths, int n_images, int size, int crop,
+                                     int pad_to_square);
+/* HOST only (no device needed): the fixed-point resampling table the kernels use for output indices [first_out, first_out +
+ * n_out) of an axis resized in_size -> out_size -- Pillow's precompute_coeffs + normalize_coeffs_8bpc for BICUBIC.  Writes
+ * n_out * ksize coefficients (if coeffs != NULL) and n_out * 2 bounds (first input index, taps); returns ksize (> 0) or an
+ * error code (< 0). */
+int lb_clip_resample_coeffs(int in_size, int out_size, int first_out, int n_out, int32_t* coeffs, int coeffs_capacity,
+                            int32_t* bounds);
+int lb_clip_preprocess(const uint8_t* images, const int64_t* offsets, const int32_t* heights, const int32_t* widths, int n_images,
+                       int size, int crop, int pad_to_square, const uint8_t* pad_rgb, const float* mean, const float* std,
+                       double rescale_factor, void* out, int out_dtype, uint8_t* out_u8, void* workspace, int64_t workspace_bytes,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

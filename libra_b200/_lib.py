@@ -23,6 +23,9 @@ SIGNATURES = {
     "lb_device_check": (I, []),
     "lb_sm_count": (I, []),
     "lb_set_pdl": (I, [I]),
+    "lb_clip_preprocess_workspace": (L, [P, P, I, I, I, I]),
+    "lb_clip_resample_coeffs": (I, [I, I, I, I, P, I, P]),
+    "lb_clip_preprocess": (I, [P, P, P, P, I, I, I, I, P, P, P, ctypes.c_double, P, I, P, P, L, P]),
     "lb_rmsnorm_fwd": (I, [P, P, P, P, P, P, L, I, F, P]),
     "lb_rmsnorm_bwd_workspace": (L, [L, I]),
     "lb_rmsnorm_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, L, I, P]),
@@ -126,6 +129,7 @@ KERNELS_PER_CALL = {
     "lb_embed_lang_fwd": 1, "lb_embed_vision_cat_fwd": 3, "lb_embed_bwd": 1, "lb_lfq_pack": 1, "lb_lfq_unpack": 1,
     "lb_attn_prep_fwd": 1, "lb_attn_prep_bwd": 1, "lb_attn_fwd": 1, "lb_attn_fwd_stream": 1, "lb_attn_bwd_prepare": 1, "lb_attn_bwd_dq": 1, "lb_attn_bwd_dq_stream": 1,
     "lb_attn_bwd_dkv": 1, "lb_attn_bwd_dkv_stream": 1, "lb_attn_decode": 2, "lb_gemm_bf16": 1, "lb_gemm_grouped": 1, "lb_gemm_skinny": 1, "lb_patch_embed_fwd": 1, "lb_patch_embed_pack_weight": 1, "lb_cross_entropy_fwd_bwd": 1, "lb_probe_umma": 1, "lb_adamw_bf16": 1, "lb_adamw_bf16_scaled": 1, "lb_grad_clip_scale": 2,
+    "lb_clip_preprocess": 2,
 }
 launch_counts: dict = {}
 

@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "liblibra_b200.so")
 SOURCES = ["host.cu", "norms.cu", "elementwise.cu", "gemm.cu", "gemm_grouped.cu", "gemm_skinny.cu", "attn_fwd.cu", "attn_fwd_stream.cu", "attn_bwd.cu", "attn_bwd_dq_stream.cu", "attn_bwd_dkv.cu", "attn_bwd_dkv_stream.cu", "attn_decode.cu",
-           "patch_embed.cu", "vqdec.cu"]
+           "patch_embed.cu", "vqdec.cu", "preprocess.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

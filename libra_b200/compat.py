@@ -29,7 +29,7 @@ def install(force: bool = False):
     cur = sys.modules.get("libra")
     if cur is not None and not getattr(cur, "__libra_b200_alias__", False) and not force:
         raise RuntimeError("a different `libra` package is already imported; call install(force=True) to replace it")
-    from . import models, registry as reg
+    from . import models, processors, registry as reg
     from .models import configuration_libra, modeling_clip, modeling_libra, tokenization_libra
     from transformers import CLIPImageProcessor          # the reference's image_processing_clip.py is HF's class verbatim
 
@@ -37,20 +37,28 @@ def install(force: bool = False):
                       LibraConfig=models.LibraConfig, modeling_libra=modeling_libra, tokenization_libra=tokenization_libra,
                       configuration_libra=configuration_libra)
     m_clip = _module("libra.models.clip", CLIPVisionModel=modeling_clip.CLIPVisionModel, CLIPImageProcessor=CLIPImageProcessor,
-                     CLIPVisionConfig=modeling_clip.CLIPVisionConfig, modeling_clip=modeling_clip)
+                     CLIPVisionConfig=modeling_clip.CLIPVisionConfig, modeling_clip=modeling_clip,
+                     CLIPImageProcessorCUDA=processors.CLIPImageProcessor)     # same pipeline on the GPU, bit-exact (N4)
     m_models = _module("libra.models", LibraTrainWrapper=models.LibraTrainWrapper, libra=m_libra, clip=m_clip,
                        __all__=["LibraTrainWrapper"])
     m_reg = _module("libra.common.registry", registry=reg.registry, Registry=reg.Registry)
     m_common = _module("libra.common", registry=m_reg)
-    root = _module("libra", models=m_models, common=m_common)
+    # libra/data/processors/libra_processor.py:65-111 ("libra_image", "libra_image_eval"): the GPU processors
+    m_lp = _module("libra.data.processors.libra_processor", LibraImageProcessor=processors.LibraImageProcessor,
+                   LibraEvalImageProcessor=processors.LibraEvalImageProcessor)
+    m_procs = _module("libra.data.processors", libra_processor=m_lp, LibraImageProcessor=processors.LibraImageProcessor,
+                      LibraEvalImageProcessor=processors.LibraEvalImageProcessor)
+    m_data = _module("libra.data", processors=m_procs)
+    root = _module("libra", models=m_models, common=m_common, data=m_data)
     root.__path__ = []                                    # a package: `import libra.models.libra` walks sys.modules
-    for m in (m_models, m_common):
+    for m in (m_models, m_common, m_data, m_procs):
         m.__path__ = []
     sys.modules.update({
         "libra": root, "libra.models": m_models, "libra.models.libra": m_libra, "libra.models.clip": m_clip,
         "libra.models.libra.modeling_libra": modeling_libra, "libra.models.libra.tokenization_libra": tokenization_libra,
         "libra.models.libra.configuration_libra": configuration_libra, "libra.models.clip.modeling_clip": modeling_clip,
         "libra.common": m_common, "libra.common.registry": m_reg,
+        "libra.data": m_data, "libra.data.processors": m_procs, "libra.data.processors.libra_processor": m_lp,
     })
     return root
 

@@ -4,7 +4,7 @@
 
 
 class Registry:
-    mapping = {"model_name_mapping": {}, "state": {}, "paths": {}}
+    mapping = {"model_name_mapping": {}, "processor_name_mapping": {}, "state": {}, "paths": {}}
 
     @classmethod
     def register_model(cls, name):
@@ -18,6 +18,19 @@ class Registry:
     @classmethod
     def get_model_class(cls, name):
         return cls.mapping["model_name_mapping"].get(name, None)
+
+    @classmethod
+    def register_processor(cls, name):             # libra/common/registry.py (processor half): "libra_image", "libra_image_eval"
+        def wrap(processor_cls):
+            if name in cls.mapping["processor_name_mapping"]:
+                raise KeyError("Name '{}' already registered for {}.".format(name, cls.mapping["processor_name_mapping"][name]))
+            cls.mapping["processor_name_mapping"][name] = processor_cls
+            return processor_cls
+        return wrap
+
+    @classmethod
+    def get_processor_class(cls, name):
+        return cls.mapping["processor_name_mapping"].get(name, None)
 
     @classmethod
     def list_models(cls):

@@ -254,13 +254,54 @@ def golden_norms_rope(m):
     return dict(x=x, w=w, y32=y32, ybf=ybf, q=q, k=k, q_rot=qe, k_rot=ke[0], k2_rot=ke[1])
 
 
+def golden_clip_preprocess(m):
+    """The reference's own image processors (libra/models/clip/image_processing_clip.py CLIPImageProcessor; libra/data/
+    processors/libra_processor.py:44-60 Expand2Square with the mean colour) on small synthetic uint8 images: plain and
+    padded-to-square pixel_values [3,336,336] float32.  Small sources keep the fixture small; up- and down-scaling, portrait
+    and landscape, smooth and noisy content."""
+    import importlib
+    import numpy as np
+    from PIL import Image
+    ip = importlib.import_module("libra.models.clip.image_processing_clip")
+    Expand2Square = refshim.load_reference_class("libra/data/processors/libra_processor.py", "Expand2Square",
+                                                  {"torch": torch, "Image": Image})
+    P = ip.CLIPImageProcessor(size={"shortest_edge": 336}, crop_size={"height": 336, "width": 336})
+    bg = tuple(int(x * 255) for x in P.image_mean)
+    # the processor's float32 output takes 256 values per channel (a function of the uint8 resize result): store it as the
+    # table the REFERENCE produces on a 0..255 ramp plus uint8 indices, after checking that the pair reproduces the
+    # reference's pixel_values exactly -- 0.3 MB per image instead of 1.4 MB
+    ramp = np.repeat(np.arange(256, dtype=np.uint8)[:, None, None], 3, axis=2)                      # [256, 1, 3]
+    lut = P.normalize(P.rescale(ramp, scale=P.rescale_factor), mean=P.image_mean, std=P.image_std)   # [256, 1, 3] float32
+    lut = np.ascontiguousarray(lut[:, 0, :].T).astype(np.float32)                                    # [3, 256]
+
+    def pack(pv):
+        idx = np.stack([np.abs(pv[c][..., None] - lut[c][None, None, :]).argmin(-1) for c in range(3)], -1).astype(np.uint8)
+        back = np.stack([lut[c][idx[..., c]] for c in range(3)])
+        assert np.array_equal(back, pv), "the table form must reproduce the reference output bit for bit"
+        return torch.from_numpy(idx)
+
+    rng = np.random.default_rng(5)
+    images, pv, pvs = [], [], []
+    for i, (h, w) in enumerate([(61, 90), (120, 75), (400, 523)]):
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        if i == 1:
+            yy, xx = np.mgrid[0:h, 0:w]
+            img = np.stack([yy * 255 // (h - 1), xx * 255 // (w - 1), (yy * 3 + xx * 5) % 256], -1).astype(np.uint8)
+        images.append(torch.from_numpy(img))
+        pv.append(pack(P(img, return_tensors="np")["pixel_values"][0]))
+        sq = Expand2Square(bg)(Image.fromarray(img))
+        pvs.append(pack(P(sq, return_tensors="np")["pixel_values"][0]))
+    return dict(images=images, index=pv, index_square=pvs, lut=torch.from_numpy(lut), background=list(bg))
+
+
 def main():
     m = refshim.import_reference()
     os.makedirs(OUT, exist_ok=True)
     only = sys.argv[1:]
     for name, fn in (("decoder_tiny", golden_decoder), ("decode_tiny", golden_decode), ("vq_decode_tiny", golden_vq_decode),
                      ("attention_hd128", golden_attention),
-                     ("clip_tiny", golden_clip), ("lfq", golden_lfq), ("norms_rope", golden_norms_rope)):
+                     ("clip_tiny", golden_clip), ("lfq", golden_lfq), ("norms_rope", golden_norms_rope),
+                     ("clip_preprocess", golden_clip_preprocess)):
         if only and name not in only:
             continue
         obj = fn(m)

@@ -127,6 +127,25 @@ def install() -> None:
     _installed = True
 
 
+def load_reference_class(relpath: str, class_name: str, namespace: dict):
+    """Execute ONE class definition of a reference file from the source where it lies (read at run time, never copied), for
+    modules whose unrelated top-level imports are unavailable here (libra/data/processors/libra_processor.py pulls in
+    omegaconf, torchvision and -- through the registry -- timm just to define `Expand2Square`).  `namespace` provides the
+    names the class body needs."""
+    import ast
+    if not reference_available():
+        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    path = os.path.join(REFERENCE_ROOT, relpath)
+    tree = ast.parse(open(path).read(), filename=path)
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name == class_name:
+            mod = ast.Module(body=[node], type_ignores=[])
+            ns = dict(namespace)
+            exec(compile(mod, path, "exec"), ns)
+            return ns[class_name]
+    raise KeyError(f"{class_name} not found in {relpath}")
+
+
 def import_reference():
     """Return the reference modules the oracle is validated against."""
     install()

@@ -1,0 +1,7 @@
+#!/bin/bash
+# Round-2 run d: CLIP preprocessing kernel (tests + bench), sampling generate tests
+cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_preprocess.py tests/test_gpu_decode.py -m gpu -x -q -p no:cacheprovider --timeout 300 > gpurun_out/pytest_d.log 2>&1
+echo "pytest exit=$? $(tail -n 1 gpurun_out/pytest_d.log)"; grep -E "^(FAILED|ERROR)|Error|assert" gpurun_out/pytest_d.log | head -20
+timeout 600 python scripts/preprocess_bench.py > gpurun_out/preprocess_bench.jsonl 2> gpurun_out/preprocess_bench.err; cat gpurun_out/preprocess_bench.jsonl; tail -3 gpurun_out/preprocess_bench.err

@@ -27,6 +27,9 @@ def test_compat_aliases_and_registry_in_a_clean_process():
         "cls = registry.get_model_class('libra_train_wrapper')\n"
         "assert cls is LibraTrainWrapper and cls.__module__.startswith('libra_b200'), cls\n"
         "assert m.LibraForCausalLM is LibraForCausalLM and hasattr(cls, 'from_config') and hasattr(cls, 'get_optimizer_parameters')\n"
+        "from libra.data.processors.libra_processor import LibraImageProcessor, LibraEvalImageProcessor\n"
+        "assert registry.get_processor_class('libra_image') is LibraImageProcessor\n"
+        "assert registry.get_processor_class('libra_image_eval') is LibraEvalImageProcessor\n"
         "print('ALIASES_OK')\n")
     r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=300)
     assert "ALIASES_OK" in r.stdout, r.stderr[-2000:]

@@ -186,3 +186,59 @@ def test_decode_with_and_without_dependent_launch(golden, monkeypatch):
     ref = outs[("0", False)]
     for k, v in outs.items():
         assert torch.equal(v, ref), k
+
+
+def test_sampling_processors_and_policy_in_generate(golden):
+    """generate(): the reference's `sample` loop on this path (modeling_libra_utils.py:330-635) -- built-in warpers, caller
+    processors, repetition penalty inside the captured step, plane-ordered pad/EOS rule, argument checking."""
+    need_gpu()
+    gm = golden("decoder_tiny")
+    model = _build(gm)
+    V = model.config.vocab_size
+    g = torch.Generator().manual_seed(21)
+    T = 19
+    ids = torch.randint(3, V, (2, T), generator=g)[None].repeat(2, 1, 1).to(dev)
+    vi = torch.full((2, T), 578, device=dev)
+    kw = dict(vision_indices=vi, max_new_tokens=12)
+    greedy = model.generate(ids, **kw)
+    # top_k = 1 sampling picks a maximiser of the processed scores at every step (bf16 logits tie, so the SEQUENCE may differ
+    # from argmax's first-index choice); through the CUDA graph (multinomial captured) a fixed seed reproduces the run
+    o = model.generate(ids, do_sample=True, top_k=1, return_dict_in_generate=True, output_scores=True, **kw)
+    for t, sc in enumerate(o.scores):
+        tok = o.sequences[:, :, T + t]
+        assert torch.equal(sc.gather(2, tok[:, :, None])[..., 0], sc.max(dim=-1).values), t
+        assert (torch.isfinite(sc).sum(-1) >= 1).all()
+    torch.manual_seed(5)
+    g1 = model.generate(ids, do_sample=True, temperature=0.9, **kw)
+    torch.manual_seed(5)
+    g2 = model.generate(ids, do_sample=True, temperature=0.9, **kw)
+    assert torch.equal(g1, g2)
+    # repetition penalty: the captured step (fixed-size history buffer) == the eager loop
+    a = model.generate(ids, repetition_penalty=1.7, **kw)
+    b = model.generate(ids, repetition_penalty=1.7, cuda_graph=False, **kw)
+    assert torch.equal(a, b)
+    # a seeded generator reproduces the eager sampling loop; tokens are valid text ids
+    s1 = model.generate(ids, do_sample=True, temperature=0.8, top_p=0.9, generator=torch.Generator(dev).manual_seed(3), **kw)
+    s2 = model.generate(ids, do_sample=True, temperature=0.8, top_p=0.9, generator=torch.Generator(dev).manual_seed(3), **kw)
+    assert torch.equal(s1, s2) and s1.shape == greedy.shape and int(s1[:, :, T:].max()) < V and int(s1.min()) >= 0
+    s3 = model.generate(ids, do_sample=True, temperature=1.5, **kw)          # default generator, graph path
+    assert s3.shape == greedy.shape and int(s3[:, :, T:].max()) < V
+    # a caller-supplied processor (applied per plane on [B, V] scores) forces the outcome
+    def only_seven(input_ids, scores):
+        assert input_ids.dim() == 2 and scores.dim() == 2
+        out = torch.full_like(scores, -float("inf"))
+        out[:, 7] = 0.0
+        return out
+    forced = model.generate(ids, logits_processor=[only_seven], **kw)
+    assert (forced[:, :, T:] == 7).all()
+    # EOS / pad: a finished sample is padded with pad_token_id, not EOS, when one is given
+    eos = int(greedy[0, 0, T + 3])
+    p = model.generate(ids, eos_token_id=eos, pad_token_id=0, max_new_tokens=12, vision_indices=vi, cuda_graph=False)
+    first = int((p[0, 0, T:] == eos).nonzero()[0, 0])
+    assert (p[:, 0, T + first + 1:] == 0).all()
+    out = model.generate(ids, return_dict_in_generate=True, output_scores=True, **kw)
+    assert torch.equal(out.sequences, greedy) and len(out.scores) == 12 and out.scores[0].shape == (2, 2, V + 514)
+    with pytest.raises(TypeError):
+        model.generate(ids, penalty_alpha=0.6, **kw)
+    with pytest.raises(NotImplementedError):
+        model.generate(ids, num_beams=4, **kw)
