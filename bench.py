@@ -567,20 +567,27 @@ def busy_trace(W) -> dict:
     t0, t1 = evs[0].time_range.start, max(e.time_range.end for e in evs)
     union, cur_s, cur_e = 0.0, evs[0].time_range.start, evs[0].time_range.end
     fam = collections.defaultdict(lambda: [0.0, 0])
+    short = lambda n: re.sub(r"<.*", "", re.sub(r"^void ", "", n)).split("(")[0]
+    gaps, prev_name, hist = [], short(evs[0].name), collections.Counter()
     for e in evs:
         s_, e_ = e.time_range.start, e.time_range.end
         if s_ > cur_e:
             union += cur_e - cur_s
+            gaps.append((s_ - cur_e, prev_name, short(e.name)))
+            hist["<2us" if s_ - cur_e < 2 else "<5us" if s_ - cur_e < 5 else "<20us" if s_ - cur_e < 20 else "<100us" if s_ - cur_e < 100 else ">=100us"] += s_ - cur_e
             cur_s, cur_e = s_, e_
         else:
             cur_e = max(cur_e, e_)
-        name = re.sub(r"<.*", "", re.sub(r"^void ", "", e.name)).split("(")[0]
+        prev_name = short(e.name)
+        name = short(e.name)
         fam[name][0] += e_ - s_
         fam[name][1] += 1
     union += cur_e - cur_s
     top = sorted(fam.items(), key=lambda kv: -kv[1][0])[:24]
     return {"span_ms": (t1 - t0) / 1e3, "busy_ms": union / 1e3, "busy_frac": union / (t1 - t0), "kernels": len(evs),
             "summed_kernel_ms": sum(v[0] for v in fam.values()) / 1e3,
+            "idle_ms_by_gap_length": {k: v / 1e3 for k, v in hist.items()},
+            "largest_gaps": [{"us": g, "after": a_, "before": b_} for g, a_, b_ in sorted(gaps, key=lambda t: -t[0])[:12]],
             "top": [{"kernel": k, "ms": v[0] / 1e3, "launches": v[1]} for k, v in top]}
 
 
