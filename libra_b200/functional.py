@@ -789,10 +789,11 @@ def plain_attention(q, k, v, work, batch, seqlen, heads, head_dim, scale=1.0):
 # ----------------------------------------------------------------------------- embeddings
 class EmbedLang(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, ids, table):
+    def forward(ctx, ids, table, padding_idx=None):
         ctx.save_for_backward(ids)
         ctx.shape = table.shape
         ctx.table = table                       # the parameter object (its .grad buffer may take the gradient directly)
+        ctx.padding_idx = padding_idx
         return ops.embed_lang(ids, table)
 
     @staticmethod
@@ -801,7 +802,9 @@ class EmbedLang(torch.autograd.Function):
         dt = torch.zeros(ctx.shape, dtype=torch.float32, device=dy.device)
         dy = dy.contiguous()
         ops.embed_bwd(ids, dy, 0, ctx.shape[1], dt)
-        return None, _param_grad(ctx.table, dt.to(dy.dtype))
+        if ctx.padding_idx is not None:         # nn.Embedding(padding_idx=...) never updates that row (modeling_libra.py:539)
+            dt[ctx.padding_idx].zero_()
+        return None, _param_grad(ctx.table, dt.to(dy.dtype)), None
 
 
 class EmbedVisionCat(torch.autograd.Function):

@@ -339,7 +339,7 @@ class LibraModel(LibraPreTrainedModel):
         nl = rt.n_lang
         perm = rt.perm.long()
         flat = input_ids.reshape(input_ids.shape[0], -1)
-        h_lang = LF.EmbedLang.apply(flat[0][perm[:nl]].contiguous(), self.embed_tokens.weight)
+        h_lang = LF.EmbedLang.apply(flat[0][perm[:nl]].contiguous(), self.embed_tokens.weight, self.embed_tokens.padding_idx)
         if rt.n_vis == 0:
             return h_lang
         vis_rows = perm[nl:]
@@ -426,9 +426,12 @@ class LibraForCausalLM(LibraPreTrainedModel):
         shift = torch.full_like(labels, -100)
         shift[:, :, :-1] = labels[:, :, 1:]
         ls = shift.reshape(Q, -1)[:, rt.perm.long()]                      # [Q, N] sorted rows
-        counts = (ls != -100).sum(dim=1).clamp(min=1).to(torch.float32)   # per plane
+        counts = (ls != -100).sum(dim=1).to(torch.float32)                # per plane; 0 => 0/0 = nan like CrossEntropyLoss(mean)
         lab_l = ls[0, :nl]
         bad = ((lab_l >= V) & (lab_l != -100)).any()
+        # one language-head pass serves every plane: the planes' text labels are copies of each other in the reference's
+        # pipeline (get_labels clones the repeated text ids, :1397-1411); if a caller breaks that, fail loudly (nan), not silently
+        planes_differ = (ls[1:, :nl] != ls[:1, :nl]).any() if Q > 1 else None
         S_l = LF.head_cross_entropy(hn[:nl], self.lm_head.weight, torch.where(lab_l >= V, -100, lab_l).contiguous())
         total = 0.0
         for c in range(Q):
@@ -441,7 +444,10 @@ class LibraForCausalLM(LibraPreTrainedModel):
             total = total + (S_l + S_v) / counts[c]
         loss = total / Q
         # a label outside its row's finite vocabulary block hits a -inf logit in the reference => loss = inf
-        return loss + torch.where(bad, float("inf"), 0.0).to(loss.dtype)
+        loss = loss + torch.where(bad, float("inf"), 0.0).to(loss.dtype)
+        if planes_differ is not None:
+            loss = loss + torch.where(planes_differ, float("nan"), 0.0).to(loss.dtype)
+        return loss
 
     def _materialize_logits(self, hn, meta):
         """cal_vl_logits (modeling_libra.py:1018-1052): [Q,B,T,V+Vv] with -inf outside the row's block."""
