@@ -18,9 +18,10 @@
 //     FMA, Pillow's C code on x86-64 does not), normalises them to sum 1 and quantises to 22-bit fixed point -- the same bits
 //     as Pillow's precompute_coeffs + normalize_coeffs_8bpc (host restatement below: lb_clip_resample_coeffs, tested against
 //     the oracle on the CPU); only the crop window's `crop` columns and `crop` rows get tables;
-//   pass 1 (horizontal): thread = (needed source row, crop column), 3 channels; taps read from the source row (or the
-//     canvas colour outside the pasted image); uint8 result into the workspace [rows_needed][crop][3];
-//   pass 2 (vertical):   thread = (crop row, crop column); taps walk down the workspace column (coalesced across the warp);
+//   pass 1 (horizontal): thread = crop column over 16 needed source rows, 3 channels; taps read from the source row (the
+//     canvas colour outside the pasted image enters as colour x sum of those taps); uint8 result into the workspace
+//     [rows_needed][crop][3];
+//   pass 2 (vertical):   thread = crop column over 8 crop rows; taps walk down the workspace column (coalesced across the warp);
 //     the uint8 result goes through a 3 x 256 float table (rescale in double -> float, (x - mean) / std in float: the
 //     reference's rounding sequence) and is stored planar [3][crop][crop] as fp32 or bf16.
 // HBM-bound byte work: algorithmic bytes per image = the source rows/columns the crop window touches (once) + 3 * crop^2 *
@@ -231,7 +232,7 @@ static int make_plan(const int64_t* offsets, const int32_t* heights, const int32
         pl.tmp_bytes += ((long long)d.rows_needed * crop * 3 + 255) / 256 * 256;
         if (d.rows_needed > pl.max_rows) pl.max_rows = d.rows_needed;
     }
-    LB_REQUIRE(pl.max_rows <= 65535, LB_EINVAL, "clip_preprocess: %d source rows per image exceed the grid limit", pl.max_rows);
+    LB_REQUIRE(pl.max_rows <= 65535 * 16, LB_EINVAL, "clip_preprocess: %d source rows per image exceed the grid limit", pl.max_rows);
     pl.tab_ints = ti;
     return LB_OK;
 }
@@ -257,64 +258,79 @@ __device__ __forceinline__ uint8_t clip8(int v) {
     return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
 }
 
-// pass 1: grid (ceil(crop / 128), max rows_needed, n_images), block 128
+constexpr int RPB_H = 16, RPB_V = 8;      // rows per block: a block's set-up (descriptor, bounds) is paid once per RPB rows
+
+// pass 1: grid (ceil(crop / 128), ceil(max rows_needed / RPB_H), n_images), block 128; thread = crop column, loops over rows
 __global__ void __launch_bounds__(128) resize_h_kernel(const Params p) {
     const ImgDesc d = p.desc[blockIdx.z];
-    const int r = blockIdx.y, xx = blockIdx.x * 128 + threadIdx.x;
-    if (r >= d.rows_needed || xx >= p.crop) return;
-    const int cy = d.y_first + r - d.pad_top;                     // source row of this canvas row (may lie outside)
+    const int r0 = blockIdx.y * RPB_H, xx = blockIdx.x * 128 + threadIdx.x;
+    if (r0 >= d.rows_needed || xx >= p.crop) return;
     const int32_t* b = p.tab + d.bh_off + 2 * xx;
-    const int x0 = b[0], n = b[1];
+    const int x0 = b[0] - d.pad_left, n = b[1];                   // first source column of the window (may lie on the canvas border)
     const int32_t* k = p.tab + d.kh_off + xx;                     // tap t at k[t * crop]
-    int s0, s1, s2;
-    s0 = s1 = s2 = 1 << (PRECISION_BITS - 1);
-    const bool row_in = cy >= 0 && cy < d.h;
-    const uint8_t* row = p.images + d.src_off + (long long)(row_in ? cy : 0) * d.w * 3;
-    for (int t = 0; t < n; ++t) {
-        const int cx = x0 + t - d.pad_left;
-        const int kv = __ldg(k + (long long)t * p.crop);
-        int v0 = p.bg[0], v1 = p.bg[1], v2 = p.bg[2];
-        if (row_in && cx >= 0 && cx < d.w) {
-            const uint8_t* px = row + 3 * cx;
-            v0 = __ldg(px); v1 = __ldg(px + 1); v2 = __ldg(px + 2);
+    const int r1 = min(r0 + RPB_H, d.rows_needed);
+    const int bg0 = p.bg[0], bg1 = p.bg[1], bg2 = p.bg[2];
+    // taps [t_in0, t_in1) fall on the pasted image, the others on the canvas colour
+    const int t_in0 = min(n, max(0, -x0)), t_in1 = max(t_in0, min(n, d.w - x0));
+    int kb = 0;                                                    // sum of the coefficients that see the canvas colour
+    for (int t = 0; t < t_in0; ++t) kb += __ldg(k + (long long)t * p.crop);
+    for (int t = t_in1; t < n; ++t) kb += __ldg(k + (long long)t * p.crop);
+    int kall = kb;
+    for (int t = t_in0; t < t_in1; ++t) kall += __ldg(k + (long long)t * p.crop);
+    for (int r = r0; r < r1; ++r) {
+        const int cy = d.y_first + r - d.pad_top;                 // source row of this canvas row (may lie outside)
+        int s0, s1, s2;
+        s0 = s1 = s2 = 1 << (PRECISION_BITS - 1);
+        if (cy >= 0 && cy < d.h) {
+            const uint8_t* px = p.images + d.src_off + ((long long)cy * d.w + (x0 + t_in0)) * 3;
+#pragma unroll 4
+            for (int t = t_in0; t < t_in1; ++t, px += 3) {
+                const int kv = __ldg(k + (long long)t * p.crop);
+                s0 += (int)__ldg(px) * kv; s1 += (int)__ldg(px + 1) * kv; s2 += (int)__ldg(px + 2) * kv;
+            }
+            s0 += bg0 * kb; s1 += bg1 * kb; s2 += bg2 * kb;
+        } else {
+            s0 += bg0 * kall; s1 += bg1 * kall; s2 += bg2 * kall;
         }
-        s0 += v0 * kv; s1 += v1 * kv; s2 += v2 * kv;
+        uint8_t* o = p.tmp + d.tmp_off + ((long long)r * p.crop + xx) * 3;
+        o[0] = clip8(s0); o[1] = clip8(s1); o[2] = clip8(s2);
     }
-    uint8_t* o = p.tmp + d.tmp_off + ((long long)r * p.crop + xx) * 3;
-    o[0] = clip8(s0); o[1] = clip8(s1); o[2] = clip8(s2);
 }
 
-// pass 2: grid (ceil(crop / 128), crop, n_images), block 128
+// pass 2: grid (ceil(crop / 128), ceil(crop / RPB_V), n_images), block 128; thread = crop column, loops over output rows
 __global__ void __launch_bounds__(128) resize_v_kernel(const Params p) {
     const ImgDesc d = p.desc[blockIdx.z];
-    const int yy = blockIdx.y, xx = blockIdx.x * 128 + threadIdx.x;
+    const int xx = blockIdx.x * 128 + threadIdx.x;
     if (xx >= p.crop) return;
-    const int32_t* b = p.tab + d.bv_off + 2 * yy;
-    const int y0 = b[0] - d.y_first, n = b[1];
-    const int32_t* k = p.tab + d.kv_off + (long long)yy * d.ksize_v;
-    int s0, s1, s2;
-    s0 = s1 = s2 = 1 << (PRECISION_BITS - 1);
-    const uint8_t* col = p.tmp + d.tmp_off + ((long long)y0 * p.crop + xx) * 3;
-    for (int t = 0; t < n; ++t) {
-        const int kv = __ldg(k + t);
-        const uint8_t* px = col + (long long)t * p.crop * 3;
-        s0 += (int)px[0] * kv; s1 += (int)px[1] * kv; s2 += (int)px[2] * kv;
-    }
-    const uint8_t u0 = clip8(s0), u1 = clip8(s1), u2 = clip8(s2);
     const long long plane = (long long)p.crop * p.crop;
-    const long long pix = (long long)yy * p.crop + xx;
-    const float f0 = __ldg(p.lut + u0), f1 = __ldg(p.lut + 256 + u1), f2 = __ldg(p.lut + 512 + u2);
-    const long long base = (long long)blockIdx.z * 3 * plane + pix;
-    if (p.out_bf16) {
-        __nv_bfloat16* o = (__nv_bfloat16*)p.out + base;
-        o[0] = __float2bfloat16_rn(f0); o[plane] = __float2bfloat16_rn(f1); o[2 * plane] = __float2bfloat16_rn(f2);
-    } else {
-        float* o = (float*)p.out + base;
-        o[0] = f0; o[plane] = f1; o[2 * plane] = f2;
-    }
-    if (p.out_u8) {
-        uint8_t* o = p.out_u8 + ((long long)blockIdx.z * plane + pix) * 3;
-        o[0] = u0; o[1] = u1; o[2] = u2;
+    const int y1 = min((int)(blockIdx.y + 1) * RPB_V, p.crop);
+    for (int yy = blockIdx.y * RPB_V; yy < y1; ++yy) {
+        const int32_t* b = p.tab + d.bv_off + 2 * yy;
+        const int y0 = b[0] - d.y_first, n = b[1];
+        const int32_t* k = p.tab + d.kv_off + (long long)yy * d.ksize_v;
+        int s0, s1, s2;
+        s0 = s1 = s2 = 1 << (PRECISION_BITS - 1);
+        const uint8_t* px = p.tmp + d.tmp_off + ((long long)y0 * p.crop + xx) * 3;
+#pragma unroll 4
+        for (int t = 0; t < n; ++t, px += (long long)p.crop * 3) {
+            const int kv = __ldg(k + t);
+            s0 += (int)px[0] * kv; s1 += (int)px[1] * kv; s2 += (int)px[2] * kv;
+        }
+        const uint8_t u0 = clip8(s0), u1 = clip8(s1), u2 = clip8(s2);
+        const long long pix = (long long)yy * p.crop + xx;
+        const float f0 = __ldg(p.lut + u0), f1 = __ldg(p.lut + 256 + u1), f2 = __ldg(p.lut + 512 + u2);
+        const long long base = (long long)blockIdx.z * 3 * plane + pix;
+        if (p.out_bf16) {
+            __nv_bfloat16* o = (__nv_bfloat16*)p.out + base;
+            o[0] = __float2bfloat16_rn(f0); o[plane] = __float2bfloat16_rn(f1); o[2 * plane] = __float2bfloat16_rn(f2);
+        } else {
+            float* o = (float*)p.out + base;
+            o[0] = f0; o[plane] = f1; o[2 * plane] = f2;
+        }
+        if (p.out_u8) {
+            uint8_t* o = p.out_u8 + ((long long)blockIdx.z * plane + pix) * 3;
+            o[0] = u0; o[1] = u1; o[2] = u2;
+        }
     }
 }
 
@@ -387,8 +403,8 @@ int lb_clip_preprocess(const uint8_t* images, const int64_t* offsets, const int3
     for (int c = 0; c < 3; ++c) p.bg[c] = pad_rgb ? pad_rgb[c] : 0;
     const unsigned gx = (unsigned)ceil_div(crop, 128);
     pp::tables_kernel<<<dim3(gx, 2, (unsigned)n_images), 128, 0, st>>>(p.desc, (int32_t*)((char*)workspace + L.tab_off), crop);
-    pp::resize_h_kernel<<<dim3(gx, (unsigned)pl.max_rows, (unsigned)n_images), 128, 0, st>>>(p);
-    pp::resize_v_kernel<<<dim3(gx, (unsigned)crop, (unsigned)n_images), 128, 0, st>>>(p);
+    pp::resize_h_kernel<<<dim3(gx, (unsigned)ceil_div(pl.max_rows, pp::RPB_H), (unsigned)n_images), 128, 0, st>>>(p);
+    pp::resize_v_kernel<<<dim3(gx, (unsigned)ceil_div(crop, pp::RPB_V), (unsigned)n_images), 128, 0, st>>>(p);
     return check_launch("clip_preprocess");
 }
 
