@@ -140,6 +140,16 @@ int lb_attn_prep_fwd(const void* q, const void* k, const void* kc, const void* v
                      const uint8_t* flag_sorted, const int32_t* sorted_of, const int32_t* pos, const float* cos_t,
                      const float* sin_t, void* Q, void* Kfv, void* Kfl, void* Vfv, void* Vfl, int64_t n_tokens, int heads,
                      int head_dim, const int32_t* kv_row, void* stream);
+/* The same prologue with the rank-r bridge products folded in (modeling_libra.py:310-319: kc = k + B_k(A_k x), vc likewise):
+ * tk / tv [N, rank] = x A_k^T / x A_v^T in sorted rows, B* [H*D, rank] the bridges' second factors for language / vision
+ * tokens, rank a multiple of 8.  kc = bf16(k + bf16(tk . B_k^T)) -- the rounding sequence of the GEMM epilogue.  Meant for
+ * the one-token decode step (N1), where a separate rank-8 GEMM launch costs more than its arithmetic; training keeps the
+ * GEMM (its backward needs kc / vc's producers anyway). */
+int lb_attn_prep_fwd_bridge(const void* q, const void* k, const void* v, const void* tk, const void* tv, const void* Bk_lang,
+                            const void* Bk_vis, const void* Bv_lang, const void* Bv_vis, int rank, const uint8_t* flag_sorted,
+                            const int32_t* sorted_of, const int32_t* pos, const float* cos_t, const float* sin_t, void* Q, void* Kfv,
+                            void* Kfl, void* Vfv, void* Vfl, int64_t n_tokens, int heads, int head_dim, const int32_t* kv_row,
+                            void* stream);
 /* adjoint: from dQ,dKfv,dKfl,dVfv,dVfl (original order) to dq,dk,dv,dkb,dvb (sorted rows, [N,H*D]) */
 int lb_attn_prep_bwd(const void* dQ, const void* dKfv, const void* dKfl, const void* dVfv, const void* dVfl,
                      const uint8_t* flag_sorted, const int32_t* sorted_of, const int32_t* pos, const float* cos_t,

@@ -43,6 +43,7 @@ SIGNATURES = {
     "lb_lfq_pack": (I, [P, I, L, I, I, I, L, L, L, P, P]),
     "lb_lfq_unpack": (I, [P, L, I, I, P, I, P]),
     "lb_attn_prep_fwd": (I, [P] * 15 + [L, I, I, P, P]),
+    "lb_attn_prep_fwd_bridge": (I, [P] * 9 + [I] + [P] * 10 + [L, I, I, P, P]),
     "lb_attn_prep_bwd": (I, [P] * 15 + [L, I, I, P]),
     "lb_attn_fwd": (I, [P, P, P, P, P, P, P, I, P, P, P, P, P, I, I, I, I, I, F, P]),
     "lb_attn_fwd_stream": (I, [P, P, P, P, P, P, P, I, P, P, I, I, I, P, P, P, P, P, I, I, I, I, I, F, P]),
@@ -127,7 +128,7 @@ KERNELS_PER_CALL = {
     "lb_rmsnorm_fwd": 1, "lb_rmsnorm_bwd": 2, "lb_layernorm_fwd": 1, "lb_layernorm_bwd": 2, "lb_swiglu_fwd": 1,
     "lb_swiglu_bwd": 1, "lb_bias_quick_gelu_fwd": 1, "lb_bias_quick_gelu_bwd": 1, "lb_gather_rows": 1,
     "lb_embed_lang_fwd": 1, "lb_embed_vision_cat_fwd": 3, "lb_embed_bwd": 1, "lb_lfq_pack": 1, "lb_lfq_unpack": 1,
-    "lb_attn_prep_fwd": 1, "lb_attn_prep_bwd": 1, "lb_attn_fwd": 1, "lb_attn_fwd_stream": 1, "lb_attn_bwd_prepare": 1, "lb_attn_bwd_dq": 1, "lb_attn_bwd_dq_stream": 1,
+    "lb_attn_prep_fwd": 1, "lb_attn_prep_fwd_bridge": 1, "lb_attn_prep_bwd": 1, "lb_attn_fwd": 1, "lb_attn_fwd_stream": 1, "lb_attn_bwd_prepare": 1, "lb_attn_bwd_dq": 1, "lb_attn_bwd_dq_stream": 1,
     "lb_attn_bwd_dkv": 1, "lb_attn_bwd_dkv_stream": 1, "lb_attn_decode": 2, "lb_gemm_bf16": 1, "lb_gemm_grouped": 1, "lb_gemm_skinny": 1, "lb_patch_embed_fwd": 1, "lb_patch_embed_pack_weight": 1, "lb_cross_entropy_fwd_bwd": 1, "lb_probe_umma": 1, "lb_adamw_bf16": 1, "lb_adamw_bf16_scaled": 1, "lb_grad_clip_scale": 2,
     "lb_clip_preprocess": 2,
 }

@@ -183,15 +183,54 @@ __global__ void lfq_unpack_kernel(const int64_t* __restrict__ idx, int64_t n, in
 }
 
 // ------------------------------------------------ attention prologue (fwd)
+// Rank-r bridge folded into the prologue (lb_attn_prep_fwd_bridge: the one-token decode step, where the separate rank-8
+// GEMM launch costs more than its arithmetic): kc = bf16(k + bf16(tk . B_k^T)), vc likewise, B picked by the token's modality.
+struct PrepBridge {
+    const __nv_bfloat16* tk;       // [n, rank] sorted rows (x . A_k^T), or null: kc / vc come precomputed (or absent)
+    const __nv_bfloat16* tv;
+    const __nv_bfloat16* Bk[2];    // [C, rank]: index 0 language tokens, 1 vision tokens
+    const __nv_bfloat16* Bv[2];
+    int rank;                      // multiple of 8
+};
+
+// bf16(x + bf16(sum_r t[r] * B[c][r])) for 8 consecutive channels c0..c0+7 (the GEMM epilogue's rounding sequence).  The eight
+// B rows of a rank chunk are requested together (one L2 round trip per chunk, not one per channel).
+__device__ __forceinline__ void bridge_add8(float (&x)[8], const __nv_bfloat16* __restrict__ t, const __nv_bfloat16* __restrict__ B,
+                                            int c0, int rank) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int r = 0; r < rank; r += 8) {
+        uint4 b4[8];
+        const uint4 t4 = __ldg(reinterpret_cast<const uint4*>(t + r));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) b4[j] = __ldg(reinterpret_cast<const uint4*>(B + (int64_t)(c0 + j) * rank + r));
+        float tb[8];
+        unpack8(t4, tb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float bb[8];
+            unpack8(b4[j], bb);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[j] = fmaf(tb[e], bb[e], acc[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float kb = __bfloat162float(__float2bfloat16_rn(acc[j]));
+        x[j] = __bfloat162float(__float2bfloat16_rn(x[j] + kb));
+    }
+}
+
 // One CTA per original token.  A "unit" is 8 rotary pairs: elements [d0,d0+8) and [d0+D/2, d0+D/2+8) of one head.
-// kc = k + kb and vc = v + vb (the bridged variants) are produced upstream by rank-r GEMMs (beta = 1).
+// kc = k + kb and vc = v + vb (the bridged variants) are produced upstream by rank-r GEMMs (beta = 1), or here (PrepBridge).
 __global__ void __launch_bounds__(256) attn_prep_fwd_kernel(
     const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ kc,
     const __nv_bfloat16* __restrict__ v, const __nv_bfloat16* __restrict__ vc, const uint8_t* __restrict__ flag_sorted,
     const int32_t* __restrict__ sorted_of, const int32_t* __restrict__ pos, const float* __restrict__ cos_t,
     const float* __restrict__ sin_t, __nv_bfloat16* __restrict__ Q, __nv_bfloat16* __restrict__ Kfv,
     __nv_bfloat16* __restrict__ Kfl, __nv_bfloat16* __restrict__ Vfv, __nv_bfloat16* __restrict__ Vfl, int heads, int D,
-    const int32_t* __restrict__ kv_row) {
+    const int32_t* __restrict__ kv_row, const PrepBridge br) {
     pdl_trigger();
     pdl_wait();
     const int64_t bt = blockIdx.x;
@@ -211,10 +250,14 @@ __global__ void __launch_bounds__(256) attn_prep_fwd_kernel(
             cs[0] = a.x; cs[1] = a.y; cs[2] = a.z; cs[3] = a.w; cs[4] = b.x; cs[5] = b.y; cs[6] = b.z; cs[7] = b.w;
             sn[0] = c.x; sn[1] = c.y; sn[2] = c.z; sn[3] = c.w; sn[4] = d.x; sn[5] = d.y; sn[6] = d.z; sn[7] = d.w;
         }
-        auto rope = [&](const __nv_bfloat16* src, uint4& lo, uint4& hi) {
+        auto rope = [&](const __nv_bfloat16* src, uint4& lo, uint4& hi, bool bridged) {
             float xl[8], xh[8], o_lo[8], o_hi[8];
             unpack8(__ldg(reinterpret_cast<const uint4*>(src + s * C + c_lo)), xl);
             unpack8(__ldg(reinterpret_cast<const uint4*>(src + s * C + c_hi)), xh);
+            if (bridged) {
+                bridge_add8(xl, br.tk + s * br.rank, br.Bk[vis ? 1 : 0], c_lo, br.rank);
+                bridge_add8(xh, br.tk + s * br.rank, br.Bk[vis ? 1 : 0], c_hi, br.rank);
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 o_lo[j] = xl[j] * cs[j] - xh[j] * sn[j];
@@ -224,12 +267,14 @@ __global__ void __launch_bounds__(256) attn_prep_fwd_kernel(
             hi = pack8(o_hi);
         };
         uint4 lo, hi;
-        rope(q, lo, hi);
+        rope(q, lo, hi, false);
         *reinterpret_cast<uint4*>(Q + bt * C + c_lo) = lo;
         *reinterpret_cast<uint4*>(Q + bt * C + c_hi) = hi;
         uint4 kp_lo, kp_hi, kc_lo, kc_hi;
-        rope(k, kp_lo, kp_hi);
-        if (kc) rope(kc, kc_lo, kc_hi); else { kc_lo = kp_lo; kc_hi = kp_hi; }
+        rope(k, kp_lo, kp_hi, false);
+        if (br.tk) rope(k, kc_lo, kc_hi, true);
+        else if (kc) rope(kc, kc_lo, kc_hi, false);
+        else { kc_lo = kp_lo; kc_hi = kp_hi; }
         // vision token: vision queries (fv) see plain, language queries (fl) see bridged; language token: the reverse
         *reinterpret_cast<uint4*>(Kfv + kr * C + c_lo) = vis ? kp_lo : kc_lo;
         *reinterpret_cast<uint4*>(Kfv + kr * C + c_hi) = vis ? kp_hi : kc_hi;
@@ -237,8 +282,17 @@ __global__ void __launch_bounds__(256) attn_prep_fwd_kernel(
         *reinterpret_cast<uint4*>(Kfl + kr * C + c_hi) = vis ? kc_hi : kp_hi;
         const uint4 vp_lo = __ldg(reinterpret_cast<const uint4*>(v + s * C + c_lo));
         const uint4 vp_hi = __ldg(reinterpret_cast<const uint4*>(v + s * C + c_hi));
-        const uint4 vc_lo = vc ? __ldg(reinterpret_cast<const uint4*>(vc + s * C + c_lo)) : vp_lo;
-        const uint4 vc_hi = vc ? __ldg(reinterpret_cast<const uint4*>(vc + s * C + c_hi)) : vp_hi;
+        uint4 vc_lo = vc ? __ldg(reinterpret_cast<const uint4*>(vc + s * C + c_lo)) : vp_lo;
+        uint4 vc_hi = vc ? __ldg(reinterpret_cast<const uint4*>(vc + s * C + c_hi)) : vp_hi;
+        if (br.tv) {
+            float xl[8], xh[8];
+            unpack8(vp_lo, xl);
+            unpack8(vp_hi, xh);
+            bridge_add8(xl, br.tv + s * br.rank, br.Bv[vis ? 1 : 0], c_lo, br.rank);
+            bridge_add8(xh, br.tv + s * br.rank, br.Bv[vis ? 1 : 0], c_hi, br.rank);
+            vc_lo = pack8(xl);
+            vc_hi = pack8(xh);
+        }
         *reinterpret_cast<uint4*>(Vfv + kr * C + c_lo) = vis ? vp_lo : vc_lo;
         *reinterpret_cast<uint4*>(Vfv + kr * C + c_hi) = vis ? vp_hi : vc_hi;
         *reinterpret_cast<uint4*>(Vfl + kr * C + c_lo) = vis ? vc_lo : vp_lo;
@@ -724,8 +778,34 @@ int lb_attn_prep_fwd(const void* q, const void* k, const void* kc, const void* v
     launch_chain(attn_prep_fwd_kernel, dim3((unsigned)n_tokens), dim3(256), 0, (cudaStream_t)stream,
                  (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)kc, (const __nv_bfloat16*)v,
                  (const __nv_bfloat16*)vc, flag_sorted, sorted_of, pos, cos_t, sin_t, (__nv_bfloat16*)Q, (__nv_bfloat16*)Kfv,
-                 (__nv_bfloat16*)Kfl, (__nv_bfloat16*)Vfv, (__nv_bfloat16*)Vfl, heads, head_dim, kv_row);
+                 (__nv_bfloat16*)Kfl, (__nv_bfloat16*)Vfv, (__nv_bfloat16*)Vfl, heads, head_dim, kv_row, PrepBridge{});
     return check_launch("attn_prep_fwd");
+}
+
+int lb_attn_prep_fwd_bridge(const void* q, const void* k, const void* v, const void* tk, const void* tv, const void* Bk_lang,
+                            const void* Bk_vis, const void* Bv_lang, const void* Bv_vis, int rank, const uint8_t* flag_sorted,
+                            const int32_t* sorted_of, const int32_t* pos, const float* cos_t, const float* sin_t, void* Q, void* Kfv,
+                            void* Kfl, void* Vfv, void* Vfl, int64_t n_tokens, int heads, int head_dim, const int32_t* kv_row,
+                            void* stream) {
+    LB_REQUIRE(n_tokens >= 0 && heads > 0 && head_dim >= 16 && head_dim % 16 == 0, LB_EINVAL,
+               "attn_prep_bridge: head_dim=%d must be a multiple of 16", head_dim);
+    LB_REQUIRE(rank > 0 && rank % 8 == 0, LB_EINVAL, "attn_prep_bridge: rank=%d must be a positive multiple of 8", rank);
+    LB_REQUIRE(q && k && v && tk && tv && Bk_lang && Bk_vis && Bv_lang && Bv_vis && flag_sorted && sorted_of && pos && cos_t &&
+                   sin_t && Q && Kfv && Kfl && Vfv && Vfl, LB_EINVAL, "attn_prep_bridge: null argument");
+    LB_REQUIRE(AL16(q) && AL16(k) && AL16(v) && AL16(tk) && AL16(tv) && AL16(Bk_lang) && AL16(Bk_vis) && AL16(Bv_lang) &&
+                   AL16(Bv_vis) && AL16(Q) && AL16(Kfv) && AL16(Kfl) && AL16(Vfv) && AL16(Vfl) && AL16(cos_t) && AL16(sin_t),
+               LB_EALIGN, "attn_prep_bridge: pointers must be 16-byte aligned");
+    if (n_tokens == 0) return LB_OK;
+    PrepBridge br;
+    br.tk = (const __nv_bfloat16*)tk; br.tv = (const __nv_bfloat16*)tv;
+    br.Bk[0] = (const __nv_bfloat16*)Bk_lang; br.Bk[1] = (const __nv_bfloat16*)Bk_vis;
+    br.Bv[0] = (const __nv_bfloat16*)Bv_lang; br.Bv[1] = (const __nv_bfloat16*)Bv_vis;
+    br.rank = rank;
+    launch_chain(attn_prep_fwd_kernel, dim3((unsigned)n_tokens), dim3(256), 0, (cudaStream_t)stream,
+                 (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)nullptr, (const __nv_bfloat16*)v,
+                 (const __nv_bfloat16*)nullptr, flag_sorted, sorted_of, pos, cos_t, sin_t, (__nv_bfloat16*)Q, (__nv_bfloat16*)Kfv,
+                 (__nv_bfloat16*)Kfl, (__nv_bfloat16*)Vfv, (__nv_bfloat16*)Vfl, heads, head_dim, kv_row, br);
+    return check_launch("attn_prep_fwd_bridge");
 }
 
 int lb_attn_prep_bwd(const void* dQ, const void* dKfv, const void* dKfl, const void* dVfv, const void* dVfl,

@@ -663,6 +663,13 @@ class AttnMeta:
     dec_kv_row: Optional[torch.Tensor] = None          # int32 [B]: b * capacity + length, the new token's row of the cache
 
 
+# Decode step: compute the rank-8 bridge products inside the attention prologue instead of a separate skinny-GEMM launch.
+# Measured on Libra-11B (B=8, graph replay, dependent launches on): 5.51-5.55 ms per step without, 5.60-5.62 ms with -- the
+# prologue grows from 4.4 to 9.3 us on its 8 CTAs while the 8.5 us GEMM launch it replaces already overlapped its neighbours.
+# Off by default; LB_FOLD_DECODE_BRIDGE=1 selects it (tests cover both).
+FOLD_DECODE_BRIDGE = os.environ.get("LB_FOLD_DECODE_BRIDGE", "0") == "1"
+
+
 class BridgeAttention(torch.autograd.Function):
     """LibraAttention core with use_bridge=True (modeling_libra.py:318-397, 267-296): bridge add + RoPE prologue,
     tcgen05 flash attention over the two key/value variants, output scattered back to sorted rows."""
@@ -671,22 +678,31 @@ class BridgeAttention(torch.autograd.Function):
     def forward(ctx, q, k, v, tk, tv, Bk_l, Bk_v, Bv_l, Bv_v, meta: AttnMeta):
         rt, w = meta.routing, meta.work
         n = rt.n_lang
-        # bridged variants k + tk.Bk^T, v + tv.Bv^T per modality segment: four rank-r problems with the addend in the
-        # epilogue, one launch
-        kc, vc = torch.empty_like(k), torch.empty_like(v)
-        es = []
-        if n > 0:
-            es += [G(tk[:n], Bk_l, kc[:n], d=k[:n]), G(tv[:n], Bv_l, vc[:n], d=v[:n])]
-        if rt.n_vis > 0:
-            es += [G(tk[n:], Bk_v, kc[n:], d=k[n:]), G(tv[n:], Bv_v, vc[n:], d=v[n:])]
-        ops.gemm_grouped(es)
         scale = 1.0 / math.sqrt(meta.head_dim)
         o = torch.empty_like(q)
+        kc = vc = None
+        fold = meta.decode and FOLD_DECODE_BRIDGE and tk.shape[1] % 8 == 0
+        if not fold:
+            # bridged variants k + tk.Bk^T, v + tv.Bv^T per modality segment: four rank-r problems with the addend in the
+            # epilogue, one launch
+            kc, vc = torch.empty_like(k), torch.empty_like(v)
+            es = []
+            if n > 0:
+                es += [G(tk[:n], Bk_l, kc[:n], d=k[:n]), G(tv[:n], Bv_l, vc[:n], d=v[:n])]
+            if rt.n_vis > 0:
+                es += [G(tk[n:], Bk_v, kc[n:], d=k[n:]), G(tv[n:], Bv_v, vc[n:], d=v[n:])]
+            ops.gemm_grouped(es)
         if meta.decode:
             # one-token step (N1): the prologue writes the new key/value operands straight into the token's cache slot
+            # (optionally computing the rank-r bridge products itself: FOLD_DECODE_BRIDGE)
             cache, i = meta.kv_cache, meta.layer_idx
-            Q = ops.attn_prep_fwd(q, k, kc, v, vc, rt.flag_sorted, rt.inv, meta.pos, meta.cos, meta.sin, meta.heads, meta.head_dim,
-                                  kv_out=(cache.k_fv[i], cache.k_fl[i], cache.v_fv[i], cache.v_fl[i]), kv_row=meta.dec_kv_row)[0]
+            kv_out = (cache.k_fv[i], cache.k_fl[i], cache.v_fv[i], cache.v_fl[i])
+            if fold:
+                Q = ops.attn_prep_fwd_bridge(q, k, v, tk, tv, Bk_l, Bk_v, Bv_l, Bv_v, rt.flag_sorted, rt.inv, meta.pos, meta.cos,
+                                             meta.sin, meta.heads, meta.head_dim, kv_out=kv_out, kv_row=meta.dec_kv_row)[0]
+            else:
+                Q = ops.attn_prep_fwd(q, k, kc, v, vc, rt.flag_sorted, rt.inv, meta.pos, meta.cos, meta.sin, meta.heads,
+                                      meta.head_dim, kv_out=kv_out, kv_row=meta.dec_kv_row)[0]
         else:
             Q, Kfv, Kfl, Vfv, Vfl = ops.attn_prep_fwd(q, k, kc, v, vc, rt.flag_sorted, rt.inv, meta.pos, meta.cos, meta.sin,
                                                      meta.heads, meta.head_dim)

@@ -398,6 +398,23 @@ def attn_prep_fwd(q, k, kc, v, vc, flag_sorted, sorted_of, pos, cos_t, sin_t, he
     return outs   # Q, Kfv, Kfl, Vfv, Vfl
 
 
+def attn_prep_fwd_bridge(q, k, v, tk, tv, Bk_l, Bk_v, Bv_l, Bv_v, flag_sorted, sorted_of, pos, cos_t, sin_t, heads, head_dim,
+                         kv_out=None, kv_row=None):
+    """attn_prep_fwd with kc = k + tk.B_k^T, vc = v + tv.B_v^T computed inside the kernel (decode step: no rank-8 GEMM launch)."""
+    n = q.shape[0]
+    C = heads * head_dim
+    rank = tk.shape[1]
+    for t in (Bk_l, Bk_v, Bv_l, Bv_v):
+        if tuple(t.shape) != (C, rank) or not t.is_contiguous():
+            raise ValueError(f"bridge factor must be a contiguous [{C}, {rank}] tensor, got {tuple(t.shape)}")
+    Q = torch.empty(n, C, dtype=BF16, device=q.device)
+    outs = [Q] + (list(kv_out) if kv_out is not None else [torch.empty(n, C, dtype=BF16, device=q.device) for _ in range(4)])
+    _lib.call("lb_attn_prep_fwd_bridge", _p(q), _p(k), _p(v), _p(tk), _p(tv), _p(Bk_l), _p(Bk_v), _p(Bv_l), _p(Bv_v), rank,
+              _p(flag_sorted), _p(sorted_of), _p(pos), _p(cos_t), _p(sin_t), *[_p(o) for o in outs], n, heads, head_dim,
+              _p(kv_row), _st())
+    return outs   # Q, Kfv, Kfl, Vfv, Vfl
+
+
 def attn_prep_bwd(dQ, dKfv, dKfl, dVfv, dVfl, flag_sorted, sorted_of, pos, cos_t, sin_t, heads, head_dim, bridge=True):
     n = dQ.shape[0]
     C = heads * head_dim

@@ -201,6 +201,19 @@ def test_attn_prep_fwd_bwd():
     Vfv_w, Vfl_w = torch.where(fo, Vs, Vc), torch.where(fo, Vc, Vs)
     for got, want, nm in ((Q, Qw, "Q"), (Kfv, Kfv_w, "Kfv"), (Kfl, Kfl_w, "Kfl"), (Vfv, Vfv_w, "Vfv"), (Vfl, Vfl_w, "Vfl")):
         assert_close(got, want, rtol=2e-2, atol=3e-2, msg=nm)
+    # the decode step's form: the rank-8 bridge products computed inside the prologue (lb_attn_prep_fwd_bridge), also with the
+    # K/V rows redirected (kv_row) as the KV cache does
+    outs = ops.attn_prep_fwd_bridge(q, k, v, tk, tv, Bk_l, Bk_v, Bv_l, Bv_v, rt.flag_sorted, rt.inv, pos, cos_t, sin_t, H, D)
+    for got, ref, want, nm in zip(outs, (Q, Kfv, Kfl, Vfv, Vfl), (Qw, Kfv_w, Kfl_w, Vfv_w, Vfl_w), ("Q", "Kfv", "Kfl", "Vfv", "Vfl")):
+        assert_close(got, want, rtol=2e-2, atol=3e-2, msg=nm + " (folded bridge)")
+        d = (got.float() - ref.float()).abs()          # vs the addmm-produced variant: same rounding sequence, fp32 sum order aside
+        assert float((d > 0).float().mean()) < 2e-2 and float(d.max()) <= 0.0625, nm
+    rows = torch.randperm(N, device=dev, generator=g).to(torch.int32)
+    big = [torch.zeros(N, C, dtype=torch.bfloat16, device=dev) for _ in range(4)]
+    ops.attn_prep_fwd_bridge(q, k, v, tk, tv, Bk_l, Bk_v, Bv_l, Bv_v, rt.flag_sorted, rt.inv, pos, cos_t, sin_t, H, D,
+                             kv_out=big, kv_row=rows)
+    for got, ref in zip(big, outs[1:]):
+        assert torch.equal(got[rows.long()], ref)
     grads = [mk(N, C) for _ in range(5)]
     dq, dk, dv, dkb, dvb = ops.attn_prep_bwd(*grads, rt.flag_sorted, rt.inv, pos, cos_t, sin_t, H, D)
     kb.retain_grad(); vb.retain_grad()

@@ -242,3 +242,22 @@ def test_sampling_processors_and_policy_in_generate(golden):
         model.generate(ids, penalty_alpha=0.6, **kw)
     with pytest.raises(NotImplementedError):
         model.generate(ids, num_beams=4, **kw)
+
+
+def test_decode_with_the_bridge_folded_into_the_prologue(golden, monkeypatch):
+    """LB_FOLD_DECODE_BRIDGE: the rank-8 bridge products computed inside lb_attn_prep_fwd_bridge instead of a skinny-GEMM launch;
+    same rounding sequence, fp32 summation order aside -- the greedy continuation agrees (ties in bf16 logits aside)."""
+    need_gpu()
+    from libra_b200 import functional as LF
+    gm = golden("decoder_tiny")
+    model = _build(gm)
+    V = model.config.vocab_size
+    g = torch.Generator().manual_seed(6)
+    T = 21
+    ids = torch.randint(3, V, (2, T), generator=g)[None].repeat(2, 1, 1).to(dev)
+    vi = torch.full((2, T), 578, device=dev)
+    ref = model.generate(ids, vision_indices=vi, max_new_tokens=16)
+    monkeypatch.setattr(LF, "FOLD_DECODE_BRIDGE", True)
+    for cg in (True, False):
+        out = model.generate(ids, vision_indices=vi, max_new_tokens=16, cuda_graph=cg)
+        assert out.shape == ref.shape and (out == ref).float().mean() > 0.9

@@ -17,7 +17,8 @@ SIZE = dict(size={"shortest_edge": 336}, crop_size={"height": 336, "width": 336}
 def test_batch_of_mixed_sizes_equals_oracle(pad):
     need_gpu()
     from libra_b200.processors import CLIPImageProcessor
-    shapes = [(500, 733), (733, 500), (336, 336), (100, 80), (1200, 1600), (337, 900), (224, 224), (2000, 350), (33, 47), (336, 1000)]
+    shapes = [(500, 733), (733, 500), (336, 336), (100, 80), (1200, 1600), (337, 900), (224, 224), (2000, 350), (33, 47), (336, 1000),
+              (1, 1), (2, 3), (1, 50), (60, 2), (335, 337)]
     imgs = [_img(h, w, h * 3 + w) for h, w in shapes]
     P = CLIPImageProcessor(pad_to_square=pad, **SIZE)
     out = P(imgs, return_tensors="pt", return_uint8=True)

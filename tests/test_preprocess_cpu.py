@@ -11,7 +11,8 @@ import torch
 
 from oracle import clip_preprocess_oracle as O
 
-SIZES = [(500, 733), (733, 500), (336, 336), (100, 80), (1200, 1600), (337, 900), (224, 224), (2000, 350), (33, 47), (336, 1000)]
+SIZES = [(500, 733), (733, 500), (336, 336), (100, 80), (1200, 1600), (337, 900), (224, 224), (2000, 350), (33, 47), (336, 1000),
+         (1, 1), (2, 3), (1, 50), (60, 2), (335, 337)]        # degenerate: one pixel, extreme aspect ratios, off-by-one sizes
 
 
 def fixture_pixel_values(g, key, i):
