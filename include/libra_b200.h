@@ -333,6 +333,10 @@ int lb_gemm_grouped(const lb_gemm_problem* problems, int n, void* workspace, int
  * the first launch (every launch leaves it zero), so one workspace serves launches with different problem lists. */
 int64_t lb_gemm_skinny_workspace_bytes(const lb_gemm_problem* problems, int n);
 int lb_gemm_skinny(const lb_gemm_problem* problems, int n, void* workspace, int64_t workspace_bytes, void* stream);
+/* debug hook (scripts/gemm_skinny_trace.py): device buffer of [work units][12] int64 that the following lb_gemm_skinny launches
+ * fill with %globaltimer stamps per CTA (start, prologue done, dependency resolved, first stage landed, accumulator complete,
+ * partial published, output written, end); NULL switches it off. */
+int lb_gemm_skinny_set_trace(void* buf);
 /* encoded TMA descriptors are cached by (pointer, shape, pitch, box): counters for the "no per-call encode" check */
 int lb_gemm_tmap_cache_stats(int64_t* hits, int64_t* misses);
 

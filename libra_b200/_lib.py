@@ -23,6 +23,7 @@ SIGNATURES = {
     "lb_device_check": (I, []),
     "lb_sm_count": (I, []),
     "lb_set_pdl": (I, [I]),
+    "lb_gemm_skinny_set_trace": (I, [P]),
     "lb_clip_preprocess_workspace": (L, [P, P, I, I, I, I]),
     "lb_clip_resample_coeffs": (I, [I, I, I, I, P, I, P]),
     "lb_clip_preprocess": (I, [P, P, P, P, I, I, I, I, P, P, P, ctypes.c_double, P, I, P, P, L, P]),

@@ -45,28 +45,34 @@ __device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(_
 
 // Split-K reduction of one output row: the partials of 16 / NF4 splits are loaded together (each is an L2 round trip of ~1 us;
 // issued one split at a time, nine splits cost ~7 us of the o-proj / down-proj launches), then added in split order, so the
-// sum is the same for every launch.  Row layout of a partial: [acc (TOK) | acc2 (TOK, SwiGLU only)] fp32.
-template <int TOK, bool TWO>
-__device__ __forceinline__ void reduce_splits(const float* __restrict__ src0, int splits, float (&acc)[32], float (&acc2)[32]) {
-    constexpr int NF4 = TOK / 4 * (TWO ? 2 : 1), RB = 16 / NF4, W = TOK * (TWO ? 2 : 1);
+// sum is the same for every launch.  Row layout of a partial: [acc (TOK) | acc2 (TOK, SwiGLU only)] fp32; only the first Q4
+// float4 of each half carry tokens (Q4 = ceil(M / 4) rounded up to a power of two): with 8 tokens all of nine splits fit one batch.
+template <int Q4, bool TWO>
+__device__ __forceinline__ void reduce_splits(const float* __restrict__ src0, int splits, int tok, float (&acc)[32], float (&acc2)[32]) {
+    constexpr int NF4 = Q4 * (TWO ? 2 : 1), RB = 16 / NF4 > 9 ? 9 : 16 / NF4;
+    const int64_t stride = (int64_t)BM * tok * (TWO ? 2 : 1);
     for (int sp0 = 0; sp0 < splits; sp0 += RB) {
         float4 buf[RB][NF4];
 #pragma unroll
         for (int r = 0; r < RB; ++r) {
-            const float* src = src0 + (int64_t)min(sp0 + r, splits - 1) * (BM * W);
+            const float* src = src0 + (int64_t)min(sp0 + r, splits - 1) * stride;
 #pragma unroll
-            for (int f = 0; f < NF4; ++f) buf[r][f] = __ldcg(reinterpret_cast<const float4*>(src) + f);
+            for (int f = 0; f < Q4; ++f) buf[r][f] = __ldcg(reinterpret_cast<const float4*>(src) + f);
+            if (TWO) {
+#pragma unroll
+                for (int f = 0; f < Q4; ++f) buf[r][Q4 + f] = __ldcg(reinterpret_cast<const float4*>(src + tok) + f);
+            }
         }
 #pragma unroll
         for (int r = 0; r < RB; ++r) {
             if (sp0 + r < splits) {
 #pragma unroll
-                for (int f = 0; f < NF4; ++f) {
+                for (int f = 0; f < Q4; ++f) {
                     const float4 v = buf[r][f];
-                    if (4 * f < TOK) {
-                        acc[4 * f] += v.x; acc[4 * f + 1] += v.y; acc[4 * f + 2] += v.z; acc[4 * f + 3] += v.w;
-                    } else {
-                        acc2[4 * f - TOK] += v.x; acc2[4 * f - TOK + 1] += v.y; acc2[4 * f - TOK + 2] += v.z; acc2[4 * f - TOK + 3] += v.w;
+                    acc[4 * f] += v.x; acc[4 * f + 1] += v.y; acc[4 * f + 2] += v.z; acc[4 * f + 3] += v.w;
+                    if (TWO) {
+                        const float4 u = buf[r][Q4 + f];
+                        acc2[4 * f] += u.x; acc2[4 * f + 1] += u.y; acc2[4 * f + 2] += u.z; acc2[4 * f + 3] += u.w;
                     }
                 }
             }
@@ -74,8 +80,17 @@ __device__ __forceinline__ void reduce_splits(const float* __restrict__ src0, in
     }
 }
 
+template <bool TWO>
+__device__ __forceinline__ void reduce_dispatch(const float* __restrict__ src0, int splits, int tok, int M, float (&acc)[32], float (&acc2)[32]) {
+    if (M <= 4) reduce_splits<1, TWO>(src0, splits, tok, acc, acc2);
+    else if (M <= 8) reduce_splits<2, TWO>(src0, splits, tok, acc, acc2);
+    else if (M <= 16) reduce_splits<4, TWO>(src0, splits, tok, acc, acc2);
+    else reduce_splits<8, TWO>(src0, splits, tok, acc, acc2);
+}
+
 struct Prob {
     int M, N, tok;                      // tok = 16 or 32 accumulator columns (tokens padded)
+    int mred;                           // token columns the split-K partials carry: M (default) or tok (LB_SKINNY_FULLTOK=1, A/B)
     int num_kb, kb_per_split, splits, tiles_n;
     int unit_begin;
     int dual;                           // SwiGLU: second weight, second accumulator
@@ -92,7 +107,15 @@ struct Params {
     CUtensorMap maps[3 * MAXP];
     Prob prob[MAXP];
     int n_prob, total_units;
+    long long* trace;                   // debug (lb_gemm_skinny_set_trace): [unit][12] globaltimer ns at the phases below, or null
 };
+
+__device__ __forceinline__ long long gtime() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define SK_TRACE(slot) do { if (p.trace) p.trace[(long long)blockIdx.x * 12 + (slot)] = gtime(); } while (0)
 
 // DUAL: the launch holds at least one SwiGLU problem (stage = W | W2 | A, fewer stages); plain problems in it skip W2
 // MINB: resident CTAs per SM the kernel is compiled for.  2 (five / three stages, ~105 KB): the stand-alone optimum.  3 (three /
@@ -119,17 +142,24 @@ __global__ void __launch_bounds__(THREADS, MINB) gemm_skinny_kernel(const __grid
     const int kb0 = split * pb.kb_per_split;
     const int kb1 = min(pb.num_kb, kb0 + pb.kb_per_split);
     const int nkb = kb1 - kb0;                                      // >= 1 by construction
+    // fields used inside the pipeline loops, read once (indexed constant loads otherwise: see the epilogue)
+    const CUtensorMap* const map_w = &p.maps[pb.w_map];
+    const CUtensorMap* const map_w2 = &p.maps[pb.w2_map];
+    const CUtensorMap* const map_a = &p.maps[pb.a_map];
+    const bool pb_dual = pb.dual != 0;
+    const int pb_tok = pb.tok;
     constexpr uint32_t TMEM_COLS = 64;
 
     pdl_trigger();
     if (threadIdx.x == 0) {
+        SK_TRACE(0);                                                // CTA start
         for (int i = 0; i < 2 * STAGES + 1; ++i) mbar_init(bars + i, 1);
         fence_barrier_init();
     }
     if (warp == 0 && elect_one()) {
-        tma_prefetch_desc(&p.maps[pb.w_map]);
-        tma_prefetch_desc(&p.maps[pb.a_map]);
-        if (pb.dual) tma_prefetch_desc(&p.maps[pb.w2_map]);
+        tma_prefetch_desc(map_w);
+        tma_prefetch_desc(map_a);
+        if (pb_dual) tma_prefetch_desc(map_w2);
     }
     if (warp == 1) {
         tmem_alloc(tmem_slot, TMEM_COLS);
@@ -143,42 +173,45 @@ __global__ void __launch_bounds__(THREADS, MINB) gemm_skinny_kernel(const __grid
 
     if (warp == 0) {
         if (elect_one()) {
-            const uint32_t tx = (uint32_t)((pb.dual ? 2 : 1) * W_BYTES + pb.tok * BK * 2);
+            const uint32_t tx = (uint32_t)((pb_dual ? 2 : 1) * W_BYTES + pb_tok * BK * 2);
             // the first ring pass of WEIGHTS depends on no earlier kernel: under a programmatic dependent launch it streams
             // while the previous kernel of the chain drains; the activations follow once that kernel's writes are visible
             const int pre = min(nkb, STAGES);
             for (int i = 0; i < pre; ++i) {
                 uint8_t* st = smem + i * STAGE_BYTES;
                 mbar_arrive_expect_tx(bars + i, tx);
-                tma_load_2d(st, &p.maps[pb.w_map], bars + i, (kb0 + i) * BK, tile * BM);
-                if (DUAL && pb.dual) tma_load_2d(st + W_BYTES, &p.maps[pb.w2_map], bars + i, (kb0 + i) * BK, tile * BM);
+                tma_load_2d(st, map_w, bars + i, (kb0 + i) * BK, tile * BM);
+                if (DUAL && pb_dual) tma_load_2d(st + W_BYTES, map_w2, bars + i, (kb0 + i) * BK, tile * BM);
             }
+            SK_TRACE(1);                                            // prologue done, first weight loads issued
             pdl_wait();
+            SK_TRACE(2);                                            // grid dependency resolved
             for (int i = 0; i < pre; ++i)
-                tma_load_2d(smem + i * STAGE_BYTES + A_OFF, &p.maps[pb.a_map], bars + i, (kb0 + i) * BK, 0);
+                tma_load_2d(smem + i * STAGE_BYTES + A_OFF, map_a, bars + i, (kb0 + i) * BK, 0);
             for (int i = pre; i < nkb; ++i) {
                 const int s = i % STAGES;
                 wait_bar(bar0 + 8 * (STAGES + s), ((uint32_t)(i / STAGES) & 1u) ^ 1u);
                 uint8_t* st = smem + s * STAGE_BYTES;
                 mbar_arrive_expect_tx(bars + s, tx);
-                tma_load_2d(st, &p.maps[pb.w_map], bars + s, (kb0 + i) * BK, tile * BM);
-                if (DUAL && pb.dual) tma_load_2d(st + W_BYTES, &p.maps[pb.w2_map], bars + s, (kb0 + i) * BK, tile * BM);
-                tma_load_2d(st + A_OFF, &p.maps[pb.a_map], bars + s, (kb0 + i) * BK, 0);
+                tma_load_2d(st, map_w, bars + s, (kb0 + i) * BK, tile * BM);
+                if (DUAL && pb_dual) tma_load_2d(st + W_BYTES, map_w2, bars + s, (kb0 + i) * BK, tile * BM);
+                tma_load_2d(st + A_OFF, map_a, bars + s, (kb0 + i) * BK, 0);
             }
         }
     } else if (warp == 1) {
         if (elect_one()) {
-            const uint32_t idesc = make_idesc_bf16(BM, pb.tok, 0, 0);
+            const uint32_t idesc = make_idesc_bf16(BM, pb_tok, 0, 0);
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % STAGES;
                 wait_bar(bar0 + 8 * s, (uint32_t)(i / STAGES) & 1u);
+                if (i == 0) SK_TRACE(3);                            // first stage landed
                 tc_fence_after_sync();
                 const uint32_t st = smem_u32(smem + s * STAGE_BYTES);
                 const uint32_t dW = desc_lo_kmajor(st), dW2 = desc_lo_kmajor(st + W_BYTES), dA = desc_lo_kmajor(st + A_OFF);
 #pragma unroll
                 for (int kk = 0; kk < BK / 16; ++kk) {
                     umma_ss_lo(tmem_base, dW + 2 * kk, dA + 2 * kk, idesc, (i | kk) ? 1u : 0u);
-                    if (DUAL && pb.dual) umma_ss_lo(tmem_base + 32, dW2 + 2 * kk, dA + 2 * kk, idesc, (i | kk) ? 1u : 0u);
+                    if (DUAL && pb_dual) umma_ss_lo(tmem_base + 32, dW2 + 2 * kk, dA + 2 * kk, idesc, (i | kk) ? 1u : 0u);
                 }
                 commit_bar(bar0 + 8 * (STAGES + s));
             }
@@ -186,18 +219,30 @@ __global__ void __launch_bounds__(THREADS, MINB) gemm_skinny_kernel(const __grid
         }
     } else {
         // ---------------- epilogue: thread <-> output feature (TMEM lane), registers <-> tokens
+        // The problem's fields live in the kernel parameters behind a run-time index: every use is an indexed constant load,
+        // and the asm barriers / fences below keep the compiler from hoisting them -- the traced epilogue spent 0.3 us per
+        // output row on them.  Read them ONCE; and request the addend and bias rows now, while the weights stream, instead
+        // of after the accumulator barrier (2-4 us of exposed load latency per launch with a residual).
         const int row = (warp & 3) * 32 + lane;                     // warps 2..5 own TMEM lanes 32*(warp%4)..
         const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        const int tok = pb.tok;
-        wait_bar(bar0 + 8 * (2 * STAGES), 0);
-        tc_fence_after_sync();
-        pdl_wait();                                                 // these threads read the addend and write C / the shared workspace
-        // the addend row of this thread's output feature, requested before the split-K round trips below (for 16 tokens; the
-        // 32-token form loads it at the end: registers)
-        float dd[16];
+        const int tok = pb.tok, pM = pb.M, pN = pb.N, splits = pb.splits, mred = pb.mred;
+        const bool dual = pb.dual != 0;
+        __nv_bfloat16* const pC = pb.C;
+        const __nv_bfloat16* const pD = pb.D;
+        const __nv_bfloat16* const pbias = pb.bias;
+        const long long ldc = pb.ldc, ldd = pb.ldd;
+        float* const ppartial = pb.partial;
+        int* const pcounters = pb.counters;
         const int n = tile * BM + row;
+        pdl_wait();                                                 // these threads read the addend and write C / the shared workspace
+        if (threadIdx.x == 64) SK_TRACE(8);
+        float dd[16];                                               // addend of tokens 0..15 (tokens 16..31 are loaded at the end: registers)
 #pragma unroll
-        for (int m = 0; m < 16; ++m) dd[m] = (pb.D && m < pb.M && n < pb.N) ? __bfloat162float(__ldg(pb.D + (int64_t)m * pb.ldd + n)) : 0.f;
+        for (int m = 0; m < 16; ++m) dd[m] = (pD && m < pM && n < pN) ? __bfloat162float(__ldg(pD + (int64_t)m * ldd + n)) : 0.f;
+        const float bias = (pbias && n < pN) ? __bfloat162float(__ldg(pbias + n)) : 0.f;
+        wait_bar(bar0 + 8 * (2 * STAGES), 0);
+        if (threadIdx.x == 64) SK_TRACE(4);                         // accumulator complete (all K blocks streamed)
+        tc_fence_after_sync();
         float acc[32], acc2[32];
         {
             uint32_t r[32];
@@ -205,70 +250,71 @@ __global__ void __launch_bounds__(THREADS, MINB) gemm_skinny_kernel(const __grid
             tc_wait_ld();
 #pragma unroll
             for (int j = 0; j < 32; ++j) acc[j] = j < tok ? __uint_as_float(r[j]) : 0.f;
-            if (pb.dual) {
+            if (dual) {
                 if (tok == 32) tmem_ld32(taddr + 32, r); else tmem_ld16(taddr + 32, r);
                 tc_wait_ld();
 #pragma unroll
                 for (int j = 0; j < 32; ++j) acc2[j] = j < tok ? __uint_as_float(r[j]) : 0.f;
             }
         }
+        if (threadIdx.x == 64) SK_TRACE(9);                         // accumulator in registers
         bool finalize = true;
-        if (pb.splits > 1) {
-            const int w = tok * (1 + pb.dual);                      // floats per row of a partial
-            float* mine = pb.partial + (((int64_t)tile * pb.splits + split) * BM + row) * w;
+        if (splits > 1) {
+            const int w = tok * (dual ? 2 : 1);                     // floats per row of a partial
+            float* mine = ppartial + (((int64_t)tile * splits + split) * BM + row) * w;
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
-                if (j < tok) *reinterpret_cast<float4*>(mine + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
-            if (pb.dual) {
+                if (j < mred) *reinterpret_cast<float4*>(mine + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+            if (dual) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
-                    if (j < tok) *reinterpret_cast<float4*>(mine + tok + j) = make_float4(acc2[j], acc2[j + 1], acc2[j + 2], acc2[j + 3]);
+                    if (j < mred) *reinterpret_cast<float4*>(mine + tok + j) = make_float4(acc2[j], acc2[j + 1], acc2[j + 2], acc2[j + 3]);
             }
             __threadfence();
             named_bar_sync(1, 128);
-            if (threadIdx.x == 64) s_last = atomicAdd(pb.counters + tile, 1) == pb.splits - 1 ? 1 : 0;
+            if (threadIdx.x == 64) s_last = atomicAdd(pcounters + tile, 1) == splits - 1 ? 1 : 0;
             named_bar_sync(1, 128);
+            if (threadIdx.x == 64) SK_TRACE(5);                     // partial published, arrival counted
             finalize = s_last != 0;
             if (finalize) {                                         // the tile's last CTA: add the partials in split order
                 __threadfence();
 #pragma unroll
                 for (int j = 0; j < 32; ++j) acc[j] = acc2[j] = 0.f;
-                const float* src0 = pb.partial + ((int64_t)tile * pb.splits * BM + row) * w;
-                if (tok == 16) {
-                    if (pb.dual) reduce_splits<16, true>(src0, pb.splits, acc, acc2); else reduce_splits<16, false>(src0, pb.splits, acc, acc2);
-                } else {
-                    if (pb.dual) reduce_splits<32, true>(src0, pb.splits, acc, acc2); else reduce_splits<32, false>(src0, pb.splits, acc, acc2);
-                }
-                if (threadIdx.x == 64) pb.counters[tile] = 0;       // ready for the next launch
+                const float* src0 = ppartial + ((int64_t)tile * splits * BM + row) * w;
+                if (dual) reduce_dispatch<true>(src0, splits, tok, mred, acc, acc2); else reduce_dispatch<false>(src0, splits, tok, mred, acc, acc2);
+                if (threadIdx.x == 64) pcounters[tile] = 0;         // ready for the next launch
             }
         }
-        if (finalize && n < pb.N) {
-            const float bias = pb.bias ? __bfloat162float(pb.bias[n]) : 0.f;
+        if (finalize && n < pN) {
+            float dhi[16];                                          // addend of tokens 16..31, requested together
+#pragma unroll
+            for (int m = 0; m < 16; ++m) dhi[m] = (pD && m + 16 < pM) ? __bfloat162float(__ldg(pD + (int64_t)(m + 16) * ldd + n)) : 0.f;
+            __nv_bfloat16* crow = pC + n;
 #pragma unroll
             for (int m = 0; m < 32; ++m) {
-                if (m < pb.M) {
+                if (m < pM) {
                     float v;
-                    if (pb.dual) {
+                    if (dual) {
                         // reference: silu(gate) rounded to bf16, then * up (modeling_libra.py:232-233); gate / up rounded first (nn.Linear)
                         const float gt = round_bf16(acc[m]), up = round_bf16(acc2[m]);
                         v = round_bf16(round_bf16(silu_f(gt)) * up);
                     } else {
                         v = round_bf16(acc[m] + bias);
                     }
-                    if (pb.D) {                                                          // bf16(bf16(x W^T) + addend)
-                        const float d = m < 16 ? dd[m & 15] : __bfloat162float(__ldg(pb.D + (int64_t)m * pb.ldd + n));
-                        v = round_bf16(v + d);
-                    }
-                    pb.C[(int64_t)m * pb.ldc + n] = __float2bfloat16_rn(v);
+                    if (pD) v = round_bf16(v + (m < 16 ? dd[m & 15] : dhi[m & 15]));      // bf16(bf16(x W^T) + addend)
+                    crow[(int64_t)m * ldc] = __float2bfloat16_rn(v);
+                    if (m == 0 && threadIdx.x == 64) SK_TRACE(10);  // first output element
                 }
             }
         }
+        if (threadIdx.x == 64) SK_TRACE(6);                         // output (or nothing, for a non-final split) written
         tc_fence_before_sync();
     }
     __syncthreads();
     if (warp == 1) {
         tc_fence_after_sync();
         tmem_dealloc(tmem_base, TMEM_COLS);
+        if (lane == 0) SK_TRACE(7);                                 // CTA end
     }
 }
 
@@ -301,6 +347,8 @@ static cudaError_t launch_variant(const Params& local, cudaStream_t st) {
     return launch_chain(kern, dim3((unsigned)local.total_units), dim3(THREADS), (size_t)smem_bytes<STAGES, DUAL>(), st, local);
 }
 
+static long long* g_trace = nullptr;
+
 constexpr int64_t CTR_BYTES = 64 * 1024;      // tile counters: fixed region at the start of the workspace
 
 struct Plan {
@@ -329,6 +377,11 @@ static int plan(const lb_gemm_problem* probs, int n, Params* P, Plan* pl) {
         Prob& g = P ? P->prob[i] : tmp;
         g.M = (int)q.M; g.N = (int)q.N;
         g.tok = q.M <= 16 ? 16 : 32;
+        {
+            static int fulltok = -1;
+            if (fulltok < 0) { const char* e = getenv("LB_SKINNY_FULLTOK"); fulltok = (e && atoi(e) == 1) ? 1 : 0; }
+            g.mred = fulltok ? g.tok : g.M;
+        }
         g.dual = q.epilogue == LB_EPI_SWIGLU ? 1 : 0;
         g.tiles_n = ceil_div(q.N, BM);
         g.num_kb = ceil_div(q.K, BK);
@@ -357,6 +410,7 @@ static int plan(const lb_gemm_problem* probs, int n, Params* P, Plan* pl) {
     if (P) {
         P->n_prob = n;
         P->total_units = units;
+        P->trace = g_trace;
     }
     pl->partial_floats = pf;
     pl->counters = ctr;
@@ -377,6 +431,12 @@ int64_t lb_gemm_skinny_workspace_bytes(const lb_gemm_problem* problems, int n) {
     sk::Plan pl{};
     if (sk::plan(problems, n, nullptr, &pl)) return -1;
     return sk::CTR_BYTES + pl.partial_floats * 4;
+}
+
+/* debug: device buffer of [units][12] int64 the next launches fill with %globaltimer stamps (NULL switches it off) */
+int lb_gemm_skinny_set_trace(void* buf) {
+    sk::g_trace = (long long*)buf;
+    return LB_OK;
 }
 
 int lb_gemm_skinny(const lb_gemm_problem* problems, int n, void* workspace, int64_t workspace_bytes, void* stream) {
