@@ -290,7 +290,12 @@ __global__ void __launch_bounds__(GG_THREADS, 1) gemm_grouped_kernel(const __gri
                 const bool dual = pb.epi == GG_EPI_SWIGLU;
                 const int n_base = dual ? tl.nt * (pb.tile_n / 2) : tl.nt * pb.tile_n + (int)rank * pb.b_part_rows;
                 const uint32_t tx = (uint32_t)(GG_A_BYTES + pb.b_tx_bytes) * CG;
-                for (int sg = 0; sg < pb.nseg; ++sg) {
+                // per-tile copies of the fields the K loop uses: p.prob[] sits behind a run-time index in the kernel parameters,
+                // every use is an indexed constant load that the asm barriers below keep the compiler from hoisting
+                const bool a_mn = pb.a_mn != 0, b_mn = pb.b_mn != 0;
+                const int b_parts = pb.b_parts, b_part_rows = pb.b_part_rows, nseg = pb.nseg;
+                const CUtensorMap* tmB2 = &p.maps[pb.aux_b2 >= 0 ? pb.aux_b2 : 0];
+                for (int sg = 0; sg < nseg; ++sg) {
                     const GGSeg& sgm = pb.seg[sg];
                     if (sgm.wait_on >= 0) {
                         // the A operand of this segment is another problem's output: wait until its tiles were published
@@ -312,7 +317,8 @@ __global__ void __launch_bounds__(GG_THREADS, 1) gemm_grouped_kernel(const __gri
                     }
                     const CUtensorMap* tmA = &p.maps[sgm.a_map];
                     const CUtensorMap* tmB0 = &p.maps[sgm.b_map];
-                    for (int kb = 0; kb < sgm.num_kb; ++kb) {
+                    const int seg_kb = sgm.num_kb;
+                    for (int kb = 0; kb < seg_kb; ++kb) {
                         gg_wait(empty_a + 8 * stage, phase ^ 1u, 100 + stage);
                         if (rank == 0) {
                             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full_a + 8 * stage), "r"(tx)
@@ -322,7 +328,7 @@ __global__ void __launch_bounds__(GG_THREADS, 1) gemm_grouped_kernel(const __gri
                         const uint32_t sa = stage_base + stage * Cfg::STAGE_BYTES;
                         const uint32_t sb = sa + GG_A_BYTES;
                         const int k0 = kb * GG_BK;
-                        if (!pb.a_mn) {
+                        if (!a_mn) {
                             if (CG == 2) tma_load_2d_cg2(sa, tmA, bar, k0, m0); else tma_load_2d_addr(sa, tmA, bar, k0, m0);
                         } else {
 #pragma unroll
@@ -331,15 +337,15 @@ __global__ void __launch_bounds__(GG_THREADS, 1) gemm_grouped_kernel(const __gri
                                 else tma_load_2d_addr(sa + c * (GG_BK * 128), tmA, bar, m0 + c * 64, k0);
                             }
                         }
-                        if (!pb.b_mn) {
-                            for (int part = 0; part < pb.b_parts; ++part) {
+                        if (!b_mn) {
+                            for (int part = 0; part < b_parts; ++part) {
                                 const int which = dual ? (CG == 2 ? (int)rank : part) : 0;
-                                const CUtensorMap* tmB = which ? &p.maps[pb.aux_b2] : tmB0;
-                                const uint32_t dst = sb + part * pb.b_part_rows * 128;
+                                const CUtensorMap* tmB = which ? tmB2 : tmB0;
+                                const uint32_t dst = sb + part * b_part_rows * 128;
                                 if (CG == 2) tma_load_2d_cg2(dst, tmB, bar, k0, n_base); else tma_load_2d_addr(dst, tmB, bar, k0, n_base);
                             }
                         } else {
-                            const int nchunk = (pb.b_part_rows + 63) >> 6;
+                            const int nchunk = (b_part_rows + 63) >> 6;
                             for (int c = 0; c < nchunk; ++c) {
                                 if (CG == 2) tma_load_2d_cg2(sb + c * (GG_BK * 128), tmB0, bar, n_base + c * 64, k0);
                                 else tma_load_2d_addr(sb + c * (GG_BK * 128), tmB0, bar, n_base + c * 64, k0);
@@ -367,8 +373,9 @@ __global__ void __launch_bounds__(GG_THREADS, 1) gemm_grouped_kernel(const __gri
                 tc_fence_after_sync();
                 const uint32_t idesc = make_idesc_bf16(GG_BM * CG, pb.tile_n, pb.a_mn, pb.b_mn);
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
-                const uint32_t a_step = pb.a_mn ? 128u : 2u;          // +2048 B / +32 B per 16 K elements, in 16 B units
-                const uint32_t b_step = pb.b_mn ? 128u : 2u;
+                const bool a_mn = pb.a_mn != 0, b_mn = pb.b_mn != 0;    // per-tile copies (see the producer)
+                const uint32_t a_step = a_mn ? 128u : 2u;             // +2048 B / +32 B per 16 K elements, in 16 B units
+                const uint32_t b_step = b_mn ? 128u : 2u;
                 int total_kb = 0;
                 for (int sg = 0; sg < pb.nseg; ++sg) total_kb += pb.seg[sg].num_kb;
                 for (int kb = 0; kb < total_kb; ++kb) {
@@ -376,8 +383,8 @@ __global__ void __launch_bounds__(GG_THREADS, 1) gemm_grouped_kernel(const __gri
                     tc_fence_after_sync();
                     const uint32_t sa = stage_base + stage * Cfg::STAGE_BYTES;
                     const uint32_t sb = sa + GG_A_BYTES;
-                    const uint32_t a_lo = pb.a_mn ? desc_lo_mnmajor(sa, GG_BK * 128) : desc_lo_kmajor(sa);
-                    const uint32_t b_lo = pb.b_mn ? desc_lo_mnmajor(sb, GG_BK * 128) : desc_lo_kmajor(sb);
+                    const uint32_t a_lo = a_mn ? desc_lo_mnmajor(sa, GG_BK * 128) : desc_lo_kmajor(sa);
+                    const uint32_t b_lo = b_mn ? desc_lo_mnmajor(sb, GG_BK * 128) : desc_lo_kmajor(sb);
 #pragma unroll
                     for (int k = 0; k < GG_BK / 16; ++k) {
                         const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
@@ -436,8 +443,17 @@ __global__ void __launch_bounds__(GG_THREADS, 1) gemm_grouped_kernel(const __gri
             const uint32_t tacc = tmem_base + (uint32_t)acc * 256u + lane_sel;
             const bool has_d = pb.aux_d >= 0;
             const CUtensorMap* tmC = &p.maps[pb.c_map];
+            // per-tile copies of the problem's fields (indexed constant loads otherwise, re-issued after every asm barrier)
+            const int epi = pb.epi, pN = pb.N, tile_n = pb.tile_n;
+            const float* const alpha_p = pb.alpha;
+            const __nv_bfloat16* const bias_p = pb.bias;
+            const CUtensorMap* const tmD = &p.maps[has_d ? pb.aux_d : 0];
+            const CUtensorMap* const tmG = pb.aux_g >= 0 ? &p.maps[pb.aux_g] : nullptr;
+            const CUtensorMap* const tmU = pb.aux_u >= 0 ? &p.maps[pb.aux_u] : nullptr;
+            const bool signal = pb.signal != 0;
+            const int counter_off = pb.counter_off;
 
-            if (pb.epi == GG_EPI_SWIGLU) {
+            if (epi == GG_EPI_SWIGLU) {
                 // accumulator columns [0,128) = gate, [128,256) = up, of output columns n0 .. n0+127
                 const int n0 = tl.nt * 128;
                 gg_wait(tfull_a + 8 * acc, ((uint32_t)it >> 1) & 1u, 400 + acc);
@@ -467,18 +483,18 @@ __global__ void __launch_bounds__(GG_THREADS, 1) gemm_grouped_kernel(const __gri
                         __syncwarp();
                         if (lane == 0) { if (CG == 2) mbar_arrive_cluster(tempty_leader + 8 * acc); else mbar_arrive(bars + 2 * STAGES + 2 + acc); }
                     }
-                    if (pb.aux_g >= 0) emit(pg, &p.maps[pb.aux_g], n0 + c * 64, m0);
-                    if (pb.aux_u >= 0) emit(pu, &p.maps[pb.aux_u], n0 + c * 64, m0);
+                    if (tmG) emit(pg, tmG, n0 + c * 64, m0);
+                    if (tmU) emit(pu, tmU, n0 + c * 64, m0);
                     emit(ph, tmC, n0 + c * 64, m0);
                 }
             } else {
-                const int n0 = tl.nt * pb.tile_n;
-                const int nch = (pb.tile_n + 63) >> 6;
+                const int n0 = tl.nt * tile_n;
+                const int nch = (tile_n + 63) >> 6;
                 if (has_d && t0) {                      // addend tile of chunk 0 -> staging buffer (cc & 1)
                     tma_store_wait_read1();
                     const uint32_t b = cc & 1u;
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dbar_a + 8 * b), "r"(GG_CHUNK_BYTES) : "memory");
-                    tma_load_2d_addr(chunk_base + b * GG_CHUNK_BYTES, &p.maps[pb.aux_d], dbar_a + 8 * b, n0, m0);
+                    tma_load_2d_addr(chunk_base + b * GG_CHUNK_BYTES, tmD, dbar_a + 8 * b, n0, m0);
                 }
                 gg_wait(tfull_a + 8 * acc, ((uint32_t)it >> 1) & 1u, 400 + acc);
                 tc_fence_after_sync();
@@ -494,17 +510,17 @@ __global__ void __launch_bounds__(GG_THREADS, 1) gemm_grouped_kernel(const __gri
                         if (lane == 0) { if (CG == 2) mbar_arrive_cluster(tempty_leader + 8 * acc); else mbar_arrive(bars + 2 * STAGES + 2 + acc); }
                     }
                     const int col0 = n0 + c * 64;
-                    if (pb.alpha) {
-                        const float al = __ldg(pb.alpha);
+                    if (alpha_p) {
+                        const float al = __ldg(alpha_p);
 #pragma unroll
                         for (int j = 0; j < 64; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * al);
                     }
-                    if (pb.bias) {
-                        const uint4* bp = reinterpret_cast<const uint4*>(pb.bias + col0);
+                    if (bias_p) {
+                        const uint4* bp = reinterpret_cast<const uint4*>(bias_p + col0);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             uint4 bv = make_uint4(0, 0, 0, 0);
-                            if (col0 + j * 8 < pb.N) bv = __ldg(bp + j);        // the bias buffer holds N rounded up to 8 elements
+                            if (col0 + j * 8 < pN) bv = __ldg(bp + j);        // the bias buffer holds N rounded up to 8 elements
                             r[8 * j + 0] = __float_as_uint(__uint_as_float(r[8 * j + 0]) + bf16_lo(bv.x));
                             r[8 * j + 1] = __float_as_uint(__uint_as_float(r[8 * j + 1]) + bf16_hi(bv.x));
                             r[8 * j + 2] = __float_as_uint(__uint_as_float(r[8 * j + 2]) + bf16_lo(bv.y));
@@ -518,9 +534,9 @@ __global__ void __launch_bounds__(GG_THREADS, 1) gemm_grouped_kernel(const __gri
                     uint32_t pk[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) pk[j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-                    if (pb.epi == GG_EPI_QGELU) {
+                    if (epi == GG_EPI_QGELU) {
                         // pre-activation (rounded to bf16, what nn.Linear returns) is kept for backward when asked for
-                        if (pb.aux_g >= 0) emit(pk, &p.maps[pb.aux_g], col0, m0);
+                        if (tmG) emit(pk, tmG, col0, m0);
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const float x0 = bf16_lo(pk[j]), x1 = bf16_hi(pk[j]);
@@ -555,20 +571,20 @@ __global__ void __launch_bounds__(GG_THREADS, 1) gemm_grouped_kernel(const __gri
                                 tma_store_wait_read1();
                                 const uint32_t nb = b ^ 1u;
                                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dbar_a + 8 * nb), "r"(GG_CHUNK_BYTES) : "memory");
-                                tma_load_2d_addr(chunk_base + nb * GG_CHUNK_BYTES, &p.maps[pb.aux_d], dbar_a + 8 * nb, col0 + 64, m0);
+                                tma_load_2d_addr(chunk_base + nb * GG_CHUNK_BYTES, tmD, dbar_a + 8 * nb, col0 + 64, m0);
                             }
                         }
                         ++cc;
                     }
                 }
             }
-            if (pb.signal) {
+            if (signal) {
                 // publish this CTA's part of the tile: stores complete -> visible device-wide -> counter bump
                 if (t0) {
                     tma_store_wait_all();
                     fence_proxy_async_all();
                     __threadfence();
-                    atomicAdd(p.counters + pb.counter_off + tl.mt, 1);
+                    atomicAdd(p.counters + counter_off + tl.mt, 1);
                 }
             }
         }
