@@ -13,7 +13,15 @@
 //   * split-K partial sums go to an fp32 workspace; the LAST CTA of a tile (a self-resetting counter) adds the partials in
 //     split order -- deterministic -- and applies the epilogue: bias, bf16 rounding, SwiGLU of a (gate, up) weight pair
 //     (two accumulators), addend (the residual), with the rounding sequence of gemm_grouped.cu;
-//   * several problems per launch (q / k / v of a layer share one launch and one read of x).
+//   * several problems per launch (q / k / v of a layer share one launch and one read of x);
+//   * what the phase trace (lb_gemm_skinny_set_trace, scripts/gemm_skinny_trace.py) showed about the ~8 us a launch costs
+//     beyond its streaming time, and what the code does about it: the problem's fields sit behind a run-time index in the
+//     kernel parameters, so every use was an indexed constant load re-issued after each asm barrier (0.3 us per output row)
+//     -> read once into registers; the residual addend was requested only after the accumulator barrier (2-4 us of exposed
+//     latency) -> requested while the weights stream; the tile's last CTA fetched nine partials one split at a time ->
+//     sixteen float4 in flight, and the partials carry only the real tokens (8 of the 16 padded columns at batch 8);
+//   * programmatic dependent launch: the first ring pass of WEIGHTS is issued before griddepcontrol.wait, so it streams
+//     while the previous kernel of the decode chain drains (lb_set_pdl).
 // Replaces for M <= 32 the same reference products as gemm_grouped.cu (modeling_llama.py:185-201, modeling_libra.py:192-238,
 // 1018-1052); the chained low-rank form and the backward layouts stay on gemm_grouped.cu.
 #include <stdlib.h>
