@@ -224,6 +224,9 @@ __device__ __forceinline__ void bridge_add8(float (&x)[8], const __nv_bfloat16* 
 
 // One CTA per original token.  A "unit" is 8 rotary pairs: elements [d0,d0+8) and [d0+D/2, d0+D/2+8) of one head.
 // kc = k + kb and vc = v + vb (the bridged variants) are produced upstream by rank-r GEMMs (beta = 1), or here (PrepBridge).
+// FOLD = false is the training prologue (no bridge code in it: folding the branch into one kernel cost the training path
+// 106 -> 145 us per launch); FOLD = true is the decode step's variant (lb_attn_prep_fwd_bridge).
+template <bool FOLD>
 __global__ void __launch_bounds__(256) attn_prep_fwd_kernel(
     const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ kc,
     const __nv_bfloat16* __restrict__ v, const __nv_bfloat16* __restrict__ vc, const uint8_t* __restrict__ flag_sorted,
@@ -254,7 +257,7 @@ __global__ void __launch_bounds__(256) attn_prep_fwd_kernel(
             float xl[8], xh[8], o_lo[8], o_hi[8];
             unpack8(__ldg(reinterpret_cast<const uint4*>(src + s * C + c_lo)), xl);
             unpack8(__ldg(reinterpret_cast<const uint4*>(src + s * C + c_hi)), xh);
-            if (bridged) {
+            if (FOLD && bridged) {
                 bridge_add8(xl, br.tk + s * br.rank, br.Bk[vis ? 1 : 0], c_lo, br.rank);
                 bridge_add8(xh, br.tk + s * br.rank, br.Bk[vis ? 1 : 0], c_hi, br.rank);
             }
@@ -272,7 +275,7 @@ __global__ void __launch_bounds__(256) attn_prep_fwd_kernel(
         *reinterpret_cast<uint4*>(Q + bt * C + c_hi) = hi;
         uint4 kp_lo, kp_hi, kc_lo, kc_hi;
         rope(k, kp_lo, kp_hi, false);
-        if (br.tk) rope(k, kc_lo, kc_hi, true);
+        if (FOLD) rope(k, kc_lo, kc_hi, true);
         else if (kc) rope(kc, kc_lo, kc_hi, false);
         else { kc_lo = kp_lo; kc_hi = kp_hi; }
         // vision token: vision queries (fv) see plain, language queries (fl) see bridged; language token: the reverse
@@ -284,7 +287,7 @@ __global__ void __launch_bounds__(256) attn_prep_fwd_kernel(
         const uint4 vp_hi = __ldg(reinterpret_cast<const uint4*>(v + s * C + c_hi));
         uint4 vc_lo = vc ? __ldg(reinterpret_cast<const uint4*>(vc + s * C + c_lo)) : vp_lo;
         uint4 vc_hi = vc ? __ldg(reinterpret_cast<const uint4*>(vc + s * C + c_hi)) : vp_hi;
-        if (br.tv) {
+        if (FOLD) {
             float xl[8], xh[8];
             unpack8(vp_lo, xl);
             unpack8(vp_hi, xh);
@@ -775,7 +778,7 @@ int lb_attn_prep_fwd(const void* q, const void* k, const void* kc, const void* v
                    AL16(Vfv) && AL16(Vfl) && AL16(cos_t) && AL16(sin_t),
                LB_EALIGN, "attn_prep: pointers must be 16-byte aligned");
     if (n_tokens == 0) return LB_OK;
-    launch_chain(attn_prep_fwd_kernel, dim3((unsigned)n_tokens), dim3(256), 0, (cudaStream_t)stream,
+    launch_chain(attn_prep_fwd_kernel<false>, dim3((unsigned)n_tokens), dim3(256), 0, (cudaStream_t)stream,
                  (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)kc, (const __nv_bfloat16*)v,
                  (const __nv_bfloat16*)vc, flag_sorted, sorted_of, pos, cos_t, sin_t, (__nv_bfloat16*)Q, (__nv_bfloat16*)Kfv,
                  (__nv_bfloat16*)Kfl, (__nv_bfloat16*)Vfv, (__nv_bfloat16*)Vfl, heads, head_dim, kv_row, PrepBridge{});
@@ -801,7 +804,7 @@ int lb_attn_prep_fwd_bridge(const void* q, const void* k, const void* v, const v
     br.Bk[0] = (const __nv_bfloat16*)Bk_lang; br.Bk[1] = (const __nv_bfloat16*)Bk_vis;
     br.Bv[0] = (const __nv_bfloat16*)Bv_lang; br.Bv[1] = (const __nv_bfloat16*)Bv_vis;
     br.rank = rank;
-    launch_chain(attn_prep_fwd_kernel, dim3((unsigned)n_tokens), dim3(256), 0, (cudaStream_t)stream,
+    launch_chain(attn_prep_fwd_kernel<true>, dim3((unsigned)n_tokens), dim3(256), 0, (cudaStream_t)stream,
                  (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)nullptr, (const __nv_bfloat16*)v,
                  (const __nv_bfloat16*)nullptr, flag_sorted, sorted_of, pos, cos_t, sin_t, (__nv_bfloat16*)Q, (__nv_bfloat16*)Kfv,
                  (__nv_bfloat16*)Kfl, (__nv_bfloat16*)Vfv, (__nv_bfloat16*)Vfl, heads, head_dim, kv_row, br);
