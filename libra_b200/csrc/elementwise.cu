@@ -497,12 +497,23 @@ __global__ void __launch_bounds__(256) cross_entropy_kernel(__nv_bfloat16* __res
     }
 }
 
+// AdamW's per-element divisions and square root with the hardware approximations (MUFU.SQRT / MUFU.RCP, <= 2 ulp in fp32):
+// the parameter and both moments are rounded to bf16 (8 mantissa bits) right after, and with the IEEE sequences (~35 of the
+// ~50 instructions per element) the update was ALU-bound at the power-capped clock of a training step: 8.9 ms inside the step
+// against 7.3 ms alone for the 8-layer model.
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // ------------------------------------------------ fused AdamW over flat bf16 buffers
 // torch.optim.AdamW semantics (decoupled weight decay, bias-corrected moments), fp32 maths, bf16 storage of p, m, v.
 __global__ void __launch_bounds__(256) adamw_bf16_kernel(__nv_bfloat16* __restrict__ p, const __nv_bfloat16* __restrict__ g,
                                                          __nv_bfloat16* __restrict__ m, __nv_bfloat16* __restrict__ v,
                                                          int64_t nvec, float lr, float beta1, float beta2, float eps,
                                                          float weight_decay, float bc1, float bc2_sqrt) {
+    const float inv_bc2_sqrt = 1.f / bc2_sqrt, step_size = lr / bc1;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
         float fp[8], fg[8], fm[8], fv[8];
         unpack8(reinterpret_cast<const uint4*>(p)[i], fp);
@@ -514,8 +525,8 @@ __global__ void __launch_bounds__(256) adamw_bf16_kernel(__nv_bfloat16* __restri
             fp[j] *= (1.f - lr * weight_decay);
             fm[j] = beta1 * fm[j] + (1.f - beta1) * fg[j];
             fv[j] = beta2 * fv[j] + (1.f - beta2) * fg[j] * fg[j];
-            const float denom = sqrtf(fv[j]) / bc2_sqrt + eps;
-            fp[j] -= (lr / bc1) * (fm[j] / denom);
+            const float denom = sqrt_approx(fv[j]) * inv_bc2_sqrt + eps;
+            fp[j] -= step_size * __fdividef(fm[j], denom);
         }
         reinterpret_cast<uint4*>(p)[i] = pack8(fp);
         reinterpret_cast<uint4*>(m)[i] = pack8(fm);
@@ -531,6 +542,7 @@ __global__ void __launch_bounds__(256) adamw_bf16_scaled_kernel(__nv_bfloat16* _
                                                                 const float* __restrict__ grad_scale,
                                                                 const int64_t* __restrict__ nodecay, int n_nodecay) {
     const float gs = grad_scale ? __ldg(grad_scale) : 1.f;
+    const float inv_bc2_sqrt = 1.f / bc2_sqrt, step_size = lr / bc1;
     // weight decay applies outside the sorted [lo, hi) vector ranges of `nodecay` (norm weights, biases).  A thread's index only
     // grows, so it keeps the end of the constant-decay interval it is in and searches the table again only after leaving it
     // (intervals are millions of vectors long; the grid stride is ~600 k vectors)
@@ -563,8 +575,8 @@ __global__ void __launch_bounds__(256) adamw_bf16_scaled_kernel(__nv_bfloat16* _
             fp[j] *= (1.f - lr * wd);
             fm[j] = beta1 * fm[j] + (1.f - beta1) * gj;
             fv[j] = beta2 * fv[j] + (1.f - beta2) * gj * gj;
-            const float denom = sqrtf(fv[j]) / bc2_sqrt + eps;
-            fp[j] -= (lr / bc1) * (fm[j] / denom);
+            const float denom = sqrt_approx(fv[j]) * inv_bc2_sqrt + eps;
+            fp[j] -= step_size * __fdividef(fm[j], denom);
         }
         reinterpret_cast<uint4*>(p)[i] = pack8(fp);
         reinterpret_cast<uint4*>(m)[i] = pack8(fm);
