@@ -44,7 +44,7 @@ __global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ gate, const 
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             // reference rounds silu(g) to bf16 before the product (act_fn output dtype); keep one rounding here
-            const float s = g[j] / (1.f + __expf(-g[j]));
+            const float s = __fdividef(g[j], 1.f + __expf(-g[j]));      // MUFU.RCP: the result is rounded to bf16 right after
             g[j] = s * u[j];
         }
         reinterpret_cast<uint4*>(out + r * ldo)[v] = pack8(g);
@@ -65,7 +65,7 @@ __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const 
         unpack8(__ldg(reinterpret_cast<const uint4*>(dout + r * ldd) + v), d);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float sg = 1.f / (1.f + __expf(-g[j]));
+            const float sg = __fdividef(1.f, 1.f + __expf(-g[j]));
             const float s = g[j] * sg;
             du[j] = d[j] * s;
             dg[j] = d[j] * u[j] * (sg * (1.f + g[j] * (1.f - sg)));
