@@ -35,9 +35,15 @@ __global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ gate, const 
                                   __nv_bfloat16* __restrict__ out, int64_t rows, int nvec, int64_t ldg, int64_t ldu,
                                   int64_t ldo) {
     const int64_t total = rows * nvec;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / nvec;
-        const int v = (int)(i - r * nvec);
+    // (row, vector) of the grid-stride index without a 64-bit division per iteration: divide once, then step
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t dr = stride / nvec;
+    const int dv = (int)(stride - dr * nvec);
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t r = i / nvec;
+    int v = (int)(i - r * nvec);
+    for (; i < total; i += stride, r += dr, v += dv) {
+        if (v >= nvec) { v -= nvec; ++r; }
         float g[8], u[8];
         unpack8(__ldg(reinterpret_cast<const uint4*>(gate + r * ldg) + v), g);
         unpack8(__ldg(reinterpret_cast<const uint4*>(up + r * ldu) + v), u);
@@ -56,9 +62,15 @@ __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const 
                                   __nv_bfloat16* __restrict__ dup, int64_t rows, int nvec, int64_t ldd, int64_t ldg,
                                   int64_t ldu, int64_t ldgg, int64_t ldgu) {
     const int64_t total = rows * nvec;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / nvec;
-        const int v = (int)(i - r * nvec);
+    // (row, vector) of the grid-stride index without a 64-bit division per iteration: divide once, then step
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t dr = stride / nvec;
+    const int dv = (int)(stride - dr * nvec);
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t r = i / nvec;
+    int v = (int)(i - r * nvec);
+    for (; i < total; i += stride, r += dr, v += dv) {
+        if (v >= nvec) { v -= nvec; ++r; }
         float g[8], u[8], d[8], dg[8], du[8];
         unpack8(__ldg(reinterpret_cast<const uint4*>(gate + r * ldg) + v), g);
         unpack8(__ldg(reinterpret_cast<const uint4*>(up + r * ldu) + v), u);
@@ -122,9 +134,15 @@ __global__ void gather_rows_kernel(const __nv_bfloat16* __restrict__ src, const 
                                    __nv_bfloat16* __restrict__ dst, int64_t rows, int nvec, int64_t ld_dst,
                                    int col0_vec) {
     const int64_t total = rows * nvec;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / nvec;
-        const int v = (int)(i - r * nvec);
+    // (row, vector) of the grid-stride index without a 64-bit division per iteration: divide once, then step
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t dr = stride / nvec;
+    const int dv = (int)(stride - dr * nvec);
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t r = i / nvec;
+    int v = (int)(i - r * nvec);
+    for (; i < total; i += stride, r += dr, v += dv) {
+        if (v >= nvec) { v -= nvec; ++r; }
         const int64_t s = index ? (int64_t)index[r] : r;
         reinterpret_cast<uint4*>(dst + r * ld_dst)[col0_vec + v] =
             __ldg(reinterpret_cast<const uint4*>(src + s * (int64_t)nvec * 8) + v);
