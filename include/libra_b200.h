@@ -408,7 +408,8 @@ int lb_probe_umma(int mode, const void* A, const void* B, float* D, int K, void*
  * libra/models/clip/image_processing_clip.py:124-217, 296-337 (resize shortest edge -> `size` with Pillow's antialiased
  * BICUBIC, center crop `crop`, rescale, normalise).  Bit-exact with Pillow's 8-bit two-pass resampler (22-bit fixed point,
  * clamp after each pass) and with the reference's float32 rounding sequence.
- * images: DEVICE buffer of packed HWC uint8 RGB images, image i at byte offsets[i]; offsets / heights / widths / pad_rgb /
+ * images: DEVICE buffer of packed HWC uint8 RGB images, image i at byte offsets[i], readable 16 bytes past the end of its
+ * last image (the word-load kernels over-read the last row's tail); offsets / heights / widths / pad_rgb /
  * mean / std are HOST arrays.  pad_to_square != 0: paste on a square canvas of colour pad_rgb first.  out: DEVICE
  * [n_images, 3, crop, crop] LB_DT_F32 or LB_DT_BF16; out_u8 (optional, may be NULL): the uint8 image after resize + crop,
  * [n_images, crop, crop, 3].  workspace: lb_clip_preprocess_workspace(...) bytes of device memory. */

@@ -334,6 +334,99 @@ __global__ void __launch_bounds__(128) resize_v_kernel(const Params p) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Word-load variants (the default when crop % 4 == 0).  The byte-per-load kernels above are bound by the load/store unit (20
+// LSU instructions per output pixel at 5 taps); here a thread fetches its taps as aligned 32-bit words:
+//   pass 1: 4 taps = 12 source bytes = 4 aligned words funnel-shifted to the window's first byte (the packed buffer must
+//     be readable 16 bytes past its last image: the last chunk of the last row over-reads, multiplied by zero coefficients);
+//   pass 2: the filter is the same for every byte of a row, so a thread owns 4 consecutive BYTES of the output row
+//     (crop * 3 bytes, a multiple of 4) and reads one word per tap; byte f maps to pixel f / 3, channel f % 3 on output.
+// Same integer sums in the same 32-bit arithmetic: bit-identical results (tests/test_gpu_preprocess.py runs both).
+__global__ void __launch_bounds__(128) resize_h_words_kernel(const Params p) {
+    const ImgDesc d = p.desc[blockIdx.z];
+    const int r0 = blockIdx.y * RPB_H, xx = blockIdx.x * 128 + threadIdx.x;
+    if (r0 >= d.rows_needed || xx >= p.crop) return;
+    const int32_t* b = p.tab + d.bh_off + 2 * xx;
+    const int x0 = b[0] - d.pad_left, n = b[1];
+    const int32_t* k = p.tab + d.kh_off + xx;                     // tap t at k[t * crop]
+    const int r1 = min(r0 + RPB_H, d.rows_needed);
+    const int bg0 = p.bg[0], bg1 = p.bg[1], bg2 = p.bg[2];
+    const int t_in0 = min(n, max(0, -x0)), t_in1 = max(t_in0, min(n, d.w - x0));
+    int kb = 0;
+    for (int t = 0; t < t_in0; ++t) kb += __ldg(k + (long long)t * p.crop);
+    for (int t = t_in1; t < n; ++t) kb += __ldg(k + (long long)t * p.crop);
+    int kall = kb;
+    for (int t = t_in0; t < t_in1; ++t) kall += __ldg(k + (long long)t * p.crop);
+    const uint8_t* const base = p.images + d.src_off;
+    for (int r = r0; r < r1; ++r) {
+        const int cy = d.y_first + r - d.pad_top;
+        int s0, s1, s2;
+        s0 = s1 = s2 = 1 << (PRECISION_BITS - 1);
+        if (cy >= 0 && cy < d.h) {
+            for (int t = t_in0; t < t_in1; t += 4) {
+                const uintptr_t A = (uintptr_t)(base + ((long long)cy * d.w + (x0 + t)) * 3);
+                const uint32_t* wp = reinterpret_cast<const uint32_t*>(A & ~(uintptr_t)3);
+                const uint32_t sh = (uint32_t)(A & 3) * 8;
+                const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3);
+                const uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh), a2 = __funnelshift_r(w2, w3, sh);
+                const int k0 = __ldg(k + (long long)t * p.crop);
+                const int k1 = t + 1 < t_in1 ? __ldg(k + (long long)(t + 1) * p.crop) : 0;
+                const int k2 = t + 2 < t_in1 ? __ldg(k + (long long)(t + 2) * p.crop) : 0;
+                const int k3 = t + 3 < t_in1 ? __ldg(k + (long long)(t + 3) * p.crop) : 0;
+                // bytes 0..11 of the window: tap q, channel c = byte 3 q + c
+                s0 += (int)(a0 & 0xff) * k0;         s1 += (int)((a0 >> 8) & 0xff) * k0;  s2 += (int)((a0 >> 16) & 0xff) * k0;
+                s0 += (int)(a0 >> 24) * k1;          s1 += (int)(a1 & 0xff) * k1;         s2 += (int)((a1 >> 8) & 0xff) * k1;
+                s0 += (int)((a1 >> 16) & 0xff) * k2; s1 += (int)(a1 >> 24) * k2;          s2 += (int)(a2 & 0xff) * k2;
+                s0 += (int)((a2 >> 8) & 0xff) * k3;  s1 += (int)((a2 >> 16) & 0xff) * k3; s2 += (int)(a2 >> 24) * k3;
+            }
+            s0 += bg0 * kb; s1 += bg1 * kb; s2 += bg2 * kb;
+        } else {
+            s0 += bg0 * kall; s1 += bg1 * kall; s2 += bg2 * kall;
+        }
+        uint8_t* o = p.tmp + d.tmp_off + ((long long)r * p.crop + xx) * 3;
+        o[0] = clip8(s0); o[1] = clip8(s1); o[2] = clip8(s2);
+    }
+}
+
+// grid (ceil(crop * 3 / 4 / 128), ceil(crop / RPB_V), n_images), block 128; thread = 4 consecutive bytes of the output row
+__global__ void __launch_bounds__(128) resize_v_words_kernel(const Params p) {
+    const ImgDesc d = p.desc[blockIdx.z];
+    const int P = p.crop * 3;                                      // bytes per row (multiple of 4)
+    const int j = blockIdx.x * 128 + threadIdx.x;
+    if (4 * j >= P) return;
+    const long long plane = (long long)p.crop * p.crop;
+    const int y1 = min((int)(blockIdx.y + 1) * RPB_V, p.crop);
+    // byte f = 4 j + i of the row is channel f % 3 of pixel f / 3
+    int px[4], chn[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { px[i] = (4 * j + i) / 3; chn[i] = (4 * j + i) - 3 * px[i]; }
+    for (int yy = blockIdx.y * RPB_V; yy < y1; ++yy) {
+        const int32_t* b = p.tab + d.bv_off + 2 * yy;
+        const int y0 = b[0] - d.y_first, n = b[1];
+        const int32_t* k = p.tab + d.kv_off + (long long)yy * d.ksize_v;
+        int s[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s[i] = 1 << (PRECISION_BITS - 1);
+        const uint8_t* src = p.tmp + d.tmp_off + (long long)y0 * P + 4 * j;
+#pragma unroll 4
+        for (int t = 0; t < n; ++t, src += P) {
+            const int kv = __ldg(k + t);
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(src);
+            s[0] += (int)(w & 0xff) * kv; s[1] += (int)((w >> 8) & 0xff) * kv; s[2] += (int)((w >> 16) & 0xff) * kv; s[3] += (int)(w >> 24) * kv;
+        }
+        uint32_t packed = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t u = clip8(s[i]);
+            packed |= u << (8 * i);
+            const float f = __ldg(p.lut + chn[i] * 256 + u);
+            const long long o = ((long long)blockIdx.z * 3 + chn[i]) * plane + (long long)yy * p.crop + px[i];
+            if (p.out_bf16) ((__nv_bfloat16*)p.out)[o] = __float2bfloat16_rn(f); else ((float*)p.out)[o] = f;
+        }
+        if (p.out_u8) *reinterpret_cast<uint32_t*>(p.out_u8 + ((long long)blockIdx.z * plane + (long long)yy * p.crop) * 3 + 4 * j) = packed;
+    }
+}
+
 }  // namespace pp
 }  // namespace lb
 
@@ -403,8 +496,15 @@ int lb_clip_preprocess(const uint8_t* images, const int64_t* offsets, const int3
     for (int c = 0; c < 3; ++c) p.bg[c] = pad_rgb ? pad_rgb[c] : 0;
     const unsigned gx = (unsigned)ceil_div(crop, 128);
     pp::tables_kernel<<<dim3(gx, 2, (unsigned)n_images), 128, 0, st>>>(p.desc, (int32_t*)((char*)workspace + L.tab_off), crop);
-    pp::resize_h_kernel<<<dim3(gx, (unsigned)ceil_div(pl.max_rows, pp::RPB_H), (unsigned)n_images), 128, 0, st>>>(p);
-    pp::resize_v_kernel<<<dim3(gx, (unsigned)ceil_div(crop, pp::RPB_V), (unsigned)n_images), 128, 0, st>>>(p);
+    static int force_bytes = -1;                                  // LB_PREPROC_BYTES=1: the byte-per-load kernels (A/B, cross-check)
+    if (force_bytes < 0) { const char* e = getenv("LB_PREPROC_BYTES"); force_bytes = (e && atoi(e) == 1) ? 1 : 0; }
+    if (crop % 4 == 0 && !force_bytes) {
+        pp::resize_h_words_kernel<<<dim3(gx, (unsigned)ceil_div(pl.max_rows, pp::RPB_H), (unsigned)n_images), 128, 0, st>>>(p);
+        pp::resize_v_words_kernel<<<dim3((unsigned)ceil_div(crop * 3 / 4, 128), (unsigned)ceil_div(crop, pp::RPB_V), (unsigned)n_images), 128, 0, st>>>(p);
+    } else {
+        pp::resize_h_kernel<<<dim3(gx, (unsigned)ceil_div(pl.max_rows, pp::RPB_H), (unsigned)n_images), 128, 0, st>>>(p);
+        pp::resize_v_kernel<<<dim3(gx, (unsigned)ceil_div(crop, pp::RPB_V), (unsigned)n_images), 128, 0, st>>>(p);
+    }
     return check_launch("clip_preprocess");
 }
 

@@ -140,6 +140,7 @@ class CLIPImageProcessor:
             offs.append(tot)
             tot += (s + 15) // 16 * 16
         offsets = (ctypes.c_int64 * n)(*offs)
+        tot += 16                                           # lb_clip_preprocess may read 16 bytes past the last image
         with torch.cuda.device(dev):
             if all(isinstance(a, torch.Tensor) for a in arrs):
                 packed = torch.empty(tot, dtype=torch.uint8, device=dev)

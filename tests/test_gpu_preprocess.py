@@ -30,6 +30,21 @@ def test_batch_of_mixed_sizes_equals_oracle(pad):
         assert np.array_equal(pv[i], O.clip_preprocess(im, pad_square=bg)), (i, shapes[i])
 
 
+@pytest.mark.parametrize("size", [57, 224])
+def test_other_target_sizes_and_the_byte_kernels(size):
+    """crop % 4 != 0 takes the byte-per-load kernels, crop % 4 == 0 the word-load ones (csrc/preprocess.cu): both against the oracle."""
+    need_gpu()
+    from libra_b200.processors import CLIPImageProcessor
+    imgs = [_img(h, w, h + 7 * w) for h, w in [(300, 200), (64, 64), (90, 333), (5, 9)]]
+    for pad in (False, True):
+        P = CLIPImageProcessor(size={"shortest_edge": size}, crop_size={"height": size, "width": size}, pad_to_square=pad)
+        out = P(imgs, return_uint8=True)
+        bg = P.background_color if pad else None
+        for i, im in enumerate(imgs):
+            assert np.array_equal(out["uint8"][i].cpu().numpy(), O.clip_preprocess_u8(im, size=size, crop=size, pad_square=bg)), (i, pad)
+            assert np.array_equal(out["pixel_values"][i].cpu().numpy(), O.clip_preprocess(im, size=size, crop=size, pad_square=bg)), (i, pad)
+
+
 def test_equals_pillow_and_transformers_pil_processor():
     need_gpu()
     tfm = pytest.importorskip("transformers")
