@@ -3,8 +3,9 @@
 
 Tolerances: the model runs in bf16 like the reference's training dtype; BASELINE.md asks logits within 1e-3 rel of the
 reference *measured against fp32 with the bf16 reference's own distance as the noise floor*.  We therefore assert
-  err(ours_bf16, ref_fp32) <= 1.5 * err(oracle_bf16, ref_fp32) + small
-on relative Frobenius errors, plus absolute caps."""
+  err(ours_bf16, ref_fp32) <= 1.1 * err(oracle_bf16, ref_fp32) + 3e-4
+on relative Frobenius errors (FACTOR / SLACK below, set from the measured values in profiles/r02_parity_tiny.jsonl), plus
+absolute caps on the loss."""
 import pytest
 import torch
 
@@ -14,6 +15,21 @@ from oracle import libra_oracle as O
 pytestmark = pytest.mark.gpu
 dev = "cuda"
 
+
+
+def _record(name, **vals):
+    """LB_PARITY_LOG=<file>: append the measured errors of a parity assertion (profiles/r02_parity_tiny.jsonl was made this way)."""
+    import json, os
+    path = os.environ.get("LB_PARITY_LOG")
+    if path:
+        with open(path, "a") as fh:
+            fh.write(json.dumps({"test": name, **{k: float(v) for k, v in vals.items()}}) + "\n")
+
+
+# "No worse than the reference's own bf16 path": relative Frobenius error against fp32 within FACTOR x the bf16 oracle's +
+# SLACK.  Measured on B200 (profiles/r02_parity_tiny.jsonl): ours 5.721e-3 / 5.401e-3 / 5.475e-3 against 5.738e-3 / 5.401e-3 /
+# 5.476e-3 for the bf16 oracle (the two round at the same points), so the round-1 bound of 1.5x + 5e-3 is tightened to:
+FACTOR, SLACK = 1.1, 3e-4
 
 def build(g):
     from libra_b200.models import LibraConfig, LibraForCausalLM
@@ -50,12 +66,16 @@ def test_forward_logits_and_loss_vs_reference_golden(golden):
     valid = inp["attention_mask"].to(dev)[:, sel].bool()[None, :, :, None].expand_as(fin) & fin
     e_ours = rel_err(got[valid], want[valid])
     e_orc = rel_err(orc["logits"][:, :, sel].float()[valid], want[valid])
-    assert e_ours <= 1.5 * e_orc + 5e-3, (e_ours, e_orc)
-    assert abs(float(out.loss) - float(g["loss"])) <= 1.5 * abs(float(orc["loss"]) - float(g["loss"])) + 2e-2
     # hidden states: [B,T,C] in original order
     h1 = out.hidden_states[1].float()
     m = inp["attention_mask"].to(dev).bool()
-    assert rel_err(h1[m], g["hidden_after_layer0"].to(dev)[m]) <= 1.5 * rel_err(orc["hidden_states"][1].float()[m], g["hidden_after_layer0"].to(dev)[m]) + 5e-3
+    eh_ours = rel_err(h1[m], g["hidden_after_layer0"].to(dev)[m])
+    eh_orc = rel_err(orc["hidden_states"][1].float()[m], g["hidden_after_layer0"].to(dev)[m])
+    _record("golden_forward", logits_ours=e_ours, logits_oracle_bf16=e_orc, hidden_ours=eh_ours, hidden_oracle_bf16=eh_orc,
+            loss_ours=abs(float(out.loss) - float(g["loss"])), loss_oracle_bf16=abs(float(orc["loss"]) - float(g["loss"])))
+    assert e_ours <= FACTOR * e_orc + SLACK, (e_ours, e_orc)
+    assert abs(float(out.loss) - float(g["loss"])) <= abs(float(orc["loss"]) - float(g["loss"])) + 2e-3      # measured 4.8e-6 vs 7.7e-3
+    assert eh_ours <= FACTOR * eh_orc + SLACK, (eh_ours, eh_orc)
     lse = torch.logsumexp(out.logits.float(), -1)
     mm = m[None].expand_as(lse)
     assert rel_err(lse[mm], g["logits_lse"].to(dev)[mm]) < 2e-2
@@ -132,8 +152,9 @@ def test_other_layouts_vs_oracle(golden):
     fin = torch.isfinite(o32["logits"]) & m
     e_ours = rel_err(out.logits.float()[fin], o32["logits"][fin])
     e_orc = rel_err(orc["logits"].float()[fin], o32["logits"][fin])
-    assert e_ours <= 1.5 * e_orc + 5e-3, (e_ours, e_orc)
-    assert abs(float(out.loss) - float(o32["loss"])) < 5e-2
+    _record("vs_fp32_oracle", logits_ours=e_ours, logits_oracle_bf16=e_orc, loss_ours=abs(float(out.loss) - float(o32["loss"])))
+    assert e_ours <= FACTOR * e_orc + SLACK, (e_ours, e_orc)
+    assert abs(float(out.loss) - float(o32["loss"])) < 2e-3                                                  # measured 1.7e-5
 
 
 def test_text_only_batch_forward_backward(golden):
@@ -218,7 +239,8 @@ def test_left_padding_with_position_ids_vs_oracle(golden):
     fin = torch.isfinite(o32["logits"]) & m
     e_ours = rel_err(out.logits.float()[fin], o32["logits"][fin])
     e_orc = rel_err(o16["logits"].float()[fin], o32["logits"][fin])
-    assert e_ours <= 1.5 * e_orc + 5e-3, (e_ours, e_orc)
+    _record("left_padding", logits_ours=e_ours, logits_oracle_bf16=e_orc)
+    assert e_ours <= FACTOR * e_orc + SLACK, (e_ours, e_orc)
 
 
 def test_full_width_layer_vs_oracle_fp32_and_bf16():
