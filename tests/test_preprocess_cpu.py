@@ -111,62 +111,79 @@ def test_normalize_lut_rounding_sequence():
 # (16 bytes of slack behind the packed buffer), canvas colour x sum of the outside taps, and in the vertical pass one thread
 # per 4 consecutive bytes of the output row.  Same integer sums as the oracle => the kernels' arithmetic is pinned on the CPU
 # (the GPU tests then only have to show that the CUDA code is this algorithm).
-PB = 22
-def clip8(v): 
+PB = O.PRECISION_BITS
+
+
+def _clip8(v):
     v >>= PB
-    return 0 if v<0 else (255 if v>255 else v)
-def fs(lo,hi,sh):  # funnelshift_r
-    return ((((hi<<32)|lo) >> sh) & 0xffffffff)
+    return 0 if v < 0 else (255 if v > 255 else v)
+
+
+def _funnelshift_r(lo, hi, sh):
+    return (((hi << 32) | lo) >> sh) & 0xFFFFFFFF
+
+
+def _word(buf, byte_off):
+    return int(buf[byte_off]) | int(buf[byte_off + 1]) << 8 | int(buf[byte_off + 2]) << 16 | int(buf[byte_off + 3]) << 24
+
+
 def emulate(img, size=336, crop=336, pad=None):
-    h,w,_=img.shape
-    ch,cw,pt,pl=h,w,0,0
-    if pad is not None and h!=w:
-        s=max(h,w)
-        if w>h: pt=(w-h)//2
-        else: pl=(h-w)//2
-        ch=cw=s
-    oh,ow=O.resize_output_size(ch,cw,size)
-    top,left=(oh-crop)//2,(ow-crop)//2
-    bh,kh,_=O.precompute_coeffs(cw,ow); bv,kv,_=O.precompute_coeffs(ch,oh)
-    bh,kh=bh[left:left+crop],kh[left:left+crop]; bv,kv=bv[top:top+crop],kv[top:top+crop]
-    y_first=int(bv[0,0]); rows=int(bv[-1,0]+bv[-1,1])-y_first
-    flat=np.concatenate([img.reshape(-1), np.zeros(16,np.uint8)])   # 16 bytes of slack
-    bg=pad if pad is not None else (0,0,0)
-    P=crop*3
-    tmp=np.zeros((rows,P),np.uint8)
-    for xx in range(crop):
-        x0=int(bh[xx,0])-pl; n=int(bh[xx,1]); k=kh[xx]
-        t0=min(n,max(0,-x0)); t1=max(t0,min(n,w-x0))
-        kb=int(k[:t0].sum()+k[t1:n].sum()); kall=kb+int(k[t0:t1].sum())
+    h, w, _ = img.shape
+    ch, cw, pad_top, pad_left = h, w, 0, 0
+    if pad is not None and h != w:                       # Expand2Square: a virtual canvas, never materialised
+        if w > h:
+            pad_top = (w - h) // 2
+        else:
+            pad_left = (h - w) // 2
+        ch = cw = max(h, w)
+    oh, ow = O.resize_output_size(ch, cw, size)
+    top, left = (oh - crop) // 2, (ow - crop) // 2
+    bh, kh, _ = O.precompute_coeffs(cw, ow)
+    bv, kv, _ = O.precompute_coeffs(ch, oh)
+    bh, kh = bh[left:left + crop], kh[left:left + crop]  # tables for the crop window only
+    bv, kv = bv[top:top + crop], kv[top:top + crop]
+    y_first = int(bv[0, 0])
+    rows = int(bv[-1, 0] + bv[-1, 1]) - y_first
+    flat = np.concatenate([img.reshape(-1), np.zeros(16, np.uint8)])       # the 16 bytes of slack the C ABI asks for
+    bg = pad if pad is not None else (0, 0, 0)
+    pitch = crop * 3
+    tmp = np.zeros((rows, pitch), np.uint8)
+    for xx in range(crop):                               # pass 1: thread = crop column
+        x0, n, k = int(bh[xx, 0]) - pad_left, int(bh[xx, 1]), kh[xx]
+        t0 = min(n, max(0, -x0))
+        t1 = max(t0, min(n, w - x0))
+        kb = int(k[:t0].sum() + k[t1:n].sum())           # taps on the canvas colour
+        kall = kb + int(k[t0:t1].sum())
         for r in range(rows):
-            cy=y_first+r-pt
-            s=[1<<(PB-1)]*3
-            if 0<=cy<h:
-                for c0 in range(0,t1-t0,4):
-                    A=(cy*w+(x0+t0+c0))*3; Aw=A&~3; sh=(A&3)*8
-                    wd=[int(flat[Aw+4*i])|int(flat[Aw+4*i+1])<<8|int(flat[Aw+4*i+2])<<16|int(flat[Aw+4*i+3])<<24 for i in range(4)]
-                    a=[fs(wd[0],wd[1],sh),fs(wd[1],wd[2],sh),fs(wd[2],wd[3],sh)]
+            cy = y_first + r - pad_top
+            s = [1 << (PB - 1)] * 3
+            if 0 <= cy < h:
+                for c0 in range(0, t1 - t0, 4):          # 4 taps = 12 bytes = 4 aligned words
+                    addr = (cy * w + (x0 + t0 + c0)) * 3
+                    aligned, sh = addr & ~3, (addr & 3) * 8
+                    wd = [_word(flat, aligned + 4 * i) for i in range(4)]
+                    a = [_funnelshift_r(wd[i], wd[i + 1], sh) for i in range(3)]
                     for q in range(4):
-                        t=t0+c0+q
-                        kq=int(k[t]) if t<t1 else 0
+                        t = t0 + c0 + q
+                        kq = int(k[t]) if t < t1 else 0
                         for c in range(3):
-                            bi=3*q+c
-                            s[c]+=((a[bi>>2]>>(8*(bi&3)))&0xff)*kq
-                for c in range(3): s[c]+=bg[c]*kb
+                            bi = 3 * q + c
+                            s[c] += ((a[bi >> 2] >> (8 * (bi & 3))) & 0xFF) * kq
+                s = [s[c] + bg[c] * kb for c in range(3)]
             else:
-                for c in range(3): s[c]+=bg[c]*kall
-            for c in range(3): tmp[r,xx*3+c]=clip8(s[c])
-    out=np.zeros((crop,P),np.uint8)
-    tw=tmp.view(np.uint32) if False else None
-    for yy in range(crop):
-        y0=int(bv[yy,0])-y_first; n=int(bv[yy,1])
-        for j in range(P//4):
-            s=[1<<(PB-1)]*4
+                s = [s[c] + bg[c] * kall for c in range(3)]
+            tmp[r, xx * 3:xx * 3 + 3] = [_clip8(v) for v in s]
+    out = np.zeros((crop, pitch), np.uint8)
+    for yy in range(crop):                               # pass 2: thread = 4 consecutive bytes of the output row
+        y0, n = int(bv[yy, 0]) - y_first, int(bv[yy, 1])
+        for j in range(pitch // 4):
+            s = [1 << (PB - 1)] * 4
             for t in range(n):
-                row=tmp[y0+t]; wv=int(row[4*j])|int(row[4*j+1])<<8|int(row[4*j+2])<<16|int(row[4*j+3])<<24
-                for b in range(4): s[b]+=((wv>>(8*b))&0xff)*int(kv[yy,t])
-            for b in range(4): out[yy,4*j+b]=clip8(s[b])
-    return out.reshape(crop,crop,3)
+                wv = _word(tmp[y0 + t], 4 * j)
+                for b in range(4):
+                    s[b] += ((wv >> (8 * b)) & 0xFF) * int(kv[yy, t])
+            out[yy, 4 * j:4 * j + 4] = [_clip8(v) for v in s]
+    return out.reshape(crop, crop, 3)
 
 
 @pytest.mark.parametrize("case", [(40, 61, 24, None), (61, 40, 24, (122, 116, 104)), (24, 24, 24, None), (7, 5, 24, (1, 2, 3)),
