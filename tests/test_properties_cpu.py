@@ -1,0 +1,112 @@
+"""Property tests (hypothesis) of the host logic the kernels rely on, and of the preprocessing oracle against Pillow on random
+sizes.  CPU only; small example counts keep the file under ~20 s."""
+import numpy as np
+import pytest
+import torch
+
+hyp = pytest.importorskip("hypothesis")
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+from libra_b200 import schedule  # noqa: E402
+from oracle import clip_preprocess_oracle as O  # noqa: E402
+
+TILE = 128
+
+
+@st.composite
+def layouts(draw):
+    """A batch layout like the reference's tokenizer produces: per sample some image spans (vision rows) inside text."""
+    B = draw(st.integers(1, 3))
+    T = draw(st.integers(1, 700))
+    flag = torch.zeros(B, T, dtype=torch.bool)
+    for b in range(B):
+        for _ in range(draw(st.integers(0, 3))):
+            s = draw(st.integers(0, T - 1))
+            e = draw(st.integers(s, min(T, s + 300)))
+            flag[b, s:e] = True
+    return flag
+
+
+@settings(max_examples=40, deadline=None)
+@given(layouts())
+def test_routing_is_a_stable_partition(flag):
+    """build_routing (the sorted-row layout that replaces cal_language_vision's boolean masks, modeling_libra.py:111-147):
+    language rows first, vision rows second, original order kept inside each segment, inv o perm = identity."""
+    rt = schedule.build_routing(flag)
+    f = flag.reshape(-1)
+    n = f.numel()
+    perm, inv = rt.perm.long(), rt.inv.long()
+    assert rt.n_tokens == n and rt.n_vis == int(f.sum()) and rt.n_lang == n - rt.n_vis
+    assert sorted(perm.tolist()) == list(range(n))
+    assert torch.equal(inv[perm], torch.arange(n)) and torch.equal(perm[inv], torch.arange(n))
+    assert not f[perm[:rt.n_lang]].any() and f[perm[rt.n_lang:]].all()
+    assert torch.equal(perm[:rt.n_lang], torch.sort(perm[:rt.n_lang]).values)          # stable
+    assert torch.equal(perm[rt.n_lang:], torch.sort(perm[rt.n_lang:]).values)
+    assert torch.equal(rt.flag_sorted.bool(), f[perm]) and torch.equal(rt.flag_orig.bool(), f)
+
+
+@settings(max_examples=40, deadline=None)
+@given(layouts(), st.booleans())
+def test_attention_work_lists_cover_exactly_what_the_mask_allows(flag, causal):
+    """build_attn_work: a forward / dQ item exists for (sample, q tile, variant) iff the tile holds a row of that modality; a
+    dK/dV item for (sample, kv tile, variant) iff some q tile at or after it (causal) holds such a row; the kv tile count of a
+    forward item is the causal triangle's; kv_cover tells where dK/dV needs no zero fill."""
+    B, T = flag.shape
+    nt = (T + TILE - 1) // TILE
+    w = schedule.build_attn_work(flag, B, T, causal, "cpu")
+    has = torch.zeros(B, 2, nt, dtype=torch.bool)
+    for b in range(B):
+        for qt in range(nt):
+            seg = flag[b, qt * TILE:(qt + 1) * TILE]
+            has[b, 0, qt] = bool((~seg).any())
+            has[b, 1, qt] = bool(seg.any())
+    assert torch.equal(w.qtile_has.bool(), has)
+    want_q = {(b, qt, v) for b in range(B) for v in range(2) for qt in range(nt) if has[b, v, qt]}
+    got_q = [(b, qt, v) for b, qt, v, _ in w.work_q.tolist()]
+    assert len(got_q) == len(set(got_q)) and set(got_q) == want_q
+    for (b, qt, v, _), n_kv in zip(w.work_q.tolist(), w.q_tiles):
+        assert n_kv == (qt + 1 if causal else nt)
+    assert w.q_tiles == sorted(w.q_tiles, reverse=True)                                 # longest items first
+    want_kv = {(b, kt, v) for b in range(B) for v in range(2) for kt in range(nt) if has[b, v, (kt if causal else 0):].any()}
+    got_kv = [(b, kt, v) for b, kt, v, _ in w.work_kv.tolist()]
+    assert len(got_kv) == len(set(got_kv)) and set(got_kv) == want_kv
+    for v in range(2):
+        full = all((b, kt, v) in want_kv for b in range(B) for kt in range(nt))
+        assert w.kv_cover[v] == full
+
+
+@settings(max_examples=25, deadline=None)
+@given(layouts(), st.integers(1, 8), st.integers(1, 200))
+def test_stream_plan_partitions_every_item_once(flag, heads, n_cta):
+    B, T = flag.shape
+    w = schedule.build_attn_work(flag, B, T, True, "cpu")
+    for which, n_work in (("q", len(w.q_tiles)), ("kv", len(w.kv_tiles))):
+        items, off, n, longest = w.stream_plan(heads, n_cta, 8, which=which)
+        total = n_work * heads
+        assert 1 <= n <= n_cta and off.shape[0] == n + 1 and int(off[0]) == 0 and int(off[-1]) == total
+        assert sorted(items.tolist()) == list(range(total))
+        sizes = (off[1:] - off[:-1]).tolist()
+        assert min(sizes) >= 0 and max(sizes) == longest
+
+
+@settings(max_examples=25, deadline=None)
+@given(st.integers(1, 260), st.integers(1, 260), st.sampled_from([24, 56, 57]), st.integers(0, 2 ** 31 - 1))
+def test_preprocessing_oracle_equals_pillow_on_random_sizes(h, w, size, seed):
+    """Pillow's BICUBIC through oracle/clip_preprocess_oracle.py at arbitrary (also degenerate) sizes: bit exact."""
+    from PIL import Image
+    oh, ow = O.resize_output_size(h, w, size)
+    if oh * ow > 300_000:                      # extreme aspect ratios explode the long edge: keep the example cheap
+        return
+    img = np.random.default_rng(seed).integers(0, 256, (h, w, 3), dtype=np.uint8)
+    ref = np.asarray(Image.fromarray(img).resize((ow, oh), resample=Image.BICUBIC))
+    assert np.array_equal(O.pil_resize_bicubic(img, ow, oh), ref)
+    # the library's host tables for this axis pair are the oracle's
+    import ctypes
+    from libra_b200 import _lib
+    for in_size, out_size in ((w, ow), (h, oh)):
+        bounds, kk, ksize = O.precompute_coeffs(in_size, out_size)
+        n = min(out_size, 64)
+        cb, bb = (ctypes.c_int32 * (n * ksize))(), (ctypes.c_int32 * (2 * n))()
+        assert _lib.load().lb_clip_resample_coeffs(in_size, out_size, 0, n, cb, n * ksize, bb) == ksize
+        assert np.array_equal(np.frombuffer(cb, dtype=np.int32).reshape(n, ksize), kk[:n])
+        assert np.array_equal(np.frombuffer(bb, dtype=np.int32).reshape(n, 2), bounds[:n])
