@@ -110,3 +110,73 @@ def test_preprocessing_oracle_equals_pillow_on_random_sizes(h, w, size, seed):
         assert _lib.load().lb_clip_resample_coeffs(in_size, out_size, 0, n, cb, n * ksize, bb) == ksize
         assert np.array_equal(np.frombuffer(cb, dtype=np.int32).reshape(n, ksize), kk[:n])
         assert np.array_equal(np.frombuffer(bb, dtype=np.int32).reshape(n, 2), bounds[:n])
+
+
+@st.composite
+def text_batches(draw):
+    """Text ids with placeholder runs of length L per image (what the reference's text tokenizer hands to LibraTokenizer.forward,
+    tokenization_libra.py:250-316), right padding on some samples."""
+    B = draw(st.integers(1, 4))
+    L = draw(st.integers(3, 12))
+    n_img = [draw(st.integers(0, 3)) for _ in range(B)]
+    gaps = [[draw(st.integers(0, 5)) for _ in range(k + 1)] for k in n_img]
+    T = max(1 + sum(g) + k * L for g, k in zip(gaps, n_img)) + draw(st.integers(0, 6))
+    seed = draw(st.integers(0, 2 ** 31 - 1))
+    g = torch.Generator().manual_seed(seed)
+    text = torch.randint(3, 300, (B, T), generator=g)
+    am = torch.ones(B, T, dtype=torch.long)
+    for b in range(B):
+        pos = 1
+        for i in range(n_img[b]):
+            pos += gaps[b][i]
+            text[b, pos:pos + L] = 999
+            pos += L
+        used = pos + gaps[b][-1]
+        if used < T and draw(st.booleans()):
+            am[b, used:] = 0
+    n = sum(n_img)
+    image_ids = torch.randint(320, 832, (2, n, L), generator=g)
+    feat = torch.randn(n, L - 2, 5, generator=g)
+    return text, am, image_ids, feat, L, n
+
+
+@settings(max_examples=40, deadline=None)
+@given(text_batches())
+def test_assemble_inputs_equals_oracle_on_random_layouts(case):
+    """The sync-free assembly (rank-of-placeholder gathers, no nonzero) against the oracle's restatement of the reference's
+    boolean-mask scatters: ids, mask, vision indices bit exact, signal rows exact."""
+    from libra_b200.models.tokenization_libra import assemble_inputs
+    from oracle import libra_oracle as LO
+    text, am, image_ids, feat, L, n = case
+    if n == 0:
+        got = assemble_inputs(text, am, 999, None, None, max_vision_token_length=L)
+        assert got["coninous_signal"] is None and (got["vision_indices"] == L).all() and torch.equal(got["input_ids"][0], text)
+        return
+    got = assemble_inputs(text, am, 999, image_ids, feat, max_vision_token_length=L, check=True)
+    want = LO.assemble_inputs(text, am, 999, image_ids, feat, max_vision_token_length=L)
+    for k in ("input_ids", "attention_mask", "vision_indices", "coninous_signal"):
+        assert torch.equal(got[k], want[k]), k
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.integers(1, 4), st.integers(2, 40), st.integers(0, 2 ** 31 - 1))
+def test_get_labels_equals_oracle_on_random_spans(B, T, seed):
+    from libra_b200.models.tokenization_libra import get_labels
+    from oracle import libra_oracle as LO
+    g = torch.Generator().manual_seed(seed)
+    ids = torch.randint(3, 300, (2, B, T), generator=g)
+    ids[:, :, 0] = 1
+    boi = 832
+    ids[:, :, 1:][torch.rand(2, B, T - 1, generator=g) < 0.1] = boi
+    am = torch.ones(B, T, dtype=torch.long)
+    rnd = np.random.default_rng(seed)
+    spans = []
+    for b in range(B):
+        if rnd.random() < 0.5:
+            am[b, int(rnd.integers(1, T)):] = 0
+        sp = []
+        for _ in range(int(rnd.integers(0, 3))):
+            s = int(rnd.integers(0, T))
+            sp.append([s, int(rnd.integers(s, T + 1))])
+        spans.append(sp)
+    assert torch.equal(get_labels(ids, am, boi, 1, spans), LO.get_labels(ids, am, boi, 1, spans))
