@@ -180,3 +180,33 @@ def test_get_labels_equals_oracle_on_random_spans(B, T, seed):
             sp.append([s, int(rnd.integers(s, T + 1))])
         spans.append(sp)
     assert torch.equal(get_labels(ids, am, boi, 1, spans), LO.get_labels(ids, am, boi, 1, spans))
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.lists(st.tuples(st.integers(1, 40), st.booleans()), min_size=1, max_size=12), st.booleans())
+def test_adamw_launch_plan_gives_every_element_its_own_decay(params, aligned):
+    """FlatAdamW._plan (N3: the reference's decay exclusions, trainer.py:27-37, as ONE launch + a device range table): for every
+    element, 'weight decay of the main launch unless inside a no-decay vector range, or redone element-wise as a tail' equals
+    the decay of the parameter the element belongs to -- also when run edges are not multiples of the 8-element vector."""
+    from libra_b200.optim import FlatAdamW
+    runs, lo = [], 0
+    for size, decays in params:
+        n = size * 8 if aligned else size
+        runs.append((lo, lo + n, 0.01 if decays else 0.0))
+        lo += n
+    p = torch.zeros(lo, dtype=torch.bfloat16)
+    opt = FlatAdamW(p, torch.zeros_like(p), weight_decay=0.01, runs=runs)
+    wd_main, tbl, tails, n8 = opt._plan()
+    eff = torch.full((lo,), float(wd_main))
+    if tbl is not None:
+        for a, b in tbl.tolist():
+            eff[a * 8:b * 8] = 0.0
+    redo = torch.zeros(lo, dtype=torch.bool)
+    for (sl,) in tails:
+        redo[sl] = True
+    want = torch.tensor([opt._wd_of(i) for i in range(lo)])
+    ok = redo | (eff == want)
+    assert ok.all(), (runs, tbl, tails)
+    assert (~redo[n8:]).sum() == 0                      # everything behind the last full vector is a tail
+    if aligned:
+        assert not tails                                 # the model's case: every parameter is a multiple of 8 elements
