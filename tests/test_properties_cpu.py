@@ -210,3 +210,63 @@ def test_adamw_launch_plan_gives_every_element_its_own_decay(params, aligned):
     assert (~redo[n8:]).sum() == 0                      # everything behind the last full vector is a tail
     if aligned:
         assert not tails                                 # the model's case: every parameter is a multiple of 8 elements
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.integers(1, 6), st.lists(st.integers(1, 64), min_size=2, max_size=4), st.integers(1, 4096))
+def test_flat_gradient_buffer_and_overlapped_pieces_tile_the_buffer(n_layers, widths, min_bytes):
+    """FlatGradBuffer lays parameters out in the order their gradients become final (heads, layer L-1 .. 0, embedding side)
+    and GradSync's pieces -- issued from the layer hooks, never smaller than min_bytes except at the layer-0 boundary and the
+    tail -- tile the buffer in ascending order, each ending on a readiness-group boundary (ONE logical all-reduce)."""
+    import torch.distributed as tdist
+    from libra_b200 import dist as D
+
+    class Layer(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.ws = torch.nn.ParameterList([torch.nn.Parameter(torch.zeros(w, 3)) for w in widths])
+
+    class Toy(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.embed_tokens = torch.nn.Embedding(7, 5)
+            self.layers = torch.nn.ModuleList([Layer() for _ in range(n_layers)])
+            self.norm = torch.nn.Parameter(torch.zeros(5))
+            self.lm_head = torch.nn.Linear(5, 11, bias=False)
+
+    m = Toy()
+    buf = D.FlatGradBuffer(m.named_parameters(), fused=False)
+    spans = sorted(buf.offsets.values())
+    assert spans[0][0] == 0 and spans[-1][1] == buf.numel and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    assert buf.groups == sorted(buf.groups)
+    for n, p in m.named_parameters():
+        lo, hi = buf.offsets[n]
+        assert p.grad.data_ptr() == buf.flat[lo:hi].data_ptr() and p.grad.shape == p.shape
+    # head side first, embedding side last
+    assert buf.offsets["lm_head.weight"][1] <= buf.offsets[f"layers.{n_layers - 1}.ws.0"][0]
+    assert buf.offsets["embed_tokens.weight"][1] == buf.numel
+
+    class _Done:
+        def wait(self):
+            return None
+
+    calls = []
+    real = tdist.all_reduce
+    tdist.all_reduce = lambda t, **kw: (calls.append(t.numel()), _Done())[1]
+    try:
+        sync = D.GradSync(buf, None, min_bytes=min_bytes, n_layers=n_layers)
+        sync.world = 2                                   # pretend: the collective itself is stubbed out
+        sync.arm(last=True)
+        for li in reversed(range(n_layers)):
+            sync.on_layer_grad_ready(li)
+        sync.finish()
+    finally:
+        tdist.all_reduce = real
+    pieces = sync.pieces
+    assert pieces[0][0] == 0 and pieces[-1][1] == buf.numel and all(a[1] == b[0] for a, b in zip(pieces, pieces[1:]))
+    assert [hi - lo for lo, hi in pieces] == calls
+    ends = set(buf.group_end.values())
+    layer0_end = buf.group_end[n_layers]
+    for lo, hi in pieces[:-1]:
+        assert hi in ends
+        assert (hi - lo) * buf.flat.element_size() >= min_bytes or hi == layer0_end
